@@ -1,0 +1,220 @@
+/*
+ * yolonano_b200.h — C ABI of the B200-native YOLO-Nano-1.0x detection forward path.
+ *
+ * The reference (yjh0410/YOLO-Nano) is pure Python and has no FFI of its own; the
+ * boundary this library sits behind is the Python class `models.yolo_nano.YOLONano`
+ * (models/yolo_nano.py:12) — see INTEGRATION.md for the ctypes stub a maintainer adds.
+ * Every entry point below names the reference code it replaces (file:line under the
+ * reference tree).
+ *
+ * Conventions
+ *   - plain C symbols, opaque handle, `int` status (0 = YNB_OK), message via
+ *     ynb_last_error(); no torch / C++ types cross the boundary.
+ *   - all `*_dev` pointers are device pointers on the engine's GPU, owned by the caller
+ *     (PyTorch allocations passed as raw addresses); `stream` is a cudaStream_t passed
+ *     as void* (NULL = legacy default stream).  Calls are asynchronous on that stream
+ *     unless stated otherwise.
+ *   - one handle per (GPU, stream); a handle is not thread-safe; there is no global state.
+ *   - tensors are float32.  Public image input is NCHW [B,3,S,S] exactly as the
+ *     reference takes it; internal activations are NHWC.
+ *   - there is NO CPU implementation behind any of these calls: without a usable
+ *     sm_100 device ynb_create fails with YNB_ERR_NO_DEVICE.
+ */
+#ifndef YOLONANO_B200_H_
+#define YOLONANO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YNB_ABI_VERSION 1
+
+/* status codes */
+#define YNB_OK               0
+#define YNB_ERR_INVALID      1   /* bad argument / shape                          */
+#define YNB_ERR_NO_DEVICE    2   /* no CUDA device, or not compute capability 10  */
+#define YNB_ERR_CUDA         3   /* a CUDA runtime / driver call failed           */
+#define YNB_ERR_STATE        4   /* call order (weights not committed, ...)       */
+#define YNB_ERR_UNSUPPORTED  5
+
+/* activation codes (utils/modules.py:14, backbone/shufflenetv2.py:48) */
+#define YNB_ACT_NONE  0
+#define YNB_ACT_RELU  1
+#define YNB_ACT_LEAKY 2          /* LeakyReLU(0.1) */
+
+/* arithmetic mode of the dense contractions (1x1 and 3x3 convs) */
+#define YNB_GEMM_FP32_FFMA   0   /* CUDA-core fp32 FMA (debug / cross-check path)            */
+#define YNB_GEMM_TC_3XTF32   1   /* tcgen05 kind::tf32, 3-term split: fp32 parity mode        */
+#define YNB_GEMM_TC_TF32     2   /* tcgen05 kind::tf32 single pass: throughput mode           */
+
+typedef struct ynb_engine ynb_engine;
+
+/* Mirrors the constructor arguments of YOLONano (models/yolo_nano.py:13). */
+typedef struct ynb_config {
+  int32_t abi_version;        /* must be YNB_ABI_VERSION                                    */
+  int32_t device;             /* CUDA device ordinal                                        */
+  int32_t input_size;         /* S, multiple of 32                                          */
+  int32_t num_classes;        /* C (20 VOC / 80 COCO)                                       */
+  int32_t num_anchors;        /* A = len(anchor_size)//3 (models/yolo_nano.py:24-25), 3      */
+  float   anchors[18];        /* [level][anchor][w,h] pixels (data/config.py:11-17)          */
+  float   conf_thresh;        /* models/yolo_nano.py:13 default 0.001                       */
+  float   nms_thresh;         /* default 0.5                                                */
+  int32_t diou_nms;           /* 0: nms (:159-188), 1: diou_nms (:191-242)                   */
+  int32_t gemm_mode;          /* YNB_GEMM_*                                                 */
+  int32_t max_batch;          /* workspace is planned for this many images per call         */
+} ynb_config;
+
+/* ---- lifecycle ------------------------------------------------------------------ */
+
+/* Replaces YOLONano.__init__ (models/yolo_nano.py:13-74) minus parameter creation. */
+int  ynb_create(const ynb_config* cfg, ynb_engine** out);
+void ynb_destroy(ynb_engine* e);
+/* Message of the last failing call on `e`; with e == NULL, of the last failing ynb_create. */
+const char* ynb_last_error(const ynb_engine* e);
+int  ynb_abi_version(void);
+
+/* Replaces YOLONano.set_grid / create_grid (models/yolo_nano.py:86-117): the grid is
+ * analytic in the kernels, so this only re-plans the workspace for the new S. */
+int  ynb_set_grid(ynb_engine* e, int32_t input_size);
+/* conf_thresh / nms_thresh / diou_nms are mutable attributes in the reference. */
+int  ynb_set_thresholds(ynb_engine* e, float conf_thresh, float nms_thresh, int32_t diou_nms);
+int  ynb_set_gemm_mode(ynb_engine* e, int32_t gemm_mode);
+/* Boxes per image N = A*(S/8)^2 + A*(S/16)^2 + A*(S/32)^2 for the current grid. */
+int64_t ynb_num_boxes(const ynb_engine* e);
+/* Bytes of device workspace the engine holds for `batch` images at the current S. */
+int64_t ynb_workspace_bytes(const ynb_engine* e, int32_t batch);
+
+/* ---- weights ---------------------------------------------------------------------- */
+
+/* The 77 convolutions of the path in engine order; names are the reference
+ * state_dict prefixes ("backbone.stage2.0.branch2.3", "head_det_1.4", ...). */
+int32_t     ynb_num_convs(void);
+const char* ynb_conv_name(int32_t index);
+/* weight shape [cout, cin_per_group, k, k] of conv `index` for a given class count. */
+int  ynb_conv_shape(int32_t index, int32_t num_classes, int32_t num_anchors,
+                    int32_t* cout, int32_t* cin_per_group, int32_t* ksize);
+
+/* Hands one conv's weights to the engine: `w_host` is the reference layout
+ * [cout, cin/groups, k, k] with BatchNorm already folded exactly as
+ * utils/fuse_conv_bn.py:6-22 does, `b_host` the folded bias [cout].  Host pointers;
+ * copied before return. */
+int  ynb_load_conv(ynb_engine* e, const char* name,
+                   const float* w_host, int64_t w_elems,
+                   const float* b_host, int64_t b_elems);
+/* Packs all 77 convs into the device layouts the kernels read (permuted / padded /
+ * tf32-split) and uploads them.  Synchronous. */
+int  ynb_commit_weights(ynb_engine* e);
+
+/* ---- the hot path ----------------------------------------------------------------- */
+
+/* backbone + neck + heads, raw head outputs in the reference's NCHW order
+ * [B, A*(1+C+4), H, W] for the three levels (models/yolo_nano.py:284-301).
+ * Parity hook. */
+int  ynb_forward_raw(ynb_engine* e, const float* x_dev, int32_t batch,
+                     float* pred_s_dev, float* pred_m_dev, float* pred_l_dev, void* stream);
+
+/* ... + re-layout, sigmoid/softmax, box decode, /S, clamp, class argmax
+ * (models/yolo_nano.py:303-330, 362-367, 253-256) for EVERY image of the batch:
+ *   boxes_dev  [B,N,4] x1y1x2y2 in [0,1];  scores_dev [B,N] = max_c softmax*obj;
+ *   cls_dev    [B,N] int32 argmax (first max wins).
+ * Parity hook for the decode stage (no threshold, no NMS). */
+int  ynb_forward_decode(ynb_engine* e, const float* x_dev, int32_t batch,
+                        float* boxes_dev, float* scores_dev, int32_t* cls_dev, void* stream);
+
+/* The whole path of YOLONano.forward in eval mode (models/yolo_nano.py:282-376):
+ * backbone, neck, heads, decode, score threshold, per-class (DIoU-)NMS — for every
+ * image.  Outputs are compacted per image in ascending anchor order:
+ *   out_boxes_dev [B,N,4], out_scores_dev [B,N], out_cls_dev [B,N] (first counts[b]
+ *   rows of image b valid), out_counts_dev [B] int32. */
+int  ynb_forward_detect(ynb_engine* e, const float* x_dev, int32_t batch,
+                        float* out_boxes_dev, float* out_scores_dev, int32_t* out_cls_dev,
+                        int32_t* out_counts_dev, void* stream);
+
+/* Same, with HOST buffers: x_host [B,3,S,S] (pinned memory recommended), results
+ * written to host arrays of the shapes above; host<->device copies are issued on
+ * `stream` and the call returns after they completed (the reference's own boundary
+ * is also synchronous: `.to('cpu').numpy()`, models/yolo_nano.py:370-371). */
+int  ynb_detect_host(ynb_engine* e, const float* x_host, int32_t batch,
+                     float* out_boxes_host, float* out_scores_host, int32_t* out_cls_host,
+                     int32_t* out_counts_host, void* stream);
+
+/* After any ynb_forward_*: copy an internal activation as canonical NCHW float32 into
+ * out_dev.  Names: "pool", "c3", "c4", "c5", "p3", "p4", "p5", and every backbone
+ * block output "stage2.0" ... "stage4.3".  Per-layer parity hook (SURVEY §8c hazard 1). */
+int  ynb_read_tap(ynb_engine* e, const char* tap, int32_t batch, float* out_dev, void* stream);
+/* Shape [C,H,W] of a tap at the current grid. */
+int  ynb_tap_shape(const ynb_engine* e, const char* tap, int32_t* c, int32_t* h, int32_t* w);
+
+/* Number of kernels the engine launched since creation (bench.py's gpu_launches). */
+int64_t ynb_launch_count(const ynb_engine* e);
+
+/* ---- individually callable kernels (unit parity + ncu) ------------------------------
+ * All take NHWC float32 device tensors with explicit channel strides (ld = floats
+ * between consecutive pixels) so that channel sub-ranges of a wider tensor can be
+ * read / written in place: that is how chunk / cat / channel_shuffle
+ * (backbone/shufflenetv2.py:14-28,70-76) cost nothing. */
+
+/* Depthwise 3x3, pad 1, stride 1|2, + bias + activation
+ * (backbone/shufflenetv2.py:66-67 + folded BN; models/yolo_nano.py:51 for the heads).
+ * w_dev is [9][C] (tap-major), b_dev [C].
+ *   out[b,y,x, out_off + c*out_step] = act(b[c] + sum_t w[t][c] * in[b, y*s+dy-1, x*s+dx-1, in_off + c]) */
+int  ynb_dwconv3x3(const float* in_dev, int32_t in_ld, int32_t in_off,
+                   float* out_dev, int32_t out_ld, int32_t out_off, int32_t out_step,
+                   const float* w_dev, const float* b_dev,
+                   int32_t batch, int32_t h_in, int32_t w_in, int32_t channels,
+                   int32_t stride, int32_t act, void* stream);
+
+/* Pointwise 1x1 conv = GEMM over pixels, + bias + activation, fp32 FFMA variant
+ * (backbone/shufflenetv2.py:46,54,60; utils/modules.py:11 with k=1).
+ * w_dev is [cout][cin] row-major, b_dev [cout].
+ *   out[m, out_off + n*out_step] = act(b[n] + sum_k w[n][k] * in[m, in_off + k]) */
+int  ynb_pwconv(const float* in_dev, int32_t in_ld, int32_t in_off,
+                float* out_dev, int32_t out_ld, int32_t out_off, int32_t out_step,
+                const float* w_dev, const float* b_dev,
+                int64_t pixels, int32_t cin, int32_t cout, int32_t act, void* stream);
+
+/* Same contraction on tcgen05 tensor cores (TMA-fed, TMEM accumulators);
+ * mode = YNB_GEMM_TC_3XTF32 | YNB_GEMM_TC_TF32.  Requires in_ld, in_off, out_ld,
+ * out_off multiples of 4 floats. */
+int  ynb_pwconv_tc(const float* in_dev, int32_t in_ld, int32_t in_off,
+                   float* out_dev, int32_t out_ld, int32_t out_off, int32_t out_step,
+                   const float* w_dev, const float* b_dev,
+                   int64_t pixels, int32_t cin, int32_t cout, int32_t act,
+                   int32_t mode, void* stream);
+
+/* Stem: Conv2d(3,24,3,2,1)+BN+ReLU then MaxPool2d(3,2,1), fused
+ * (backbone/shufflenetv2.py:109-116,158-159).  x_dev NCHW [B,3,S,S];
+ * out_dev NHWC [B,S/4,S/4,24]; w_dev [27][24] ((ci,ky,kx)-major), b_dev [24]. */
+int  ynb_stem_pool(const float* x_dev, float* out_dev, const float* w_dev, const float* b_dev,
+                   int32_t batch, int32_t input_size, void* stream);
+
+/* Decode of raw head outputs (models/yolo_nano.py:120-156, 303-330, 362-367, 253-256).
+ * raw_dev is NHWC [B, H*W, ld] for ONE level with the reference channel map
+ * (obj a | cls a*C+c | box 4a+k).  Writes rows [level_off, level_off + H*W*A) of
+ * boxes_dev [B,N,4], scores_dev [B,N], cls_dev [B,N]. */
+int  ynb_decode_level(const float* raw_dev, int32_t raw_ld,
+                      float* boxes_dev, float* scores_dev, int32_t* cls_dev,
+                      int32_t batch, int32_t grid, int32_t stride_px, int32_t input_size,
+                      const float* anchors_wh /* host, A*2 */, int32_t num_anchors,
+                      int32_t num_classes, int64_t boxes_per_image, int64_t level_off,
+                      void* stream);
+
+/* Threshold + per-image per-class greedy NMS (models/yolo_nano.py:159-279) on decoded
+ * candidates.  Inputs boxes_dev [B,N,4], scores_dev [B,N], cls_dev [B,N]; outputs as
+ * ynb_forward_detect, plus keep_dev [B,N] uint8 flags (may be NULL).
+ * Candidate order inside a class: score descending, ties by ascending anchor index.
+ * workspace_dev: ynb_nms_workspace_bytes(batch, n) bytes. */
+int64_t ynb_nms_workspace_bytes(int32_t batch, int64_t n);
+int  ynb_nms(const float* boxes_dev, const float* scores_dev, const int32_t* cls_dev,
+             int32_t batch, int64_t n, int32_t num_classes,
+             float conf_thresh, float nms_thresh, int32_t diou,
+             float* out_boxes_dev, float* out_scores_dev, int32_t* out_cls_dev,
+             int32_t* out_counts_dev, uint8_t* keep_dev,
+             void* workspace_dev, int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* YOLONANO_B200_H_ */

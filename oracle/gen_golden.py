@@ -1,0 +1,154 @@
+"""Generates tests/golden/*.npz by running the REAL reference (/root/reference).
+
+Run in the build container only (the reference checkout does not exist on the GPU
+box):   python -m oracle.gen_golden
+The fixtures pin the oracle restatement (tests/test_oracle_golden.py) and are the
+reference-side truth the CUDA path is compared with (tests/test_gpu_*.py).
+
+Recipe = SURVEY App. C: PYTHONDONTWRITEBYTECODE (read-only tree), `np.int = int` shim for
+models/yolo_nano.py:264, construct with trainable=False (no download).
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
+
+
+def _import_reference():
+    sys.dont_write_bytecode = True
+    np.int = int  # noqa: NPY001 - shim for the reference on NumPy >= 1.24
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    with contextlib.redirect_stdout(io.StringIO()):
+        from models.yolo_nano import YOLONano  # type: ignore
+        from data import config  # type: ignore
+        from utils.fuse_conv_bn import fuse_conv_bn  # type: ignore
+    return YOLONano, config, fuse_conv_bn
+
+
+def _build(YOLONano, size, classes, anchors, sd=None, seed=0, **kw):
+    torch.manual_seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = YOLONano(device=torch.device("cpu"), input_size=size, num_classes=classes,
+                     anchor_size=anchors, **kw).eval()
+    if sd is not None:
+        m.load_state_dict(sd, strict=True)
+    return m
+
+
+def _run_one(m, x1, tap_names=()):
+    """Reference forward on ONE image with taps; returns dict of numpy arrays."""
+    rec = {}
+    hooks = []
+
+    def hook(name):
+        def f(_mod, _inp, out):
+            rec[name] = out.detach().numpy().copy()
+        return f
+
+    named = dict(m.named_modules())
+    tapmap = {"pool": "backbone.maxpool", "lat3": "conv1x1_0", "lat4": "conv1x1_1", "lat5": "conv1x1_2",
+              "p3": "smooth_1", "p4": "smooth_2", "p5": "smooth_3", "fpn4": "smooth_0",
+              "pred_s": "head_det_1", "pred_m": "head_det_2", "pred_l": "head_det_3"}
+    for st, rep in ((2, 4), (3, 8), (4, 4)):
+        for i in range(rep):
+            tapmap[f"stage{st}.{i}"] = f"backbone.stage{st}.{i}"
+    tapmap["c3"], tapmap["c4"], tapmap["c5"] = "backbone.stage2", "backbone.stage3", "backbone.stage4"
+    for t in tap_names:
+        hooks.append(named[tapmap[t]].register_forward_hook(hook(t)))
+
+    orig_post = m.postprocess
+
+    def post(all_local, all_conf):
+        rec["all_bbox"] = all_local.copy()
+        cls = np.argmax(all_conf, axis=1)
+        rec["all_score"] = all_conf[(np.arange(all_conf.shape[0]), cls)].copy()
+        rec["all_cls"] = cls.astype(np.int32)
+        # 5th column carries the anchor index through the reference's own row selection
+        aug = np.concatenate([all_local, np.arange(len(all_local), dtype=np.float32)[:, None]], 1)
+        b, s, c = orig_post(aug, all_conf)
+        rec["keep_idx"] = b[:, 4].astype(np.int64)
+        return b[:, :4].copy(), s, c
+
+    m.postprocess = post
+    with torch.no_grad():
+        b, s, c = m(x1)
+    m.postprocess = orig_post
+    for h in hooks:
+        h.remove()
+    rec["bboxes"], rec["scores"], rec["cls_inds"] = b, s, c.astype(np.int64)
+    return rec
+
+
+def main():
+    from oracle import weights as W
+    YOLONano, config, fuse_conv_bn = _import_reference()
+    OUT.mkdir(parents=True, exist_ok=True)
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    meta_common = dict(torch=torch.__version__, numpy=np.__version__)
+
+    # ---- G1: BASELINE config C1 — 320x320, VOC-20, B=1, reference init --------------------
+    m = _build(YOLONano, 320, 20, config.MULTI_ANCHOR_SIZE, seed=0)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    mine = W.reference_init(20, seed=0)
+    assert list(mine.keys()) == list(sd.keys()) and all(torch.equal(mine[k], sd[k]) for k in sd), \
+        "parameter containers do not reproduce the reference init"
+    x = W.synthetic_input(1, 320, seed=0)
+    r = _run_one(m, x, ("c3", "c4", "c5", "pred_s", "pred_m", "pred_l"))
+    np.savez_compressed(OUT / "g1_voc320_refinit.npz", sd_digest=W.digest(sd), x_digest=W.digest(x),
+                        size=320, classes=20, seed=0, conf_thresh=0.001, nms_thresh=0.5, **meta_common, **r)
+    print("g1", r["bboxes"].shape, W.digest(sd))
+
+    # ---- G2: 128x128, COCO-80, B=2, calibrated weights, every tap ---------------------------
+    sd = W.calibrated(80, seed=1)
+    m = _build(YOLONano, 128, 80, config.MULTI_ANCHOR_SIZE_COCO, sd=sd)
+    x = W.synthetic_input(2, 128, seed=1)
+    taps = ["pool", "c3", "c4", "c5", "lat3", "lat4", "lat5", "fpn4", "p3", "p4", "p5",
+            "pred_s", "pred_m", "pred_l"] + [f"stage{s}.{i}" for s, n in ((2, 4), (3, 8), (4, 4)) for i in range(n)]
+    out = {}
+    for i in range(2):
+        r = _run_one(m, x[i:i + 1], taps)
+        for k, v in r.items():
+            out[f"img{i}.{k}"] = v
+    # DIoU + other thresholds on the same decoded candidates
+    for tag, kw in (("diou", dict(diou_nms=True)), ("t45c10", dict(conf_thresh=0.1, nms_thresh=0.45))):
+        m2 = _build(YOLONano, 128, 80, config.MULTI_ANCHOR_SIZE_COCO, sd=sd, **kw)
+        for i in range(2):
+            r = _run_one(m2, x[i:i + 1])
+            out[f"img{i}.{tag}.keep_idx"] = r["keep_idx"]
+    # fused model (utils/fuse_conv_bn.py): outputs after folding
+    m3 = fuse_conv_bn(_build(YOLONano, 128, 80, config.MULTI_ANCHOR_SIZE_COCO, sd=sd))
+    assert len(m3.state_dict()) == 154
+    r = _run_one(m3, x[0:1], ("pred_s",))
+    out["img0.fused.pred_s"] = r["pred_s"]
+    out["img0.fused.keep_idx"] = r["keep_idx"]
+    np.savez_compressed(OUT / "g2_coco128_calibrated.npz", sd_digest=W.digest(sd), x_digest=W.digest(x),
+                        size=128, classes=80, seed=1, conf_thresh=0.001, nms_thresh=0.5, **meta_common, **out)
+    print("g2", out["img0.bboxes"].shape, out["img1.bboxes"].shape, W.digest(sd))
+
+    # ---- G3: 416x416, COCO-80 (the bench config's shape), calibrated + reference init -------
+    for tag, sd, seed in (("calibrated", W.calibrated(80, seed=2), 2), ("refinit", W.reference_init(80, seed=3), 3)):
+        m = _build(YOLONano, 416, 80, config.MULTI_ANCHOR_SIZE_COCO, sd=sd)
+        x = W.synthetic_input(2, 416, seed=seed)
+        out = {}
+        for i in range(2):
+            r = _run_one(m, x[i:i + 1])
+            for k in ("all_bbox", "all_score", "all_cls", "keep_idx", "bboxes", "scores", "cls_inds"):
+                out[f"img{i}.{k}"] = r[k]
+        np.savez_compressed(OUT / f"g3_coco416_{tag}.npz", sd_digest=W.digest(sd), x_digest=W.digest(x),
+                            size=416, classes=80, seed=seed, conf_thresh=0.001, nms_thresh=0.5,
+                            **meta_common, **out)
+        print("g3", tag, out["img0.bboxes"].shape, out["img1.bboxes"].shape)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,198 @@
+"""Thin Python handle over the C-ABI engine (include/yolonano_b200.h).
+
+PyTorch is used here only for device memory and the current stream; every
+computation happens inside libyolonano_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from .topology import conv_table, num_anchor_boxes
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream_ptr(device: torch.device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class Engine:
+    """One engine per (GPU, stream).  Not thread-safe (same as the C handle)."""
+
+    def __init__(self, device: torch.device, input_size: int, num_classes: int,
+                 anchor_size: Sequence[Sequence[float]], conf_thresh: float = 0.001,
+                 nms_thresh: float = 0.5, diou_nms: bool = False,
+                 gemm_mode: int = _lib.GEMM_TC_3XTF32, max_batch: int = 1):
+        self.lib = _lib.load()
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise EngineError("the B200 engine only runs on a CUDA device (no CPU fallback)")
+        self.device = torch.device("cuda", device.index if device.index is not None
+                                   else torch.cuda.current_device())
+        flat = [float(v) for wh in anchor_size for v in wh]
+        if len(flat) != 18:
+            raise EngineError("anchor_size must hold 9 [w,h] pairs (3 levels x 3 anchors)")
+        cfg = _lib.YnbConfig()
+        cfg.abi_version = _lib.YNB_ABI_VERSION
+        cfg.device = self.device.index
+        cfg.input_size = int(input_size)
+        cfg.num_classes = int(num_classes)
+        cfg.num_anchors = 3
+        cfg.anchors = (C.c_float * 18)(*flat)
+        cfg.conf_thresh = float(conf_thresh)
+        cfg.nms_thresh = float(nms_thresh)
+        cfg.diou_nms = int(bool(diou_nms))
+        cfg.gemm_mode = int(gemm_mode)
+        cfg.max_batch = int(max_batch)
+        self.num_classes = int(num_classes)
+        self.input_size = int(input_size)
+        self.table = conv_table(self.num_classes)
+        self._h = C.c_void_p()
+        rc = self.lib.ynb_create(C.byref(cfg), C.byref(self._h))
+        if rc != _lib.YNB_OK:
+            msg = self.lib.ynb_last_error(None)
+            self._h = C.c_void_p()
+            raise EngineError(f"ynb_create failed ({rc}): {msg.decode() if msg else '?'}")
+
+    # -- plumbing -----------------------------------------------------------------
+    def _check(self, rc: int, what: str):
+        if rc != _lib.YNB_OK:
+            msg = self.lib.ynb_last_error(self._h)
+            raise EngineError(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.ynb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def num_boxes(self) -> int:
+        return int(self.lib.ynb_num_boxes(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.ynb_launch_count(self._h))
+
+    def workspace_bytes(self, batch: int) -> int:
+        return int(self.lib.ynb_workspace_bytes(self._h, batch))
+
+    def set_grid(self, input_size: int):
+        self._check(self.lib.ynb_set_grid(self._h, int(input_size)), "ynb_set_grid")
+        self.input_size = int(input_size)
+
+    def set_thresholds(self, conf: float, nms: float, diou: bool):
+        self._check(self.lib.ynb_set_thresholds(self._h, float(conf), float(nms), int(bool(diou))),
+                    "ynb_set_thresholds")
+
+    def set_gemm_mode(self, mode: int):
+        self._check(self.lib.ynb_set_gemm_mode(self._h, int(mode)), "ynb_set_gemm_mode")
+
+    # -- weights ------------------------------------------------------------------
+    def load_weights(self, fused: Dict[str, Tuple[torch.Tensor, torch.Tensor]]):
+        """`fused[name] = (W [cout,cin/g,k,k], b [cout])`, BN already folded, any device."""
+        for spec in self.table:
+            w, b = fused[spec.name]
+            w = w.detach().to("cpu", torch.float32).contiguous()
+            b = b.detach().to("cpu", torch.float32).contiguous()
+            if tuple(w.shape) != spec.weight_shape() or b.numel() != spec.cout:
+                raise EngineError(f"{spec.name}: weight {tuple(w.shape)} / bias {tuple(b.shape)} "
+                                  f"do not match {spec.weight_shape()}")
+            self._check(self.lib.ynb_load_conv(self._h, spec.name.encode(), _ptr(w), w.numel(),
+                                               _ptr(b), b.numel()), f"ynb_load_conv({spec.name})")
+        self._check(self.lib.ynb_commit_weights(self._h), "ynb_commit_weights")
+
+    # -- the path -----------------------------------------------------------------
+    def _check_input(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise EngineError("input must live on the engine's GPU (no CPU fallback)")
+        if x.device != self.device:
+            raise EngineError(f"input on {x.device}, engine on {self.device}")
+        if x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != 3:
+            raise EngineError("input must be float32 [B,3,S,S]")
+        s = self.input_size
+        if x.shape[2] != s or x.shape[3] != s:
+            # the reference fails with a broadcasting RuntimeError here
+            raise RuntimeError(f"input is {tuple(x.shape[2:])} but the grid is set for {s}x{s}; "
+                               "call set_grid first")
+        return x.contiguous()
+
+    def forward_raw(self, x: torch.Tensor):
+        x = self._check_input(x)
+        b, s = x.shape[0], self.input_size
+        ch = 3 * (1 + self.num_classes + 4)
+        outs = [torch.empty((b, ch, s // st, s // st), device=self.device, dtype=torch.float32)
+                for st in (8, 16, 32)]
+        self._check(self.lib.ynb_forward_raw(self._h, _ptr(x), b, _ptr(outs[0]), _ptr(outs[1]),
+                                             _ptr(outs[2]), _stream_ptr(self.device)),
+                    "ynb_forward_raw")
+        return outs
+
+    def forward_decode(self, x: torch.Tensor):
+        x = self._check_input(x)
+        b, n = x.shape[0], self.num_boxes
+        boxes = torch.empty((b, n, 4), device=self.device, dtype=torch.float32)
+        scores = torch.empty((b, n), device=self.device, dtype=torch.float32)
+        cls = torch.empty((b, n), device=self.device, dtype=torch.int32)
+        self._check(self.lib.ynb_forward_decode(self._h, _ptr(x), b, _ptr(boxes), _ptr(scores),
+                                                _ptr(cls), _stream_ptr(self.device)),
+                    "ynb_forward_decode")
+        return boxes, scores, cls
+
+    def forward_detect(self, x: torch.Tensor, out=None):
+        """Returns device tensors (boxes [B,N,4], scores [B,N], cls [B,N] i32, counts [B] i32)."""
+        x = self._check_input(x)
+        b, n = x.shape[0], self.num_boxes
+        if out is None:
+            out = self.alloc_outputs(b)
+        boxes, scores, cls, counts = out
+        self._check(self.lib.ynb_forward_detect(self._h, _ptr(x), b, _ptr(boxes), _ptr(scores),
+                                                _ptr(cls), _ptr(counts), _stream_ptr(self.device)),
+                    "ynb_forward_detect")
+        return boxes, scores, cls, counts
+
+    def alloc_outputs(self, batch: int, pinned_host: bool = False):
+        n = self.num_boxes
+        kw = dict(device="cpu", pin_memory=True) if pinned_host else dict(device=self.device)
+        return (torch.empty((batch, n, 4), dtype=torch.float32, **kw),
+                torch.empty((batch, n), dtype=torch.float32, **kw),
+                torch.empty((batch, n), dtype=torch.int32, **kw),
+                torch.empty((batch,), dtype=torch.int32, **kw))
+
+    def detect_host(self, x_host: torch.Tensor, out_host=None):
+        """Host buffers in, host buffers out; copies happen inside the call."""
+        if x_host.is_cuda or x_host.dtype != torch.float32 or x_host.dim() != 4:
+            raise EngineError("detect_host wants a float32 host tensor [B,3,S,S]")
+        x_host = x_host.contiguous()
+        b = x_host.shape[0]
+        if out_host is None:
+            out_host = self.alloc_outputs(b, pinned_host=True)
+        boxes, scores, cls, counts = out_host
+        self._check(self.lib.ynb_detect_host(self._h, _ptr(x_host), b, _ptr(boxes), _ptr(scores),
+                                             _ptr(cls), _ptr(counts), _stream_ptr(self.device)),
+                    "ynb_detect_host")
+        return boxes, scores, cls, counts
+
+    def read_tap(self, name: str, batch: int) -> torch.Tensor:
+        c, h, w = C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(self.lib.ynb_tap_shape(self._h, name.encode(), C.byref(c), C.byref(h), C.byref(w)),
+                    f"ynb_tap_shape({name})")
+        out = torch.empty((batch, c.value, h.value, w.value), device=self.device, dtype=torch.float32)
+        self._check(self.lib.ynb_read_tap(self._h, name.encode(), batch, _ptr(out),
+                                          _stream_ptr(self.device)), f"ynb_read_tap({name})")
+        return out
