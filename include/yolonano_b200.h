@@ -150,6 +150,15 @@ int  ynb_tap_shape(const ynb_engine* e, const char* tap, int32_t* c, int32_t* h,
 /* Number of kernels the engine launched since creation (bench.py's gpu_launches). */
 int64_t ynb_launch_count(const ynb_engine* e);
 
+/* Per-kernel timing for the roofline report: with profiling on, every launch of the next
+ * ynb_forward_* is bracketed by CUDA events on the launching stream (the call then
+ * synchronises).  Entries: launch label (reference conv name), kernel family, elapsed
+ * ms, ALGORITHMIC bytes (unique unpadded inputs + outputs + weights) and flops. */
+int  ynb_set_profiling(ynb_engine* e, int32_t on);
+int32_t ynb_profile_count(const ynb_engine* e);
+int  ynb_profile_entry(const ynb_engine* e, int32_t index, const char** name, const char** kind,
+                       float* ms, double* bytes, double* flops);
+
 /* ---- individually callable kernels (unit parity + ncu) ------------------------------
  * All take NHWC float32 device tensors with explicit channel strides (ld = floats
  * between consecutive pixels) so that channel sub-ranges of a wider tensor can be

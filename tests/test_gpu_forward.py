@@ -1,0 +1,204 @@
+"""End-to-end parity of the engine and the drop-in module on a real B200."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import weights as W  # noqa: E402
+from oracle import yolo_nano_oracle as O  # noqa: E402
+
+TAPS = ["pool"] + [f"stage{s}.{i}" for s, n in ((2, 4), (3, 8), (4, 4)) for i in range(n)] + \
+       ["c3", "c4", "c5", "lat3", "lat4", "lat5", "fpn4", "p3", "p4", "p5", "pred_s", "pred_m", "pred_l"]
+# per-layer tolerance relative to the layer's own scale, per arithmetic mode
+LAYER_TOL = {"ffma": 2e-5, "3xtf32": 2e-5, "tf32": 2e-2}
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpu_util
+    return gpu_util
+
+
+@pytest.fixture(scope="module")
+def g2(golden):
+    return golden("g2_coco128_calibrated.npz")
+
+
+@pytest.mark.parametrize("mode", ["ffma", "3xtf32", "tf32"])
+def test_every_layer_matches_reference_calibrated(G, g2, mode):
+    """Per-layer parity against tensors recorded from the REAL reference with calibrated
+    weights (O(1) activations everywhere; SURVEY §8c hazard 1)."""
+    sd = W.calibrated(80, seed=1)
+    x = W.synthetic_input(2, 128, 1).to(G.DEV)
+    eng = G.make_engine(sd, 128, 80, mode)
+    raw = eng.forward_raw(x)
+    torch.cuda.synchronize()
+    worst = {}
+    for name in TAPS:
+        got = eng.read_tap(name, 2).cpu().numpy()
+        for i in range(2):
+            worst[name] = max(worst.get(name, 0.0), G.rel_err(got[i:i + 1], g2[f"img{i}.{name}"]))
+    bad = {k: v for k, v in worst.items() if not v < LAYER_TOL[mode]}
+    assert not bad, f"{mode}: layers out of tolerance {bad}"
+    if mode != "tf32":
+        # north_star: raw head outputs within 1e-3 absolute and 1e-4 relative
+        for i, k in enumerate(("pred_s", "pred_m", "pred_l")):
+            for b in range(2):
+                np.testing.assert_allclose(raw[i][b:b + 1].cpu().numpy(), g2[f"img{b}.{k}"], rtol=1e-4, atol=1e-3)
+    eng.close()
+
+
+@pytest.mark.parametrize("mode", ["ffma", "3xtf32"])
+def test_c1_config_voc320_reference_init(G, golden, mode):
+    """BASELINE config C1 (320x320, VOC-20, batch 1, reference init) against the reference."""
+    g1 = golden("g1_voc320_refinit.npz")
+    sd = W.reference_init(20, seed=0)
+    x = W.synthetic_input(1, 320, 0).to(G.DEV)
+    eng = G.make_engine(sd, 320, 20, mode, max_batch=1)
+    raw = eng.forward_raw(x)
+    for got, k in zip(raw, ("pred_s", "pred_m", "pred_l")):
+        np.testing.assert_allclose(got.cpu().numpy(), g1[k], rtol=1e-4, atol=1e-3)
+    for k in ("c3", "c4", "c5"):   # collapsed activations: compare relative to their own scale
+        assert G.rel_err(eng.read_tap(k, 1).cpu().numpy(), g1[k]) < 2e-5, k
+    boxes, scores, cls = eng.forward_decode(x)
+    assert float(np.abs(boxes[0].cpu().numpy() - g1["all_bbox"]).max()) * 320 < 1e-3    # px
+    np.testing.assert_allclose(scores[0].cpu().numpy(), g1["all_score"], rtol=1e-4, atol=1e-7)
+    ob, os_, oc, on = eng.forward_detect(x)
+    k = int(on[0])
+    # keep-set: exact w.r.t. the oracle on the engine's own candidates ...
+    bh, sh, ch = boxes[0].cpu().numpy(), scores[0].cpu().numpy(), cls[0].cpu().numpy().astype(np.int64)
+    b, s, c, idx = O.postprocess_flat(bh, sh, ch, 20, 0.001, 0.5)
+    assert k == len(idx)
+    np.testing.assert_array_equal(ob[0, :k].cpu().numpy(), b)
+    # ... and against the reference's own keep-set the difference is bounded and reported:
+    # reference-init scores tie by the hundreds (hazard 2) and sit 1e-8 apart, so ordering
+    # flips from 1-ulp score differences are expected here; the calibrated test below is exact.
+    diff = np.setxor1d(idx, g1["keep_idx"])
+    print(f"[report] C1 {mode}: kept {k} vs reference {len(g1['keep_idx'])}, {len(diff)} boxes differ (ties / ulp order)")
+    assert len(diff) <= 0.05 * len(g1["keep_idx"])
+    eng.close()
+
+
+def test_detect_matches_reference_keepset_calibrated(G, g2):
+    """Tie-free weights: the full CUDA path must reproduce the reference detections:
+    same kept anchors, boxes within 1e-3 px, same classes.  Pairs whose IoU is within 1e-5
+    of the threshold may flip (north_star exception) — counted and reported."""
+    sd = W.calibrated(80, seed=1)
+    x = W.synthetic_input(2, 128, 1).to(G.DEV)
+    eng = G.make_engine(sd, 128, 80, "3xtf32")
+    boxes, scores, cls = eng.forward_decode(x)
+    ob, os_, oc, on = eng.forward_detect(x)
+    total_diff = 0
+    for i in range(2):
+        k = int(on[i])
+        bh, sh, ch = boxes[i].cpu().numpy(), scores[i].cpu().numpy(), cls[i].cpu().numpy().astype(np.int64)
+        assert float(np.abs(bh - g2[f"img{i}.all_bbox"]).max()) * 128 < 1e-3
+        np.testing.assert_allclose(sh, g2[f"img{i}.all_score"], rtol=1e-4, atol=1e-7)
+        assert (ch != g2[f"img{i}.all_cls"]).mean() < 1e-3
+        _, _, _, idx = O.postprocess_flat(bh, sh, ch, 80, 0.001, 0.5)
+        assert k == len(idx)
+        np.testing.assert_array_equal(ob[i, :k].cpu().numpy(), bh[idx])
+        np.testing.assert_array_equal(oc[i, :k].cpu().numpy(), ch[idx])
+        diff = np.setxor1d(idx, g2[f"img{i}.keep_idx"])
+        total_diff += len(diff)
+        print(f"[report] img{i}: kept {k}, reference kept {len(g2[f'img{i}.keep_idx'])}, differing {len(diff)}")
+    assert total_diff <= 4, "keep-sets differ by more than near-threshold / near-tie flips explain"
+    eng.close()
+
+
+def test_fused_and_unfused_weights_agree(G, g2):
+    """fuse_conv_bn'd module (154 keys) through the drop-in gives the same engine weights."""
+    import yolo_nano_b200 as pkg
+    sd = W.calibrated(80, seed=1)
+    x = W.synthetic_input(2, 128, 1).to(G.DEV)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = pkg.YOLONano(G.DEV, 128, 80, anchor_size=pkg.MULTI_ANCHOR_SIZE_COCO)
+    m.load_state_dict(sd)
+    m = m.to(G.DEV).eval()
+    r1 = m(x)
+    pkg.fuse_conv_bn(m)
+    assert len(m.state_dict()) == 154
+    r2 = m(x)
+    for a, b in zip(r1, r2):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(np.sort(np.unique(r1[2])), np.sort(np.unique(g2["img0.cls_inds"])))
+
+
+def test_dropin_module_contract(G, golden):
+    """forward(x) -> (bboxes ndarray [K,4] f32 writable, scores [K] f32, cls_inds [K] i64),
+    image 0 only; set_grid between calls; K=0 shapes; CPU input raises."""
+    import yolo_nano_b200 as pkg
+    g1 = golden("g1_voc320_refinit.npz")
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = pkg.YOLONano(G.DEV, 320, 20, anchor_size=pkg.MULTI_ANCHOR_SIZE)
+    m.load_state_dict(W.reference_init(20, 0))
+    m = m.to(G.DEV).eval()
+    x = W.synthetic_input(1, 320, 0).to(G.DEV)
+    b, s, c = m(torch.cat([x, torch.zeros_like(x)]))          # image 1 is ignored like the reference
+    assert b.dtype == np.float32 and s.dtype == np.float32 and c.dtype == np.int64
+    assert b.ndim == 2 and b.shape[1] == 4 and b.flags.writeable and b.flags.owndata
+    assert abs(len(b) - len(g1["bboxes"])) <= 0.05 * len(g1["bboxes"])
+    assert b.min() >= 0 and b.max() <= 1
+    b -= 0.1                                                    # callers rescale in place
+    m.conf_thresh = 0.9                                         # nothing survives
+    b0, s0, c0 = m(x)
+    assert b0.shape == (0, 4) and s0.shape == (0,) and c0.shape == (0,)
+    m.conf_thresh = 0.001
+    m.set_grid(160)                                             # TTA / multi-scale path
+    b2, _, _ = m(W.synthetic_input(1, 160, 3).to(G.DEV))
+    assert b2.shape[1] == 4
+    with pytest.raises(RuntimeError):
+        m(x)                                                    # 320 input on a 160 grid
+    with pytest.raises(pkg.EngineError):
+        m(x.cpu())
+    res = m.detect(W.synthetic_input(3, 160, 4).to(G.DEV))
+    assert len(res) == 3
+
+
+def test_batch64_equals_per_image_and_host_path(G):
+    """BASELINE config 2 shape (416x416, COCO-80, batch 64): every image of the batch gives
+    bit-identical detections to running it alone (batch extension = loop the reference),
+    and the host-buffer entry point returns the same rows."""
+    sd = W.calibrated(80, seed=2)
+    bsz = 64
+    x = W.synthetic_input(bsz, 416, 2).to(G.DEV)
+    eng = G.make_engine(sd, 416, 80, "3xtf32", max_batch=bsz)
+    ob, os_, oc, on = [t.clone() for t in eng.forward_detect(x)]
+    torch.cuda.synchronize()
+    assert int(on.min()) > 0
+    for i in (0, 17, 63):
+        b1, s1, c1, n1 = eng.forward_detect(x[i:i + 1])
+        k = int(n1[0])
+        assert k == int(on[i])
+        assert torch.equal(b1[0, :k], ob[i, :k]) and torch.equal(s1[0, :k], os_[i, :k]) and torch.equal(c1[0, :k], oc[i, :k])
+    xh = x.cpu().pin_memory()
+    hb, hs, hc, hn = eng.detect_host(xh)
+    assert torch.equal(hn, on.cpu())
+    for i in (0, 31, 63):
+        k = int(hn[i])
+        assert torch.equal(hb[i, :k], ob[i, :k].cpu()) and torch.equal(hc[i, :k], oc[i, :k].cpu())
+    # one image against the reference-recorded keep-set (g3 was generated with seed 2, images 0..1)
+    eng.close()
+
+
+def test_g3_416_against_reference(G, golden):
+    g = golden("g3_coco416_calibrated.npz")
+    sd = W.calibrated(80, seed=2)
+    x = W.synthetic_input(2, 416, 2).to(G.DEV)
+    eng = G.make_engine(sd, 416, 80, "3xtf32")
+    boxes, scores, cls = eng.forward_decode(x)
+    ob, os_, oc, on = eng.forward_detect(x)
+    for i in range(2):
+        assert float(np.abs(boxes[i].cpu().numpy() - g[f"img{i}.all_bbox"]).max()) * 416 < 1e-3
+        k = int(on[i])
+        _, _, _, idx = O.postprocess_flat(boxes[i].cpu().numpy(), scores[i].cpu().numpy(),
+                                          cls[i].cpu().numpy().astype(np.int64), 80, 0.001, 0.5)
+        assert k == len(idx)
+        diff = np.setxor1d(idx, g[f"img{i}.keep_idx"])
+        print(f"[report] 416 img{i}: kept {k}, reference {len(g[f'img{i}.keep_idx'])}, differing {len(diff)}")
+        assert len(diff) <= 0.002 * k + 2
+    eng.close()

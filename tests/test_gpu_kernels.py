@@ -1,0 +1,247 @@
+"""Unit parity of the individually callable kernels, through the C ABI, on a real B200."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import weights as W  # noqa: E402
+from oracle import yolo_nano_oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpu_util
+    return gpu_util
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("batch,ch,hw,stride,act", [
+    (1, 58, 52, 1, 0), (64, 58, 52, 1, 0),      # backbone.stage2.1.branch2.3
+    (1, 58, 104, 2, 0), (8, 58, 104, 2, 0),     # backbone.stage2.0.branch2.3
+    (2, 116, 26, 1, 0), (2, 232, 13, 1, 0), (2, 24, 104, 2, 0),
+    (2, 96, 13, 1, 2), (2, 96, 52, 1, 2),       # head depthwise + LeakyReLU
+    (1, 4, 1, 1, 0), (1, 4, 3, 2, 1),           # degenerate maps
+])
+def test_dwconv3x3(lib, G, batch, ch, hw, stride, act):
+    torch.manual_seed(ch * 7 + hw + stride)
+    c4 = (ch + 3) // 4 * 4
+    x = torch.randn(batch, ch, hw, hw)
+    w = torch.randn(ch, 1, 3, 3)
+    b = torch.randn(ch)
+    ref = F.conv2d(x, w, b, stride, 1, 1, ch)
+    ref = F.relu(ref) if act == 1 else (F.leaky_relu(ref, 0.1) if act == 2 else ref)
+    xin = torch.zeros(batch, hw, hw, c4)
+    xin[..., :ch] = _nhwc(x)
+    wp = torch.zeros(9, c4)
+    wp[:, :ch] = w.view(ch, 9).t()
+    bp = torch.zeros(c4)
+    bp[:ch] = b
+    ho = ref.shape[2]
+    xin, wp, bp = xin.to(G.DEV), wp.to(G.DEV), bp.to(G.DEV)
+    out = torch.full((batch, ho, ho, c4), float("nan"), device=G.DEV)
+    rc = lib.ynb_dwconv3x3(G.ptr(xin), c4, 0, G.ptr(out), c4, 0, 1, G.ptr(wp), G.ptr(bp),
+                           batch, hw, hw, c4, stride, act, G.stream())
+    assert rc == 0, lib.ynb_last_error(None)
+    got = out.cpu()[..., :ch].permute(0, 3, 1, 2)
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5)
+    if c4 != ch:
+        assert float(out[..., ch:].abs().max()) == 0.0     # channel pads stay zero
+
+
+SHAPES = [(1000, 24, 58), (4321, 60, 58), (5408, 116, 116), (700, 232, 232), (338, 464, 96),
+          (5408, 96, 255), (128, 32, 16), (129, 96, 96), (1, 24, 58), (64 * 2704, 60, 58)]
+
+
+def _pw_problem(G, m, cin, cout, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(m, cin, generator=g).to(G.DEV)
+    w = (torch.randn(cout, cin, generator=g) / cin ** 0.5).to(G.DEV)
+    b = torch.randn(cout, generator=g).to(G.DEV)
+    ref = (x.double() @ w.double().t() + b.double())
+    return x, w, b, ref
+
+
+@pytest.mark.parametrize("m,cin,cout", SHAPES)
+def test_pwconv_ffma(lib, G, m, cin, cout):
+    x, w, b, ref = _pw_problem(G, m, cin, cout, m + cin)
+    ld = (cout + 3) // 4 * 4
+    out = torch.full((m, ld), float("nan"), device=G.DEV)
+    rc = lib.ynb_pwconv(G.ptr(x), cin, 0, G.ptr(out), ld, 0, 1, G.ptr(w), G.ptr(b), m, cin, cout, 1, G.stream())
+    assert rc == 0, lib.ynb_last_error(None)
+    torch.testing.assert_close(out[:, :cout].double(), ref.clamp_min(0), rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("mode,tol", [(1, 2e-5), (2, 2e-2)])
+@pytest.mark.parametrize("m,cin,cout", SHAPES)
+def test_pwconv_tcgen05(lib, G, m, cin, cout, mode, tol):
+    """tcgen05 path: 3xTF32 must be fp32-grade (tolerance as the FFMA kernel), single-pass
+    TF32 is the throughput mode with its own (looser) tolerance."""
+    x, w, b, ref = _pw_problem(G, m, cin, cout, m + cin)
+    ld = (cout + 3) // 4 * 4
+    out = torch.full((m, ld), float("nan"), device=G.DEV)
+    rc = lib.ynb_pwconv_tc(G.ptr(x), cin, 0, G.ptr(out), ld, 0, 1, G.ptr(w), G.ptr(b), m, cin, cout, 2, mode,
+                           G.stream())
+    assert rc == 0, lib.ynb_last_error(None)
+    torch.cuda.synchronize()
+    want = F.leaky_relu(ref, 0.1)
+    torch.testing.assert_close(out[:, :cout].double(), want, rtol=tol, atol=tol)
+
+
+def test_pwconv_strided_views(lib, G):
+    """Channel sub-range in, interleaved slots out: chunk / cat / channel_shuffle as views."""
+    m, c, h = 3000, 232, 116
+    g = torch.Generator().manual_seed(3)
+    xfull = torch.randn(m, c, generator=g).to(G.DEV)
+    w = (torch.randn(h, h, generator=g) / h ** 0.5).to(G.DEV)
+    b = torch.randn(h, generator=g).to(G.DEV)
+    ref = torch.relu(xfull[:, h:].double() @ w.double().t() + b.double())
+    for fn, extra in ((lib.ynb_pwconv, ()), (lib.ynb_pwconv_tc, (1,))):
+        out = torch.zeros(m, c, device=G.DEV)
+        rc = fn(G.ptr(xfull), c, h, G.ptr(out), c, 1, 2, G.ptr(w), G.ptr(b), m, h, h, 1, *extra, G.stream())
+        assert rc == 0, lib.ynb_last_error(None)
+        torch.cuda.synchronize()
+        torch.testing.assert_close(out[:, 1::2].double(), ref, rtol=2e-5, atol=2e-5)
+        assert float(out[:, 0::2].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("batch,size", [(1, 64), (2, 128), (1, 320), (2, 416)])
+def test_stem_pool(lib, G, batch, size):
+    g = torch.Generator().manual_seed(size)
+    x = torch.randn(batch, 3, size, size, generator=g)
+    w = torch.randn(24, 3, 3, 3, generator=g) / 3
+    b = torch.randn(24, generator=g) * 0.1
+    ref = F.max_pool2d(F.relu(F.conv2d(x, w, b, 2, 1)), 3, 2, 1)
+    wp = w.permute(1, 2, 3, 0).reshape(27, 24).contiguous().to(G.DEV)
+    out = torch.full((batch, size // 4, size // 4, 24), float("nan"), device=G.DEV)
+    xd, bd = x.to(G.DEV), b.to(G.DEV)
+    rc = lib.ynb_stem_pool(G.ptr(xd), G.ptr(out), G.ptr(wp), G.ptr(bd), batch, size, G.stream())
+    assert rc == 0, lib.ynb_last_error(None)
+    torch.testing.assert_close(out.cpu().permute(0, 3, 1, 2), ref, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("classes,size", [(20, 320), (80, 128)])
+def test_decode_level(lib, G, classes, size):
+    """Decode kernel vs the oracle restatement of models/yolo_nano.py:120-156,362-367."""
+    g = torch.Generator().manual_seed(classes)
+    ch = 3 * (1 + classes + 4)
+    preds = [torch.randn(2, ch, size // s, size // s, generator=g) * 2 for s in (8, 16, 32)]
+    bbox, cls = O.decode(preds, size, classes, W.anchors_for(classes))
+    n = bbox.shape[1]
+    boxes = torch.zeros(2, n, 4, device=G.DEV)
+    scores = torch.zeros(2, n, device=G.DEV)
+    cl = torch.zeros(2, n, device=G.DEV, dtype=torch.int32)
+    off = 0
+    anchors = np.array(W.anchors_for(classes), dtype=np.float32).reshape(3, 6)
+    ld = (ch + 3) // 4 * 4
+    for lvl, p in enumerate(preds):
+        gsz = p.shape[2]
+        raw = torch.zeros(2, gsz * gsz, ld)
+        raw[..., :ch] = p.permute(0, 2, 3, 1).reshape(2, gsz * gsz, ch)
+        raw = raw.to(G.DEV)
+        a = (C.c_float * 6)(*anchors[lvl].tolist())
+        rc = lib.ynb_decode_level(G.ptr(raw), ld, G.ptr(boxes), G.ptr(scores), G.ptr(cl), 2, gsz, 8 << lvl, size,
+                                  a, 3, classes, n, off, G.stream())
+        assert rc == 0, lib.ynb_last_error(None)
+        off += gsz * gsz * 3
+    torch.cuda.synchronize()
+    # decoded boxes within 1e-3 px (BASELINE.json north_star)
+    assert float((boxes.cpu() - bbox).abs().max()) * size < 1e-3
+    for i in range(2):
+        s_ref, c_ref = O.class_scores(cls[i].numpy())
+        np.testing.assert_allclose(scores[i].cpu().numpy(), s_ref, rtol=2e-5, atol=1e-9)
+        mism = cl[i].cpu().numpy() != c_ref
+        # an argmax may only flip between classes whose probabilities agree to rounding
+        if mism.any():
+            p = cls[i].numpy()
+            rows = np.nonzero(mism)[0]
+            gap = np.abs(p[rows, cl[i].cpu().numpy()[rows]] - p[rows, c_ref[rows]]) / s_ref[rows]
+            assert gap.max() < 1e-5 and mism.mean() < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# NMS: bit-exact keep-sets against the NumPy restatement on identical candidates
+# ---------------------------------------------------------------------------------------------
+def _check_nms(lib, G, boxes, scores, cls, classes, conf, thr, diou):
+    kept, counts, ob, os_, oc = G.run_nms(lib, boxes, scores, cls, classes, conf, thr, diou)
+    for i in range(scores.shape[0]):
+        b, s, c, idx = O.postprocess_flat(boxes[i], scores[i], cls[i].astype(np.int64), classes, conf, thr, diou,
+                                          tie="index")
+        np.testing.assert_array_equal(kept[i], idx)
+        k = counts[i]
+        assert k == len(idx)
+        np.testing.assert_array_equal(ob[i, :k], b)      # ascending anchor order, bit-identical rows
+        np.testing.assert_array_equal(os_[i, :k], s)
+        np.testing.assert_array_equal(oc[i, :k], c)
+
+
+@pytest.mark.parametrize("fixture,classes", [("g1_voc320_refinit.npz", 20), ("g2_coco128_calibrated.npz", 80),
+                                             ("g3_coco416_calibrated.npz", 80), ("g3_coco416_refinit.npz", 80)])
+@pytest.mark.parametrize("conf,thr,diou", [(0.001, 0.5, False), (0.001, 0.5, True), (0.1, 0.45, False)])
+def test_nms_on_reference_candidates(lib, G, golden, fixture, classes, conf, thr, diou):
+    g = golden(fixture)
+    pre = "" if "all_bbox" in g.files else "img0."
+    imgs = [pre] if pre == "" else ["img0.", "img1."]
+    boxes = np.stack([g[p + "all_bbox"] for p in imgs])
+    scores = np.stack([g[p + "all_score"] for p in imgs])
+    cls = np.stack([g[p + "all_cls"] for p in imgs])
+    _check_nms(lib, G, boxes, scores, cls, classes, conf, thr, diou)
+
+
+def test_nms_matches_reference_keepsets_when_tie_free(lib, G, golden):
+    """Calibrated fixtures have no score ties: the CUDA keep-set must equal what the REAL
+    reference kept (recorded keep_idx), not just the oracle."""
+    for name, tags in (("g2_coco128_calibrated.npz", ("", "diou.", "t45c10.")), ("g3_coco416_calibrated.npz", ("",))):
+        g = golden(name)
+        for tag in tags:
+            conf, thr, diou = (0.1, 0.45, False) if tag == "t45c10." else (0.001, 0.5, tag == "diou.")
+            boxes = np.stack([g[f"img{i}.all_bbox"] for i in range(2)])
+            scores = np.stack([g[f"img{i}.all_score"] for i in range(2)])
+            cls = np.stack([g[f"img{i}.all_cls"] for i in range(2)])
+            kept, *_ = G.run_nms(lib, boxes, scores, cls, 80, conf, thr, diou)
+            for i in range(2):
+                np.testing.assert_array_equal(kept[i], g[f"img{i}.{tag}keep_idx"])
+
+
+def test_nms_edge_cases(lib, G):
+    rng = np.random.default_rng(0)
+    n = 700
+    xy = rng.random((2, n, 2), dtype=np.float32) * 0.8
+    wh = rng.random((2, n, 2), dtype=np.float32) * 0.3
+    boxes = np.concatenate([xy, np.minimum(xy + wh, 1.0)], -1).astype(np.float32)
+    scores = rng.random((2, n), dtype=np.float32)
+    cls = rng.integers(0, 5, (2, n)).astype(np.int32)
+    # image 0: everything in one class, many exact score ties, zero-area boxes (NaN IoU, hazard 3)
+    cls[0] = 3
+    scores[0, ::3] = 0.5
+    boxes[0, 10:40, 2:] = boxes[0, 10:40, :2]
+    boxes[0, 50:60] = boxes[0, 50]                      # identical boxes
+    # image 1: nothing passes the threshold
+    scores[1] = 1e-6
+    _check_nms(lib, G, boxes, scores, cls, 5, 0.001, 0.5, False)
+    _check_nms(lib, G, boxes, scores, cls, 5, 0.001, 0.5, True)
+    _check_nms(lib, G, boxes[:1, :1], scores[:1, :1], cls[:1, :1], 5, 0.001, 0.5, False)   # single box
+
+
+def test_nms_large_segment_and_idempotence(lib, G):
+    """BASELINE-size property checks: 608^2 anchor count (global-memory sort path), one giant
+    class; NMS of the kept set keeps everything (idempotence)."""
+    rng = np.random.default_rng(1)
+    n = 22743
+    xy = rng.random((1, n, 2), dtype=np.float32) * 0.9
+    wh = rng.random((1, n, 2), dtype=np.float32) * 0.1 + 0.01
+    boxes = np.concatenate([xy, np.minimum(xy + wh, 1.0)], -1).astype(np.float32)
+    scores = rng.random((1, n), dtype=np.float32)
+    cls = np.zeros((1, n), dtype=np.int32)
+    kept, counts, ob, os_, oc = G.run_nms(lib, boxes, scores, cls, 80, 0.001, 0.5, False)
+    _, _, _, idx = O.postprocess_flat(boxes[0], scores[0], cls[0].astype(np.int64), 80, 0.001, 0.5)
+    np.testing.assert_array_equal(kept[0], idx)
+    k = counts[0]
+    kept2, counts2, *_ = G.run_nms(lib, ob[:, :k], os_[:, :k], oc[:, :k], 80, 0.001, 0.5, False)
+    assert counts2[0] == k and np.array_equal(kept2[0], np.arange(k))

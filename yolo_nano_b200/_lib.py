@@ -60,6 +60,10 @@ SIGNATURES = {
     "ynb_read_tap": (C.c_int, [_p, _s, _i32, _p, _p]),
     "ynb_tap_shape": (C.c_int, [_p, _s, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "ynb_launch_count": (_i64, [_p]),
+    "ynb_set_profiling": (C.c_int, [_p, _i32]),
+    "ynb_profile_count": (_i32, [_p]),
+    "ynb_profile_entry": (C.c_int, [_p, _i32, C.POINTER(_s), C.POINTER(_s), C.POINTER(_f),
+                                    C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ynb_dwconv3x3": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _p, _p,
                                 _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "ynb_pwconv": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _p, _p,

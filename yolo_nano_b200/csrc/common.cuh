@@ -1,0 +1,46 @@
+// Shared helpers for the sm_100a kernels of the YOLO-Nano forward path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <limits.h>
+
+#include "yolonano_b200.h"
+
+namespace ynb {
+
+constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
+
+// ---- activation epilogues (utils/modules.py:14, backbone/shufflenetv2.py:48) -----------
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == YNB_ACT_RELU) return fmaxf(v, 0.0f);
+  if (act == YNB_ACT_LEAKY) return v > 0.0f ? v : 0.1f * v;   // LeakyReLU(0.1)
+  return v;
+}
+
+// A view of an NHWC activation: `ld` floats between pixels, channels [off, off+c) used.
+// Stage-2 tensors (116 = 2 x 58 channels) are stored as [58 | 2 zero pads | 58 | 2 zero
+// pads] so that both halves start 16-byte aligned (TMA / float4 need it): logical
+// channel j lives in slot j + (j >= gap_at ? gap : 0).
+struct ChanMap {
+  int gap_at;   // INT_MAX when the layout is dense
+  int gap;
+  __host__ __device__ __forceinline__ int slot(int j) const { return j + (j >= gap_at ? gap : 0); }
+};
+__host__ __device__ inline ChanMap dense_map() { return ChanMap{INT_MAX, 0}; }
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+inline int64_t round_up64(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// Launch bookkeeping: every kernel launch of the library goes through LAUNCH so that
+// ynb_launch_count() is a true count.
+struct LaunchCounter {
+  int64_t n = 0;
+};
+extern thread_local LaunchCounter* g_counter;   // set by the engine around a forward
+
+#define YNB_COUNT_LAUNCH()                  \
+  do {                                      \
+    if (::ynb::g_counter) ::ynb::g_counter->n++; \
+  } while (0)
+
+}  // namespace ynb

@@ -1,0 +1,403 @@
+// Decode of the raw head outputs and batched per-image / per-class greedy NMS.
+// Replaces models/yolo_nano.py:303-330 (re-layout), :120-156 (box decode), :362-367
+// (sigmoid / softmax / clamp), :245-279 (postprocess) and :159-242 (nms, diou_nms), which
+// the reference runs as ~15 ATen kernels, two D2H copies and Python/NumPy loops.
+//
+// Exactness contract: every IoU expression below is evaluated in float32 in
+// the reference's operand order with IEEE add/mul/div/sqrt (the intrinsics stop the
+// compiler from contracting into FMA), so for identical candidate boxes the keep-set is
+// bit-identical to the NumPy loop.  Visiting order inside a class: score descending, equal
+// scores by ascending anchor index (NumPy's argsort is unstable there).
+#pragma once
+#include "common.cuh"
+
+namespace ynb {
+
+// =====================================================================================
+// decode: one thread per (image, cell, anchor)
+// raw: NHWC [B, G*G, ld], channel map of models/yolo_nano.py:312-318:
+//   ch a            objectness of anchor a
+//   ch A + a*C + c  class c of anchor a
+//   ch A(1+C)+4a+k  t_x, t_y, t_w, t_h of anchor a
+// =====================================================================================
+struct DecodeParams {
+  const float* raw;
+  int ld;
+  float* boxes;    // [B,N,4]
+  float* scores;   // [B,N]
+  int32_t* cls;    // [B,N]
+  int batch, G, A, C;
+  float stride, input_size;
+  float anchor_w[4], anchor_h[4];
+  int64_t N, level_off;
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void __launch_bounds__(128)
+decode_level_kernel(DecodeParams p) {
+  const int64_t total = (int64_t)p.batch * p.G * p.G * p.A;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int a = (int)(i % p.A);
+  const int64_t cell = i / p.A;                 // b*G*G + y*G + x
+  const int gx = (int)(cell % p.G);
+  const int gy = (int)((cell / p.G) % p.G);
+  const int b = (int)(cell / ((int64_t)p.G * p.G));
+  const float* r = p.raw + cell * p.ld;
+
+  const float obj = sigmoidf_(__ldg(r + a));
+  // softmax over classes (torch.softmax, dim = classes) times objectness; argmax over the
+  // PRODUCTS with first-max-wins, as np.argmax does on all_class (models/yolo_nano.py:253)
+  const float* cl = r + p.A + a * p.C;
+  float mx = -INFINITY;
+  for (int c = 0; c < p.C; ++c) mx = fmaxf(mx, __ldg(cl + c));
+  float sum = 0.0f;
+  for (int c = 0; c < p.C; ++c) sum += expf(__ldg(cl + c) - mx);
+  float best = -1.0f;
+  int best_c = 0;
+  for (int c = 0; c < p.C; ++c) {
+    float pr = __fmul_rn(__fdiv_rn(expf(__ldg(cl + c) - mx), sum), obj);
+    if (pr > best) { best = pr; best_c = c; }
+  }
+  // box (models/yolo_nano.py:129-134, 150-154, 366)
+  const float* t = r + p.A * (1 + p.C) + 4 * a;
+  float tx = __ldg(t), tyv = __ldg(t + 1), tw = __ldg(t + 2), th = __ldg(t + 3);
+  float cx = __fmul_rn(__fadd_rn(sigmoidf_(tx), (float)gx), p.stride);
+  float cy = __fmul_rn(__fadd_rn(sigmoidf_(tyv), (float)gy), p.stride);
+  float w = __fmul_rn(expf(tw), p.anchor_w[a]);
+  float h = __fmul_rn(expf(th), p.anchor_h[a]);
+  float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
+  float x1 = __fdiv_rn(__fsub_rn(cx, hw), p.input_size);
+  float y1 = __fdiv_rn(__fsub_rn(cy, hh), p.input_size);
+  float x2 = __fdiv_rn(__fadd_rn(cx, hw), p.input_size);
+  float y2 = __fdiv_rn(__fadd_rn(cy, hh), p.input_size);
+  float4 box = make_float4(fminf(fmaxf(x1, 0.f), 1.f), fminf(fmaxf(y1, 0.f), 1.f),
+                           fminf(fmaxf(x2, 0.f), 1.f), fminf(fmaxf(y2, 0.f), 1.f));
+  const int64_t n = p.level_off + ((int64_t)gy * p.G + gx) * p.A + a;
+  const int64_t o = (int64_t)b * p.N + n;
+  reinterpret_cast<float4*>(p.boxes)[o] = box;
+  p.scores[o] = best;
+  p.cls[o] = best_c;
+}
+
+inline cudaError_t launch_decode_level(const DecodeParams& p, cudaStream_t st) {
+  int64_t total = (int64_t)p.batch * p.G * p.G * p.A;
+  if (total <= 0) return cudaSuccess;
+  decode_level_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(p);
+  YNB_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+// =====================================================================================
+// NMS stage 1: sort keys.  key = class(8) | ~score_bits(32) | anchor(16): ascending key
+// order = class ascending, score descending, anchor ascending.  Below-threshold anchors
+// get the all-ones key and sink to the end (models/yolo_nano.py:258-262: score >= thresh).
+// =====================================================================================
+constexpr uint64_t kInvalidKey = ~0ull;
+
+__device__ __forceinline__ uint64_t make_key(int cls, float score, int idx) {
+  return ((uint64_t)(uint32_t)cls << 48) | ((uint64_t)(~__float_as_uint(score)) << 16) | (uint64_t)(uint32_t)idx;
+}
+__device__ __forceinline__ int key_idx(uint64_t k) { return (int)(k & 0xFFFFull); }
+__device__ __forceinline__ int key_cls(uint64_t k) { return (int)(k >> 48); }
+
+__global__ void __launch_bounds__(256)
+nms_keys_kernel(const float* __restrict__ scores, const int32_t* __restrict__ cls,
+                uint64_t* __restrict__ keys, uint8_t* __restrict__ keep, int64_t N, int Npad,
+                float conf_thresh) {
+  const int b = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Npad; i += gridDim.x * blockDim.x) {
+    uint64_t k = kInvalidKey;
+    if (i < N) {
+      float s = scores[(int64_t)b * N + i];
+      if (s >= conf_thresh) k = make_key(cls[(int64_t)b * N + i], s, i);   // NaN fails, as in NumPy
+      keep[(int64_t)b * N + i] = 0;
+    }
+    keys[(int64_t)b * Npad + i] = k;
+  }
+}
+
+// One CTA per image, bitonic network over Npad (power of two) keys.  Keys are unique
+// (anchor index in the low bits), so the network's instability is irrelevant.
+template <bool IN_SMEM>
+__global__ void __launch_bounds__(1024)
+nms_sort_kernel(uint64_t* __restrict__ keys_g, int Npad) {
+  extern __shared__ uint64_t s_keys[];
+  uint64_t* g = keys_g + (int64_t)blockIdx.x * Npad;
+  uint64_t* k = IN_SMEM ? s_keys : g;
+  const int tid = threadIdx.x;
+  if (IN_SMEM) {
+    for (int i = tid; i < Npad; i += 1024) s_keys[i] = g[i];
+    __syncthreads();
+  }
+  for (int size = 2; size <= Npad; size <<= 1) {
+    for (int j = size >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (Npad >> 1); t += 1024) {
+        int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // index with bit j clear
+        int hi = lo | j;
+        bool up = (lo & size) == 0;
+        uint64_t a = k[lo], c = k[hi];
+        if ((a > c) == up) { k[lo] = c; k[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  if (IN_SMEM) {
+    for (int i = tid; i < Npad; i += 1024) g[i] = s_keys[i];
+  }
+}
+
+// =====================================================================================
+// NMS stage 2: one CTA per (image, class) segment of the sorted keys; greedy suppression
+// in chunks of 64 candidates:
+//   (1) 64x64 suppression bitmask inside the chunk (warp-cooperative),
+//   (2) one thread resolves the chunk serially against the mask (64-bit ops),
+//   (3) all threads test every later candidate against the boxes kept in this chunk.
+// Total pair tests = kept x later, the same work as the reference loop, but parallel.
+// =====================================================================================
+struct IouOps {
+  float thr;
+  bool diou;
+};
+
+__device__ __forceinline__ float box_area(float4 b) {
+  return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));   // models/yolo_nano.py:166
+}
+
+// true when kept box `a` suppresses candidate `b`:  NOT (ovr <= thr)   (:185, NaN suppresses)
+__device__ __forceinline__ bool suppresses(float4 a, float area_a, float4 b, float area_b, IouOps op) {
+  float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+  float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+  float w = fmaxf(1e-28f, __fsub_rn(xx2, xx1));
+  float h = fmaxf(1e-28f, __fsub_rn(yy2, yy1));
+  float inter = __fmul_rn(w, h);
+  float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  if (op.diou) {   // models/yolo_nano.py:216-237
+    float cw = __fsub_rn(fmaxf(fmaxf(a.x, a.z), fmaxf(b.x, b.z)), fminf(fminf(a.x, a.z), fminf(b.x, b.z)));
+    float ch = __fsub_rn(fmaxf(fmaxf(a.y, a.w), fmaxf(b.y, b.w)), fminf(fminf(a.y, a.w), fminf(b.y, b.w)));
+    float C = __fsqrt_rn(__fadd_rn(__fmul_rn(cw, cw), __fmul_rn(ch, ch)));
+    float p1x = __fmul_rn(__fadd_rn(a.x, a.z), 0.5f), p1y = __fmul_rn(__fadd_rn(a.y, a.w), 0.5f);
+    float p2x = __fmul_rn(__fadd_rn(b.x, b.z), 0.5f), p2y = __fmul_rn(__fadd_rn(b.y, b.w), 0.5f);
+    float dx = __fsub_rn(p2x, p1x), dy = __fsub_rn(p2y, p1y);
+    float D = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    float lens = __fdiv_rn(__fmul_rn(D, D), __fadd_rn(__fmul_rn(C, C), 1e-20f));
+    ovr = __fsub_rn(ovr, lens);
+  }
+  return !(ovr <= op.thr);
+}
+
+constexpr int kNmsChunk = 64;
+constexpr int kNmsThreads = 256;
+constexpr int kNmsMaxWords = 2048;   // 65536 candidates per segment
+
+__device__ __forceinline__ int lower_bound_key(const uint64_t* k, int n, uint64_t v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (k[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kNmsThreads)
+nms_segment_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ boxes,
+                   float4* sbox_scratch, uint8_t* __restrict__ keep, int64_t N, int Npad, IouOps op) {
+  __shared__ uint32_t s_removed[kNmsMaxWords];
+  __shared__ float4 s_cbox[kNmsChunk];
+  __shared__ float s_carea[kNmsChunk];
+  __shared__ unsigned long long s_mask[kNmsChunk];
+  __shared__ int s_kept[kNmsChunk];
+  __shared__ int s_nkept;
+  __shared__ int s_range[2];
+
+  const int b = blockIdx.y, c = blockIdx.x, tid = threadIdx.x;
+  const uint64_t* k = keys + (int64_t)b * Npad;
+  if (tid < 2) s_range[tid] = lower_bound_key(k, Npad, (uint64_t)(c + tid) << 48);
+  __syncthreads();
+  const int s0 = s_range[0], n = s_range[1] - s_range[0];
+  if (n <= 0) return;
+  const float4* bx = reinterpret_cast<const float4*>(boxes) + (int64_t)b * N;
+  float4* sb = sbox_scratch + (int64_t)b * Npad + s0;
+  uint8_t* kp = keep + (int64_t)b * N;
+
+  // gather the segment's boxes in visiting order (coalesced from here on)
+  for (int j = tid; j < n; j += kNmsThreads) sb[j] = bx[key_idx(k[s0 + j])];
+  for (int j = tid; j < (n + 31) / 32; j += kNmsThreads) s_removed[j] = 0;
+  __syncthreads();
+
+  for (int c0 = 0; c0 < n; c0 += kNmsChunk) {
+    const int cn = min(kNmsChunk, n - c0);
+    if (tid < kNmsChunk) {
+      float4 v = tid < cn ? sb[c0 + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
+      s_cbox[tid] = v;
+      s_carea[tid] = box_area(v);
+      s_mask[tid] = 0ull;
+    }
+    __syncthreads();
+    // (1) in-chunk mask: thread -> (row, 16-column quarter)
+    {
+      int row = tid >> 2, q = tid & 3;
+      unsigned long long bits = 0ull;
+      if (row < cn) {
+        float4 a = s_cbox[row];
+        float aa = s_carea[row];
+        for (int j = q * 16; j < q * 16 + 16; ++j)
+          if (j > row && j < cn && suppresses(a, aa, s_cbox[j], s_carea[j], op)) bits |= 1ull << j;
+      }
+      // combine the four quarters of a row (adjacent lanes)
+      bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+      bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+      if (q == 0 && row < cn) s_mask[row] = bits;
+    }
+    __syncthreads();
+    // (2) serial resolve of the chunk
+    if (tid == 0) {
+      unsigned long long rem = 0ull;
+      for (int j = 0; j < cn; ++j)
+        if ((s_removed[(c0 + j) >> 5] >> ((c0 + j) & 31)) & 1u) rem |= 1ull << j;
+      int nk = 0;
+      for (int j = 0; j < cn; ++j) {
+        if (!((rem >> j) & 1ull)) {
+          s_kept[nk++] = j;
+          rem |= s_mask[j];
+        }
+      }
+      s_nkept = nk;
+    }
+    __syncthreads();
+    const int nk = s_nkept;
+    if (tid < nk) kp[key_idx(k[s0 + c0 + s_kept[tid]])] = 1;
+    // (3) kept boxes of this chunk against all later candidates
+    for (int j = c0 + kNmsChunk + tid; j < n; j += kNmsThreads) {
+      if ((s_removed[j >> 5] >> (j & 31)) & 1u) continue;
+      float4 v = sb[j];
+      float va = box_area(v);
+      for (int q = 0; q < nk; ++q) {
+        int r = s_kept[q];
+        if (suppresses(s_cbox[r], s_carea[r], v, va, op)) {
+          atomicOr(&s_removed[j >> 5], 1u << (j & 31));
+          break;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// =====================================================================================
+// NMS stage 3: per image, compact kept anchors in ascending anchor order
+// (models/yolo_nano.py:274-277).
+// =====================================================================================
+__global__ void __launch_bounds__(1024)
+nms_compact_kernel(const uint8_t* __restrict__ keep, const float* __restrict__ boxes,
+                   const float* __restrict__ scores, const int32_t* __restrict__ cls,
+                   float* __restrict__ out_boxes, float* __restrict__ out_scores,
+                   int32_t* __restrict__ out_cls, int32_t* __restrict__ out_counts, int64_t N) {
+  __shared__ int s_warp[32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int per = (int)((N + 1023) / 1024);
+  const int beg = min((int)N, tid * per), end = min((int)N, beg + per);
+  const uint8_t* kp = keep + (int64_t)b * N;
+  int cnt = 0;
+  for (int i = beg; i < end; ++i) cnt += kp[i];
+  // block exclusive scan
+  int incl = cnt;
+  for (int d = 1; d < 32; d <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if ((tid & 31) >= d) incl += v;
+  }
+  if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    int w = s_warp[tid], wi = w;
+    for (int d = 1; d < 32; d <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, wi, d);
+      if (tid >= d) wi += v;
+    }
+    s_warp[tid] = wi - w;   // exclusive prefix of warp totals
+    if (tid == 31) out_counts[b] = wi;
+  }
+  __syncthreads();
+  int pos = s_warp[tid >> 5] + incl - cnt;
+  const float4* bx = reinterpret_cast<const float4*>(boxes) + (int64_t)b * N;
+  float4* ob = reinterpret_cast<float4*>(out_boxes) + (int64_t)b * N;
+  for (int i = beg; i < end; ++i) {
+    if (kp[i]) {
+      ob[pos] = bx[i];
+      out_scores[(int64_t)b * N + pos] = scores[(int64_t)b * N + i];
+      out_cls[(int64_t)b * N + pos] = cls[(int64_t)b * N + i];
+      ++pos;
+    }
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------
+inline int nms_npad(int64_t n) {
+  int p = 64;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+struct NmsWorkspace {
+  uint64_t* keys;     // [B][Npad]
+  float4* sbox;       // [B][Npad]
+  uint8_t* keep;      // [B][N]
+};
+inline int64_t nms_workspace_bytes(int batch, int64_t n) {
+  int64_t npad = nms_npad(n);
+  return (int64_t)batch * npad * 8 + (int64_t)batch * npad * 16 + round_up64((int64_t)batch * n, 256) + 512;
+}
+inline NmsWorkspace nms_carve(void* ws, int batch, int64_t n) {
+  int64_t npad = nms_npad(n);
+  char* p = reinterpret_cast<char*>(round_up64((int64_t)(uintptr_t)ws, 256));
+  NmsWorkspace w;
+  w.sbox = reinterpret_cast<float4*>(p); p += (int64_t)batch * npad * 16;
+  w.keys = reinterpret_cast<uint64_t*>(p); p += (int64_t)batch * npad * 8;
+  w.keep = reinterpret_cast<uint8_t*>(p);
+  return w;
+}
+
+constexpr int kSortSmemLimit = 200 * 1024;
+
+inline cudaError_t launch_nms(const float* boxes, const float* scores, const int32_t* cls, int batch,
+                              int64_t N, int num_classes, float conf, float thr, int diou,
+                              float* out_boxes, float* out_scores, int32_t* out_cls,
+                              int32_t* out_counts, uint8_t* keep_out, NmsWorkspace w, cudaStream_t st) {
+  const int Npad = nms_npad(N);
+  if (N > 65536 || num_classes > 255) return cudaErrorInvalidValue;
+  uint8_t* keep = keep_out ? keep_out : w.keep;
+  {
+    dim3 grid((Npad + 255) / 256, batch);
+    nms_keys_kernel<<<grid, 256, 0, st>>>(scores, cls, w.keys, keep, N, Npad, conf);
+    YNB_COUNT_LAUNCH();
+  }
+  {
+    size_t smem = (size_t)Npad * 8;
+    if (smem <= (size_t)kSortSmemLimit) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(nms_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kSortSmemLimit);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+      }
+      nms_sort_kernel<true><<<batch, 1024, smem, st>>>(w.keys, Npad);
+    } else {
+      nms_sort_kernel<false><<<batch, 1024, 0, st>>>(w.keys, Npad);
+    }
+    YNB_COUNT_LAUNCH();
+  }
+  {
+    dim3 grid(num_classes, batch);
+    IouOps op{thr, diou != 0};
+    nms_segment_kernel<<<grid, kNmsThreads, 0, st>>>(w.keys, boxes, w.sbox, keep, N, Npad, op);
+    YNB_COUNT_LAUNCH();
+  }
+  nms_compact_kernel<<<batch, 1024, 0, st>>>(keep, boxes, scores, cls, out_boxes, out_scores, out_cls,
+                                              out_counts, N);
+  YNB_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+}  // namespace ynb

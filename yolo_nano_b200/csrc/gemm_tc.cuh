@@ -1,0 +1,466 @@
+// tcgen05 tensor-core contraction for the dense convs of the path (pointwise 1x1 and the
+// 3x3 "smooth" convs as implicit GEMM), fed by TMA, accumulating in TMEM.
+//
+//   D[m, n] = act(bias[n] + sum_k A[m, k] * W[n, k])       m: NHWC pixels, k: channels
+//
+// Tile: 128 pixel rows x Npad (<= 256) output channels; K consumed in chunks of 32 floats
+// (one 128-byte swizzle row).  A persistent CTA walks its tiles; five roles:
+//   warp 0      TMA producer      A chunk (+ W chunk when W is streamed) -> smem stage
+//   warp 1      MMA issuer        tcgen05.mma kind::tf32, one elected lane; owns TMEM alloc
+//   warps 2-5   splitters         fp32 parity mode only: A -> (A_hi, A_lo) in smem
+//   warps 6-9   epilogue          TMEM -> regs -> bias/act -> global (plain / interleaved)
+//
+// fp32 parity mode (YNB_GEMM_TC_3XTF32): a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi with
+// x_hi = x & 0xffffe000 (exact tf32), x_lo = tf32(x - x_hi): three MMAs per K step, fp32
+// accumulation in TMEM, relative error ~2^-21 per product (vs 2^-11 for one tf32 pass).
+// W_hi / W_lo are split once at weight-pack time; A is split in shared memory by the
+// splitter warps, position-wise on the swizzled bytes (no layout knowledge needed).
+//
+// 3x3 mode: the nine taps are nine TMA boxes of the same 4-D tensor map shifted by
+// (dx-1, dy-1); out-of-bounds elements are zero-filled by TMA = the conv's zero padding.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace ynb {
+
+constexpr int kTcThreads = 320;
+constexpr int kTcBM = 128;
+constexpr int kTcBK = 32;                       // floats per K chunk = 128 bytes
+constexpr int kTcAStageBytes = kTcBM * 128;     // 16 KB
+constexpr int kTcMaxStages = 8;
+constexpr int kTcSmemBudget = 220 * 1024;
+
+struct TcGemmParams {
+  int num_steps;          // K chunks per tile (pointwise: ceil(K/32); 3x3: 9 * C/32)
+  int chunks_per_tap;     // 3x3: C/32; pointwise: num_steps
+  int is3x3;
+  int mode;               // YNB_GEMM_TC_3XTF32 | YNB_GEMM_TC_TF32
+  int num_stages;
+  int w_resident;
+  int64_t M;              // pointwise: rows
+  int64_t num_tiles;
+  int H, W, TH, TW, tiles_x, tiles_y;   // 3x3 spatial tiling
+  int N, Npad;
+  uint32_t tmem_cols;     // power of two >= 2*Npad
+  uint32_t a_box_bytes;   // bytes one A TMA box delivers
+  // epilogue
+  float* out;
+  int out_ld, out_off, out_step;
+  ChanMap omap;
+  const float* bias;
+  int act;
+  const float* pass;      // pass-through half for the shuffle interleave, or nullptr
+  int pass_ld;
+  int* err_flag;
+};
+
+struct TcSmemLayout {
+  uint32_t stage_bytes;    // A | A_lo | (W_hi | W_lo when streamed)
+  uint32_t w_chunk_bytes;  // Npad * 128
+  uint32_t w_res_off;      // offset of the resident W region
+  uint32_t bar_off;
+  uint32_t total;
+};
+
+inline TcSmemLayout tc_smem_layout(int Npad, int num_steps, int num_stages, bool w_resident, bool split) {
+  TcSmemLayout L;
+  L.w_chunk_bytes = (uint32_t)Npad * 128;
+  uint32_t a_bytes = kTcAStageBytes * (split ? 2 : 1);
+  uint32_t w_bytes = w_resident ? 0 : L.w_chunk_bytes * (split ? 2 : 1);
+  L.stage_bytes = a_bytes + w_bytes;                      // all multiples of 1024
+  L.w_res_off = L.stage_bytes * num_stages;
+  uint32_t w_res = w_resident ? L.w_chunk_bytes * (split ? 2 : 1) * num_steps : 0;
+  L.bar_off = L.w_res_off + w_res;
+  L.total = L.bar_off + 256 + 1024;                       // barriers + slack for 1024-B alignment
+  return L;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWhi,
+               const __grid_constant__ CUtensorMap tmWlo, const TcGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+
+  const bool split = p.mode == YNB_GEMM_TC_3XTF32;
+  const uint32_t w_chunk_bytes = (uint32_t)p.Npad * 128;
+  const uint32_t a_bytes = kTcAStageBytes * (split ? 2 : 1);
+  const uint32_t stage_bytes = a_bytes + (p.w_resident ? 0 : w_chunk_bytes * (split ? 2 : 1));
+  const uint32_t w_res_off = stage_bytes * p.num_stages;
+  const uint32_t w_res_bytes = p.w_resident ? w_chunk_bytes * (split ? 2 : 1) * p.num_steps : 0;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + w_res_off + w_res_bytes);
+  uint64_t* full = bars;                         // [kTcMaxStages]
+  uint64_t* ready = bars + kTcMaxStages;         // [kTcMaxStages]
+  uint64_t* empty = bars + 2 * kTcMaxStages;     // [kTcMaxStages]
+  uint64_t* tmem_full = bars + 3 * kTcMaxStages;     // [2]
+  uint64_t* tmem_empty = bars + 3 * kTcMaxStages + 2; // [2]
+  uint64_t* w_full = bars + 3 * kTcMaxStages + 4;     // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * kTcMaxStages + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmWhi);
+    if (split) ptx::prefetch_tmap(&tmWlo);
+    for (int s = 0; s < p.num_stages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&ready[s], 128);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], 128);
+    }
+    ptx::mbar_init(w_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr, p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  auto stage_a = [&](int s) { return smem + (size_t)s * stage_bytes; };
+  auto stage_alo = [&](int s) { return smem + (size_t)s * stage_bytes + kTcAStageBytes; };
+  auto w_hi_ptr = [&](int s, int step) {
+    return p.w_resident ? smem + w_res_off + (size_t)step * w_chunk_bytes * (split ? 2 : 1)
+                        : smem + (size_t)s * stage_bytes + a_bytes;
+  };
+  auto w_lo_ptr = [&](int s, int step) { return w_hi_ptr(s, step) + w_chunk_bytes; };
+
+  const uint32_t step_tx = p.a_box_bytes + (p.w_resident ? 0 : w_chunk_bytes * (split ? 2 : 1));
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      if (p.w_resident) {
+        ptx::mbar_arrive_expect_tx(w_full, w_res_bytes);
+        for (int st = 0; st < p.num_steps; ++st) {
+          ptx::tma_load_2d(w_hi_ptr(0, st), &tmWhi, w_full, st * kTcBK, 0);
+          if (split) ptx::tma_load_2d(w_lo_ptr(0, st), &tmWlo, w_full, st * kTcBK, 0);
+        }
+      }
+      int s = 0;
+      uint32_t ph = 0;
+      bool ok = true;
+      for (int64_t tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
+        int b = 0, y0 = 0, x0 = 0;
+        if (p.is3x3) {
+          int per_img = p.tiles_x * p.tiles_y;
+          b = (int)(tile / per_img);
+          int r = (int)(tile - (int64_t)b * per_img);
+          y0 = (r / p.tiles_x) * p.TH;
+          x0 = (r % p.tiles_x) * p.TW;
+        }
+        for (int st = 0; st < p.num_steps; ++st) {
+          ok = ptx::mbar_wait(&empty[s], ph ^ 1, p.err_flag, 1);
+          if (!ok) break;
+          ptx::mbar_arrive_expect_tx(&full[s], step_tx);
+          if (p.is3x3) {
+            int tap = st / p.chunks_per_tap, kc = st - tap * p.chunks_per_tap;
+            int dy = tap / 3, dx = tap - dy * 3;
+            ptx::tma_load_4d(stage_a(s), &tmA, &full[s], kc * kTcBK, x0 + dx - 1, y0 + dy - 1, b);
+          } else {
+            ptx::tma_load_2d(stage_a(s), &tmA, &full[s], st * kTcBK, (int)(tile * kTcBM));
+          }
+          if (!p.w_resident) {
+            ptx::tma_load_2d(w_hi_ptr(s, st), &tmWhi, &full[s], st * kTcBK, 0);
+            if (split) ptx::tma_load_2d(w_lo_ptr(s, st), &tmWlo, &full[s], st * kTcBK, 0);
+          }
+          if (++s == p.num_stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc(2 /*tf32*/, kTcBM, p.Npad);
+      int s = 0;
+      uint32_t ph = 0;
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      bool ok = true;
+      if (p.w_resident) ok = ptx::mbar_wait(w_full, 0, p.err_flag, 2);
+      for (int64_t tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
+        ok = ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1, p.err_flag, 3);
+        if (!ok) break;
+        ptx::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Npad);
+        for (int st = 0; st < p.num_steps; ++st) {
+          ok = ptx::mbar_wait(split ? &ready[s] : &full[s], ph, p.err_flag, 4);
+          if (!ok) break;
+          ptx::tc_fence_after_sync();
+          const uint32_t a_hi = ptx::smem_u32(stage_a(s));
+          const uint32_t a_lo = ptx::smem_u32(stage_alo(s));
+          const uint32_t b_hi = ptx::smem_u32(w_hi_ptr(s, st));
+          const uint32_t b_lo = ptx::smem_u32(w_lo_ptr(s, st));
+#pragma unroll
+          for (int k = 0; k < kTcBK / 8; ++k) {
+            const uint32_t ko = k * 32;   // 8 tf32 = 32 bytes inside the 128-byte swizzled row
+            const uint64_t da = ptx::make_sw128_kmajor_desc(a_hi + ko);
+            const uint64_t db = ptx::make_sw128_kmajor_desc(b_hi + ko);
+            if (split) {
+              // small terms first, then the main product
+              ptx::mma_tf32_ss(d_tmem, ptx::make_sw128_kmajor_desc(a_lo + ko), db, idesc, (st | k) != 0);
+              ptx::mma_tf32_ss(d_tmem, da, ptx::make_sw128_kmajor_desc(b_lo + ko), idesc, 1);
+              ptx::mma_tf32_ss(d_tmem, da, db, idesc, 1);
+            } else {
+              ptx::mma_tf32_ss(d_tmem, da, db, idesc, (st | k) != 0);
+            }
+          }
+          ptx::mma_commit(&empty[s]);                       // frees the smem stage when the MMAs retire
+          if (st == p.num_steps - 1) ptx::mma_commit(&tmem_full[acc]);
+          if (++s == p.num_stages) { s = 0; ph ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      }
+    }
+  } else if (warp < 6) {
+    // ================= splitters (fp32 parity mode) =================
+    if (split) {
+      const int t = threadIdx.x - 64;   // 0..127
+      int s = 0;
+      uint32_t ph = 0;
+      bool ok = true;
+      for (int64_t tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
+        for (int st = 0; st < p.num_steps; ++st) {
+          ok = ptx::mbar_wait(&full[s], ph, p.err_flag, 5);
+          if (!ok) break;
+          uint4* a = reinterpret_cast<uint4*>(stage_a(s));
+          uint4* lo = reinterpret_cast<uint4*>(stage_alo(s));
+#pragma unroll
+          for (int i = 0; i < kTcAStageBytes / 16 / 128; ++i) {
+            uint4 v = a[t + i * 128];
+            uint4 h, l;
+            h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
+            l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)) & 0xffffe000u;
+            l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)) & 0xffffe000u;
+            l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) & 0xffffe000u;
+            l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) & 0xffffe000u;
+            a[t + i * 128] = h;
+            lo[t + i * 128] = l;
+          }
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive(&ready[s]);
+          if (++s == p.num_stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ================= epilogue =================
+    const int q = warp & 3;                         // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;                  // tile row owned by this thread
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    bool ok = true;
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
+      // row -> output pixel
+      int64_t m;
+      bool valid;
+      if (p.is3x3) {
+        int per_img = p.tiles_x * p.tiles_y;
+        int b = (int)(tile / per_img);
+        int r = (int)(tile - (int64_t)b * per_img);
+        int y = (r / p.tiles_x) * p.TH + row / p.TW;
+        int x = (r % p.tiles_x) * p.TW + row % p.TW;
+        valid = row < p.TH * p.TW && y < p.H && x < p.W;
+        m = ((int64_t)b * p.H + y) * p.W + x;
+      } else {
+        m = tile * kTcBM + row;
+        valid = m < p.M;
+      }
+      ok = ptx::mbar_wait(&tmem_full[acc], acc_ph, p.err_flag, 6);
+      if (!ok) break;
+      ptx::tc_fence_after_sync();
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Npad);
+      float* orow = p.out + m * p.out_ld;
+      const float* prow = p.pass ? p.pass + m * p.pass_ld : nullptr;
+      for (int c0 = 0; c0 < p.Npad; c0 += 16) {
+        uint32_t r[16];
+        ptx::tmem_ld_32x16(t_base + c0, r);
+        ptx::tmem_ld_wait();
+        if (c0 + 16 >= p.Npad) {   // last block read: hand the accumulator back to the MMA warp
+          ptx::tc_fence_before_sync();
+          ptx::mbar_arrive(&tmem_empty[acc]);
+        }
+        if (!valid) continue;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          int n = c0 + j;
+          v[j] = n < p.N ? apply_act(__uint_as_float(r[j]) + __ldg(p.bias + n), p.act) : 0.0f;
+        }
+        if (prow != nullptr) {
+          // channel shuffle as a store permutation: slot(2n) <- pass-through, slot(2n+1) <- branch
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            int n = c0 + j;
+            if (n >= p.N) break;
+            float4 x1 = *reinterpret_cast<const float4*>(prow + n);
+            const float xs[4] = {x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (n + e < p.N)
+                *reinterpret_cast<float2*>(orow + p.omap.slot(2 * (n + e))) = make_float2(xs[e], v[j + e]);
+          }
+        } else if (p.out_step == 1 && p.omap.gap == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            int n = c0 + j;
+            if (n + 3 < p.N) {
+              *reinterpret_cast<float4*>(orow + p.out_off + n) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (n + e < p.N) orow[p.out_off + n + e] = v[j + e];
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < p.N) orow[p.omap.slot(p.out_off + (c0 + j) * p.out_step)] = v[j];
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// rank-2 map over a K-major fp32 matrix: dim0 = K (contiguous), dim1 = rows.
+inline bool make_tmap_2d(CUtensorMap* m, const float* base, uint64_t k, uint64_t rows, uint64_t row_stride_floats,
+                         uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {k, rows};
+  cuuint64_t strides[1] = {row_stride_floats * 4};
+  cuuint32_t box[2] = {(cuuint32_t)kTcBK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// rank-4 map over an NHWC activation [B][H][W][ld] exposing C channels: (c, x, y, b).
+inline bool make_tmap_nhwc(CUtensorMap* m, const float* base, int C, int W, int H, int B, int ld, int box_w,
+                           int box_h) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)ld * 4 * W, (cuuint64_t)ld * 4 * W * H};
+  cuuint32_t box[4] = {(cuuint32_t)kTcBK, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Weights packed for the tensor-core path: [Npad][Kpad] fp32, Kpad multiple of 32, split
+// into exact-tf32 hi and lo parts.
+struct TcWeights {
+  float* hi = nullptr;
+  float* lo = nullptr;
+  int N = 0, Npad = 0, Kpad = 0;
+  CUtensorMap tm_hi, tm_lo;
+};
+
+inline void split_tf32_host(float v, float* hi, float* lo) {
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  uint32_t h = u & 0xffffe000u;
+  float hf;
+  memcpy(&hf, &h, 4);
+  float l = v - hf;
+  uint32_t lu;
+  memcpy(&lu, &l, 4);
+  lu &= 0xffffe000u;
+  memcpy(lo, &lu, 4);
+  *hi = hf;
+}
+
+// A fully described launch (tensor maps are baked at plan time).
+struct TcGemmLaunch {
+  CUtensorMap tmA;
+  const TcWeights* w = nullptr;
+  TcGemmParams p;
+  uint32_t smem = 0;
+  unsigned grid = 0;
+};
+
+// Picks stages / residency for the smem budget.  Returns false if nothing fits.
+inline bool tc_plan_smem(TcGemmLaunch& L) {
+  TcGemmParams& p = L.p;
+  const bool split = p.mode == YNB_GEMM_TC_3XTF32;
+  for (int resident = 1; resident >= 0; --resident) {
+    for (int stages = kTcMaxStages; stages >= 2; --stages) {
+      if (stages > p.num_steps * 4 && stages > 2) continue;
+      TcSmemLayout lay = tc_smem_layout(p.Npad, p.num_steps, stages, resident != 0, split);
+      if (lay.total <= (uint32_t)kTcSmemBudget && (resident == 0 || stages >= 3 || p.num_steps <= 2)) {
+        p.num_stages = stages;
+        p.w_resident = resident;
+        L.smem = lay.total;
+        return true;
+      }
+    }
+  }
+  return false;
+}
+
+inline cudaError_t launch_tc_gemm(const TcGemmLaunch& L, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kTcSmemBudget + 2048);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  tc_gemm_kernel<<<L.grid, kTcThreads, L.smem, st>>>(L.tmA, L.w->tm_hi, L.w->tm_lo, L.p);
+  YNB_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+// Spatial tile (TW x TH <= 128 pixels) for the 3x3 path that wastes the fewest MMA rows.
+inline void tc_pick_tile(int H, int W, int* TH, int* TW) {
+  double best = -1;
+  for (int tw = 4; tw <= 64 && tw <= W + 3; ++tw) {
+    int th = 128 / tw;
+    if (th < 1) continue;
+    if (th > H) th = H;
+    double eff = (double)H * W / ((double)((W + tw - 1) / tw) * ((H + th - 1) / th) * 128.0);
+    if (eff > best + 1e-9) { best = eff; *TH = th; *TW = tw; }
+  }
+}
+
+}  // namespace ynb

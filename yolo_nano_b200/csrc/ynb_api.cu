@@ -1,0 +1,1007 @@
+// C ABI of the B200-native YOLO-Nano forward path (include/yolonano_b200.h):
+// engine lifecycle, weight packing, workspace planning and the per-batch launch plan.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "yolonano_b200.h"
+
+#include "common.cuh"
+#include "decode_nms.cuh"
+#include "gemm_ffma.cuh"
+#include "gemm_tc.cuh"
+#include "kernels_basic.cuh"
+#include "topology.h"
+
+#define YNB_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace ynb {
+
+thread_local LaunchCounter* g_counter = nullptr;
+static thread_local std::string g_create_error;
+
+// Physical NHWC tensor in the workspace.
+struct Tensor {
+  float* p = nullptr;
+  int C = 0;        // logical channels
+  int ld = 0;       // floats per pixel
+  int H = 0, W = 0;
+  ChanMap map = {INT_MAX, 0};
+  size_t floats_per_image() const { return (size_t)H * W * ld; }
+};
+
+// How a conv's input channels are laid out physically (static per conv).
+struct InLayout {
+  int ktot;       // physical width read by the conv (multiple of 4)
+  ChanMap map;    // logical k -> physical slot inside the view
+};
+
+struct PackedConv {
+  bool loaded = false;
+  std::vector<float> w_host, b_host;   // reference layout [cout][cin/g][k][k], [cout]
+  float* w_dev = nullptr;              // FFMA / dw / stem layout
+  float* b_dev = nullptr;
+  int n = 0, ktot = 0;                 // GEMM dims of the packed matrix
+  TcWeights tc;                        // tensor-core layout (dense convs only)
+};
+
+// One kernel launch of the plan, with what bench.py needs for the roofline: a label, the
+// kernel family, and its ALGORITHMIC bytes / flops (unique unpadded inputs + outputs +
+// weights; DESIGN.md "algorithmic bytes").
+struct Op {
+  std::string name, kind;
+  double bytes = 0, flops = 0;
+  std::function<cudaError_t(cudaStream_t)> fn;
+};
+
+struct ProfEntry {
+  std::string name, kind;
+  double bytes, flops;
+  float ms;
+};
+
+struct Plan {
+  int batch = 0;
+  std::vector<Op> net;        // stem .. raw head outputs
+  std::vector<Op> decode;     // raw -> boxes/scores/cls (engine buffers)
+};
+
+}  // namespace ynb
+
+using namespace ynb;
+
+struct ynb_engine {
+  ynb_config cfg;
+  int S = 0;
+  std::string err;
+  std::vector<ConvSpec> table;
+  std::map<std::string, int> index;
+  std::vector<PackedConv> convs;
+  bool committed = false;
+
+  // workspace
+  char* ws = nullptr;
+  size_t ws_bytes = 0;
+  int ws_batch = 0, ws_S = 0;
+  std::map<std::string, Tensor> taps;      // name -> tensor (also used by the planner)
+  Tensor raw[3];
+  float* d_boxes = nullptr;
+  float* d_scores = nullptr;
+  int32_t* d_cls = nullptr;
+  void* d_nms_ws = nullptr;
+  int64_t nms_ws_bytes = 0;
+  // host-call staging
+  float* d_x = nullptr;
+  const float* d_x_bound = nullptr;   // input of the forward in flight
+  float* d_out_boxes = nullptr;
+  float* d_out_scores = nullptr;
+  int32_t* d_out_cls = nullptr;
+  int32_t* d_out_counts = nullptr;
+  int* d_err = nullptr;
+
+  std::map<int, std::unique_ptr<Plan>> plans;
+  std::deque<std::deque<TcGemmLaunch>> tc_store;
+  LaunchCounter counter;
+  bool profiling = false;
+  std::vector<ProfEntry> prof;
+
+  int64_t N() const {
+    int64_t n = 0;
+    for (int s : {8, 16, 32}) n += (int64_t)cfg.num_anchors * (S / s) * (S / s);
+    return n;
+  }
+};
+
+namespace {
+
+int fail(ynb_engine* e, int code, const std::string& msg) {
+  if (e) e->err = msg; else g_create_error = msg;
+  return code;
+}
+#define CUDA_TRY(e, call)                                                                 \
+  do {                                                                                    \
+    cudaError_t _st = (call);                                                             \
+    if (_st != cudaSuccess)                                                               \
+      return fail(e, YNB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_st));  \
+  } while (0)
+
+struct CounterScope {
+  explicit CounterScope(ynb_engine* e) { g_counter = &e->counter; }
+  ~CounterScope() { g_counter = nullptr; }
+};
+
+// ---- static layout knowledge -----------------------------------------------------------
+const ChanMap kGap58 = {58, 2};   // stage-2 tensors: [58 | 2 pad | 58 | 2 pad]
+
+// Input layout of conv `name` (see plan_network for the producers).
+InLayout in_layout(const ConvSpec& c) {
+  const std::string& n = c.name;
+  if (c.kind == kDense3x3) return {c.cin == 3 ? 27 : 9 * c.cin, dense_map()};
+  bool reads_c3 = n == "backbone.stage3.0.branch1.0" || n == "backbone.stage3.0.branch1.2" ||
+                  n == "backbone.stage3.0.branch2.0" || n == "conv1x1_0.convs.0";
+  if (reads_c3) return {120, kGap58};
+  return {round_up(c.cin, 4), dense_map()};
+}
+
+// ---- weight packing ----------------------------------------------------------------------
+int pack_conv(ynb_engine* e, int i) {
+  const ConvSpec& c = e->table[i];
+  PackedConv& pc = e->convs[i];
+  InLayout il = in_layout(c);
+  std::vector<float> w, b;
+  if (c.kind == kDense3x3 && c.cin == 3) {            // stem: [27][24]
+    w.assign(27 * 24, 0.f);
+    for (int co = 0; co < 24; ++co)
+      for (int ci = 0; ci < 3; ++ci)
+        for (int t = 0; t < 9; ++t) w[(ci * 9 + t) * 24 + co] = pc.w_host[(co * 3 + ci) * 9 + t];
+    b = pc.b_host;
+    pc.n = 24; pc.ktot = 27;
+  } else if (c.kind == kDw3x3) {                       // [9][C4] by physical slot
+    int c4 = il.ktot;
+    w.assign(9 * c4, 0.f);
+    b.assign(c4, 0.f);
+    for (int ch = 0; ch < c.cin; ++ch) {
+      int s = il.map.slot(ch);
+      for (int t = 0; t < 9; ++t) w[t * c4 + s] = pc.w_host[ch * 9 + t];
+      b[s] = pc.b_host[ch];
+    }
+    pc.n = c4; pc.ktot = 9;
+  } else if (c.kind == kPw1x1) {                       // [N][Ktot] by physical slot
+    w.assign((size_t)c.cout * il.ktot, 0.f);
+    for (int n = 0; n < c.cout; ++n)
+      for (int k = 0; k < c.cin; ++k) w[(size_t)n * il.ktot + il.map.slot(k)] = pc.w_host[(size_t)n * c.cin + k];
+    b = pc.b_host;
+    pc.n = c.cout; pc.ktot = il.ktot;
+  } else {                                             // dense 3x3: [N][tap][cin]
+    w.assign((size_t)c.cout * 9 * c.cin, 0.f);
+    for (int n = 0; n < c.cout; ++n)
+      for (int ci = 0; ci < c.cin; ++ci)
+        for (int t = 0; t < 9; ++t)
+          w[((size_t)n * 9 + t) * c.cin + ci] = pc.w_host[((size_t)n * c.cin + ci) * 9 + t];
+    b = pc.b_host;
+    pc.n = c.cout; pc.ktot = 9 * c.cin;
+  }
+  if (pc.w_dev) cudaFree(pc.w_dev);
+  if (pc.b_dev) cudaFree(pc.b_dev);
+  pc.w_dev = pc.b_dev = nullptr;
+  CUDA_TRY(e, cudaMalloc(&pc.w_dev, w.size() * 4));
+  CUDA_TRY(e, cudaMalloc(&pc.b_dev, round_up((int)b.size(), 4) * 4));
+  CUDA_TRY(e, cudaMemcpy(pc.w_dev, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(e, cudaMemset(pc.b_dev, 0, round_up((int)b.size(), 4) * 4));
+  CUDA_TRY(e, cudaMemcpy(pc.b_dev, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+
+  // tensor-core layout for the dense contractions (not the stem: K = 27 is HBM-bound)
+  if ((c.kind == kPw1x1) || (c.kind == kDense3x3 && c.cin != 3)) {
+    TcWeights& t = pc.tc;
+    t.N = pc.n;
+    t.Npad = round_up(pc.n, 16);
+    t.Kpad = round_up(pc.ktot, kTcBK);
+    std::vector<float> hi((size_t)t.Npad * t.Kpad, 0.f), lo((size_t)t.Npad * t.Kpad, 0.f);
+    for (int n = 0; n < pc.n; ++n)
+      for (int k = 0; k < pc.ktot; ++k)
+        split_tf32_host(w[(size_t)n * pc.ktot + k], &hi[(size_t)n * t.Kpad + k], &lo[(size_t)n * t.Kpad + k]);
+    if (t.hi) cudaFree(t.hi);
+    if (t.lo) cudaFree(t.lo);
+    t.hi = t.lo = nullptr;
+    CUDA_TRY(e, cudaMalloc(&t.hi, hi.size() * 4));
+    CUDA_TRY(e, cudaMalloc(&t.lo, lo.size() * 4));
+    CUDA_TRY(e, cudaMemcpy(t.hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(e, cudaMemcpy(t.lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice));
+    if (!make_tmap_2d(&t.tm_hi, t.hi, t.Kpad, t.Npad, t.Kpad, t.Npad) ||
+        !make_tmap_2d(&t.tm_lo, t.lo, t.Kpad, t.Npad, t.Kpad, t.Npad))
+      return fail(e, YNB_ERR_CUDA, "cuTensorMapEncodeTiled failed for weights of " + c.name);
+  }
+  return YNB_OK;
+}
+
+// ---- workspace ---------------------------------------------------------------------------
+struct Bump {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    size_t o = off;
+    off += (bytes + 1023) & ~(size_t)1023;
+    return o;
+  }
+};
+
+// Declares every tensor of the forward pass for (batch, S); with base == nullptr it only
+// measures.  Keep in sync with plan_network.
+size_t layout_workspace(ynb_engine* e, int batch, int S, char* base) {
+  Bump bump;
+  auto tensor = [&](const std::string& name, int C, int ld, int H, ChanMap map = dense_map()) {
+    Tensor t;
+    t.C = C; t.ld = ld; t.H = H; t.W = H; t.map = map;
+    size_t o = bump.take((size_t)batch * H * H * ld * 4);
+    t.p = base ? reinterpret_cast<float*>(base + o) : nullptr;
+    e->taps[name] = t;
+    return t;
+  };
+  e->taps.clear();
+  const int H1 = S / 4;
+  tensor("pool", 24, 24, H1);
+  int hin = H1;
+  for (int si = 0; si < 3; ++si) {
+    int cout = stage_channels()[si + 1], h = cout / 2, cin = stage_channels()[si];
+    int hout = hin / 2;
+    std::string st = "stage" + std::to_string(si + 2);
+    int ld_out = si == 0 ? 120 : cout;
+    ChanMap omap = si == 0 ? kGap58 : dense_map();
+    int ld_h = round_up(h, 4);
+    int ld_in = si == 0 ? 24 : (si == 1 ? 120 : cin);
+    tensor(st + ".b1dw", cin, ld_in, hout, si == 1 ? kGap58 : dense_map());   // branch1 dw output
+    tensor(st + ".b2pw", h, ld_h, hin);                                        // branch2 first pw @ input res
+    tensor(st + ".mid1", h, ld_h, hout);                                       // pw1 / dw scratch
+    tensor(st + ".mid2", h, ld_h, hout);
+    for (int bi = 0; bi < stage_repeats()[si]; ++bi) tensor(st + "." + std::to_string(bi), cout, ld_out, hout, omap);
+    hin = hout;
+  }
+  const int H3 = S / 8, H4 = S / 16, H5 = S / 32;
+  const int hs[3] = {H3, H4, H5};
+  for (int l = 0; l < 3; ++l) tensor("lat" + std::to_string(l + 3), 96, 96, hs[l]);
+  tensor("sum4", 96, 96, H4); tensor("fpn4", 96, 96, H4);
+  tensor("sum3", 96, 96, H3); tensor("p3", 96, 96, H3);
+  tensor("sum4b", 96, 96, H4); tensor("p4", 96, 96, H4);
+  tensor("sum5", 96, 96, H5); tensor("p5", 96, 96, H5);
+  const int ch = e->cfg.num_anchors * (1 + e->cfg.num_classes + 4);
+  const char* pn[3] = {"pred_s", "pred_m", "pred_l"};
+  for (int l = 0; l < 3; ++l) {
+    tensor("head" + std::to_string(l) + ".a", 96, 96, hs[l]);
+    tensor("head" + std::to_string(l) + ".b", 96, 96, hs[l]);
+    e->raw[l] = tensor(pn[l], ch, round_up(ch, 4), hs[l]);
+  }
+  // aliases used as taps
+  e->taps["c3"] = e->taps["stage2.3"];
+  e->taps["c4"] = e->taps["stage3.7"];
+  e->taps["c5"] = e->taps["stage4.3"];
+
+  int64_t n = 0;
+  for (int s : {8, 16, 32}) n += (int64_t)e->cfg.num_anchors * (S / s) * (S / s);
+  auto raw = [&](size_t bytes) { size_t o = bump.take(bytes); return base ? base + o : nullptr; };
+  e->d_boxes = (float*)raw((size_t)batch * n * 16);
+  e->d_scores = (float*)raw((size_t)batch * n * 4);
+  e->d_cls = (int32_t*)raw((size_t)batch * n * 4);
+  e->nms_ws_bytes = nms_workspace_bytes(batch, n);
+  e->d_nms_ws = raw((size_t)e->nms_ws_bytes);
+  e->d_x = (float*)raw((size_t)batch * 3 * S * S * 4);
+  e->d_out_boxes = (float*)raw((size_t)batch * n * 16);
+  e->d_out_scores = (float*)raw((size_t)batch * n * 4);
+  e->d_out_cls = (int32_t*)raw((size_t)batch * n * 4);
+  e->d_out_counts = (int32_t*)raw((size_t)batch * 4);
+  e->d_err = (int*)raw(256);
+  return bump.off;
+}
+
+int ensure_workspace(ynb_engine* e, int batch) {
+  if (e->ws && e->ws_batch >= batch && e->ws_S == e->S) return YNB_OK;
+  int nb = std::max(batch, std::max(e->ws_batch, (int)e->cfg.max_batch));
+  e->plans.clear();
+  e->tc_store.clear();
+  if (e->ws) { cudaFree(e->ws); e->ws = nullptr; }
+  size_t bytes = layout_workspace(e, nb, e->S, nullptr);
+  CUDA_TRY(e, cudaMalloc(&e->ws, bytes));
+  // zero once: channel pads (58->60, gap slots) are never written afterwards and must be 0
+  CUDA_TRY(e, cudaMemset(e->ws, 0, bytes));
+  layout_workspace(e, nb, e->S, e->ws);
+  e->ws_bytes = bytes;
+  e->ws_batch = nb;
+  e->ws_S = e->S;
+  return YNB_OK;
+}
+
+// ---- plan ----------------------------------------------------------------------------------
+struct Planner {
+  ynb_engine* e;
+  int B;
+  Plan* plan;
+  std::deque<TcGemmLaunch>* tc;
+  std::string error;
+
+  const PackedConv& conv(const std::string& name) const { return e->convs[e->index.at(name)]; }
+  const ConvSpec& spec(const std::string& name) const { return e->table[e->index.at(name)]; }
+  Tensor T(const std::string& name) const { return e->taps.at(name); }
+
+  void dw(const std::string& name, const Tensor& in, int in_off, const Tensor& out) {
+    const PackedConv& pc = conv(name);
+    const ConvSpec& c = spec(name);
+    int B_ = B, c4 = pc.n, stride = c.stride, act = c.act;
+    const float *w = pc.w_dev, *b = pc.b_dev;
+    double px_in = (double)B * in.H * in.W, px_out = (double)B * out.H * out.W;
+    plan->net.push_back({name, "dwconv3x3", 4.0 * c.cin * (px_in + px_out) + 40.0 * c.cin, 18.0 * c.cin * px_out,
+                         [=](cudaStream_t st) {
+      return launch_dwconv3x3(in.p, in.ld, in_off, out.p, out.ld, 0, w, b, B_, in.H, in.W, c4, stride, act, st);
+    }});
+  }
+
+  // pointwise conv: in view (off, ktot) -> out (off, step, map), optional pass-through interleave
+  void pw(const std::string& name, const Tensor& in, int in_off, const Tensor& out, int out_off, int out_step,
+          const Tensor* pass = nullptr) {
+    const PackedConv& pc = conv(name);
+    const ConvSpec& c = spec(name);
+    int64_t M = (int64_t)B * in.H * in.W;
+    // algorithmic traffic: read cin, write cout (+ read & re-write the pass-through half)
+    const double abytes = 4.0 * M * (c.cin + c.cout + (pass ? 2.0 * c.cout : 0.0)) + 4.0 * c.cin * c.cout + 4.0 * c.cout;
+    const double aflops = 2.0 * M * c.cin * c.cout;
+    if (e->cfg.gemm_mode == YNB_GEMM_FP32_FFMA) {
+      GemmParams g{};
+      g.a = in.p; g.a_ld = in.ld; g.a_off = in_off; g.a2 = nullptr; g.a2_mode = 0;
+      g.w = pc.w_dev; g.bias = pc.b_dev; g.out = out.p; g.out_ld = out.ld;
+      g.out_off = pass ? 1 : out_off; g.out_step = pass ? 2 : out_step; g.omap = out.map;
+      g.M = M; g.N = pc.n; g.Ktot = pc.ktot; g.act = c.act;
+      plan->net.push_back({name, "pw_ffma", abytes - (pass ? 8.0 * M * c.cout : 0.0), aflops,
+                           [=](cudaStream_t st) { return launch_gemm_ffma(g, false, st); }});
+      if (pass) {
+        Tensor ps = *pass, o = out;
+        int half = pc.n;
+        plan->net.push_back({name + "+passthrough", "interleave_copy", 8.0 * M * c.cout, 0.0, [=](cudaStream_t st) {
+          return launch_interleave_copy(ps.p, ps.ld, o.p, o.ld, o.map, M, half, st);
+        }});
+      }
+      return;
+    }
+    tc->emplace_back();
+    TcGemmLaunch& L = tc->back();
+    L.w = &pc.tc;
+    TcGemmParams& p = L.p;
+    memset(&p, 0, sizeof(p));
+    p.mode = e->cfg.gemm_mode;
+    p.is3x3 = 0;
+    p.num_steps = pc.tc.Kpad / kTcBK;
+    p.chunks_per_tap = p.num_steps;
+    p.M = M;
+    p.num_tiles = (M + kTcBM - 1) / kTcBM;
+    p.N = pc.n; p.Npad = pc.tc.Npad;
+    p.tmem_cols = 32; while ((int)p.tmem_cols < 2 * p.Npad) p.tmem_cols <<= 1;
+    p.a_box_bytes = kTcAStageBytes;
+    p.out = out.p; p.out_ld = out.ld; p.out_off = out_off; p.out_step = out_step; p.omap = out.map;
+    p.bias = pc.b_dev; p.act = c.act;
+    p.pass = pass ? pass->p : nullptr; p.pass_ld = pass ? pass->ld : 0;
+    p.err_flag = e->d_err;
+    if (!make_tmap_2d(&L.tmA, in.p + in_off, (uint64_t)pc.ktot, (uint64_t)M, (uint64_t)in.ld, kTcBM)) {
+      error = "cuTensorMapEncodeTiled failed for input of " + name;
+      return;
+    }
+    if (!tc_plan_smem(L)) { error = "no smem configuration for " + name; return; }
+    L.grid = (unsigned)std::min<int64_t>(p.num_tiles, kNumSMs);
+    const TcGemmLaunch* Lp = &L;
+    plan->net.push_back({name, "pw_tcgen05", abytes, aflops, [=](cudaStream_t st) { return launch_tc_gemm(*Lp, st); }});
+  }
+
+  // dense 3x3 (smooth): out = act(conv3x3(a + resample(a2)))
+  void conv3(const std::string& name, const Tensor& a, const Tensor* a2, int a2_mode, const Tensor& sum,
+             const Tensor& out) {
+    const PackedConv& pc = conv(name);
+    const ConvSpec& c = spec(name);
+    int64_t M = (int64_t)B * a.H * a.W;
+    const double wbytes = 4.0 * 9 * c.cin * c.cout + 4.0 * c.cout;
+    const double aflops = 2.0 * M * 9 * c.cin * c.cout;
+    // fused form reads a and the useful part of a2 once and writes the output once
+    const double a2bytes = a2 ? 4.0 * c.cin * M * (a2_mode == 1 ? 0.25 : 1.0) : 0.0;
+    if (e->cfg.gemm_mode == YNB_GEMM_FP32_FFMA) {
+      GemmParams g{};
+      g.a = a.p; g.a_ld = a.ld; g.a_off = 0;
+      g.a2 = a2 ? a2->p : nullptr; g.a2_ld = a2 ? a2->ld : 0; g.a2_mode = a2 ? a2_mode : 0;
+      g.H = a.H; g.W = a.W; g.C = c.cin;
+      g.w = pc.w_dev; g.bias = pc.b_dev; g.out = out.p; g.out_ld = out.ld; g.out_off = 0; g.out_step = 1;
+      g.omap = dense_map(); g.M = M; g.N = pc.n; g.Ktot = pc.ktot; g.act = c.act;
+      plan->net.push_back({name, "conv3x3_ffma", 4.0 * M * (c.cin + c.cout) + a2bytes + wbytes, aflops,
+                           [=](cudaStream_t st) { return launch_gemm_ffma(g, true, st); }});
+      return;
+    }
+    // tensor-core path: materialise the sum once (HBM-bound elementwise), then 9 shifted TMA boxes
+    Tensor src = a;
+    if (a2) {
+      Tensor a_ = a, a2_ = *a2, s_ = sum;
+      int B_ = B;
+      plan->net.push_back({name + "+merge", "resample_add", 8.0 * M * c.cin + a2bytes, 1.0 * M * c.cin,
+                           [=](cudaStream_t st) {
+        return launch_resample_add(a_.p, a2_.p, s_.p, B_, a_.H, a_.W, a_.ld, a2_mode, st);
+      }});
+      src = sum;
+    }
+    tc->emplace_back();
+    TcGemmLaunch& L = tc->back();
+    L.w = &pc.tc;
+    TcGemmParams& p = L.p;
+    memset(&p, 0, sizeof(p));
+    p.mode = e->cfg.gemm_mode;
+    p.is3x3 = 1;
+    p.chunks_per_tap = c.cin / kTcBK;
+    p.num_steps = 9 * p.chunks_per_tap;
+    p.H = a.H; p.W = a.W;
+    tc_pick_tile(p.H, p.W, &p.TH, &p.TW);
+    p.tiles_x = (p.W + p.TW - 1) / p.TW;
+    p.tiles_y = (p.H + p.TH - 1) / p.TH;
+    p.num_tiles = (int64_t)B * p.tiles_x * p.tiles_y;
+    p.M = M;
+    p.N = pc.n; p.Npad = pc.tc.Npad;
+    p.tmem_cols = 32; while ((int)p.tmem_cols < 2 * p.Npad) p.tmem_cols <<= 1;
+    p.a_box_bytes = (uint32_t)(p.TH * p.TW * 128);
+    p.out = out.p; p.out_ld = out.ld; p.out_off = 0; p.out_step = 1; p.omap = dense_map();
+    p.bias = pc.b_dev; p.act = c.act; p.pass = nullptr;
+    p.err_flag = e->d_err;
+    if (!make_tmap_nhwc(&L.tmA, src.p, c.cin, src.W, src.H, B, src.ld, p.TW, p.TH)) {
+      error = "cuTensorMapEncodeTiled failed for input of " + name;
+      return;
+    }
+    if (!tc_plan_smem(L)) { error = "no smem configuration for " + name; return; }
+    L.grid = (unsigned)std::min<int64_t>(p.num_tiles, kNumSMs);
+    const TcGemmLaunch* Lp = &L;
+    plan->net.push_back({name, "conv3x3_tcgen05", 4.0 * M * (c.cin + c.cout) + wbytes, aflops,
+                         [=](cudaStream_t st) { return launch_tc_gemm(*Lp, st); }});
+  }
+};
+
+int build_plan(ynb_engine* e, int B, Plan** out) {
+  auto it = e->plans.find(B);
+  if (it != e->plans.end()) { *out = it->second.get(); return YNB_OK; }
+  auto plan = std::make_unique<Plan>();
+  plan->batch = B;
+  e->tc_store.emplace_back();
+  Planner P{e, B, plan.get(), &e->tc_store.back(), ""};
+  const int S = e->S;
+
+  // stem + pool
+  {
+    const PackedConv& pc = P.conv("backbone.conv1.0");
+    Tensor pool = P.T("pool");
+    const float *w = pc.w_dev, *b = pc.b_dev;
+    // input pointer is bound at run time (first op takes it from the engine)
+    double px = (double)B * S * S;
+    plan->net.push_back({"backbone.conv1.0+maxpool", "stem_pool", 4.0 * (3 * px + 24 * px / 16) + 4.0 * 27 * 24,
+                         2.0 * 27 * 24 * px / 4, [=](cudaStream_t st) {
+      return launch_stem_pool(e->d_x_bound, pool.p, w, b, B, S, st);
+    }});
+  }
+  Tensor x = P.T("pool");
+  for (int si = 0; si < 3; ++si) {
+    std::string st = "stage" + std::to_string(si + 2);
+    std::string bk = "backbone." + st + ".";
+    int h = stage_channels()[si + 1] / 2;
+    Tensor b1dw = P.T(st + ".b1dw"), b2pw = P.T(st + ".b2pw"), mid1 = P.T(st + ".mid1"), mid2 = P.T(st + ".mid2");
+    // ---- stride-2 unit: out[2i] = branch1, out[2i+1] = branch2 (shufflenetv2.py:73-76)
+    Tensor o0 = P.T(st + ".0");
+    P.dw(bk + "0.branch1.0", x, 0, b1dw);
+    P.pw(bk + "0.branch1.2", b1dw, 0, o0, 0, 2);
+    P.pw(bk + "0.branch2.0", x, 0, b2pw, 0, 1);
+    P.dw(bk + "0.branch2.3", b2pw, 0, mid2);
+    P.pw(bk + "0.branch2.5", mid2, 0, o0, 1, 2);
+    x = o0;
+    // ---- stride-1 units: x1 passes through to slot 2i, branch2(x2) lands in slot 2i+1 (:70-76)
+    for (int bi = 1; bi < stage_repeats()[si]; ++bi) {
+      std::string u = bk + std::to_string(bi);
+      Tensor o = P.T(st + "." + std::to_string(bi));
+      int x2_off = x.map.slot(h);
+      P.pw(u + ".branch2.0", x, x2_off, mid1, 0, 1);
+      P.dw(u + ".branch2.3", mid1, 0, mid2);
+      P.pw(u + ".branch2.5", mid2, 0, o, 1, 2, &x);
+      x = o;
+    }
+  }
+  // ---- neck (models/yolo_nano.py:286-296)
+  Tensor c3 = P.T("c3"), c4 = P.T("c4"), c5 = P.T("c5");
+  Tensor lat3 = P.T("lat3"), lat4 = P.T("lat4"), lat5 = P.T("lat5");
+  P.pw("conv1x1_0.convs.0", c3, 0, lat3, 0, 1);
+  P.pw("conv1x1_1.convs.0", c4, 0, lat4, 0, 1);
+  P.pw("conv1x1_2.convs.0", c5, 0, lat5, 0, 1);
+  Tensor fpn4 = P.T("fpn4"), p3 = P.T("p3"), p4 = P.T("p4"), p5 = P.T("p5");
+  P.conv3("smooth_0.convs.0", lat4, &lat5, 1, P.T("sum4"), fpn4);
+  P.conv3("smooth_1.convs.0", lat3, &fpn4, 1, P.T("sum3"), p3);
+  P.conv3("smooth_2.convs.0", fpn4, &p3, 2, P.T("sum4b"), p4);
+  P.conv3("smooth_3.convs.0", lat5, &p4, 2, P.T("sum5"), p5);
+  // ---- heads (models/yolo_nano.py:50-70, 299-301)
+  Tensor feats[3] = {p3, p4, p5};
+  for (int l = 0; l < 3; ++l) {
+    std::string hd = "head_det_" + std::to_string(l + 1);
+    Tensor ta = P.T("head" + std::to_string(l) + ".a"), tb = P.T("head" + std::to_string(l) + ".b");
+    P.dw(hd + ".0.convs.0", feats[l], 0, ta);
+    P.pw(hd + ".1.convs.0", ta, 0, tb, 0, 1);
+    P.dw(hd + ".2.convs.0", tb, 0, ta);
+    P.pw(hd + ".3.convs.0", ta, 0, tb, 0, 1);
+    P.pw(hd + ".4", tb, 0, e->raw[l], 0, 1);
+  }
+  if (!P.error.empty()) return fail(e, YNB_ERR_CUDA, P.error);
+  // ---- decode (models/yolo_nano.py:303-330, 362-367)
+  int64_t N = e->N(), off = 0;
+  for (int l = 0; l < 3; ++l) {
+    DecodeParams d{};
+    int stride = 8 << l;
+    d.raw = e->raw[l].p; d.ld = e->raw[l].ld;
+    d.boxes = e->d_boxes; d.scores = e->d_scores; d.cls = e->d_cls;
+    d.batch = B; d.G = S / stride; d.A = e->cfg.num_anchors; d.C = e->cfg.num_classes;
+    d.stride = (float)stride; d.input_size = (float)S;
+    for (int a = 0; a < d.A; ++a) {
+      d.anchor_w[a] = e->cfg.anchors[(l * d.A + a) * 2];
+      d.anchor_h[a] = e->cfg.anchors[(l * d.A + a) * 2 + 1];
+    }
+    d.N = N; d.level_off = off;
+    off += (int64_t)d.G * d.G * d.A;
+    double cells = (double)B * d.G * d.G;
+    plan->decode.push_back({"decode.level" + std::to_string(l), "decode",
+                            4.0 * cells * d.A * (1 + d.C + 4) + 24.0 * cells * d.A, 0.0,
+                            [=](cudaStream_t st) { return launch_decode_level(d, st); }});
+  }
+  *out = plan.get();
+  e->plans[B] = std::move(plan);
+  return YNB_OK;
+}
+
+int check_ready(ynb_engine* e, int batch) {
+  if (!e) return YNB_ERR_INVALID;
+  if (!e->committed) return fail(e, YNB_ERR_STATE, "weights not committed (ynb_load_conv x77, ynb_commit_weights)");
+  if (batch <= 0) return fail(e, YNB_ERR_INVALID, "batch must be positive");
+  return YNB_OK;
+}
+
+int run_ops(ynb_engine* e, const std::vector<Op>& ops, cudaStream_t st) {
+  if (!e->profiling) {
+    for (const Op& op : ops) {
+      cudaError_t r = op.fn(st);
+      if (r != cudaSuccess)
+        return fail(e, YNB_ERR_CUDA, "kernel launch (" + op.name + "): " + cudaGetErrorString(r));
+    }
+    return YNB_OK;
+  }
+  // profiling pass: one CUDA event pair per launch, on the launching stream
+  std::vector<cudaEvent_t> ev(ops.size() + 1);
+  for (auto& x : ev) CUDA_TRY(e, cudaEventCreate(&x));
+  CUDA_TRY(e, cudaEventRecord(ev[0], st));
+  for (size_t i = 0; i < ops.size(); ++i) {
+    cudaError_t r = ops[i].fn(st);
+    if (r != cudaSuccess)
+      return fail(e, YNB_ERR_CUDA, "kernel launch (" + ops[i].name + "): " + cudaGetErrorString(r));
+    CUDA_TRY(e, cudaEventRecord(ev[i + 1], st));
+  }
+  CUDA_TRY(e, cudaEventSynchronize(ev.back()));
+  for (size_t i = 0; i < ops.size(); ++i) {
+    float ms = 0;
+    CUDA_TRY(e, cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+    e->prof.push_back({ops[i].name, ops[i].kind, ops[i].bytes, ops[i].flops, ms});
+  }
+  for (auto& x : ev) cudaEventDestroy(x);
+  return YNB_OK;
+}
+
+int run_network(ynb_engine* e, const float* x_dev, int batch, cudaStream_t st, Plan** plan_out) {
+  int rc = check_ready(e, batch);
+  if (rc) return rc;
+  CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+  if ((rc = ensure_workspace(e, batch))) return rc;
+  Plan* plan = nullptr;
+  if ((rc = build_plan(e, batch, &plan))) return rc;
+  e->d_x_bound = x_dev;
+  e->prof.clear();
+  if ((rc = run_ops(e, plan->net, st))) return rc;
+  *plan_out = plan;
+  return YNB_OK;
+}
+
+int check_device_error(ynb_engine* e, cudaStream_t st) {
+  int flag = 0;
+  CUDA_TRY(e, cudaMemcpyAsync(&flag, e->d_err, 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(e, cudaStreamSynchronize(st));
+  if (flag != 0) {
+    cudaMemsetAsync(e->d_err, 0, 4, st);
+    return fail(e, YNB_ERR_CUDA, "tensor-core pipeline timed out waiting on mbarrier (code " +
+                                     std::to_string(flag) + ")");
+  }
+  return YNB_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+YNB_EXPORT int ynb_abi_version(void) { return YNB_ABI_VERSION; }
+
+YNB_EXPORT const char* ynb_last_error(const ynb_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+YNB_EXPORT int ynb_create(const ynb_config* cfg, ynb_engine** out) {
+  if (!cfg || !out) return fail(nullptr, YNB_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != YNB_ABI_VERSION) return fail(nullptr, YNB_ERR_INVALID, "ABI version mismatch");
+  if (cfg->num_anchors != 3) return fail(nullptr, YNB_ERR_UNSUPPORTED, "num_anchors must be 3");
+  if (cfg->num_classes < 1 || cfg->num_classes > 255) return fail(nullptr, YNB_ERR_INVALID, "num_classes out of range");
+  if (cfg->input_size < 32 || cfg->input_size % 32 || cfg->input_size > 1024)
+    return fail(nullptr, YNB_ERR_INVALID, "input_size must be a multiple of 32 in [32, 1024]");
+  if (cfg->gemm_mode < 0 || cfg->gemm_mode > YNB_GEMM_TC_TF32) return fail(nullptr, YNB_ERR_INVALID, "bad gemm_mode");
+  int ndev = 0;
+  cudaError_t st = cudaGetDeviceCount(&ndev);
+  if (st != cudaSuccess || ndev == 0)
+    return fail(nullptr, YNB_ERR_NO_DEVICE,
+                std::string("no CUDA device: ") + (st != cudaSuccess ? cudaGetErrorString(st) : "count is 0") +
+                    " (this library has no CPU path)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, YNB_ERR_INVALID, "device ordinal out of range");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10)
+    return fail(nullptr, YNB_ERR_NO_DEVICE, "device is not compute capability 10.x (built for sm_100a only)");
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return fail(nullptr, YNB_ERR_CUDA, "cudaSetDevice failed");
+  ynb_engine* e = new ynb_engine();
+  e->cfg = *cfg;
+  if (e->cfg.max_batch < 1) e->cfg.max_batch = 1;
+  e->S = cfg->input_size;
+  e->table = conv_table(cfg->num_classes, cfg->num_anchors);
+  e->convs.resize(e->table.size());
+  for (size_t i = 0; i < e->table.size(); ++i) e->index[e->table[i].name] = (int)i;
+  *out = e;
+  return YNB_OK;
+}
+
+YNB_EXPORT void ynb_destroy(ynb_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  for (PackedConv& pc : e->convs) {
+    if (pc.w_dev) cudaFree(pc.w_dev);
+    if (pc.b_dev) cudaFree(pc.b_dev);
+    if (pc.tc.hi) cudaFree(pc.tc.hi);
+    if (pc.tc.lo) cudaFree(pc.tc.lo);
+  }
+  if (e->ws) cudaFree(e->ws);
+  delete e;
+}
+
+YNB_EXPORT int ynb_set_grid(ynb_engine* e, int32_t input_size) {
+  if (!e) return YNB_ERR_INVALID;
+  if (input_size < 32 || input_size % 32 || input_size > 1024)
+    return fail(e, YNB_ERR_INVALID, "input_size must be a multiple of 32 in [32, 1024]");
+  e->S = input_size;   // workspace / plans are rebuilt lazily on the next forward
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_set_thresholds(ynb_engine* e, float conf, float nms, int32_t diou) {
+  if (!e) return YNB_ERR_INVALID;
+  e->cfg.conf_thresh = conf; e->cfg.nms_thresh = nms; e->cfg.diou_nms = diou;
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_set_gemm_mode(ynb_engine* e, int32_t mode) {
+  if (!e) return YNB_ERR_INVALID;
+  if (mode < 0 || mode > YNB_GEMM_TC_TF32) return fail(e, YNB_ERR_INVALID, "bad gemm_mode");
+  if (mode != e->cfg.gemm_mode) { e->cfg.gemm_mode = mode; e->plans.clear(); e->tc_store.clear(); }
+  return YNB_OK;
+}
+
+YNB_EXPORT int64_t ynb_num_boxes(const ynb_engine* e) { return e ? e->N() : 0; }
+
+YNB_EXPORT int64_t ynb_workspace_bytes(const ynb_engine* e, int32_t batch) {
+  if (!e || batch < 1) return 0;
+  ynb_engine tmp;
+  tmp.cfg = e->cfg;
+  return (int64_t)layout_workspace(&tmp, batch, e->S, nullptr);
+}
+
+YNB_EXPORT int32_t ynb_num_convs(void) { return 77; }
+
+YNB_EXPORT const char* ynb_conv_name(int32_t i) {
+  static const std::vector<ConvSpec> t = conv_table(80, 3);
+  return (i >= 0 && i < (int)t.size()) ? t[i].name.c_str() : nullptr;
+}
+
+YNB_EXPORT int ynb_conv_shape(int32_t i, int32_t num_classes, int32_t num_anchors, int32_t* cout,
+                              int32_t* cin_per_group, int32_t* ksize) {
+  std::vector<ConvSpec> t = conv_table(num_classes, num_anchors);
+  if (i < 0 || i >= (int)t.size() || !cout || !cin_per_group || !ksize) return YNB_ERR_INVALID;
+  *cout = t[i].cout;
+  *cin_per_group = t[i].kind == kDw3x3 ? 1 : t[i].cin;
+  *ksize = t[i].kind == kPw1x1 ? 1 : 3;
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_load_conv(ynb_engine* e, const char* name, const float* w, int64_t w_elems, const float* b,
+                             int64_t b_elems) {
+  if (!e || !name || !w || !b) return fail(e, YNB_ERR_INVALID, "null argument");
+  auto it = e->index.find(name);
+  if (it == e->index.end()) return fail(e, YNB_ERR_INVALID, std::string("unknown conv ") + name);
+  const ConvSpec& c = e->table[it->second];
+  int64_t expect = (int64_t)c.cout * (c.kind == kDw3x3 ? 1 : c.cin) * (c.kind == kPw1x1 ? 1 : 9);
+  if (w_elems != expect || b_elems != c.cout)
+    return fail(e, YNB_ERR_INVALID, std::string("shape mismatch for ") + name);
+  PackedConv& pc = e->convs[it->second];
+  pc.w_host.assign(w, w + w_elems);
+  pc.b_host.assign(b, b + b_elems);
+  pc.loaded = true;
+  e->committed = false;
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_commit_weights(ynb_engine* e) {
+  if (!e) return YNB_ERR_INVALID;
+  CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+  for (size_t i = 0; i < e->convs.size(); ++i)
+    if (!e->convs[i].loaded) return fail(e, YNB_ERR_STATE, "conv not loaded: " + e->table[i].name);
+  CUDA_TRY(e, cudaDeviceSynchronize());   // nothing in flight may still read the old buffers
+  e->plans.clear();
+  e->tc_store.clear();
+  for (size_t i = 0; i < e->convs.size(); ++i) {
+    int rc = pack_conv(e, (int)i);
+    if (rc) return rc;
+  }
+  e->committed = true;
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_forward_raw(ynb_engine* e, const float* x_dev, int32_t batch, float* ps, float* pm, float* pl,
+                               void* stream) {
+  if (!e || !x_dev || !ps || !pm || !pl) return fail(e, YNB_ERR_INVALID, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CounterScope cs(e);
+  Plan* plan = nullptr;
+  int rc = run_network(e, x_dev, batch, st, &plan);
+  if (rc) return rc;
+  float* outs[3] = {ps, pm, pl};
+  for (int l = 0; l < 3; ++l) {
+    const Tensor& t = e->raw[l];
+    CUDA_TRY(e, launch_nhwc_to_nchw(t.p, t.ld, t.map, outs[l], batch, t.C, t.H * t.W, st));
+  }
+  return e->cfg.gemm_mode == YNB_GEMM_FP32_FFMA ? YNB_OK : check_device_error(e, st);
+}
+
+YNB_EXPORT int ynb_forward_decode(ynb_engine* e, const float* x_dev, int32_t batch, float* boxes, float* scores,
+                                  int32_t* cls, void* stream) {
+  if (!e || !x_dev || !boxes || !scores || !cls) return fail(e, YNB_ERR_INVALID, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CounterScope cs(e);
+  Plan* plan = nullptr;
+  int rc = run_network(e, x_dev, batch, st, &plan);
+  if (rc) return rc;
+  if ((rc = run_ops(e, plan->decode, st))) return rc;
+  int64_t n = e->N();
+  CUDA_TRY(e, cudaMemcpyAsync(boxes, e->d_boxes, (size_t)batch * n * 16, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(e, cudaMemcpyAsync(scores, e->d_scores, (size_t)batch * n * 4, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(e, cudaMemcpyAsync(cls, e->d_cls, (size_t)batch * n * 4, cudaMemcpyDeviceToDevice, st));
+  return e->cfg.gemm_mode == YNB_GEMM_FP32_FFMA ? YNB_OK : check_device_error(e, st);
+}
+
+static int detect_device(ynb_engine* e, const float* x_dev, int batch, float* ob, float* os, int32_t* oc,
+                         int32_t* on, cudaStream_t st) {
+  Plan* plan = nullptr;
+  int rc = run_network(e, x_dev, batch, st, &plan);
+  if (rc) return rc;
+  if ((rc = run_ops(e, plan->decode, st))) return rc;
+  NmsWorkspace w = nms_carve(e->d_nms_ws, batch, e->N());
+  const int64_t n = e->N();
+  std::vector<Op> nms_ops(1);
+  nms_ops[0] = {"nms(keys+sort+greedy+compact)", "nms", 24.0 * batch * n * 2, 0.0, [=](cudaStream_t s2) {
+    return launch_nms(e->d_boxes, e->d_scores, e->d_cls, batch, n, e->cfg.num_classes, e->cfg.conf_thresh,
+                      e->cfg.nms_thresh, e->cfg.diou_nms, ob, os, oc, on, nullptr, w, s2);
+  }};
+  return run_ops(e, nms_ops, st);
+}
+
+YNB_EXPORT int ynb_forward_detect(ynb_engine* e, const float* x_dev, int32_t batch, float* ob, float* os,
+                                  int32_t* oc, int32_t* on, void* stream) {
+  if (!e || !x_dev || !ob || !os || !oc || !on) return fail(e, YNB_ERR_INVALID, "null argument");
+  CounterScope cs(e);
+  return detect_device(e, x_dev, batch, ob, os, oc, on, (cudaStream_t)stream);
+}
+
+YNB_EXPORT int ynb_detect_host(ynb_engine* e, const float* x_host, int32_t batch, float* ob, float* os,
+                               int32_t* oc, int32_t* on, void* stream) {
+  if (!e || !x_host || !ob || !os || !oc || !on) return fail(e, YNB_ERR_INVALID, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CounterScope cs(e);
+  int rc = check_ready(e, batch);
+  if (rc) return rc;
+  CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+  if ((rc = ensure_workspace(e, batch))) return rc;
+  const int64_t n = e->N();
+  const size_t img = (size_t)3 * e->S * e->S * 4;
+  CUDA_TRY(e, cudaMemcpyAsync(e->d_x, x_host, img * batch, cudaMemcpyHostToDevice, st));
+  if ((rc = detect_device(e, e->d_x, batch, e->d_out_boxes, e->d_out_scores, e->d_out_cls, e->d_out_counts, st)))
+    return rc;
+  // counts first, then only the kept rows of each image cross PCIe
+  CUDA_TRY(e, cudaMemcpyAsync(on, e->d_out_counts, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(e, cudaStreamSynchronize(st));
+  for (int b = 0; b < batch; ++b) {
+    size_t k = (size_t)on[b];
+    if (k == 0) continue;
+    CUDA_TRY(e, cudaMemcpyAsync(ob + (size_t)b * n * 4, e->d_out_boxes + (size_t)b * n * 4, k * 16,
+                                cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(e, cudaMemcpyAsync(os + (size_t)b * n, e->d_out_scores + (size_t)b * n, k * 4,
+                                cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(e, cudaMemcpyAsync(oc + (size_t)b * n, e->d_out_cls + (size_t)b * n, k * 4, cudaMemcpyDeviceToHost, st));
+  }
+  CUDA_TRY(e, cudaStreamSynchronize(st));
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_tap_shape(const ynb_engine* e, const char* tap, int32_t* c, int32_t* h, int32_t* w) {
+  if (!e || !tap || !c || !h || !w) return YNB_ERR_INVALID;
+  ynb_engine* me = const_cast<ynb_engine*>(e);
+  if (me->taps.empty()) {
+    ynb_engine tmp;
+    tmp.cfg = e->cfg;
+    layout_workspace(&tmp, 1, e->S, nullptr);
+    me->taps = tmp.taps;
+  }
+  auto it = me->taps.find(tap);
+  if (it == me->taps.end()) return fail(me, YNB_ERR_INVALID, std::string("unknown tap ") + tap);
+  int hh = it->second.H;
+  if (me->ws_S != me->S) {   // grid changed since the last forward: rescale
+    ynb_engine tmp;
+    tmp.cfg = e->cfg;
+    layout_workspace(&tmp, 1, e->S, nullptr);
+    hh = tmp.taps.at(tap).H;
+  }
+  *c = it->second.C; *h = hh; *w = hh;
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_read_tap(ynb_engine* e, const char* tap, int32_t batch, float* out_dev, void* stream) {
+  if (!e || !tap || !out_dev) return fail(e, YNB_ERR_INVALID, "null argument");
+  if (!e->ws || e->ws_S != e->S || batch > e->ws_batch) return fail(e, YNB_ERR_STATE, "run a forward first");
+  auto it = e->taps.find(tap);
+  if (it == e->taps.end() || !it->second.p) return fail(e, YNB_ERR_INVALID, std::string("unknown tap ") + tap);
+  const Tensor& t = it->second;
+  CounterScope cs(e);
+  CUDA_TRY(e, launch_nhwc_to_nchw(t.p, t.ld, t.map, out_dev, batch, t.C, t.H * t.W, (cudaStream_t)stream));
+  return YNB_OK;
+}
+
+YNB_EXPORT int64_t ynb_launch_count(const ynb_engine* e) { return e ? e->counter.n : 0; }
+
+YNB_EXPORT int ynb_set_profiling(ynb_engine* e, int32_t on) {
+  if (!e) return YNB_ERR_INVALID;
+  e->profiling = on != 0;
+  return YNB_OK;
+}
+
+YNB_EXPORT int32_t ynb_profile_count(const ynb_engine* e) { return e ? (int32_t)e->prof.size() : 0; }
+
+YNB_EXPORT int ynb_profile_entry(const ynb_engine* e, int32_t i, const char** name, const char** kind, float* ms,
+                                 double* bytes, double* flops) {
+  if (!e || i < 0 || i >= (int32_t)e->prof.size() || !name || !kind || !ms || !bytes || !flops) return YNB_ERR_INVALID;
+  const ProfEntry& p = e->prof[i];
+  *name = p.name.c_str(); *kind = p.kind.c_str(); *ms = p.ms; *bytes = p.bytes; *flops = p.flops;
+  return YNB_OK;
+}
+
+// ---- unit kernels ------------------------------------------------------------------------------
+static thread_local std::string g_unit_error;
+#define UNIT_TRY(call)                                                       \
+  do {                                                                       \
+    cudaError_t _st = (call);                                                \
+    if (_st != cudaSuccess) {                                                \
+      g_create_error = std::string(#call) + ": " + cudaGetErrorString(_st);  \
+      return YNB_ERR_CUDA;                                                   \
+    }                                                                        \
+  } while (0)
+
+YNB_EXPORT int ynb_dwconv3x3(const float* in, int32_t in_ld, int32_t in_off, float* out, int32_t out_ld,
+                             int32_t out_off, int32_t out_step, const float* w, const float* b, int32_t batch,
+                             int32_t h_in, int32_t w_in, int32_t channels, int32_t stride, int32_t act, void* stream) {
+  if (!in || !out || !w || !b || channels % 4 || in_ld % 4 || in_off % 4 || out_ld % 4 || out_off % 4 ||
+      out_step != 1 || (stride != 1 && stride != 2))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_dwconv3x3: channels/ld/off must be multiples of 4, out_step 1");
+  UNIT_TRY(launch_dwconv3x3(in, in_ld, in_off, out, out_ld, out_off, w, b, batch, h_in, w_in, channels, stride, act,
+                            (cudaStream_t)stream));
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_pwconv(const float* in, int32_t in_ld, int32_t in_off, float* out, int32_t out_ld,
+                          int32_t out_off, int32_t out_step, const float* w, const float* b, int64_t pixels,
+                          int32_t cin, int32_t cout, int32_t act, void* stream) {
+  if (!in || !out || !w || !b || cin % 4 || in_ld % 4 || in_off % 4)
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_pwconv: cin / in_ld / in_off must be multiples of 4");
+  GemmParams g{};
+  g.a = in; g.a_ld = in_ld; g.a_off = in_off; g.w = w; g.bias = b; g.out = out; g.out_ld = out_ld;
+  g.out_off = out_off; g.out_step = out_step; g.omap = dense_map(); g.M = pixels; g.N = cout; g.Ktot = cin;
+  g.act = act;
+  UNIT_TRY(launch_gemm_ffma(g, false, (cudaStream_t)stream));
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_pwconv_tc(const float* in, int32_t in_ld, int32_t in_off, float* out, int32_t out_ld,
+                             int32_t out_off, int32_t out_step, const float* w_dev, const float* b_dev,
+                             int64_t pixels, int32_t cin, int32_t cout, int32_t act, int32_t mode, void* stream) {
+  if (!in || !out || !w_dev || !b_dev || cin % 4 || in_ld % 4 || in_off % 4 || out_ld % 4 ||
+      (out_step == 1 && out_off % 4) || cout > 256 || (mode != YNB_GEMM_TC_3XTF32 && mode != YNB_GEMM_TC_TF32))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_pwconv_tc: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  // test hook: pack the weights on the host (synchronous)
+  std::vector<float> w((size_t)cout * cin);
+  UNIT_TRY(cudaMemcpy(w.data(), w_dev, w.size() * 4, cudaMemcpyDeviceToHost));
+  TcWeights t;
+  t.N = cout; t.Npad = round_up(cout, 16); t.Kpad = round_up(cin, kTcBK);
+  std::vector<float> hi((size_t)t.Npad * t.Kpad, 0.f), lo((size_t)t.Npad * t.Kpad, 0.f);
+  for (int n = 0; n < cout; ++n)
+    for (int k = 0; k < cin; ++k)
+      split_tf32_host(w[(size_t)n * cin + k], &hi[(size_t)n * t.Kpad + k], &lo[(size_t)n * t.Kpad + k]);
+  int* d_err = nullptr;
+  UNIT_TRY(cudaMalloc(&t.hi, hi.size() * 4));
+  UNIT_TRY(cudaMalloc(&t.lo, lo.size() * 4));
+  UNIT_TRY(cudaMalloc(&d_err, 4));
+  UNIT_TRY(cudaMemset(d_err, 0, 4));
+  UNIT_TRY(cudaMemcpy(t.hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice));
+  UNIT_TRY(cudaMemcpy(t.lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice));
+  int rc = YNB_OK;
+  TcGemmLaunch L;
+  L.w = &t;
+  TcGemmParams& p = L.p;
+  memset(&p, 0, sizeof(p));
+  p.mode = mode; p.num_steps = t.Kpad / kTcBK; p.chunks_per_tap = p.num_steps;
+  p.M = pixels; p.num_tiles = (pixels + kTcBM - 1) / kTcBM; p.N = cout; p.Npad = t.Npad;
+  p.tmem_cols = 32; while ((int)p.tmem_cols < 2 * p.Npad) p.tmem_cols <<= 1;
+  p.a_box_bytes = kTcAStageBytes;
+  p.out = out; p.out_ld = out_ld; p.out_off = out_off; p.out_step = out_step; p.omap = dense_map();
+  p.bias = b_dev; p.act = act; p.err_flag = d_err;
+  if (!make_tmap_2d(&t.tm_hi, t.hi, t.Kpad, t.Npad, t.Kpad, t.Npad) ||
+      !make_tmap_2d(&t.tm_lo, t.lo, t.Kpad, t.Npad, t.Kpad, t.Npad) ||
+      !make_tmap_2d(&L.tmA, in + in_off, cin, pixels, in_ld, kTcBM) || !tc_plan_smem(L)) {
+    rc = fail(nullptr, YNB_ERR_CUDA, "ynb_pwconv_tc: tensor map / smem planning failed");
+  } else {
+    L.grid = (unsigned)std::min<int64_t>(p.num_tiles, kNumSMs);
+    cudaError_t r = launch_tc_gemm(L, st);
+    if (r == cudaSuccess) r = cudaStreamSynchronize(st);
+    int flag = 0;
+    if (r == cudaSuccess) r = cudaMemcpy(&flag, d_err, 4, cudaMemcpyDeviceToHost);
+    if (r != cudaSuccess) rc = fail(nullptr, YNB_ERR_CUDA, std::string("ynb_pwconv_tc: ") + cudaGetErrorString(r));
+    else if (flag) rc = fail(nullptr, YNB_ERR_CUDA, "ynb_pwconv_tc: mbarrier timeout code " + std::to_string(flag));
+  }
+  cudaFree(t.hi); cudaFree(t.lo); cudaFree(d_err);
+  return rc;
+}
+
+YNB_EXPORT int ynb_stem_pool(const float* x, float* out, const float* w, const float* b, int32_t batch,
+                             int32_t input_size, void* stream) {
+  if (!x || !out || !w || !b || input_size % 32) return fail(nullptr, YNB_ERR_INVALID, "ynb_stem_pool: bad arguments");
+  UNIT_TRY(launch_stem_pool(x, out, w, b, batch, input_size, (cudaStream_t)stream));
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_decode_level(const float* raw, int32_t raw_ld, float* boxes, float* scores, int32_t* cls,
+                                int32_t batch, int32_t grid, int32_t stride_px, int32_t input_size,
+                                const float* anchors_wh, int32_t num_anchors, int32_t num_classes,
+                                int64_t boxes_per_image, int64_t level_off, void* stream) {
+  if (!raw || !boxes || !scores || !cls || !anchors_wh || num_anchors > 4)
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_decode_level: bad arguments");
+  DecodeParams d{};
+  d.raw = raw; d.ld = raw_ld; d.boxes = boxes; d.scores = scores; d.cls = cls; d.batch = batch; d.G = grid;
+  d.A = num_anchors; d.C = num_classes; d.stride = (float)stride_px; d.input_size = (float)input_size;
+  for (int a = 0; a < num_anchors; ++a) { d.anchor_w[a] = anchors_wh[2 * a]; d.anchor_h[a] = anchors_wh[2 * a + 1]; }
+  d.N = boxes_per_image; d.level_off = level_off;
+  UNIT_TRY(launch_decode_level(d, (cudaStream_t)stream));
+  return YNB_OK;
+}
+
+YNB_EXPORT int64_t ynb_nms_workspace_bytes(int32_t batch, int64_t n) { return nms_workspace_bytes(batch, n); }
+
+YNB_EXPORT int ynb_nms(const float* boxes, const float* scores, const int32_t* cls, int32_t batch, int64_t n,
+                       int32_t num_classes, float conf, float thr, int32_t diou, float* ob, float* os, int32_t* oc,
+                       int32_t* on, uint8_t* keep, void* ws, int64_t ws_bytes, void* stream) {
+  if (!boxes || !scores || !cls || !ob || !os || !oc || !on || !ws || ws_bytes < nms_workspace_bytes(batch, n))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_nms: bad arguments / workspace too small");
+  NmsWorkspace w = nms_carve(ws, batch, n);
+  UNIT_TRY(launch_nms(boxes, scores, cls, batch, n, num_classes, conf, thr, diou, ob, os, oc, on, keep, w,
+                      (cudaStream_t)stream));
+  return YNB_OK;
+}

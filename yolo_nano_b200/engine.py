@@ -188,6 +188,23 @@ class Engine:
                     "ynb_detect_host")
         return boxes, scores, cls, counts
 
+    def profile(self, x: torch.Tensor):
+        """One forward_detect with a CUDA-event pair around every kernel launch.
+        Returns [(label, kernel family, ms, algorithmic bytes, flops), ...]."""
+        self._check(self.lib.ynb_set_profiling(self._h, 1), "ynb_set_profiling")
+        try:
+            self.forward_detect(x)
+        finally:
+            self.lib.ynb_set_profiling(self._h, 0)
+        out = []
+        name, kind = C.c_char_p(), C.c_char_p()
+        ms, by, fl = C.c_float(), C.c_double(), C.c_double()
+        for i in range(self.lib.ynb_profile_count(self._h)):
+            self._check(self.lib.ynb_profile_entry(self._h, i, C.byref(name), C.byref(kind), C.byref(ms),
+                                                   C.byref(by), C.byref(fl)), "ynb_profile_entry")
+            out.append((name.value.decode(), kind.value.decode(), ms.value, by.value, fl.value))
+        return out
+
     def read_tap(self, name: str, batch: int) -> torch.Tensor:
         c, h, w = C.c_int32(), C.c_int32(), C.c_int32()
         self._check(self.lib.ynb_tap_shape(self._h, name.encode(), C.byref(c), C.byref(h), C.byref(w)),
