@@ -119,13 +119,16 @@ nms_keys_kernel(const float* __restrict__ scores, const int32_t* __restrict__ cl
 }
 
 // One CTA per image, bitonic network over Npad (power of two) keys.  Keys are unique
-// (anchor index in the low bits), so the network's instability is irrelevant.
+// (anchor index in the low bits), so the network's instability is irrelevant.  After the sort
+// the CTA also writes the class segment table seg[b][0..C]: class c owns sorted positions
+// [seg[c], seg[c+1]).
 template <bool IN_SMEM>
 __global__ void __launch_bounds__(1024)
-nms_sort_kernel(uint64_t* __restrict__ keys_g, int Npad) {
+nms_sort_kernel(uint64_t* __restrict__ keys_g, int32_t* __restrict__ seg_g, int Npad, int C) {
   extern __shared__ uint64_t s_keys[];
   uint64_t* g = keys_g + (int64_t)blockIdx.x * Npad;
   uint64_t* k = IN_SMEM ? s_keys : g;
+  int32_t* seg = seg_g + (int64_t)blockIdx.x * (C + 1);
   const int tid = threadIdx.x;
   if (IN_SMEM) {
     for (int i = tid; i < Npad; i += 1024) s_keys[i] = g[i];
@@ -143,8 +146,11 @@ nms_sort_kernel(uint64_t* __restrict__ keys_g, int Npad) {
       __syncthreads();
     }
   }
-  if (IN_SMEM) {
-    for (int i = tid; i < Npad; i += 1024) g[i] = s_keys[i];
+  for (int i = tid; i <= Npad; i += 1024) {
+    int ci = i < Npad ? min(key_cls(k[i]), C) : C;          // virtual sentinel of class C at the end
+    int cp = i > 0 ? min(key_cls(k[i - 1]), C) : -1;
+    for (int c = cp + 1; c <= ci; ++c) seg[c] = i;
+    if (IN_SMEM && i < Npad) g[i] = k[i];
   }
 }
 
@@ -166,13 +172,29 @@ __device__ __forceinline__ float box_area(float4 b) {
 }
 
 // true when kept box `a` suppresses candidate `b`:  NOT (ovr <= thr)   (:185, NaN suppresses)
+//
+// The reference decision is RN(inter / union) <= thr.  Almost every pair is far from the
+// threshold, so it is decided without the IEEE division: with q = inter/union exact,
+//   inter < thr*union*(1-1e-6)  =>  q < thr*(1-8e-7)  =>  RN(q) <= thr      (keep)
+//   inter > thr*union*(1+1e-6)  =>  q > thr*(1+8e-7)  =>  RN(q) >  thr      (suppress)
+// (the two fp32 roundings of the right-hand side cost < 2.4e-7 relative; the next float
+// above thr is at most thr*(1+2.4e-7) away).  Everything else — the 2e-6 band around the
+// threshold, zero / negative / non-finite unions — takes the exact path, so the result is
+// bit-identical to the NumPy loop.  The division's slow path (tiny numerators of
+// non-overlapping pairs, inter ~ 1e-28*h) is what made the exact test expensive.
 __device__ __forceinline__ bool suppresses(float4 a, float area_a, float4 b, float area_b, IouOps op) {
   float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
   float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
   float w = fmaxf(1e-28f, __fsub_rn(xx2, xx1));
   float h = fmaxf(1e-28f, __fsub_rn(yy2, yy1));
   float inter = __fmul_rn(w, h);
-  float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  if (!op.diou && uni > 1e-20f && uni < 4.0f) {
+    float tu = __fmul_rn(op.thr, uni);
+    if (inter < __fmul_rn(tu, 0.999999f)) return false;
+    if (inter > __fmul_rn(tu, 1.000001f)) return true;
+  }
+  float ovr = __fdiv_rn(inter, uni);
   if (op.diou) {   // models/yolo_nano.py:216-237
     float cw = __fsub_rn(fmaxf(fmaxf(a.x, a.z), fmaxf(b.x, b.z)), fminf(fminf(a.x, a.z), fminf(b.x, b.z)));
     float ch = __fsub_rn(fmaxf(fmaxf(a.y, a.w), fmaxf(b.y, b.w)), fminf(fminf(a.y, a.w), fminf(b.y, b.w)));
@@ -187,75 +209,86 @@ __device__ __forceinline__ bool suppresses(float4 a, float area_a, float4 b, flo
   return !(ovr <= op.thr);
 }
 
-constexpr int kNmsChunk = 64;
-constexpr int kNmsThreads = 256;
-constexpr int kNmsMaxWords = 2048;   // 65536 candidates per segment
-
-__device__ __forceinline__ int lower_bound_key(const uint64_t* k, int n, uint64_t v) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (k[mid] < v) lo = mid + 1; else hi = mid;
-  }
-  return lo;
+// 8x8 occupancy mask of a box on the unit square (closed cell ranges): two boxes whose masks
+// do not intersect are disjoint, so w or h is clamped to 1e-28, ovr <= 1e-16 and the pair
+// can never suppress — unless an area is ~0 (0/0 = NaN suppresses, SURVEY hazard 3) or a
+// coordinate is not finite; such boxes get the all-ones mask and always take the full test.
+__device__ __forceinline__ unsigned long long coarse_mask(float4 b, float area) {
+  if (!(area > 1e-12f) || !(b.x >= 0.f && b.y >= 0.f && b.z <= 1.f && b.w <= 1.f)) return ~0ull;
+  int cx1 = min(7, (int)(b.x * 8.f)), cx2 = min(7, (int)(b.z * 8.f));
+  int cy1 = min(7, (int)(b.y * 8.f)), cy2 = min(7, (int)(b.w * 8.f));
+  unsigned long long row = (unsigned long long)((2u << cx2) - (1u << cx1)) & 0xffull;
+  unsigned long long m = 0ull;
+#pragma unroll
+  for (int cy = 0; cy < 8; ++cy)
+    if (cy >= cy1 && cy <= cy2) m |= row << (8 * cy);
+  return m;
 }
 
+constexpr int kNmsChunk = 64;
+constexpr int kNmsThreads = 512;
+constexpr int kNmsMaxWords = 1024;   // 65536 candidates per segment, 64 per word
+
 __global__ void __launch_bounds__(kNmsThreads)
-nms_segment_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ boxes,
-                   float4* sbox_scratch, uint8_t* __restrict__ keep, int64_t N, int Npad, IouOps op) {
-  __shared__ uint32_t s_removed[kNmsMaxWords];
+nms_segment_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ seg,
+                   const float* __restrict__ boxes, float4* sbox_scratch, uint8_t* __restrict__ keep,
+                   int64_t N, int Npad, int C, IouOps op) {
+  __shared__ unsigned long long s_removed[kNmsMaxWords];
   __shared__ float4 s_cbox[kNmsChunk];
   __shared__ float s_carea[kNmsChunk];
-  __shared__ unsigned long long s_mask[kNmsChunk];
+  __shared__ unsigned long long s_cmask[kNmsChunk];   // coarse occupancy masks of the chunk
+  __shared__ unsigned long long s_mask[kNmsChunk];    // in-chunk suppression rows
   __shared__ int s_kept[kNmsChunk];
   __shared__ int s_nkept;
-  __shared__ int s_range[2];
 
   const int b = blockIdx.y, c = blockIdx.x, tid = threadIdx.x;
-  const uint64_t* k = keys + (int64_t)b * Npad;
-  if (tid < 2) s_range[tid] = lower_bound_key(k, Npad, (uint64_t)(c + tid) << 48);
-  __syncthreads();
-  const int s0 = s_range[0], n = s_range[1] - s_range[0];
+  const int s0 = seg[(int64_t)b * (C + 1) + c];
+  const int n = seg[(int64_t)b * (C + 1) + c + 1] - s0;
   if (n <= 0) return;
+  const uint64_t* k = keys + (int64_t)b * Npad;
   const float4* bx = reinterpret_cast<const float4*>(boxes) + (int64_t)b * N;
   float4* sb = sbox_scratch + (int64_t)b * Npad + s0;
   uint8_t* kp = keep + (int64_t)b * N;
+  const bool use_masks = op.thr >= 1e-6f;
 
   // gather the segment's boxes in visiting order (coalesced from here on)
   for (int j = tid; j < n; j += kNmsThreads) sb[j] = bx[key_idx(k[s0 + j])];
-  for (int j = tid; j < (n + 31) / 32; j += kNmsThreads) s_removed[j] = 0;
+  for (int j = tid; j < (n + 63) / 64; j += kNmsThreads) s_removed[j] = 0ull;
   __syncthreads();
 
   for (int c0 = 0; c0 < n; c0 += kNmsChunk) {
     const int cn = min(kNmsChunk, n - c0);
     if (tid < kNmsChunk) {
       float4 v = tid < cn ? sb[c0 + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
+      float a = box_area(v);
       s_cbox[tid] = v;
-      s_carea[tid] = box_area(v);
-      s_mask[tid] = 0ull;
+      s_carea[tid] = a;
+      s_cmask[tid] = use_masks ? coarse_mask(v, a) : ~0ull;
     }
     __syncthreads();
-    // (1) in-chunk mask: thread -> (row, 16-column quarter)
+    // (1) in-chunk mask: thread -> (row, 8-column octet); octets of a row sit in adjacent lanes
     {
-      int row = tid >> 2, q = tid & 3;
+      int row = tid >> 3, q = tid & 7;
       unsigned long long bits = 0ull;
       if (row < cn) {
         float4 a = s_cbox[row];
         float aa = s_carea[row];
-        for (int j = q * 16; j < q * 16 + 16; ++j)
-          if (j > row && j < cn && suppresses(a, aa, s_cbox[j], s_carea[j], op)) bits |= 1ull << j;
+        unsigned long long am = s_cmask[row];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          int j = q * 8 + e;
+          if (j > row && j < cn && (am & s_cmask[j]) && suppresses(a, aa, s_cbox[j], s_carea[j], op)) bits |= 1ull << j;
+        }
       }
-      // combine the four quarters of a row (adjacent lanes)
       bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
       bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
-      if (q == 0 && row < cn) s_mask[row] = bits;
+      bits |= __shfl_xor_sync(0xffffffffu, bits, 4);
+      if (q == 0) s_mask[row] = bits;
     }
     __syncthreads();
-    // (2) serial resolve of the chunk
+    // (2) serial resolve of the chunk (c0 is a multiple of 64: one word of the removed set)
     if (tid == 0) {
-      unsigned long long rem = 0ull;
-      for (int j = 0; j < cn; ++j)
-        if ((s_removed[(c0 + j) >> 5] >> ((c0 + j) & 31)) & 1u) rem |= 1ull << j;
+      unsigned long long rem = s_removed[c0 >> 6];
       int nk = 0;
       for (int j = 0; j < cn; ++j) {
         if (!((rem >> j) & 1ull)) {
@@ -270,13 +303,14 @@ nms_segment_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ 
     if (tid < nk) kp[key_idx(k[s0 + c0 + s_kept[tid]])] = 1;
     // (3) kept boxes of this chunk against all later candidates
     for (int j = c0 + kNmsChunk + tid; j < n; j += kNmsThreads) {
-      if ((s_removed[j >> 5] >> (j & 31)) & 1u) continue;
+      if ((s_removed[j >> 6] >> (j & 63)) & 1ull) continue;
       float4 v = sb[j];
       float va = box_area(v);
+      unsigned long long vm = use_masks ? coarse_mask(v, va) : ~0ull;
       for (int q = 0; q < nk; ++q) {
         int r = s_kept[q];
-        if (suppresses(s_cbox[r], s_carea[r], v, va, op)) {
-          atomicOr(&s_removed[j >> 5], 1u << (j & 31));
+        if ((vm & s_cmask[r]) && suppresses(s_cbox[r], s_carea[r], v, va, op)) {
+          atomicOr(&s_removed[j >> 6], 1ull << (j & 63));
           break;
         }
       }
@@ -342,11 +376,14 @@ inline int nms_npad(int64_t n) {
 struct NmsWorkspace {
   uint64_t* keys;     // [B][Npad]
   float4* sbox;       // [B][Npad]
+  int32_t* seg;       // [B][257] class segment starts
   uint8_t* keep;      // [B][N]
 };
+constexpr int kNmsSegStride = 257;
 inline int64_t nms_workspace_bytes(int batch, int64_t n) {
   int64_t npad = nms_npad(n);
-  return (int64_t)batch * npad * 8 + (int64_t)batch * npad * 16 + round_up64((int64_t)batch * n, 256) + 512;
+  return (int64_t)batch * npad * 8 + (int64_t)batch * npad * 16 + round_up64((int64_t)batch * kNmsSegStride * 4, 256) +
+         round_up64((int64_t)batch * n, 256) + 512;
 }
 inline NmsWorkspace nms_carve(void* ws, int batch, int64_t n) {
   int64_t npad = nms_npad(n);
@@ -354,6 +391,7 @@ inline NmsWorkspace nms_carve(void* ws, int batch, int64_t n) {
   NmsWorkspace w;
   w.sbox = reinterpret_cast<float4*>(p); p += (int64_t)batch * npad * 16;
   w.keys = reinterpret_cast<uint64_t*>(p); p += (int64_t)batch * npad * 8;
+  w.seg = reinterpret_cast<int32_t*>(p); p += round_up64((int64_t)batch * kNmsSegStride * 4, 256);
   w.keep = reinterpret_cast<uint8_t*>(p);
   return w;
 }
@@ -382,16 +420,16 @@ inline cudaError_t launch_nms(const float* boxes, const float* scores, const int
         if (e != cudaSuccess) return e;
         attr_set = true;
       }
-      nms_sort_kernel<true><<<batch, 1024, smem, st>>>(w.keys, Npad);
+      nms_sort_kernel<true><<<batch, 1024, smem, st>>>(w.keys, w.seg, Npad, num_classes);
     } else {
-      nms_sort_kernel<false><<<batch, 1024, 0, st>>>(w.keys, Npad);
+      nms_sort_kernel<false><<<batch, 1024, 0, st>>>(w.keys, w.seg, Npad, num_classes);
     }
     YNB_COUNT_LAUNCH();
   }
   {
     dim3 grid(num_classes, batch);
     IouOps op{thr, diou != 0};
-    nms_segment_kernel<<<grid, kNmsThreads, 0, st>>>(w.keys, boxes, w.sbox, keep, N, Npad, op);
+    nms_segment_kernel<<<grid, kNmsThreads, 0, st>>>(w.keys, w.seg, boxes, w.sbox, keep, N, Npad, num_classes, op);
     YNB_COUNT_LAUNCH();
   }
   nms_compact_kernel<<<batch, 1024, 0, st>>>(keep, boxes, scores, cls, out_boxes, out_scores, out_cls,

@@ -8,11 +8,18 @@
 //   warp 0      TMA producer      A chunk (+ W chunk when W is streamed) -> smem stage
 //   warp 1      MMA issuer        tcgen05.mma kind::tf32, one elected lane; owns TMEM alloc
 //   warps 2-5   splitters         fp32 parity mode only: A -> (A_hi, A_lo) in smem
-//   warps 6-9   epilogue          TMEM -> regs -> bias/act -> global (plain / interleaved)
+//   warps 6-9   epilogue          TMEM -> regs -> bias/act -> global (plain / slot-mapped)
 //
 // fp32 parity mode (YNB_GEMM_TC_3XTF32): a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi with
-// x_hi = x & 0xffffe000 (exact tf32), x_lo = tf32(x - x_hi): three MMAs per K step, fp32
-// accumulation in TMEM, relative error ~2^-21 per product (vs 2^-11 for one tf32 pass).
+// x_hi = RN_tf32(x), x_lo = RN_tf32(x - x_hi): three MMAs per K step.  Measured on B200
+// (tools/gpu_accum_probe.py, profiles/):
+//   * a truncating split (x & 0xffffe000) leaves a -2.7e-7 relative bias and 4.4e-7 rms
+//     (the dropped a_lo*b_lo term is then one-signed); round-to-nearest makes the split
+//     unbiased with 9.5e-8 rms — hence RN;
+//   * the tensor core TRUNCATES when it adds into the accumulator: bias ~ -0.4 ulp per
+//     accumulation step (K=464: -2.9e-6 on one-signed sums, FFMA: 1e-9).  So the exact
+//     main products a_hi*b_hi are spread round-robin over `nmain` TMEM accumulators and the
+//     two correction products get their own; the epilogue adds them in fp32 (RN).
 // W_hi / W_lo are split once at weight-pack time; A is split in shared memory by the
 // splitter warps, position-wise on the swizzled bytes (no layout knowledge needed).
 //
@@ -20,6 +27,8 @@
 // (dx-1, dy-1); out-of-bounds elements are zero-filled by TMA = the conv's zero padding.
 #pragma once
 #include <cuda.h>
+
+#include <cstring>
 
 #include "common.cuh"
 #include "ptx_sm100.cuh"
@@ -32,6 +41,7 @@ constexpr int kTcBK = 32;                       // floats per K chunk = 128 byte
 constexpr int kTcAStageBytes = kTcBM * 128;     // 16 KB
 constexpr int kTcMaxStages = 8;
 constexpr int kTcSmemBudget = 220 * 1024;
+constexpr int kTcMaxMain = 4;
 
 struct TcGemmParams {
   int num_steps;          // K chunks per tile (pointwise: ceil(K/32); 3x3: 9 * C/32)
@@ -44,7 +54,10 @@ struct TcGemmParams {
   int64_t num_tiles;
   int H, W, TH, TW, tiles_x, tiles_y;   // 3x3 spatial tiling
   int N, Npad;
-  uint32_t tmem_cols;     // power of two >= 2*Npad
+  int nmain;              // main accumulators (round-robin over K steps), 1..4
+  int nacc;               // accumulators per stage = nmain + (parity mode ? 1 correction : 0)
+  int acc_stages;         // TMEM accumulator stages (2 = epilogue overlaps the next tile's MMAs)
+  uint32_t tmem_cols;     // power of two >= acc_stages * nacc * Npad
   uint32_t a_box_bytes;   // bytes one A TMA box delivers
   // epilogue
   float* out;
@@ -52,8 +65,6 @@ struct TcGemmParams {
   ChanMap omap;
   const float* bias;
   int act;
-  const float* pass;      // pass-through half for the shuffle interleave, or nullptr
-  int pass_ld;
   int* err_flag;
 };
 
@@ -61,11 +72,13 @@ struct TcSmemLayout {
   uint32_t stage_bytes;    // A | A_lo | (W_hi | W_lo when streamed)
   uint32_t w_chunk_bytes;  // Npad * 128
   uint32_t w_res_off;      // offset of the resident W region
+  uint32_t bias_off;
   uint32_t bar_off;
   uint32_t total;
 };
 
-inline TcSmemLayout tc_smem_layout(int Npad, int num_steps, int num_stages, bool w_resident, bool split) {
+__host__ __device__ inline TcSmemLayout tc_smem_layout(int Npad, int num_steps, int num_stages, bool w_resident,
+                                                       bool split) {
   TcSmemLayout L;
   L.w_chunk_bytes = (uint32_t)Npad * 128;
   uint32_t a_bytes = kTcAStageBytes * (split ? 2 : 1);
@@ -73,10 +86,14 @@ inline TcSmemLayout tc_smem_layout(int Npad, int num_steps, int num_stages, bool
   L.stage_bytes = a_bytes + w_bytes;                      // all multiples of 1024
   L.w_res_off = L.stage_bytes * num_stages;
   uint32_t w_res = w_resident ? L.w_chunk_bytes * (split ? 2 : 1) * num_steps : 0;
-  L.bar_off = L.w_res_off + w_res;
+  L.bias_off = L.w_res_off + w_res;
+  L.bar_off = L.bias_off + 1024;                          // bias: up to 256 floats
   L.total = L.bar_off + 256 + 1024;                       // barriers + slack for 1024-B alignment
   return L;
 }
+
+// round-to-nearest (ties away) to TF32 on the raw bits; exact for values already in TF32
+__host__ __device__ __forceinline__ uint32_t rn_tf32_bits(uint32_t u) { return (u + 0x1000u) & 0xffffe000u; }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWhi,
@@ -85,18 +102,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
   const bool split = p.mode == YNB_GEMM_TC_3XTF32;
-  const uint32_t w_chunk_bytes = (uint32_t)p.Npad * 128;
+  const TcSmemLayout lay = tc_smem_layout(p.Npad, p.num_steps, p.num_stages, p.w_resident != 0, split);
+  const uint32_t w_chunk_bytes = lay.w_chunk_bytes;
   const uint32_t a_bytes = kTcAStageBytes * (split ? 2 : 1);
-  const uint32_t stage_bytes = a_bytes + (p.w_resident ? 0 : w_chunk_bytes * (split ? 2 : 1));
-  const uint32_t w_res_off = stage_bytes * p.num_stages;
-  const uint32_t w_res_bytes = p.w_resident ? w_chunk_bytes * (split ? 2 : 1) * p.num_steps : 0;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + w_res_off + w_res_bytes);
-  uint64_t* full = bars;                         // [kTcMaxStages]
-  uint64_t* ready = bars + kTcMaxStages;         // [kTcMaxStages]
-  uint64_t* empty = bars + 2 * kTcMaxStages;     // [kTcMaxStages]
-  uint64_t* tmem_full = bars + 3 * kTcMaxStages;     // [2]
-  uint64_t* tmem_empty = bars + 3 * kTcMaxStages + 2; // [2]
-  uint64_t* w_full = bars + 3 * kTcMaxStages + 4;     // [1]
+  const uint32_t stage_bytes = lay.stage_bytes;
+  const uint32_t w_res_bytes = lay.bias_off - lay.w_res_off;
+  float* s_bias = reinterpret_cast<float*>(smem + lay.bias_off);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_off);
+  uint64_t* full = bars;                         // [kTcMaxStages]  TMA landed
+  uint64_t* ready = bars + kTcMaxStages;         // [kTcMaxStages]  A split done (parity mode)
+  uint64_t* empty = bars + 2 * kTcMaxStages;     // [kTcMaxStages]  MMAs retired, stage reusable
+  uint64_t* tmem_full = bars + 3 * kTcMaxStages;       // [2]
+  uint64_t* tmem_empty = bars + 3 * kTcMaxStages + 2;  // [2]
+  uint64_t* w_full = bars + 3 * kTcMaxStages + 4;      // [1]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * kTcMaxStages + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -107,12 +125,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (split) ptx::prefetch_tmap(&tmWlo);
     for (int s = 0; s < p.num_stages; ++s) {
       ptx::mbar_init(&full[s], 1);
-      ptx::mbar_init(&ready[s], 128);
+      ptx::mbar_init(&ready[s], 4);      // one arrival per splitter warp
       ptx::mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], 128);
+      ptx::mbar_init(&tmem_empty[a], 4); // one arrival per epilogue warp
     }
     ptx::mbar_init(w_full, 1);
     ptx::fence_barrier_init();
@@ -120,6 +138,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     ptx::tmem_alloc(tmem_ptr, p.tmem_cols);
     ptx::tmem_relinquish();
+  }
+  if (warp >= 6) {   // epilogue warps stage the bias once (no global latency inside the tile loop)
+    for (int i = threadIdx.x - 192; i < p.Npad; i += 128) s_bias[i] = i < p.N ? __ldg(p.bias + i) : 0.0f;
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -129,11 +150,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto stage_a = [&](int s) { return smem + (size_t)s * stage_bytes; };
   auto stage_alo = [&](int s) { return smem + (size_t)s * stage_bytes + kTcAStageBytes; };
   auto w_hi_ptr = [&](int s, int step) {
-    return p.w_resident ? smem + w_res_off + (size_t)step * w_chunk_bytes * (split ? 2 : 1)
+    return p.w_resident ? smem + lay.w_res_off + (size_t)step * w_chunk_bytes * (split ? 2 : 1)
                         : smem + (size_t)s * stage_bytes + a_bytes;
   };
   auto w_lo_ptr = [&](int s, int step) { return w_hi_ptr(s, step) + w_chunk_bytes; };
 
+  const int acc_cols = p.Npad * p.nacc;   // TMEM columns per accumulator stage
   const uint32_t step_tx = p.a_box_bytes + (p.w_resident ? 0 : w_chunk_bytes * (split ? 2 : 1));
 
   if (warp == 0) {
@@ -191,7 +213,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ok = ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1, p.err_flag, 3);
         if (!ok) break;
         ptx::tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Npad);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
+        const uint32_t c_tmem = d_tmem + (uint32_t)(p.nmain * p.Npad);   // correction accumulator
+        int t = 0;                                                       // K-step counter of the tile
         for (int st = 0; st < p.num_steps; ++st) {
           ok = ptx::mbar_wait(split ? &ready[s] : &full[s], ph, p.err_flag, 4);
           if (!ok) break;
@@ -201,24 +225,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t b_hi = ptx::smem_u32(w_hi_ptr(s, st));
           const uint32_t b_lo = ptx::smem_u32(w_lo_ptr(s, st));
 #pragma unroll
-          for (int k = 0; k < kTcBK / 8; ++k) {
+          for (int k = 0; k < kTcBK / 8; ++k, ++t) {
             const uint32_t ko = k * 32;   // 8 tf32 = 32 bytes inside the 128-byte swizzled row
             const uint64_t da = ptx::make_sw128_kmajor_desc(a_hi + ko);
             const uint64_t db = ptx::make_sw128_kmajor_desc(b_hi + ko);
+            const int slot = t % p.nmain;
             if (split) {
-              // small terms first, then the main product
-              ptx::mma_tf32_ss(d_tmem, ptx::make_sw128_kmajor_desc(a_lo + ko), db, idesc, (st | k) != 0);
-              ptx::mma_tf32_ss(d_tmem, da, ptx::make_sw128_kmajor_desc(b_lo + ko), idesc, 1);
-              ptx::mma_tf32_ss(d_tmem, da, db, idesc, 1);
-            } else {
-              ptx::mma_tf32_ss(d_tmem, da, db, idesc, (st | k) != 0);
+              ptx::mma_tf32_ss(c_tmem, ptx::make_sw128_kmajor_desc(a_lo + ko), db, idesc, t != 0);
+              ptx::mma_tf32_ss(c_tmem, da, ptx::make_sw128_kmajor_desc(b_lo + ko), idesc, 1);
             }
+            ptx::mma_tf32_ss(d_tmem + (uint32_t)(slot * p.Npad), da, db, idesc, t >= p.nmain);
           }
           ptx::mma_commit(&empty[s]);                       // frees the smem stage when the MMAs retire
           if (st == p.num_steps - 1) ptx::mma_commit(&tmem_full[acc]);
           if (++s == p.num_stages) { s = 0; ph ^= 1; }
         }
-        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1; }
       }
     }
   } else if (warp < 6) {
@@ -236,18 +258,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint4* lo = reinterpret_cast<uint4*>(stage_alo(s));
 #pragma unroll
           for (int i = 0; i < kTcAStageBytes / 16 / 128; ++i) {
-            uint4 v = a[t + i * 128];
+            const uint4 v = a[t + i * 128];
             uint4 h, l;
-            h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
-            l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)) & 0xffffe000u;
-            l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)) & 0xffffe000u;
-            l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) & 0xffffe000u;
-            l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) & 0xffffe000u;
+            h.x = rn_tf32_bits(v.x); h.y = rn_tf32_bits(v.y); h.z = rn_tf32_bits(v.z); h.w = rn_tf32_bits(v.w);
+            l.x = rn_tf32_bits(__float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)));
+            l.y = rn_tf32_bits(__float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)));
+            l.z = rn_tf32_bits(__float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)));
+            l.w = rn_tf32_bits(__float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)));
             a[t + i * 128] = h;
             lo[t + i * 128] = l;
           }
-          ptx::fence_proxy_async_smem();
-          ptx::mbar_arrive(&ready[s]);
+          ptx::fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&ready[s]);
           if (++s == p.num_stages) { s = 0; ph ^= 1; }
         }
       }
@@ -259,6 +282,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_ph = 0;
     bool ok = true;
+    const bool vec = p.out_step == 1 && p.omap.gap == 0;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
       // row -> output pixel
       int64_t m;
@@ -278,38 +302,33 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ok = ptx::mbar_wait(&tmem_full[acc], acc_ph, p.err_flag, 6);
       if (!ok) break;
       ptx::tc_fence_after_sync();
-      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Npad);
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_cols);
       float* orow = p.out + m * p.out_ld;
-      const float* prow = p.pass ? p.pass + m * p.pass_ld : nullptr;
       for (int c0 = 0; c0 < p.Npad; c0 += 16) {
         uint32_t r[16];
         ptx::tmem_ld_32x16(t_base + c0, r);
-        ptx::tmem_ld_wait();
-        if (c0 + 16 >= p.Npad) {   // last block read: hand the accumulator back to the MMA warp
+        if (p.nacc > 1) {
+          // sum the accumulators in fp32: main_0 + main_1 + ... + correction (smallest last)
+          for (int a = 1; a < p.nacc; ++a) {
+            uint32_t r2[16];
+            ptx::tmem_ld_32x16(t_base + (uint32_t)(a * p.Npad) + c0, r2);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+          }
+        } else {
+          ptx::tmem_ld_wait();
+        }
+        if (c0 + 16 >= p.Npad) {   // last block read: hand the accumulator stage back to the MMA warp
           ptx::tc_fence_before_sync();
-          ptx::mbar_arrive(&tmem_empty[acc]);
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
         }
         if (!valid) continue;
         float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          int n = c0 + j;
-          v[j] = n < p.N ? apply_act(__uint_as_float(r[j]) + __ldg(p.bias + n), p.act) : 0.0f;
-        }
-        if (prow != nullptr) {
-          // channel shuffle as a store permutation: slot(2n) <- pass-through, slot(2n+1) <- branch
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            int n = c0 + j;
-            if (n >= p.N) break;
-            float4 x1 = *reinterpret_cast<const float4*>(prow + n);
-            const float xs[4] = {x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (n + e < p.N)
-                *reinterpret_cast<float2*>(orow + p.omap.slot(2 * (n + e))) = make_float2(xs[e], v[j + e]);
-          }
-        } else if (p.out_step == 1 && p.omap.gap == 0) {
+        for (int j = 0; j < 16; ++j) v[j] = apply_act(__uint_as_float(r[j]) + s_bias[c0 + j], p.act);
+        if (vec) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             int n = c0 + j;
@@ -322,12 +341,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         } else {
+          // channel split / concat / shuffle as a store permutation (slot map + stride)
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             if (c0 + j < p.N) orow[p.omap.slot(p.out_off + (c0 + j) * p.out_step)] = v[j];
         }
       }
-      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1; }
     }
   }
 
@@ -399,13 +419,13 @@ struct TcWeights {
 inline void split_tf32_host(float v, float* hi, float* lo) {
   uint32_t u;
   memcpy(&u, &v, 4);
-  uint32_t h = u & 0xffffe000u;
+  uint32_t h = rn_tf32_bits(u);
   float hf;
   memcpy(&hf, &h, 4);
   float l = v - hf;
   uint32_t lu;
   memcpy(&lu, &l, 4);
-  lu &= 0xffffe000u;
+  lu = rn_tf32_bits(lu);
   memcpy(lo, &lu, 4);
   *hi = hf;
 }
@@ -418,6 +438,32 @@ struct TcGemmLaunch {
   uint32_t smem = 0;
   unsigned grid = 0;
 };
+
+// TMEM plan (512 columns).  Parity mode: one correction accumulator plus `nmain` main
+// accumulators — more of them the deeper K is (truncation bias grows with the number of
+// accumulation steps).  Two accumulator stages (epilogue of tile i overlaps the MMAs of tile
+// i+1) whenever they fit; a shallow K gives up an extra main accumulator for that overlap, a
+// deep K (3x3 convs: 108 steps, K=464 laterals) keeps the accumulators and runs single-stage.
+inline void tc_plan_tmem(TcGemmParams& p) {
+  const bool split = p.mode == YNB_GEMM_TC_3XTF32;
+  const int corr = split ? 1 : 0;
+  int want = 1;
+  if (split) {
+    const int ksteps = p.num_steps * (kTcBK / 8);
+    want = ksteps >= 64 ? 4 : (ksteps >= 24 ? 3 : (ksteps >= 12 ? 2 : 1));
+  }
+  p.nmain = want;
+  while (p.nmain > 1 && (p.nmain + corr) * p.Npad > 512) p.nmain--;
+  p.nacc = p.nmain + corr;
+  p.acc_stages = 2 * p.nacc * p.Npad <= 512 ? 2 : 1;
+  if (p.acc_stages == 1 && want <= 2 && p.nmain > 1 && 2 * (p.nmain - 1 + corr) * p.Npad <= 512) {
+    p.nmain--;
+    p.nacc--;
+    p.acc_stages = 2;
+  }
+  p.tmem_cols = 32;
+  while ((int)p.tmem_cols < p.acc_stages * p.nacc * p.Npad) p.tmem_cols <<= 1;
+}
 
 // Picks stages / residency for the smem budget.  Returns false if nothing fits.
 inline bool tc_plan_smem(TcGemmLaunch& L) {

@@ -20,14 +20,21 @@ constexpr int kStemConv = 2 * kStemTile + 1;   // 17
 constexpr int kStemIn = 2 * kStemConv + 1;     // 35
 constexpr int kStemInPitch = 36;
 constexpr int kStemC = 24;
+constexpr int kStemThreads = 320;              // 289 conv positions of a tile, one per thread
 
-__global__ void __launch_bounds__(256)
-stem_pool_kernel(const float* __restrict__ x, float* __restrict__ out,
-                 const float* __restrict__ w, const float* __restrict__ bias, int S) {
+// Folded stem weights travel as a kernel parameter: they then live in the constant bank
+// and every FFMA takes its weight operand straight from c[0][..] (warp-uniform, no
+// shared-memory traffic) — the conv is FMA-bound instead of LDS-bound.
+struct StemWeights {
+  float w[27][kStemC];   // [(ci*3+ky)*3+kx][co]
+  float b[kStemC];
+};
+
+__global__ void __launch_bounds__(kStemThreads)
+stem_pool_kernel(const float* __restrict__ x, float* __restrict__ out, const __grid_constant__ StemWeights wt,
+                 int S) {
   __shared__ float s_in[3][kStemIn][kStemInPitch];
   __shared__ float s_conv[kStemConv * kStemConv][kStemC + 1];
-  __shared__ float s_w[27 * kStemC];
-  __shared__ float s_b[kStemC];
 
   const int Hc = S / 2, Hp = S / 4;
   const int b = blockIdx.z;
@@ -36,10 +43,8 @@ stem_pool_kernel(const float* __restrict__ x, float* __restrict__ out,
   const int iy0 = 2 * cy0 - 1, ix0 = 2 * cx0 - 1;   // first input row / col
   const int tid = threadIdx.x;
 
-  for (int i = tid; i < 27 * kStemC; i += 256) s_w[i] = w[i];
-  if (tid < kStemC) s_b[tid] = bias[tid];
   const float* xb = x + (size_t)b * 3 * S * S;
-  for (int i = tid; i < 3 * kStemIn * kStemIn; i += 256) {
+  for (int i = tid; i < 3 * kStemIn * kStemIn; i += kStemThreads) {
     int c = i / (kStemIn * kStemIn);
     int r = (i / kStemIn) % kStemIn;
     int q = i % kStemIn;
@@ -50,30 +55,30 @@ stem_pool_kernel(const float* __restrict__ x, float* __restrict__ out,
   }
   __syncthreads();
 
-  // conv: (position, channel) pairs; consecutive threads take consecutive channels so the
-  // weight reads are conflict-free and the input reads broadcast.
-  for (int i = tid; i < kStemConv * kStemConv * kStemC; i += 256) {
-    int co = i % kStemC;
-    int p = i / kStemC;
-    int r = p / kStemConv, q = p % kStemConv;
-    int cy = cy0 + r, cx = cx0 + q;
-    float acc = 0.0f;
-    if (cy >= 0 && cy < Hc && cx >= 0 && cx < Hc) {
-      acc = s_b[co];
+  // conv + bias + ReLU: one thread per conv position, all 24 output channels in registers
+  if (tid < kStemConv * kStemConv) {
+    const int r = tid / kStemConv, q = tid % kStemConv;
+    const int cy = cy0 + r, cx = cx0 + q;
+    float acc[kStemC];
 #pragma unroll
-      for (int ci = 0; ci < 3; ++ci)
+    for (int co = 0; co < kStemC; ++co) acc[co] = wt.b[co];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+    for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx)
-            acc = fmaf(s_in[ci][2 * r + ky][2 * q + kx], s_w[(ci * 9 + ky * 3 + kx) * kStemC + co], acc);
-      acc = fmaxf(acc, 0.0f);
-    }
-    s_conv[p][co] = acc;
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float v = s_in[ci][2 * r + ky][2 * q + kx];
+#pragma unroll
+          for (int co = 0; co < kStemC; ++co) acc[co] = fmaf(v, wt.w[(ci * 3 + ky) * 3 + kx][co], acc[co]);
+        }
+    const bool inside = cy >= 0 && cy < Hc && cx >= 0 && cx < Hc;
+#pragma unroll
+    for (int co = 0; co < kStemC; ++co) s_conv[tid][co] = inside ? fmaxf(acc[co], 0.0f) : 0.0f;
   }
   __syncthreads();
 
-  for (int i = tid; i < kStemTile * kStemTile * kStemC; i += 256) {
+  for (int i = tid; i < kStemTile * kStemTile * kStemC; i += kStemThreads) {
     int co = i % kStemC;
     int p = i / kStemC;
     int r = p / kStemTile, q = p % kStemTile;
@@ -89,11 +94,12 @@ stem_pool_kernel(const float* __restrict__ x, float* __restrict__ out,
   }
 }
 
-inline cudaError_t launch_stem_pool(const float* x, float* out, const float* w, const float* b,
-                                    int batch, int S, cudaStream_t st) {
+// w: [27][24] device or host floats are copied into the parameter block by the caller.
+inline cudaError_t launch_stem_pool(const float* x, float* out, const StemWeights& wt, int batch, int S,
+                                    cudaStream_t st) {
   int Hp = S / 4;
   dim3 grid((Hp + kStemTile - 1) / kStemTile, (Hp + kStemTile - 1) / kStemTile, batch);
-  stem_pool_kernel<<<grid, 256, 0, st>>>(x, out, w, b, S);
+  stem_pool_kernel<<<grid, kStemThreads, 0, st>>>(x, out, wt, S);
   YNB_COUNT_LAUNCH();
   return cudaGetLastError();
 }

@@ -43,18 +43,19 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   return t;
 }
 // Bounded wait: a wrong descriptor / byte count must fail loudly, not hang the GPU box.
-// Gives up after ~2 s of wall time and records `code` in the global error word the host
-// checks after the launch.
+// try_wait suspends in hardware until the phase completes or a time slice expires, so the
+// loop costs nothing while waiting; the wall clock is only consulted every 4096 slices and
+// the wait gives up after ~2 s, recording `code` in the error word the host reads.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* timeout_flag, int code) {
-  if (mbar_try_wait(bar, parity)) return true;
-  const uint64_t t0 = globaltimer_ns();
+  uint64_t t0 = 0;
 #pragma unroll 1
-  for (;;) {
-#pragma unroll 1
-    for (int spin = 0; spin < 256; ++spin)
-      if (mbar_try_wait(bar, parity)) return true;
-    if (globaltimer_ns() - t0 > 2000000000ull) break;
-    if (timeout_flag && *reinterpret_cast<volatile int*>(timeout_flag) != 0) break;   // someone else gave up
+  for (uint32_t spin = 0;; ++spin) {
+    if (mbar_try_wait(bar, parity)) return true;
+    if ((spin & 4095u) == 4095u) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) break;
+    }
   }
   if (timeout_flag) atomicCAS(timeout_flag, 0, code);
   return false;
@@ -165,6 +166,11 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Named barrier among a subset of warps (id 1..15; 0 is __syncthreads).
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 __device__ __forceinline__ bool elect_one() {

@@ -284,7 +284,10 @@ class YOLONano(nn.Module):
         res = []
         for b in range(x.shape[0]):
             k = int(counts_h[b])
-            res.append((boxes[b, :k].cpu().numpy(), scores[b, :k].cpu().numpy(),
+            # owned, writable host arrays: callers rescale boxes in place
+            # (evaluator/cocoapi_evaluator.py:85-87, test.py:133-135)
+            res.append((np.array(boxes[b, :k].cpu().numpy(), dtype=np.float32, copy=True),
+                        np.array(scores[b, :k].cpu().numpy(), dtype=np.float32, copy=True),
                         cls[b, :k].cpu().numpy().astype(np.int64)))
         return res
 
