@@ -234,10 +234,13 @@ nms_segment_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict_
                    const float* __restrict__ boxes, float4* sbox_scratch, uint8_t* __restrict__ keep,
                    int64_t N, int Npad, int C, IouOps op) {
   __shared__ unsigned long long s_removed[kNmsMaxWords];
-  __shared__ float4 s_cbox[kNmsChunk];
+  __shared__ float4 s_cbox[kNmsChunk];                // chunk candidates (visiting order)
   __shared__ float s_carea[kNmsChunk];
-  __shared__ unsigned long long s_cmask[kNmsChunk];   // coarse occupancy masks of the chunk
+  __shared__ unsigned long long s_cmask[kNmsChunk];   // their coarse occupancy masks
   __shared__ unsigned long long s_mask[kNmsChunk];    // in-chunk suppression rows
+  __shared__ float4 s_kbox[kNmsChunk];                // boxes kept in this chunk, compacted
+  __shared__ float s_karea[kNmsChunk];
+  __shared__ unsigned long long s_cell[64];           // coarse cell -> bitmap of kept boxes touching it
   __shared__ int s_kept[kNmsChunk];
   __shared__ int s_nkept;
 
@@ -300,16 +303,43 @@ nms_segment_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict_
     }
     __syncthreads();
     const int nk = s_nkept;
-    if (tid < nk) kp[key_idx(k[s0 + c0 + s_kept[tid]])] = 1;
-    // (3) kept boxes of this chunk against all later candidates
+    if (c0 + kNmsChunk >= n) {   // last chunk: nothing left to suppress
+      if (tid < nk) kp[key_idx(k[s0 + c0 + s_kept[tid]])] = 1;
+      break;
+    }
+    // (2b) compact the kept boxes and index them by coarse cell
+    if (tid < nk) {
+      int r = s_kept[tid];
+      s_kbox[tid] = s_cbox[r];
+      s_karea[tid] = s_carea[r];
+      kp[key_idx(k[s0 + c0 + r])] = 1;
+    } else if (tid >= 64 && tid < 128) {
+      const int cell = tid - 64;
+      unsigned long long m = 0ull;
+      for (int q = 0; q < nk; ++q) m |= ((s_cmask[s_kept[q]] >> cell) & 1ull) << q;
+      s_cell[cell] = m;
+    }
+    __syncthreads();
+    // (3) every later candidate against the kept boxes whose coarse cells it touches
     for (int j = c0 + kNmsChunk + tid; j < n; j += kNmsThreads) {
       if ((s_removed[j >> 6] >> (j & 63)) & 1ull) continue;
-      float4 v = sb[j];
-      float va = box_area(v);
+      const float4 v = sb[j];
+      const float va = box_area(v);
       unsigned long long vm = use_masks ? coarse_mask(v, va) : ~0ull;
-      for (int q = 0; q < nk; ++q) {
-        int r = s_kept[q];
-        if ((vm & s_cmask[r]) && suppresses(s_cbox[r], s_carea[r], v, va, op)) {
+      unsigned long long hits = 0ull;
+      if (vm == ~0ull) {
+        hits = nk >= 64 ? ~0ull : ((1ull << nk) - 1ull);
+      } else {
+        while (vm) {
+          int cell = __ffsll((long long)vm) - 1;
+          vm &= vm - 1;
+          hits |= s_cell[cell];
+        }
+      }
+      while (hits) {   // ascending q = visiting order of the kept boxes
+        int q = __ffsll((long long)hits) - 1;
+        hits &= hits - 1;
+        if (suppresses(s_kbox[q], s_karea[q], v, va, op)) {
           atomicOr(&s_removed[j >> 6], 1ull << (j & 63));
           break;
         }

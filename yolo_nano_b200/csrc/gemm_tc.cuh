@@ -5,10 +5,11 @@
 //
 // Tile: 128 pixel rows x Npad (<= 256) output channels; K consumed in chunks of 32 floats
 // (one 128-byte swizzle row).  A persistent CTA walks its tiles; five roles:
-//   warp 0      TMA producer      A chunk (+ W chunk when W is streamed) -> smem stage
-//   warp 1      MMA issuer        tcgen05.mma kind::tf32, one elected lane; owns TMEM alloc
-//   warps 2-5   splitters         fp32 parity mode only: A -> (A_hi, A_lo) in smem
-//   warps 6-9   epilogue          TMEM -> regs -> bias/act -> global (plain / slot-mapped)
+//   warps 0-3   epilogue          TMEM -> regs -> bias/act -> global (plain / interleaved)
+//   warps 4-7   splitters         fp32 parity mode only: A -> (A_hi, A_lo) in smem
+//   warp 8      TMA producer      A chunk (+ W chunk when W is streamed) -> smem stage
+//   warp 9      MMA issuer        tcgen05.mma kind::tf32, one elected lane; owns TMEM alloc
+//   (warps 10-11 idle: three full warpgroups, roles aligned to warpgroup boundaries)
 //
 // fp32 parity mode (YNB_GEMM_TC_3XTF32): a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi with
 // x_hi = RN_tf32(x), x_lo = RN_tf32(x - x_hi): three MMAs per K step.  Measured on B200
@@ -35,7 +36,7 @@
 
 namespace ynb {
 
-constexpr int kTcThreads = 320;
+constexpr int kTcThreads = 384;
 constexpr int kTcBM = 128;
 constexpr int kTcBK = 32;                       // floats per K chunk = 128 bytes
 constexpr int kTcAStageBytes = kTcBM * 128;     // 16 KB
@@ -65,6 +66,12 @@ struct TcGemmParams {
   ChanMap omap;
   const float* bias;
   int act;
+  // Stride-1 ShuffleNetV2 unit: this GEMM is branch2's last conv; `pass` points at the
+  // pass-through half x1 (same pixels, `N` channels).  The epilogue then writes whole
+  // interleaved rows out[slot(2i)] = x1[i], out[slot(2i+1)] = branch2[i]  — torch.cat +
+  // channel_shuffle (backbone/shufflenetv2.py:70-76, 14-28) as one coalesced store.
+  const float* pass;
+  int pass_ld;
   int* err_flag;
 };
 
@@ -73,9 +80,12 @@ struct TcSmemLayout {
   uint32_t w_chunk_bytes;  // Npad * 128
   uint32_t w_res_off;      // offset of the resident W region
   uint32_t bias_off;
+  uint32_t stg_off;        // per-epilogue-warp transpose staging (interleaved stores)
   uint32_t bar_off;
   uint32_t total;
 };
+constexpr int kTcStgPitch = 36;                                  // floats per staged row (conflict-free)
+constexpr int kTcStgBytes = 4 * 32 * kTcStgPitch * 4;            // 4 warps x 32 rows
 
 __host__ __device__ inline TcSmemLayout tc_smem_layout(int Npad, int num_steps, int num_stages, bool w_resident,
                                                        bool split) {
@@ -87,7 +97,8 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int Npad, int num_steps, 
   L.w_res_off = L.stage_bytes * num_stages;
   uint32_t w_res = w_resident ? L.w_chunk_bytes * (split ? 2 : 1) * num_steps : 0;
   L.bias_off = L.w_res_off + w_res;
-  L.bar_off = L.bias_off + 1024;                          // bias: up to 256 floats
+  L.stg_off = L.bias_off + 1024;                          // bias: up to 256 floats
+  L.bar_off = L.stg_off + kTcStgBytes;
   L.total = L.bar_off + 256 + 1024;                       // barriers + slack for 1024-B alignment
   return L;
 }
@@ -95,6 +106,7 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int Npad, int num_steps, 
 // round-to-nearest (ties away) to TF32 on the raw bits; exact for values already in TF32
 __host__ __device__ __forceinline__ uint32_t rn_tf32_bits(uint32_t u) { return (u + 0x1000u) & 0xffffe000u; }
 
+template <bool kPass>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWhi,
                const __grid_constant__ CUtensorMap tmWlo, const TcGemmParams p) {
@@ -119,7 +131,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmWhi);
     if (split) ptx::prefetch_tmap(&tmWlo);
@@ -135,12 +147,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::mbar_init(w_full, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == 9) {
     ptx::tmem_alloc(tmem_ptr, p.tmem_cols);
     ptx::tmem_relinquish();
   }
-  if (warp >= 6) {   // epilogue warps stage the bias once (no global latency inside the tile loop)
-    for (int i = threadIdx.x - 192; i < p.Npad; i += 128) s_bias[i] = i < p.N ? __ldg(p.bias + i) : 0.0f;
+  if (warp < 4) {    // epilogue warps stage the bias once (no global latency inside the tile loop)
+    for (int i = threadIdx.x; i < p.Npad; i += 128) s_bias[i] = i < p.N ? __ldg(p.bias + i) : 0.0f;
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -158,7 +170,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int acc_cols = p.Npad * p.nacc;   // TMEM columns per accumulator stage
   const uint32_t step_tx = p.a_box_bytes + (p.w_resident ? 0 : w_chunk_bytes * (split ? 2 : 1));
 
-  if (warp == 0) {
+  if (warp == 8) {
     // ================= TMA producer =================
     if (lane == 0) {
       if (p.w_resident) {
@@ -199,7 +211,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = ptx::make_idesc(2 /*tf32*/, kTcBM, p.Npad);
@@ -243,10 +255,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1; }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp >= 4 && warp < 8) {
     // ================= splitters (fp32 parity mode) =================
     if (split) {
-      const int t = threadIdx.x - 64;   // 0..127
+      const int t = threadIdx.x - 128;  // 0..127
       int s = 0;
       uint32_t ph = 0;
       bool ok = true;
@@ -275,9 +287,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else {
+  } else if (warp < 4) {
     // ================= epilogue =================
-    const int q = warp & 3;                         // TMEM lane quarter this warp may read
+    const int q = warp;                             // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;                  // tile row owned by this thread
     int acc = 0;
     uint32_t acc_ph = 0;
@@ -299,16 +311,36 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         m = tile * kTcBM + row;
         valid = m < p.M;
       }
+      // Pass-through prefetch (interleave mode): the x1 values this warp will store do not
+      // depend on the MMAs, so the loads of the first 32-channel block are issued BEFORE
+      // waiting for the accumulator, and each half (16 rows) is re-armed for the next block
+      // right after it has been stored: 32 independent 128-byte row reads per lane-set in
+      // flight at all times, in 32 registers.
+      const int64_t m_base = tile * kTcBM + q * 32;            // first row of this warp (pointwise)
+      float xa[16], xb[16];
+      auto fetch_x1 = [&](int c0, int r0, float (&x)[16]) {
+        const int i = c0 + lane;
+        const bool col_ok = kPass && i < p.N;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const int64_t mr = m_base + r0 + r;
+          x[r] = (col_ok && mr < p.M) ? __ldg(p.pass + mr * p.pass_ld + i) : 0.0f;
+        }
+      };
+      if (kPass) {
+        fetch_x1(0, 0, xa);
+        fetch_x1(0, 16, xb);
+      }
       ok = ptx::mbar_wait(&tmem_full[acc], acc_ph, p.err_flag, 6);
       if (!ok) break;
       ptx::tc_fence_after_sync();
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_cols);
       float* orow = p.out + m * p.out_ld;
-      for (int c0 = 0; c0 < p.Npad; c0 += 16) {
+      // sum of the accumulators of 16 columns (main_0 + main_1 + ... + correction), + bias, act
+      auto load16 = [&](int c0, float (&v)[16]) {
         uint32_t r[16];
         ptx::tmem_ld_32x16(t_base + c0, r);
         if (p.nacc > 1) {
-          // sum the accumulators in fp32: main_0 + main_1 + ... + correction (smallest last)
           for (int a = 1; a < p.nacc; ++a) {
             uint32_t r2[16];
             ptx::tmem_ld_32x16(t_base + (uint32_t)(a * p.Npad) + c0, r2);
@@ -319,32 +351,77 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else {
           ptx::tmem_ld_wait();
         }
-        if (c0 + 16 >= p.Npad) {   // last block read: hand the accumulator stage back to the MMA warp
-          ptx::tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
-        }
-        if (!valid) continue;
-        float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = apply_act(__uint_as_float(r[j]) + s_bias[c0 + j], p.act);
-        if (vec) {
+      };
+      auto release_acc = [&]() {   // all TMEM reads of this tile are done: hand the stage back
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      };
+
+      if (kPass) {
+        // ---- interleaved store through a warp-private transpose buffer --------------------
+        float* stg = reinterpret_cast<float*>(smem + lay.stg_off) + warp * 32 * kTcStgPitch;
+        // one 32-channel block: accumulators -> smem rows -> coalesced float2 (x1, branch2) stores
+        for (int c0 = 0; c0 < p.Npad; c0 += 32) {
+          float* srow = stg + lane * kTcStgPitch;
+          {
+            float v[16];
+            load16(c0, v);
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            int n = c0 + j;
-            if (n + 3 < p.N) {
-              *reinterpret_cast<float4*>(orow + p.out_off + n) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (n + e < p.N) orow[p.out_off + n + e] = v[j + e];
-            }
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(srow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           }
-        } else {
-          // channel split / concat / shuffle as a store permutation (slot map + stride)
+          if (c0 + 16 < p.Npad) {
+            float v[16];
+            load16(c0 + 16, v);
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (c0 + j < p.N) orow[p.omap.slot(p.out_off + (c0 + j) * p.out_step)] = v[j];
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(srow + 16 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+          if (c0 + 32 >= p.Npad) release_acc();
+          __syncwarp();
+          const int i = c0 + lane;                              // channel inside each half
+          const bool col_ok = i < p.N;
+          float* o = p.out + m_base * p.out_ld + p.omap.slot(2 * (col_ok ? i : 0));
+          // rows 0..15 with xa, then re-arm xa for the next block; rows 16..31 with xb, re-arm xb
+#pragma unroll
+          for (int r = 0; r < 16; ++r)
+            if (col_ok && m_base + r < p.M)
+              *reinterpret_cast<float2*>(o + (int64_t)r * p.out_ld) = make_float2(xa[r], stg[r * kTcStgPitch + lane]);
+          if (c0 + 32 < p.Npad) fetch_x1(c0 + 32, 0, xa);
+#pragma unroll
+          for (int r = 16; r < 32; ++r)
+            if (col_ok && m_base + r < p.M)
+              *reinterpret_cast<float2*>(o + (int64_t)r * p.out_ld) = make_float2(xb[r - 16], stg[r * kTcStgPitch + lane]);
+          if (c0 + 32 < p.Npad) fetch_x1(c0 + 32, 16, xb);
+          __syncwarp();
+        }
+      } else {
+        for (int c0 = 0; c0 < p.Npad; c0 += 16) {
+          float v[16];
+          load16(c0, v);
+          if (c0 + 16 >= p.Npad) release_acc();
+          if (!valid) continue;
+          if (vec) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              int n = c0 + j;
+              if (n + 3 < p.N) {
+                *reinterpret_cast<float4*>(orow + p.out_off + n) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (n + e < p.N) orow[p.out_off + n + e] = v[j + e];
+              }
+            }
+          } else {
+            // channel split / concat as a store permutation (slot map + stride)
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < p.N) orow[p.omap.slot(p.out_off + (c0 + j) * p.out_step)] = v[j];
+          }
         }
       }
       if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1; }
@@ -353,7 +430,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 9) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, p.tmem_cols);
   }
@@ -487,12 +564,18 @@ inline bool tc_plan_smem(TcGemmLaunch& L) {
 inline cudaError_t launch_tc_gemm(const TcGemmLaunch& L, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kTcSmemBudget + 2048);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               kTcSmemBudget + 2048);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  tc_gemm_kernel<<<L.grid, kTcThreads, L.smem, st>>>(L.tmA, L.w->tm_hi, L.w->tm_lo, L.p);
+  if (L.p.pass != nullptr)
+    tc_gemm_kernel<true><<<L.grid, kTcThreads, L.smem, st>>>(L.tmA, L.w->tm_hi, L.w->tm_lo, L.p);
+  else
+    tc_gemm_kernel<false><<<L.grid, kTcThreads, L.smem, st>>>(L.tmA, L.w->tm_hi, L.w->tm_lo, L.p);
   YNB_COUNT_LAUNCH();
   return cudaGetLastError();
 }

@@ -111,45 +111,70 @@ inline cudaError_t launch_stem_pool(const float* x, float* out, const StemWeight
 // models/yolo_nano.py:51,53)
 //   w [9][C4] tap-major, b [C4]  (C4 = channels rounded to 4; pads are zero)
 // =====================================================================================
+// Each thread produces kDwTX consecutive output pixels of one 4-channel group: the 3 x
+// ((TX-1)*stride+3) input window is loaded once into registers (4.5 instead of 9 16-byte
+// loads per output at stride 1) and the 9 filter taps once per thread, which takes the
+// kernel off the L1 bandwidth limit the one-pixel-per-thread version sat on.
+constexpr int kDwTX = 4;
+
+template <int STRIDE>
 __global__ void __launch_bounds__(256)
 dwconv3x3_kernel(const float* __restrict__ in, int in_ld, int in_off,
                  float* __restrict__ out, int out_ld, int out_off,
                  const float* __restrict__ w, const float* __restrict__ bias,
-                 int batch, int Hin, int Win, int C4, int stride, int act) {
-  const int Ho = (Hin - 1) / stride + 1, Wo = (Win - 1) / stride + 1;
+                 int batch, int Hin, int Win, int C4, int act) {
+  constexpr int NIN = (kDwTX - 1) * STRIDE + 3;
+  const int Ho = (Hin - 1) / STRIDE + 1, Wo = (Win - 1) / STRIDE + 1;
   const int groups = C4 >> 2;
-  const int64_t total = (int64_t)batch * Ho * Wo * groups;
+  const int xgroups = (Wo + kDwTX - 1) / kDwTX;
+  const int64_t total = (int64_t)batch * Ho * xgroups * groups;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
-    int g = (int)(i % groups);
+    const int g = (int)(i % groups);
     int64_t p = i / groups;
-    int xo = (int)(p % Wo);
-    int yo = (int)((p / Wo) % Ho);
-    int b = (int)(p / ((int64_t)Wo * Ho));
+    const int xg = (int)(p % xgroups);
+    const int yo = (int)((p / xgroups) % Ho);
+    const int b = (int)(p / ((int64_t)xgroups * Ho));
     const int c = g << 2;
-    float4 acc = __ldg(reinterpret_cast<const float4*>(bias + c));
+    const int xo0 = xg * kDwTX;
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c));
+    float4 acc[kDwTX];
+#pragma unroll
+    for (int t = 0; t < kDwTX; ++t) acc[t] = bv;
     const float* inb = in + (size_t)b * Hin * Win * in_ld + in_off + c;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
-      int yi = yo * stride + ky - 1;
+      const int yi = yo * STRIDE + ky - 1;
       if (yi < 0 || yi >= Hin) continue;
+      float4 v[NIN];
+#pragma unroll
+      for (int j = 0; j < NIN; ++j) {
+        const int xi = xo0 * STRIDE - 1 + j;
+        v[j] = (xi >= 0 && xi < Win) ? __ldg(reinterpret_cast<const float4*>(inb + ((size_t)yi * Win + xi) * in_ld))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        int xi = xo * stride + kx - 1;
-        if (xi < 0 || xi >= Win) continue;
-        float4 v = __ldg(reinterpret_cast<const float4*>(inb + ((size_t)yi * Win + xi) * in_ld));
-        float4 k = __ldg(reinterpret_cast<const float4*>(w + (ky * 3 + kx) * C4 + c));
-        acc.x = fmaf(v.x, k.x, acc.x);
-        acc.y = fmaf(v.y, k.y, acc.y);
-        acc.z = fmaf(v.z, k.z, acc.z);
-        acc.w = fmaf(v.w, k.w, acc.w);
+        const float4 k = __ldg(reinterpret_cast<const float4*>(w + (ky * 3 + kx) * C4 + c));
+#pragma unroll
+        for (int t = 0; t < kDwTX; ++t) {
+          const float4 u = v[t * STRIDE + kx];
+          acc[t].x = fmaf(u.x, k.x, acc[t].x);
+          acc[t].y = fmaf(u.y, k.y, acc[t].y);
+          acc[t].z = fmaf(u.z, k.z, acc[t].z);
+          acc[t].w = fmaf(u.w, k.w, acc[t].w);
+        }
       }
     }
-    acc.x = apply_act(acc.x, act);
-    acc.y = apply_act(acc.y, act);
-    acc.z = apply_act(acc.z, act);
-    acc.w = apply_act(acc.w, act);
-    *reinterpret_cast<float4*>(out + (size_t)p * out_ld + out_off + c) = acc;
+    float* ob = out + (((size_t)b * Ho + yo) * Wo + xo0) * out_ld + out_off + c;
+#pragma unroll
+    for (int t = 0; t < kDwTX; ++t) {
+      if (xo0 + t < Wo) {
+        float4 a = acc[t];
+        a.x = apply_act(a.x, act); a.y = apply_act(a.y, act); a.z = apply_act(a.z, act); a.w = apply_act(a.w, act);
+        *reinterpret_cast<float4*>(ob + (size_t)t * out_ld) = a;
+      }
+    }
   }
 }
 
@@ -157,13 +182,17 @@ inline cudaError_t launch_dwconv3x3(const float* in, int in_ld, int in_off, floa
                                     int out_off, const float* w, const float* b, int batch, int Hin,
                                     int Win, int C4, int stride, int act, cudaStream_t st) {
   const int Ho = (Hin - 1) / stride + 1, Wo = (Win - 1) / stride + 1;
-  int64_t total = (int64_t)batch * Ho * Wo * (C4 / 4);
+  int64_t total = (int64_t)batch * Ho * ((Wo + kDwTX - 1) / kDwTX) * (C4 / 4);
   int64_t blocks = (total + 255) / 256;
   int64_t cap = (int64_t)kNumSMs * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  dwconv3x3_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, in_ld, in_off, out, out_ld, out_off, w, b,
-                                                     batch, Hin, Win, C4, stride, act);
+  if (stride == 1)
+    dwconv3x3_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(in, in_ld, in_off, out, out_ld, out_off, w, b, batch, Hin,
+                                                          Win, C4, act);
+  else
+    dwconv3x3_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(in, in_ld, in_off, out, out_ld, out_off, w, b, batch, Hin,
+                                                          Win, C4, act);
   YNB_COUNT_LAUNCH();
   return cudaGetLastError();
 }

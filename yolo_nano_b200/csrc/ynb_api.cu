@@ -384,12 +384,15 @@ struct Planner {
   }
 
   // pointwise conv: in view (off, ktot) -> out (off, step, map)
+  // `pass`: stride-1 unit tail — out[slot(2i)] = pass[i], out[slot(2i+1)] = conv[i]
   void pw(const std::string& name, const Tensor& in, int in_off, const Tensor& out, int out_off, int out_step,
-          bool join = false) {
+          bool join = false, const Tensor* pass = nullptr) {
     const PackedConv& pc = conv(name);
     const ConvSpec& c = spec(name);
     int64_t M = (int64_t)B * in.H * in.W;
-    const double abytes = 4.0 * M * (c.cin + c.cout) + 4.0 * c.cin * c.cout + 4.0 * c.cout;
+    const bool tc_mode = e->cfg.gemm_mode != YNB_GEMM_FP32_FFMA;
+    const double abytes = 4.0 * M * (c.cin + c.cout + (pass && tc_mode ? 2.0 * c.cout : 0.0)) + 4.0 * c.cin * c.cout +
+                          4.0 * c.cout;
     const double aflops = 2.0 * M * c.cin * c.cout;
     if (e->cfg.gemm_mode == YNB_GEMM_FP32_FFMA) {
       GemmParams g{};
@@ -397,6 +400,7 @@ struct Planner {
       g.w = pc.w_dev; g.bias = pc.b_dev; g.out = out.p; g.out_ld = out.ld;
       g.out_off = out_off; g.out_step = out_step; g.omap = out.map;
       g.M = M; g.N = pc.n; g.Ktot = pc.ktot; g.act = c.act;
+      if (pass) { g.out_off = 1; g.out_step = 2; }
       Op op{name, "pw_ffma", abytes, aflops, [=](cudaStream_t st) { return launch_gemm_ffma(g, false, st); }};
       op.join = join;
       plan->net.push_back(op);
@@ -418,6 +422,7 @@ struct Planner {
     p.a_box_bytes = kTcAStageBytes;
     p.out = out.p; p.out_ld = out.ld; p.out_off = out_off; p.out_step = out_step; p.omap = out.map;
     p.bias = pc.b_dev; p.act = c.act;
+    p.pass = pass ? pass->p : nullptr; p.pass_ld = pass ? pass->ld : 0;
     p.err_flag = e->d_err;
     if (!make_tmap_2d(&L.tmA, in.p + in_off, (uint64_t)pc.ktot, (uint64_t)M, (uint64_t)in.ld, kTcBM)) {
       error = "cuTensorMapEncodeTiled failed for input of " + name;
@@ -536,11 +541,15 @@ int build_plan(ynb_engine* e, int B, Plan** out) {
       Tensor o = P.T(st + "." + std::to_string(bi));
       int x2_off = x.map.slot(h);
       // the previous unit's pass-through copy wrote half of x: join before reading it
-      P.pw(u + ".branch2.0", x, x2_off, mid1, 0, 1, /*join=*/bi > 1);
-      plan->net.back().mark = true;              // fork point: x is complete here
-      P.passthrough(u, x, o, h);                 // side stream: o[slot(2i)] = x[i]
+      const bool ffma = e->cfg.gemm_mode == YNB_GEMM_FP32_FFMA;
+      P.pw(u + ".branch2.0", x, x2_off, mid1, 0, 1, /*join=*/ffma && bi > 1);
+      if (ffma) {   // cross-check path: pass-through as a side-stream copy next to the unit's convs
+        plan->net.back().mark = true;            // fork point: x is complete here
+        P.passthrough(u, x, o, h);               // o[slot(2i)] = x[i]
+      }
       P.dw(u + ".branch2.3", mid1, 0, mid2);
-      P.pw(u + ".branch2.5", mid2, 0, o, 1, 2);  // o[slot(2i+1)] = branch2
+      // tensor-core path: the epilogue writes whole interleaved rows (x1 | branch2)
+      P.pw(u + ".branch2.5", mid2, 0, o, 1, 2, false, &x);
       x = o;
     }
   }
