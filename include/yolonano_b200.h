@@ -140,6 +140,16 @@ int  ynb_detect_host(ynb_engine* e, const float* x_host, int32_t batch,
                      float* out_boxes_host, float* out_scores_host, int32_t* out_cls_host,
                      int32_t* out_counts_host, void* stream);
 
+/* The same in two halves, double-buffered (slot 0 | 1), so that a stream of batches overlaps
+ * the PCIe copy of batch i+1 with the computation of batch i:
+ *   ynb_submit_host(slot)  enqueues H2D (copy stream) + the whole path (compute stream);
+ *   ynb_wait_host(slot)    blocks until that step finished and its kept rows are in the
+ *                          host arrays given to submit.  ynb_detect_host == submit + wait. */
+int  ynb_submit_host(ynb_engine* e, int32_t slot, const float* x_host, int32_t batch,
+                     float* out_boxes_host, float* out_scores_host, int32_t* out_cls_host,
+                     int32_t* out_counts_host, void* stream);
+int  ynb_wait_host(ynb_engine* e, int32_t slot);
+
 /* After any ynb_forward_*: copy an internal activation as canonical NCHW float32 into
  * out_dev.  Names: "pool", "c3", "c4", "c5", "p3", "p4", "p5", and every backbone
  * block output "stage2.0" ... "stage4.3".  Per-layer parity hook (SURVEY §8c hazard 1). */

@@ -191,7 +191,18 @@ def test_batch64_equals_per_image_and_host_path(G):
     for i in (0, 31, 63):
         k = int(hn[i])
         assert torch.equal(hb[i, :k], ob[i, :k].cpu()) and torch.equal(hc[i, :k], oc[i, :k].cpu())
-    # one image against the reference-recorded keep-set (g3 was generated with seed 2, images 0..1)
+    # double-buffered streaming API: two steps in flight, same rows
+    outs = [eng.alloc_outputs(bsz, pinned_host=True) for _ in range(2)]
+    xh2 = torch.flip(x, dims=[0]).cpu().pin_memory()
+    eng.submit_host(0, xh, outs[0])
+    eng.submit_host(1, xh2, outs[1])
+    with pytest.raises(Exception):
+        eng.submit_host(0, xh, outs[0])                 # slot 0 still in flight
+    eng.wait_host(0)
+    eng.wait_host(1)
+    assert torch.equal(outs[0][3], on.cpu()) and torch.equal(outs[1][3], torch.flip(on.cpu(), dims=[0]))
+    k = int(outs[1][3][0])
+    assert torch.equal(outs[1][0][0, :k], ob[bsz - 1, :k].cpu())
     eng.close()
 
 

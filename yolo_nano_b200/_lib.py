@@ -57,6 +57,8 @@ SIGNATURES = {
     "ynb_forward_decode": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p]),
     "ynb_forward_detect": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _p]),
     "ynb_detect_host": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _p]),
+    "ynb_submit_host": (C.c_int, [_p, _i32, _p, _i32, _p, _p, _p, _p, _p]),
+    "ynb_wait_host": (C.c_int, [_p, _i32]),
     "ynb_read_tap": (C.c_int, [_p, _s, _i32, _p, _p]),
     "ynb_tap_shape": (C.c_int, [_p, _s, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "ynb_launch_count": (_i64, [_p]),

@@ -34,39 +34,60 @@ struct DecodeParams {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-__global__ void __launch_bounds__(128)
+// A block stages kDecCells consecutive cells (whole NHWC rows, contiguous in memory) in shared
+// memory with 16-byte coalesced loads; then one thread per (cell, anchor) reads its 1+C+4
+// values from there.  The raw head map is read exactly once, at full line efficiency.
+constexpr int kDecCells = 32;
+
+__global__ void __launch_bounds__(kDecCells * 3)
 decode_level_kernel(DecodeParams p) {
-  const int64_t total = (int64_t)p.batch * p.G * p.G * p.A;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int a = (int)(i % p.A);
-  const int64_t cell = i / p.A;                 // b*G*G + y*G + x
+  extern __shared__ float s_raw[];               // [kDecCells][pitch]
+  const int pitch = p.ld + 1;                    // odd pitch: cells land in different banks
+  const int64_t cells_total = (int64_t)p.batch * p.G * p.G;
+  const int64_t cell0 = (int64_t)blockIdx.x * kDecCells;
+  const int ncell = (int)min((int64_t)kDecCells, cells_total - cell0);
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.raw + cell0 * p.ld);
+    const int ld4 = p.ld >> 2;
+    for (int i = threadIdx.x; i < ncell * ld4; i += blockDim.x) {
+      float4 v = __ldg(src + i);
+      int cc = i / ld4, k = (i - cc * ld4) << 2;
+      float* d = s_raw + cc * pitch + k;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+  }
+  __syncthreads();
+  const int cc = threadIdx.x / p.A, a = threadIdx.x - cc * p.A;
+  if (cc >= ncell) return;
+  const int64_t cell = cell0 + cc;                // b*G*G + y*G + x
   const int gx = (int)(cell % p.G);
   const int gy = (int)((cell / p.G) % p.G);
   const int b = (int)(cell / ((int64_t)p.G * p.G));
-  const float* r = p.raw + cell * p.ld;
+  const float* r = s_raw + cc * pitch;
 
-  const float obj = sigmoidf_(__ldg(r + a));
+  const float obj = sigmoidf_(r[a]);
   // softmax over classes (torch.softmax, dim = classes) times objectness; argmax over the
   // PRODUCTS with first-max-wins, as np.argmax does on all_class (models/yolo_nano.py:253)
   const float* cl = r + p.A + a * p.C;
   float mx = -INFINITY;
-  for (int c = 0; c < p.C; ++c) mx = fmaxf(mx, __ldg(cl + c));
+  for (int c = 0; c < p.C; ++c) mx = fmaxf(mx, cl[c]);
   float sum = 0.0f;
-  for (int c = 0; c < p.C; ++c) sum += expf(__ldg(cl + c) - mx);
+  for (int c = 0; c < p.C; ++c) sum += expf(cl[c] - mx);
   float best = -1.0f;
   int best_c = 0;
   for (int c = 0; c < p.C; ++c) {
-    float pr = __fmul_rn(__fdiv_rn(expf(__ldg(cl + c) - mx), sum), obj);
+    float pr = __fmul_rn(__fdiv_rn(expf(cl[c] - mx), sum), obj);
     if (pr > best) { best = pr; best_c = c; }
   }
   // box (models/yolo_nano.py:129-134, 150-154, 366)
   const float* t = r + p.A * (1 + p.C) + 4 * a;
-  float tx = __ldg(t), tyv = __ldg(t + 1), tw = __ldg(t + 2), th = __ldg(t + 3);
+  float tx = t[0], tyv = t[1], tw = t[2], th = t[3];
+  const float aw = a == 0 ? p.anchor_w[0] : (a == 1 ? p.anchor_w[1] : (a == 2 ? p.anchor_w[2] : p.anchor_w[3]));
+  const float ah = a == 0 ? p.anchor_h[0] : (a == 1 ? p.anchor_h[1] : (a == 2 ? p.anchor_h[2] : p.anchor_h[3]));
   float cx = __fmul_rn(__fadd_rn(sigmoidf_(tx), (float)gx), p.stride);
   float cy = __fmul_rn(__fadd_rn(sigmoidf_(tyv), (float)gy), p.stride);
-  float w = __fmul_rn(expf(tw), p.anchor_w[a]);
-  float h = __fmul_rn(expf(th), p.anchor_h[a]);
+  float w = __fmul_rn(expf(tw), aw);
+  float h = __fmul_rn(expf(th), ah);
   float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
   float x1 = __fdiv_rn(__fsub_rn(cx, hw), p.input_size);
   float y1 = __fdiv_rn(__fsub_rn(cy, hh), p.input_size);
@@ -82,9 +103,11 @@ decode_level_kernel(DecodeParams p) {
 }
 
 inline cudaError_t launch_decode_level(const DecodeParams& p, cudaStream_t st) {
-  int64_t total = (int64_t)p.batch * p.G * p.G * p.A;
-  if (total <= 0) return cudaSuccess;
-  decode_level_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(p);
+  int64_t cells = (int64_t)p.batch * p.G * p.G;
+  if (cells <= 0) return cudaSuccess;
+  if (p.A != 3 || (p.ld & 3)) return cudaErrorInvalidValue;
+  size_t smem = (size_t)kDecCells * (p.ld + 1) * 4;
+  decode_level_kernel<<<(unsigned)((cells + kDecCells - 1) / kDecCells), kDecCells * 3, smem, st>>>(p);
   YNB_COUNT_LAUNCH();
   return cudaGetLastError();
 }

@@ -41,7 +41,7 @@ constexpr int kTcBM = 128;
 constexpr int kTcBK = 32;                       // floats per K chunk = 128 bytes
 constexpr int kTcAStageBytes = kTcBM * 128;     // 16 KB
 constexpr int kTcMaxStages = 8;
-constexpr int kTcSmemBudget = 220 * 1024;
+constexpr int kTcSmemBudget = 232448;                   // 227 KB opt-in maximum (layout totals include the alignment slack)
 constexpr int kTcMaxMain = 4;
 
 struct TcGemmParams {
@@ -72,8 +72,24 @@ struct TcGemmParams {
   // channel_shuffle (backbone/shufflenetv2.py:70-76, 14-28) as one coalesced store.
   const float* pass;
   int pass_ld;
+  int tma_store;          // plain pointwise outputs leave through TMA bulk tensor stores (tmOut)
   int* err_flag;
+  // debug timeline (tools/gpu_tc_trace.py): CTA 0 appends {role, tile, step, clock64}
+  long long* trace;
+  int trace_cap;
 };
+
+// roles: 1 producer-issued, 2 split-done, 3 mma-issued, 4 epilogue-start, 5 epilogue-end, 6 tile accumulators ready
+#define YNB_TRACE(role, a, b)                                                          \
+  do {                                                                                 \
+    if (p.trace != nullptr && blockIdx.x == 0) {                                       \
+      int _i = atomicAdd(reinterpret_cast<int*>(p.trace), 1);                          \
+      if (_i < p.trace_cap) {                                                          \
+        long long* _e = p.trace + 1 + (long long)_i * 4;                               \
+        _e[0] = (role); _e[1] = (a); _e[2] = (b); _e[3] = clock64();                   \
+      }                                                                                \
+    }                                                                                  \
+  } while (0)
 
 struct TcSmemLayout {
   uint32_t stage_bytes;    // A | A_lo | (W_hi | W_lo when streamed)
@@ -85,7 +101,8 @@ struct TcSmemLayout {
   uint32_t total;
 };
 constexpr int kTcStgPitch = 36;                                  // floats per staged row (conflict-free)
-constexpr int kTcStgBytes = 4 * 32 * kTcStgPitch * 4;            // 4 warps x 32 rows
+constexpr int kTcStgBytes = 4 * 2 * 4096;                        // 4 warps x 2 swizzled [32 rows x 128 B] boxes
+static_assert(kTcStgBytes >= 4 * 32 * kTcStgPitch * 4, "staging region too small");
 
 __host__ __device__ inline TcSmemLayout tc_smem_layout(int Npad, int num_steps, int num_stages, bool w_resident,
                                                        bool split) {
@@ -97,7 +114,7 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int Npad, int num_steps, 
   L.w_res_off = L.stage_bytes * num_stages;
   uint32_t w_res = w_resident ? L.w_chunk_bytes * (split ? 2 : 1) * num_steps : 0;
   L.bias_off = L.w_res_off + w_res;
-  L.stg_off = L.bias_off + 1024;                          // bias: up to 256 floats
+  L.stg_off = L.bias_off + 1024;                          // bias: up to 256 floats (keeps 1024-B alignment)
   L.bar_off = L.stg_off + kTcStgBytes;
   L.total = L.bar_off + 256 + 1024;                       // barriers + slack for 1024-B alignment
   return L;
@@ -109,9 +126,12 @@ __host__ __device__ __forceinline__ uint32_t rn_tf32_bits(uint32_t u) { return (
 template <bool kPass>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWhi,
-               const __grid_constant__ CUtensorMap tmWlo, const TcGemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+               const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmOut,
+               const TcGemmParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  // 1024-byte alignment (128-byte swizzle atoms) by OFFSET arithmetic on the __shared__ array,
+  // so that every access below stays in the shared address space (LDS / STS, not generic)
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
 
   const bool split = p.mode == YNB_GEMM_TC_3XTF32;
   const TcSmemLayout lay = tc_smem_layout(p.Npad, p.num_steps, p.num_stages, p.w_resident != 0, split);
@@ -135,6 +155,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmWhi);
     if (split) ptx::prefetch_tmap(&tmWlo);
+    if (p.tma_store) ptx::prefetch_tmap(&tmOut);
     for (int s = 0; s < p.num_stages; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&ready[s], 4);      // one arrival per splitter warp
@@ -207,6 +228,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::tma_load_2d(w_hi_ptr(s, st), &tmWhi, &full[s], st * kTcBK, 0);
             if (split) ptx::tma_load_2d(w_lo_ptr(s, st), &tmWlo, &full[s], st * kTcBK, 0);
           }
+          YNB_TRACE(1, tile, st);
           if (++s == p.num_stages) { s = 0; ph ^= 1; }
         }
       }
@@ -248,6 +270,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             ptx::mma_tf32_ss(d_tmem + (uint32_t)(slot * p.Npad), da, db, idesc, t >= p.nmain);
           }
+          YNB_TRACE(3, tile, st);
           ptx::mma_commit(&empty[s]);                       // frees the smem stage when the MMAs retire
           if (st == p.num_steps - 1) ptx::mma_commit(&tmem_full[acc]);
           if (++s == p.num_stages) { s = 0; ph ^= 1; }
@@ -283,6 +306,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&ready[s]);
+          if (t == 0) YNB_TRACE(2, tile, st);
           if (++s == p.num_stages) { s = 0; ph ^= 1; }
         }
       }
@@ -295,6 +319,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t acc_ph = 0;
     bool ok = true;
     const bool vec = p.out_step == 1 && p.omap.gap == 0;
+    int tma_blk = 0;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
       // row -> output pixel
       int64_t m;
@@ -331,16 +356,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         fetch_x1(0, 0, xa);
         fetch_x1(0, 16, xb);
       }
+      if (threadIdx.x == 0) YNB_TRACE(4, tile, 0);
       ok = ptx::mbar_wait(&tmem_full[acc], acc_ph, p.err_flag, 6);
       if (!ok) break;
       ptx::tc_fence_after_sync();
+      if (threadIdx.x == 0) YNB_TRACE(6, tile, 0);
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_cols);
-      float* orow = p.out + m * p.out_ld;
       // sum of the accumulators of 16 columns (main_0 + main_1 + ... + correction), + bias, act
+      const float slope = p.act == YNB_ACT_RELU ? 0.0f : (p.act == YNB_ACT_LEAKY ? 0.1f : 1.0f);
       auto load16 = [&](int c0, float (&v)[16]) {
         uint32_t r[16];
         ptx::tmem_ld_32x16(t_base + c0, r);
-        if (p.nacc > 1) {
+        if (p.nacc == 2) {            // main + correction (the common case): both loads, one wait
+          uint32_t r2[16];
+          ptx::tmem_ld_32x16(t_base + (uint32_t)p.Npad + c0, r2);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        } else if (p.nacc > 2) {
           for (int a = 1; a < p.nacc; ++a) {
             uint32_t r2[16];
             ptx::tmem_ld_32x16(t_base + (uint32_t)(a * p.Npad) + c0, r2);
@@ -351,8 +384,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else {
           ptx::tmem_ld_wait();
         }
+        // bias + activation, branch-free: act(x) = max(x, slope * x) with slope 1 / 0 / 0.1
+        // (identity / ReLU / LeakyReLU(0.1): for x < 0, 0.1x > x, same product as the reference)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = apply_act(__uint_as_float(r[j]) + s_bias[c0 + j], p.act);
+        for (int j = 0; j < 16; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+          float x0 = __uint_as_float(r[j]) + b4.x, x1 = __uint_as_float(r[j + 1]) + b4.y;
+          float x2 = __uint_as_float(r[j + 2]) + b4.z, x3 = __uint_as_float(r[j + 3]) + b4.w;
+          v[j] = fmaxf(x0, x0 * slope); v[j + 1] = fmaxf(x1, x1 * slope);
+          v[j + 2] = fmaxf(x2, x2 * slope); v[j + 3] = fmaxf(x3, x3 * slope);
+        }
       };
       auto release_acc = [&]() {   // all TMEM reads of this tile are done: hand the stage back
         ptx::tc_fence_before_sync();
@@ -360,72 +401,114 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
       };
 
-      if (kPass) {
-        // ---- interleaved store through a warp-private transpose buffer --------------------
-        float* stg = reinterpret_cast<float*>(smem + lay.stg_off) + warp * 32 * kTcStgPitch;
-        // one 32-channel block: accumulators -> smem rows -> coalesced float2 (x1, branch2) stores
-        for (int c0 = 0; c0 < p.Npad; c0 += 32) {
-          float* srow = stg + lane * kTcStgPitch;
+      // Every store goes through a warp-private transpose buffer: a thread owns one tile ROW
+      // in TMEM, but a coalesced store wants a warp on consecutive CHANNELS of one row.  Each
+      // 32-channel block is written row-wise to shared memory (conflict-free pitch), then the
+      // warp writes the 32 rows out one 128-byte (plain) / 256-byte (interleaved) line at a time.
+      if (!kPass && p.tma_store) {
+        // ---- plain pointwise output: swizzled [32 rows x 32 ch] box per warp -> TMA store ----
+        // thread = row: its 8 16-byte chunks go to chunk (j ^ (row & 7)) of its 128-byte line
+        // (the SWIZZLE_128B pattern the store map expects; conflict-free for the warp).
+        uint8_t* boxes2 = smem + lay.stg_off + warp * 8192;
+        for (int c0 = 0; c0 < p.Npad; c0 += 32, ++tma_blk) {
+          uint8_t* sbox = boxes2 + (tma_blk & 1) * 4096;
+          if (lane == 0) ptx::bulk_wait_read<1>();     // the store issued from this buffer 2 blocks ago has read it
+          __syncwarp();
+          uint8_t* line = sbox + lane * 128;
           {
             float v[16];
             load16(c0, v);
 #pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              *reinterpret_cast<float4*>(srow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(line + ((j ^ (lane & 7)) << 4)) =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
           if (c0 + 16 < p.Npad) {
             float v[16];
             load16(c0 + 16, v);
 #pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              *reinterpret_cast<float4*>(srow + 16 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(line + (((j + 4) ^ (lane & 7)) << 4)) =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
           if (c0 + 32 >= p.Npad) release_acc();
+          ptx::fence_proxy_async_smem();
           __syncwarp();
-          const int i = c0 + lane;                              // channel inside each half
-          const bool col_ok = i < p.N;
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmOut, sbox, c0, (int)m_base);   // rows >= M / cols >= N4 are clipped
+            ptx::bulk_commit();
+          }
+        }
+        if (threadIdx.x == 0) YNB_TRACE(5, tile, 0);
+        if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1; }
+        continue;
+      }
+      float* stg = reinterpret_cast<float*>(smem + lay.stg_off) + warp * 32 * kTcStgPitch;
+      for (int c0 = 0; c0 < p.Npad; c0 += 32) {
+        float* srow = stg + lane * kTcStgPitch;
+        long long tq0 = 0, tq1 = 0, tq2 = 0;
+        if (p.trace != nullptr) tq0 = clock64();
+        {
+          float v[16];
+          load16(c0, v);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(srow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        if (c0 + 16 < p.Npad) {
+          float v[16];
+          load16(c0 + 16, v);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(srow + 16 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        if (c0 + 32 >= p.Npad) release_acc();
+        __syncwarp();
+        if (p.trace != nullptr) tq1 = clock64();
+        const int i = c0 + lane;                                // output channel of this lane
+        const bool col_ok = i < p.N;
+        const float* sl = stg + lane;
+        if (kPass) {
+          // out[slot(2i)] = x1[i] (pass-through), out[slot(2i+1)] = branch2[i]
+          const int nrow = col_ok ? (int)min((int64_t)32, p.M - m_base) : 0;   // rows this lane stores
           float* o = p.out + m_base * p.out_ld + p.omap.slot(2 * (col_ok ? i : 0));
           // rows 0..15 with xa, then re-arm xa for the next block; rows 16..31 with xb, re-arm xb
 #pragma unroll
-          for (int r = 0; r < 16; ++r)
-            if (col_ok && m_base + r < p.M)
-              *reinterpret_cast<float2*>(o + (int64_t)r * p.out_ld) = make_float2(xa[r], stg[r * kTcStgPitch + lane]);
+          for (int r = 0; r < 16; ++r, o += p.out_ld)
+            if (r < nrow) *reinterpret_cast<float2*>(o) = make_float2(xa[r], sl[r * kTcStgPitch]);
           if (c0 + 32 < p.Npad) fetch_x1(c0 + 32, 0, xa);
 #pragma unroll
-          for (int r = 16; r < 32; ++r)
-            if (col_ok && m_base + r < p.M)
-              *reinterpret_cast<float2*>(o + (int64_t)r * p.out_ld) = make_float2(xb[r - 16], stg[r * kTcStgPitch + lane]);
+          for (int r = 16; r < 32; ++r, o += p.out_ld)
+            if (r < nrow) *reinterpret_cast<float2*>(o) = make_float2(xb[r - 16], sl[r * kTcStgPitch]);
           if (c0 + 32 < p.Npad) fetch_x1(c0 + 32, 16, xb);
-          __syncwarp();
-        }
-      } else {
-        for (int c0 = 0; c0 < p.Npad; c0 += 16) {
-          float v[16];
-          load16(c0, v);
-          if (c0 + 16 >= p.Npad) release_acc();
-          if (!valid) continue;
-          if (vec) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              int n = c0 + j;
-              if (n + 3 < p.N) {
-                *reinterpret_cast<float4*>(orow + p.out_off + n) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  if (n + e < p.N) orow[p.out_off + n + e] = v[j + e];
-              }
-            }
+        } else {
+          const int col = vec ? p.out_off + i : p.omap.slot(p.out_off + (col_ok ? i : 0) * p.out_step);
+          if (!p.is3x3) {
+            const int nrow = col_ok ? (int)min((int64_t)32, p.M - m_base) : 0;
+            float* o = p.out + m_base * p.out_ld + col;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r, o += p.out_ld)
+              if (r < nrow) *o = sl[r * kTcStgPitch];
           } else {
-            // channel split / concat as a store permutation (slot map + stride)
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (c0 + j < p.N) orow[p.omap.slot(p.out_off + (c0 + j) * p.out_step)] = v[j];
+            // spatial tile: row -> pixel is not affine, take it from the lane that owns the row
+            const int64_t off = valid && true ? m * p.out_ld : -1;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              const int64_t offr = __shfl_sync(0xffffffffu, off, r);
+              if (col_ok && offr >= 0) p.out[offr + col] = sl[r * kTcStgPitch];
+            }
           }
         }
+        __syncwarp();
+        if (p.trace != nullptr && threadIdx.x == 0) {
+          tq2 = clock64();
+          YNB_TRACE(7, tq1 - tq0, tq2 - tq1);   // (tmem->smem cycles, smem->global cycles) of this block
+        }
       }
+      if (threadIdx.x == 0) YNB_TRACE(5, tile, 0);
       if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1; }
     }
+    if (p.tma_store && lane == 0) ptx::bulk_wait<0>();   // all output boxes have landed
   }
 
   ptx::tc_fence_before_sync();
@@ -484,6 +567,20 @@ inline bool make_tmap_nhwc(CUtensorMap* m, const float* base, int C, int W, int 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// rank-2 STORE map over an output view [rows][ld] exposing `cols` channels (multiple of 4):
+// boxes of 32 channels x 32 rows, 128-byte swizzle (matches the epilogue's staging layout).
+inline bool make_tmap_out(CUtensorMap* m, float* base, uint64_t cols, uint64_t rows, uint64_t ld) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
+         CUDA_SUCCESS;
+}
+
 // Weights packed for the tensor-core path: [Npad][Kpad] fp32, Kpad multiple of 32, split
 // into exact-tf32 hi and lo parts.
 struct TcWeights {
@@ -510,6 +607,7 @@ inline void split_tf32_host(float v, float* hi, float* lo) {
 // A fully described launch (tensor maps are baked at plan time).
 struct TcGemmLaunch {
   CUtensorMap tmA;
+  CUtensorMap tmOut;      // valid when p.tma_store
   const TcWeights* w = nullptr;
   TcGemmParams p;
   uint32_t smem = 0;
@@ -565,17 +663,18 @@ inline cudaError_t launch_tc_gemm(const TcGemmLaunch& L, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kTcSmemBudget + 2048);
+                                         kTcSmemBudget);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               kTcSmemBudget + 2048);
+                               kTcSmemBudget);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  const CUtensorMap& tmo = L.p.tma_store ? L.tmOut : L.tmA;   // unused unless tma_store
   if (L.p.pass != nullptr)
-    tc_gemm_kernel<true><<<L.grid, kTcThreads, L.smem, st>>>(L.tmA, L.w->tm_hi, L.w->tm_lo, L.p);
+    tc_gemm_kernel<true><<<L.grid, kTcThreads, L.smem, st>>>(L.tmA, L.w->tm_hi, L.w->tm_lo, tmo, L.p);
   else
-    tc_gemm_kernel<false><<<L.grid, kTcThreads, L.smem, st>>>(L.tmA, L.w->tm_hi, L.w->tm_lo, L.p);
+    tc_gemm_kernel<false><<<L.grid, kTcThreads, L.smem, st>>>(L.tmA, L.w->tm_hi, L.w->tm_lo, tmo, L.p);
   YNB_COUNT_LAUNCH();
   return cudaGetLastError();
 }

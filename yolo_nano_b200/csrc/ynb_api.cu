@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <functional>
@@ -105,7 +106,17 @@ struct ynb_engine {
   void* d_nms_ws = nullptr;
   int64_t nms_ws_bytes = 0;
   // host-call staging
-  float* d_x = nullptr;
+  float* d_x = nullptr;                // == slot[0].x
+  struct HostSlot {                    // double-buffered host I/O (ynb_submit_host / ynb_wait_host)
+    float* x = nullptr; float* boxes = nullptr; float* scores = nullptr; int32_t* cls = nullptr;
+    int32_t* counts = nullptr;
+    cudaEvent_t h2d = nullptr, done = nullptr;
+    bool busy = false;
+    int batch = 0;
+    float* ob = nullptr; float* os = nullptr; int32_t* oc = nullptr; int32_t* on = nullptr;   // host destinations
+    int* flag_host = nullptr;          // pinned: device error word of this step
+  } slot[2];
+  cudaStream_t s_copy = nullptr;       // H2D / D2H next to the compute stream
   const float* d_x_bound = nullptr;   // input of the forward in flight
   float* d_out_boxes = nullptr;
   float* d_out_scores = nullptr;
@@ -317,11 +328,18 @@ size_t layout_workspace(ynb_engine* e, int batch, int S, char* base) {
   e->d_cls = (int32_t*)raw((size_t)batch * n * 4);
   e->nms_ws_bytes = nms_workspace_bytes(batch, n);
   e->d_nms_ws = raw((size_t)e->nms_ws_bytes);
-  e->d_x = (float*)raw((size_t)batch * 3 * S * S * 4);
-  e->d_out_boxes = (float*)raw((size_t)batch * n * 16);
-  e->d_out_scores = (float*)raw((size_t)batch * n * 4);
-  e->d_out_cls = (int32_t*)raw((size_t)batch * n * 4);
-  e->d_out_counts = (int32_t*)raw((size_t)batch * 4);
+  for (int k = 0; k < 2; ++k) {
+    e->slot[k].x = (float*)raw((size_t)batch * 3 * S * S * 4);
+    e->slot[k].boxes = (float*)raw((size_t)batch * n * 16);
+    e->slot[k].scores = (float*)raw((size_t)batch * n * 4);
+    e->slot[k].cls = (int32_t*)raw((size_t)batch * n * 4);
+    e->slot[k].counts = (int32_t*)raw((size_t)batch * 4);
+  }
+  e->d_x = e->slot[0].x;
+  e->d_out_boxes = e->slot[0].boxes;
+  e->d_out_scores = e->slot[0].scores;
+  e->d_out_cls = e->slot[0].cls;
+  e->d_out_counts = e->slot[0].counts;
   e->d_err = (int*)raw(256);
   return bump.off;
 }
@@ -424,6 +442,12 @@ struct Planner {
     p.bias = pc.b_dev; p.act = c.act;
     p.pass = pass ? pass->p : nullptr; p.pass_ld = pass ? pass->ld : 0;
     p.err_flag = e->d_err;
+    p.tma_store = (!pass && out_step == 1 && out.map.gap == 0 && out_off % 4 == 0 && out.ld % 4 == 0) ? 1 : 0;
+    if (p.tma_store && !make_tmap_out(&L.tmOut, out.p + out_off, (uint64_t)round_up(pc.n, 4), (uint64_t)M,
+                                      (uint64_t)out.ld)) {
+      error = "cuTensorMapEncodeTiled failed for output of " + name;
+      return;
+    }
     if (!make_tmap_2d(&L.tmA, in.p + in_off, (uint64_t)pc.ktot, (uint64_t)M, (uint64_t)in.ld, kTcBM)) {
       error = "cuTensorMapEncodeTiled failed for input of " + name;
       return;
@@ -758,6 +782,11 @@ YNB_EXPORT int ynb_create(const ynb_config* cfg, ynb_engine** out) {
             cudaStreamCreateWithFlags(&e->s_side, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking) == cudaSuccess;
+  for (int k = 0; k < 2 && ok; ++k)
+    ok = cudaEventCreateWithFlags(&e->slot[k].h2d, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&e->slot[k].done, cudaEventDisableTiming) == cudaSuccess &&
+         cudaHostAlloc(&e->slot[k].flag_host, 64, cudaHostAllocDefault) == cudaSuccess;
   e->events.resize(64);
   for (auto& ev : e->events) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
@@ -782,6 +811,12 @@ YNB_EXPORT void ynb_destroy(ynb_engine* e) {
   for (auto ev : e->events) cudaEventDestroy(ev);
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_out) cudaEventDestroy(e->ev_out);
+  for (int k = 0; k < 2; ++k) {
+    if (e->slot[k].h2d) cudaEventDestroy(e->slot[k].h2d);
+    if (e->slot[k].done) cudaEventDestroy(e->slot[k].done);
+    if (e->slot[k].flag_host) cudaFreeHost(e->slot[k].flag_host);
+  }
+  if (e->s_copy) cudaStreamDestroy(e->s_copy);
   if (e->s_main) cudaStreamDestroy(e->s_main);
   if (e->s_side) cudaStreamDestroy(e->s_side);
   for (PackedConv& pc : e->convs) {
@@ -972,40 +1007,67 @@ YNB_EXPORT int ynb_forward_detect(ynb_engine* e, const float* x_dev, int32_t bat
   return leave(e, user);
 }
 
-YNB_EXPORT int ynb_detect_host(ynb_engine* e, const float* x_host, int32_t batch, float* ob, float* os,
-                               int32_t* oc, int32_t* on, void* stream) {
+// Host-buffer path, split in two so that consecutive steps overlap: submit(i+1) copies the
+// next batch over PCIe on the copy stream while the compute stream is still busy with step i.
+YNB_EXPORT int ynb_submit_host(ynb_engine* e, int32_t slot_id, const float* x_host, int32_t batch, float* ob,
+                               float* os, int32_t* oc, int32_t* on, void* stream) {
   if (!e || !x_host || !ob || !os || !oc || !on) return fail(e, YNB_ERR_INVALID, "null argument");
+  if (slot_id < 0 || slot_id > 1) return fail(e, YNB_ERR_INVALID, "slot must be 0 or 1");
   cudaStream_t user = (cudaStream_t)stream;
   CounterScope cs(e);
   Plan* plan = nullptr;
   int rc = prepare(e, batch, &plan);
-  if (rc || (rc = enter(e, user))) return rc;
-  cudaStream_t st = e->s_main;
-  const int64_t n = e->N();
+  if (rc) return rc;
+  ynb_engine::HostSlot& sl = e->slot[slot_id];
+  if (sl.busy) return fail(e, YNB_ERR_STATE, "slot still in flight: call ynb_wait_host first");
   const size_t img = (size_t)3 * e->S * e->S * 4;
-  CUDA_TRY(e, cudaMemcpyAsync(e->d_x, x_host, img * batch, cudaMemcpyHostToDevice, st));
-  if ((rc = detect_device(e, e->d_x, batch, e->d_out_boxes, e->d_out_scores, e->d_out_cls, e->d_out_counts)))
-    return rc;
-  // counts (and the device error word) first, then only the kept rows of each image cross PCIe
-  int flag = 0;
-  CUDA_TRY(e, cudaMemcpyAsync(on, e->d_out_counts, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(e, cudaMemcpyAsync(&flag, e->d_err, 4, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(e, cudaStreamSynchronize(st));
-  if (flag != 0) {
-    cudaMemsetAsync(e->d_err, 0, 4, st);
-    return fail(e, YNB_ERR_CUDA, "tensor-core pipeline timed out waiting on mbarrier (code " + std::to_string(flag) + ")");
-  }
-  for (int b = 0; b < batch; ++b) {
-    size_t k = (size_t)on[b];
-    if (k == 0) continue;
-    CUDA_TRY(e, cudaMemcpyAsync(ob + (size_t)b * n * 4, e->d_out_boxes + (size_t)b * n * 4, k * 16,
-                                cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(e, cudaMemcpyAsync(os + (size_t)b * n, e->d_out_scores + (size_t)b * n, k * 4,
-                                cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(e, cudaMemcpyAsync(oc + (size_t)b * n, e->d_out_cls + (size_t)b * n, k * 4, cudaMemcpyDeviceToHost, st));
-  }
-  CUDA_TRY(e, cudaStreamSynchronize(st));
+  // order after the caller's stream, then: H2D on the copy stream, compute on the main stream
+  CUDA_TRY(e, cudaEventRecord(e->ev_in, user));
+  CUDA_TRY(e, cudaStreamWaitEvent(e->s_copy, e->ev_in, 0));
+  CUDA_TRY(e, cudaMemcpyAsync(sl.x, x_host, img * batch, cudaMemcpyHostToDevice, e->s_copy));
+  CUDA_TRY(e, cudaEventRecord(sl.h2d, e->s_copy));
+  CUDA_TRY(e, cudaStreamWaitEvent(e->s_main, sl.h2d, 0));
+  if ((rc = detect_device(e, sl.x, batch, sl.boxes, sl.scores, sl.cls, sl.counts))) return rc;
+  CUDA_TRY(e, cudaMemcpyAsync(on, sl.counts, (size_t)batch * 4, cudaMemcpyDeviceToHost, e->s_main));
+  CUDA_TRY(e, cudaMemcpyAsync(sl.flag_host, e->d_err, 4, cudaMemcpyDeviceToHost, e->s_main));
+  CUDA_TRY(e, cudaEventRecord(sl.done, e->s_main));
+  sl.busy = true; sl.batch = batch; sl.ob = ob; sl.os = os; sl.oc = oc; sl.on = on;
   return YNB_OK;
+}
+
+YNB_EXPORT int ynb_wait_host(ynb_engine* e, int32_t slot_id) {
+  if (!e || slot_id < 0 || slot_id > 1) return fail(e, YNB_ERR_INVALID, "bad slot");
+  ynb_engine::HostSlot& sl = e->slot[slot_id];
+  if (!sl.busy) return fail(e, YNB_ERR_STATE, "nothing submitted on this slot");
+  CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+  CUDA_TRY(e, cudaEventSynchronize(sl.done));
+  sl.busy = false;
+  if (*sl.flag_host != 0) {
+    int code = *sl.flag_host;
+    cudaMemsetAsync(e->d_err, 0, 4, e->s_main);
+    return fail(e, YNB_ERR_CUDA, "tensor-core pipeline timed out waiting on mbarrier (code " + std::to_string(code) + ")");
+  }
+  // counts are on the host now: only the kept rows of each image cross PCIe (copy stream)
+  const int64_t n = e->N();
+  for (int b = 0; b < sl.batch; ++b) {
+    size_t k = (size_t)sl.on[b];
+    if (k == 0) continue;
+    CUDA_TRY(e, cudaMemcpyAsync(sl.ob + (size_t)b * n * 4, sl.boxes + (size_t)b * n * 4, k * 16, cudaMemcpyDeviceToHost,
+                                e->s_copy));
+    CUDA_TRY(e, cudaMemcpyAsync(sl.os + (size_t)b * n, sl.scores + (size_t)b * n, k * 4, cudaMemcpyDeviceToHost,
+                                e->s_copy));
+    CUDA_TRY(e, cudaMemcpyAsync(sl.oc + (size_t)b * n, sl.cls + (size_t)b * n, k * 4, cudaMemcpyDeviceToHost, e->s_copy));
+  }
+  CUDA_TRY(e, cudaStreamSynchronize(e->s_copy));
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_detect_host(ynb_engine* e, const float* x_host, int32_t batch, float* ob, float* os,
+                               int32_t* oc, int32_t* on, void* stream) {
+  if (!e) return YNB_ERR_INVALID;
+  if (e->slot[0].busy) return fail(e, YNB_ERR_STATE, "slot 0 in flight (ynb_submit_host without ynb_wait_host)");
+  int rc = ynb_submit_host(e, 0, x_host, batch, ob, os, oc, on, stream);
+  return rc ? rc : ynb_wait_host(e, 0);
 }
 
 YNB_EXPORT int ynb_tap_shape(const ynb_engine* e, const char* tap, int32_t* c, int32_t* h, int32_t* w) {
@@ -1130,8 +1192,23 @@ YNB_EXPORT int ynb_pwconv_tc(const float* in, int32_t in_ld, int32_t in_off, flo
   p.a_box_bytes = kTcAStageBytes;
   p.out = out; p.out_ld = out_ld; p.out_off = out_off; p.out_step = out_step; p.omap = dense_map();
   p.bias = b_dev; p.act = act; p.err_flag = d_err;
+  long long* d_trace = nullptr;
+  const int trace_cap = 4096;
+  const bool want_trace = getenv("YNB_TC_TRACE") != nullptr;
+  if (want_trace) {
+    UNIT_TRY(cudaMalloc(&d_trace, (1 + 4 * trace_cap) * 8));
+    UNIT_TRY(cudaMemset(d_trace, 0, (1 + 4 * trace_cap) * 8));
+    p.trace = d_trace; p.trace_cap = trace_cap;
+  }
+  p.tma_store = (out_step == 1 && out_off % 4 == 0 && getenv("YNB_TC_NO_TMA_STORE") == nullptr) ? 1 : 0;
+  if (getenv("YNB_TC_PASS") != nullptr && cin >= cout && out_ld >= 2 * cout) {
+    // timeline hook for the interleave epilogue: pass-through = first `cout` channels of the input rows
+    p.pass = in; p.pass_ld = in_ld; p.tma_store = 0; p.out_off = 1; p.out_step = 2;
+  }
   if (!make_tmap_2d(&t.tm_hi, t.hi, t.Kpad, t.Npad, t.Kpad, t.Npad) ||
       !make_tmap_2d(&t.tm_lo, t.lo, t.Kpad, t.Npad, t.Kpad, t.Npad) ||
+      (p.tma_store && !make_tmap_out(&L.tmOut, out + out_off, (uint64_t)round_up(cout, 4), (uint64_t)pixels,
+                                     (uint64_t)out_ld)) ||
       !make_tmap_2d(&L.tmA, in + in_off, cin, pixels, in_ld, kTcBM) || !tc_plan_smem(L)) {
     rc = fail(nullptr, YNB_ERR_CUDA, "ynb_pwconv_tc: tensor map / smem planning failed");
   } else {
@@ -1142,7 +1219,17 @@ YNB_EXPORT int ynb_pwconv_tc(const float* in, int32_t in_ld, int32_t in_off, flo
     if (r == cudaSuccess) r = cudaMemcpy(&flag, d_err, 4, cudaMemcpyDeviceToHost);
     if (r != cudaSuccess) rc = fail(nullptr, YNB_ERR_CUDA, std::string("ynb_pwconv_tc: ") + cudaGetErrorString(r));
     else if (flag) rc = fail(nullptr, YNB_ERR_CUDA, "ynb_pwconv_tc: mbarrier timeout code " + std::to_string(flag));
+    if (want_trace && r == cudaSuccess) {
+      std::vector<long long> h(1 + 4 * trace_cap);
+      cudaMemcpy(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost);
+      int n = (int)std::min<long long>(*reinterpret_cast<int*>(h.data()), trace_cap);
+      fprintf(stderr, "YNB_TC_TRACE stages=%d resident=%d nmain=%d acc_stages=%d steps=%d grid=%u events=%d\n",
+              p.num_stages, p.w_resident, p.nmain, p.acc_stages, p.num_steps, L.grid, n);
+      for (int i = 0; i < n; ++i)
+        fprintf(stderr, "TRACE %lld %lld %lld %lld\n", h[1 + 4 * i], h[2 + 4 * i], h[3 + 4 * i], h[4 + 4 * i]);
+    }
   }
+  if (d_trace) cudaFree(d_trace);
   cudaFree(t.hi); cudaFree(t.lo); cudaFree(d_err);
   return rc;
 }

@@ -188,6 +188,19 @@ class Engine:
                     "ynb_detect_host")
         return boxes, scores, cls, counts
 
+    def submit_host(self, slot: int, x_host: torch.Tensor, out_host):
+        """Asynchronous half of detect_host: H2D + compute are enqueued, nothing is waited for.
+        `x_host` and `out_host` (pinned) must stay alive until wait_host(slot)."""
+        if x_host.is_cuda or x_host.dtype != torch.float32 or x_host.dim() != 4 or not x_host.is_contiguous():
+            raise EngineError("submit_host wants a contiguous float32 host tensor [B,3,S,S]")
+        boxes, scores, cls, counts = out_host
+        self._check(self.lib.ynb_submit_host(self._h, int(slot), _ptr(x_host), x_host.shape[0], _ptr(boxes),
+                                             _ptr(scores), _ptr(cls), _ptr(counts), _stream_ptr(self.device)),
+                    "ynb_submit_host")
+
+    def wait_host(self, slot: int):
+        self._check(self.lib.ynb_wait_host(self._h, int(slot)), "ynb_wait_host")
+
     def profile(self, x: torch.Tensor):
         """One forward_detect with a CUDA-event pair around every kernel launch.
         Returns [(label, kernel family, ms, algorithmic bytes, flops), ...]."""
