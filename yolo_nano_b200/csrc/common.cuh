@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <limits.h>
+#include <stdlib.h>
 
 #include "yolonano_b200.h"
 
@@ -37,6 +38,36 @@ struct LaunchCounter {
   int64_t n = 0;
 };
 extern thread_local LaunchCounter* g_counter;   // set by the engine around a forward
+
+// Programmatic dependent launch: every kernel of the forward is launched with the
+// programmatic-stream-serialization attribute, lets its successor start early
+// (pdl_trigger at the top) and waits for its predecessor's results right before its first
+// dependent global access (pdl_wait) — prologues (barrier init, TMEM alloc, weight loads)
+// overlap the previous kernel's tail instead of adding to the critical path.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("YNB_NO_PDL") ? 0 : 1;
+  return v == 1;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 #define YNB_COUNT_LAUNCH()                  \
   do {                                      \

@@ -46,6 +46,8 @@ decode_level_kernel(DecodeParams p) {
   const int64_t cells_total = (int64_t)p.batch * p.G * p.G;
   const int64_t cell0 = (int64_t)blockIdx.x * kDecCells;
   const int ncell = (int)min((int64_t)kDecCells, cells_total - cell0);
+  pdl_trigger();
+  pdl_wait();
   {
     const float4* src = reinterpret_cast<const float4*>(p.raw + cell0 * p.ld);
     const int ld4 = p.ld >> 2;
@@ -107,9 +109,9 @@ inline cudaError_t launch_decode_level(const DecodeParams& p, cudaStream_t st) {
   if (cells <= 0) return cudaSuccess;
   if (p.A != 3 || (p.ld & 3)) return cudaErrorInvalidValue;
   size_t smem = (size_t)kDecCells * (p.ld + 1) * 4;
-  decode_level_kernel<<<(unsigned)((cells + kDecCells - 1) / kDecCells), kDecCells * 3, smem, st>>>(p);
+  cudaError_t r = launch_pdl(decode_level_kernel, dim3((unsigned)((cells + kDecCells - 1) / kDecCells)), dim3(kDecCells * 3), smem, st, p);
   YNB_COUNT_LAUNCH();
-  return cudaGetLastError();
+  return r;
 }
 
 // =====================================================================================
@@ -130,6 +132,8 @@ nms_keys_kernel(const float* __restrict__ scores, const int32_t* __restrict__ cl
                 uint64_t* __restrict__ keys, uint8_t* __restrict__ keep, int64_t N, int Npad,
                 float conf_thresh) {
   const int b = blockIdx.y;
+  pdl_trigger();
+  pdl_wait();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Npad; i += gridDim.x * blockDim.x) {
     uint64_t k = kInvalidKey;
     if (i < N) {
@@ -153,6 +157,8 @@ nms_sort_kernel(uint64_t* __restrict__ keys_g, int32_t* __restrict__ seg_g, int 
   uint64_t* k = IN_SMEM ? s_keys : g;
   int32_t* seg = seg_g + (int64_t)blockIdx.x * (C + 1);
   const int tid = threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (IN_SMEM) {
     for (int i = tid; i < Npad; i += 1024) s_keys[i] = g[i];
     __syncthreads();
@@ -248,26 +254,44 @@ __device__ __forceinline__ unsigned long long coarse_mask(float4 b, float area) 
   return m;
 }
 
-constexpr int kNmsChunk = 64;
+constexpr int kNmsChunk = 512;                 // candidates resolved per round (= threads)
 constexpr int kNmsThreads = 512;
-constexpr int kNmsMaxWords = 1024;   // 65536 candidates per segment, 64 per word
+constexpr int kNmsWpr = kNmsChunk / 64;        // 64-bit words per suppression row
+constexpr int kNmsMaxWords = 1024;             // 65536 candidates per segment, 64 per word
 
+struct NmsSmem {
+  unsigned long long removed[kNmsMaxWords];          // segment-wide "suppressed" bitmap
+  float4 cbox[kNmsChunk];                            // chunk candidates, visiting order
+  float carea[kNmsChunk];
+  unsigned long long cmask[kNmsChunk];               // coarse 8x8 occupancy masks
+  unsigned long long rows[kNmsChunk][kNmsWpr];       // rows[r] bit j: r suppresses j (j > r)
+  unsigned long long cellocc[64][kNmsWpr];           // coarse cell -> chunk candidates touching it
+  unsigned long long kept[kNmsWpr];                  // chunk candidates kept by this round
+};
+
+__device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) {
+  return __shfl_sync(0xffffffffu, v, src);
+}
+
+// One CTA per (image, class) segment; rounds of 512 candidates:
+//   A  load the chunk (boxes, areas, coarse masks)
+//   B  coarse-cell inverted index of the chunk (cell -> 512-bit set of candidates touching it)
+//   C  suppression rows: candidate r against the later candidates that share a coarse cell
+//   D  one warp resolves the chunk greedily, 64 rows at a time, with shuffles on the diagonal
+//      64x64 blocks and deferred OR-propagation to the later words
+//   E  every later candidate of the segment against the kept boxes that share a cell with it
+// The pair tests are exactly those of the reference loop (kept box vs every later survivor),
+// minus pairs that cannot overlap.
 __global__ void __launch_bounds__(kNmsThreads)
 nms_segment_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ seg,
                    const float* __restrict__ boxes, float4* sbox_scratch, uint8_t* __restrict__ keep,
                    int64_t N, int Npad, int C, IouOps op) {
-  __shared__ unsigned long long s_removed[kNmsMaxWords];
-  __shared__ float4 s_cbox[kNmsChunk];                // chunk candidates (visiting order)
-  __shared__ float s_carea[kNmsChunk];
-  __shared__ unsigned long long s_cmask[kNmsChunk];   // their coarse occupancy masks
-  __shared__ unsigned long long s_mask[kNmsChunk];    // in-chunk suppression rows
-  __shared__ float4 s_kbox[kNmsChunk];                // boxes kept in this chunk, compacted
-  __shared__ float s_karea[kNmsChunk];
-  __shared__ unsigned long long s_cell[64];           // coarse cell -> bitmap of kept boxes touching it
-  __shared__ int s_kept[kNmsChunk];
-  __shared__ int s_nkept;
+  extern __shared__ __align__(16) unsigned char nms_smem_raw[];
+  NmsSmem& S = *reinterpret_cast<NmsSmem*>(nms_smem_raw);
 
-  const int b = blockIdx.y, c = blockIdx.x, tid = threadIdx.x;
+  const int b = blockIdx.y, c = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  pdl_trigger();
+  pdl_wait();
   const int s0 = seg[(int64_t)b * (C + 1) + c];
   const int n = seg[(int64_t)b * (C + 1) + c + 1] - s0;
   if (n <= 0) return;
@@ -279,94 +303,149 @@ nms_segment_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict_
 
   // gather the segment's boxes in visiting order (coalesced from here on)
   for (int j = tid; j < n; j += kNmsThreads) sb[j] = bx[key_idx(k[s0 + j])];
-  for (int j = tid; j < (n + 63) / 64; j += kNmsThreads) s_removed[j] = 0ull;
+  for (int j = tid; j < (n + 63) / 64 + kNmsWpr; j += kNmsThreads)
+    if (j < kNmsMaxWords) S.removed[j] = 0ull;
   __syncthreads();
 
   for (int c0 = 0; c0 < n; c0 += kNmsChunk) {
     const int cn = min(kNmsChunk, n - c0);
-    if (tid < kNmsChunk) {
+    // ---- A: chunk -------------------------------------------------------------------------
+    {
       float4 v = tid < cn ? sb[c0 + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
       float a = box_area(v);
-      s_cbox[tid] = v;
-      s_carea[tid] = a;
-      s_cmask[tid] = use_masks ? coarse_mask(v, a) : ~0ull;
+      S.cbox[tid] = v;
+      S.carea[tid] = a;
+      S.cmask[tid] = tid < cn ? (use_masks ? coarse_mask(v, a) : ~0ull) : 0ull;
     }
     __syncthreads();
-    // (1) in-chunk mask: thread -> (row, 8-column octet); octets of a row sit in adjacent lanes
+    // ---- B: inverted index: thread -> (cell, word) ------------------------------------------
     {
-      int row = tid >> 3, q = tid & 7;
-      unsigned long long bits = 0ull;
-      if (row < cn) {
-        float4 a = s_cbox[row];
-        float aa = s_carea[row];
-        unsigned long long am = s_cmask[row];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          int j = q * 8 + e;
-          if (j > row && j < cn && (am & s_cmask[j]) && suppresses(a, aa, s_cbox[j], s_carea[j], op)) bits |= 1ull << j;
-        }
-      }
-      bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
-      bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
-      bits |= __shfl_xor_sync(0xffffffffu, bits, 4);
-      if (q == 0) s_mask[row] = bits;
-    }
-    __syncthreads();
-    // (2) serial resolve of the chunk (c0 is a multiple of 64: one word of the removed set)
-    if (tid == 0) {
-      unsigned long long rem = s_removed[c0 >> 6];
-      int nk = 0;
-      for (int j = 0; j < cn; ++j) {
-        if (!((rem >> j) & 1ull)) {
-          s_kept[nk++] = j;
-          rem |= s_mask[j];
-        }
-      }
-      s_nkept = nk;
-    }
-    __syncthreads();
-    const int nk = s_nkept;
-    if (c0 + kNmsChunk >= n) {   // last chunk: nothing left to suppress
-      if (tid < nk) kp[key_idx(k[s0 + c0 + s_kept[tid]])] = 1;
-      break;
-    }
-    // (2b) compact the kept boxes and index them by coarse cell
-    if (tid < nk) {
-      int r = s_kept[tid];
-      s_kbox[tid] = s_cbox[r];
-      s_karea[tid] = s_carea[r];
-      kp[key_idx(k[s0 + c0 + r])] = 1;
-    } else if (tid >= 64 && tid < 128) {
-      const int cell = tid - 64;
+      const int cell = tid >> 3, w = tid & 7;
       unsigned long long m = 0ull;
-      for (int q = 0; q < nk; ++q) m |= ((s_cmask[s_kept[q]] >> cell) & 1ull) << q;
-      s_cell[cell] = m;
+#pragma unroll 8
+      for (int q = 0; q < 64; ++q) m |= ((S.cmask[w * 64 + q] >> cell) & 1ull) << q;
+      S.cellocc[cell][w] = m;
     }
     __syncthreads();
-    // (3) every later candidate against the kept boxes whose coarse cells it touches
+    // ---- C: suppression row of candidate `tid` --------------------------------------------------
+    {
+      unsigned long long rw[kNmsWpr];
+#pragma unroll
+      for (int w = 0; w < kNmsWpr; ++w) rw[w] = 0ull;
+      if (tid < cn) {
+        const float4 a = S.cbox[tid];
+        const float aa = S.carea[tid];
+        unsigned long long am = S.cmask[tid];
+        unsigned long long cand[kNmsWpr];
+        if (am == ~0ull) {
+#pragma unroll
+          for (int w = 0; w < kNmsWpr; ++w) cand[w] = ~0ull;
+        } else {
+#pragma unroll
+          for (int w = 0; w < kNmsWpr; ++w) cand[w] = 0ull;
+          while (am) {
+            const int cell = __ffsll((long long)am) - 1;
+            am &= am - 1;
+#pragma unroll
+            for (int w = 0; w < kNmsWpr; ++w) cand[w] |= S.cellocc[cell][w];
+          }
+        }
+        // only later candidates (j > tid) that exist (j < cn).  Degenerate boxes carry the all-ones
+        // mask, i.e. they sit in every cell of the index and are met from any row.
+#pragma unroll
+        for (int w = 0; w < kNmsWpr; ++w) {
+          const int base = w * 64;
+          unsigned long long later = tid >= base + 63 ? 0ull : (tid < base ? ~0ull : (~0ull << (tid - base + 1)));
+          unsigned long long exist = cn >= base + 64 ? ~0ull : (cn <= base ? 0ull : ((1ull << (cn - base)) - 1ull));
+          unsigned long long todo = cand[w] & later & exist;
+          while (todo) {
+            const int q = __ffsll((long long)todo) - 1;
+            todo &= todo - 1;
+            const int j = base + q;
+            if (suppresses(a, aa, S.cbox[j], S.carea[j], op)) rw[w] |= 1ull << q;
+          }
+        }
+      }
+#pragma unroll
+      for (int w = 0; w < kNmsWpr; ++w) S.rows[tid][w] = rw[w];
+    }
+    __syncthreads();
+    // ---- D: greedy resolve of the chunk by warp 0 ----------------------------------------------
+    if (tid < 32) {
+      // rem: lane w (< 8) holds the suppressed bits of block w (from earlier rounds, then from
+      // kept rows of earlier blocks of this round); pend[w']: this lane's not-yet-reduced
+      // contribution to block w' from the kept rows it owns
+      unsigned long long rem = lane < kNmsWpr ? S.removed[(c0 >> 6) + lane] : 0ull;
+      unsigned long long pend[kNmsWpr];
+#pragma unroll
+      for (int w = 0; w < kNmsWpr; ++w) pend[w] = 0ull;
+      unsigned long long my_kept = 0ull;
+#pragma unroll
+      for (int w = 0; w < kNmsWpr; ++w) {
+        const int base = w * 64;
+        // fold the pending contributions for this block (OR-reduce over the warp)
+        unsigned long long inc = pend[w];
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) inc |= __shfl_xor_sync(0xffffffffu, inc, d);
+        unsigned long long cur = shfl64(rem, w) | inc;
+        const unsigned long long exist = cn >= base + 64 ? ~0ull : (cn <= base ? 0ull : ((1ull << (cn - base)) - 1ull));
+        // diagonal block: lane owns rows base+lane and base+32+lane
+        const unsigned long long d0 = S.rows[base + lane][w], d1 = S.rows[base + 32 + lane][w];
+        unsigned long long alive = ~cur & exist, kept_bits = 0ull;
+        while (alive) {
+          const int j = __ffsll((long long)alive) - 1;
+          kept_bits |= 1ull << j;
+          const unsigned long long dj = shfl64(j < 32 ? d0 : d1, j & 31);
+          alive &= ~dj;
+          alive &= ~(1ull << j);
+        }
+        if (lane == w) my_kept = kept_bits;
+        // kept rows owned by this lane suppress candidates of the later blocks
+        const bool k0 = (kept_bits >> lane) & 1ull, k1 = (kept_bits >> (lane + 32)) & 1ull;
+#pragma unroll
+        for (int w2 = w + 1; w2 < kNmsWpr; ++w2) {
+          if (k0) pend[w2] |= S.rows[base + lane][w2];
+          if (k1) pend[w2] |= S.rows[base + 32 + lane][w2];
+        }
+      }
+      if (lane < kNmsWpr) S.kept[lane] = my_kept;
+    }
+    __syncthreads();
+    // ---- E: flags of the kept candidates; kept boxes vs every later candidate ------------------
+    if ((S.kept[tid >> 6] >> (tid & 63)) & 1ull) kp[key_idx(k[s0 + c0 + tid])] = 1;
     for (int j = c0 + kNmsChunk + tid; j < n; j += kNmsThreads) {
-      if ((s_removed[j >> 6] >> (j & 63)) & 1ull) continue;
+      if ((S.removed[j >> 6] >> (j & 63)) & 1ull) continue;
       const float4 v = sb[j];
       const float va = box_area(v);
       unsigned long long vm = use_masks ? coarse_mask(v, va) : ~0ull;
-      unsigned long long hits = 0ull;
+      unsigned long long hits[kNmsWpr];
       if (vm == ~0ull) {
-        hits = nk >= 64 ? ~0ull : ((1ull << nk) - 1ull);
+#pragma unroll
+        for (int w = 0; w < kNmsWpr; ++w) hits[w] = S.kept[w];
       } else {
+#pragma unroll
+        for (int w = 0; w < kNmsWpr; ++w) hits[w] = 0ull;
         while (vm) {
-          int cell = __ffsll((long long)vm) - 1;
+          const int cell = __ffsll((long long)vm) - 1;
           vm &= vm - 1;
-          hits |= s_cell[cell];
+#pragma unroll
+          for (int w = 0; w < kNmsWpr; ++w) hits[w] |= S.cellocc[cell][w];
+        }
+#pragma unroll
+        for (int w = 0; w < kNmsWpr; ++w) hits[w] &= S.kept[w];
+      }
+      bool gone = false;
+#pragma unroll
+      for (int w = 0; w < kNmsWpr; ++w) {
+        unsigned long long h = hits[w];
+        while (h && !gone) {
+          const int q = __ffsll((long long)h) - 1;
+          h &= h - 1;
+          const int r = w * 64 + q;
+          if (suppresses(S.cbox[r], S.carea[r], v, va, op)) gone = true;
         }
       }
-      while (hits) {   // ascending q = visiting order of the kept boxes
-        int q = __ffsll((long long)hits) - 1;
-        hits &= hits - 1;
-        if (suppresses(s_kbox[q], s_karea[q], v, va, op)) {
-          atomicOr(&s_removed[j >> 6], 1ull << (j & 63));
-          break;
-        }
-      }
+      if (gone) atomicOr(&S.removed[j >> 6], 1ull << (j & 63));
     }
     __syncthreads();
   }
@@ -386,6 +465,8 @@ nms_compact_kernel(const uint8_t* __restrict__ keep, const float* __restrict__ b
   const int per = (int)((N + 1023) / 1024);
   const int beg = min((int)N, tid * per), end = min((int)N, beg + per);
   const uint8_t* kp = keep + (int64_t)b * N;
+  pdl_trigger();
+  pdl_wait();
   int cnt = 0;
   for (int i = beg; i < end; ++i) cnt += kp[i];
   // block exclusive scan
@@ -460,7 +541,8 @@ inline cudaError_t launch_nms(const float* boxes, const float* scores, const int
   uint8_t* keep = keep_out ? keep_out : w.keep;
   {
     dim3 grid((Npad + 255) / 256, batch);
-    nms_keys_kernel<<<grid, 256, 0, st>>>(scores, cls, w.keys, keep, N, Npad, conf);
+    cudaError_t r = launch_pdl(nms_keys_kernel, grid, dim3(256), 0, st, scores, cls, w.keys, keep, N, Npad, conf);
+    if (r != cudaSuccess) return r;
     YNB_COUNT_LAUNCH();
   }
   {
@@ -473,22 +555,33 @@ inline cudaError_t launch_nms(const float* boxes, const float* scores, const int
         if (e != cudaSuccess) return e;
         attr_set = true;
       }
-      nms_sort_kernel<true><<<batch, 1024, smem, st>>>(w.keys, w.seg, Npad, num_classes);
+      cudaError_t r = launch_pdl(nms_sort_kernel<true>, dim3(batch), dim3(1024), smem, st, w.keys, w.seg, Npad, num_classes);
+      if (r != cudaSuccess) return r;
     } else {
-      nms_sort_kernel<false><<<batch, 1024, 0, st>>>(w.keys, w.seg, Npad, num_classes);
+      cudaError_t r = launch_pdl(nms_sort_kernel<false>, dim3(batch), dim3(1024), 0, st, w.keys, w.seg, Npad, num_classes);
+      if (r != cudaSuccess) return r;
     }
     YNB_COUNT_LAUNCH();
   }
   {
     dim3 grid(num_classes, batch);
     IouOps op{thr, diou != 0};
-    nms_segment_kernel<<<grid, kNmsThreads, 0, st>>>(w.keys, w.seg, boxes, w.sbox, keep, N, Npad, num_classes, op);
+    static bool seg_attr = false;
+    if (!seg_attr) {
+      cudaError_t e2 = cudaFuncSetAttribute(nms_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)sizeof(NmsSmem));
+      if (e2 != cudaSuccess) return e2;
+      seg_attr = true;
+    }
+    cudaError_t r = launch_pdl(nms_segment_kernel, grid, dim3(kNmsThreads), sizeof(NmsSmem), st, w.keys, w.seg, boxes,
+                               w.sbox, keep, N, Npad, num_classes, op);
+    if (r != cudaSuccess) return r;
     YNB_COUNT_LAUNCH();
   }
-  nms_compact_kernel<<<batch, 1024, 0, st>>>(keep, boxes, scores, cls, out_boxes, out_scores, out_cls,
-                                              out_counts, N);
+  cudaError_t r = launch_pdl(nms_compact_kernel, dim3(batch), dim3(1024), 0, st, (const uint8_t*)keep, boxes, scores, cls,
+                             out_boxes, out_scores, out_cls, out_counts, N);
   YNB_COUNT_LAUNCH();
-  return cudaGetLastError();
+  return r;
 }
 
 }  // namespace ynb

@@ -150,6 +150,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * kTcMaxStages + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
 
   if (warp == 8 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -191,16 +192,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int acc_cols = p.Npad * p.nacc;   // TMEM columns per accumulator stage
   const uint32_t step_tx = p.a_box_bytes + (p.w_resident ? 0 : w_chunk_bytes * (split ? 2 : 1));
 
+  // Weights do not depend on the previous kernel: the resident W planes are requested before
+  // the programmatic-dependency wait, i.e. while the predecessor is still draining.
+  if (warp == 8 && lane == 0 && p.w_resident) {
+    ptx::mbar_arrive_expect_tx(w_full, w_res_bytes);
+    for (int st = 0; st < p.num_steps; ++st) {
+      ptx::tma_load_2d(w_hi_ptr(0, st), &tmWhi, w_full, st * kTcBK, 0);
+      if (split) ptx::tma_load_2d(w_lo_ptr(0, st), &tmWlo, w_full, st * kTcBK, 0);
+    }
+  }
+  pdl_wait();
+
   if (warp == 8) {
     // ================= TMA producer =================
     if (lane == 0) {
-      if (p.w_resident) {
-        ptx::mbar_arrive_expect_tx(w_full, w_res_bytes);
-        for (int st = 0; st < p.num_steps; ++st) {
-          ptx::tma_load_2d(w_hi_ptr(0, st), &tmWhi, w_full, st * kTcBK, 0);
-          if (split) ptx::tma_load_2d(w_lo_ptr(0, st), &tmWlo, w_full, st * kTcBK, 0);
-        }
-      }
       int s = 0;
       uint32_t ph = 0;
       bool ok = true;
@@ -648,7 +653,8 @@ inline bool tc_plan_smem(TcGemmLaunch& L) {
     for (int stages = kTcMaxStages; stages >= 2; --stages) {
       if (stages > p.num_steps * 4 && stages > 2) continue;
       TcSmemLayout lay = tc_smem_layout(p.Npad, p.num_steps, stages, resident != 0, split);
-      if (lay.total <= (uint32_t)kTcSmemBudget && (resident == 0 || stages >= 3 || p.num_steps <= 2)) {
+      static const bool res2 = getenv("YNB_TC_RES2") != nullptr;   // experiment: W resident with 2 A stages
+      if (lay.total <= (uint32_t)kTcSmemBudget && (resident == 0 || stages >= 3 || p.num_steps <= 2 || res2)) {
         p.num_stages = stages;
         p.w_resident = resident;
         L.smem = lay.total;
@@ -671,12 +677,10 @@ inline cudaError_t launch_tc_gemm(const TcGemmLaunch& L, cudaStream_t st) {
     attr_set = true;
   }
   const CUtensorMap& tmo = L.p.tma_store ? L.tmOut : L.tmA;   // unused unless tma_store
-  if (L.p.pass != nullptr)
-    tc_gemm_kernel<true><<<L.grid, kTcThreads, L.smem, st>>>(L.tmA, L.w->tm_hi, L.w->tm_lo, tmo, L.p);
-  else
-    tc_gemm_kernel<false><<<L.grid, kTcThreads, L.smem, st>>>(L.tmA, L.w->tm_hi, L.w->tm_lo, tmo, L.p);
+  cudaError_t r = launch_pdl(L.p.pass != nullptr ? tc_gemm_kernel<true> : tc_gemm_kernel<false>, dim3(L.grid),
+                             dim3(kTcThreads), (size_t)L.smem, st, L.tmA, L.w->tm_hi, L.w->tm_lo, tmo, L.p);
   YNB_COUNT_LAUNCH();
-  return cudaGetLastError();
+  return r;
 }
 
 // Spatial tile (TW x TH <= 128 pixels) for the 3x3 path that wastes the fewest MMA rows.

@@ -42,6 +42,8 @@ stem_pool_kernel(const float* __restrict__ x, float* __restrict__ out, const __g
   const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;   // first conv row / col of the tile
   const int iy0 = 2 * cy0 - 1, ix0 = 2 * cx0 - 1;   // first input row / col
   const int tid = threadIdx.x;
+  pdl_trigger();
+  pdl_wait();          // the previous forward may still be reading / writing these buffers
 
   const float* xb = x + (size_t)b * 3 * S * S;
   for (int i = tid; i < 3 * kStemIn * kStemIn; i += kStemThreads) {
@@ -99,9 +101,9 @@ inline cudaError_t launch_stem_pool(const float* x, float* out, const StemWeight
                                     cudaStream_t st) {
   int Hp = S / 4;
   dim3 grid((Hp + kStemTile - 1) / kStemTile, (Hp + kStemTile - 1) / kStemTile, batch);
-  stem_pool_kernel<<<grid, kStemThreads, 0, st>>>(x, out, wt, S);
+  cudaError_t r = launch_pdl(stem_pool_kernel, grid, dim3(kStemThreads), 0, st, x, out, wt, S);
   YNB_COUNT_LAUNCH();
-  return cudaGetLastError();
+  return r;
 }
 
 // =====================================================================================
@@ -128,6 +130,8 @@ dwconv3x3_kernel(const float* __restrict__ in, int in_ld, int in_off,
   const int groups = C4 >> 2;
   const int xgroups = (Wo + kDwTX - 1) / kDwTX;
   const int64_t total = (int64_t)batch * Ho * xgroups * groups;
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int g = (int)(i % groups);
@@ -187,14 +191,10 @@ inline cudaError_t launch_dwconv3x3(const float* in, int in_ld, int in_off, floa
   int64_t cap = (int64_t)kNumSMs * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  if (stride == 1)
-    dwconv3x3_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(in, in_ld, in_off, out, out_ld, out_off, w, b, batch, Hin,
-                                                          Win, C4, act);
-  else
-    dwconv3x3_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(in, in_ld, in_off, out, out_ld, out_off, w, b, batch, Hin,
-                                                          Win, C4, act);
+  cudaError_t r = launch_pdl(stride == 1 ? dwconv3x3_kernel<1> : dwconv3x3_kernel<2>, dim3((unsigned)blocks), dim3(256),
+                             0, st, in, in_ld, in_off, out, out_ld, out_off, w, b, batch, Hin, Win, C4, act);
   YNB_COUNT_LAUNCH();
-  return cudaGetLastError();
+  return r;
 }
 
 // =====================================================================================
@@ -268,6 +268,8 @@ resample_add_kernel(const float* __restrict__ a, const float* __restrict__ a2, f
   const int groups = ld >> 2;
   const int64_t total = (int64_t)batch * H * W * groups;
   const int H2 = mode == 1 ? H >> 1 : H << 1, W2 = mode == 1 ? W >> 1 : W << 1;
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     int g = (int)(i % groups);
@@ -290,9 +292,9 @@ inline cudaError_t launch_resample_add(const float* a, const float* a2, float* o
   int64_t cap = (int64_t)kNumSMs * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  resample_add_kernel<<<(unsigned)blocks, 256, 0, st>>>(a, a2, out, batch, H, W, ld, mode);
+  cudaError_t r = launch_pdl(resample_add_kernel, dim3((unsigned)blocks), dim3(256), 0, st, a, a2, out, batch, H, W, ld, mode);
   YNB_COUNT_LAUNCH();
-  return cudaGetLastError();
+  return r;
 }
 
 }  // namespace ynb
