@@ -5,11 +5,11 @@
 //
 // Tile: 128 pixel rows x Npad (<= 256) output channels; K consumed in chunks of 32 floats
 // (one 128-byte swizzle row).  A persistent CTA walks its tiles; five roles:
-//   warps 0-3   epilogue          TMEM -> regs -> bias/act -> global (plain / interleaved)
-//   warps 4-7   splitters         fp32 parity mode only: A -> (A_hi, A_lo) in smem
-//   warp 8      TMA producer      A chunk (+ W chunk when W is streamed) -> smem stage
-//   warp 9      MMA issuer        tcgen05.mma kind::tf32, one elected lane; owns TMEM alloc
-//   (warps 10-11 idle: three full warpgroups, roles aligned to warpgroup boundaries)
+//   warps 0-3   epilogue group 0  TMEM -> regs -> bias/act -> swizzled smem box -> TMA store /
+//   warps 4-7   epilogue group 1  coalesced (interleaved) row stores; group g owns TMEM stage g
+//   warps 8-11  splitters         fp32 parity mode only: A -> (A_hi, A_lo) in smem
+//   warp 12     TMA producer      A chunk (+ W chunk when W is streamed) -> smem stage
+//   warp 13     MMA issuer        tcgen05.mma kind::tf32, one elected lane; owns TMEM alloc
 //
 // fp32 parity mode (YNB_GEMM_TC_3XTF32): a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi with
 // x_hi = RN_tf32(x), x_lo = RN_tf32(x - x_hi): three MMAs per K step.  Measured on B200
@@ -36,7 +36,8 @@
 
 namespace ynb {
 
-constexpr int kTcThreads = 384;
+constexpr int kTcThreads = 512;
+constexpr int kTcSplitWarp0 = 8, kTcProducerWarp = 12, kTcMmaWarp = 13;   // warps 0-7: two epilogue groups
 constexpr int kTcBM = 128;
 constexpr int kTcBK = 32;                       // floats per K chunk = 128 bytes
 constexpr int kTcAStageBytes = kTcBM * 128;     // 16 KB
@@ -100,9 +101,7 @@ struct TcSmemLayout {
   uint32_t bar_off;
   uint32_t total;
 };
-constexpr int kTcStgPitch = 36;                                  // floats per staged row (conflict-free)
-constexpr int kTcStgBytes = 4 * 2 * 4096;                        // 4 warps x 2 swizzled [32 rows x 128 B] boxes
-static_assert(kTcStgBytes >= 4 * 32 * kTcStgPitch * 4, "staging region too small");
+constexpr int kTcStgBytes = 8 * 4096;                            // 8 epilogue warps x one swizzled [32 rows x 128 B] box
 
 __host__ __device__ inline TcSmemLayout tc_smem_layout(int Npad, int num_steps, int num_stages, bool w_resident,
                                                        bool split) {
@@ -152,7 +151,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_trigger();
 
-  if (warp == 8 && lane == 0) {
+  if (warp == kTcProducerWarp && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmWhi);
     if (split) ptx::prefetch_tmap(&tmWlo);
@@ -164,16 +163,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], 4); // one arrival per epilogue warp
+      ptx::mbar_init(&tmem_empty[a], 4); // one arrival per warp of the epilogue group that owns the stage
     }
     ptx::mbar_init(w_full, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 9) {
+  if (warp == kTcMmaWarp) {
     ptx::tmem_alloc(tmem_ptr, p.tmem_cols);
     ptx::tmem_relinquish();
   }
-  if (warp < 4) {    // epilogue warps stage the bias once (no global latency inside the tile loop)
+  if (warp < 4) {    // stage the bias once (no global latency inside the tile loop)
     for (int i = threadIdx.x; i < p.Npad; i += 128) s_bias[i] = i < p.N ? __ldg(p.bias + i) : 0.0f;
   }
   ptx::tc_fence_before_sync();
@@ -194,7 +193,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   // Weights do not depend on the previous kernel: the resident W planes are requested before
   // the programmatic-dependency wait, i.e. while the predecessor is still draining.
-  if (warp == 8 && lane == 0 && p.w_resident) {
+  if (warp == kTcProducerWarp && lane == 0 && p.w_resident) {
     ptx::mbar_arrive_expect_tx(w_full, w_res_bytes);
     for (int st = 0; st < p.num_steps; ++st) {
       ptx::tma_load_2d(w_hi_ptr(0, st), &tmWhi, w_full, st * kTcBK, 0);
@@ -203,7 +202,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   pdl_wait();
 
-  if (warp == 8) {
+  if (warp == kTcProducerWarp) {
     // ================= TMA producer =================
     if (lane == 0) {
       int s = 0;
@@ -238,7 +237,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kTcMmaWarp) {
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = ptx::make_idesc(2 /*tf32*/, kTcBM, p.Npad);
@@ -283,10 +282,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1; }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= kTcSplitWarp0 && warp < kTcSplitWarp0 + 4) {
     // ================= splitters (fp32 parity mode) =================
     if (split) {
-      const int t = threadIdx.x - 128;  // 0..127
+      const int t = threadIdx.x - kTcSplitWarp0 * 32;  // 0..127
       int s = 0;
       uint32_t ph = 0;
       bool ok = true;
@@ -316,16 +315,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp < 4) {
-    // ================= epilogue =================
-    const int q = warp;                             // TMEM lane quarter this warp may read
+  } else if (warp < 8) {
+    // ================= epilogue: two groups of four warps =================
+    // Group g owns accumulator stage g and the tiles with (local index % 2) == g, so the
+    // TMEM drain + stores of tile i overlap those of tile i+1 (and the MMAs of tile i+2).
+    // With a single accumulator stage group 1 stays idle.
+    const int group = warp >> 2;
+    const int q = warp & 3;                         // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;                  // tile row owned by this thread
-    int acc = 0;
-    uint32_t acc_ph = 0;
-    bool ok = true;
     const bool vec = p.out_step == 1 && p.omap.gap == 0;
-    int tma_blk = 0;
-    for (int64_t tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
+    const float slope = p.act == YNB_ACT_RELU ? 0.0f : (p.act == YNB_ACT_LEAKY ? 0.1f : 1.0f);
+    uint8_t* sbox = smem + lay.stg_off + warp * 4096;          // this warp's [32 rows x 128 B] swizzled box
+    const int sw = lane & 7;                                    // swizzle phase of this thread's row
+    bool ok = group < p.acc_stages;
+    int lt = group;                                             // local tile index handled next
+    for (int64_t tile = blockIdx.x + (int64_t)group * gridDim.x; tile < p.num_tiles && ok;
+         tile += (int64_t)p.acc_stages * gridDim.x, lt += p.acc_stages) {
+      const int acc = p.acc_stages == 2 ? group : 0;
+      const uint32_t acc_ph = (uint32_t)((lt / p.acc_stages) & 1);
       // row -> output pixel
       int64_t m;
       bool valid;
@@ -344,8 +351,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // Pass-through prefetch (interleave mode): the x1 values this warp will store do not
       // depend on the MMAs, so the loads of the first 32-channel block are issued BEFORE
       // waiting for the accumulator, and each half (16 rows) is re-armed for the next block
-      // right after it has been stored: 32 independent 128-byte row reads per lane-set in
-      // flight at all times, in 32 registers.
+      // right after it has been stored.
       const int64_t m_base = tile * kTcBM + q * 32;            // first row of this warp (pointwise)
       float xa[16], xb[16];
       auto fetch_x1 = [&](int c0, int r0, float (&x)[16]) {
@@ -361,15 +367,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         fetch_x1(0, 0, xa);
         fetch_x1(0, 16, xb);
       }
-      if (threadIdx.x == 0) YNB_TRACE(4, tile, 0);
+      if (lane == 0 && q == 0) YNB_TRACE(4, tile, group);
       ok = ptx::mbar_wait(&tmem_full[acc], acc_ph, p.err_flag, 6);
       if (!ok) break;
       ptx::tc_fence_after_sync();
-      if (threadIdx.x == 0) YNB_TRACE(6, tile, 0);
+      if (lane == 0 && q == 0) YNB_TRACE(6, tile, group);
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_cols);
-      // sum of the accumulators of 16 columns (main_0 + main_1 + ... + correction), + bias, act
-      const float slope = p.act == YNB_ACT_RELU ? 0.0f : (p.act == YNB_ACT_LEAKY ? 0.1f : 1.0f);
-      auto load16 = [&](int c0, float (&v)[16]) {
+      // 16 columns: sum of the accumulators (main_0 + main_1 + ... + correction) + bias, activation
+      // (branch-free: act(x) = max(x, slope*x), slope 1 / 0 / 0.1 = identity / ReLU / LeakyReLU(0.1)),
+      // written as chunks jc..jc+3 of this thread's swizzled 128-byte line
+      auto drain16 = [&](int c0, int jc) {
         uint32_t r[16];
         ptx::tmem_ld_32x16(t_base + c0, r);
         if (p.nacc == 2) {            // main + correction (the common case): both loads, one wait
@@ -389,102 +396,56 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else {
           ptx::tmem_ld_wait();
         }
-        // bias + activation, branch-free: act(x) = max(x, slope * x) with slope 1 / 0 / 0.1
-        // (identity / ReLU / LeakyReLU(0.1): for x < 0, 0.1x > x, same product as the reference)
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + j);
-          float x0 = __uint_as_float(r[j]) + b4.x, x1 = __uint_as_float(r[j + 1]) + b4.y;
-          float x2 = __uint_as_float(r[j + 2]) + b4.z, x3 = __uint_as_float(r[j + 3]) + b4.w;
-          v[j] = fmaxf(x0, x0 * slope); v[j + 1] = fmaxf(x1, x1 * slope);
-          v[j + 2] = fmaxf(x2, x2 * slope); v[j + 3] = fmaxf(x3, x3 * slope);
+        for (int j = 0; j < 4; ++j) {
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * j);
+          float x0 = __uint_as_float(r[4 * j]) + b4.x, x1 = __uint_as_float(r[4 * j + 1]) + b4.y;
+          float x2 = __uint_as_float(r[4 * j + 2]) + b4.z, x3 = __uint_as_float(r[4 * j + 3]) + b4.w;
+          *reinterpret_cast<float4*>(sbox + lane * 128 + (((jc + j) ^ sw) << 4)) =
+              make_float4(fmaxf(x0, x0 * slope), fmaxf(x1, x1 * slope), fmaxf(x2, x2 * slope), fmaxf(x3, x3 * slope));
         }
       };
-      auto release_acc = [&]() {   // all TMEM reads of this tile are done: hand the stage back
-        ptx::tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      // value (row r, column l of the block) back out of the swizzled box
+      auto staged = [&](int r, int l) {
+        return *reinterpret_cast<const float*>(sbox + r * 128 + ((((l >> 2) ^ (r & 7)) << 4) | ((l & 3) << 2)));
       };
 
-      // Every store goes through a warp-private transpose buffer: a thread owns one tile ROW
-      // in TMEM, but a coalesced store wants a warp on consecutive CHANNELS of one row.  Each
-      // 32-channel block is written row-wise to shared memory (conflict-free pitch), then the
-      // warp writes the 32 rows out one 128-byte (plain) / 256-byte (interleaved) line at a time.
-      if (!kPass && p.tma_store) {
-        // ---- plain pointwise output: swizzled [32 rows x 32 ch] box per warp -> TMA store ----
-        // thread = row: its 8 16-byte chunks go to chunk (j ^ (row & 7)) of its 128-byte line
-        // (the SWIZZLE_128B pattern the store map expects; conflict-free for the warp).
-        uint8_t* boxes2 = smem + lay.stg_off + warp * 8192;
-        for (int c0 = 0; c0 < p.Npad; c0 += 32, ++tma_blk) {
-          uint8_t* sbox = boxes2 + (tma_blk & 1) * 4096;
-          if (lane == 0) ptx::bulk_wait_read<1>();     // the store issued from this buffer 2 blocks ago has read it
+      for (int c0 = 0; c0 < p.Npad; c0 += 32) {
+        if (p.tma_store) {
+          if (lane == 0) ptx::bulk_wait_read<0>();   // the previous store has finished reading the box
           __syncwarp();
-          uint8_t* line = sbox + lane * 128;
-          {
-            float v[16];
-            load16(c0, v);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<float4*>(line + ((j ^ (lane & 7)) << 4)) =
-                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          if (c0 + 16 < p.Npad) {
-            float v[16];
-            load16(c0 + 16, v);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<float4*>(line + (((j + 4) ^ (lane & 7)) << 4)) =
-                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          if (c0 + 32 >= p.Npad) release_acc();
+        }
+        drain16(c0, 0);
+        if (c0 + 16 < p.Npad) drain16(c0 + 16, 4);
+        if (c0 + 32 >= p.Npad) {   // all TMEM reads of this tile are done: hand the stage back
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+        }
+        if (!kPass && p.tma_store) {
+          // ---- plain pointwise output: the swizzled box leaves through one TMA store ----
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
             ptx::tma_store_2d(&tmOut, sbox, c0, (int)m_base);   // rows >= M / cols >= N4 are clipped
             ptx::bulk_commit();
           }
+          continue;
         }
-        if (threadIdx.x == 0) YNB_TRACE(5, tile, 0);
-        if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1; }
-        continue;
-      }
-      float* stg = reinterpret_cast<float*>(smem + lay.stg_off) + warp * 32 * kTcStgPitch;
-      for (int c0 = 0; c0 < p.Npad; c0 += 32) {
-        float* srow = stg + lane * kTcStgPitch;
-        long long tq0 = 0, tq1 = 0, tq2 = 0;
-        if (p.trace != nullptr) tq0 = clock64();
-        {
-          float v[16];
-          load16(c0, v);
-#pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<float4*>(srow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-        if (c0 + 16 < p.Npad) {
-          float v[16];
-          load16(c0 + 16, v);
-#pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<float4*>(srow + 16 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-        if (c0 + 32 >= p.Npad) release_acc();
         __syncwarp();
-        if (p.trace != nullptr) tq1 = clock64();
         const int i = c0 + lane;                                // output channel of this lane
         const bool col_ok = i < p.N;
-        const float* sl = stg + lane;
         if (kPass) {
-          // out[slot(2i)] = x1[i] (pass-through), out[slot(2i+1)] = branch2[i]
+          // out[slot(2i)] = x1[i] (pass-through), out[slot(2i+1)] = branch2[i]: 256-byte row segments
           const int nrow = col_ok ? (int)min((int64_t)32, p.M - m_base) : 0;   // rows this lane stores
           float* o = p.out + m_base * p.out_ld + p.omap.slot(2 * (col_ok ? i : 0));
-          // rows 0..15 with xa, then re-arm xa for the next block; rows 16..31 with xb, re-arm xb
 #pragma unroll
           for (int r = 0; r < 16; ++r, o += p.out_ld)
-            if (r < nrow) *reinterpret_cast<float2*>(o) = make_float2(xa[r], sl[r * kTcStgPitch]);
+            if (r < nrow) *reinterpret_cast<float2*>(o) = make_float2(xa[r], staged(r, lane));
           if (c0 + 32 < p.Npad) fetch_x1(c0 + 32, 0, xa);
 #pragma unroll
           for (int r = 16; r < 32; ++r, o += p.out_ld)
-            if (r < nrow) *reinterpret_cast<float2*>(o) = make_float2(xb[r - 16], sl[r * kTcStgPitch]);
+            if (r < nrow) *reinterpret_cast<float2*>(o) = make_float2(xb[r - 16], staged(r, lane));
           if (c0 + 32 < p.Npad) fetch_x1(c0 + 32, 16, xb);
         } else {
           const int col = vec ? p.out_off + i : p.omap.slot(p.out_off + (col_ok ? i : 0) * p.out_step);
@@ -493,32 +454,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float* o = p.out + m_base * p.out_ld + col;
 #pragma unroll 8
             for (int r = 0; r < 32; ++r, o += p.out_ld)
-              if (r < nrow) *o = sl[r * kTcStgPitch];
+              if (r < nrow) *o = staged(r, lane);
           } else {
             // spatial tile: row -> pixel is not affine, take it from the lane that owns the row
-            const int64_t off = valid && true ? m * p.out_ld : -1;
+            const int64_t off = valid ? m * p.out_ld : -1;
 #pragma unroll 8
             for (int r = 0; r < 32; ++r) {
               const int64_t offr = __shfl_sync(0xffffffffu, off, r);
-              if (col_ok && offr >= 0) p.out[offr + col] = sl[r * kTcStgPitch];
+              if (col_ok && offr >= 0) p.out[offr + col] = staged(r, lane);
             }
           }
         }
         __syncwarp();
-        if (p.trace != nullptr && threadIdx.x == 0) {
-          tq2 = clock64();
-          YNB_TRACE(7, tq1 - tq0, tq2 - tq1);   // (tmem->smem cycles, smem->global cycles) of this block
-        }
       }
-      if (threadIdx.x == 0) YNB_TRACE(5, tile, 0);
-      if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1; }
+      if (lane == 0 && q == 0) YNB_TRACE(5, tile, group);
     }
     if (p.tma_store && lane == 0) ptx::bulk_wait<0>();   // all output boxes have landed
   }
 
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == kTcMmaWarp) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, p.tmem_cols);
   }
