@@ -37,8 +37,8 @@ CONF, NMS_T = 0.001, 0.5
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--size", type=int, default=SIZE)
@@ -69,7 +69,7 @@ class ClockSampler(threading.Thread):
                 self.samples.append([v.strip() for v in out.strip().split(",")])
             except Exception:  # noqa: BLE001
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.05)
 
     def summary(self):
         sm = [float(s[0]) for s in self.samples if len(s) >= 7 and s[0].replace(".", "").isdigit()]
@@ -108,6 +108,29 @@ def cpu_baseline(sd, seconds: float, size: int):
             "sample": f"{n} images of the bench workload, batch 1 loop, torch {torch.__version__} CPU + NumPy NMS "
                       f"(oracle/yolo_nano_oracle.py), {el:.1f} s",
             "network_ms_per_image": 1e3 * net_t / n, "nms_ms_per_image": 1e3 * (el - net_t) / n}
+
+
+def load_traffic(kernel_substr: str):
+    """DRAM bytes per launch (read + write) of a kernel family from the committed ncu capture
+    of this same command (profiles/r01_dram_traffic.csv); None if the capture is absent."""
+    import csv
+    p = ROOT / "profiles" / "r01_dram_traffic.csv"
+    if not p.exists():
+        return None
+    rows, hdr = [], None
+    for r in csv.reader(open(p)):
+        if len(r) > 5 and r[0] == "ID":
+            hdr = r
+        elif hdr and len(r) == len(hdr):
+            rows.append(dict(zip(hdr, r)))
+    per_launch = {}
+    for d in rows:
+        if kernel_substr not in d["Kernel Name"] or not d["Metric Name"].startswith("dram__bytes"):
+            continue
+        v = float(d["Metric Value"].replace(",", ""))
+        v *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(d["Metric Unit"], 1)
+        per_launch[d["ID"]] = per_launch.get(d["ID"], 0.0) + v
+    return sum(per_launch.values()) / len(per_launch) if per_launch else None
 
 
 def load_peaks():
@@ -283,8 +306,12 @@ def main():
     dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
     dk, dd = dom
     ach = dd["bytes"] / (dd["ms"] * 1e-3) / 1e9
+    sass_name = {"pw_tcgen05": "tc_gemm_kernel", "conv3x3_tcgen05": "tc_gemm_kernel", "nms": "nms_segment_kernel",
+                 "dwconv3x3": "dwconv3x3_kernel", "stem_pool": "stem_pool_kernel", "decode": "decode_level_kernel"}.get(dk, dk)
     roofline = {"bound": "hbm", "kernel": dk, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": load_traffic(sass_name), "traffic_note": "avg DRAM read+write bytes per launch of " + sass_name +
+                " (ncu, profiles/r01_dram_traffic.csv); algorithmic bytes per launch = " +
+                f"{dd['bytes'] / max(dd['launches'], 1e-9):.3e}", "peak_source": peak_src,
                 "launches_per_step": dd["launches"], "ms_per_step": dd["ms"],
                 "share_of_step": dd["ms"] / total_prof_ms,
                 "achieved_tflops": dd["flops"] / (dd["ms"] * 1e-3) / 1e12,
