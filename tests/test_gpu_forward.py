@@ -225,3 +225,22 @@ def test_g3_416_against_reference(G, golden):
         print(f"[report] 416 img{i}: kept {k}, reference {len(g[f'img{i}.keep_idx'])}, differing {len(diff)}")
         assert len(diff) <= 0.002 * k + 2
     eng.close()
+
+
+@pytest.mark.parametrize("classes,size", [(80, 128), (20, 160)])
+def test_fused_decode_epilogue_equals_decode_kernel(G, classes, size, monkeypatch):
+    """head_det_*.4 with the decode in the GEMM epilogue (no raw map in HBM) against the same
+    conv followed by decode_level_kernel: identical raw sums feed identical arithmetic, so
+    boxes and scores are bit-equal; classes may differ only where two products round equal."""
+    sd = W.calibrated(classes, seed=5)
+    x = W.synthetic_input(3, size, 5).to(G.DEV)
+    eng_f = G.make_engine(sd, size, classes, "3xtf32")
+    bf, sf, cf = [t.cpu().numpy() for t in eng_f.forward_decode(x)]
+    eng_f.close()
+    monkeypatch.setenv("YNB_NO_FUSED_DECODE", "1")
+    eng_u = G.make_engine(sd, size, classes, "3xtf32")
+    bu, su, cu = [t.cpu().numpy() for t in eng_u.forward_decode(x)]
+    eng_u.close()
+    np.testing.assert_array_equal(bf, bu)
+    np.testing.assert_array_equal(sf, su)
+    assert (cf != cu).mean() < 1e-4

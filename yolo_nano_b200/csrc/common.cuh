@@ -18,6 +18,13 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+// Class softmax pieces shared by decode_level_kernel and the fused decode epilogue of the head
+// GEMM (models/yolo_nano.py:362-365).  d = logit - max <= 0; the denominator only needs ~1e-6
+// relative accuracy (scores are compared at rtol 1e-4), so ex2.approx on d*log2(e) is used:
+// 2 instructions instead of expf's 7.
+__device__ __forceinline__ float softmax_exp(float d) { return __expf(d); }
+__device__ __forceinline__ float class_score(float sum, float obj) { return __fmul_rn(__fdiv_rn(1.0f, sum), obj); }
+
 // A view of an NHWC activation: `ld` floats between pixels, channels [off, off+c) used.
 // Stage-2 tensors (116 = 2 x 58 channels) are stored as [58 | 2 zero pads | 58 | 2 zero
 // pads] so that both halves start 16-byte aligned (TMA / float4 need it): logical

@@ -68,19 +68,17 @@ decode_level_kernel(DecodeParams p) {
   const float* r = s_raw + cc * pitch;
 
   const float obj = sigmoidf_(r[a]);
-  // softmax over classes (torch.softmax, dim = classes) times objectness; argmax over the
-  // PRODUCTS with first-max-wins, as np.argmax does on all_class (models/yolo_nano.py:253)
+  // softmax over classes (torch.softmax, dim = classes) times objectness, arg-max class.  The
+  // reference takes np.argmax over the products (models/yolo_nano.py:253); products are monotone
+  // in the logit, so the first maximal logit is that class, and its softmax is exp(0)/sum.
   const float* cl = r + p.A + a * p.C;
   float mx = -INFINITY;
-  for (int c = 0; c < p.C; ++c) mx = fmaxf(mx, cl[c]);
-  float sum = 0.0f;
-  for (int c = 0; c < p.C; ++c) sum += expf(cl[c] - mx);
-  float best = -1.0f;
   int best_c = 0;
-  for (int c = 0; c < p.C; ++c) {
-    float pr = __fmul_rn(__fdiv_rn(expf(cl[c] - mx), sum), obj);
-    if (pr > best) { best = pr; best_c = c; }
-  }
+  for (int c = 0; c < p.C; ++c)
+    if (cl[c] > mx) { mx = cl[c]; best_c = c; }
+  float sum = 0.0f;
+  for (int c = 0; c < p.C; ++c) sum += softmax_exp(cl[c] - mx);
+  const float best = class_score(sum, obj);
   // box (models/yolo_nano.py:129-134, 150-154, 366)
   const float* t = r + p.A * (1 + p.C) + 4 * a;
   float tx = t[0], tyv = t[1], tw = t[2], th = t[3];

@@ -58,6 +58,7 @@ struct TcGemmParams {
   int N, Npad;
   int nmain;              // main accumulators (round-robin over K steps), 1..4
   int nacc;               // accumulators per stage = nmain + (parity mode ? 1 correction : 0)
+  int merge_corr;         // parity mode, shallow K: corrections go into the single main accumulator (nacc = 1)
   int acc_stages;         // TMEM accumulator stages (2 = epilogue overlaps the next tile's MMAs)
   uint32_t tmem_cols;     // power of two >= acc_stages * nacc * Npad
   uint32_t a_box_bytes;   // bytes one A TMA box delivers
@@ -74,6 +75,19 @@ struct TcGemmParams {
   const float* pass;
   int pass_ld;
   int tma_store;          // plain pointwise outputs leave through TMA bulk tensor stores (tmOut)
+  // Fused detection decode (head_det_*.4): instead of writing the raw [M, A(1+C+4)] map, the
+  // epilogue thread that owns a pixel row turns it into boxes / scores / classes
+  // (models/yolo_nano.py:303-330, 120-156, 362-367, 253-256) — the largest activation of the
+  // network never reaches HBM.
+  struct Decode {
+    float* boxes;        // [B, Ntot, 4]
+    float* scores;       // [B, Ntot]
+    int32_t* cls;        // [B, Ntot]
+    int G, HW;           // grid side, cells per image
+    float stride, input_size;
+    float aw[3], ah[3];
+    int64_t Ntot, level_off;
+  } dec;
   int* err_flag;
   // debug timeline (tools/gpu_tc_trace.py): CTA 0 appends {role, tile, step, clock64}
   long long* trace;
@@ -122,7 +136,7 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int Npad, int num_steps, 
 // round-to-nearest (ties away) to TF32 on the raw bits; exact for values already in TF32
 __host__ __device__ __forceinline__ uint32_t rn_tf32_bits(uint32_t u) { return (u + 0x1000u) & 0xffffe000u; }
 
-template <bool kPass>
+template <bool kPass, int kDecC>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWhi,
                const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmOut,
@@ -252,7 +266,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (!ok) break;
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
-        const uint32_t c_tmem = d_tmem + (uint32_t)(p.nmain * p.Npad);   // correction accumulator
+        // correction accumulator (the main one itself when merged: its first MMA initialises it)
+        const uint32_t c_tmem = p.merge_corr ? d_tmem : d_tmem + (uint32_t)(p.nmain * p.Npad);
         int t = 0;                                                       // K-step counter of the tile
         for (int st = 0; st < p.num_steps; ++st) {
           ok = ptx::mbar_wait(split ? &ready[s] : &full[s], ph, p.err_flag, 4);
@@ -272,7 +287,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               ptx::mma_tf32_ss(c_tmem, ptx::make_sw128_kmajor_desc(a_lo + ko), db, idesc, t != 0);
               ptx::mma_tf32_ss(c_tmem, da, ptx::make_sw128_kmajor_desc(b_lo + ko), idesc, 1);
             }
-            ptx::mma_tf32_ss(d_tmem + (uint32_t)(slot * p.Npad), da, db, idesc, t >= p.nmain);
+            ptx::mma_tf32_ss(d_tmem + (uint32_t)(slot * p.Npad), da, db, idesc,
+                             (split && p.merge_corr) ? 1 : (t >= p.nmain));
           }
           YNB_TRACE(3, tile, st);
           ptx::mma_commit(&empty[s]);                       // frees the smem stage when the MMAs retire
@@ -373,6 +389,92 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::tc_fence_after_sync();
       if (lane == 0 && q == 0) YNB_TRACE(6, tile, group);
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_cols);
+      if constexpr (kDecC > 0) {
+        // ================= fused decode epilogue (one pixel = one thread) =================
+        constexpr int A = 3, C = kDecC, NCOL = A * (1 + C + 4), NBLK = (NCOL + 15) / 16;
+        // 16 raw columns (accumulator sum + bias) into registers
+        auto raw16 = [&](int c0, float (&v)[16]) {
+          uint32_t r[16];
+          ptx::tmem_ld_32x16(t_base + c0, r);
+          for (int a = 1; a < p.nacc; ++a) {
+            uint32_t r2[16];
+            ptx::tmem_ld_32x16(t_base + (uint32_t)(a * p.Npad) + c0, r2);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+          }
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + s_bias[c0 + j];
+        };
+        float objl[A], mx[A], sum[A], tb[4 * A];
+        int am[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) { mx[a] = -INFINITY; sum[a] = 0.0f; am[a] = 0; objl[a] = 0.0f; }
+        // pass 1: objectness / box logits, class max + first argmax (channel map of :312-318)
+#pragma unroll
+        for (int blk = 0; blk < NBLK; ++blk) {
+          float v[16];
+          raw16(blk * 16, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = blk * 16 + j;            // compile-time after unrolling
+            if (col < A) {
+              objl[col] = v[j];
+            } else if (col < A + A * C) {
+              const int a = (col - A) / C, c = (col - A) % C;
+              if (v[j] > mx[a]) { mx[a] = v[j]; am[a] = c; }
+            } else if (col < NCOL) {
+              tb[col - A - A * C] = v[j];
+            }
+          }
+        }
+        // pass 2: softmax denominators (TMEM is re-read: cheaper than holding 3*C logits)
+#pragma unroll
+        for (int blk = 0; blk < NBLK; ++blk) {
+          if (blk * 16 + 15 < A || blk * 16 >= A + A * C) continue;
+          float v[16];
+          raw16(blk * 16, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = blk * 16 + j;
+            if (col >= A && col < A + A * C) sum[(col - A) / C] += softmax_exp(v[j] - mx[(col - A) / C]);
+          }
+        }
+        {   // all TMEM reads of this tile are done: hand the stage back
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+        }
+        if (valid) {
+          const int b = (int)(m / p.dec.HW);
+          const int pix = (int)(m - (int64_t)b * p.dec.HW);
+          const int gy = pix / p.dec.G, gx = pix - gy * p.dec.G;
+          const int64_t o0 = (int64_t)b * p.dec.Ntot + p.dec.level_off + (int64_t)pix * A;
+#pragma unroll
+          for (int a = 0; a < A; ++a) {
+            const float obj = 1.0f / (1.0f + expf(-objl[a]));
+            const float score = class_score(sum[a], obj);
+            const float tx = tb[4 * a], ty = tb[4 * a + 1], tw = tb[4 * a + 2], th = tb[4 * a + 3];
+            float cx = __fmul_rn(__fadd_rn(1.0f / (1.0f + expf(-tx)), (float)gx), p.dec.stride);
+            float cy = __fmul_rn(__fadd_rn(1.0f / (1.0f + expf(-ty)), (float)gy), p.dec.stride);
+            float w = __fmul_rn(expf(tw), p.dec.aw[a]);
+            float h = __fmul_rn(expf(th), p.dec.ah[a]);
+            float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
+            float x1 = __fdiv_rn(__fsub_rn(cx, hw), p.dec.input_size);
+            float y1 = __fdiv_rn(__fsub_rn(cy, hh), p.dec.input_size);
+            float x2 = __fdiv_rn(__fadd_rn(cx, hw), p.dec.input_size);
+            float y2 = __fdiv_rn(__fadd_rn(cy, hh), p.dec.input_size);
+            reinterpret_cast<float4*>(p.dec.boxes)[o0 + a] =
+                make_float4(fminf(fmaxf(x1, 0.f), 1.f), fminf(fmaxf(y1, 0.f), 1.f), fminf(fmaxf(x2, 0.f), 1.f),
+                            fminf(fmaxf(y2, 0.f), 1.f));
+            p.dec.scores[o0 + a] = score;
+            p.dec.cls[o0 + a] = am[a];
+          }
+        }
+        if (lane == 0 && q == 0) YNB_TRACE(5, tile, group);
+        continue;
+      }
       // 16 columns: sum of the accumulators (main_0 + main_1 + ... + correction) + bias, activation
       // (branch-free: act(x) = max(x, slope*x), slope 1 / 0 / 0.1 = identity / ReLU / LeakyReLU(0.1)),
       // written as chunks jc..jc+3 of this thread's swizzled 128-byte line
@@ -573,6 +675,7 @@ struct TcGemmLaunch {
   TcGemmParams p;
   uint32_t smem = 0;
   unsigned grid = 0;
+  int dec_classes = 0;    // 80 | 20: fused decode epilogue (p.dec valid); 0: ordinary epilogue
 };
 
 // TMEM plan (512 columns).  Parity mode: one correction accumulator plus `nmain` main
@@ -580,8 +683,18 @@ struct TcGemmLaunch {
 // accumulation steps).  Two accumulator stages (epilogue of tile i overlaps the MMAs of tile
 // i+1) whenever they fit; a shallow K gives up an extra main accumulator for that overlap, a
 // deep K (3x3 convs: 108 steps, K=464 laterals) keeps the accumulators and runs single-stage.
-inline void tc_plan_tmem(TcGemmParams& p) {
+inline void tc_plan_tmem(TcGemmParams& p, bool allow_merge = false) {
   const bool split = p.mode == YNB_GEMM_TC_3XTF32;
+  p.merge_corr = 0;
+  if (split && allow_merge && p.num_steps * (kTcBK / 8) <= 16 && 2 * p.Npad <= 512) {
+    // <= 16 K steps (48 accumulations): the one-sided truncation of a single accumulator stays
+    // below 3e-6 relative — buys two accumulator stages for N = 256 (fused decode heads)
+    p.merge_corr = 1;
+    p.nmain = 1; p.nacc = 1; p.acc_stages = 2;
+    p.tmem_cols = 32;
+    while ((int)p.tmem_cols < 2 * p.Npad) p.tmem_cols <<= 1;
+    return;
+  }
   const int corr = split ? 1 : 0;
   int want = 1;
   if (split) {
@@ -622,19 +735,21 @@ inline bool tc_plan_smem(TcGemmLaunch& L) {
 }
 
 inline cudaError_t launch_tc_gemm(const TcGemmLaunch& L, cudaStream_t st) {
+  using KernelT = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcGemmParams);
+  static const KernelT kernels[4] = {tc_gemm_kernel<false, 0>, tc_gemm_kernel<true, 0>, tc_gemm_kernel<false, 80>,
+                                     tc_gemm_kernel<false, 20>};
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kTcSmemBudget);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               kTcSmemBudget);
-    if (e != cudaSuccess) return e;
+    for (KernelT k : kernels) {
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBudget);
+      if (e != cudaSuccess) return e;
+    }
     attr_set = true;
   }
   const CUtensorMap& tmo = L.p.tma_store ? L.tmOut : L.tmA;   // unused unless tma_store
-  cudaError_t r = launch_pdl(L.p.pass != nullptr ? tc_gemm_kernel<true> : tc_gemm_kernel<false>, dim3(L.grid),
-                             dim3(kTcThreads), (size_t)L.smem, st, L.tmA, L.w->tm_hi, L.w->tm_lo, tmo, L.p);
+  KernelT kern = L.dec_classes == 80 ? kernels[2] : (L.dec_classes == 20 ? kernels[3] : kernels[L.p.pass != nullptr ? 1 : 0]);
+  cudaError_t r = launch_pdl(kern, dim3(L.grid), dim3(kTcThreads), (size_t)L.smem, st, L.tmA, L.w->tm_hi,
+                             L.w->tm_lo, tmo, L.p);
   YNB_COUNT_LAUNCH();
   return r;
 }

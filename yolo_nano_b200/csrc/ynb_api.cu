@@ -76,8 +76,11 @@ struct ProfEntry {
 
 struct Plan {
   int batch = 0;
-  std::vector<Op> net;        // stem .. raw head outputs
-  std::vector<Op> decode;     // raw -> boxes/scores/cls (engine buffers)
+  std::vector<Op> net;        // stem .. the last hidden conv of every head
+  std::vector<Op> raw_tail;   // head_det_*.4 -> raw maps (ynb_forward_raw, FFMA mode, odd class counts)
+  std::vector<Op> decode;     // raw -> boxes/scores/cls (engine buffers), after raw_tail
+  std::vector<Op> fused_tail; // head_det_*.4 with the decode in the GEMM epilogue: no raw map
+  bool fused = false;
 };
 
 }  // namespace ynb
@@ -372,6 +375,8 @@ struct Planner {
   Plan* plan;
   std::deque<TcGemmLaunch>* tc;
   std::string error;
+  std::vector<Op>* dst = nullptr;   // op list under construction (defaults to plan->net)
+  std::vector<Op>& ops() { return dst ? *dst : plan->net; }
 
   const PackedConv& conv(const std::string& name) const { return e->convs[e->index.at(name)]; }
   const ConvSpec& spec(const std::string& name) const { return e->table[e->index.at(name)]; }
@@ -404,7 +409,7 @@ struct Planner {
   // pointwise conv: in view (off, ktot) -> out (off, step, map)
   // `pass`: stride-1 unit tail — out[slot(2i)] = pass[i], out[slot(2i+1)] = conv[i]
   void pw(const std::string& name, const Tensor& in, int in_off, const Tensor& out, int out_off, int out_step,
-          bool join = false, const Tensor* pass = nullptr) {
+          bool join = false, const Tensor* pass = nullptr, const TcGemmParams::Decode* dec = nullptr) {
     const PackedConv& pc = conv(name);
     const ConvSpec& c = spec(name);
     int64_t M = (int64_t)B * in.H * in.W;
@@ -421,7 +426,7 @@ struct Planner {
       if (pass) { g.out_off = 1; g.out_step = 2; }
       Op op{name, "pw_ffma", abytes, aflops, [=](cudaStream_t st) { return launch_gemm_ffma(g, false, st); }};
       op.join = join;
-      plan->net.push_back(op);
+      ops().push_back(op);
       return;
     }
     tc->emplace_back();
@@ -436,13 +441,19 @@ struct Planner {
     p.M = M;
     p.num_tiles = (M + kTcBM - 1) / kTcBM;
     p.N = pc.n; p.Npad = pc.tc.Npad;
-    tc_plan_tmem(p);
+    // head_det_*.4 (K = 96, N = 255): single merged accumulator, in the raw tail too so that the
+    // raw-map parity tests measure exactly the sums the fused decode epilogue consumes
+    tc_plan_tmem(p, name.size() > 2 && name.compare(0, 8, "head_det") == 0 && name.compare(name.size() - 2, 2, ".4") == 0);
     p.a_box_bytes = kTcAStageBytes;
     p.out = out.p; p.out_ld = out.ld; p.out_off = out_off; p.out_step = out_step; p.omap = out.map;
     p.bias = pc.b_dev; p.act = c.act;
     p.pass = pass ? pass->p : nullptr; p.pass_ld = pass ? pass->ld : 0;
     p.err_flag = e->d_err;
-    p.tma_store = (!pass && out_step == 1 && out.map.gap == 0 && out_off % 4 == 0 && out.ld % 4 == 0) ? 1 : 0;
+    if (dec) {
+      p.dec = *dec;
+      L.dec_classes = e->cfg.num_classes;
+    }
+    p.tma_store = (!dec && !pass && out_step == 1 && out.map.gap == 0 && out_off % 4 == 0 && out.ld % 4 == 0) ? 1 : 0;
     if (p.tma_store && !make_tmap_out(&L.tmOut, out.p + out_off, (uint64_t)round_up(pc.n, 4), (uint64_t)M,
                                       (uint64_t)out.ld)) {
       error = "cuTensorMapEncodeTiled failed for output of " + name;
@@ -455,9 +466,12 @@ struct Planner {
     if (!tc_plan_smem(L)) { error = "no smem configuration for " + name; return; }
     L.grid = (unsigned)std::min<int64_t>(p.num_tiles, kNumSMs);
     const TcGemmLaunch* Lp = &L;
-    Op op{name, "pw_tcgen05", abytes, aflops, [=](cudaStream_t st) { return launch_tc_gemm(*Lp, st); }};
+    // fused decode: the raw map (4*M*cout) is not written; boxes/scores/classes (24 B per anchor) are
+    const double obytes = dec ? abytes - 4.0 * M * c.cout + 24.0 * M * 3 : abytes;
+    Op op{dec ? name + "+decode" : name, dec ? "pw_decode_tcgen05" : "pw_tcgen05", obytes, aflops,
+          [=](cudaStream_t st) { return launch_tc_gemm(*Lp, st); }};
     op.join = join;
-    plan->net.push_back(op);
+    ops().push_back(op);
   }
 
   // dense 3x3 (smooth): out = act(conv3x3(a + resample(a2)))
@@ -590,6 +604,7 @@ int build_plan(ynb_engine* e, int B, Plan** out) {
   P.conv3("smooth_3.convs.0", lat5, &p4, 2, P.T("sum5"), p5);
   // ---- heads (models/yolo_nano.py:50-70, 299-301)
   Tensor feats[3] = {p3, p4, p5};
+  Tensor head_in[3];
   for (int l = 0; l < 3; ++l) {
     std::string hd = "head_det_" + std::to_string(l + 1);
     Tensor ta = P.T("head" + std::to_string(l) + ".a"), tb = P.T("head" + std::to_string(l) + ".b");
@@ -597,8 +612,32 @@ int build_plan(ynb_engine* e, int B, Plan** out) {
     P.pw(hd + ".1.convs.0", ta, 0, tb, 0, 1);
     P.dw(hd + ".2.convs.0", tb, 0, ta);
     P.pw(hd + ".3.convs.0", ta, 0, tb, 0, 1);
-    P.pw(hd + ".4", tb, 0, e->raw[l], 0, 1);
+    head_in[l] = tb;
   }
+  P.dst = &plan->raw_tail;
+  for (int l = 0; l < 3; ++l) P.pw("head_det_" + std::to_string(l + 1) + ".4", head_in[l], 0, e->raw[l], 0, 1);
+  // fused tail: tensor-core modes with the class counts the decode epilogue is instantiated for
+  plan->fused = e->cfg.gemm_mode != YNB_GEMM_FP32_FFMA && e->cfg.num_anchors == 3 &&
+                (e->cfg.num_classes == 80 || e->cfg.num_classes == 20) && !getenv("YNB_NO_FUSED_DECODE");
+  if (plan->fused) {
+    P.dst = &plan->fused_tail;
+    int64_t off = 0;
+    for (int l = 0; l < 3; ++l) {
+      TcGemmParams::Decode d{};
+      const int stride = 8 << l;
+      d.boxes = e->d_boxes; d.scores = e->d_scores; d.cls = e->d_cls;
+      d.G = S / stride; d.HW = d.G * d.G;
+      d.stride = (float)stride; d.input_size = (float)S;
+      for (int a = 0; a < 3; ++a) {
+        d.aw[a] = e->cfg.anchors[(l * 3 + a) * 2];
+        d.ah[a] = e->cfg.anchors[(l * 3 + a) * 2 + 1];
+      }
+      d.Ntot = e->N(); d.level_off = off;
+      off += (int64_t)d.HW * 3;
+      P.pw("head_det_" + std::to_string(l + 1) + ".4", head_in[l], 0, e->raw[l], 0, 1, false, nullptr, &d);
+    }
+  }
+  P.dst = nullptr;
   if (!P.error.empty()) return fail(e, YNB_ERR_CUDA, P.error);
   // ---- decode (models/yolo_nano.py:303-330, 362-367)
   int64_t N = e->N(), off = 0;
@@ -721,10 +760,24 @@ int prepare(ynb_engine* e, int batch, Plan** plan_out) {
 }
 
 // backbone + neck + heads on the engine's main stream
+// stem .. raw head maps (the parity hook's path)
 int run_network(ynb_engine* e, const float* x_dev, Plan* plan) {
   e->d_x_bound = x_dev;
   e->prof.clear();
-  return run_ops(e, plan->net);
+  int rc = run_ops(e, plan->net);
+  return rc ? rc : run_ops(e, plan->raw_tail);
+}
+
+// stem .. decoded boxes / scores / classes in the engine buffers (the product path)
+int run_decoded(ynb_engine* e, const float* x_dev, Plan* plan) {
+  if (!plan->fused) {
+    int rc = run_network(e, x_dev, plan);
+    return rc ? rc : run_ops(e, plan->decode);
+  }
+  e->d_x_bound = x_dev;
+  e->prof.clear();
+  int rc = run_ops(e, plan->net);
+  return rc ? rc : run_ops(e, plan->fused_tail);
 }
 
 int check_device_error(ynb_engine* e) {
@@ -937,7 +990,7 @@ YNB_EXPORT int ynb_forward_decode(ynb_engine* e, const float* x_dev, int32_t bat
   CounterScope cs(e);
   Plan* plan = nullptr;
   int rc = prepare(e, batch, &plan);
-  if (rc || (rc = enter(e, user)) || (rc = run_network(e, x_dev, plan)) || (rc = run_ops(e, plan->decode))) return rc;
+  if (rc || (rc = enter(e, user)) || (rc = run_decoded(e, x_dev, plan))) return rc;
   int64_t n = e->N();
   cudaStream_t st = e->s_main;
   CUDA_TRY(e, cudaMemcpyAsync(boxes, e->d_boxes, (size_t)batch * n * 16, cudaMemcpyDeviceToDevice, st));
@@ -950,8 +1003,8 @@ YNB_EXPORT int ynb_forward_decode(ynb_engine* e, const float* x_dev, int32_t bat
 // network + decode + NMS on the engine's main stream (eager, or into a stream capture)
 static int detect_ops(ynb_engine* e, Plan* plan, const float* x_dev, int batch, float* ob, float* os, int32_t* oc,
                       int32_t* on) {
-  int rc = run_network(e, x_dev, plan);
-  if (rc || (rc = run_ops(e, plan->decode))) return rc;
+  int rc = run_decoded(e, x_dev, plan);
+  if (rc) return rc;
   NmsWorkspace w = nms_carve(e->d_nms_ws, batch, e->N());
   const int64_t n = e->N();
   std::vector<Op> nms_ops(1);
