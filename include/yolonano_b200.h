@@ -233,6 +233,23 @@ int  ynb_nms(const float* boxes_dev, const float* scores_dev, const int32_t* cls
              int32_t* out_counts_dev, uint8_t* keep_dev,
              void* workspace_dev, int64_t workspace_bytes, void* stream);
 
+/* The same function (identical keep set and output order) for candidates that sit on the
+ * model's anchor grid: n = 3 * sum_l (input_size / stride_l)^2 boxes per image in the order
+ * ynb_forward_decode produces (level, cell row, cell column, anchor).  This is what
+ * ynb_forward_detect runs: no sort and no serial scan — each candidate collects the preceding
+ * same-class candidates that suppress it from a window of cells around itself (a pair with
+ * IoU > t has bounded size ratio and centre distance), then a fixed-point pass resolves
+ * kept / removed (models/yolo_nano.py:159-279).  Boxes that do not touch their own cell or have
+ * no area are still handled exactly (they are compared with everything).
+ * workspace_dev: ynb_nms_grid_workspace_bytes(batch, input_size) bytes; input_size % 32 == 0. */
+int64_t ynb_nms_grid_workspace_bytes(int32_t batch, int32_t input_size);
+int  ynb_nms_grid(const float* boxes_dev, const float* scores_dev, const int32_t* cls_dev,
+                  int32_t batch, int32_t input_size, int32_t num_classes,
+                  float conf_thresh, float nms_thresh, int32_t diou,
+                  float* out_boxes_dev, float* out_scores_dev, int32_t* out_cls_dev,
+                  int32_t* out_counts_dev, uint8_t* keep_dev,
+                  void* workspace_dev, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

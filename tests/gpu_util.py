@@ -36,8 +36,9 @@ def stream():
     return C.c_void_p(torch.cuda.current_stream(DEV).cuda_stream)
 
 
-def run_nms(lib, boxes, scores, cls, classes, conf=0.001, thr=0.5, diou=False):
-    """boxes [B,N,4], scores [B,N], cls [B,N] numpy -> list of kept anchor index arrays + outputs."""
+def run_nms(lib, boxes, scores, cls, classes, conf=0.001, thr=0.5, diou=False, grid_size=0):
+    """boxes [B,N,4], scores [B,N], cls [B,N] numpy -> list of kept anchor index arrays + outputs.
+    grid_size > 0: the anchor-grid NMS (ynb_nms_grid) for that input size instead of ynb_nms."""
     b, n = scores.shape
     d_boxes = torch.from_numpy(np.ascontiguousarray(boxes, dtype=np.float32)).to(DEV)
     d_scores = torch.from_numpy(np.ascontiguousarray(scores, dtype=np.float32)).to(DEV)
@@ -47,10 +48,17 @@ def run_nms(lib, boxes, scores, cls, classes, conf=0.001, thr=0.5, diou=False):
     oc = torch.zeros((b, n), device=DEV, dtype=torch.int32)
     on = torch.zeros((b,), device=DEV, dtype=torch.int32)
     keep = torch.zeros((b, n), device=DEV, dtype=torch.uint8)
-    wsb = lib.ynb_nms_workspace_bytes(b, n)
-    ws = torch.empty((wsb,), device=DEV, dtype=torch.uint8)
-    rc = lib.ynb_nms(ptr(d_boxes), ptr(d_scores), ptr(d_cls), b, n, classes, conf, thr, int(diou),
-                     ptr(ob), ptr(os_), ptr(oc), ptr(on), ptr(keep), ptr(ws), wsb, stream())
+    if grid_size:
+        assert n == sum(3 * (grid_size // s) ** 2 for s in (8, 16, 32))
+        wsb = lib.ynb_nms_grid_workspace_bytes(b, grid_size)
+        ws = torch.empty((wsb,), device=DEV, dtype=torch.uint8)
+        rc = lib.ynb_nms_grid(ptr(d_boxes), ptr(d_scores), ptr(d_cls), b, grid_size, classes, conf, thr, int(diou),
+                              ptr(ob), ptr(os_), ptr(oc), ptr(on), ptr(keep), ptr(ws), wsb, stream())
+    else:
+        wsb = lib.ynb_nms_workspace_bytes(b, n)
+        ws = torch.empty((wsb,), device=DEV, dtype=torch.uint8)
+        rc = lib.ynb_nms(ptr(d_boxes), ptr(d_scores), ptr(d_cls), b, n, classes, conf, thr, int(diou),
+                         ptr(ob), ptr(os_), ptr(oc), ptr(on), ptr(keep), ptr(ws), wsb, stream())
     assert rc == 0, lib.ynb_last_error(None)
     torch.cuda.synchronize()
     keep_h = keep.cpu().numpy()

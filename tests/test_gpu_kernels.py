@@ -168,8 +168,8 @@ def test_decode_level(lib, G, classes, size):
 # ---------------------------------------------------------------------------------------------
 # NMS: bit-exact keep-sets against the NumPy restatement on identical candidates
 # ---------------------------------------------------------------------------------------------
-def _check_nms(lib, G, boxes, scores, cls, classes, conf, thr, diou):
-    kept, counts, ob, os_, oc = G.run_nms(lib, boxes, scores, cls, classes, conf, thr, diou)
+def _check_nms(lib, G, boxes, scores, cls, classes, conf, thr, diou, grid_size=0):
+    kept, counts, ob, os_, oc = G.run_nms(lib, boxes, scores, cls, classes, conf, thr, diou, grid_size)
     for i in range(scores.shape[0]):
         b, s, c, idx = O.postprocess_flat(boxes[i], scores[i], cls[i].astype(np.int64), classes, conf, thr, diou,
                                           tie="index")
@@ -192,6 +192,8 @@ def test_nms_on_reference_candidates(lib, G, golden, fixture, classes, conf, thr
     scores = np.stack([g[p + "all_score"] for p in imgs])
     cls = np.stack([g[p + "all_cls"] for p in imgs])
     _check_nms(lib, G, boxes, scores, cls, classes, conf, thr, diou)
+    size = {"g1": 320, "g2": 128, "g3": 416}[fixture[:2]]
+    _check_nms(lib, G, boxes, scores, cls, classes, conf, thr, diou, grid_size=size)     # anchor-grid NMS
 
 
 def test_nms_matches_reference_keepsets_when_tie_free(lib, G, golden):
@@ -204,9 +206,11 @@ def test_nms_matches_reference_keepsets_when_tie_free(lib, G, golden):
             boxes = np.stack([g[f"img{i}.all_bbox"] for i in range(2)])
             scores = np.stack([g[f"img{i}.all_score"] for i in range(2)])
             cls = np.stack([g[f"img{i}.all_cls"] for i in range(2)])
-            kept, *_ = G.run_nms(lib, boxes, scores, cls, 80, conf, thr, diou)
-            for i in range(2):
-                np.testing.assert_array_equal(kept[i], g[f"img{i}.{tag}keep_idx"])
+            size = 128 if name.startswith("g2") else 416
+            for grid_size in (0, size):
+                kept, *_ = G.run_nms(lib, boxes, scores, cls, 80, conf, thr, diou, grid_size)
+                for i in range(2):
+                    np.testing.assert_array_equal(kept[i], g[f"img{i}.{tag}keep_idx"])
 
 
 def test_nms_edge_cases(lib, G):
@@ -245,3 +249,83 @@ def test_nms_large_segment_and_idempotence(lib, G):
     k = counts[0]
     kept2, counts2, *_ = G.run_nms(lib, ob[:, :k], os_[:, :k], oc[:, :k], 80, 0.001, 0.5, False)
     assert counts2[0] == k and np.array_equal(kept2[0], np.arange(k))
+
+
+# ---------------------------------------------------------------------------------------------
+# anchor-grid NMS (ynb_nms_grid): exact on any input, fast on decode-shaped input
+def _decode_like_boxes(rng, size, batch, log_lo, log_hi, classes):
+    """Boxes with the decode's structure (models/yolo_nano.py:120-156, 366): centre inside the
+    anchor's cell, any size from sub-pixel to several images wide, clipped to the unit square."""
+    bx, sc, cl = [], [], []
+    for stride in (8, 16, 32):
+        g = size // stride
+        gy, gx = np.meshgrid(np.arange(g), np.arange(g), indexing="ij")
+        gx = np.repeat(gx.reshape(-1), 3).astype(np.float32)
+        gy = np.repeat(gy.reshape(-1), 3).astype(np.float32)
+        n = gx.size
+        u = rng.random((batch, n, 2), dtype=np.float32)
+        u[rng.random((batch, n, 2)) < 0.02] = 0.0            # sigmoid saturating at a cell border
+        u[rng.random((batch, n, 2)) < 0.02] = 1.0
+        cx = (u[..., 0] + gx) * np.float32(stride)
+        cy = (u[..., 1] + gy) * np.float32(stride)
+        wh = np.exp(rng.uniform(log_lo, log_hi, (batch, n, 2))).astype(np.float32)
+        x1 = (cx - wh[..., 0] * np.float32(0.5)) / np.float32(size)
+        y1 = (cy - wh[..., 1] * np.float32(0.5)) / np.float32(size)
+        x2 = (cx + wh[..., 0] * np.float32(0.5)) / np.float32(size)
+        y2 = (cy + wh[..., 1] * np.float32(0.5)) / np.float32(size)
+        bx.append(np.clip(np.stack([x1, y1, x2, y2], -1), 0.0, 1.0).astype(np.float32))
+    boxes = np.concatenate(bx, 1)
+    n = boxes.shape[1]
+    scores = rng.random((batch, n), dtype=np.float32)
+    scores[:, ::7] = np.float32(0.25)                          # exact ties
+    cls = rng.integers(0, classes, (batch, n)).astype(np.int32)
+    return boxes, scores, cls
+
+
+@pytest.mark.parametrize("thr,diou", [(0.5, False), (0.5, True), (0.3, False), (0.7, False), (0.05, False),
+                                      (0.0, False), (0.9, True)])
+def test_nms_grid_decode_like_boxes_all_scales(lib, G, thr, diou):
+    """Window search against the oracle on boxes from 0.3 px to 3 images wide, clipped at every
+    border, 2 classes (long suppressor lists), conf cutting ~10 %."""
+    rng = np.random.default_rng(int(thr * 100) + diou)
+    size = 160
+    boxes, scores, cls = _decode_like_boxes(rng, size, 3, np.log(0.3), np.log(3 * size), 2)
+    _check_nms(lib, G, boxes, scores, cls, 2, 0.1, thr, diou, grid_size=size)
+
+
+def test_nms_grid_uniform_scale_segments(lib, G):
+    """The bench-shaped case: every (level, anchor) is one class with near-identical box sizes
+    (reference-init behaviour), long dependency chains between neighbouring cells."""
+    rng = np.random.default_rng(5)
+    size = 256
+    boxes, scores, cls = _decode_like_boxes(rng, size, 2, 0.0, 0.0, 1)
+    n0, n1 = 3 * 32 * 32, 3 * 16 * 16
+    for lvl, (beg, end) in enumerate(((0, n0), (n0, n0 + n1), (n0 + n1, boxes.shape[1]))):
+        for a in range(3):
+            anchor = np.float32((8 << lvl) * (1.5 + a))
+            idx = np.arange(beg + a, end, 3)
+            c = (boxes[:, idx, :2] + boxes[:, idx, 2:]) * np.float32(0.5)
+            half = anchor * np.exp(rng.normal(0, 0.05, (2, idx.size, 2))).astype(np.float32) / np.float32(2 * size)
+            boxes[:, idx, :2] = np.clip(c - half, 0, 1)
+            boxes[:, idx, 2:] = np.clip(c + half, 0, 1)
+            cls[:, idx] = (lvl * 3 + a) % 4
+    _check_nms(lib, G, boxes, scores, cls, 4, 0.001, 0.5, False, grid_size=size)
+    _check_nms(lib, G, boxes, scores, cls, 4, 0.001, 0.45, True, grid_size=size)
+
+
+def test_nms_grid_crowded_and_irregular(lib, G):
+    """More suppressors than the list holds (re-scan path), zero-area / out-of-cell / NaN-IoU
+    boxes (irregular list), arbitrary boxes unrelated to the grid."""
+    rng = np.random.default_rng(9)
+    size = 128
+    boxes, scores, cls = _decode_like_boxes(rng, size, 3, np.log(40.0), np.log(60.0), 1)   # everything overlaps
+    boxes[0, 100:140, 2:] = boxes[0, 100:140, :2]          # zero area (0/0 = NaN suppresses, hazard 3)
+    boxes[0, 200:210] = boxes[0, 200]                       # identical boxes in foreign cells
+    n = boxes.shape[1]
+    xy = rng.random((n, 2), dtype=np.float32) * 0.8         # image 2: boxes that ignore the grid entirely
+    boxes[2] = np.concatenate([xy, np.minimum(xy + rng.random((n, 2), dtype=np.float32) * 0.3, 1.0)], -1)
+    cls[2] = rng.integers(0, 3, n)
+    for thr, diou in ((0.5, False), (0.6, True)):
+        _check_nms(lib, G, boxes, scores, cls, 3, 0.001, thr, diou, grid_size=size)
+    scores[1] = 1e-6                                        # nothing passes the threshold
+    _check_nms(lib, G, boxes[1:2], scores[1:2], cls[1:2], 3, 0.001, 0.5, False, grid_size=size)

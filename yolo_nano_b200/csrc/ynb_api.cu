@@ -19,6 +19,7 @@
 
 #include "common.cuh"
 #include "decode_nms.cuh"
+#include "nms_grid.cuh"
 #include "gemm_ffma.cuh"
 #include "gemm_tc.cuh"
 #include "kernels_basic.cuh"
@@ -329,7 +330,7 @@ size_t layout_workspace(ynb_engine* e, int batch, int S, char* base) {
   e->d_boxes = (float*)raw((size_t)batch * n * 16);
   e->d_scores = (float*)raw((size_t)batch * n * 4);
   e->d_cls = (int32_t*)raw((size_t)batch * n * 4);
-  e->nms_ws_bytes = nms_workspace_bytes(batch, n);
+  e->nms_ws_bytes = std::max(nms_workspace_bytes(batch, n), grid_nms_workspace_bytes(batch, n));
   e->d_nms_ws = raw((size_t)e->nms_ws_bytes);
   for (int k = 0; k < 2; ++k) {
     e->slot[k].x = (float*)raw((size_t)batch * 3 * S * S * 4);
@@ -1005,9 +1006,21 @@ static int detect_ops(ynb_engine* e, Plan* plan, const float* x_dev, int batch, 
                       int32_t* on) {
   int rc = run_decoded(e, x_dev, plan);
   if (rc) return rc;
-  NmsWorkspace w = nms_carve(e->d_nms_ws, batch, e->N());
   const int64_t n = e->N();
   std::vector<Op> nms_ops(1);
+  // product path: anchor-grid NMS (nms_grid.cuh); the sorted greedy NMS stays as the generic
+  // kernel (ynb_nms) and as a cross-check (YNB_NMS_SORTED=1)
+  static const bool sorted_nms = getenv("YNB_NMS_SORTED") != nullptr;
+  if (!sorted_nms && e->cfg.num_anchors == 3 && n <= 65535 && e->S % 32 == 0) {
+    GridNmsWorkspace gw = grid_nms_carve(e->d_nms_ws, batch, n);
+    const int S = e->S;
+    nms_ops[0] = {"nms(prep+build+resolve+compact)", "nms", 24.0 * batch * n * 2, 0.0, [=](cudaStream_t s2) {
+      return launch_nms_grid(e->d_boxes, e->d_scores, e->d_cls, batch, S, e->cfg.num_classes, e->cfg.conf_thresh,
+                             e->cfg.nms_thresh, e->cfg.diou_nms, ob, os, oc, on, nullptr, gw, s2);
+    }};
+    return run_ops(e, nms_ops);
+  }
+  NmsWorkspace w = nms_carve(e->d_nms_ws, batch, e->N());
   nms_ops[0] = {"nms(keys+sort+greedy+compact)", "nms", 24.0 * batch * n * 2, 0.0, [=](cudaStream_t s2) {
     return launch_nms(e->d_boxes, e->d_scores, e->d_cls, batch, n, e->cfg.num_classes, e->cfg.conf_thresh,
                       e->cfg.nms_thresh, e->cfg.diou_nms, ob, os, oc, on, nullptr, w, s2);
@@ -1313,6 +1326,23 @@ YNB_EXPORT int ynb_decode_level(const float* raw, int32_t raw_ld, float* boxes, 
 }
 
 YNB_EXPORT int64_t ynb_nms_workspace_bytes(int32_t batch, int64_t n) { return nms_workspace_bytes(batch, n); }
+
+YNB_EXPORT int64_t ynb_nms_grid_workspace_bytes(int32_t batch, int32_t input_size) {
+  return grid_nms_workspace_bytes(batch, make_grid_geom(input_size).N);
+}
+
+YNB_EXPORT int ynb_nms_grid(const float* boxes, const float* scores, const int32_t* cls, int32_t batch,
+                            int32_t input_size, int32_t num_classes, float conf, float thr, int32_t diou, float* ob,
+                            float* os, int32_t* oc, int32_t* on, uint8_t* keep, void* ws, int64_t ws_bytes,
+                            void* stream) {
+  if (!boxes || !scores || !cls || !ob || !os || !oc || !on || !ws || input_size <= 0 || input_size % 32 ||
+      ws_bytes < ynb_nms_grid_workspace_bytes(batch, input_size))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_nms_grid: bad arguments / workspace too small");
+  GridNmsWorkspace w = grid_nms_carve(ws, batch, make_grid_geom(input_size).N);
+  UNIT_TRY(launch_nms_grid(boxes, scores, cls, batch, input_size, num_classes, conf, thr, diou, ob, os, oc, on, keep,
+                           w, (cudaStream_t)stream));
+  return YNB_OK;
+}
 
 YNB_EXPORT int ynb_nms(const float* boxes, const float* scores, const int32_t* cls, int32_t batch, int64_t n,
                        int32_t num_classes, float conf, float thr, int32_t diou, float* ob, float* os, int32_t* oc,
