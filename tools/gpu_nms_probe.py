@@ -26,7 +26,8 @@ def main():
     for rep in range(3):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        kept, counts, *_ = G.run_nms(lib, boxes, scores, cls, 80, 0.001, 0.5, False)
+        kept, counts, *_ = G.run_nms(lib, boxes, scores, cls, 80, 0.001, 0.5, False,
+                                     grid_size=416 if "grid" in sys.argv else 0)
         dt = time.perf_counter() - t0
     print("kept per image", counts[:4], "wall incl. H2D/D2H", dt)
 
