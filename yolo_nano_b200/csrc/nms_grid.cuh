@@ -31,7 +31,7 @@
 
 namespace ynb {
 
-constexpr int kSupCap = 32;            // listed suppressors per candidate
+constexpr int kSupCap = 64;            // listed suppressors per candidate (longer lists: re-scan path)
 constexpr uint32_t kMetaIrregular = 0x80000000u;
 constexpr uint32_t kMetaClsMask = 0x1ffu;   // class + 1 (0 = not a candidate)
 
@@ -463,20 +463,39 @@ nms_grid_resolve_kernel(const float* __restrict__ boxes, const float* __restrict
     const int base = s_warp[tid >> 5] + incl0 - mine;
     in_smem = base + mine <= list_cap;
     if (in_smem) {
+      // copy this thread's lists, four candidates at a time so that their first 16-byte parts
+      // (8 entries: most lists) are in flight together
       int off = base;
-      for (unsigned long long m = und; m; m &= m - 1) {
-        const int j = tid + (__ffsll((long long)m) - 1) * kResolveThreads;
-        const int n = min((int)s_cnt[j], kSupCap);
-        s_off[j] = (uint32_t)off;
-        const uint4* src = reinterpret_cast<const uint4*>(sup + (int64_t)j * kSupCap);
-        for (int v = 0; v * 8 < n; ++v) {
-          const uint4 q = src[v];
-          const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+      auto put8 = [&](uint4 q, int dst, int n) {
+        const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-          for (int h = 0; h < 8; ++h)
-            if (v * 8 + h < n) s_list[off + v * 8 + h] = (uint16_t)(wd[h >> 1] >> ((h & 1) * 16));
+        for (int h = 0; h < 8; ++h)
+          if (h < n) s_list[dst + h] = (uint16_t)(wd[h >> 1] >> ((h & 1) * 16));
+      };
+      unsigned long long m = und;
+      while (m) {
+        int jj[4], nn[4];
+        uint4 q0[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          jj[u] = -1;
+          nn[u] = 0;
+          if (m) {
+            jj[u] = tid + (__ffsll((long long)m) - 1) * kResolveThreads;
+            m &= m - 1;
+            nn[u] = min((int)s_cnt[jj[u]], kSupCap);
+            q0[u] = *reinterpret_cast<const uint4*>(sup + (int64_t)jj[u] * kSupCap);
+          }
         }
-        off += n;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (jj[u] < 0) continue;
+          s_off[jj[u]] = (uint32_t)off;
+          put8(q0[u], off, nn[u]);
+          const uint4* src = reinterpret_cast<const uint4*>(sup + (int64_t)jj[u] * kSupCap);
+          for (int v = 1; v * 8 < nn[u]; ++v) put8(src[v], off + v * 8, nn[u] - v * 8);
+          off += nn[u];
+        }
       }
     }
   }
@@ -507,7 +526,7 @@ nms_grid_resolve_kernel(const float* __restrict__ boxes, const float* __restrict
           pending |= s == 1;
         }
       }
-      if (n == 255 && !removed) {           // the list is incomplete: evaluate the definition itself
+      if (n == 255 && !removed && !pending) {   // list incomplete and exhausted: evaluate the definition itself
         SupRescan f{s_state, false, false};
         GridSelf me;
         me.j = j;
@@ -526,22 +545,20 @@ nms_grid_resolve_kernel(const float* __restrict__ boxes, const float* __restrict
     __syncthreads();
     if (!s_progress) break;
   }
-  // ---- compaction, anchor order
-  const int per = (N + kResolveThreads - 1) / kResolveThreads;
-  const int beg = min(N, tid * per), end = min(N, beg + per);
+  // ---- compaction, anchor order: warp w owns anchors [w * per, (w + 1) * per), 32 at a time
+  const int lane = tid & 31, wid = tid >> 5;
+  const int per = ((N + 31) / 32 + 31) & ~31;                 // multiple of 32 anchors per warp
+  const int beg = min(N, wid * per), end = min(N, beg + per);
   uint8_t* kp = keep + (int64_t)b * N;
-  int kept_mine = 0;
-  for (int i = beg; i < end; ++i) {
-    const uint8_t k = s_state[i] == 2;
-    kp[i] = k;
-    kept_mine += k;
+  int wtotal = 0;
+  for (int i0 = beg; i0 < end; i0 += 32) {
+    const int i = i0 + lane;
+    const bool k = i < end && s_state[i] == 2;
+    if (i < end) kp[i] = k;
+    wtotal += __popc(__ballot_sync(0xffffffffu, k));
   }
-  int incl = kept_mine;
-  for (int d = 1; d < 32; d <<= 1) {
-    int v = __shfl_up_sync(0xffffffffu, incl, d);
-    if ((tid & 31) >= d) incl += v;
-  }
-  if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+  __syncthreads();                                            // s_warp is free again
+  if (lane == 0) s_warp[wid] = wtotal;
   __syncthreads();
   if (tid < 32) {
     int wv = s_warp[tid], wi = wv;
@@ -553,16 +570,25 @@ nms_grid_resolve_kernel(const float* __restrict__ boxes, const float* __restrict
     if (tid == 31) out_counts[b] = wi;
   }
   __syncthreads();
-  int pos = s_warp[tid >> 5] + incl - kept_mine;
+  int pos0 = s_warp[wid];
   const float4* bx = reinterpret_cast<const float4*>(boxes) + (int64_t)b * N;
+  const float* sc = scores + (int64_t)b * N;
+  const int32_t* cl = cls + (int64_t)b * N;
   float4* ob = reinterpret_cast<float4*>(out_boxes) + (int64_t)b * N;
-  for (int i = beg; i < end; ++i) {
-    if (s_state[i] == 2) {
+  float* os = out_scores + (int64_t)b * N;
+  int32_t* oc = out_cls + (int64_t)b * N;
+#pragma unroll 4
+  for (int i0 = beg; i0 < end; i0 += 32) {
+    const int i = i0 + lane;
+    const bool k = i < end && s_state[i] == 2;
+    const unsigned bal = __ballot_sync(0xffffffffu, k);
+    if (k) {
+      const int pos = pos0 + __popc(bal & ((1u << lane) - 1u));
       ob[pos] = bx[i];
-      out_scores[(int64_t)b * N + pos] = scores[(int64_t)b * N + i];
-      out_cls[(int64_t)b * N + pos] = cls[(int64_t)b * N + i];
-      ++pos;
+      os[pos] = sc[i];
+      oc[pos] = cl[i];
     }
+    pos0 += __popc(bal);
   }
 }
 
