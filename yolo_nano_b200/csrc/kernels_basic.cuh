@@ -20,21 +20,29 @@ constexpr int kStemConv = 2 * kStemTile + 1;   // 17
 constexpr int kStemIn = 2 * kStemConv + 1;     // 35
 constexpr int kStemInPitch = 36;
 constexpr int kStemC = 24;
-constexpr int kStemThreads = 320;              // 289 conv positions of a tile, one per thread
+constexpr int kStemPairs = (kStemConv + 1) / 2;                  // 9 column pairs per conv row
+constexpr int kStemTasks = kStemConv * kStemPairs * 2;           // (row, column pair, channel half) = 306
+constexpr int kStemThreads = 320;
 
-// Folded stem weights travel as a kernel parameter: they then live in the constant bank
-// and every FFMA takes its weight operand straight from c[0][..] (warp-uniform, no
-// shared-memory traffic) — the conv is FMA-bound instead of LDS-bound.
+// Folded stem weights travel as a kernel parameter (constant bank) and are staged in shared
+// memory by every CTA.
 struct StemWeights {
   float w[27][kStemC];   // [(ci*3+ky)*3+kx][co]
   float b[kStemC];
 };
 
+// The conv is bound by the FMA pipe (648 FMAs per conv output, one FFMA issue every other cycle
+// per scheduler), so it is written with the packed FFMA2 (two fp32 FMAs per instruction, each
+// rounded exactly like fmaf): a thread owns two horizontally adjacent conv positions and 12 of
+// the 24 output channels = 12 float2 accumulators; per tap it reads two input pixels and three
+// 16-byte weight vectors (broadcast) and issues 12 FFMA2.
 __global__ void __launch_bounds__(kStemThreads)
 stem_pool_kernel(const float* __restrict__ x, float* __restrict__ out, const __grid_constant__ StemWeights wt,
                  int S) {
   __shared__ float s_in[3][kStemIn][kStemInPitch];
   __shared__ float s_conv[kStemConv * kStemConv][kStemC + 1];
+  __shared__ __align__(16) float s_w[27][kStemC];
+  __shared__ __align__(16) float s_b[kStemC];
 
   const int Hc = S / 2, Hp = S / 4;
   const int b = blockIdx.z;
@@ -43,40 +51,89 @@ stem_pool_kernel(const float* __restrict__ x, float* __restrict__ out, const __g
   const int iy0 = 2 * cy0 - 1, ix0 = 2 * cx0 - 1;   // first input row / col
   const int tid = threadIdx.x;
   pdl_trigger();
+  for (int i = tid; i < 27 * kStemC; i += kStemThreads) (&s_w[0][0])[i] = (&wt.w[0][0])[i];
+  if (tid < kStemC) s_b[tid] = wt.b[tid];
   pdl_wait();          // the previous forward may still be reading / writing these buffers
 
+  // input patch: all of a thread's loads are issued before the first one is consumed (one
+  // global round trip per CTA instead of twelve)
   const float* xb = x + (size_t)b * 3 * S * S;
-  for (int i = tid; i < 3 * kStemIn * kStemIn; i += kStemThreads) {
-    int c = i / (kStemIn * kStemIn);
-    int r = (i / kStemIn) % kStemIn;
-    int q = i % kStemIn;
-    int iy = iy0 + r, ix = ix0 + q;
-    float v = 0.0f;
-    if (iy >= 0 && iy < S && ix >= 0 && ix < S) v = __ldg(xb + ((size_t)c * S + iy) * S + ix);
-    s_in[c][r][q] = v;
+  constexpr int kLoads = (3 * kStemIn * kStemIn + kStemThreads - 1) / kStemThreads;   // 12
+  float lv[kLoads];
+#pragma unroll
+  for (int u = 0; u < kLoads; ++u) {
+    const int i = tid + u * kStemThreads;
+    const int c = i / (kStemIn * kStemIn);
+    const int rem = i - c * (kStemIn * kStemIn);
+    const int r = rem / kStemIn, q = rem - r * kStemIn;
+    const int iy = iy0 + r, ix = ix0 + q;
+    lv[u] = 0.0f;
+    if (i < 3 * kStemIn * kStemIn && iy >= 0 && iy < S && ix >= 0 && ix < S)
+      lv[u] = __ldg(xb + ((size_t)c * S + iy) * S + ix);
+  }
+#pragma unroll
+  for (int u = 0; u < kLoads; ++u) {
+    const int i = tid + u * kStemThreads;
+    const int c = i / (kStemIn * kStemIn);
+    const int rem = i - c * (kStemIn * kStemIn);
+    const int r = rem / kStemIn, q = rem - r * kStemIn;
+    if (i < 3 * kStemIn * kStemIn) s_in[c][r][q] = lv[u];
   }
   __syncthreads();
 
-  // conv + bias + ReLU: one thread per conv position, all 24 output channels in registers
-  if (tid < kStemConv * kStemConv) {
-    const int r = tid / kStemConv, q = tid % kStemConv;
-    const int cy = cy0 + r, cx = cx0 + q;
-    float acc[kStemC];
+  // conv + bias + ReLU
+  if (tid < kStemTasks) {
+    const int half = tid & 1;                     // channels [12*half, 12*half + 12)
+    const int pr = tid >> 1;
+    const int r = pr / kStemPairs, q0 = (pr - r * kStemPairs) * 2;
+    const bool has2 = q0 + 1 < kStemConv;
+    const int c0 = half * 12;
+    float2 acc0[6], acc1[6];
 #pragma unroll
-    for (int co = 0; co < kStemC; ++co) acc[co] = wt.b[co];
+    for (int j = 0; j < 6; ++j) acc0[j] = acc1[j] = make_float2(s_b[c0 + 2 * j], s_b[c0 + 2 * j + 1]);
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
+      for (int ky = 0; ky < 3; ++ky) {
+        // input columns 2*q0 .. 2*q0+4 of row 2r+ky feed both positions (the last pair of a row
+        // reads up to column 36 > pitch only when has2 is false: clamp the index instead)
+        const float* row = &s_in[ci][2 * r + ky][0];
+        float in[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) in[j] = row[min(2 * q0 + j, kStemIn - 1)];
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const float v = s_in[ci][2 * r + ky][2 * q + kx];
+          const float4* wv = reinterpret_cast<const float4*>(&s_w[(ci * 3 + ky) * 3 + kx][c0]);
+          const float2 v0 = make_float2(in[kx], in[kx]), v1 = make_float2(in[kx + 2], in[kx + 2]);
 #pragma unroll
-          for (int co = 0; co < kStemC; ++co) acc[co] = fmaf(v, wt.w[(ci * 3 + ky) * 3 + kx][co], acc[co]);
+          for (int j = 0; j < 3; ++j) {
+            const float4 w4 = wv[j];
+            const float2 wa = make_float2(w4.x, w4.y), wb = make_float2(w4.z, w4.w);
+            acc0[2 * j] = __ffma2_rn(v0, wa, acc0[2 * j]);
+            acc0[2 * j + 1] = __ffma2_rn(v0, wb, acc0[2 * j + 1]);
+            acc1[2 * j] = __ffma2_rn(v1, wa, acc1[2 * j]);
+            acc1[2 * j + 1] = __ffma2_rn(v1, wb, acc1[2 * j + 1]);
+          }
         }
-    const bool inside = cy >= 0 && cy < Hc && cx >= 0 && cx < Hc;
+      }
+    const int cy = cy0 + r;
+    const bool row_in = cy >= 0 && cy < Hc;
+    const bool in0 = row_in && cx0 + q0 >= 0 && cx0 + q0 < Hc;
+    const bool in1 = row_in && cx0 + q0 + 1 >= 0 && cx0 + q0 + 1 < Hc;
+    float* d0 = &s_conv[r * kStemConv + q0][c0];
 #pragma unroll
-    for (int co = 0; co < kStemC; ++co) s_conv[tid][co] = inside ? fmaxf(acc[co], 0.0f) : 0.0f;
+    for (int j = 0; j < 6; ++j) {
+      d0[2 * j] = in0 ? fmaxf(acc0[j].x, 0.0f) : 0.0f;
+      d0[2 * j + 1] = in0 ? fmaxf(acc0[j].y, 0.0f) : 0.0f;
+    }
+    if (has2) {
+      float* d1 = d0 + (kStemC + 1);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        d1[2 * j] = in1 ? fmaxf(acc1[j].x, 0.0f) : 0.0f;
+        d1[2 * j + 1] = in1 ? fmaxf(acc1[j].y, 0.0f) : 0.0f;
+      }
+    }
   }
   __syncthreads();
 
@@ -119,65 +176,66 @@ inline cudaError_t launch_stem_pool(const float* x, float* out, const StemWeight
 // kernel off the L1 bandwidth limit the one-pixel-per-thread version sat on.
 constexpr int kDwTX = 4;
 
+constexpr int kDwThreads = 128;
+
+// grid: x = ceil(channel groups * x groups / 128), y = output row, z = image — the only index
+// arithmetic left per thread is one division; all addressing inside an image is 32-bit.
 template <int STRIDE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kDwThreads)
 dwconv3x3_kernel(const float* __restrict__ in, int in_ld, int in_off,
                  float* __restrict__ out, int out_ld, int out_off,
                  const float* __restrict__ w, const float* __restrict__ bias,
-                 int batch, int Hin, int Win, int C4, int act) {
+                 int Hin, int Win, int Ho, int Wo, int groups, int xgroups, int C4, int act) {
   constexpr int NIN = (kDwTX - 1) * STRIDE + 3;
-  const int Ho = (Hin - 1) / STRIDE + 1, Wo = (Win - 1) / STRIDE + 1;
-  const int groups = C4 >> 2;
-  const int xgroups = (Wo + kDwTX - 1) / kDwTX;
-  const int64_t total = (int64_t)batch * Ho * xgroups * groups;
   pdl_trigger();
+  const int t = blockIdx.x * kDwThreads + threadIdx.x;
+  if (t >= groups * xgroups) { pdl_wait(); return; }
+  const int xg = t / groups, g = t - xg * groups;
+  const int yo = blockIdx.y, b = blockIdx.z;
+  const int c = g << 2;
+  const int xo0 = xg * kDwTX;
+  const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c));
+  float4 kw[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) kw[k] = __ldg(reinterpret_cast<const float4*>(w + k * C4 + c));
   pdl_wait();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(i % groups);
-    int64_t p = i / groups;
-    const int xg = (int)(p % xgroups);
-    const int yo = (int)((p / xgroups) % Ho);
-    const int b = (int)(p / ((int64_t)xgroups * Ho));
-    const int c = g << 2;
-    const int xo0 = xg * kDwTX;
-    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c));
-    float4 acc[kDwTX];
+  float4 acc[kDwTX];
 #pragma unroll
-    for (int t = 0; t < kDwTX; ++t) acc[t] = bv;
-    const float* inb = in + (size_t)b * Hin * Win * in_ld + in_off + c;
+  for (int q = 0; q < kDwTX; ++q) acc[q] = bv;
+  const float* inb = in + (size_t)b * Hin * Win * in_ld + in_off + c;
+  const int xi0 = xo0 * STRIDE - 1;
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int yi = yo * STRIDE + ky - 1;
-      if (yi < 0 || yi >= Hin) continue;
-      float4 v[NIN];
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yi = yo * STRIDE + ky - 1;
+    if (yi < 0 || yi >= Hin) continue;
+    const float* rowp = inb + (yi * Win + xi0) * in_ld;          // 32-bit offsets inside an image
+    float4 v[NIN];
 #pragma unroll
-      for (int j = 0; j < NIN; ++j) {
-        const int xi = xo0 * STRIDE - 1 + j;
-        v[j] = (xi >= 0 && xi < Win) ? __ldg(reinterpret_cast<const float4*>(inb + ((size_t)yi * Win + xi) * in_ld))
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+    for (int j = 0; j < NIN; ++j) {
+      const int xi = xi0 + j;
+      v[j] = (xi >= 0 && xi < Win) ? __ldg(reinterpret_cast<const float4*>(rowp + j * in_ld))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const float4 k = __ldg(reinterpret_cast<const float4*>(w + (ky * 3 + kx) * C4 + c));
+    for (int kx = 0; kx < 3; ++kx) {
+      const float4 k = kw[ky * 3 + kx];
 #pragma unroll
-        for (int t = 0; t < kDwTX; ++t) {
-          const float4 u = v[t * STRIDE + kx];
-          acc[t].x = fmaf(u.x, k.x, acc[t].x);
-          acc[t].y = fmaf(u.y, k.y, acc[t].y);
-          acc[t].z = fmaf(u.z, k.z, acc[t].z);
-          acc[t].w = fmaf(u.w, k.w, acc[t].w);
-        }
+      for (int q = 0; q < kDwTX; ++q) {
+        const float4 u = v[q * STRIDE + kx];
+        // packed FFMA2: two fp32 FMAs per issue slot, each rounded like fmaf
+        const float2 lo = __ffma2_rn(make_float2(u.x, u.y), make_float2(k.x, k.y), make_float2(acc[q].x, acc[q].y));
+        const float2 hi = __ffma2_rn(make_float2(u.z, u.w), make_float2(k.z, k.w), make_float2(acc[q].z, acc[q].w));
+        acc[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
       }
     }
-    float* ob = out + (((size_t)b * Ho + yo) * Wo + xo0) * out_ld + out_off + c;
+  }
+  float* ob = out + (size_t)b * Ho * Wo * out_ld + (yo * Wo + xo0) * out_ld + out_off + c;
 #pragma unroll
-    for (int t = 0; t < kDwTX; ++t) {
-      if (xo0 + t < Wo) {
-        float4 a = acc[t];
-        a.x = apply_act(a.x, act); a.y = apply_act(a.y, act); a.z = apply_act(a.z, act); a.w = apply_act(a.w, act);
-        *reinterpret_cast<float4*>(ob + (size_t)t * out_ld) = a;
-      }
+  for (int q = 0; q < kDwTX; ++q) {
+    if (xo0 + q < Wo) {
+      float4 a = acc[q];
+      a.x = apply_act(a.x, act); a.y = apply_act(a.y, act); a.z = apply_act(a.z, act); a.w = apply_act(a.w, act);
+      *reinterpret_cast<float4*>(ob + q * out_ld) = a;
     }
   }
 }
@@ -186,13 +244,12 @@ inline cudaError_t launch_dwconv3x3(const float* in, int in_ld, int in_off, floa
                                     int out_off, const float* w, const float* b, int batch, int Hin,
                                     int Win, int C4, int stride, int act, cudaStream_t st) {
   const int Ho = (Hin - 1) / stride + 1, Wo = (Win - 1) / stride + 1;
-  int64_t total = (int64_t)batch * Ho * ((Wo + kDwTX - 1) / kDwTX) * (C4 / 4);
-  int64_t blocks = (total + 255) / 256;
-  int64_t cap = (int64_t)kNumSMs * 16;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  cudaError_t r = launch_pdl(stride == 1 ? dwconv3x3_kernel<1> : dwconv3x3_kernel<2>, dim3((unsigned)blocks), dim3(256),
-                             0, st, in, in_ld, in_off, out, out_ld, out_off, w, b, batch, Hin, Win, C4, act);
+  const int groups = C4 / 4, xgroups = (Wo + kDwTX - 1) / kDwTX;
+  if (batch <= 0 || Ho <= 0 || groups <= 0) return cudaSuccess;
+  if (Ho > 65535 || batch > 65535) return cudaErrorInvalidValue;
+  dim3 grid((unsigned)((groups * xgroups + kDwThreads - 1) / kDwThreads), (unsigned)Ho, (unsigned)batch);
+  cudaError_t r = launch_pdl(stride == 1 ? dwconv3x3_kernel<1> : dwconv3x3_kernel<2>, grid, dim3(kDwThreads), 0, st, in,
+                             in_ld, in_off, out, out_ld, out_off, w, b, Hin, Win, Ho, Wo, groups, xgroups, C4, act);
   YNB_COUNT_LAUNCH();
   return r;
 }
