@@ -630,6 +630,21 @@ inline bool make_tmap_nhwc(CUtensorMap* m, const float* base, int C, int W, int 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// rank-4 map over the NCHW fp32 network input [B][3][S][S] for the stem: boxes of
+// [40 x 35 x 3 x 1] floats, no swizzle, zero fill outside the image (the conv's padding).  The start
+// coordinate of the innermost dimension must keep the global address 16-byte aligned.
+inline bool make_tmap_stem_input(CUtensorMap* m, const float* x, int S, int B) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc || (reinterpret_cast<uintptr_t>(x) & 15u) || (S & 3)) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)S, (cuuint64_t)S, 3, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)S * 4, (cuuint64_t)S * S * 4, (cuuint64_t)S * S * 12};
+  cuuint32_t box[4] = {40, 35, 3, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // rank-2 STORE map over an output view [rows][ld] exposing `cols` channels (multiple of 4):
 // boxes of 32 channels x 32 rows, 128-byte swizzle (matches the epilogue's staging layout).
 inline bool make_tmap_out(CUtensorMap* m, float* base, uint64_t cols, uint64_t rows, uint64_t ld) {

@@ -2,6 +2,7 @@
 // interleave (channel shuffle as a store permutation) and layout conversion for taps.
 #pragma once
 #include "common.cuh"
+#include "ptx_sm100.cuh"
 
 namespace ynb {
 
@@ -18,8 +19,10 @@ namespace ynb {
 constexpr int kStemTile = 8;
 constexpr int kStemConv = 2 * kStemTile + 1;   // 17
 constexpr int kStemIn = 2 * kStemConv + 1;     // 35
-constexpr int kStemInPitch = 36;
+constexpr int kStemInPitch = 40;               // TMA box rows: 40 floats; the box starts ONE column left of the
+                                               // patch so that its first element is 16-byte aligned in global memory
 constexpr int kStemC = 24;
+constexpr int kStemCP = 24;                    // s_conv pitch: 16-byte aligned rows, 45.5 KB static smem in total
 constexpr int kStemPairs = (kStemConv + 1) / 2;                  // 9 column pairs per conv row
 constexpr int kStemTasks = kStemConv * kStemPairs * 2;           // (row, column pair, channel half) = 306
 constexpr int kStemThreads = 320;
@@ -31,18 +34,25 @@ struct StemWeights {
   float b[kStemC];
 };
 
-// The conv is bound by the FMA pipe (648 FMAs per conv output, one FFMA issue every other cycle
-// per scheduler), so it is written with the packed FFMA2 (two fp32 FMAs per instruction, each
-// rounded exactly like fmaf): a thread owns two horizontally adjacent conv positions and 12 of
-// the 24 output channels = 12 float2 accumulators; per tap it reads two input pixels and three
-// 16-byte weight vectors (broadcast) and issues 12 FFMA2.
+// Input patch: ONE TMA box load per CTA — [40 x 35 x 3] floats of the NCHW image at (ix0 - 1, iy0),
+// out-of-image elements zero-filled by the copy engine (= the conv's zero padding) — instead of
+// twelve bounds-checked scalar loads per thread.  tmX == nullptr-equivalent (use_tma = 0, input
+// not 16-byte aligned) falls back to those loads.
+//
+// The conv is bound by the FMA pipe / issue slots (648 FMAs per conv output), so it is written
+// with the packed FFMA2 (two fp32 FMAs per instruction, each rounded exactly like fmaf): a thread
+// owns two horizontally adjacent conv positions and 12 of the 24 output channels = 12 float2
+// accumulators; per tap it reads two input pixels and three 16-byte weight vectors (broadcast)
+// and issues 12 FFMA2.  (Measured on B200, tools/fma_probe.cu: FFMA with a constant-bank /
+// uniform-register operand runs at half rate, which is what the previous version did.)
 __global__ void __launch_bounds__(kStemThreads)
 stem_pool_kernel(const float* __restrict__ x, float* __restrict__ out, const __grid_constant__ StemWeights wt,
-                 int S) {
-  __shared__ float s_in[3][kStemIn][kStemInPitch];
-  __shared__ float s_conv[kStemConv * kStemConv][kStemC + 1];
+                 const __grid_constant__ CUtensorMap tmX, int use_tma, int S) {
+  __shared__ __align__(128) float s_in[3][kStemIn][kStemInPitch];
+  __shared__ __align__(16) float s_conv[kStemConv * kStemConv][kStemCP];
   __shared__ __align__(16) float s_w[27][kStemC];
   __shared__ __align__(16) float s_b[kStemC];
+  __shared__ __align__(8) uint64_t s_bar;
 
   const int Hc = S / 2, Hp = S / 4;
   const int b = blockIdx.z;
@@ -51,35 +61,34 @@ stem_pool_kernel(const float* __restrict__ x, float* __restrict__ out, const __g
   const int iy0 = 2 * cy0 - 1, ix0 = 2 * cx0 - 1;   // first input row / col
   const int tid = threadIdx.x;
   pdl_trigger();
+  if (use_tma && tid == 0) {
+    ptx::mbar_init(&s_bar, 1);
+    ptx::fence_barrier_init();
+  }
   for (int i = tid; i < 27 * kStemC; i += kStemThreads) (&s_w[0][0])[i] = (&wt.w[0][0])[i];
   if (tid < kStemC) s_b[tid] = wt.b[tid];
   pdl_wait();          // the previous forward may still be reading / writing these buffers
 
-  // input patch: all of a thread's loads are issued before the first one is consumed (one
-  // global round trip per CTA instead of twelve)
-  const float* xb = x + (size_t)b * 3 * S * S;
-  constexpr int kLoads = (3 * kStemIn * kStemIn + kStemThreads - 1) / kStemThreads;   // 12
-  float lv[kLoads];
-#pragma unroll
-  for (int u = 0; u < kLoads; ++u) {
-    const int i = tid + u * kStemThreads;
-    const int c = i / (kStemIn * kStemIn);
-    const int rem = i - c * (kStemIn * kStemIn);
-    const int r = rem / kStemIn, q = rem - r * kStemIn;
-    const int iy = iy0 + r, ix = ix0 + q;
-    lv[u] = 0.0f;
-    if (i < 3 * kStemIn * kStemIn && iy >= 0 && iy < S && ix >= 0 && ix < S)
-      lv[u] = __ldg(xb + ((size_t)c * S + iy) * S + ix);
+  if (use_tma) {
+    if (tid == 0) {
+      ptx::mbar_arrive_expect_tx(&s_bar, 3 * kStemIn * kStemInPitch * 4);
+      ptx::tma_load_4d(&s_in[0][0][0], &tmX, &s_bar, ix0 - 1, iy0, 0, b);   // 16*bx - 4: multiple of 4 floats
+    }
+    __syncthreads();                                   // barrier init visible + weights staged
+    ptx::mbar_wait(&s_bar, 0, nullptr, 0);
+  } else {
+    const float* xb = x + (size_t)b * 3 * S * S;
+    for (int i = tid; i < 3 * kStemIn * kStemIn; i += kStemThreads) {
+      const int c = i / (kStemIn * kStemIn);
+      const int rem = i - c * (kStemIn * kStemIn);
+      const int r = rem / kStemIn, q = rem - r * kStemIn;
+      const int iy = iy0 + r, ix = ix0 + q;
+      float v = 0.0f;
+      if (iy >= 0 && iy < S && ix >= 0 && ix < S) v = __ldg(xb + ((size_t)c * S + iy) * S + ix);
+      s_in[c][r][q + 1] = v;
+    }
+    __syncthreads();
   }
-#pragma unroll
-  for (int u = 0; u < kLoads; ++u) {
-    const int i = tid + u * kStemThreads;
-    const int c = i / (kStemIn * kStemIn);
-    const int rem = i - c * (kStemIn * kStemIn);
-    const int r = rem / kStemIn, q = rem - r * kStemIn;
-    if (i < 3 * kStemIn * kStemIn) s_in[c][r][q] = lv[u];
-  }
-  __syncthreads();
 
   // conv + bias + ReLU
   if (tid < kStemTasks) {
@@ -95,9 +104,9 @@ stem_pool_kernel(const float* __restrict__ x, float* __restrict__ out, const __g
     for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
-        // input columns 2*q0 .. 2*q0+4 of row 2r+ky feed both positions (the last pair of a row
-        // reads up to column 36 > pitch only when has2 is false: clamp the index instead)
-        const float* row = &s_in[ci][2 * r + ky][0];
+        // input columns 2*q0 .. 2*q0+4 of row 2r+ky feed both positions (the last pair of a row has
+        // one position only: clamp the index)
+        const float* row = &s_in[ci][2 * r + ky][1];
         float in[5];
 #pragma unroll
         for (int j = 0; j < 5; ++j) in[j] = row[min(2 * q0 + j, kStemIn - 1)];
@@ -120,45 +129,48 @@ stem_pool_kernel(const float* __restrict__ x, float* __restrict__ out, const __g
     const bool row_in = cy >= 0 && cy < Hc;
     const bool in0 = row_in && cx0 + q0 >= 0 && cx0 + q0 < Hc;
     const bool in1 = row_in && cx0 + q0 + 1 >= 0 && cx0 + q0 + 1 < Hc;
-    float* d0 = &s_conv[r * kStemConv + q0][c0];
+    float4* d0 = reinterpret_cast<float4*>(&s_conv[r * kStemConv + q0][c0]);
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      d0[2 * j] = in0 ? fmaxf(acc0[j].x, 0.0f) : 0.0f;
-      d0[2 * j + 1] = in0 ? fmaxf(acc0[j].y, 0.0f) : 0.0f;
-    }
+    for (int j = 0; j < 3; ++j)
+      d0[j] = in0 ? make_float4(fmaxf(acc0[2 * j].x, 0.f), fmaxf(acc0[2 * j].y, 0.f), fmaxf(acc0[2 * j + 1].x, 0.f),
+                                fmaxf(acc0[2 * j + 1].y, 0.f))
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
     if (has2) {
-      float* d1 = d0 + (kStemC + 1);
+      float4* d1 = reinterpret_cast<float4*>(&s_conv[r * kStemConv + q0 + 1][c0]);
 #pragma unroll
-      for (int j = 0; j < 6; ++j) {
-        d1[2 * j] = in1 ? fmaxf(acc1[j].x, 0.0f) : 0.0f;
-        d1[2 * j + 1] = in1 ? fmaxf(acc1[j].y, 0.0f) : 0.0f;
-      }
+      for (int j = 0; j < 3; ++j)
+        d1[j] = in1 ? make_float4(fmaxf(acc1[2 * j].x, 0.f), fmaxf(acc1[2 * j].y, 0.f), fmaxf(acc1[2 * j + 1].x, 0.f),
+                                  fmaxf(acc1[2 * j + 1].y, 0.f))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   __syncthreads();
 
-  for (int i = tid; i < kStemTile * kStemTile * kStemC; i += kStemThreads) {
-    int co = i % kStemC;
-    int p = i / kStemC;
-    int r = p / kStemTile, q = p % kStemTile;
-    int py = py0 + r, px = px0 + q;
+  // 3x3 / stride 2 max-pool: a thread takes 4 channels of one pooled pixel (16-byte accesses)
+  for (int i = tid; i < kStemTile * kStemTile * (kStemC / 4); i += kStemThreads) {
+    const int p = i / (kStemC / 4), c4 = (i - p * (kStemC / 4)) * 4;
+    const int r = p / kStemTile, q = p - r * kStemTile;
+    const int py = py0 + r, px = px0 + q;
     if (py >= Hp || px >= Hp) continue;
-    float m = 0.0f;
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx)
-        m = fmaxf(m, s_conv[(2 * r + dy) * kStemConv + 2 * q + dx][co]);
-    out[(((size_t)b * Hp + py) * Hp + px) * kStemC + co] = m;
+      for (int dx = 0; dx < 3; ++dx) {
+        const float4 v = *reinterpret_cast<const float4*>(&s_conv[(2 * r + dy) * kStemConv + 2 * q + dx][c4]);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    *reinterpret_cast<float4*>(out + (((size_t)b * Hp + py) * Hp + px) * kStemC + c4) = m;
   }
 }
 
-// w: [27][24] device or host floats are copied into the parameter block by the caller.
-inline cudaError_t launch_stem_pool(const float* x, float* out, const StemWeights& wt, int batch, int S,
-                                    cudaStream_t st) {
+// tmX: rank-4 map over the NCHW input (make_tmap_stem_input); pass use_tma = 0 (any map) when the
+// input pointer is not 16-byte aligned.
+inline cudaError_t launch_stem_pool(const float* x, float* out, const StemWeights& wt, const CUtensorMap& tmX,
+                                    int use_tma, int batch, int S, cudaStream_t st) {
   int Hp = S / 4;
   dim3 grid((Hp + kStemTile - 1) / kStemTile, (Hp + kStemTile - 1) / kStemTile, batch);
-  cudaError_t r = launch_pdl(stem_pool_kernel, grid, dim3(kStemThreads), 0, st, x, out, wt, S);
+  cudaError_t r = launch_pdl(stem_pool_kernel, grid, dim3(kStemThreads), 0, st, x, out, wt, tmX, use_tma, S);
   YNB_COUNT_LAUNCH();
   return r;
 }

@@ -96,6 +96,8 @@ struct ynb_engine {
   std::map<std::string, int> index;
   std::vector<PackedConv> convs;
   StemWeights stem_w;                      // folded stem weights, passed as a kernel parameter
+  struct StemMap { CUtensorMap tm; int ok; };
+  std::map<std::pair<const float*, int>, StemMap> stem_maps;   // TMA maps over caller inputs
   bool committed = false;
 
   // workspace
@@ -556,7 +558,17 @@ int build_plan(ynb_engine* e, int B, Plan** out) {
     double px = (double)B * S * S;
     plan->net.push_back({"backbone.conv1.0+maxpool", "stem_pool", 4.0 * (3 * px + 24 * px / 16) + 4.0 * 27 * 24,
                          2.0 * 27 * 24 * px / 4, [=](cudaStream_t st) {
-      return launch_stem_pool(e->d_x_bound, pool.p, e->stem_w, B, S, st);
+      // the input pointer is the caller's: one tensor map per (pointer, batch), built on first sight
+      const float* xin = e->d_x_bound;
+      auto key = std::make_pair(xin, B);
+      auto it = e->stem_maps.find(key);
+      if (it == e->stem_maps.end()) {
+        ynb_engine::StemMap sm{};
+        sm.ok = make_tmap_stem_input(&sm.tm, xin, S, B) ? 1 : 0;
+        if (e->stem_maps.size() > 64) e->stem_maps.clear();
+        it = e->stem_maps.emplace(key, sm).first;
+      }
+      return launch_stem_pool(xin, pool.p, e->stem_w, it->second.tm, it->second.ok, B, S, st);
     }});
   }
   Tensor x = P.T("pool");
@@ -1306,7 +1318,9 @@ YNB_EXPORT int ynb_stem_pool(const float* x, float* out, const float* w, const f
   StemWeights wt;   // test hook: fetch the weights into the parameter block (synchronous)
   UNIT_TRY(cudaMemcpy(wt.w, w, sizeof(wt.w), cudaMemcpyDeviceToHost));
   UNIT_TRY(cudaMemcpy(wt.b, b, sizeof(wt.b), cudaMemcpyDeviceToHost));
-  UNIT_TRY(launch_stem_pool(x, out, wt, batch, input_size, (cudaStream_t)stream));
+  CUtensorMap tmx{};
+  const int use_tma = make_tmap_stem_input(&tmx, x, input_size, batch) ? 1 : 0;
+  UNIT_TRY(launch_stem_pool(x, out, wt, tmx, use_tma, batch, input_size, (cudaStream_t)stream));
   return YNB_OK;
 }
 
