@@ -288,7 +288,8 @@ def main():
         sampler.join(timeout=3)
     kept = int(out_host2[(a.steps - 1) & 1][3].sum())
     h2d = a.batch * 3 * a.size * a.size * 4
-    d2h = a.batch * 4 + kept * 24
+    kmax = int(out_host2[(a.steps - 1) & 1][3].max())
+    d2h = a.batch * 4 + a.batch * kmax * 24      # rows [0, max count) of every image (strided copies)
 
     # ---- per-kernel roofline (CUDA events around every launch, same process) ----------------
     prof = {}

@@ -122,7 +122,8 @@ struct ynb_engine {
     float* ob = nullptr; float* os = nullptr; int32_t* oc = nullptr; int32_t* on = nullptr;   // host destinations
     int* flag_host = nullptr;          // pinned: device error word of this step
   } slot[2];
-  cudaStream_t s_copy = nullptr;       // H2D / D2H next to the compute stream
+  cudaStream_t s_copy = nullptr;       // H2D next to the compute stream
+  cudaStream_t s_d2h = nullptr;        // results back to the host (PCIe is full duplex: its own stream)
   const float* d_x_bound = nullptr;   // input of the forward in flight
   float* d_out_boxes = nullptr;
   float* d_out_scores = nullptr;
@@ -849,6 +850,7 @@ YNB_EXPORT int ynb_create(const ynb_config* cfg, ynb_engine** out) {
             cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
   for (int k = 0; k < 2 && ok; ++k)
     ok = cudaEventCreateWithFlags(&e->slot[k].h2d, cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&e->slot[k].done, cudaEventDisableTiming) == cudaSuccess &&
@@ -883,6 +885,7 @@ YNB_EXPORT void ynb_destroy(ynb_engine* e) {
     if (e->slot[k].flag_host) cudaFreeHost(e->slot[k].flag_host);
   }
   if (e->s_copy) cudaStreamDestroy(e->s_copy);
+  if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
   if (e->s_main) cudaStreamDestroy(e->s_main);
   if (e->s_side) cudaStreamDestroy(e->s_side);
   for (PackedConv& pc : e->convs) {
@@ -1125,18 +1128,20 @@ YNB_EXPORT int ynb_wait_host(ynb_engine* e, int32_t slot_id) {
     cudaMemsetAsync(e->d_err, 0, 4, e->s_main);
     return fail(e, YNB_ERR_CUDA, "tensor-core pipeline timed out waiting on mbarrier (code " + std::to_string(code) + ")");
   }
-  // counts are on the host now: only the kept rows of each image cross PCIe (copy stream)
+  // counts are on the host now: only the kept rows cross PCIe — three strided copies (rows
+  // [0, max count) of every image) on the D2H stream, not 3 x batch small ones behind the next H2D
   const int64_t n = e->N();
-  for (int b = 0; b < sl.batch; ++b) {
-    size_t k = (size_t)sl.on[b];
-    if (k == 0) continue;
-    CUDA_TRY(e, cudaMemcpyAsync(sl.ob + (size_t)b * n * 4, sl.boxes + (size_t)b * n * 4, k * 16, cudaMemcpyDeviceToHost,
-                                e->s_copy));
-    CUDA_TRY(e, cudaMemcpyAsync(sl.os + (size_t)b * n, sl.scores + (size_t)b * n, k * 4, cudaMemcpyDeviceToHost,
-                                e->s_copy));
-    CUDA_TRY(e, cudaMemcpyAsync(sl.oc + (size_t)b * n, sl.cls + (size_t)b * n, k * 4, cudaMemcpyDeviceToHost, e->s_copy));
+  size_t kmax = 0;
+  for (int b = 0; b < sl.batch; ++b) kmax = std::max(kmax, (size_t)sl.on[b]);
+  if (kmax > 0) {
+    CUDA_TRY(e, cudaMemcpy2DAsync(sl.ob, (size_t)n * 16, sl.boxes, (size_t)n * 16, kmax * 16, sl.batch,
+                                  cudaMemcpyDeviceToHost, e->s_d2h));
+    CUDA_TRY(e, cudaMemcpy2DAsync(sl.os, (size_t)n * 4, sl.scores, (size_t)n * 4, kmax * 4, sl.batch,
+                                  cudaMemcpyDeviceToHost, e->s_d2h));
+    CUDA_TRY(e, cudaMemcpy2DAsync(sl.oc, (size_t)n * 4, sl.cls, (size_t)n * 4, kmax * 4, sl.batch,
+                                  cudaMemcpyDeviceToHost, e->s_d2h));
+    CUDA_TRY(e, cudaStreamSynchronize(e->s_d2h));
   }
-  CUDA_TRY(e, cudaStreamSynchronize(e->s_copy));
   return YNB_OK;
 }
 
