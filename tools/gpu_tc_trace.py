@@ -1,5 +1,5 @@
 """Timeline of one CTA of the tcgen05 GEMM (YNB_TC_TRACE): who waits for whom.
-    python tools/gpu_tc_trace.py M K N
+    python tools/gpu_tc_trace.py M K N [mode]
 """
 import os
 import subprocess
@@ -15,21 +15,23 @@ import gpu_util as G
 from yolo_nano_b200 import _lib
 lib = _lib.load()
 m, k, n = %d, %d, %d
+mode = %d
 x = torch.randn(m, k, device=G.DEV); w = torch.randn(n, k, device=G.DEV); b = torch.zeros(n, device=G.DEV)
 ld = (n + 3) // 4 * 4
 import os
 if os.environ.get('YNB_TC_PASS'): ld = 2 * ld
 out = torch.zeros(m, ld, device=G.DEV)
 for _ in range(2):
-    rc = lib.ynb_pwconv_tc(G.ptr(x), k, 0, G.ptr(out), ld, 0, 1, G.ptr(w), G.ptr(b), m, k, n, 1, 1, G.stream())
+    rc = lib.ynb_pwconv_tc(G.ptr(x), k, 0, G.ptr(out), ld, 0, 1, G.ptr(w), G.ptr(b), m, k, n, 1, mode, G.stream())
 assert rc == 0
 '''
 
 
 def main():
     m, k, n = (int(v) for v in sys.argv[1:4])
+    mode = int(sys.argv[4]) if len(sys.argv) > 4 else 1      # 1 = 3xTF32, 2 = single-pass TF32
     env = dict(os.environ, YNB_TC_TRACE="1")
-    code = CHILD % (str(ROOT), str(ROOT / "tests"), m, k, n)
+    code = CHILD % (str(ROOT), str(ROOT / "tests"), m, k, n, mode)
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     lines = res.stderr.splitlines()
     hdrs = [l for l in lines if l.startswith("YNB_TC_TRACE")]

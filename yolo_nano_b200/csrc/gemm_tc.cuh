@@ -95,15 +95,16 @@ struct TcGemmParams {
 };
 
 // roles: 1 producer-issued, 2 split-done, 3 mma-issued, 4 epilogue-start, 5 epilogue-end, 6 tile accumulators ready
-#define YNB_TRACE(role, a, b)                                                          \
-  do {                                                                                 \
-    if (p.trace != nullptr && blockIdx.x == 0) {                                       \
-      int _i = atomicAdd(reinterpret_cast<int*>(p.trace), 1);                          \
-      if (_i < p.trace_cap) {                                                          \
-        long long* _e = p.trace + 1 + (long long)_i * 4;                               \
-        _e[0] = (role); _e[1] = (a); _e[2] = (b); _e[3] = clock64();                   \
-      }                                                                                \
-    }                                                                                  \
+// Non-intrusive: every (role, local tile, step) has its own slot — plain stores, no atomics, no
+// round trip in the traced thread (an atomic counter costs ~1000 cycles per event and paces the
+// very loops being observed).  Slots: ((role * 64 + local_tile % 64) * 32 + step % 32) * 4.
+#define YNB_TRACE(role, a, b)                                                                        \
+  do {                                                                                               \
+    if (p.trace != nullptr && blockIdx.x == 0) {                                                     \
+      const int _lt = (int)(((long long)(a) - (long long)blockIdx.x) / (long long)gridDim.x) & 63;   \
+      long long* _e = p.trace + 1 + (long long)((((role) * 64 + _lt) * 32) + ((int)(b) & 31)) * 4;   \
+      _e[0] = (role); _e[1] = (a); _e[2] = (b); _e[3] = clock64();                                   \
+    }                                                                                                \
   } while (0)
 
 struct TcSmemLayout {

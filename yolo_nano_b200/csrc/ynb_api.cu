@@ -1276,7 +1276,7 @@ YNB_EXPORT int ynb_pwconv_tc(const float* in, int32_t in_ld, int32_t in_off, flo
   p.out = out; p.out_ld = out_ld; p.out_off = out_off; p.out_step = out_step; p.omap = dense_map();
   p.bias = b_dev; p.act = act; p.err_flag = d_err;
   long long* d_trace = nullptr;
-  const int trace_cap = 4096;
+  const int trace_cap = 8 * 64 * 32;     // (role, local tile, step) slots, see YNB_TRACE
   const bool want_trace = getenv("YNB_TC_TRACE") != nullptr;
   if (want_trace) {
     UNIT_TRY(cudaMalloc(&d_trace, (1 + 4 * trace_cap) * 8));
@@ -1305,11 +1305,13 @@ YNB_EXPORT int ynb_pwconv_tc(const float* in, int32_t in_ld, int32_t in_off, flo
     if (want_trace && r == cudaSuccess) {
       std::vector<long long> h(1 + 4 * trace_cap);
       cudaMemcpy(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost);
-      int n = (int)std::min<long long>(*reinterpret_cast<int*>(h.data()), trace_cap);
+      int n = 0;
+      for (int i = 0; i < trace_cap; ++i) n += h[4 + 4 * i] != 0;
       fprintf(stderr, "YNB_TC_TRACE stages=%d resident=%d nmain=%d acc_stages=%d steps=%d grid=%u events=%d\n",
               p.num_stages, p.w_resident, p.nmain, p.acc_stages, p.num_steps, L.grid, n);
-      for (int i = 0; i < n; ++i)
-        fprintf(stderr, "TRACE %lld %lld %lld %lld\n", h[1 + 4 * i], h[2 + 4 * i], h[3 + 4 * i], h[4 + 4 * i]);
+      for (int i = 0; i < trace_cap; ++i)
+        if (h[4 + 4 * i] != 0)
+          fprintf(stderr, "TRACE %lld %lld %lld %lld\n", h[1 + 4 * i], h[2 + 4 * i], h[3 + 4 * i], h[4 + 4 * i]);
     }
   }
   if (d_trace) cudaFree(d_trace);
