@@ -286,6 +286,32 @@ def main():
     if sampler:
         sampler.stop_flag.set()
         sampler.join(timeout=3)
+
+    # ---- the same loop through the uint8 entry (Normalize + ToTensor on the device;
+    # images cross PCIe as bytes).  Extra information next to `e2e`, which stays the float32 boundary.
+    gu = torch.Generator().manual_seed(11 + rank)
+    host_u8 = [torch.randint(0, 256, (a.batch, a.size, a.size, 3), dtype=torch.uint8, generator=gu).pin_memory()
+               for _ in range(nbuf)]
+
+    def run_host_u8(steps):
+        for i in range(steps):
+            eng.submit_host_u8(i & 1, host_u8[i % nbuf], out_host2[i & 1])
+            if i > 0:
+                eng.wait_host((i - 1) & 1)
+        eng.wait_host((steps - 1) & 1)
+
+    run_host_u8(3)
+    barrier()
+    t0 = time.perf_counter()
+    run_host_u8(a.steps)
+    torch.cuda.synchronize(dev)
+    wall = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([wall], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    barrier()
+    wall_u8 = float(t[0])
+    run_host(2)      # leave the float32 results in the output buffers read below
     kept = int(out_host2[(a.steps - 1) & 1][3].sum())
     h2d = a.batch * 3 * a.size * a.size * 4
     kmax = int(out_host2[(a.steps - 1) & 1][3].max())
@@ -341,6 +367,10 @@ def main():
                     "d2h_bytes_per_step": d2h, "ms_per_step": wall_e2e / a.steps,
                     "call": "ynb_submit_host / ynb_wait_host, 2 slots (pinned host input, host outputs; "
                             "step i's PCIe copy overlaps step i-1's compute)"},
+            "e2e_u8": {"value": imgs / (wall_u8 * 1e-3), "unit": "images/s",
+                       "h2d_bytes_per_step": a.batch * 3 * a.size * a.size, "ms_per_step": wall_u8 / a.steps,
+                       "call": "ynb_submit_host_u8 / ynb_wait_host: uint8 HWC BGR images, Normalize + ToTensor of "
+                               "data/transforms.py on the device (bit-identical tensor), then the same path"},
             "gpu_launches": launches, "clocks": sampler.summary() if sampler else None,
             "roofline": roofline, "cpu_baseline": cpu,
             "detections_per_image": float(counts.mean())}

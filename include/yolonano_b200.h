@@ -150,6 +150,22 @@ int  ynb_submit_host(ynb_engine* e, int32_t slot, const float* x_host, int32_t b
                      int32_t* out_counts_host, void* stream);
 int  ynb_wait_host(ynb_engine* e, int32_t slot);
 
+/* ---- pre-processing on the device ---------------------------------------
+ * The tail of ValTransforms (data/transforms.py:445-458): Normalize (:59-70: float32(u8) / 255,
+ * - mean, / std, channel-wise in BGR order), ToTensor (:394-398: BGR -> RGB, HWC -> CHW) and the
+ * padding value of Resize (:73-119: mean * 255 outside the letterboxed content).  cv2.resize itself
+ * stays on the host: img is uint8 [B,S,S,3] BGR already resized / letterboxed to S x S; rects
+ * [B][4] = (x0, y0, w, h) of the content inside the canvas (NULL = the whole canvas).  The result is
+ * bit-identical to the reference's tensor (the normalisation is a 3 x 256 table computed with the
+ * reference's float32 sequence).  Inputs cross PCIe as 1 byte per element instead of 4. */
+int  ynb_set_normalization(ynb_engine* e, const float* mean_bgr /*[3]*/, const float* std_bgr /*[3]*/);
+int  ynb_preprocess_u8(ynb_engine* e, const uint8_t* img_dev, const int32_t* rects_dev, int32_t batch,
+                       float* x_dev /*[B,3,S,S]*/, void* stream);
+/* ynb_submit_host with uint8 images: H2D of the bytes + pre-processing + the whole path. */
+int  ynb_submit_host_u8(ynb_engine* e, int32_t slot, const uint8_t* img_host, const int32_t* rects_host,
+                        int32_t batch, float* out_boxes_host, float* out_scores_host,
+                        int32_t* out_cls_host, int32_t* out_counts_host, void* stream);
+
 /* After any ynb_forward_*: copy an internal activation as canonical NCHW float32 into
  * out_dev.  Names: "pool", "c3", "c4", "c5", "p3", "p4", "p5", and every backbone
  * block output "stage2.0" ... "stage4.3".  Per-layer parity hook (SURVEY §8c hazard 1). */

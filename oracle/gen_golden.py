@@ -150,5 +150,47 @@ def main():
         print("g3", tag, out["img0.bboxes"].shape, out["img1.bboxes"].shape)
 
 
+def preprocess_golden():
+    """G4: the reference's ValTransforms (data/transforms.py:445-458) on uint8 BGR images — square
+    (no resize), landscape and portrait (cv2.resize + padding with mean*255).  Stored: the letterboxed
+    uint8 canvas + content rectangle our pre-processing entry takes, and the reference's tensor."""
+    import cv2
+    sys.dont_write_bytecode = True
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from data.transforms import ValTransforms  # type: ignore
+    rng = np.random.default_rng(7)
+    size = 64
+    out = {}
+    for name, (h0, w0) in (("square", (64, 64)), ("landscape", (48, 80)), ("portrait", (90, 50))):
+        img = rng.integers(0, 256, (h0, w0, 3), dtype=np.uint8)
+        tensor, _, _, scale, offset = ValTransforms(size)(img)
+        tensor = tensor.numpy()
+        # what the host side of OUR entry does: the same cv2.resize call, content placed on a canvas
+        canvas = np.zeros((size, size, 3), np.uint8)
+        if h0 > w0:
+            content = cv2.resize(img, (int(w0 / h0 * size), size))
+            left = (size - content.shape[1]) // 2
+            rect = (left, 0, content.shape[1], size)
+        elif h0 < w0:
+            content = cv2.resize(img, (size, int(h0 / w0 * size)))
+            top = (size - content.shape[0]) // 2
+            rect = (0, top, size, content.shape[0])
+        else:
+            content = img if h0 == size else cv2.resize(img, (size, size))
+            rect = (0, 0, size, size)
+        canvas[rect[1]:rect[1] + rect[3], rect[0]:rect[0] + rect[2]] = content
+        assert tensor.shape == (3, size, size), tensor.shape
+        out[f"{name}.canvas"] = canvas
+        out[f"{name}.rect"] = np.array(rect, np.int32)
+        out[f"{name}.tensor"] = tensor.astype(np.float32)
+    np.savez_compressed(OUT / "g4_preprocess64.npz", size=size, numpy=np.__version__, cv2=cv2.__version__, **out)
+    print("g4", {k: v.shape for k, v in out.items() if k.endswith("tensor")})
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "preprocess":
+        preprocess_golden()
+    else:
+        main()
+        preprocess_golden()

@@ -337,3 +337,29 @@ def fold_state_dict(sd: StateDict, table) -> Dict[str, Tuple[torch.Tensor, torch
             b = torch.zeros(w.shape[0])
         out[spec.name] = (w, b)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Pre-processing: the tail of ValTransforms, data/transforms.py:445-458
+VAL_MEAN_BGR = (0.406, 0.456, 0.485)
+VAL_STD_BGR = (0.225, 0.224, 0.229)
+
+
+def preprocess_u8(canvas: np.ndarray, rect=None, mean=VAL_MEAN_BGR, std=VAL_STD_BGR) -> np.ndarray:
+    """uint8 [S,S,3] BGR canvas (content already resized by cv2 on the host) -> float32 [3,S,S] RGB.
+    Resize padding (:84-88,98-102: `np.ones(...) * mean*255`, float64), Normalize (:59-70: astype
+    float32, /= 255., -= mean, /= std), ToTensor (:394-398: BGR->RGB, HWC->CHW)."""
+    mean = np.array(mean, dtype=np.float32)
+    std = np.array(std, dtype=np.float32)
+    image = canvas.astype(np.float32)
+    if rect is not None:
+        x0, y0, w, h = (int(v) for v in rect)
+        padded = np.ones(canvas.shape) * np.array([v * 255 for v in mean])
+        padded[y0:y0 + h, x0:x0 + w, :] = image[y0:y0 + h, x0:x0 + w, :]
+        image = padded
+    image = image.astype(np.float32)
+    image /= 255.
+    image -= mean
+    image /= std
+    image = image[..., (2, 1, 0)]
+    return np.ascontiguousarray(np.transpose(image, (2, 0, 1))).astype(np.float32)

@@ -244,3 +244,50 @@ def test_fused_decode_epilogue_equals_decode_kernel(G, classes, size, monkeypatc
     np.testing.assert_array_equal(bf, bu)
     np.testing.assert_array_equal(sf, su)
     assert (cf != cu).mean() < 1e-4
+
+
+def test_preprocess_u8_bit_exact_and_u8_entry_equals_float_entry(G, golden):
+    """Normalize + ToTensor (+ Resize padding) on the device.  (1) the tensor is
+    bit-identical to the real reference's ValTransforms output (golden g4); (2) the uint8 host entry
+    returns exactly the detections of the float32 host entry fed with that tensor."""
+    g = golden("g4_preprocess64.npz")
+    names = ("square", "landscape", "portrait")
+    sd = W.calibrated(20, seed=3)
+    eng = G.make_engine(sd, 64, 20, "3xtf32")
+    canvas = torch.from_numpy(np.stack([g[f"{n}.canvas"] for n in names]))
+    rects = torch.from_numpy(np.stack([g[f"{n}.rect"] for n in names]).astype(np.int32))
+    x = eng.preprocess_u8(canvas.to(G.DEV), rects.to(G.DEV))
+    ref = np.stack([g[f"{n}.tensor"] for n in names])
+    np.testing.assert_array_equal(x.cpu().numpy(), ref)
+    # whole canvas (no rectangle) == oracle without padding
+    x2 = eng.preprocess_u8(canvas.to(G.DEV))
+    np.testing.assert_array_equal(x2.cpu().numpy(), np.stack([O.preprocess_u8(g[f"{n}.canvas"]) for n in names]))
+    # end to end through the host entries
+    out_f = eng.alloc_outputs(3, pinned_host=True)
+    out_u = eng.alloc_outputs(3, pinned_host=True)
+    eng.submit_host(0, torch.from_numpy(ref).pin_memory(), out_f)
+    eng.wait_host(0)
+    eng.submit_host_u8(1, canvas.pin_memory(), out_u, rects.pin_memory())
+    eng.wait_host(1)
+    assert np.array_equal(out_f[3].numpy(), out_u[3].numpy())
+    for i in range(3):
+        k = int(out_f[3][i])
+        for a, b in zip(out_f[:3], out_u[:3]):
+            np.testing.assert_array_equal(a[i, :k].numpy(), b[i, :k].numpy())
+    eng.close()
+
+
+def test_dropin_detect_images_equals_detect_on_reference_tensor(G, golden):
+    """Drop-in class: detect_images(uint8 canvases) == detect(the reference's ValTransforms tensor)."""
+    import yolo_nano_b200 as pkg
+    g = golden("g4_preprocess64.npz")
+    names = ("square", "landscape", "portrait")
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = pkg.YOLONano(G.DEV, 64, 20, anchor_size=pkg.MULTI_ANCHOR_SIZE)
+    m.load_state_dict(W.calibrated(20, seed=3))
+    m = m.to(G.DEV).eval()
+    ref = m.detect(torch.from_numpy(np.stack([g[f"{n}.tensor"] for n in names])).to(G.DEV))
+    got = m.detect_images(np.stack([g[f"{n}.canvas"] for n in names]), np.stack([g[f"{n}.rect"] for n in names]))
+    for r, q in zip(ref, got):
+        for a, b in zip(r, q):
+            np.testing.assert_array_equal(a, b)

@@ -137,3 +137,13 @@ def test_g3_keepsets(golden):
                 np.testing.assert_array_equal(idx2, g[f"img{i}.keep_idx"])
             else:
                 assert len(np.setxor1d(idx2, g[f"img{i}.keep_idx"])) <= 0.02 * len(idx)
+
+
+def test_preprocess_restatement_matches_reference_valtransforms(golden):
+    """oracle.preprocess_u8 against the real ValTransforms (data/transforms.py:445-458) recorded by
+    oracle/gen_golden.py: square (no resize), landscape and portrait (padding with mean*255)."""
+    g = golden("g4_preprocess64.npz")
+    for name in ("square", "landscape", "portrait"):
+        rect = g[f"{name}.rect"]
+        t = O.preprocess_u8(g[f"{name}.canvas"], None if name == "square" else rect)
+        np.testing.assert_array_equal(t, g[f"{name}.tensor"])

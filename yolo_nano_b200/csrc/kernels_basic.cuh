@@ -176,6 +176,91 @@ inline cudaError_t launch_stem_pool(const float* x, float* out, const StemWeight
 }
 
 // =====================================================================================
+// Pre-processing: the tail of data/transforms.py ValTransforms on the device.
+//   Normalize (:59-70): x = float32(u8); x /= 255; x -= mean[c]; x /= std[c]   (c in BGR order)
+//   ToTensor  (:394-398): BGR -> RGB, HWC -> CHW
+//   Resize    (:73-119): pixels outside the letterboxed content carry the value mean*255
+// in : uint8 [B,S,S,3] BGR, already resized / letterboxed to S x S on the host (cv2.resize stays there)
+// out: float32 [B,3,S,S] RGB — what the stem reads.
+// The normalisation is a pure function of (byte, channel): a 3 x 256 table computed on the host
+// with the reference's exact float32 sequence, so the device result is bit-identical by
+// construction.  4 pixels per thread: three 4-byte loads, three 16-byte stores.
+// =====================================================================================
+struct PreLut {
+  float v[3][256];   // [input channel (B,G,R)][byte]
+  float pad[3];      // normalised padding value per input channel
+};
+
+constexpr int kPreRows = 8;    // image rows per CTA (amortises the table load)
+
+__global__ void __launch_bounds__(128)
+preprocess_u8_kernel(const uint8_t* __restrict__ img, const int32_t* __restrict__ rects, float* __restrict__ out,
+                     const PreLut* __restrict__ lut, int S) {
+  __shared__ float s_lut[3][256];
+  __shared__ float s_pad[3];
+  pdl_trigger();
+  const float* lg = &lut->v[0][0];
+  for (int i = threadIdx.x; i < 768; i += 128) (&s_lut[0][0])[i] = __ldg(lg + i);   // coalesced, L2-resident
+  if (threadIdx.x < 3) s_pad[threadIdx.x] = __ldg(&lut->pad[threadIdx.x]);
+  pdl_wait();
+  __syncthreads();
+  const int x0 = (blockIdx.x * 128 + threadIdx.x) * 4;
+  if (x0 >= S) return;
+  const int b = blockIdx.z;
+  int rx = 0, ry = 0, rw = S, rh = S;
+  if (rects) { rx = rects[4 * b]; ry = rects[4 * b + 1]; rw = rects[4 * b + 2]; rh = rects[4 * b + 3]; }
+#pragma unroll 2
+  for (int y = blockIdx.y * kPreRows; y < min(S, (int)(blockIdx.y + 1) * kPreRows); ++y) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(img + ((size_t)((size_t)b * S + y) * S + x0) * 3);
+    const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+    const bool row_in = y >= ry && y < ry + rh;
+#pragma unroll
+    for (int oc = 0; oc < 3; ++oc) {
+      const int ic = 2 - oc;                            // RGB output plane <- BGR input channel
+      float r[4];
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        const int byte_idx = 3 * px + ic;               // 0..11 inside the three words
+        const uint32_t word = byte_idx < 4 ? w0 : (byte_idx < 8 ? w1 : w2);
+        const uint32_t v = (word >> ((byte_idx & 3) * 8)) & 0xffu;
+        const bool in = row_in && x0 + px >= rx && x0 + px < rx + rw;
+        r[px] = in ? s_lut[ic][v] : s_pad[ic];
+      }
+      *reinterpret_cast<float4*>(out + (((size_t)b * 3 + oc) * S + y) * S + x0) = make_float4(r[0], r[1], r[2], r[3]);
+    }
+  }
+}
+
+inline void make_prelut(PreLut* lut, const float mean_bgr[3], const float std_bgr[3]) {
+  for (int c = 0; c < 3; ++c) {
+    for (int v = 0; v < 256; ++v) {
+      volatile float f = (float)v;      // volatile: every step rounds to float32, as the NumPy in-place ops do
+      f = f / 255.0f;
+      f = f - mean_bgr[c];
+      f = f / std_bgr[c];
+      lut->v[c][v] = f;
+    }
+    volatile float f = mean_bgr[c] * 255.0f;          // Resize.mean = [v * 255 for v in mean] (float32)
+    f = f / 255.0f;
+    f = f - mean_bgr[c];
+    f = f / std_bgr[c];
+    lut->pad[c] = f;
+  }
+}
+
+// lut: DEVICE copy of the table
+inline cudaError_t launch_preprocess_u8(const uint8_t* img, const int32_t* rects, float* out, const PreLut* lut,
+                                        int batch, int S, cudaStream_t st) {
+  if (batch <= 0) return cudaSuccess;
+  if ((S & 3) || (reinterpret_cast<uintptr_t>(img) & 3u) || (reinterpret_cast<uintptr_t>(out) & 15u))
+    return cudaErrorInvalidValue;
+  dim3 grid((unsigned)((S / 4 + 127) / 128), (unsigned)((S + kPreRows - 1) / kPreRows), (unsigned)batch);
+  cudaError_t r = launch_pdl(preprocess_u8_kernel, grid, dim3(128), 0, st, img, rects, out, lut, S);
+  YNB_COUNT_LAUNCH();
+  return r;
+}
+
+// =====================================================================================
 // Depthwise 3x3, pad 1, stride 1|2, + bias (+ activation).  NHWC, 4 channels per thread
 // with 16-byte loads; consecutive threads take consecutive channel groups of one pixel,
 // so a warp reads whole 128-byte lines.  (backbone/shufflenetv2.py:66-67; heads

@@ -96,6 +96,8 @@ struct ynb_engine {
   std::map<std::string, int> index;
   std::vector<PackedConv> convs;
   StemWeights stem_w;                      // folded stem weights, passed as a kernel parameter
+  PreLut prelut;                           // uint8 -> normalised float32 table (ynb_set_normalization)
+  PreLut* d_prelut = nullptr;              // its device copy
   struct StemMap { CUtensorMap tm; int ok; };
   std::map<std::pair<const float*, int>, StemMap> stem_maps;   // TMA maps over caller inputs
   bool committed = false;
@@ -116,6 +118,8 @@ struct ynb_engine {
   struct HostSlot {                    // double-buffered host I/O (ynb_submit_host / ynb_wait_host)
     float* x = nullptr; float* boxes = nullptr; float* scores = nullptr; int32_t* cls = nullptr;
     int32_t* counts = nullptr;
+    uint8_t* img_u8 = nullptr;         // [B,S,S,3] staging for the uint8 entry
+    int32_t* rects = nullptr;          // [B][4]
     cudaEvent_t h2d = nullptr, done = nullptr;
     bool busy = false;
     int batch = 0;
@@ -341,6 +345,8 @@ size_t layout_workspace(ynb_engine* e, int batch, int S, char* base) {
     e->slot[k].scores = (float*)raw((size_t)batch * n * 4);
     e->slot[k].cls = (int32_t*)raw((size_t)batch * n * 4);
     e->slot[k].counts = (int32_t*)raw((size_t)batch * 4);
+    e->slot[k].img_u8 = (uint8_t*)raw((size_t)batch * 3 * S * S);
+    e->slot[k].rects = (int32_t*)raw((size_t)batch * 16);
   }
   e->d_x = e->slot[0].x;
   e->d_out_boxes = e->slot[0].boxes;
@@ -842,6 +848,10 @@ YNB_EXPORT int ynb_create(const ynb_config* cfg, ynb_engine** out) {
   e->cfg = *cfg;
   if (e->cfg.max_batch < 1) e->cfg.max_batch = 1;
   e->S = cfg->input_size;
+  {   // ValTransforms defaults (data/transforms.py:447), BGR order
+    const float mean[3] = {0.406f, 0.456f, 0.485f}, stdv[3] = {0.225f, 0.224f, 0.229f};
+    make_prelut(&e->prelut, mean, stdv);
+  }
   e->table = conv_table(cfg->num_classes, cfg->num_anchors);
   e->convs.resize(e->table.size());
   for (size_t i = 0; i < e->table.size(); ++i) e->index[e->table[i].name] = (int)i;
@@ -851,6 +861,8 @@ YNB_EXPORT int ynb_create(const ynb_config* cfg, ynb_engine** out) {
             cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->d_prelut, sizeof(PreLut)) == cudaSuccess &&
+       cudaMemcpy(e->d_prelut, &e->prelut, sizeof(PreLut), cudaMemcpyHostToDevice) == cudaSuccess;
   for (int k = 0; k < 2 && ok; ++k)
     ok = cudaEventCreateWithFlags(&e->slot[k].h2d, cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&e->slot[k].done, cudaEventDisableTiming) == cudaSuccess &&
@@ -886,6 +898,7 @@ YNB_EXPORT void ynb_destroy(ynb_engine* e) {
   }
   if (e->s_copy) cudaStreamDestroy(e->s_copy);
   if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
+  if (e->d_prelut) cudaFree(e->d_prelut);
   if (e->s_main) cudaStreamDestroy(e->s_main);
   if (e->s_side) cudaStreamDestroy(e->s_side);
   for (PackedConv& pc : e->convs) {
@@ -1090,9 +1103,11 @@ YNB_EXPORT int ynb_forward_detect(ynb_engine* e, const float* x_dev, int32_t bat
 
 // Host-buffer path, split in two so that consecutive steps overlap: submit(i+1) copies the
 // next batch over PCIe on the copy stream while the compute stream is still busy with step i.
-YNB_EXPORT int ynb_submit_host(ynb_engine* e, int32_t slot_id, const float* x_host, int32_t batch, float* ob,
-                               float* os, int32_t* oc, int32_t* on, void* stream) {
-  if (!e || !x_host || !ob || !os || !oc || !on) return fail(e, YNB_ERR_INVALID, "null argument");
+// x_host != nullptr: float32 [B,3,S,S] input; else img_host uint8 [B,S,S,3] BGR (+ optional rects)
+static int submit_host_common(ynb_engine* e, int32_t slot_id, const float* x_host, const uint8_t* img_host,
+                              const int32_t* rects_host, int32_t batch, float* ob, float* os, int32_t* oc,
+                              int32_t* on, void* stream) {
+  if (!e || (!x_host && !img_host) || !ob || !os || !oc || !on) return fail(e, YNB_ERR_INVALID, "null argument");
   if (slot_id < 0 || slot_id > 1) return fail(e, YNB_ERR_INVALID, "slot must be 0 or 1");
   cudaStream_t user = (cudaStream_t)stream;
   CounterScope cs(e);
@@ -1101,18 +1116,60 @@ YNB_EXPORT int ynb_submit_host(ynb_engine* e, int32_t slot_id, const float* x_ho
   if (rc) return rc;
   ynb_engine::HostSlot& sl = e->slot[slot_id];
   if (sl.busy) return fail(e, YNB_ERR_STATE, "slot still in flight: call ynb_wait_host first");
-  const size_t img = (size_t)3 * e->S * e->S * 4;
+  const size_t px = (size_t)3 * e->S * e->S;
   // order after the caller's stream, then: H2D on the copy stream, compute on the main stream
   CUDA_TRY(e, cudaEventRecord(e->ev_in, user));
   CUDA_TRY(e, cudaStreamWaitEvent(e->s_copy, e->ev_in, 0));
-  CUDA_TRY(e, cudaMemcpyAsync(sl.x, x_host, img * batch, cudaMemcpyHostToDevice, e->s_copy));
+  if (x_host) {
+    CUDA_TRY(e, cudaMemcpyAsync(sl.x, x_host, px * 4 * batch, cudaMemcpyHostToDevice, e->s_copy));
+  } else {
+    CUDA_TRY(e, cudaMemcpyAsync(sl.img_u8, img_host, px * batch, cudaMemcpyHostToDevice, e->s_copy));
+    if (rects_host)
+      CUDA_TRY(e, cudaMemcpyAsync(sl.rects, rects_host, (size_t)batch * 16, cudaMemcpyHostToDevice, e->s_copy));
+  }
   CUDA_TRY(e, cudaEventRecord(sl.h2d, e->s_copy));
   CUDA_TRY(e, cudaStreamWaitEvent(e->s_main, sl.h2d, 0));
+  if (!x_host)   // uint8 HWC BGR -> normalised float32 NCHW RGB, 4x fewer bytes over PCIe
+    CUDA_TRY(e, launch_preprocess_u8(sl.img_u8, rects_host ? sl.rects : nullptr, sl.x, e->d_prelut, batch, e->S,
+                                     e->s_main));
   if ((rc = detect_device(e, sl.x, batch, sl.boxes, sl.scores, sl.cls, sl.counts))) return rc;
   CUDA_TRY(e, cudaMemcpyAsync(on, sl.counts, (size_t)batch * 4, cudaMemcpyDeviceToHost, e->s_main));
   CUDA_TRY(e, cudaMemcpyAsync(sl.flag_host, e->d_err, 4, cudaMemcpyDeviceToHost, e->s_main));
   CUDA_TRY(e, cudaEventRecord(sl.done, e->s_main));
   sl.busy = true; sl.batch = batch; sl.ob = ob; sl.os = os; sl.oc = oc; sl.on = on;
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_submit_host(ynb_engine* e, int32_t slot_id, const float* x_host, int32_t batch, float* ob,
+                               float* os, int32_t* oc, int32_t* on, void* stream) {
+  if (!x_host) return fail(e, YNB_ERR_INVALID, "null argument");
+  return submit_host_common(e, slot_id, x_host, nullptr, nullptr, batch, ob, os, oc, on, stream);
+}
+
+YNB_EXPORT int ynb_submit_host_u8(ynb_engine* e, int32_t slot_id, const uint8_t* img_host, const int32_t* rects_host,
+                                  int32_t batch, float* ob, float* os, int32_t* oc, int32_t* on, void* stream) {
+  if (!img_host) return fail(e, YNB_ERR_INVALID, "null argument");
+  return submit_host_common(e, slot_id, nullptr, img_host, rects_host, batch, ob, os, oc, on, stream);
+}
+
+YNB_EXPORT int ynb_set_normalization(ynb_engine* e, const float* mean_bgr, const float* std_bgr) {
+  if (!e || !mean_bgr || !std_bgr) return fail(e, YNB_ERR_INVALID, "null argument");
+  for (int c = 0; c < 3; ++c)
+    if (!(std_bgr[c] > 0.0f)) return fail(e, YNB_ERR_INVALID, "std must be positive");
+  make_prelut(&e->prelut, mean_bgr, std_bgr);
+  CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+  CUDA_TRY(e, cudaDeviceSynchronize());
+  CUDA_TRY(e, cudaMemcpy(e->d_prelut, &e->prelut, sizeof(PreLut), cudaMemcpyHostToDevice));
+  return YNB_OK;
+}
+
+// Parity hook: the pre-processing alone, device buffers.
+YNB_EXPORT int ynb_preprocess_u8(ynb_engine* e, const uint8_t* img_dev, const int32_t* rects_dev, int32_t batch,
+                                 float* x_dev, void* stream) {
+  if (!e || !img_dev || !x_dev || batch <= 0) return fail(e, YNB_ERR_INVALID, "null argument");
+  CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+  cudaError_t r = launch_preprocess_u8(img_dev, rects_dev, x_dev, e->d_prelut, batch, e->S, (cudaStream_t)stream);
+  if (r != cudaSuccess) return fail(e, YNB_ERR_CUDA, std::string("preprocess_u8: ") + cudaGetErrorString(r));
   return YNB_OK;
 }
 

@@ -198,6 +198,37 @@ class Engine:
                                              _ptr(scores), _ptr(cls), _ptr(counts), _stream_ptr(self.device)),
                     "ynb_submit_host")
 
+    def submit_host_u8(self, slot: int, img_host: torch.Tensor, out_host, rects_host: torch.Tensor = None):
+        """submit_host for uint8 images [B,S,S,3] BGR (letterboxed to S x S on the host); `rects_host`
+        int32 [B,4] = (x0, y0, w, h) of the content, None = whole canvas.  Normalize + ToTensor of
+        data/transforms.py run on the device."""
+        if img_host.is_cuda or img_host.dtype != torch.uint8 or img_host.dim() != 4 or img_host.shape[-1] != 3 \
+                or not img_host.is_contiguous():
+            raise EngineError("submit_host_u8 wants a contiguous uint8 host tensor [B,S,S,3]")
+        if rects_host is not None and (rects_host.dtype != torch.int32 or tuple(rects_host.shape) != (img_host.shape[0], 4)
+                                       or not rects_host.is_contiguous() or rects_host.is_cuda):
+            raise EngineError("rects_host must be a contiguous int32 host tensor [B,4]")
+        boxes, scores, cls, counts = out_host
+        self._check(self.lib.ynb_submit_host_u8(self._h, int(slot), _ptr(img_host),
+                                                _ptr(rects_host) if rects_host is not None else None,
+                                                img_host.shape[0], _ptr(boxes), _ptr(scores), _ptr(cls), _ptr(counts),
+                                                _stream_ptr(self.device)), "ynb_submit_host_u8")
+
+    def preprocess_u8(self, img: torch.Tensor, rects: torch.Tensor = None) -> torch.Tensor:
+        """uint8 [B,S,S,3] BGR device tensor -> the float32 [B,3,S,S] RGB tensor of ValTransforms."""
+        if not img.is_cuda or img.dtype != torch.uint8 or img.dim() != 4 or not img.is_contiguous():
+            raise EngineError("preprocess_u8 wants a contiguous uint8 CUDA tensor [B,S,S,3]")
+        b, s = img.shape[0], img.shape[1]
+        x = torch.empty((b, 3, s, s), dtype=torch.float32, device=img.device)
+        self._check(self.lib.ynb_preprocess_u8(self._h, _ptr(img), _ptr(rects) if rects is not None else None, b,
+                                               _ptr(x), _stream_ptr(self.device)), "ynb_preprocess_u8")
+        return x
+
+    def set_normalization(self, mean_bgr, std_bgr):
+        m = (C.c_float * 3)(*[float(v) for v in mean_bgr])
+        sd = (C.c_float * 3)(*[float(v) for v in std_bgr])
+        self._check(self.lib.ynb_set_normalization(self._h, m, sd), "ynb_set_normalization")
+
     def wait_host(self, slot: int):
         self._check(self.lib.ynb_wait_host(self._h, int(slot)), "ynb_wait_host")
 

@@ -291,6 +291,30 @@ class YOLONano(nn.Module):
                         cls[b, :k].cpu().numpy().astype(np.int64)))
         return res
 
+    def detect_images(self, canvases, rects=None) -> List[Tuple[np.ndarray, np.ndarray, np.ndarray]]:
+        """`detect` for uint8 BGR images [B,S,S,3] already resized / letterboxed to the grid size on the
+        host (`rects` int32 [B,4] = x0, y0, w, h of the content; None = whole canvas): Normalize +
+        ToTensor of the reference's ValTransforms (data/transforms.py:445-458) run on the device and
+        the images cross PCIe as bytes.  Same results as `detect(ValTransforms(...)(img))`."""
+        canvases = torch.as_tensor(canvases)
+        if canvases.dtype != torch.uint8 or canvases.dim() != 4 or canvases.shape[-1] != 3:
+            raise ValueError("detect_images wants uint8 [B,S,S,3]")
+        b = canvases.shape[0]
+        eng = self.engine(b)
+        if rects is not None:
+            rects = torch.as_tensor(rects, dtype=torch.int32).contiguous()
+        out = eng.alloc_outputs(b, pinned_host=True)
+        eng.submit_host_u8(0, canvases.contiguous(), out, rects)
+        eng.wait_host(0)
+        boxes, scores, cls, counts = out
+        res = []
+        for i in range(b):
+            k = int(counts[i])
+            res.append((np.array(boxes[i, :k].numpy(), dtype=np.float32, copy=True),
+                        np.array(scores[i, :k].numpy(), dtype=np.float32, copy=True),
+                        cls[i, :k].numpy().astype(np.int64)))
+        return res
+
     def forward(self, x, target=None):
         if self.trainable:
             raise NotImplementedError(
