@@ -371,14 +371,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // right after it has been stored.
       const int64_t m_base = tile * kTcBM + q * 32;            // first row of this warp (pointwise)
       float xa[16], xb[16];
+      // one 64-bit address per call, 32-bit row offsets after that (the math was 22 % of the kernel's
+      // instructions when every row recomputed m * ld in 64 bits)
+      const int rows_left = (int)min((int64_t)32, p.M - m_base);   // valid rows of this warp's 32 (<= 0: none)
       auto fetch_x1 = [&](int c0, int r0, float (&x)[16]) {
         const int i = c0 + lane;
         const bool col_ok = kPass && i < p.N;
+        const float* src = p.pass + (m_base + r0) * (int64_t)p.pass_ld + i;
+        const int nr = col_ok ? rows_left - r0 : 0;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          const int64_t mr = m_base + r0 + r;
-          x[r] = (col_ok && mr < p.M) ? __ldg(p.pass + mr * p.pass_ld + i) : 0.0f;
-        }
+        for (int r = 0; r < 16; ++r) x[r] = r < nr ? __ldg(src + r * p.pass_ld) : 0.0f;
       };
       if (kPass) {
         fetch_x1(0, 0, xa);
