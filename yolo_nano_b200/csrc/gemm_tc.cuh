@@ -59,6 +59,9 @@ struct TcGemmParams {
   int nmain;              // main accumulators (round-robin over K steps), 1..4
   int nacc;               // accumulators per stage = nmain + (parity mode ? 1 correction : 0)
   int merge_corr;         // parity mode, shallow K: corrections go into the single main accumulator (nacc = 1)
+  int stack_b;            // parity mode, nmain = 1, 2*Npad <= 256: a_hi x [b_hi; b_lo] as ONE MMA of N = 2*Npad
+                          // into [main | corr] (the planes are adjacent in smem and in TMEM): 2 MMAs per
+                          // K-step instead of 3, a_hi and b_hi are fetched once less
   int acc_stages;         // TMEM accumulator stages (2 = epilogue overlaps the next tile's MMAs)
   uint32_t tmem_cols;     // power of two >= acc_stages * nacc * Npad
   uint32_t a_box_bytes;   // bytes one A TMA box delivers
@@ -256,6 +259,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = ptx::make_idesc(2 /*tf32*/, kTcBM, p.Npad);
+      const uint32_t idesc2 = ptx::make_idesc(2, kTcBM, 2 * p.Npad);
       int s = 0;
       uint32_t ph = 0;
       int acc = 0;
@@ -284,6 +288,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t da = ptx::make_sw128_kmajor_desc(a_hi + ko);
             const uint64_t db = ptx::make_sw128_kmajor_desc(b_hi + ko);
             const int slot = t % p.nmain;
+            if (p.stack_b) {
+              // [main | corr] (+)= a_hi x [b_hi; b_lo]   then   corr += a_lo x b_hi
+              ptx::mma_tf32_ss(d_tmem, da, db, idesc2, t != 0);
+              ptx::mma_tf32_ss(c_tmem, ptx::make_sw128_kmajor_desc(a_lo + ko), db, idesc, 1);
+              continue;
+            }
             if (split) {
               ptx::mma_tf32_ss(c_tmem, ptx::make_sw128_kmajor_desc(a_lo + ko), db, idesc, t != 0);
               ptx::mma_tf32_ss(c_tmem, da, ptx::make_sw128_kmajor_desc(b_lo + ko), idesc, 1);
@@ -708,6 +718,7 @@ inline void tc_plan_tmem(TcGemmParams& p, bool allow_merge = false) {
     // <= 16 K steps (48 accumulations): the one-sided truncation of a single accumulator stays
     // below 3e-6 relative — buys two accumulator stages for N = 256 (fused decode heads)
     p.merge_corr = 1;
+    p.stack_b = 0;
     p.nmain = 1; p.nacc = 1; p.acc_stages = 2;
     p.tmem_cols = 32;
     while ((int)p.tmem_cols < 2 * p.Npad) p.tmem_cols <<= 1;
@@ -730,6 +741,8 @@ inline void tc_plan_tmem(TcGemmParams& p, bool allow_merge = false) {
   }
   p.tmem_cols = 32;
   while ((int)p.tmem_cols < p.acc_stages * p.nacc * p.Npad) p.tmem_cols <<= 1;
+  static const bool no_stack = getenv("YNB_TC_NO_STACK") != nullptr;
+  p.stack_b = (split && !no_stack && p.nmain == 1 && p.nacc == 2 && 2 * p.Npad <= 256 && (2 * p.Npad) % 16 == 0) ? 1 : 0;
 }
 
 // Picks stages / residency for the smem budget.  Returns false if nothing fits.
