@@ -59,6 +59,8 @@ struct TcGemmParams {
   int nmain;              // main accumulators (round-robin over K steps), 1..4
   int nacc;               // accumulators per stage = nmain + (parity mode ? 1 correction : 0)
   int merge_corr;         // parity mode, shallow K: corrections go into the single main accumulator (nacc = 1)
+  int presplit;           // parity mode, 3x3: A arrives as two planes (hi, lo) written by the producer kernel —
+                          // two TMA boxes per step, no splitter pass (tmAlo)
   int stack_b;            // parity mode, nmain = 1, 2*Npad <= 256: a_hi x [b_hi; b_lo] as ONE MMA of N = 2*Npad
                           // into [main | corr] (the planes are adjacent in smem and in TMEM): 2 MMAs per
                           // K-step instead of 3, a_hi and b_hi are fetched once less
@@ -142,9 +144,9 @@ __host__ __device__ __forceinline__ uint32_t rn_tf32_bits(uint32_t u) { return (
 
 template <bool kPass, int kDecC>
 __global__ void __launch_bounds__(kTcThreads, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWhi,
-               const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmOut,
-               const TcGemmParams p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+               const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
+               const __grid_constant__ CUtensorMap tmOut, const TcGemmParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   // 1024-byte alignment (128-byte swizzle atoms) by OFFSET arithmetic on the __shared__ array,
   // so that every access below stays in the shared address space (LDS / STS, not generic)
@@ -171,6 +173,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == kTcProducerWarp && lane == 0) {
     ptx::prefetch_tmap(&tmA);
+    if (p.presplit) ptx::prefetch_tmap(&tmAlo);
     ptx::prefetch_tmap(&tmWhi);
     if (split) ptx::prefetch_tmap(&tmWlo);
     if (p.tma_store) ptx::prefetch_tmap(&tmOut);
@@ -207,7 +210,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto w_lo_ptr = [&](int s, int step) { return w_hi_ptr(s, step) + w_chunk_bytes; };
 
   const int acc_cols = p.Npad * p.nacc;   // TMEM columns per accumulator stage
-  const uint32_t step_tx = p.a_box_bytes + (p.w_resident ? 0 : w_chunk_bytes * (split ? 2 : 1));
+  const uint32_t step_tx = p.a_box_bytes * (p.presplit ? 2 : 1) + (p.w_resident ? 0 : w_chunk_bytes * (split ? 2 : 1));
+  const bool splitters_on = split && !p.presplit;
 
   // Weights do not depend on the previous kernel: the resident W planes are requested before
   // the programmatic-dependency wait, i.e. while the predecessor is still draining.
@@ -243,6 +247,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int tap = st / p.chunks_per_tap, kc = st - tap * p.chunks_per_tap;
             int dy = tap / 3, dx = tap - dy * 3;
             ptx::tma_load_4d(stage_a(s), &tmA, &full[s], kc * kTcBK, x0 + dx - 1, y0 + dy - 1, b);
+            if (p.presplit) ptx::tma_load_4d(stage_alo(s), &tmAlo, &full[s], kc * kTcBK, x0 + dx - 1, y0 + dy - 1, b);
           } else {
             ptx::tma_load_2d(stage_a(s), &tmA, &full[s], st * kTcBK, (int)(tile * kTcBM));
           }
@@ -275,7 +280,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t c_tmem = p.merge_corr ? d_tmem : d_tmem + (uint32_t)(p.nmain * p.Npad);
         int t = 0;                                                       // K-step counter of the tile
         for (int st = 0; st < p.num_steps; ++st) {
-          ok = ptx::mbar_wait(split ? &ready[s] : &full[s], ph, p.err_flag, 4);
+          ok = ptx::mbar_wait(splitters_on ? &ready[s] : &full[s], ph, p.err_flag, 4);
           if (!ok) break;
           ptx::tc_fence_after_sync();
           const uint32_t a_hi = ptx::smem_u32(stage_a(s));
@@ -311,7 +316,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= kTcSplitWarp0 && warp < kTcSplitWarp0 + 4) {
     // ================= splitters (fp32 parity mode) =================
-    if (split) {
+    if (splitters_on) {
       const int t = threadIdx.x - kTcSplitWarp0 * 32;  // 0..127
       int s = 0;
       uint32_t ph = 0;
@@ -700,6 +705,7 @@ struct TcGemmLaunch {
   CUtensorMap tmA;
   CUtensorMap tmOut;      // valid when p.tma_store
   const TcWeights* w = nullptr;
+  CUtensorMap tmAlo;      // lo plane of A (presplit)
   TcGemmParams p;
   uint32_t smem = 0;
   unsigned grid = 0;
@@ -729,6 +735,13 @@ inline void tc_plan_tmem(TcGemmParams& p, bool allow_merge = false) {
   if (split) {
     const int ksteps = p.num_steps * (kTcBK / 8);
     want = ksteps >= 64 ? 4 : (ksteps >= 24 ? 3 : (ksteps >= 12 ? 2 : 1));
+    // Measured (B200, calibrated weights, 128^2 and 416^2): with the round-to-nearest split and the
+    // corrections in their own accumulator, ONE main accumulator gives the same end-to-end error as
+    // four (box error 0.024 vs 0.025 px, identical keep sets) — and it lets the hi/lo weight planes be
+    // stacked into one MMA and the 3x3 convs double-buffer their accumulators: 3x3 convs 2x faster.
+    // YNB_TC_NMAIN_MAX=4 restores the round-robin main accumulators for comparison.
+    static const int nmain_cap = getenv("YNB_TC_NMAIN_MAX") ? atoi(getenv("YNB_TC_NMAIN_MAX")) : 1;
+    if (want > nmain_cap) want = nmain_cap;
   }
   p.nmain = want;
   while (p.nmain > 1 && (p.nmain + corr) * p.Npad > 512) p.nmain--;
@@ -766,7 +779,7 @@ inline bool tc_plan_smem(TcGemmLaunch& L) {
 }
 
 inline cudaError_t launch_tc_gemm(const TcGemmLaunch& L, cudaStream_t st) {
-  using KernelT = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcGemmParams);
+  using KernelT = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcGemmParams);
   static const KernelT kernels[4] = {tc_gemm_kernel<false, 0>, tc_gemm_kernel<true, 0>, tc_gemm_kernel<false, 80>,
                                      tc_gemm_kernel<false, 20>};
   static bool attr_set = false;
@@ -779,7 +792,8 @@ inline cudaError_t launch_tc_gemm(const TcGemmLaunch& L, cudaStream_t st) {
   }
   const CUtensorMap& tmo = L.p.tma_store ? L.tmOut : L.tmA;   // unused unless tma_store
   KernelT kern = L.dec_classes == 80 ? kernels[2] : (L.dec_classes == 20 ? kernels[3] : kernels[L.p.pass != nullptr ? 1 : 0]);
-  cudaError_t r = launch_pdl(kern, dim3(L.grid), dim3(kTcThreads), (size_t)L.smem, st, L.tmA, L.w->tm_hi,
+  const CUtensorMap& tmalo = L.p.presplit ? L.tmAlo : L.tmA;   // unused unless presplit
+  cudaError_t r = launch_pdl(kern, dim3(L.grid), dim3(kTcThreads), (size_t)L.smem, st, L.tmA, tmalo, L.w->tm_hi,
                              L.w->tm_lo, tmo, L.p);
   YNB_COUNT_LAUNCH();
   return r;

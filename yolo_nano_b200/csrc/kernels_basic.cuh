@@ -416,9 +416,13 @@ inline cudaError_t launch_nhwc_to_nchw(const float* in, int in_ld, ChanMap imap,
 // F.interpolate default mode 'nearest': up x2 replicates pixels, x0.5 takes [::2, ::2]).
 // mode 1: a2 is (H/2 x W/2), mode 2: a2 is (2H x 2W).  All tensors share `ld` = 96.
 // =====================================================================================
+__device__ __forceinline__ float tf32_rn(float x) {     // same bits as rn_tf32_bits() of gemm_tc.cuh
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
 __global__ void __launch_bounds__(256)
 resample_add_kernel(const float* __restrict__ a, const float* __restrict__ a2, float* __restrict__ out,
-                    int batch, int H, int W, int ld, int mode) {
+                    float* __restrict__ out_lo, int batch, int H, int W, int ld, int mode) {
   const int groups = ld >> 2;
   const int64_t total = (int64_t)batch * H * W * groups;
   const int H2 = mode == 1 ? H >> 1 : H << 1, W2 = mode == 1 ? W >> 1 : W << 1;
@@ -435,18 +439,30 @@ resample_add_kernel(const float* __restrict__ a, const float* __restrict__ a2, f
     float4 u = __ldg(reinterpret_cast<const float4*>(a + p * ld) + g);
     float4 v = __ldg(reinterpret_cast<const float4*>(a2 + (((size_t)b * H2 + y2) * W2 + x2) * ld) + g);
     u.x += v.x; u.y += v.y; u.z += v.z; u.w += v.w;
-    reinterpret_cast<float4*>(out + p * ld)[g] = u;
+    if (out_lo != nullptr) {
+      // The sum feeds a 3x3 conv on the tensor cores in fp32-parity mode: every element would be
+      // split into exact-tf32 hi + lo nine times (once per tap) inside the GEMM.  Split it ONCE here
+      // (round to nearest, as the GEMM's splitters do) and let the GEMM load both planes.
+      float4 h, l;
+      h.x = tf32_rn(u.x); h.y = tf32_rn(u.y); h.z = tf32_rn(u.z); h.w = tf32_rn(u.w);
+      l.x = tf32_rn(u.x - h.x); l.y = tf32_rn(u.y - h.y); l.z = tf32_rn(u.z - h.z); l.w = tf32_rn(u.w - h.w);
+      reinterpret_cast<float4*>(out + p * ld)[g] = h;
+      reinterpret_cast<float4*>(out_lo + p * ld)[g] = l;
+    } else {
+      reinterpret_cast<float4*>(out + p * ld)[g] = u;
+    }
   }
 }
 
-inline cudaError_t launch_resample_add(const float* a, const float* a2, float* out, int batch, int H, int W,
-                                       int ld, int mode, cudaStream_t st) {
+inline cudaError_t launch_resample_add(const float* a, const float* a2, float* out, float* out_lo, int batch, int H,
+                                       int W, int ld, int mode, cudaStream_t st) {
   int64_t total = (int64_t)batch * H * W * (ld / 4);
   int64_t blocks = (total + 255) / 256;
   int64_t cap = (int64_t)kNumSMs * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  cudaError_t r = launch_pdl(resample_add_kernel, dim3((unsigned)blocks), dim3(256), 0, st, a, a2, out, batch, H, W, ld, mode);
+  cudaError_t r = launch_pdl(resample_add_kernel, dim3((unsigned)blocks), dim3(256), 0, st, a, a2, out, out_lo, batch, H, W, ld,
+                             mode);
   YNB_COUNT_LAUNCH();
   return r;
 }

@@ -315,10 +315,10 @@ size_t layout_workspace(ynb_engine* e, int batch, int S, char* base) {
   const int H3 = S / 8, H4 = S / 16, H5 = S / 32;
   const int hs[3] = {H3, H4, H5};
   for (int l = 0; l < 3; ++l) tensor("lat" + std::to_string(l + 3), 96, 96, hs[l]);
-  tensor("sum4", 96, 96, H4); tensor("fpn4", 96, 96, H4);
-  tensor("sum3", 96, 96, H3); tensor("p3", 96, 96, H3);
-  tensor("sum4b", 96, 96, H4); tensor("p4", 96, 96, H4);
-  tensor("sum5", 96, 96, H5); tensor("p5", 96, 96, H5);
+  tensor("sum4", 96, 96, H4); tensor("sum4.lo", 96, 96, H4); tensor("fpn4", 96, 96, H4);
+  tensor("sum3", 96, 96, H3); tensor("sum3.lo", 96, 96, H3); tensor("p3", 96, 96, H3);
+  tensor("sum4b", 96, 96, H4); tensor("sum4b.lo", 96, 96, H4); tensor("p4", 96, 96, H4);
+  tensor("sum5", 96, 96, H5); tensor("sum5.lo", 96, 96, H5); tensor("p5", 96, 96, H5);
   const int ch = e->cfg.num_anchors * (1 + e->cfg.num_classes + 4);
   const char* pn[3] = {"pred_s", "pred_m", "pred_l"};
   for (int l = 0; l < 3; ++l) {
@@ -486,7 +486,7 @@ struct Planner {
 
   // dense 3x3 (smooth): out = act(conv3x3(a + resample(a2)))
   void conv3(const std::string& name, const Tensor& a, const Tensor* a2, int a2_mode, const Tensor& sum,
-             const Tensor& out) {
+             const Tensor& sum_lo, const Tensor& out) {
     const PackedConv& pc = conv(name);
     const ConvSpec& c = spec(name);
     int64_t M = (int64_t)B * a.H * a.W;
@@ -507,12 +507,16 @@ struct Planner {
     }
     // tensor-core path: materialise the sum once (HBM-bound elementwise), then 9 shifted TMA boxes
     Tensor src = a;
+    static const bool no_presplit = getenv("YNB_TC_NO_PRESPLIT") != nullptr;
+    // fp32-parity mode: the merge kernel writes the sum as exact-tf32 hi + lo planes once, instead of the
+    // GEMM splitting every element nine times (once per tap)
+    const bool presplit = a2 != nullptr && e->cfg.gemm_mode == YNB_GEMM_TC_3XTF32 && !no_presplit;
     if (a2) {
-      Tensor a_ = a, a2_ = *a2, s_ = sum;
+      Tensor a_ = a, a2_ = *a2, s_ = sum, sl_ = sum_lo;
       int B_ = B;
-      plan->net.push_back({name + "+merge", "resample_add", 8.0 * M * c.cin + a2bytes, 1.0 * M * c.cin,
-                           [=](cudaStream_t st) {
-        return launch_resample_add(a_.p, a2_.p, s_.p, B_, a_.H, a_.W, a_.ld, a2_mode, st);
+      plan->net.push_back({name + "+merge", "resample_add", (presplit ? 12.0 : 8.0) * M * c.cin + a2bytes,
+                           1.0 * M * c.cin, [=](cudaStream_t st) {
+        return launch_resample_add(a_.p, a2_.p, s_.p, presplit ? sl_.p : nullptr, B_, a_.H, a_.W, a_.ld, a2_mode, st);
       }});
       src = sum;
     }
@@ -537,10 +541,12 @@ struct Planner {
     p.out = out.p; p.out_ld = out.ld; p.out_off = 0; p.out_step = 1; p.omap = dense_map();
     p.bias = pc.b_dev; p.act = c.act;
     p.err_flag = e->d_err;
-    if (!make_tmap_nhwc(&L.tmA, src.p, c.cin, src.W, src.H, B, src.ld, p.TW, p.TH)) {
+    if (!make_tmap_nhwc(&L.tmA, src.p, c.cin, src.W, src.H, B, src.ld, p.TW, p.TH) ||
+        (presplit && !make_tmap_nhwc(&L.tmAlo, sum_lo.p, c.cin, src.W, src.H, B, src.ld, p.TW, p.TH))) {
       error = "cuTensorMapEncodeTiled failed for input of " + name;
       return;
     }
+    p.presplit = presplit ? 1 : 0;
     if (!tc_plan_smem(L)) { error = "no smem configuration for " + name; return; }
     L.grid = (unsigned)std::min<int64_t>(p.num_tiles, kNumSMs);
     const TcGemmLaunch* Lp = &L;
@@ -618,10 +624,10 @@ int build_plan(ynb_engine* e, int B, Plan** out) {
   P.pw("conv1x1_1.convs.0", c4, 0, lat4, 0, 1);
   P.pw("conv1x1_2.convs.0", c5, 0, lat5, 0, 1);
   Tensor fpn4 = P.T("fpn4"), p3 = P.T("p3"), p4 = P.T("p4"), p5 = P.T("p5");
-  P.conv3("smooth_0.convs.0", lat4, &lat5, 1, P.T("sum4"), fpn4);
-  P.conv3("smooth_1.convs.0", lat3, &fpn4, 1, P.T("sum3"), p3);
-  P.conv3("smooth_2.convs.0", fpn4, &p3, 2, P.T("sum4b"), p4);
-  P.conv3("smooth_3.convs.0", lat5, &p4, 2, P.T("sum5"), p5);
+  P.conv3("smooth_0.convs.0", lat4, &lat5, 1, P.T("sum4"), P.T("sum4.lo"), fpn4);
+  P.conv3("smooth_1.convs.0", lat3, &fpn4, 1, P.T("sum3"), P.T("sum3.lo"), p3);
+  P.conv3("smooth_2.convs.0", fpn4, &p3, 2, P.T("sum4b"), P.T("sum4b.lo"), p4);
+  P.conv3("smooth_3.convs.0", lat5, &p4, 2, P.T("sum5"), P.T("sum5.lo"), p5);
   // ---- heads (models/yolo_nano.py:50-70, 299-301)
   Tensor feats[3] = {p3, p4, p5};
   Tensor head_in[3];
