@@ -720,7 +720,8 @@ struct TcGemmLaunch {
 inline void tc_plan_tmem(TcGemmParams& p, bool allow_merge = false) {
   const bool split = p.mode == YNB_GEMM_TC_3XTF32;
   p.merge_corr = 0;
-  if (split && allow_merge && p.num_steps * (kTcBK / 8) <= 16 && 2 * p.Npad <= 512) {
+  static const bool merge_all = getenv("YNB_TC_MERGE_ALL") != nullptr;     // experiment: one accumulator everywhere
+  if (split && ((allow_merge && p.num_steps * (kTcBK / 8) <= 16) || merge_all) && 2 * p.Npad <= 512) {
     // <= 16 K steps (48 accumulations): the one-sided truncation of a single accumulator stays
     // below 3e-6 relative — buys two accumulator stages for N = 256 (fused decode heads)
     p.merge_corr = 1;

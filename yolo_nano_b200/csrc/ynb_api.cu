@@ -137,6 +137,7 @@ struct ynb_engine {
 
   std::map<int, std::unique_ptr<Plan>> plans;
   std::deque<std::deque<TcGemmLaunch>> tc_store;
+  std::deque<CUtensorMap> dw_maps;         // input maps of the depthwise launches (stable addresses)
 
   // execution resources: all engine work runs on the engine's own streams, ordered against
   // the caller's stream with events (stream capture is not allowed on the legacy stream)
@@ -362,7 +363,7 @@ int ensure_workspace(ynb_engine* e, int batch) {
   int nb = std::max(batch, std::max(e->ws_batch, (int)e->cfg.max_batch));
   CUDA_TRY(e, cudaDeviceSynchronize());
   e->plans.clear();
-  e->tc_store.clear();
+  e->tc_store.clear(); e->dw_maps.clear();
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
   e->graphs.clear();
   e->graph_seen.clear();
@@ -398,8 +399,18 @@ struct Planner {
     int B_ = B, c4 = pc.n, stride = c.stride, act = c.act;
     const float *w = pc.w_dev, *b = pc.b_dev;
     double px_in = (double)B * in.H * in.W, px_out = (double)B * out.H * out.W;
-    plan->net.push_back({name, "dwconv3x3", 4.0 * c.cin * (px_in + px_out) + 40.0 * c.cin, 18.0 * c.cin * px_out,
-                         [=](cudaStream_t st) {
+    const double bytes = 4.0 * c.cin * (px_in + px_out) + 40.0 * c.cin, flops = 18.0 * c.cin * px_out;
+    // product path: halo tiles through TMA; register-tiled global loads if the view is not 16-byte aligned
+    static const bool no_tma = getenv("YNB_DW_NO_TMA") != nullptr;
+    e->dw_maps.emplace_back();
+    CUtensorMap* tm = &e->dw_maps.back();
+    if (!no_tma && make_tmap_dw(tm, in.p, in.ld, in_off, B, in.H, in.W, c4, stride)) {
+      plan->net.push_back({name, "dwconv3x3", bytes, flops, [=](cudaStream_t st) {
+        return launch_dwconv3x3_tma(*tm, out.p, out.ld, 0, w, b, B_, in.H, in.W, c4, stride, act, st);
+      }});
+      return;
+    }
+    plan->net.push_back({name, "dwconv3x3", bytes, flops, [=](cudaStream_t st) {
       return launch_dwconv3x3(in.p, in.ld, in_off, out.p, out.ld, 0, w, b, B_, in.H, in.W, c4, stride, act, st);
     }});
   }
@@ -936,7 +947,7 @@ YNB_EXPORT int ynb_set_gemm_mode(ynb_engine* e, int32_t mode) {
   if (mode < 0 || mode > YNB_GEMM_TC_TF32) return fail(e, YNB_ERR_INVALID, "bad gemm_mode");
   if (mode != e->cfg.gemm_mode) {
     cudaDeviceSynchronize();
-    e->cfg.gemm_mode = mode; e->plans.clear(); e->tc_store.clear(); drop_graphs(e);
+    e->cfg.gemm_mode = mode; e->plans.clear(); e->tc_store.clear(); e->dw_maps.clear(); drop_graphs(e);
   }
   return YNB_OK;
 }
@@ -991,7 +1002,7 @@ YNB_EXPORT int ynb_commit_weights(ynb_engine* e) {
     if (!e->convs[i].loaded) return fail(e, YNB_ERR_STATE, "conv not loaded: " + e->table[i].name);
   CUDA_TRY(e, cudaDeviceSynchronize());   // nothing in flight may still read the old buffers
   e->plans.clear();
-  e->tc_store.clear();
+  e->tc_store.clear(); e->dw_maps.clear();
   drop_graphs(e);
   for (size_t i = 0; i < e->convs.size(); ++i) {
     int rc = pack_conv(e, (int)i);
@@ -1286,6 +1297,12 @@ YNB_EXPORT int ynb_dwconv3x3(const float* in, int32_t in_ld, int32_t in_off, flo
   if (!in || !out || !w || !b || channels % 4 || in_ld % 4 || in_off % 4 || out_ld % 4 || out_off % 4 ||
       out_step != 1 || (stride != 1 && stride != 2))
     return fail(nullptr, YNB_ERR_INVALID, "ynb_dwconv3x3: channels/ld/off must be multiples of 4, out_step 1");
+  CUtensorMap tm;
+  if (!getenv("YNB_DW_NO_TMA") && make_tmap_dw(&tm, in, in_ld, in_off, batch, h_in, w_in, channels, stride)) {
+    UNIT_TRY(launch_dwconv3x3_tma(tm, out, out_ld, out_off, w, b, batch, h_in, w_in, channels, stride, act,
+                                  (cudaStream_t)stream));
+    return YNB_OK;
+  }
   UNIT_TRY(launch_dwconv3x3(in, in_ld, in_off, out, out_ld, out_off, w, b, batch, h_in, w_in, channels, stride, act,
                             (cudaStream_t)stream));
   return YNB_OK;
