@@ -127,6 +127,8 @@ def load_traffic(kernel_substr: str):
     for d in rows:
         if kernel_substr not in d["Kernel Name"] or not d["Metric Name"].startswith("dram__bytes"):
             continue
+        if kernel_substr == "tc_gemm_kernel" and ("80>" in d["Kernel Name"] or "20>" in d["Kernel Name"]):
+            continue        # the fused decode variants are their own family (pw_decode_tcgen05)
         v = float(d["Metric Value"].replace(",", ""))
         v *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(d["Metric Unit"], 1)
         per_launch[d["ID"]] = per_launch.get(d["ID"], 0.0) + v
