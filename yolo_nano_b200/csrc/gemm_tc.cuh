@@ -429,11 +429,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int am[A];
 #pragma unroll
         for (int a = 0; a < A; ++a) { mx[a] = -INFINITY; sum[a] = 0.0f; am[a] = 0; objl[a] = 0.0f; }
-        // pass 1: objectness / box logits, class max + first argmax (channel map of :312-318)
-#pragma unroll
-        for (int blk = 0; blk < NBLK; ++blk) {
-          float v[16];
-          raw16(blk * 16, v);
+        // what each pass does with 16 raw columns
+        auto pass1 = [&](int blk, const float (&v)[16]) {     // objectness / box logits, class max + first arg-max
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int col = blk * 16 + j;            // compile-time after unrolling
@@ -446,17 +443,60 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tb[col - A - A * C] = v[j];
             }
           }
-        }
-        // pass 2: softmax denominators (TMEM is re-read: cheaper than holding 3*C logits)
-#pragma unroll
-        for (int blk = 0; blk < NBLK; ++blk) {
-          if (blk * 16 + 15 < A || blk * 16 >= A + A * C) continue;
-          float v[16];
-          raw16(blk * 16, v);
+        };
+        auto pass2 = [&](int blk, const float (&v)[16]) {     // softmax denominators
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int col = blk * 16 + j;
             if (col >= A && col < A + A * C) sum[(col - A) / C] += softmax_exp(v[j] - mx[(col - A) / C]);
+          }
+        };
+        constexpr int P2_FIRST = 0, P2_LAST = (A + A * C - 1) / 16;     // blocks that hold class logits
+        if (p.nacc == 1) {
+          // One accumulator (the head convs): software-pipelined TMEM reads — block k+1 is in flight
+          // while block k is processed, so the ~32 tcgen05.ld latencies per tile overlap the math.
+          uint32_t ra[16], rb[16];
+          float v[16];
+          ptx::tmem_ld_32x16(t_base, ra);
+#pragma unroll
+          for (int blk = 0; blk < NBLK; ++blk) {
+            ptx::tmem_ld_wait();
+            if (blk + 1 < NBLK) {
+              if (blk & 1) ptx::tmem_ld_32x16(t_base + (blk + 1) * 16, ra);
+              else ptx::tmem_ld_32x16(t_base + (blk + 1) * 16, rb);
+            } else {
+              ptx::tmem_ld_32x16(t_base + P2_FIRST * 16, (blk & 1) ? ra : rb);     // first block of pass 2
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float((blk & 1) ? rb[j] : ra[j]) + s_bias[blk * 16 + j];
+            pass1(blk, v);
+          }
+          // pass 2 (TMEM is re-read: cheaper than holding 3*C logits); parity continues from pass 1
+#pragma unroll
+          for (int blk = P2_FIRST; blk <= P2_LAST; ++blk) {
+            ptx::tmem_ld_wait();
+            // the prefetch at the end of pass 1 landed in the set pass 1's last block did not use
+            const bool cur_is_a = (((NBLK - 1) & 1) != 0) ^ (((blk - P2_FIRST) & 1) != 0);
+            if (blk < P2_LAST) {
+              if (cur_is_a) ptx::tmem_ld_32x16(t_base + (blk + 1) * 16, rb);
+              else ptx::tmem_ld_32x16(t_base + (blk + 1) * 16, ra);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(cur_is_a ? ra[j] : rb[j]) + s_bias[blk * 16 + j];
+            pass2(blk, v);
+          }
+        } else {
+#pragma unroll
+          for (int blk = 0; blk < NBLK; ++blk) {
+            float v[16];
+            raw16(blk * 16, v);
+            pass1(blk, v);
+          }
+#pragma unroll
+          for (int blk = P2_FIRST; blk <= P2_LAST; ++blk) {
+            float v[16];
+            raw16(blk * 16, v);
+            pass2(blk, v);
           }
         }
         {   // all TMEM reads of this tile are done: hand the stage back
