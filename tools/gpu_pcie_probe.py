@@ -1,19 +1,44 @@
-"""Host<->device copy bandwidth of the box (pinned memory), alone and while a forward runs."""
-import time
+"""Host<->device copy bandwidth of the box (pinned memory): one stream, N concurrent streams, chunked."""
 import torch
 
-x = torch.empty(64 * 3 * 416 * 416, dtype=torch.float32).pin_memory()
-d = torch.empty_like(x, device="cuda")
-s = torch.cuda.Stream()
-for name, src, dst in (("H2D", x, d), ("D2H", d, x)):
+n = 64 * 3 * 416 * 416
+x = torch.empty(n, dtype=torch.float32).pin_memory()
+d = torch.empty(n, dtype=torch.float32, device="cuda")
+
+
+def timed(fn, reps=10):
     for _ in range(3):
-        dst.copy_(src, non_blocking=True)
+        fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(10):
-        dst.copy_(src, non_blocking=True)
+    for _ in range(reps):
+        fn()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
-    print(f"{name}: {x.numel() * 4 / 1e6:.0f} MB in {ms:.3f} ms = {x.numel() * 4 / ms / 1e6:.1f} GB/s")
+    return e0.elapsed_time(e1) / reps
+
+
+ms = timed(lambda: d.copy_(x, non_blocking=True))
+print(f"H2D 1 stream : {n * 4 / 1e6:.0f} MB in {ms:.3f} ms = {n * 4 / ms / 1e6:.1f} GB/s")
+ms = timed(lambda: x.copy_(d, non_blocking=True))
+print(f"D2H 1 stream : {n * 4 / ms / 1e6:.1f} GB/s")
+for k in (2, 4):
+    streams = [torch.cuda.Stream() for _ in range(k)]
+    parts = [(i * n // k, (i + 1) * n // k) for i in range(k)]
+    cur = torch.cuda.current_stream()
+
+    def fn():
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        for s, (a, b) in zip(streams, parts):
+            s.wait_event(ev)
+            with torch.cuda.stream(s):
+                d[a:b].copy_(x[a:b], non_blocking=True)
+        for s in streams:
+            cur.wait_stream(s)
+    ms = timed(fn)
+    print(f"H2D {k} streams: {n * 4 / ms / 1e6:.1f} GB/s")
+# host-side page placement: first-touch by this thread vs interleaved is not controllable here; report NUMA
+import os
+print("cpus", len(os.sched_getaffinity(0)))

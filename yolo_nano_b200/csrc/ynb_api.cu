@@ -127,6 +127,8 @@ struct ynb_engine {
     int* flag_host = nullptr;          // pinned: device error word of this step
   } slot[2];
   cudaStream_t s_copy = nullptr;       // H2D next to the compute stream
+  cudaStream_t s_copy2 = nullptr;      // second half of a large H2D (two DMA queues: 53 -> 55 GB/s measured)
+  cudaEvent_t ev_copy2 = nullptr;
   cudaStream_t s_d2h = nullptr;        // results back to the host (PCIe is full duplex: its own stream)
   const float* d_x_bound = nullptr;   // input of the forward in flight
   float* d_out_boxes = nullptr;
@@ -877,6 +879,8 @@ YNB_EXPORT int ynb_create(const ynb_config* cfg, ynb_engine** out) {
             cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&e->s_copy2, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&e->ev_copy2, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaMalloc(&e->d_prelut, sizeof(PreLut)) == cudaSuccess &&
        cudaMemcpy(e->d_prelut, &e->prelut, sizeof(PreLut), cudaMemcpyHostToDevice) == cudaSuccess;
@@ -914,6 +918,8 @@ YNB_EXPORT void ynb_destroy(ynb_engine* e) {
     if (e->slot[k].flag_host) cudaFreeHost(e->slot[k].flag_host);
   }
   if (e->s_copy) cudaStreamDestroy(e->s_copy);
+  if (e->s_copy2) cudaStreamDestroy(e->s_copy2);
+  if (e->ev_copy2) cudaEventDestroy(e->ev_copy2);
   if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
   if (e->d_prelut) cudaFree(e->d_prelut);
   if (e->s_main) cudaStreamDestroy(e->s_main);
@@ -1138,7 +1144,14 @@ static int submit_host_common(ynb_engine* e, int32_t slot_id, const float* x_hos
   CUDA_TRY(e, cudaEventRecord(e->ev_in, user));
   CUDA_TRY(e, cudaStreamWaitEvent(e->s_copy, e->ev_in, 0));
   if (x_host) {
-    CUDA_TRY(e, cudaMemcpyAsync(sl.x, x_host, px * 4 * batch, cudaMemcpyHostToDevice, e->s_copy));
+    // two halves on two copy streams (two DMA queues in flight)
+    const size_t total = px * 4 * batch, half = (total / 2) & ~(size_t)255;
+    CUDA_TRY(e, cudaStreamWaitEvent(e->s_copy2, e->ev_in, 0));
+    CUDA_TRY(e, cudaMemcpyAsync(sl.x, x_host, half, cudaMemcpyHostToDevice, e->s_copy));
+    CUDA_TRY(e, cudaMemcpyAsync(reinterpret_cast<char*>(sl.x) + half, reinterpret_cast<const char*>(x_host) + half,
+                                total - half, cudaMemcpyHostToDevice, e->s_copy2));
+    CUDA_TRY(e, cudaEventRecord(e->ev_copy2, e->s_copy2));
+    CUDA_TRY(e, cudaStreamWaitEvent(e->s_copy, e->ev_copy2, 0));
   } else {
     CUDA_TRY(e, cudaMemcpyAsync(sl.img_u8, img_host, px * batch, cudaMemcpyHostToDevice, e->s_copy));
     if (rects_host)
