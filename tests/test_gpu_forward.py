@@ -291,3 +291,26 @@ def test_dropin_detect_images_equals_detect_on_reference_tensor(G, golden):
     for r, q in zip(ref, got):
         for a, b in zip(r, q):
             np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("size,classes,batch", [(608, 80, 2), (224, 20, 5)])
+def test_detect_other_sizes_keepset_exact_on_own_candidates(G, size, classes, batch):
+    """BASELINE config 3 geometry (608^2, N = 22 743 anchors) and an odd small one: the whole CUDA path
+    (fused decode + anchor-grid NMS, CUDA graph on the second call) against the oracle NMS run on the
+    engine's own decoded candidates, reference-init weights (every anchor is a candidate)."""
+    sd = W.reference_init(classes, seed=4)
+    x = W.synthetic_input(batch, size, 4).to(G.DEV)
+    eng = G.make_engine(sd, size, classes, "3xtf32")
+    boxes, scores, cls = eng.forward_decode(x)
+    for rep in range(2):                                   # eager, then graph replay
+        ob, os_, oc, on = eng.forward_detect(x)
+        for i in range(batch):
+            bh, sh = boxes[i].cpu().numpy(), scores[i].cpu().numpy()
+            ch = cls[i].cpu().numpy().astype(np.int64)
+            b, s, c, idx = O.postprocess_flat(bh, sh, ch, classes, 0.001, 0.5)
+            k = int(on[i])
+            assert k == len(idx)
+            np.testing.assert_array_equal(ob[i, :k].cpu().numpy(), b)
+            np.testing.assert_array_equal(os_[i, :k].cpu().numpy(), s)
+            np.testing.assert_array_equal(oc[i, :k].cpu().numpy().astype(np.int64), c)
+    eng.close()

@@ -1092,6 +1092,7 @@ static int detect_device(ynb_engine* e, const float* x_dev, int batch, float* ob
                            e->cfg.diou_nms, e->cfg.gemm_mode, e->S};
   auto it = e->graphs.find(key);
   if (it == e->graphs.end()) {
+    if (e->graph_seen.size() > 256) e->graph_seen.clear();      // callers that never reuse a buffer stay eager
     if (e->graph_seen[key]++ == 0) return detect_ops(e, plan, x_dev, batch, ob, os, oc, on);   // first sighting
     if (e->graphs.size() >= 32) drop_graphs(e);
     cudaGraph_t graph = nullptr;
