@@ -161,6 +161,11 @@ int  ynb_wait_host(ynb_engine* e, int32_t slot);
 int  ynb_set_normalization(ynb_engine* e, const float* mean_bgr /*[3]*/, const float* std_bgr /*[3]*/);
 int  ynb_preprocess_u8(ynb_engine* e, const uint8_t* img_dev, const int32_t* rects_dev, int32_t batch,
                        float* x_dev /*[B,3,S,S]*/, void* stream);
+/* Test-time augmentation input (utils/misc.py:104-121): torch.nn.functional.interpolate(x, (s, s),
+ * mode='bilinear', align_corners=False) of a float32 NCHW batch [B,3,h,w] and, with_flip != 0, the
+ * torch.flip(.., [-1]) copy: out [B or 2B, 3, s, s] with out[2b] = resized, out[2b+1] = flipped. */
+int  ynb_resize_bilinear(const float* in_dev, int32_t batch, int32_t h_in, int32_t w_in, float* out_dev,
+                         int32_t s_out, int32_t with_flip, void* stream);
 /* ynb_submit_host with uint8 images: H2D of the bytes + pre-processing + the whole path. */
 int  ynb_submit_host_u8(ynb_engine* e, int32_t slot, const uint8_t* img_host, const int32_t* rects_host,
                         int32_t batch, float* out_boxes_host, float* out_scores_host,

@@ -188,9 +188,30 @@ def preprocess_golden():
     print("g4", {k: v.shape for k, v in out.items() if k.endswith("tensor")})
 
 
+def tta_golden():
+    """G5: the reference's TestTimeAugmentation (utils/misc.py:90-148) driving the reference model:
+    calibrated VOC-20 weights, 128^2 input, scales 96 / 128 / 160, flips, merge NMS 0.4."""
+    from oracle import weights as W
+    YOLONano, config, _ = _import_reference()
+    from utils.misc import TestTimeAugmentation  # type: ignore
+    sd = W.calibrated(20, seed=6)
+    m = _build(YOLONano, 128, 20, config.MULTI_ANCHOR_SIZE, sd=sd)
+    x = W.synthetic_input(1, 128, 6)
+    tta = TestTimeAugmentation(num_classes=20, nms_thresh=0.4, scale_range=[96, 160, 32])
+    with torch.no_grad():
+        b, s, c = tta(x, m)
+    np.savez_compressed(OUT / "g5_tta128_calibrated.npz", bboxes=b.astype(np.float32), scores=s.astype(np.float32),
+                        labels=c.astype(np.int64), scales=np.array(tta.scales), seed=6, numpy=np.__version__,
+                        torch=torch.__version__)
+    print("g5", b.shape, np.bincount(c, minlength=20).tolist())
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "preprocess":
         preprocess_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == "tta":
+        tta_golden()
     else:
         main()
         preprocess_golden()
+        tta_golden()

@@ -363,3 +363,41 @@ def preprocess_u8(canvas: np.ndarray, rect=None, mean=VAL_MEAN_BGR, std=VAL_STD_
     image /= std
     image = image[..., (2, 1, 0)]
     return np.ascontiguousarray(np.transpose(image, (2, 0, 1))).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# Test-time augmentation: utils/misc.py:90-148
+def tta_merge(bboxes: np.ndarray, scores: np.ndarray, labels: np.ndarray, num_classes: int, nms_thresh: float,
+              tie: str = "index"):
+    """Second per-class NMS over the union (utils/misc.py:131-146; nms of utils/misc.py:8-37 is the
+    same loop as models/yolo_nano.py:159-188)."""
+    keep = np.zeros(len(bboxes), dtype=np.int64)
+    for i in range(num_classes):
+        inds = np.where(labels == i)[0]
+        if len(inds) == 0:
+            continue
+        c_keep = nms(bboxes[inds], scores[inds], nms_thresh, tie)
+        keep[inds[c_keep]] = 1
+    keep = np.where(keep > 0)
+    return bboxes[keep], scores[keep], labels[keep]
+
+
+@torch.no_grad()
+def tta(sd: StateDict, x: torch.Tensor, num_classes: int, anchor_size, scales, nms_thresh: float = 0.4,
+        conf_thresh: float = 0.001, model_nms_thresh: float = 0.5, tie: str = "index"):
+    """TestTimeAugmentation.__call__ (utils/misc.py:97-148): for every scale, the image and its
+    horizontal flip through the model (image 0 only), boxes of the flip mirrored back, union, NMS."""
+    import torch.nn.functional as F
+    bl, sl, ll = [], [], []
+    for s in scales:
+        s = int(s)
+        xs = x if (x.size(-1) == s and x.size(-2) == s) else F.interpolate(x, size=(s, s), mode="bilinear",
+                                                                               align_corners=False)
+        b, sc, lb = detect(sd, xs[:1], s, num_classes, anchor_size, conf_thresh, model_nms_thresh, False, tie)[0]
+        bl.append(b); sl.append(sc); ll.append(lb)
+        b, sc, lb = detect(sd, torch.flip(xs, [-1])[:1], s, num_classes, anchor_size, conf_thresh, model_nms_thresh,
+                           False, tie)[0]
+        b = b.copy()
+        b[:, 0::2] = 1.0 - b[:, 2::-2]
+        bl.append(b); sl.append(sc); ll.append(lb)
+    return tta_merge(np.concatenate(bl), np.concatenate(sl), np.concatenate(ll), num_classes, nms_thresh, tie)

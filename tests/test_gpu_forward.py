@@ -314,3 +314,58 @@ def test_detect_other_sizes_keepset_exact_on_own_candidates(G, size, classes, ba
             np.testing.assert_array_equal(os_[i, :k].cpu().numpy(), s)
             np.testing.assert_array_equal(oc[i, :k].cpu().numpy().astype(np.int64), c)
     eng.close()
+
+
+def test_resize_bilinear_matches_interpolate_and_flip(G):
+    """ynb_resize_bilinear against torch.nn.functional.interpolate(bilinear, align_corners=False) and
+    torch.flip (utils/misc.py:104-121): up- and down-scaling within 2e-6, identity size bit-exact."""
+    import torch.nn.functional as F
+    import yolo_nano_b200 as pkg
+    x = W.synthetic_input(2, 128, 8)
+    for s in (96, 128, 160, 320):
+        got = pkg.resize_bilinear(x.to(G.DEV), s, with_flip=True).cpu()
+        ref = F.interpolate(x, size=(s, s), mode="bilinear", align_corners=False)
+        for b in range(2):
+            if s == 128:
+                assert torch.equal(got[2 * b], x[b])
+            torch.testing.assert_close(got[2 * b], ref[b], rtol=0, atol=2e-6)
+            assert torch.equal(got[2 * b + 1], torch.flip(got[2 * b], [-1]))
+        plain = pkg.resize_bilinear(x.to(G.DEV), s).cpu()
+        assert torch.equal(plain, got[0::2])
+
+
+def test_tta_driver_against_reference_driver(G, golden):
+    """Drop-in TestTimeAugmentation (3 scales x flip through the engine, merge NMS on the device) against
+    the real reference driver's recorded result.  The merge NMS is exact on its inputs; the per-scale
+    detections carry the network tolerance, so boxes are matched by label within 0.3 px."""
+    import yolo_nano_b200 as pkg
+    g = golden("g5_tta128_calibrated.npz")
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = pkg.YOLONano(G.DEV, 128, 20, anchor_size=pkg.MULTI_ANCHOR_SIZE)
+    m.load_state_dict(W.calibrated(20, seed=6))
+    m = m.to(G.DEV).eval()
+    x = W.synthetic_input(1, 128, 6).to(G.DEV)
+    tta = pkg.TestTimeAugmentation(num_classes=20, nms_thresh=0.4, scale_range=[96, 160, 32])
+    b, s, c = tta(x, m)
+    # (a) the merge step alone is exact: ynb_nms on the union == oracle merge on the same union
+    from yolo_nano_b200.tta import merge_nms
+    rng = np.random.default_rng(0)
+    ub = np.concatenate([g["bboxes"], np.clip(g["bboxes"] + rng.normal(0, 0.01, g["bboxes"].shape), 0, 1)]).astype(np.float32)
+    us = np.concatenate([g["scores"], g["scores"] * np.float32(0.9)]).astype(np.float32)
+    ul = np.concatenate([g["labels"], g["labels"]])
+    mb, ms, ml = merge_nms(ub, us, ul, 20, 0.4, G.DEV)
+    ob, os_, ol = O.tta_merge(ub, us, ul, 20, 0.4)
+    np.testing.assert_array_equal(mb, ob)
+    np.testing.assert_array_equal(ms, os_)
+    np.testing.assert_array_equal(ml, ol)
+    # (b) end to end against the reference driver
+    gb, gl = g["bboxes"], g["labels"]
+    print(f"[report] TTA: kept {len(b)} vs reference {len(gb)}")
+    assert abs(len(b) - len(gb)) <= 0.01 * len(gb) + 2
+    unmatched = 0
+    for k in range(len(gb)):
+        cand = np.nonzero(c == gl[k])[0]
+        d = np.abs(b[cand] - gb[k]).max(axis=1).min() * 128 if len(cand) else 1e9
+        unmatched += d > 0.3
+    print(f"[report] TTA: {unmatched} of {len(gb)} reference boxes without a match within 0.3 px")
+    assert unmatched <= 0.01 * len(gb) + 2

@@ -147,3 +147,15 @@ def test_preprocess_restatement_matches_reference_valtransforms(golden):
         rect = g[f"{name}.rect"]
         t = O.preprocess_u8(g[f"{name}.canvas"], None if name == "square" else rect)
         np.testing.assert_array_equal(t, g[f"{name}.tensor"])
+
+
+def test_tta_restatement_matches_reference_driver(golden):
+    """oracle.tta against the real TestTimeAugmentation + reference model (utils/misc.py:90-148):
+    3 scales x flip, merge NMS 0.4 — identical boxes, scores, labels."""
+    g = golden("g5_tta128_calibrated.npz")
+    sd = W.calibrated(20, seed=6)
+    x = W.synthetic_input(1, 128, 6)
+    b, s, c = O.tta(sd, x, 20, W.anchors_for(20), g["scales"], 0.4)
+    np.testing.assert_array_equal(c, g["labels"])
+    np.testing.assert_array_equal(b, g["bboxes"])
+    np.testing.assert_array_equal(s, g["scores"])

@@ -1,6 +1,7 @@
 // HBM-bound kernels of the path: stem conv + max-pool, depthwise 3x3, pass-through
 // interleave (channel shuffle as a store permutation) and layout conversion for taps.
 #pragma once
+#include <algorithm>
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
@@ -171,6 +172,55 @@ inline cudaError_t launch_stem_pool(const float* x, float* out, const StemWeight
   int Hp = S / 4;
   dim3 grid((Hp + kStemTile - 1) / kStemTile, (Hp + kStemTile - 1) / kStemTile, batch);
   cudaError_t r = launch_pdl(stem_pool_kernel, grid, dim3(kStemThreads), 0, st, x, out, wt, tmX, use_tma, S);
+  YNB_COUNT_LAUNCH();
+  return r;
+}
+
+// =====================================================================================
+// Test-time augmentation input (utils/misc.py:104-121): bilinear resize of the
+// NCHW input to s x s with align_corners=False (torch.nn.functional.interpolate) and, optionally, the
+// horizontally flipped copy (torch.flip(x, [-1])) — written as out[2b] = resized, out[2b+1] = flipped.
+//   src = (dst + 0.5) * (in / out) - 0.5, clamped at 0; neighbours clamped at in - 1
+//   out = (1-ly) * ((1-lx) v00 + lx v01) + ly * ((1-lx) v10 + lx v11)
+// =====================================================================================
+__global__ void __launch_bounds__(256)
+resize_bilinear_kernel(const float* __restrict__ in, float* __restrict__ out, int planes, int Hi, int Wi, int So,
+                       int with_flip) {
+  const int64_t total = (int64_t)planes * So * So;
+  const float sy = (float)Hi / (float)So, sx = (float)Wi / (float)So;
+  pdl_trigger();
+  pdl_wait();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % So);
+    const int oy = (int)((i / So) % So);
+    const int64_t pl = i / ((int64_t)So * So);                 // b * C + c
+    const float fy = fmaxf(sy * ((float)oy + 0.5f) - 0.5f, 0.0f), fx = fmaxf(sx * ((float)ox + 0.5f) - 0.5f, 0.0f);
+    const int y0 = min((int)fy, Hi - 1), x0 = min((int)fx, Wi - 1);
+    const int y1 = min(y0 + 1, Hi - 1), x1 = min(x0 + 1, Wi - 1);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float* src = in + pl * Hi * Wi;
+    const float v00 = __ldg(src + y0 * Wi + x0), v01 = __ldg(src + y0 * Wi + x1);
+    const float v10 = __ldg(src + y1 * Wi + x0), v11 = __ldg(src + y1 * Wi + x1);
+    const float v = (1.0f - ly) * ((1.0f - lx) * v00 + lx * v01) + ly * ((1.0f - lx) * v10 + lx * v11);
+    if (!with_flip) {
+      out[i] = v;
+    } else {
+      // planes of image b go to out images 2b (as is) and 2b+1 (mirrored): plane index b*C + c with C = 3
+      const int64_t b = pl / 3, c = pl - b * 3;
+      float* o0 = out + ((2 * b) * 3 + c) * (int64_t)So * So + (int64_t)oy * So;
+      o0[ox] = v;
+      o0[3 * (int64_t)So * So + (So - 1 - ox)] = v;
+    }
+  }
+}
+
+inline cudaError_t launch_resize_bilinear(const float* in, float* out, int batch, int Hi, int Wi, int So, int with_flip,
+                                          cudaStream_t st) {
+  const int64_t total = (int64_t)batch * 3 * So * So;
+  if (total <= 0) return cudaSuccess;
+  int64_t blocks = std::min<int64_t>((total + 255) / 256, (int64_t)kNumSMs * 16);
+  cudaError_t r = launch_pdl(resize_bilinear_kernel, dim3((unsigned)blocks), dim3(256), 0, st, in, out, batch * 3, Hi, Wi,
+                             So, with_flip);
   YNB_COUNT_LAUNCH();
   return r;
 }

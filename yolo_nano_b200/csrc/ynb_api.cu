@@ -1322,6 +1322,15 @@ YNB_EXPORT int ynb_dwconv3x3(const float* in, int32_t in_ld, int32_t in_off, flo
   return YNB_OK;
 }
 
+// TTA input: bilinear resize (+ flipped copy) of an NCHW float32 batch, device buffers (utils/misc.py:104-121).
+YNB_EXPORT int ynb_resize_bilinear(const float* in_dev, int32_t batch, int32_t h_in, int32_t w_in, float* out_dev,
+                                   int32_t s_out, int32_t with_flip, void* stream) {
+  if (!in_dev || !out_dev || batch <= 0 || h_in <= 0 || w_in <= 0 || s_out <= 0)
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_resize_bilinear: bad arguments");
+  UNIT_TRY(launch_resize_bilinear(in_dev, out_dev, batch, h_in, w_in, s_out, with_flip, (cudaStream_t)stream));
+  return YNB_OK;
+}
+
 YNB_EXPORT int ynb_pwconv(const float* in, int32_t in_ld, int32_t in_off, float* out, int32_t out_ld,
                           int32_t out_off, int32_t out_step, const float* w, const float* b, int64_t pixels,
                           int32_t cin, int32_t cout, int32_t act, void* stream) {
