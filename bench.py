@@ -135,6 +135,26 @@ def load_traffic(kernel_substr: str):
     return sum(per_launch.values()) / len(per_launch) if per_launch else None
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Restrict this rank to the CPU cores NVML reports as local to its GPU (before any pinned host
+    buffer is allocated: first touch places the pages on that NUMA node).  With 8 ranks pushing
+    133 MB per step each, cross-socket input copies halve the host-side bandwidth.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {w * 64 + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus and len(cpus) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)[0], len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def load_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -208,6 +228,7 @@ def main():
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)      # pinned host buffers are then allocated next to the GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     modes = {"ffma": _lib.GEMM_FP32_FFMA, "3xtf32": _lib.GEMM_TC_3XTF32, "tf32": _lib.GEMM_TC_TF32}
@@ -373,6 +394,7 @@ def main():
                        "h2d_bytes_per_step": a.batch * 3 * a.size * a.size, "ms_per_step": wall_u8 / a.steps,
                        "call": "ynb_submit_host_u8 / ynb_wait_host: uint8 HWC BGR images, Normalize + ToTensor of "
                                "data/transforms.py on the device (bit-identical tensor), then the same path"},
+            "host_affinity": None if numa is None else {"first_cpu": numa[0], "cpus": numa[1]},
             "gpu_launches": launches, "clocks": sampler.summary() if sampler else None,
             "roofline": roofline, "cpu_baseline": cpu,
             "detections_per_image": float(counts.mean())}
