@@ -359,11 +359,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const float slope = p.act == YNB_ACT_RELU ? 0.0f : (p.act == YNB_ACT_LEAKY ? 0.1f : 1.0f);
     uint8_t* sbox = smem + lay.stg_off + warp * 4096;          // this warp's [32 rows x 128 B] swizzled box
     const int sw = lane & 7;                                    // swizzle phase of this thread's row
-    bool ok = group < p.acc_stages;
-    int lt = group;                                             // local tile index handled next
-    for (int64_t tile = blockIdx.x + (int64_t)group * gridDim.x; tile < p.num_tiles && ok;
-         tile += (int64_t)p.acc_stages * gridDim.x, lt += p.acc_stages) {
-      const int acc = p.acc_stages == 2 ? group : 0;
+    // The LAST tile of this CTA is drained by BOTH groups, half of the columns each: nothing is left to
+    // overlap with, so the kernel's tail (one epilogue: 7 k cycles plain, 18 k interleaved) halves.
+    // Not for the decode epilogue (a thread needs all columns of its row).
+    const int nloc = (int64_t)blockIdx.x < p.num_tiles
+                         ? (int)((p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;   // tiles of this CTA
+    const bool share_last = kDecC == 0;
+    const int col_split = min(p.Npad, ((p.Npad / 2 + 31) / 32) * 32);      // group 0: [0, split), group 1: [split, Npad)
+    bool ok = true;
+    for (int lt = 0; lt < nloc && ok; ++lt) {
+      const int64_t tile = blockIdx.x + (int64_t)lt * gridDim.x;
+      const int acc = p.acc_stages == 2 ? (lt & 1) : 0;
+      const bool shared = share_last && lt == nloc - 1 && col_split < p.Npad;
+      if (!shared && group != acc) {                            // owner group only
+        // With ONE accumulator stage group 1 owns nothing: it still observes every phase of the barrier,
+        // so that its parity wait for the shared last tile cannot match an older phase.  (With two stages
+        // the non-owner has just drained tile lt-1, whose completion implies tile lt-2's — in-order commits.)
+        if (p.acc_stages == 1 && share_last) ok = ptx::mbar_wait(&tmem_full[0], (uint32_t)(lt & 1), p.err_flag, 7);
+        continue;
+      }
+      const int col_begin = shared && group == 1 ? col_split : 0;
+      const int col_end = shared && group == 0 ? col_split : p.Npad;
       const uint32_t acc_ph = (uint32_t)((lt / p.acc_stages) & 1);
       // row -> output pixel
       int64_t m;
@@ -398,8 +414,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int r = 0; r < 16; ++r) x[r] = r < nr ? __ldg(src + r * p.pass_ld) : 0.0f;
       };
       if (kPass) {
-        fetch_x1(0, 0, xa);
-        fetch_x1(0, 16, xb);
+        fetch_x1(col_begin, 0, xa);
+        fetch_x1(col_begin, 16, xb);
       }
       if (lane == 0 && q == 0) YNB_TRACE(4, tile, group);
       ok = ptx::mbar_wait(&tmem_full[acc], acc_ph, p.err_flag, 6);
@@ -570,15 +586,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         return *reinterpret_cast<const float*>(sbox + r * 128 + ((((l >> 2) ^ (r & 7)) << 4) | ((l & 3) << 2)));
       };
 
-      for (int c0 = 0; c0 < p.Npad; c0 += 32) {
+      for (int c0 = col_begin; c0 < col_end; c0 += 32) {
         if (p.tma_store) {
           if (lane == 0) ptx::bulk_wait_read<0>();   // the previous store has finished reading the box
           __syncwarp();
         }
         drain16(c0, 0);
-        if (c0 + 16 < p.Npad) drain16(c0 + 16, 4);
-        if (c0 + 32 >= p.Npad) {   // all TMEM reads of this tile are done: hand the stage back
-          ptx::tc_fence_before_sync();
+        if (c0 + 16 < col_end) drain16(c0 + 16, 4);
+        if (c0 + 32 >= col_end && !shared) {   // all TMEM reads of this tile are done: hand the stage back
+          ptx::tc_fence_before_sync();          // (a shared tile is the CTA's last: nobody waits for the stage)
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
         }
@@ -602,11 +618,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int r = 0; r < 16; ++r, o += p.out_ld)
             if (r < nrow) *reinterpret_cast<float2*>(o) = make_float2(xa[r], staged(r, lane));
-          if (c0 + 32 < p.Npad) fetch_x1(c0 + 32, 0, xa);
+          if (c0 + 32 < col_end) fetch_x1(c0 + 32, 0, xa);
 #pragma unroll
           for (int r = 16; r < 32; ++r, o += p.out_ld)
             if (r < nrow) *reinterpret_cast<float2*>(o) = make_float2(xb[r - 16], staged(r, lane));
-          if (c0 + 32 < p.Npad) fetch_x1(c0 + 32, 16, xb);
+          if (c0 + 32 < col_end) fetch_x1(c0 + 32, 16, xb);
         } else {
           const int col = vec ? p.out_off + i : p.omap.slot(p.out_off + (col_ok ? i : 0) * p.out_step);
           if (!p.is3x3) {
