@@ -18,11 +18,20 @@
 //     (the dropped a_lo*b_lo term is then one-signed); round-to-nearest makes the split
 //     unbiased with 9.5e-8 rms — hence RN;
 //   * the tensor core TRUNCATES when it adds into the accumulator: bias ~ -0.4 ulp per
-//     accumulation step (K=464: -2.9e-6 on one-signed sums, FFMA: 1e-9).  So the exact
-//     main products a_hi*b_hi are spread round-robin over `nmain` TMEM accumulators and the
-//     two correction products get their own; the epilogue adds them in fp32 (RN).
+//     accumulation step (K=464: -2.9e-6 on one-signed sums, FFMA: 1e-9).  The small correction
+//     products must therefore not be added into the large sum: they get their OWN accumulator and
+//     the epilogue adds main + correction in fp32 (one merged accumulator doubles the end-to-end
+//     error; spreading the main products over several accumulators buys nothing measurable).
+//     With main and correction adjacent in TMEM and W_hi / W_lo adjacent in smem,
+//     a_hi x [b_hi; b_lo] is ONE MMA of N = 2*Npad (`stack_b`): two MMAs per K step.
 // W_hi / W_lo are split once at weight-pack time; A is split in shared memory by the
-// splitter warps, position-wise on the swizzled bytes (no layout knowledge needed).
+// splitter warps, position-wise on the swizzled bytes (no layout knowledge needed) — or once
+// by the kernel that produces it (`presplit`, 3x3 convs: two TMA boxes per step, no splitters).
+//
+// Epilogue variants: plain (TMA bulk tensor store of the swizzled box), pass-through
+// interleave (stride-1 ShuffleNet unit tail: out[2i] = x1[i], out[2i+1] = conv[i]), slot-mapped /
+// spatial-tile stores, and the fused detection decode (kDecC = 80 | 20).  The CTA's last tile is
+// drained by both epilogue groups, half of the columns each.
 //
 // 3x3 mode: the nine taps are nine TMA boxes of the same 4-D tensor map shifted by
 // (dx-1, dy-1); out-of-bounds elements are zero-filled by TMA = the conv's zero padding.
