@@ -206,8 +206,103 @@ def tta_golden():
     print("g5", b.shape, np.bincount(c, minlength=20).tolist())
 
 
+def evalfmt_golden():
+    """G6: the reference evaluators' own code on fixed detections — COCOAPIEvaluator.evaluate up to the
+    result JSON (evaluator/cocoapi_evaluator.py:47-112, fake dataset / model / COCO object) and
+    VOCAPIEvaluator.write_voc_results_file (evaluator/vocapi_evaluator.py:142-157)."""
+    import json
+    import tempfile
+    from types import SimpleNamespace
+    _import_reference()
+    with contextlib.redirect_stdout(io.StringIO()):
+        from evaluator.cocoapi_evaluator import COCOAPIEvaluator  # type: ignore
+        from evaluator.vocapi_evaluator import VOCAPIEvaluator  # type: ignore
+    rng = np.random.default_rng(12)
+    n_img, sizes = 2, [(480, 640), (500, 375)]          # (h, w)
+    dets, scales, offsets = [], [], []
+    for h, w in sizes:
+        k = 7
+        xy = rng.random((k, 2), dtype=np.float32) * 0.6
+        b = np.concatenate([xy, xy + rng.random((k, 2), dtype=np.float32) * 0.3 + 0.05], 1).astype(np.float32)
+        dets.append((b, rng.random(k, dtype=np.float32), rng.integers(0, 5, k).astype(np.int64)))
+        if h < w:
+            scales.append(np.array([1., h / w, 1., h / w])); offsets.append(np.array([[0., (w - h) // 2 / w, 0., (w - h) // 2 / w]]))
+        else:
+            scales.append(np.array([[w / h, 1., w / h, 1.]])); offsets.append(np.array([[(h - w) // 2 / h, 0., (h - w) // 2 / h, 0.]]))
+    class_ids = [1, 3, 7, 18, 44]
+    state = {"i": 0}
+
+    class FakeModel:
+        def eval(self):
+            return self
+        def __call__(self, x):
+            b, s, c = dets[state["i"]]
+            return b.copy(), s.copy(), c.copy()
+
+    def transform(img):
+        i = state["i"]
+        return torch.zeros(3, 8, 8), None, None, scales[i], offsets[i]
+
+    class FakeDataset:
+        class_ids = [1, 3, 7, 18, 44]
+        coco = SimpleNamespace(loadRes=lambda path: None)
+        def __len__(self):
+            return n_img
+        def pull_image(self, index):
+            state["i"] = index
+            h, w = sizes[index]
+            return np.zeros((h, w, 3), np.uint8), 1000 + index
+
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            fake = SimpleNamespace(dataset=FakeDataset(), transform=transform, device=torch.device("cpu"), testset=True)
+            with contextlib.redirect_stdout(io.StringIO()):
+                COCOAPIEvaluator.evaluate(fake, FakeModel())
+            coco_json = open("coco_test-dev.json").read()
+            # VOC: boxes mapped exactly as evaluate() does (:72-74), per-class arrays (:76-86), then the writer
+            labelmap = ["aeroplane", "bicycle", "bird", "boat", "bottle"]
+            all_boxes = [[[] for _ in range(n_img)] for _ in labelmap]
+            mapped = []
+            for i, (h, w) in enumerate(sizes):
+                b, s, c = (v.copy() for v in dets[i])
+                size = np.array([[w, h, w, h]])
+                b -= offsets[i]; b /= scales[i]; b *= size
+                mapped.append(b.copy())
+                for j in range(len(labelmap)):
+                    inds = np.where(c == j)[0]
+                    if len(inds) == 0:
+                        all_boxes[j][i] = np.empty([0, 5], dtype=np.float32)
+                        continue
+                    all_boxes[j][i] = np.hstack((b[inds], s[inds][:, np.newaxis])).astype(np.float32, copy=False)
+            # `if dets == []` (:150) raises on NumPy >= 2 for arrays; old NumPy answered False: same shim idea as np.int
+            class _Arr(np.ndarray):
+                def __eq__(self, other):
+                    return False if isinstance(other, list) else np.ndarray.__eq__(self, other)
+            all_boxes = [[a.view(_Arr) for a in row] for row in all_boxes]
+            fake_voc = SimpleNamespace(labelmap=labelmap, display=False,
+                                       dataset=SimpleNamespace(ids=[("VOC2007", "000001"), ("VOC2007", "000002")]),
+                                       get_voc_results_file_template=lambda cls: os.path.join(tmp, "det_test_%s.txt" % cls))
+            VOCAPIEvaluator.write_voc_results_file(fake_voc, all_boxes)
+            voc_files = {cls: open(os.path.join(tmp, "det_test_%s.txt" % cls)).read() for cls in labelmap}
+        finally:
+            os.chdir(cwd)
+    out = {"coco_json": np.array(coco_json), "class_ids": np.array(class_ids), "sizes": np.array(sizes),
+           "labelmap": np.array(labelmap)}
+    for i in range(n_img):
+        out[f"img{i}.bboxes"], out[f"img{i}.scores"], out[f"img{i}.cls"] = dets[i]
+        out[f"img{i}.scale"], out[f"img{i}.offset"], out[f"img{i}.mapped"] = scales[i], offsets[i], mapped[i]
+    for cls, txt in voc_files.items():
+        out[f"voc.{cls}"] = np.array(txt)
+    np.savez_compressed(OUT / "g6_evalfmt.npz", **out)
+    print("g6", len(json.loads(coco_json)), "coco rows;", {k: len(v.splitlines()) for k, v in voc_files.items()})
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "preprocess":
+    if len(sys.argv) > 1 and sys.argv[1] == "evalfmt":
+        evalfmt_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == "preprocess":
         preprocess_golden()
     elif len(sys.argv) > 1 and sys.argv[1] == "tta":
         tta_golden()
@@ -215,3 +310,4 @@ if __name__ == "__main__":
         main()
         preprocess_golden()
         tta_golden()
+        evalfmt_golden()

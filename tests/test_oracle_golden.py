@@ -159,3 +159,27 @@ def test_tta_restatement_matches_reference_driver(golden):
     np.testing.assert_array_equal(c, g["labels"])
     np.testing.assert_array_equal(b, g["bboxes"])
     np.testing.assert_array_equal(s, g["scores"])
+
+
+def test_evaluator_glue_matches_reference_evaluators(golden):
+    """yolo_nano_b200.evalfmt against the real evaluators run on fixed detections (golden g6):
+    inverse letterbox mapping, COCO result rows (cocoapi_evaluator.py:85-100), VOC per-class arrays and
+    det-file lines (vocapi_evaluator.py:72-86,148-157)."""
+    import json
+    from yolo_nano_b200 import evalfmt
+    g = golden("g6_evalfmt.npz")
+    class_ids = g["class_ids"].tolist()
+    labelmap = [str(v) for v in g["labelmap"]]
+    rows, voc = [], {c: "" for c in labelmap}
+    for i, (h, w) in enumerate(g["sizes"].tolist()):
+        b = g[f"img{i}.bboxes"].copy()
+        evalfmt.map_to_image(b, g[f"img{i}.scale"], g[f"img{i}.offset"], w, h)
+        np.testing.assert_array_equal(b, g[f"img{i}.mapped"])
+        rows += evalfmt.coco_result_rows(1000 + i, b, g[f"img{i}.scores"], g[f"img{i}.cls"], class_ids)
+        per_cls = evalfmt.voc_class_dets(b, g[f"img{i}.scores"], g[f"img{i}.cls"], len(labelmap))
+        for c, d in zip(labelmap, per_cls):
+            assert d.dtype == np.float32 and d.shape[1] == 5
+            voc[c] += "".join(evalfmt.voc_result_lines(f"{i + 1:06d}", d))
+    assert rows == json.loads(str(g["coco_json"]))
+    for c in labelmap:
+        assert voc[c] == str(g[f"voc.{c}"]), c
