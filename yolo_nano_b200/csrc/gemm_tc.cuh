@@ -68,6 +68,8 @@ struct TcGemmParams {
   int nmain;              // main accumulators (round-robin over K steps), 1..4
   int nacc;               // accumulators per stage = nmain + (parity mode ? 1 correction : 0)
   int merge_corr;         // parity mode, shallow K: corrections go into the single main accumulator (nacc = 1)
+  int ksub;               // pointwise: valid 8-float K sub-steps = ceil(K / 8) (sub-steps made only of zero padding are
+                          // not issued: K = 116 needs 15 of 16, K = 232 29 of 32, K = 24 3 of 4); 0 = all
   int presplit;           // parity mode, 3x3: A arrives as two planes (hi, lo) written by the producer kernel —
                           // two TMA boxes per step, no splitter pass (tmAlo)
   int stack_b;            // parity mode, nmain = 1, 2*Npad <= 256: a_hi x [b_hi; b_lo] as ONE MMA of N = 2*Npad
@@ -296,8 +298,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t a_lo = ptx::smem_u32(stage_alo(s));
           const uint32_t b_hi = ptx::smem_u32(w_hi_ptr(s, st));
           const uint32_t b_lo = ptx::smem_u32(w_lo_ptr(s, st));
+          const int nk = p.ksub > 0 ? min(kTcBK / 8, p.ksub - st * (kTcBK / 8)) : kTcBK / 8;
 #pragma unroll
           for (int k = 0; k < kTcBK / 8; ++k, ++t) {
+            if (k >= nk) break;
             const uint32_t ko = k * 32;   // 8 tf32 = 32 bytes inside the 128-byte swizzled row
             const uint64_t da = ptx::make_sw128_kmajor_desc(a_hi + ko);
             const uint64_t db = ptx::make_sw128_kmajor_desc(b_hi + ko);

@@ -461,6 +461,7 @@ struct Planner {
     p.is3x3 = 0;
     p.num_steps = pc.tc.Kpad / kTcBK;
     p.chunks_per_tap = p.num_steps;
+    p.ksub = (pc.ktot + 7) / 8;
     p.M = M;
     p.num_tiles = (M + kTcBM - 1) / kTcBM;
     p.N = pc.n; p.Npad = pc.tc.Npad;
@@ -1372,7 +1373,7 @@ YNB_EXPORT int ynb_pwconv_tc(const float* in, int32_t in_ld, int32_t in_off, flo
   L.w = &t;
   TcGemmParams& p = L.p;
   memset(&p, 0, sizeof(p));
-  p.mode = mode; p.num_steps = t.Kpad / kTcBK; p.chunks_per_tap = p.num_steps;
+  p.mode = mode; p.num_steps = t.Kpad / kTcBK; p.chunks_per_tap = p.num_steps; p.ksub = (cin + 7) / 8;
   p.M = pixels; p.num_tiles = (pixels + kTcBM - 1) / kTcBM; p.N = cout; p.Npad = t.Npad;
   tc_plan_tmem(p);
   p.a_box_bytes = kTcAStageBytes;
