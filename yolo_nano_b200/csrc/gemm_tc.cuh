@@ -47,6 +47,7 @@ namespace ynb {
 
 constexpr int kTcThreads = 512;
 constexpr int kTcSplitWarp0 = 8, kTcProducerWarp = 12, kTcMmaWarp = 13;   // warps 0-7: two epilogue groups
+constexpr int kTcProducers = 3;                                            // producer roles: warps 12, 14, 15
 constexpr int kTcBM = 128;
 constexpr int kTcBK = 32;                       // floats per K chunk = 128 bytes
 constexpr int kTcAStageBytes = kTcBM * 128;     // 16 KB
@@ -164,6 +165,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
 
   const bool split = p.mode == YNB_GEMM_TC_3XTF32;
+  // TMA boxes per K step: A (hi) [, A_lo when pre-split] [, W_hi [, W_lo] when W is streamed].  Issuing a
+  // box costs the issuing thread ~600 cycles whatever its size (tools/tma_probe.cu), and that cost
+  // overlaps across warps (1 issuer 27 B/clk/SM, 2: 54, 4: 104) — so the boxes of a step are spread over
+  // up to three producer warps instead of being issued one after the other by one.
+  const int box_alo = p.presplit ? 1 : -1;
+  const int box_whi = p.w_resident ? -1 : 1 + (p.presplit ? 1 : 0);
+  const int box_wlo = (p.w_resident || !split) ? -1 : box_whi + 1;
+  const int nboxes = 1 + (box_alo >= 0) + (box_whi >= 0) + (box_wlo >= 0);
+  const int nprod = nboxes < kTcProducers ? nboxes : kTcProducers;
   const TcSmemLayout lay = tc_smem_layout(p.Npad, p.num_steps, p.num_stages, p.w_resident != 0, split);
   const uint32_t w_chunk_bytes = lay.w_chunk_bytes;
   const uint32_t a_bytes = kTcAStageBytes * (split ? 2 : 1);
@@ -189,7 +199,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (split) ptx::prefetch_tmap(&tmWlo);
     if (p.tma_store) ptx::prefetch_tmap(&tmOut);
     for (int s = 0; s < p.num_stages; ++s) {
-      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&full[s], nprod);   // one arrive.expect_tx per producer role
       ptx::mbar_init(&ready[s], 4);      // one arrival per splitter warp
       ptx::mbar_init(&empty[s], 1);
     }
@@ -235,9 +245,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   pdl_wait();
 
-  if (warp == kTcProducerWarp) {
-    // ================= TMA producer =================
-    if (lane == 0) {
+  const int prole = warp == kTcProducerWarp ? 0 : (warp == 14 ? 1 : (warp == 15 ? 2 : -1));
+  if (prole >= 0) {
+    // ================= TMA producers (role r issues the boxes j with j % nprod == r) =================
+    if (lane == 0 && prole < nprod) {
+      const bool do_a = 0 % nprod == prole;
+      const bool do_alo = box_alo >= 0 && box_alo % nprod == prole;
+      const bool do_whi = box_whi >= 0 && box_whi % nprod == prole;
+      const bool do_wlo = box_wlo >= 0 && box_wlo % nprod == prole;
+      const uint32_t my_tx = (do_a ? p.a_box_bytes : 0u) + (do_alo ? p.a_box_bytes : 0u) +
+                             (do_whi ? w_chunk_bytes : 0u) + (do_wlo ? w_chunk_bytes : 0u);
       int s = 0;
       uint32_t ph = 0;
       bool ok = true;
@@ -253,20 +270,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int st = 0; st < p.num_steps; ++st) {
           ok = ptx::mbar_wait(&empty[s], ph ^ 1, p.err_flag, 1);
           if (!ok) break;
-          ptx::mbar_arrive_expect_tx(&full[s], step_tx);
+          ptx::mbar_arrive_expect_tx(&full[s], my_tx);
           if (p.is3x3) {
             int tap = st / p.chunks_per_tap, kc = st - tap * p.chunks_per_tap;
             int dy = tap / 3, dx = tap - dy * 3;
-            ptx::tma_load_4d(stage_a(s), &tmA, &full[s], kc * kTcBK, x0 + dx - 1, y0 + dy - 1, b);
-            if (p.presplit) ptx::tma_load_4d(stage_alo(s), &tmAlo, &full[s], kc * kTcBK, x0 + dx - 1, y0 + dy - 1, b);
+            if (do_a) ptx::tma_load_4d(stage_a(s), &tmA, &full[s], kc * kTcBK, x0 + dx - 1, y0 + dy - 1, b);
+            if (do_alo) ptx::tma_load_4d(stage_alo(s), &tmAlo, &full[s], kc * kTcBK, x0 + dx - 1, y0 + dy - 1, b);
           } else {
-            ptx::tma_load_2d(stage_a(s), &tmA, &full[s], st * kTcBK, (int)(tile * kTcBM));
+            if (do_a) ptx::tma_load_2d(stage_a(s), &tmA, &full[s], st * kTcBK, (int)(tile * kTcBM));
           }
-          if (!p.w_resident) {
-            ptx::tma_load_2d(w_hi_ptr(s, st), &tmWhi, &full[s], st * kTcBK, 0);
-            if (split) ptx::tma_load_2d(w_lo_ptr(s, st), &tmWlo, &full[s], st * kTcBK, 0);
-          }
-          YNB_TRACE(1, tile, st);
+          if (do_whi) ptx::tma_load_2d(w_hi_ptr(s, st), &tmWhi, &full[s], st * kTcBK, 0);
+          if (do_wlo) ptx::tma_load_2d(w_lo_ptr(s, st), &tmWlo, &full[s], st * kTcBK, 0);
+          if (prole == 0) YNB_TRACE(1, tile, st);
           if (++s == p.num_stages) { s = 0; ph ^= 1; }
         }
       }
