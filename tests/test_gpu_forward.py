@@ -369,3 +369,24 @@ def test_tta_driver_against_reference_driver(G, golden):
         unmatched += d > 0.3
     print(f"[report] TTA: {unmatched} of {len(gb)} reference boxes without a match within 0.3 px")
     assert unmatched <= 0.01 * len(gb) + 2
+
+
+def test_detect_is_deterministic_and_batch_independent(G):
+    """The NMS build appends suppressor-list entries with atomics (arbitrary order); the result must not
+    depend on it: two runs of a 16-image batch are bit-identical, and image i of the batch equals the
+    same image run alone (the defined batch semantics, SURVEY 8c hazard 4)."""
+    sd = W.reference_init(80, seed=3)
+    x = W.synthetic_input(16, 416, 11).to(G.DEV)
+    eng = G.make_engine(sd, 416, 80, "3xtf32", max_batch=16)
+    a = [t.clone() for t in eng.forward_detect(x)]
+    b = [t.clone() for t in eng.forward_detect(x)]
+    c = [t.clone() for t in eng.forward_detect(x)]          # third call: CUDA-graph replay
+    for u, v, w_ in zip(a, b, c):
+        assert torch.equal(u, v) and torch.equal(u, w_)
+    for i in (0, 7, 15):
+        one = eng.forward_detect(x[i:i + 1].contiguous())
+        k = int(one[3][0])
+        assert k == int(a[3][i])
+        for u, v in zip(one[:3], a[:3]):
+            assert torch.equal(u[0, :k], v[i, :k])
+    eng.close()
