@@ -424,4 +424,4 @@ def test_raw_outputs_at_baseline_size_calibrated_reported(G):
               f"vs fp64 {b[0]:.2f} tol ({b[1]} over); fp32 oracle vs fp64 {o64[0]:.2f} tol")
     assert res["ffma"][0][1] == 0                                  # true fp32: inside the bar
     w, v, n = res["3xtf32"][0]
-    assert v <= 2e-5 * n and w < 2.0                               # parity mode: a few per million, < 2x tol
+    assert v <= 5e-5 * n and w < 2.0                               # parity mode: a few per 100 k, < 2x tol
