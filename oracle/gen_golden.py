@@ -299,6 +299,78 @@ def evalfmt_golden():
     print("g6", len(json.loads(coco_json)), "coco rows;", {k: len(v.splitlines()) for k, v in voc_files.items()})
 
 
+def train_labels(batch: int, seed: int):
+    """Synthetic normalised labels [[xmin,ymin,xmax,ymax,cls],...] per image: random boxes plus the
+    edge cases of tools.py:97-216 (a 'dirty' sub-pixel box, two boxes on the same cell/anchor, a
+    box matching several anchors -> ignored (-1) entries, a box with no anchor above the threshold)."""
+    rng = np.random.RandomState(seed)
+    out = []
+    for b in range(batch):
+        labs = []
+        for _ in range(6):
+            cx, cy = rng.uniform(0.15, 0.85, 2)
+            w, h = rng.uniform(0.05, 0.6, 2)
+            labs.append([max(cx - w / 2, 0.0), max(cy - h / 2, 0.0), min(cx + w / 2, 1.0), min(cy + h / 2, 1.0),
+                         float(rng.randint(0, 20))])
+        labs.append([0.5, 0.5, 0.503, 0.7, 3.0])                 # dirty: narrower than one pixel
+        labs.append([0.30, 0.30, 0.52, 0.50, 7.0])               # same cell and anchor ...
+        labs.append([0.305, 0.305, 0.525, 0.505, 9.0])           # ... the later one wins
+        labs.append([0.1, 0.4, 0.9, 0.45, 11.0])                 # extreme aspect: no anchor above 0.5
+        labs.append([0.109375, 0.03125, 0.890625, 0.96875, 13.0])  # 100x120 px at 128: three anchors > 0.5
+        labs.append([0.2, 0.1, 0.2 + 60 / 128, 0.1 + 90 / 128, 2.0])  # 60x90 px: two anchors > 0.5
+        out.append(labs)
+    return out
+
+
+def train_golden():
+    """g7: the reference's training branch at the head boundary: targets from
+    tools.multi_gt_creator, the four losses of forward(x, target) with trainable=True (BN in eval
+    mode so that the network part is the inference network), d(total)/d(raw head maps)."""
+    from oracle import weights as W
+    YOLONano, config, _ = _import_reference()
+    import tools  # type: ignore  (reference)
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    size, classes, batch, seed = 128, 20, 2, 7
+    sd = W.calibrated(classes, seed=seed)
+    m = _build(YOLONano, size, classes, config.MULTI_ANCHOR_SIZE, sd=sd)
+    m.trainable = True           # constructing with trainable=True would download weights (:32)
+    x = W.synthetic_input(batch, size, seed=seed)
+    labels = train_labels(batch, seed)
+    target = tools.multi_gt_creator(size, m.stride, labels, anchor_size=config.MULTI_ANCHOR_SIZE)
+    rec = {}
+    hooks = []
+    for name, mod in (("pred_s", m.head_det_1), ("pred_m", m.head_det_2), ("pred_l", m.head_det_3)):
+        def f(_mod, _inp, out, name=name):
+            out.retain_grad()
+            rec[name] = out
+        hooks.append(mod.register_forward_hook(f))
+    ls = m(x, target=target)
+    sum(ls).backward()
+    for h in hooks:
+        h.remove()
+    out = {"target": target.numpy(), "losses": np.array([float(v.detach()) for v in ls], dtype=np.float32)}
+    for k, v in rec.items():
+        out[k] = v.detach().numpy().copy()
+        out["grad_" + k] = v.grad.numpy().copy()
+    lab = np.full((batch, max(len(l) for l in labels), 5), -1.0, dtype=np.float64)
+    for b, l in enumerate(labels):
+        lab[b, :len(l)] = np.asarray(l)
+    # one torch.optim.SGD step (train.py:167-171) on a flat vector, twice (first step / momentum)
+    g = torch.Generator().manual_seed(seed)
+    p0 = torch.randn(20011, generator=g)
+    g1, g2 = torch.randn(20011, generator=g) * 0.1, torch.randn(20011, generator=g) * 0.1
+    prm = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.SGD([prm], lr=1e-3, momentum=0.9, weight_decay=5e-4)
+    prm.grad = g1.clone(); opt.step()
+    p1 = prm.detach().clone()
+    prm.grad = g2.clone(); opt.step()
+    np.savez_compressed(OUT / "g7_train128.npz", size=size, classes=classes, seed=seed, labels=lab,
+                        n_labels=np.array([len(l) for l in labels]), sd_digest=W.digest(sd), x_digest=W.digest(x),
+                        sgd_p0=p0.numpy(), sgd_g1=g1.numpy(), sgd_g2=g2.numpy(), sgd_p1=p1.numpy(),
+                        sgd_p2=prm.detach().numpy(), torch=torch.__version__, numpy=np.__version__, **out)
+    print("g7 losses", out["losses"], "positives", int((target[:, :, 0] > 0).sum()), "ignored", int((target[:, :, 0] < 0).sum()))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "evalfmt":
         evalfmt_golden()
@@ -306,8 +378,11 @@ if __name__ == "__main__":
         preprocess_golden()
     elif len(sys.argv) > 1 and sys.argv[1] == "tta":
         tta_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == "train":
+        train_golden()
     else:
         main()
         preprocess_golden()
         tta_golden()
         evalfmt_golden()
+        train_golden()

@@ -1,0 +1,42 @@
+"""Pins oracle/train_oracle.py (training branch at the head boundary) against
+g7_train128.npz recorded from the REAL reference (oracle/gen_golden.py train).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import train_oracle as T
+from oracle import weights as W
+
+
+@pytest.fixture(scope="module")
+def g7(golden):
+    return golden("g7_train128.npz")
+
+
+def _labels(g7):
+    return [[list(r) for r in g7["labels"][b][: int(g7["n_labels"][b])]] for b in range(len(g7["n_labels"]))]
+
+
+def test_target_assignment_matches_reference(g7):
+    """tools.multi_gt_creator: positives, ignored (-1) anchors, dirty boxes, overwrite order."""
+    t = T.multi_gt_creator(int(g7["size"]), _labels(g7), W.anchors_for(int(g7["classes"])))
+    want = g7["target"]
+    assert (want[:, :, 0] < 0).sum() > 0 and (want[:, :, 0] > 0).sum() > 0
+    np.testing.assert_array_equal(t.numpy(), want)
+
+
+def test_losses_and_head_gradients_match_reference(g7):
+    preds = [torch.from_numpy(g7[k]) for k in ("pred_s", "pred_m", "pred_l")]
+    ls, grads = T.losses_and_grads(preds, torch.from_numpy(g7["target"]), int(g7["size"]), int(g7["classes"]),
+                                   W.anchors_for(int(g7["classes"])))
+    np.testing.assert_allclose(np.array(ls, dtype=np.float32), g7["losses"], rtol=1e-6)
+    for k, g in zip(("pred_s", "pred_m", "pred_l"), grads):
+        np.testing.assert_allclose(g.numpy(), g7["grad_" + k], rtol=1e-5, atol=1e-8, err_msg=k)
+
+
+def test_sgd_step_matches_torch_optim(g7):
+    p0, g1, g2 = (torch.from_numpy(g7[k]) for k in ("sgd_p0", "sgd_g1", "sgd_g2"))
+    p1, buf = T.sgd_step(p0, g1, None, 1e-3)
+    np.testing.assert_array_equal(p1.numpy(), g7["sgd_p1"])
+    p2, _ = T.sgd_step(p1, g2, buf, 1e-3)
+    np.testing.assert_array_equal(p2.numpy(), g7["sgd_p2"])

@@ -6,13 +6,14 @@
 #include "ptx_sm100.cuh"
 using namespace ynb;
 
-__global__ void __launch_bounds__(128) mma_rate_kernel(int N, int iters, int nacc, long long* out) {
+__global__ void __launch_bounds__(128) mma_rate_kernel(int N, int iters, int nacc, long long* out, int commit_every) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t bar;
+  __shared__ uint64_t bar2[4];
   __shared__ uint32_t tmem_ptr;
   for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 0.0f;
-  if (threadIdx.x == 0) { ptx::mbar_init(&bar, 1); ptx::fence_barrier_init(); }
+  if (threadIdx.x == 0) { ptx::mbar_init(&bar, 1); for (int i = 0; i < 4; ++i) ptx::mbar_init(&bar2[i], 1); ptx::fence_barrier_init(); }
   if (threadIdx.x < 32) { ptx::tmem_alloc(&tmem_ptr, 512); ptx::tmem_relinquish(); }
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before_sync();
@@ -27,6 +28,7 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int N, int iters, int nac
       const uint32_t ko = (i & 3) * 32;
       ptx::mma_tf32_ss(tmem + (uint32_t)((i % nacc) * N), ptx::make_sw128_kmajor_desc(a + ko),
                        ptx::make_sw128_kmajor_desc(b + ko), idesc, i >= nacc);
+      if (commit_every > 0 && (i + 1) % commit_every == 0) ptx::mma_commit(&bar2[(i / commit_every) & 3]);   // nobody waits
     }
     ptx::mma_commit(&bar);
     while (!ptx::mbar_try_wait(&bar, 0)) {}
@@ -46,7 +48,7 @@ int main() {
     for (int N : {64, 96, 128, 256}) {
       for (int nacc : {1, 2}) {
         if (nacc * N > 512) continue;
-        mma_rate_kernel<<<grid, 128, 64 * 1024>>>(N, iters, nacc, d);
+        mma_rate_kernel<<<grid, 128, 64 * 1024>>>(N, iters, nacc, d, 0);
         cudaError_t e = cudaDeviceSynchronize();
         long long cyc = 0; cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
         const double per = (double)cyc / iters;
@@ -54,6 +56,12 @@ int main() {
                grid, N, nacc, per, N, 2.0 * 128 * N * 8 / per * 148 * 1.9e9 / 1e12, cudaGetErrorString(e));
       }
     }
+  }
+  for (int ce : {0, 16, 8, 4, 2, 1}) {
+    mma_rate_kernel<<<148, 128, 64 * 1024>>>(128, iters, 2, d, ce);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long cyc = 0; cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
+    printf("N=128, tcgen05.commit every %2d MMAs: %7.1f cycles per MMA  [%s]\n", ce, (double)cyc / iters, cudaGetErrorString(e));
   }
   return 0;
 }
