@@ -271,6 +271,74 @@ int  ynb_nms_grid(const float* boxes_dev, const float* scores_dev, const int32_t
                   int32_t* out_counts_dev, uint8_t* keep_dev,
                   void* workspace_dev, int64_t workspace_bytes, void* stream);
 
+/* ---- training branch at the head boundary (BASELINE config 5) -----------
+ * What is here: target assignment, the four losses with their gradient w.r.t. the raw head maps, the
+ * SGD update, and the backward kernels of the depthwise / pointwise convolutions and activations, each
+ * individually callable.  What is NOT here: BatchNorm in training mode (batch statistics) and the
+ * chaining of these kernels into YOLONano.forward(x, target) — that call raises NotImplementedError. */
+
+/* tools.multi_gt_creator (tools.py:97-216) on the device.  labels_dev [B, max_labels, 5] float32 =
+ * xmin, ymin, xmax, ymax normalised to [0,1], class; counts_dev [B] int32 (NULL: all max_labels rows
+ * are valid).  Writes target_dev [B, N, 11] float32 = obj (1 / 0 / -1 ignored), class, tx, ty, tw, th,
+ * box-scale weight, x1, y1, x2, y2, rows in the anchor order of ynb_forward_decode.  Labels are applied
+ * in order (a later label overwrites an earlier one on the same cell / anchor); float64 arithmetic in
+ * the reference's operation order.  anchors_wh: host, [3][A][2] pixels. */
+int  ynb_build_targets(const float* labels_dev, const int32_t* counts_dev, int32_t batch, int32_t max_labels,
+                       int32_t input_size, const float* anchors_wh, int32_t num_anchors, float* target_dev,
+                       void* stream);
+
+/* The training branch of YOLONano.forward after the heads (models/yolo_nano.py:333-358): box decode
+ * (no clamp) / input_size, tools.iou_score (tools.py:219-233) against the target boxes, the detached
+ * IoU as objectness label, tools.loss (tools.py:236-276, MSEWithLogitsLoss :12-34).
+ * raw_*_dev: NHWC [B, H*W, raw_ld] raw head maps of the three levels with the reference channel map
+ * (as ynb_decode_level); target_dev [B, N, 11].  Outputs: losses_dev [4] = conf, cls, bbox (txty +
+ * twth), iou, each already divided by the batch size; grad_*_dev (same layout as raw_*) =
+ * d(conf + cls + bbox + iou) / d raw, the quantity train.py:222-229 back-propagates into the heads.
+ * Deterministic (two-stage reduction).  workspace_dev: ynb_train_loss_workspace_bytes() bytes. */
+int64_t ynb_train_loss_workspace_bytes(void);
+int  ynb_train_loss(const float* raw_s_dev, const float* raw_m_dev, const float* raw_l_dev, int32_t raw_ld,
+                    const float* target_dev, int32_t batch, int32_t input_size, const float* anchors_wh,
+                    int32_t num_anchors, int32_t num_classes, float* losses_dev, float* grad_s_dev,
+                    float* grad_m_dev, float* grad_l_dev, void* workspace_dev, int64_t workspace_bytes,
+                    void* stream);
+
+/* One torch.optim.SGD step (train.py:167-171,230) over a flat float32 vector of n elements:
+ *   d = grad_scale * g + weight_decay * p;  buf = first_step ? d : momentum * buf + d;  p -= lr * buf.
+ * grad_scale = 1 / world_size folds the averaging of the data-parallel all-reduce into the
+ * update; with grad_scale == 1 the result is bit-identical to the CPU optimiser.  16-byte aligned buffers. */
+int  ynb_sgd_step(float* params_dev, const float* grads_dev, float* momentum_buf_dev, int64_t n, float lr,
+                  float momentum, float weight_decay, int32_t first_step, float grad_scale, void* stream);
+
+/* Backward of ynb_dwconv3x3 (depthwise 3x3, pad 1, stride 1|2; backbone/shufflenetv2.py:66-67,
+ * models/yolo_nano.py:51) without its activation.  w_dev [9][C] as in the forward.
+ *   d_in[b,yi,xi,c] = sum_t w[t][c] * d_out[b,(yi+1-dy)/s,(xi+1-dx)/s,c]  */
+int  ynb_dwconv3x3_bwd_data(const float* dout_dev, int32_t dout_ld, int32_t dout_off,
+                            float* din_dev, int32_t din_ld, int32_t din_off, const float* w_dev,
+                            int32_t batch, int32_t h_in, int32_t w_in, int32_t channels, int32_t stride,
+                            void* stream);
+/* dwdb_dev [10][C]: rows 0..8 = d w[t][c] = sum d_out * in(shifted by tap t), row 9 = d bias[c]. */
+int64_t ynb_dwconv3x3_bwd_weight_workspace_bytes(int32_t batch, int32_t h_in, int32_t channels, int32_t stride);
+int  ynb_dwconv3x3_bwd_weight(const float* dout_dev, int32_t dout_ld, int32_t dout_off,
+                              const float* in_dev, int32_t in_ld, int32_t in_off, float* dwdb_dev,
+                              int32_t batch, int32_t h_in, int32_t w_in, int32_t channels, int32_t stride,
+                              void* workspace_dev, int64_t workspace_bytes, void* stream);
+
+/* Backward of the pointwise conv (ynb_pwconv) w.r.t. weights and bias:
+ *   dw[n][k] = sum_m d_out[m, dout_off + n] * in[m, in_off + k];  db[n] = sum_m d_out[m, dout_off + n].
+ * (The gradient w.r.t. the input is the forward GEMM with the transposed weight matrix and no bias:
+ * ynb_pwconv / ynb_pwconv_tc.)  Deterministic split-M reduction. */
+int64_t ynb_pwconv_bwd_weight_workspace_bytes(int64_t pixels, int32_t cin, int32_t cout);
+int  ynb_pwconv_bwd_weight(const float* dout_dev, int32_t dout_ld, int32_t dout_off,
+                           const float* in_dev, int32_t in_ld, int32_t in_off, float* dw_dev, float* db_dev,
+                           int64_t pixels, int32_t cin, int32_t cout,
+                           void* workspace_dev, int64_t workspace_bytes, void* stream);
+
+/* Backward of ReLU / LeakyReLU(0.1) (YNB_ACT_RELU | YNB_ACT_LEAKY) from the forward OUTPUT:
+ *   dpre[m, c] = dout[m, c] * (out[m, c] > 0 ? 1 : slope). */
+int  ynb_act_bwd(const float* dout_dev, int32_t dout_ld, int32_t dout_off, const float* out_dev, int32_t out_ld,
+                 int32_t out_off, float* dpre_dev, int32_t dpre_ld, int32_t dpre_off, int64_t pixels,
+                 int32_t channels, int32_t act, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -318,7 +318,9 @@ def train_labels(batch: int, seed: int):
         labs.append([0.1, 0.4, 0.9, 0.45, 11.0])                 # extreme aspect: no anchor above 0.5
         labs.append([0.109375, 0.03125, 0.890625, 0.96875, 13.0])  # 100x120 px at 128: three anchors > 0.5
         labs.append([0.2, 0.1, 0.2 + 60 / 128, 0.1 + 90 / 128, 2.0])  # 60x90 px: two anchors > 0.5
-        out.append(labs)
+        # the data loader hands the labels over as float32 tensors (train.py:211): keep the fixture on
+        # float32-representable values so that the device entry (float32 labels) sees the same numbers
+        out.append([[float(np.float32(v)) for v in lab] for lab in labs])
     return out
 
 

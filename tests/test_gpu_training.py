@@ -1,0 +1,179 @@
+"""Training branch at the head boundary through the C ABI on a real
+B200, against the oracle restatement (oracle/train_oracle.py) and the fixture recorded from the REAL
+reference (tests/golden/g7_train128.npz)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import train_oracle as T  # noqa: E402
+from oracle import weights as W  # noqa: E402
+
+# float32 tolerances of this stage: the losses are sums of 1e3..1e5 float32 terms (torch sums in
+# float32, the kernel combines block partials in float64); gradients are per-element closed forms
+# (expf / logf / division rounding differences only).
+LOSS_RTOL = 2e-5
+GRAD_RTOL, GRAD_ATOL = 2e-5, 2e-8
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpu_util
+    return gpu_util
+
+
+@pytest.fixture(scope="module")
+def TR():
+    from yolo_nano_b200 import training
+    return training
+
+
+@pytest.fixture(scope="module")
+def g7(golden):
+    return golden("g7_train128.npz")
+
+
+def _nhwc_maps(preds, ld, dev):
+    out = []
+    for p in preds:
+        b, ch, h, w = p.shape
+        m = torch.zeros(b, h * w, ld)
+        m[:, :, :ch] = p.permute(0, 2, 3, 1).reshape(b, h * w, ch)
+        out.append(m.to(dev))
+    return out
+
+
+def _nchw_grads(grads, preds):
+    out = []
+    for g, p in zip(grads, preds):
+        b, ch, h, w = p.shape
+        out.append(g.cpu()[:, :, :ch].reshape(b, h, w, ch).permute(0, 3, 1, 2).numpy())
+    return out
+
+
+def _labels_f32(g7):
+    lab = g7["labels"].astype(np.float32)
+    return lab, g7["n_labels"].astype(np.int32)
+
+
+def test_build_targets_matches_reference_fixture(G, TR, g7):
+    """tools.multi_gt_creator on the device: positives, ignored (-1), dirty boxes, overwrite order."""
+    lab, cnt = _labels_f32(g7)
+    size, classes = int(g7["size"]), int(g7["classes"])
+    got = TR.build_targets(torch.from_numpy(lab).to(G.DEV), torch.from_numpy(cnt).to(G.DEV), size,
+                           W.anchors_for(classes)).cpu().numpy()
+    assert np.array_equal(lab.astype(np.float64), g7["labels"])      # the fixture's labels are float32 values
+    lists = [[[float(v) for v in lab[b, i]] for i in range(cnt[b])] for b in range(len(cnt))]
+    want = T.multi_gt_creator(size, lists, W.anchors_for(classes)).numpy()
+    assert (want[:, :, 0] > 0).sum() >= 16 and (want[:, :, 0] < 0).sum() > 0
+    np.testing.assert_array_equal(got[:, :, [0, 1]], want[:, :, [0, 1]])           # obj / class: exact
+    np.testing.assert_allclose(got, want, rtol=2e-7, atol=1e-7)                      # double log -> float32
+    # and against the REAL reference's tools.multi_gt_creator on the same labels
+    np.testing.assert_array_equal(got[:, :, [0, 1]], g7["target"][:, :, [0, 1]])
+    np.testing.assert_allclose(got, g7["target"], rtol=2e-7, atol=1e-7)
+
+
+@pytest.mark.parametrize("ld", [76, 80])
+def test_train_loss_matches_reference_fixture(G, TR, g7, ld):
+    """Losses and d(total)/d(raw head maps) against the REAL reference's forward(x, target) + backward."""
+    size, classes = int(g7["size"]), int(g7["classes"])
+    preds = [torch.from_numpy(g7[k]) for k in ("pred_s", "pred_m", "pred_l")]
+    raw = _nhwc_maps(preds, ld, G.DEV)
+    losses, grads = TR.train_loss(raw, torch.from_numpy(g7["target"]).to(G.DEV), size, classes, W.anchors_for(classes))
+    np.testing.assert_allclose(losses.cpu().numpy(), g7["losses"], rtol=LOSS_RTOL)
+    for k, got in zip(("pred_s", "pred_m", "pred_l"), _nchw_grads(grads, preds)):
+        np.testing.assert_allclose(got, g7["grad_" + k], rtol=GRAD_RTOL, atol=GRAD_ATOL, err_msg=k)
+    for g in grads:                                   # padding channels of the gradient map are zero
+        if ld > preds[0].shape[1]:
+            assert float(g[:, :, preds[0].shape[1]:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("size,classes,batch", [(416, 80, 4), (320, 20, 3)])
+def test_train_loss_matches_oracle_at_baseline_shape(G, TR, size, classes, batch):
+    """Config-5 shape (416^2, COCO-80): random logits, targets from random labels; oracle = autograd."""
+    torch.manual_seed(size + classes)
+    rng = np.random.RandomState(size)
+    anchors = W.anchors_for(classes)
+    labels = []
+    for b in range(batch):
+        labs = []
+        for _ in range(12):
+            cx, cy = rng.uniform(0.1, 0.9, 2)
+            w, h = rng.uniform(0.02, 0.7, 2)
+            labs.append([float(np.float32(v)) for v in (max(cx - w / 2, 0), max(cy - h / 2, 0), min(cx + w / 2, 1),
+                                                         min(cy + h / 2, 1))] + [float(rng.randint(0, classes))])
+        labels.append(labs)
+    target = T.multi_gt_creator(size, labels, anchors)
+    ch = 3 * (1 + classes + 4)
+    preds = [torch.randn(batch, ch, size // s, size // s) * 1.5 for s in (8, 16, 32)]
+    want_l, want_g = T.losses_and_grads(preds, target, size, classes, anchors)
+    raw = _nhwc_maps(preds, (ch + 3) // 4 * 4, G.DEV)
+    losses, grads = TR.train_loss(raw, target.to(G.DEV), size, classes, anchors)
+    np.testing.assert_allclose(losses.cpu().numpy(), np.array(want_l, dtype=np.float32), rtol=LOSS_RTOL)
+    for lvl, (got, want) in enumerate(zip(_nchw_grads(grads, preds), want_g)):
+        np.testing.assert_allclose(got, want.numpy(), rtol=GRAD_RTOL, atol=GRAD_ATOL, err_msg=f"level {lvl}")
+    # deterministic: a second run gives bit-identical losses and gradients
+    losses2, grads2 = TR.train_loss(raw, target.to(G.DEV), size, classes, anchors)
+    assert torch.equal(losses, losses2) and all(torch.equal(a, b) for a, b in zip(grads, grads2))
+
+
+def test_sgd_step_bit_exact(G, TR, g7):
+    """torch.optim.SGD(momentum 0.9, weight decay 5e-4), two steps, vs the recorded CPU optimiser."""
+    p = torch.from_numpy(g7["sgd_p0"]).to(G.DEV)
+    opt = TR.FlatSGD(p, lr=1e-3)
+    opt.step(torch.from_numpy(g7["sgd_g1"]).to(G.DEV))
+    np.testing.assert_array_equal(p.cpu().numpy(), g7["sgd_p1"])
+    opt.step(torch.from_numpy(g7["sgd_g2"]).to(G.DEV))
+    np.testing.assert_array_equal(p.cpu().numpy(), g7["sgd_p2"])
+    with pytest.raises(Exception):
+        TR.FlatSGD(torch.zeros(8), lr=0.1)            # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("batch,ch,hw,stride", [(2, 58, 52, 1), (2, 58, 104, 2), (3, 116, 26, 1), (2, 232, 13, 1),
+                                                (2, 24, 104, 2), (4, 96, 13, 1), (1, 4, 3, 2), (1, 5, 7, 1)])
+def test_dwconv3x3_backward(G, TR, batch, ch, hw, stride):
+    torch.manual_seed(ch + hw)
+    x = torch.randn(batch, ch, hw, hw, requires_grad=True)
+    w = torch.randn(ch, 1, 3, 3, requires_grad=True)
+    b = torch.randn(ch, requires_grad=True)
+    y = F.conv2d(x, w, b, stride, 1, 1, ch)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    nhwc = lambda t: t.detach().permute(0, 2, 3, 1).contiguous().to(G.DEV)  # noqa: E731
+    dx, dw, db = TR.dwconv3x3_backward(nhwc(dy), nhwc(x), w.detach().view(ch, 9).t().contiguous().to(G.DEV), stride)
+    torch.testing.assert_close(dx.cpu().permute(0, 3, 1, 2), x.grad, rtol=1e-5, atol=1e-5)
+    scale = float(w.grad.abs().max())
+    torch.testing.assert_close(dw.cpu().t().reshape(ch, 1, 3, 3), w.grad, rtol=1e-4, atol=1e-5 * scale)
+    torch.testing.assert_close(db.cpu(), b.grad, rtol=1e-4, atol=1e-5 * float(b.grad.abs().max()))
+
+
+@pytest.mark.parametrize("m,k,n", [(2 * 2704, 116, 116), (2 * 676, 232, 232), (338, 464, 96), (5408, 96, 256),
+                                   (1000, 24, 60), (33, 8, 4), (64 * 2704, 60, 60)])
+def test_pwconv_backward(G, TR, m, k, n):
+    torch.manual_seed(m + k + n)
+    x = torch.randn(m, k, requires_grad=True)
+    w = (torch.randn(n, k) / k ** 0.5).requires_grad_(True)
+    b = torch.randn(n, requires_grad=True)
+    y = F.linear(x, w, b)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    dw, db = TR.pwconv_backward_weight(dy.to(G.DEV), x.detach().to(G.DEV))
+    sw, sb = float(w.grad.abs().max()), float(b.grad.abs().max())
+    torch.testing.assert_close(dw.cpu(), w.grad, rtol=1e-4, atol=2e-5 * sw)
+    torch.testing.assert_close(db.cpu(), b.grad, rtol=1e-4, atol=2e-5 * sb)
+    for tc in (False, True):
+        dx = TR.pwconv_backward_data(dy.to(G.DEV), w.detach().to(G.DEV), tensor_cores=tc)
+        torch.testing.assert_close(dx.cpu(), x.grad, rtol=1e-4, atol=1e-4 * float(x.grad.abs().max()))
+
+
+@pytest.mark.parametrize("act", [1, 2])
+def test_act_backward(G, TR, act):
+    torch.manual_seed(act)
+    pre = torch.randn(777, 58, requires_grad=True)
+    out = F.relu(pre) if act == 1 else F.leaky_relu(pre, 0.1)
+    dy = torch.randn_like(out)
+    out.backward(dy)
+    got = TR.act_backward(dy.to(G.DEV), out.detach().to(G.DEV), act)
+    np.testing.assert_array_equal(got.cpu().numpy(), pre.grad.numpy())

@@ -66,3 +66,36 @@ def test_gather_world2_gloo(n_images):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _grad_worker(rank, world, port, q):
+    """Config 5: one all-reduce (sum) of the flat gradient; the 1/world is folded into
+    the SGD kernel on the device, here into the oracle update."""
+    from oracle import train_oracle as T
+    from yolo_nano_b200 import training as TR
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(100 + rank)
+    grad = torch.randn(1001, generator=g)
+    TR.allreduce_gradients(grad)
+    want = sum(torch.randn(1001, generator=torch.Generator().manual_seed(100 + r)) for r in range(world))
+    p0 = torch.randn(1001, generator=torch.Generator().manual_seed(7))
+    p1, _ = T.sgd_step(p0, grad * (1.0 / world), None, 1e-3)
+    ref, _ = T.sgd_step(p0, want * (1.0 / world), None, 1e-3)
+    q.put((rank, bool(torch.equal(grad, want)) and bool(torch.equal(p1, ref))))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2_gloo():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]

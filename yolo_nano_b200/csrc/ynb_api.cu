@@ -23,6 +23,7 @@
 #include "gemm_ffma.cuh"
 #include "gemm_tc.cuh"
 #include "kernels_basic.cuh"
+#include "train_ops.cuh"
 #include "topology.h"
 
 #define YNB_EXPORT extern "C" __attribute__((visibility("default")))
@@ -1477,5 +1478,165 @@ YNB_EXPORT int ynb_nms(const float* boxes, const float* scores, const int32_t* c
   NmsWorkspace w = nms_carve(ws, batch, n);
   UNIT_TRY(launch_nms(boxes, scores, cls, batch, n, num_classes, conf, thr, diou, ob, os, oc, on, keep, w,
                       (cudaStream_t)stream));
+  return YNB_OK;
+}
+
+// ---- training branch at the head boundary ------------------------------
+
+namespace {
+bool level_geometry(int input_size, int grid[3], int stride[3]) {
+  if (input_size <= 0 || input_size % 32) return false;
+  const int st[3] = {8, 16, 32};
+  for (int l = 0; l < 3; ++l) { stride[l] = st[l]; grid[l] = input_size / st[l]; }
+  return true;
+}
+}  // namespace
+
+YNB_EXPORT int64_t ynb_train_loss_workspace_bytes(void) { return (int64_t)kLossBlocks * 4 * sizeof(double); }
+
+YNB_EXPORT int ynb_train_loss(const float* raw_s, const float* raw_m, const float* raw_l, int32_t raw_ld,
+                              const float* target, int32_t batch, int32_t input_size, const float* anchors_wh,
+                              int32_t num_anchors, int32_t num_classes, float* losses, float* grad_s, float* grad_m,
+                              float* grad_l, void* ws, int64_t ws_bytes, void* stream) {
+  TrainLossParams p{};
+  if (!raw_s || !raw_m || !raw_l || !target || !anchors_wh || !losses || !grad_s || !grad_m || !grad_l || !ws ||
+      batch <= 0 || num_anchors <= 0 || num_anchors > kTrainMaxAnchors || num_classes <= 0 ||
+      raw_ld < num_anchors * (1 + num_classes + 4) || ws_bytes < ynb_train_loss_workspace_bytes() ||
+      !level_geometry(input_size, p.grid, p.stride))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_train_loss: bad arguments / workspace too small");
+  p.raw[0] = raw_s; p.raw[1] = raw_m; p.raw[2] = raw_l;
+  p.grad[0] = grad_s; p.grad[1] = grad_m; p.grad[2] = grad_l;
+  p.target = target; p.partials = (double*)ws; p.ld = raw_ld; p.B = batch; p.A = num_anchors; p.C = num_classes;
+  p.S = input_size;
+  int off = 0;
+  for (int l = 0; l < 3; ++l) {
+    p.cells[l] = p.grid[l] * p.grid[l];
+    p.cell_off[l] = off;
+    off += p.cells[l];
+    for (int a = 0; a < num_anchors; ++a) {
+      p.anchors[l][a][0] = anchors_wh[(l * num_anchors + a) * 2];
+      p.anchors[l][a][1] = anchors_wh[(l * num_anchors + a) * 2 + 1];
+    }
+  }
+  p.cells_total = off;
+  UNIT_TRY(launch_train_loss(p, losses, (cudaStream_t)stream));
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_build_targets(const float* labels, const int32_t* counts, int32_t batch, int32_t max_labels,
+                                 int32_t input_size, const float* anchors_wh, int32_t num_anchors, float* target,
+                                 void* stream) {
+  TargetParams p{};
+  if (!labels || !target || !anchors_wh || batch <= 0 || max_labels < 0 || num_anchors <= 0 ||
+      num_anchors > kTrainMaxAnchors || !level_geometry(input_size, p.grid, p.stride))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_build_targets: bad arguments");
+  p.labels = labels; p.counts = counts; p.target = target; p.B = batch; p.L = max_labels; p.A = num_anchors;
+  p.S = input_size;
+  long long off = 0;
+  for (int l = 0; l < 3; ++l) {
+    p.row_off[l] = off;
+    off += (long long)p.grid[l] * p.grid[l] * num_anchors;
+  }
+  p.N = off;
+  for (int k = 0; k < 3 * num_anchors; ++k) {
+    p.anchors[k][0] = (double)anchors_wh[2 * k];
+    p.anchors[k][1] = (double)anchors_wh[2 * k + 1];
+  }
+  UNIT_TRY(launch_build_targets(p, (cudaStream_t)stream));
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n, float lr,
+                            float momentum, float weight_decay, int32_t first_step, float grad_scale, void* stream) {
+  if (!params || !grads || !momentum_buf || n <= 0 || ((uintptr_t)params | (uintptr_t)grads | (uintptr_t)momentum_buf) % 16)
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_sgd_step: null / unaligned (16 B) buffers");
+  UNIT_TRY(launch_sgd_step(params, grads, momentum_buf, n, lr, momentum, weight_decay, first_step, grad_scale,
+                           (cudaStream_t)stream));
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_dwconv3x3_bwd_data(const float* dout, int32_t do_ld, int32_t do_off, float* din, int32_t di_ld,
+                                      int32_t di_off, const float* w, int32_t batch, int32_t h_in, int32_t w_in,
+                                      int32_t channels, int32_t stride, void* stream) {
+  if (!dout || !din || !w || batch <= 0 || h_in <= 0 || w_in <= 0 || channels <= 0 || (stride != 1 && stride != 2))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_dwconv3x3_bwd_data: bad arguments");
+  const long long total = (long long)batch * h_in * w_in * ((channels + 3) / 4);
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
+  dwconv3x3_bwd_data_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dout, do_ld, do_off, din, di_ld, di_off, w, batch,
+                                                                      h_in, w_in, channels, stride);
+  YNB_COUNT_LAUNCH();
+  UNIT_TRY(cudaGetLastError());
+  return YNB_OK;
+}
+
+YNB_EXPORT int64_t ynb_dwconv3x3_bwd_weight_workspace_bytes(int32_t batch, int32_t h_in, int32_t channels, int32_t stride) {
+  const int h_out = (h_in - 1) / stride + 1;
+  return (int64_t)dw_bwd_chunks(batch, h_out) * 10 * channels * sizeof(float);
+}
+
+YNB_EXPORT int ynb_dwconv3x3_bwd_weight(const float* dout, int32_t do_ld, int32_t do_off, const float* in, int32_t in_ld,
+                                        int32_t in_off, float* dwdb, int32_t batch, int32_t h_in, int32_t w_in,
+                                        int32_t channels, int32_t stride, void* ws, int64_t ws_bytes, void* stream) {
+  if (!dout || !in || !dwdb || !ws || batch <= 0 || h_in <= 0 || w_in <= 0 || channels <= 0 ||
+      (stride != 1 && stride != 2) || ws_bytes < ynb_dwconv3x3_bwd_weight_workspace_bytes(batch, h_in, channels, stride))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_dwconv3x3_bwd_weight: bad arguments / workspace too small");
+  const int h_out = (h_in - 1) / stride + 1;
+  const int chunks = dw_bwd_chunks(batch, h_out);
+  const long long rows = (long long)batch * h_out;
+  const int rows_per_chunk = (int)((rows + chunks - 1) / chunks);
+  dim3 grid(chunks, (channels + kDwBwdChan - 1) / kDwBwdChan), block(kDwBwdChan, kDwBwdSlices);
+  cudaStream_t st = (cudaStream_t)stream;
+  UNIT_TRY(cudaMemsetAsync(ws, 0, (size_t)chunks * 10 * channels * sizeof(float), st));
+  dwconv3x3_bwd_weight_kernel<<<grid, block, 0, st>>>(dout, do_ld, do_off, in, in_ld, in_off, (float*)ws, batch, h_in,
+                                                      w_in, channels, stride, rows_per_chunk);
+  YNB_COUNT_LAUNCH();
+  const long long elems = 10LL * channels;
+  reduce_partials_kernel<<<(int)((elems + 127) / 128), 128, 0, st>>>((const float*)ws, chunks, elems, dwdb);
+  YNB_COUNT_LAUNCH();
+  UNIT_TRY(cudaGetLastError());
+  return YNB_OK;
+}
+
+YNB_EXPORT int64_t ynb_pwconv_bwd_weight_workspace_bytes(int64_t pixels, int32_t cin, int32_t cout) {
+  return (int64_t)pw_bwd_chunks(pixels, cin, cout) * ((int64_t)cout * cin + cout) * sizeof(float);
+}
+
+YNB_EXPORT int ynb_pwconv_bwd_weight(const float* dout, int32_t do_ld, int32_t do_off, const float* in, int32_t in_ld,
+                                     int32_t in_off, float* dw, float* db, int64_t pixels, int32_t cin, int32_t cout,
+                                     void* ws, int64_t ws_bytes, void* stream) {
+  if (!dout || !in || !dw || !db || !ws || pixels <= 0 || cin <= 0 || cout <= 0 ||
+      ws_bytes < ynb_pwconv_bwd_weight_workspace_bytes(pixels, cin, cout))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_pwconv_bwd_weight: bad arguments / workspace too small");
+  const int chunks = pw_bwd_chunks(pixels, cin, cout);
+  long long m_per_chunk = (pixels + chunks - 1) / chunks;
+  m_per_chunk = (m_per_chunk + kPwBwdSlab - 1) / kPwBwdSlab * kPwBwdSlab;
+  float* pw = (float*)ws;
+  float* pb = pw + (long long)chunks * cout * cin;
+  cudaStream_t st = (cudaStream_t)stream;
+  UNIT_TRY(cudaMemsetAsync(ws, 0, (size_t)chunks * ((size_t)cout * cin + cout) * sizeof(float), st));
+  dim3 grid(chunks, (cout + kPwBwdTile - 1) / kPwBwdTile, (cin + kPwBwdTile - 1) / kPwBwdTile);
+  pwconv_bwd_weight_kernel<<<grid, 256, 0, st>>>(dout, do_ld, do_off, in, in_ld, in_off, pw, pb, pixels, cin, cout,
+                                                 m_per_chunk);
+  YNB_COUNT_LAUNCH();
+  const long long ew = (long long)cout * cin;
+  reduce_partials_kernel<<<(int)std::min<long long>((ew + 127) / 128, kNumSMs * 8), 128, 0, st>>>(pw, chunks, ew, dw);
+  YNB_COUNT_LAUNCH();
+  reduce_partials_kernel<<<(cout + 127) / 128, 128, 0, st>>>(pb, chunks, cout, db);
+  YNB_COUNT_LAUNCH();
+  UNIT_TRY(cudaGetLastError());
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_act_bwd(const float* dout, int32_t do_ld, int32_t do_off, const float* out, int32_t o_ld,
+                           int32_t o_off, float* dpre, int32_t dp_ld, int32_t dp_off, int64_t pixels, int32_t channels,
+                           int32_t act, void* stream) {
+  if (!dout || !out || !dpre || pixels <= 0 || channels <= 0 || (act != YNB_ACT_RELU && act != YNB_ACT_LEAKY))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_act_bwd: bad arguments");
+  const long long total = (long long)pixels * channels;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
+  act_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dout, do_ld, do_off, out, o_ld, o_off, dpre, dp_ld, dp_off,
+                                                           pixels, channels, act == YNB_ACT_RELU ? 0.0f : 0.1f);
+  YNB_COUNT_LAUNCH();
+  UNIT_TRY(cudaGetLastError());
   return YNB_OK;
 }

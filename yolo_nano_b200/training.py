@@ -1,0 +1,182 @@
+"""Host side of the training branch at the head boundary (SURVEY §8 row a14, §8f row 4;
+BASELINE config 5), over the C ABI of include/yolonano_b200.h.
+
+Built: target assignment (`tools.multi_gt_creator`), the four losses + their gradient w.r.t. the raw
+head maps (`models/yolo_nano.py:333-358`, `tools.py:12-34,219-276`), the SGD update
+(`train.py:167-171`), the gradient all-reduce of the data-parallel config, and the
+backward kernels of the depthwise / pointwise convolutions.  NOT built: BatchNorm with batch
+statistics and the chaining into `YOLONano.forward(x, target)` (raises NotImplementedError).
+
+PyTorch supplies device memory, the stream and `torch.distributed`; every computation is in
+libyolonano_b200.so.  No CPU fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .engine import EngineError, _ptr, _stream_ptr
+
+STRIDES = (8, 16, 32)
+
+
+def _check(rc: int, what: str):
+    if rc != _lib.YNB_OK:
+        msg = _lib.load().ynb_last_error(None)
+        raise EngineError(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+def _dev(*ts: torch.Tensor) -> torch.device:
+    for t in ts:
+        if t is not None and (not t.is_cuda or t.dtype not in (torch.float32, torch.int32) or not t.is_contiguous()):
+            raise EngineError("training kernels take contiguous float32 / int32 CUDA tensors (no CPU fallback)")
+    return ts[0].device
+
+
+def _anchors(anchor_size) -> "C.Array":
+    flat = [float(v) for wh in anchor_size for v in wh]
+    if len(flat) % 6:
+        raise EngineError("anchor_size must hold 3 levels x A [w,h] pairs")
+    return (C.c_float * len(flat))(*flat), len(flat) // 6
+
+
+def build_targets(labels: torch.Tensor, counts: Optional[torch.Tensor], input_size: int, anchor_size) -> torch.Tensor:
+    """`tools.multi_gt_creator(input_size, strides, label_lists, anchor_size)` (tools.py:97-216).
+    labels [B, L, 5] float32 CUDA (xmin, ymin, xmax, ymax normalised, class), counts [B] int32 or None
+    -> target [B, N, 11] float32 on the same device."""
+    dev = _dev(labels, counts)
+    anc, a = _anchors(anchor_size)
+    b, l, five = labels.shape
+    assert five == 5
+    n = sum(a * (input_size // s) ** 2 for s in STRIDES)
+    target = torch.empty((b, n, 11), device=dev, dtype=torch.float32)
+    _check(_lib.load().ynb_build_targets(_ptr(labels), _ptr(counts), b, l, input_size, anc, a, _ptr(target),
+                                         _stream_ptr(dev)), "ynb_build_targets")
+    return target
+
+
+def train_loss(raw: Sequence[torch.Tensor], target: torch.Tensor, input_size: int, num_classes: int, anchor_size,
+               ) -> Tuple[torch.Tensor, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
+    """raw = three NHWC maps [B, H*W, ld] (reference channel map) -> (losses [4] = conf, cls, bbox, iou
+    on the device, gradients of their sum w.r.t. the three maps)."""
+    dev = _dev(*raw, target)
+    lib = _lib.load()
+    anc, a = _anchors(anchor_size)
+    b, ld = raw[0].shape[0], raw[0].shape[-1]
+    for r, s in zip(raw, STRIDES):
+        if r.shape[0] != b or r.shape[-1] != ld or r.numel() != b * (input_size // s) ** 2 * ld:
+            raise EngineError("raw head maps must be [B, (S/stride)^2, ld] with one ld")
+    if tuple(target.shape) != (b, sum(a * (input_size // s) ** 2 for s in STRIDES), 11):
+        raise EngineError("target must be [B, N, 11]")
+    grads = tuple(torch.empty_like(r) for r in raw)
+    losses = torch.empty(4, device=dev, dtype=torch.float32)
+    wsb = lib.ynb_train_loss_workspace_bytes()
+    ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
+    _check(lib.ynb_train_loss(_ptr(raw[0]), _ptr(raw[1]), _ptr(raw[2]), ld, _ptr(target), b, input_size, anc, a,
+                              num_classes, _ptr(losses), _ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2]),
+                              _ptr(ws), wsb, _stream_ptr(dev)), "ynb_train_loss")
+    return losses, grads
+
+
+class FlatSGD:
+    """`torch.optim.SGD(params, lr, momentum=0.9, weight_decay=5e-4)` (train.py:167-171) over ONE flat
+    float32 device vector (the 1.33 M parameters of the model are 5.3 MB: one launch, one all-reduce).
+    `step(grad)` with `world_size > 1` first all-reduces (sum) the gradient over the process group —
+    NCCL over NVLink on GPUs — and folds the 1 / world_size into the update kernel."""
+
+    def __init__(self, params: torch.Tensor, lr: float, momentum: float = 0.9, weight_decay: float = 5e-4):
+        _dev(params)
+        self.params = params
+        self.lr, self.momentum, self.weight_decay = float(lr), float(momentum), float(weight_decay)
+        self.buf = torch.zeros_like(params)
+        self.steps = 0
+
+    def set_lr(self, lr: float):          # train.py:337-339
+        self.lr = float(lr)
+
+    def step(self, grad: torch.Tensor, group=None):
+        dev = _dev(grad)
+        scale = 1.0
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            allreduce_gradients(grad, group)
+            scale = 1.0 / dist.get_world_size(group)
+        _check(_lib.load().ynb_sgd_step(_ptr(self.params), _ptr(grad), _ptr(self.buf), self.params.numel(), self.lr,
+                                        self.momentum, self.weight_decay, int(self.steps == 0), scale,
+                                        _stream_ptr(dev)), "ynb_sgd_step")
+        self.steps += 1
+
+
+def allreduce_gradients(flat_grad: torch.Tensor, group=None) -> torch.Tensor:
+    """ONE all-reduce (sum) of the flat gradient per step; the division by the
+    world size happens in the SGD kernel.  In place; returns its argument."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+    return flat_grad
+
+
+# ---- backward of the conv kernels (individually callable, NHWC with (ld, off) channel windows) ----------
+def dwconv3x3_backward(dout: torch.Tensor, x: torch.Tensor, w9c: torch.Tensor, stride: int):
+    """dout [B,Ho,Wo,C], x [B,H,W,C], w9c [9,C] -> (dx [B,H,W,C], dw [9,C], db [C])."""
+    dev = _dev(dout, x, w9c)
+    lib = _lib.load()
+    b, h, w, c = x.shape
+    dx = torch.empty_like(x)
+    _check(lib.ynb_dwconv3x3_bwd_data(_ptr(dout), c, 0, _ptr(dx), c, 0, _ptr(w9c), b, h, w, c, stride,
+                                      _stream_ptr(dev)), "ynb_dwconv3x3_bwd_data")
+    wsb = lib.ynb_dwconv3x3_bwd_weight_workspace_bytes(b, h, c, stride)
+    ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
+    dwdb = torch.empty((10, c), device=dev, dtype=torch.float32)
+    _check(lib.ynb_dwconv3x3_bwd_weight(_ptr(dout), c, 0, _ptr(x), c, 0, _ptr(dwdb), b, h, w, c, stride,
+                                        _ptr(ws), wsb, _stream_ptr(dev)), "ynb_dwconv3x3_bwd_weight")
+    return dx, dwdb[:9], dwdb[9]
+
+
+def pwconv_backward_weight(dout: torch.Tensor, x: torch.Tensor):
+    """dout [M, N], x [M, K] -> (dw [N, K], db [N])."""
+    dev = _dev(dout, x)
+    lib = _lib.load()
+    m, n = dout.shape
+    k = x.shape[1]
+    wsb = lib.ynb_pwconv_bwd_weight_workspace_bytes(m, k, n)
+    ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
+    dw = torch.empty((n, k), device=dev, dtype=torch.float32)
+    db = torch.empty((n,), device=dev, dtype=torch.float32)
+    _check(lib.ynb_pwconv_bwd_weight(_ptr(dout), n, 0, _ptr(x), k, 0, _ptr(dw), _ptr(db), m, k, n, _ptr(ws), wsb,
+                                     _stream_ptr(dev)), "ynb_pwconv_bwd_weight")
+    return dw, db
+
+
+def pwconv_backward_data(dout: torch.Tensor, w_nk: torch.Tensor, tensor_cores: bool = True) -> torch.Tensor:
+    """dx [M, K] = dout [M, N] . w [N, K]: the forward pointwise GEMM with the transposed weights and a
+    zero bias (tcgen05 3xTF32 by default).  N and K must be multiples of 4."""
+    dev = _dev(dout, w_nk)
+    lib = _lib.load()
+    m, n = dout.shape
+    k = w_nk.shape[1]
+    wt = w_nk.t().contiguous()                      # [K][N]: "cout" = K, "cin" = N
+    zero = torch.zeros(k, device=dev, dtype=torch.float32)
+    dx = torch.empty((m, k), device=dev, dtype=torch.float32)
+    if tensor_cores:
+        for k0 in range(0, k, 256):                 # the tcgen05 GEMM holds at most 256 output columns in TMEM
+            kc = min(256, k - k0)
+            _check(lib.ynb_pwconv_tc(_ptr(dout), n, 0, _ptr(dx), k, k0, 1, _ptr(wt[k0:k0 + kc]), _ptr(zero), m, n, kc, 0,
+                                     _lib.GEMM_TC_3XTF32, _stream_ptr(dev)), "ynb_pwconv_tc")
+    else:
+        _check(lib.ynb_pwconv(_ptr(dout), n, 0, _ptr(dx), k, 0, 1, _ptr(wt), _ptr(zero), m, n, k, 0,
+                              _stream_ptr(dev)), "ynb_pwconv")
+    return dx
+
+
+def act_backward(dout: torch.Tensor, out: torch.Tensor, act: int) -> torch.Tensor:
+    """dout, out [M, C]; act 1 = ReLU, 2 = LeakyReLU(0.1)."""
+    dev = _dev(dout, out)
+    m, c = dout.shape
+    dpre = torch.empty_like(dout)
+    _check(_lib.load().ynb_act_bwd(_ptr(dout), c, 0, _ptr(out), c, 0, _ptr(dpre), c, 0, m, c, act, _stream_ptr(dev)),
+           "ynb_act_bwd")
+    return dpre
+
