@@ -294,8 +294,8 @@ int  ynb_build_targets(const float* labels_dev, const int32_t* counts_dev, int32
  * (as ynb_decode_level); target_dev [B, N, 11].  Outputs: losses_dev [4] = conf, cls, bbox (txty +
  * twth), iou, each already divided by the batch size; grad_*_dev (same layout as raw_*) =
  * d(conf + cls + bbox + iou) / d raw, the quantity train.py:222-229 back-propagates into the heads.
- * Deterministic (two-stage reduction).  workspace_dev: ynb_train_loss_workspace_bytes() bytes. */
-int64_t ynb_train_loss_workspace_bytes(void);
+ * Deterministic (two-stage reduction).  workspace_dev: ynb_train_loss_workspace_bytes(batch, input_size) bytes. */
+int64_t ynb_train_loss_workspace_bytes(int32_t batch, int32_t input_size);
 int  ynb_train_loss(const float* raw_s_dev, const float* raw_m_dev, const float* raw_l_dev, int32_t raw_ld,
                     const float* target_dev, int32_t batch, int32_t input_size, const float* anchors_wh,
                     int32_t num_anchors, int32_t num_classes, float* losses_dev, float* grad_s_dev,
@@ -317,7 +317,8 @@ int  ynb_dwconv3x3_bwd_data(const float* dout_dev, int32_t dout_ld, int32_t dout
                             int32_t batch, int32_t h_in, int32_t w_in, int32_t channels, int32_t stride,
                             void* stream);
 /* dwdb_dev [10][C]: rows 0..8 = d w[t][c] = sum d_out * in(shifted by tap t), row 9 = d bias[c]. */
-int64_t ynb_dwconv3x3_bwd_weight_workspace_bytes(int32_t batch, int32_t h_in, int32_t channels, int32_t stride);
+int64_t ynb_dwconv3x3_bwd_weight_workspace_bytes(int32_t batch, int32_t h_in, int32_t w_in, int32_t channels,
+                                                 int32_t stride);
 int  ynb_dwconv3x3_bwd_weight(const float* dout_dev, int32_t dout_ld, int32_t dout_off,
                               const float* in_dev, int32_t in_ld, int32_t in_off, float* dwdb_dev,
                               int32_t batch, int32_t h_in, int32_t w_in, int32_t channels, int32_t stride,

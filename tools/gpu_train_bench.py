@@ -55,11 +55,20 @@ def main():
     # ---- loss + head gradient: 4 rotating sets of raw maps (3 x 4 x 116 MB > L2)
     sets = 4
     raws = [[torch.randn(B, g * g, ld, device=DEV) for g in grids] for _ in range(sets)]
-    ms = timed(lambda i: TR.train_loss(raws[i], target, S, C, anchors), sets)
+    lib = TR._lib.load()
+    anc, _a = TR._anchors(anchors)
+    grads = [torch.empty_like(r) for r in raws[0]]          # preallocated: the timed region is launches only
+    losses = torch.empty(4, device=DEV)
+    wsb = lib.ynb_train_loss_workspace_bytes(B, S)
+    ws = torch.empty(wsb, device=DEV, dtype=torch.uint8)
+    st = TR._stream_ptr(DEV)
+    ms = timed(lambda i: lib.ynb_train_loss(TR._ptr(raws[i][0]), TR._ptr(raws[i][1]), TR._ptr(raws[i][2]), ld,
+                                            TR._ptr(target), B, S, anc, A, C, TR._ptr(losses), TR._ptr(grads[0]),
+                                            TR._ptr(grads[1]), TR._ptr(grads[2]), TR._ptr(ws), wsb, st), sets)
     cells = B * sum(g * g for g in grids)
     out.append(row("train_loss + finalize", ms, cells * (A * 5 * 4 + A * 11 * 4 + ld * 4),
                    "reads obj/box logits + targets, class logits of positives only; writes the gradient map once"))
-    del raws
+    del raws, grads
     # ---- SGD: the model (1.326 M parameters) and a bandwidth-sized vector
     for n, tag in ((1326305, "model-sized: launch-latency bound"), (64 * 1024 * 1024, "bandwidth-sized")):
         ps = [torch.randn(n, device=DEV) for _ in range(2)]
@@ -77,13 +86,11 @@ def main():
         ho = (hw - 1) // s + 1
         dys = [torch.randn(b, ho, ho, c, device=DEV) for _ in range(sets)]
         w = torch.randn(9, c, device=DEV)
-        lib = TR._lib.load()
         dx = torch.empty_like(xs[0])
-        st = TR._stream_ptr(DEV)
         ms = timed(lambda i: lib.ynb_dwconv3x3_bwd_data(TR._ptr(dys[i]), c, 0, TR._ptr(dx), c, 0, TR._ptr(w), b, hw, hw,
                                                         c, s, st), sets)
         out.append(row(f"dwconv3x3_bwd_data B={b} C={c} {hw}^2 s{s}", ms, 4 * c * b * (hw * hw + ho * ho)))
-        wsb = lib.ynb_dwconv3x3_bwd_weight_workspace_bytes(b, hw, c, s)
+        wsb = lib.ynb_dwconv3x3_bwd_weight_workspace_bytes(b, hw, hw, c, s)
         ws = torch.empty(wsb, device=DEV, dtype=torch.uint8)
         dwdb = torch.empty(10, c, device=DEV)
         ms = timed(lambda i: lib.ynb_dwconv3x3_bwd_weight(TR._ptr(dys[i]), c, 0, TR._ptr(xs[i]), c, 0, TR._ptr(dwdb), b,
@@ -94,7 +101,11 @@ def main():
         sets = 3
         xs = [torch.randn(m, k, device=DEV) for _ in range(sets)]
         dys = [torch.randn(m, n, device=DEV) for _ in range(sets)]
-        ms = timed(lambda i: TR.pwconv_backward_weight(dys[i], xs[i]), sets)
+        wsb = lib.ynb_pwconv_bwd_weight_workspace_bytes(m, k, n)
+        ws = torch.empty(wsb, device=DEV, dtype=torch.uint8)
+        dw, db = torch.empty(n, k, device=DEV), torch.empty(n, device=DEV)
+        ms = timed(lambda i: lib.ynb_pwconv_bwd_weight(TR._ptr(dys[i]), n, 0, TR._ptr(xs[i]), k, 0, TR._ptr(dw), TR._ptr(db),
+                                                       m, k, n, TR._ptr(ws), wsb, st), sets)
         r = row(f"pwconv_bwd_weight M={m} K={k} N={n}", ms, 4 * m * (k + n))
         r["tflops"] = round(2 * m * k * n / ms / 1e9, 1)
         out.append(r)

@@ -404,7 +404,9 @@ struct DwTile {
   static constexpr int BYTES = IW * IH * 128;
 };
 
-template <int STRIDE>
+// REV: taps reversed and no bias = the gradient of a stride-1 depthwise conv w.r.t. its input
+// (train_ops.cuh / ynb_dwconv3x3_bwd_data).
+template <int STRIDE, bool REV = false>
 __global__ void __launch_bounds__(DwTile<STRIDE>::THREADS)
 dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmIn, float* __restrict__ out, int out_ld, int out_off,
                      const float* __restrict__ w, const float* __restrict__ bias, int Ho, int Wo, int C4,
@@ -427,9 +429,9 @@ dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmIn, float* __restrict
   const bool c_ok = c < C4;
   float4 kw[9], bv = make_float4(0.f, 0.f, 0.f, 0.f);
   if (c_ok) {
-    bv = __ldg(reinterpret_cast<const float4*>(bias + c));
+    if (!REV) bv = __ldg(reinterpret_cast<const float4*>(bias + c));
 #pragma unroll
-    for (int k = 0; k < 9; ++k) kw[k] = __ldg(reinterpret_cast<const float4*>(w + k * C4 + c));
+    for (int k = 0; k < 9; ++k) kw[k] = __ldg(reinterpret_cast<const float4*>(w + (REV ? 8 - k : k) * C4 + c));
   }
   pdl_wait();
   if (tid == 0) {
@@ -487,12 +489,19 @@ inline bool make_tmap_dw(CUtensorMap* m, const float* in, int in_ld, int in_off,
 
 inline cudaError_t launch_dwconv3x3_tma(const CUtensorMap& tm, float* out, int out_ld, int out_off, const float* w,
                                         const float* b, int batch, int Hin, int Win, int C4, int stride, int act,
-                                        cudaStream_t st) {
+                                        cudaStream_t st, bool reversed_taps = false) {
   const int Ho = (Hin - 1) / stride + 1, Wo = (Win - 1) / stride + 1;
   if (batch <= 0 || C4 <= 0) return cudaSuccess;
   const int TW = stride == 1 ? DwTile<1>::TW : DwTile<2>::TW, TH = DwTile<1>::TH;
   const int tiles_x = (Wo + TW - 1) / TW, tiles_y = (Ho + TH - 1) / TH;
   dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)((C4 + 31) / 32), (unsigned)batch);
+  if (reversed_taps) {
+    if (stride != 1) return cudaErrorInvalidValue;
+    cudaError_t rr = launch_pdl(dwconv3x3_tma_kernel<1, true>, grid, dim3(DwTile<1>::THREADS), 0, st, tm, out, out_ld,
+                                out_off, w, b, Ho, Wo, C4, tiles_x, act);
+    YNB_COUNT_LAUNCH();
+    return rr;
+  }
   cudaError_t r = stride == 1
       ? launch_pdl(dwconv3x3_tma_kernel<1>, grid, dim3(DwTile<1>::THREADS), 0, st, tm, out, out_ld, out_off, w, b, Ho, Wo,
                    C4, tiles_x, act)

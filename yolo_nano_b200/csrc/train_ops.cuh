@@ -8,8 +8,8 @@
 namespace ynb {
 
 constexpr int kTrainMaxAnchors = 8;
-constexpr int kLossBlocks = kNumSMs * 8;      // persistent grid of the loss kernel
 constexpr int kLossThreads = 256;
+constexpr int kLossCells = 64;                // cells (pixels of one level of one image) per block
 
 struct TrainLossParams {
   const float* raw[3];     // NHWC [B, HW_l, ld], channel map obj a | cls A + a*C + c | box A(1+C) + 4a + k
@@ -20,6 +20,8 @@ struct TrainLossParams {
   int grid[3], stride[3];
   int cells[3];            // HW_l
   int cell_off[3];         // prefix of cells
+  int tiles[3];            // ceil(HW_l / kLossCells)
+  int tiles_per_image;
   int cells_total;         // sum HW_l
   float anchors[3][kTrainMaxAnchors][2];
 };
@@ -36,133 +38,175 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// One warp per (image, cell): the cell's A*(1+C+4) logits are one contiguous row (1020 B at
-// A=3, C=80) read and written with lane-strided accesses.  Class logits are only read for
-// positive anchors (their gradient is zero everywhere else), which is what keeps the kernel at
-// "write the gradient map once" traffic.
+// One block per tile of 64 cells of one level of one image (= 64 contiguous rows of the raw map and
+// 64*A contiguous target rows).
+//   phase 0: the tile's targets (64*A*11 floats, contiguous) are staged in shared memory, coalesced;
+//   phase 1: one thread per anchor does the scalar work — decode, IoU, objectness / box / IoU losses
+//            and their gradients (5 floats per anchor -> shared memory);
+//   phase 2: all threads write the 64 gradient rows ONCE with 16-byte stores: objectness and box
+//            columns from shared memory, zeros in the class columns (their gradient is zero for every
+//            non-positive anchor, so the class logits of those are never read);
+//   phase 3: one warp per positive anchor: cross entropy and the softmax gradient of its C
+//            class columns.
+// HBM traffic = obj/box logits + targets + the gradient map written once (+ C logits per positive).
 //   models/yolo_nano.py:333-358: decode (no clamp) -> iou_score -> gt_conf = iou (detached)
 //   tools.py:12-34   MSEWithLogitsLoss: 5*pos*(sigmoid(l) - iou)^2 + neg*sigmoid(l)^2
 //   tools.py:236-276 CE on positives, BCE-with-logits (txty) and MSE (twth) weighted by
 //                    gt_box_scale_weight*mask, SmoothL1(iou, mask) over ALL anchors; each sum / B.
 __global__ void __launch_bounds__(kLossThreads) train_loss_kernel(const TrainLossParams p) {
-  const int lane = threadIdx.x & 31;
-  const int warp_in_block = threadIdx.x >> 5;
-  const long long warps_total = (long long)gridDim.x * (kLossThreads / 32);
-  const long long rows = (long long)p.B * p.cells_total;
+  extern __shared__ __align__(16) float sh_dyn[];
   const int A = p.A, C = p.C;
+  float* sh_t = sh_dyn;                                   // [64*A][11] targets
+  float* sh_g = sh_t + kLossCells * A * 11;               // [64*A][5] g_conf, g_tx, g_ty, g_tw, g_th
+  __shared__ double part[kLossThreads / 32][4];
+
+  const int b = blockIdx.x / p.tiles_per_image;
+  int tile = blockIdx.x - b * p.tiles_per_image;
+  int lvl = 0;
+  if (tile >= p.tiles[0]) { tile -= p.tiles[0]; lvl = 1; }
+  if (lvl == 1 && tile >= p.tiles[1]) { tile -= p.tiles[1]; lvl = 2; }
+  const int cell0 = tile * kLossCells;
+  const int ncell = min(kLossCells, p.cells[lvl] - cell0);
+  const int nanch = ncell * A;
   const int used = A * (1 + C + 4);
   const float invB = 1.0f / (float)p.B;
   const float fS = (float)p.S;
+  const float fs = (float)p.stride[lvl];
   const long long N = (long long)p.cells_total * A;
-  float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};    // lane 0 only carries the scalar losses
+  const float* __restrict__ raw = p.raw[lvl] + ((long long)b * p.cells[lvl] + cell0) * p.ld;
+  float* __restrict__ g = p.grad[lvl] + ((long long)b * p.cells[lvl] + cell0) * p.ld;
+  const float* __restrict__ tg = p.target + ((long long)b * N + ((long long)p.cell_off[lvl] + cell0) * A) * 11;
 
-  for (long long row = (long long)blockIdx.x * (kLossThreads / 32) + warp_in_block; row < rows; row += warps_total) {
-    const int b = (int)(row / p.cells_total);
-    const int r = (int)(row - (long long)b * p.cells_total);
-    const int lvl = r >= p.cell_off[2] ? 2 : (r >= p.cell_off[1] ? 1 : 0);
-    const int cell = r - p.cell_off[lvl];
+  for (int i = threadIdx.x; i < nanch * 11; i += kLossThreads) sh_t[i] = tg[i];
+  __syncthreads();
+
+  float l_conf = 0.0f, l_box = 0.0f, l_iou = 0.0f, l_cls = 0.0f;
+  for (int i = threadIdx.x; i < nanch; i += kLossThreads) {      // one pass when 64*A <= 256
+    const int cl = i / A, a = i - cl * A;
+    const int cell = cell0 + cl;
     const int gy = cell / p.grid[lvl], gx = cell - gy * p.grid[lvl];
-    const float fs = (float)p.stride[lvl];
-    const float* __restrict__ raw = p.raw[lvl] + ((long long)b * p.cells[lvl] + cell) * p.ld;
-    float* __restrict__ g = p.grad[lvl] + ((long long)b * p.cells[lvl] + cell) * p.ld;
-    const float* __restrict__ trow = p.target + ((long long)b * N + (long long)p.cell_off[lvl] * A + (long long)cell * A) * 11;
-    for (int c = used + lane; c < p.ld; c += 32) g[c] = 0.0f;     // padding channels of the map
+    const float* __restrict__ t = sh_t + i * 11;
+    const float* __restrict__ row = raw + (long long)cl * p.ld;
+    const float obj = t[0];
+    const float mask = obj > 0.0f ? 1.0f : 0.0f;
+    const float pos = obj == 1.0f ? 1.0f : 0.0f;
+    const float neg = obj == 0.0f ? 1.0f : 0.0f;
+    const float lconf = row[a];
+    const int bo = A * (1 + C) + 4 * a;
+    const float tx = row[bo], ty = row[bo + 1], tw = row[bo + 2], th = row[bo + 3];
+    // decode_boxes / input_size (models/yolo_nano.py:120-156,337)
+    const float sx = sigmoid_precise(tx), sy = sigmoid_precise(ty);
+    const float ew = expf(tw), eh = expf(th);
+    const float aw = p.anchors[lvl][a][0], ah = p.anchors[lvl][a][1];
+    const float cx = __fmul_rn(__fadd_rn(sx, (float)gx), fs), cy = __fmul_rn(__fadd_rn(sy, (float)gy), fs);
+    const float bw = __fmul_rn(ew, aw), bh = __fmul_rn(eh, ah);
+    const float x1 = __fsub_rn(cx, bw * 0.5f) / fS, y1 = __fsub_rn(cy, bh * 0.5f) / fS;
+    const float x2 = __fadd_rn(cx, bw * 0.5f) / fS, y2 = __fadd_rn(cy, bh * 0.5f) / fS;
+    // iou_score (tools.py:219-233)
+    const float q1x = t[7], q1y = t[8], q2x = t[9], q2y = t[10];
+    const float tlx = fmaxf(x1, q1x), tly = fmaxf(y1, q1y), brx = fminf(x2, q2x), bry = fminf(y2, q2y);
+    const float wa = __fsub_rn(x2, x1), ha = __fsub_rn(y2, y1);
+    const float area_a = __fmul_rn(wa, ha);
+    const float area_b = __fmul_rn(__fsub_rn(q2x, q1x), __fsub_rn(q2y, q1y));
+    const float en = (tlx < brx && tly < bry) ? 1.0f : 0.0f;
+    const float iw = __fsub_rn(brx, tlx), ih = __fsub_rn(bry, tly);
+    const float area_i = __fmul_rn(__fmul_rn(iw, ih), en);
+    const float uni = __fsub_rn(__fadd_rn(area_a, area_b), area_i);
+    const float iou = area_i / uni;
+    // objectness (tools.py:12-34); the label is the detached IoU
+    const float pc = sigmoid_precise(lconf);
+    const float dpi = pc - iou;
+    l_conf += 5.0f * (pos * dpi * dpi) + neg * pc * pc;
+    const float g_conf = (10.0f * pos * dpi + 2.0f * neg * pc) * pc * (1.0f - pc) * invB;
+    // iou loss: SmoothL1(iou, mask), beta = 1 (tools.py:273)
+    const float d = iou - mask, ad = fabsf(d);
+    l_iou += ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
+    const float g_iou = (ad < 1.0f ? d : (d > 0.0f ? 1.0f : -1.0f)) * invB;
+    // ... back through iou = I / (Aa + Ab - I)
+    const float inv_u = 1.0f / uni;
+    const float g_I = g_iou * (inv_u + area_i * inv_u * inv_u);
+    const float g_Aa = -g_iou * area_i * inv_u * inv_u;
+    const float g_iw = g_I * ih * en, g_ih = g_I * iw * en;
+    // torch.max / torch.min of two tensors split the gradient evenly on ties
+    const float sx2 = x2 < q2x ? 1.0f : (x2 == q2x ? 0.5f : 0.0f), sx1 = x1 > q1x ? 1.0f : (x1 == q1x ? 0.5f : 0.0f);
+    const float sy2 = y2 < q2y ? 1.0f : (y2 == q2y ? 0.5f : 0.0f), sy1 = y1 > q1y ? 1.0f : (y1 == q1y ? 0.5f : 0.0f);
+    const float g_x2 = (g_iw * sx2 + g_Aa * ha) / fS, g_x1 = (-g_iw * sx1 - g_Aa * ha) / fS;
+    const float g_y2 = (g_ih * sy2 + g_Aa * wa) / fS, g_y1 = (-g_ih * sy1 - g_Aa * wa) / fS;
+    float g_tx = (g_x1 + g_x2) * fs * sx * (1.0f - sx);
+    float g_ty = (g_y1 + g_y2) * fs * sy * (1.0f - sy);
+    float g_tw = (g_x2 - g_x1) * 0.5f * bw;
+    float g_th = (g_y2 - g_y1) * 0.5f * bh;
+    if (mask > 0.0f) {   // box loss (tools.py:267-270)
+      const float wm = t[6];
+      const float ttx = t[2], tty = t[3], ttw = t[4], tth = t[5];
+      const float bce = (fmaxf(tx, 0.0f) - tx * ttx + log1pf(expf(-fabsf(tx)))) +
+                        (fmaxf(ty, 0.0f) - ty * tty + log1pf(expf(-fabsf(ty))));
+      const float mse = (tw - ttw) * (tw - ttw) + (th - tth) * (th - tth);
+      l_box += bce * wm + mse * wm;
+      g_tx += wm * (sx - ttx) * invB;
+      g_ty += wm * (sy - tty) * invB;
+      g_tw += wm * 2.0f * (tw - ttw) * invB;
+      g_th += wm * 2.0f * (th - tth) * invB;
+    }
+    float* gq = sh_g + i * 5;
+    gq[0] = g_conf; gq[1] = g_tx; gq[2] = g_ty; gq[3] = g_tw; gq[4] = g_th;
+  }
+  __syncthreads();
 
-    for (int a = 0; a < A; ++a) {
-      const float* __restrict__ t = trow + a * 11;
-      const float obj = t[0];
-      const float mask = obj > 0.0f ? 1.0f : 0.0f;
-      const float pos = obj == 1.0f ? 1.0f : 0.0f;
-      const float neg = obj == 0.0f ? 1.0f : 0.0f;
-      const float lconf = raw[a];
-      const int bo = A * (1 + C) + 4 * a;
-      const float tx = raw[bo], ty = raw[bo + 1], tw = raw[bo + 2], th = raw[bo + 3];
-      // decode_boxes / input_size (models/yolo_nano.py:120-156,337)
-      const float sx = sigmoid_precise(tx), sy = sigmoid_precise(ty);
-      const float ew = expf(tw), eh = expf(th);
-      const float aw = p.anchors[lvl][a][0], ah = p.anchors[lvl][a][1];
-      const float cx = __fmul_rn(__fadd_rn(sx, (float)gx), fs), cy = __fmul_rn(__fadd_rn(sy, (float)gy), fs);
-      const float bw = __fmul_rn(ew, aw), bh = __fmul_rn(eh, ah);
-      const float x1 = __fsub_rn(cx, bw * 0.5f) / fS, y1 = __fsub_rn(cy, bh * 0.5f) / fS;
-      const float x2 = __fadd_rn(cx, bw * 0.5f) / fS, y2 = __fadd_rn(cy, bh * 0.5f) / fS;
-      // iou_score (tools.py:219-233)
-      const float q1x = t[7], q1y = t[8], q2x = t[9], q2y = t[10];
-      const float tlx = fmaxf(x1, q1x), tly = fmaxf(y1, q1y), brx = fminf(x2, q2x), bry = fminf(y2, q2y);
-      const float wa = __fsub_rn(x2, x1), ha = __fsub_rn(y2, y1);
-      const float area_a = __fmul_rn(wa, ha);
-      const float area_b = __fmul_rn(__fsub_rn(q2x, q1x), __fsub_rn(q2y, q1y));
-      const float en = (tlx < brx && tly < bry) ? 1.0f : 0.0f;
-      const float iw = __fsub_rn(brx, tlx), ih = __fsub_rn(bry, tly);
-      const float area_i = __fmul_rn(__fmul_rn(iw, ih), en);
-      const float uni = __fsub_rn(__fadd_rn(area_a, area_b), area_i);
-      const float iou = area_i / uni;
-
-      // objectness (tools.py:12-34); the label is the detached IoU
-      const float pc = sigmoid_precise(lconf);
-      const float dpi = pc - iou;
-      const float l_conf = 5.0f * (pos * dpi * dpi) + neg * pc * pc;
-      const float g_conf = (10.0f * pos * dpi + 2.0f * neg * pc) * pc * (1.0f - pc) * invB;
-      // iou loss: SmoothL1(iou, mask), beta = 1 (tools.py:273)
-      const float d = iou - mask, ad = fabsf(d);
-      const float l_iou = ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
-      const float g_iou = (ad < 1.0f ? d : (d > 0.0f ? 1.0f : -1.0f)) * invB;
-      // ... back through iou = I / (Aa + Ab - I)
-      const float inv_u = 1.0f / uni;
-      const float g_I = g_iou * (inv_u + area_i * inv_u * inv_u);
-      const float g_Aa = -g_iou * area_i * inv_u * inv_u;
-      const float g_iw = g_I * ih * en, g_ih = g_I * iw * en;
-      // torch.max / torch.min of two tensors split the gradient evenly on ties
-      const float sx2 = x2 < q2x ? 1.0f : (x2 == q2x ? 0.5f : 0.0f), sx1 = x1 > q1x ? 1.0f : (x1 == q1x ? 0.5f : 0.0f);
-      const float sy2 = y2 < q2y ? 1.0f : (y2 == q2y ? 0.5f : 0.0f), sy1 = y1 > q1y ? 1.0f : (y1 == q1y ? 0.5f : 0.0f);
-      const float g_x2 = (g_iw * sx2 + g_Aa * ha) / fS, g_x1 = (-g_iw * sx1 - g_Aa * ha) / fS;
-      const float g_y2 = (g_ih * sy2 + g_Aa * wa) / fS, g_y1 = (-g_ih * sy1 - g_Aa * wa) / fS;
-      float g_tx = (g_x1 + g_x2) * fs * sx * (1.0f - sx);
-      float g_ty = (g_y1 + g_y2) * fs * sy * (1.0f - sy);
-      float g_tw = (g_x2 - g_x1) * 0.5f * bw;
-      float g_th = (g_y2 - g_y1) * 0.5f * bh;
-      // box loss (tools.py:267-270)
-      const float wm = t[6] * mask;
-      float l_box = 0.0f, l_cls = 0.0f;
-      if (mask > 0.0f) {
-        const float ttx = t[2], tty = t[3], ttw = t[4], tth = t[5];
-        const float bce = (fmaxf(tx, 0.0f) - tx * ttx + log1pf(expf(-fabsf(tx)))) +
-                          (fmaxf(ty, 0.0f) - ty * tty + log1pf(expf(-fabsf(ty))));
-        const float mse = (tw - ttw) * (tw - ttw) + (th - tth) * (th - tth);
-        l_box = bce * wm + mse * wm;
-        g_tx += wm * (sx - ttx) * invB;
-        g_ty += wm * (sy - tty) * invB;
-        g_tw += wm * 2.0f * (tw - ttw) * invB;
-        g_th += wm * 2.0f * (th - tth) * invB;
+  // phase 2: the gradient rows, written once.  Column c of a row: c < A -> g_conf of anchor c;
+  // c in [A(1+C), used) -> box gradient; everything else (class columns, padding) 0.
+  const int box0 = A * (1 + C);
+  if ((p.ld & 3) == 0) {
+    const int ld4 = p.ld >> 2;
+    for (int i = threadIdx.x; i < ncell * ld4; i += kLossThreads) {
+      const int cl = i / ld4, c = (i - cl * ld4) << 2;
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int cc = c + k;
+        float val = 0.0f;
+        if (cc < A) val = sh_g[(cl * A + cc) * 5];
+        else if (cc >= box0 && cc < used) val = sh_g[(cl * A + ((cc - box0) >> 2)) * 5 + 1 + ((cc - box0) & 3)];
+        v[k] = val;
       }
-      // class loss: cross entropy on positives (tools.py:264)
-      const int co = A + a * C;
-      if (mask > 0.0f) {
-        const int gt = (int)t[1];
-        float m = -INFINITY;
-        for (int c = lane; c < C; c += 32) m = fmaxf(m, raw[co + c]);
-        m = warp_max(m);
-        float s = 0.0f;
-        for (int c = lane; c < C; c += 32) s += expf(raw[co + c] - m);
-        s = warp_sum(s);
-        l_cls = logf(s) + m - raw[co + gt];
-        const float inv_s = 1.0f / s;
-        for (int c = lane; c < C; c += 32)
-          g[co + c] = (expf(raw[co + c] - m) * inv_s - (c == gt ? 1.0f : 0.0f)) * invB;
-      } else {
-        for (int c = lane; c < C; c += 32) g[co + c] = 0.0f;
-      }
-      if (lane == 0) {
-        g[a] = g_conf;
-        acc[0] += l_conf; acc[1] += l_cls; acc[2] += l_box; acc[3] += l_iou;
-      }
-      if (lane < 4) g[bo + lane] = lane == 0 ? g_tx : (lane == 1 ? g_ty : (lane == 2 ? g_tw : g_th));
+      reinterpret_cast<float4*>(g + (long long)cl * p.ld)[c >> 2] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  } else {
+    for (int i = threadIdx.x; i < ncell * p.ld; i += kLossThreads) {
+      const int cl = i / p.ld, cc = i - cl * p.ld;
+      float val = 0.0f;
+      if (cc < A) val = sh_g[(cl * A + cc) * 5];
+      else if (cc >= box0 && cc < used) val = sh_g[(cl * A + ((cc - box0) >> 2)) * 5 + 1 + ((cc - box0) & 3)];
+      g[(long long)cl * p.ld + cc] = val;
     }
   }
+  __syncthreads();
 
-  __shared__ double part[kLossThreads / 32][4];
-  if (lane == 0) {
+  // phase 3: class loss of the positives: cross entropy (tools.py:264), one warp per positive.
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = warp; i < nanch; i += kLossThreads / 32) {      // fixed anchor -> warp map: deterministic sums
+    if (!(sh_t[i * 11] > 0.0f)) continue;
+    const int cl = i / A, a = i - cl * A;
+    const float* __restrict__ row = raw + (long long)cl * p.ld + A + a * C;
+    float* __restrict__ grow = g + (long long)cl * p.ld + A + a * C;
+    const int gt = (int)sh_t[i * 11 + 1];
+    float m = -INFINITY;
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, row[c]);
+    m = warp_max(m);
+    float s = 0.0f;
+    for (int c = lane; c < C; c += 32) s += expf(row[c] - m);
+    s = warp_sum(s);
+    const float inv_s = 1.0f / s;
+    for (int c = lane; c < C; c += 32) grow[c] = (expf(row[c] - m) * inv_s - (c == gt ? 1.0f : 0.0f)) * invB;
+    if (lane == 0) l_cls += logf(s) + m - row[gt];
+  }
+
+  // block partial of the four sums (float per thread, double across threads; fixed order)
+  float acc[4] = {l_conf, l_cls, l_box, l_iou};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) part[warp_in_block][k] = (double)acc[k];
+  for (int k = 0; k < 4; ++k) {
+    const float wsum = warp_sum(acc[k]);
+    if (lane == 0) part[warp][k] = (double)wsum;
   }
   __syncthreads();
   if (threadIdx.x < 4) {
@@ -187,11 +231,21 @@ __global__ void train_loss_finalize_kernel(const double* __restrict__ partials, 
   }
 }
 
+inline int train_loss_blocks(int batch, int input_size) {
+  int tiles = 0;
+  for (int s = 8; s <= 32; s *= 2) tiles += ((input_size / s) * (input_size / s) + kLossCells - 1) / kLossCells;
+  return tiles * batch;
+}
+
 inline cudaError_t launch_train_loss(TrainLossParams p, float* losses, cudaStream_t st) {
-  const long long rows = (long long)p.B * p.cells_total;
-  const long long need = (rows + kLossThreads / 32 - 1) / (kLossThreads / 32);
-  const int blocks = (int)(need < kLossBlocks ? need : kLossBlocks);
-  train_loss_kernel<<<blocks, kLossThreads, 0, st>>>(p);
+  p.tiles_per_image = 0;
+  for (int l = 0; l < 3; ++l) {
+    p.tiles[l] = (p.cells[l] + kLossCells - 1) / kLossCells;
+    p.tiles_per_image += p.tiles[l];
+  }
+  const int blocks = p.tiles_per_image * p.B;
+  const size_t smem = (size_t)kLossCells * p.A * (11 + 5) * sizeof(float);
+  train_loss_kernel<<<blocks, kLossThreads, smem, st>>>(p);
   YNB_COUNT_LAUNCH();
   train_loss_finalize_kernel<<<1, 128, 0, st>>>(p.partials, blocks, p.B, losses);
   YNB_COUNT_LAUNCH();
@@ -320,8 +374,11 @@ inline cudaError_t launch_build_targets(const TargetParams& p, cudaStream_t st) 
 
 // ---- backward of the depthwise 3x3 convolution (config 5: "backward of the dw/pw conv kernels") -----
 // Forward (ynb_dwconv3x3): out[b,y,x,c] = bias[c] + sum_t w[t][c] * in[b, y*s+dy-1, x*s+dx-1, c].
-// NHWC, channels innermost: a thread owns 4 channels of one pixel (16-byte accesses).
 //   dIn[b,yi,xi,c] = sum_t w[t][c] * dOut[b, (yi+1-dy)/s, (xi+1-dx)/s, c]   (where divisible and inside)
+// Stride 1 is the forward convolution of dOut with the taps reversed: it runs on the TMA halo-tile kernel
+// of the forward path (dwconv3x3_tma_kernel<1, true>).  This kernel is the stride-2 / unaligned path:
+// NHWC, a thread owns 4 channels of one input pixel (16-byte accesses when VEC).
+template <bool VEC>
 __global__ void __launch_bounds__(256) dwconv3x3_bwd_data_kernel(const float* __restrict__ dout, int do_ld, int do_off,
                                                                  float* __restrict__ din, int di_ld, int di_off,
                                                                  const float* __restrict__ w, int B, int h_in, int w_in,
@@ -352,144 +409,252 @@ __global__ void __launch_bounds__(256) dwconv3x3_bwd_data_kernel(const float* __
         if (xo >= w_out) continue;
         const float* dp = dout + (((long long)b * h_out + yo) * w_out + xo) * do_ld + do_off + c;
         const float* wp = w + (dy * 3 + dx) * C + c;
+        if (VEC) {
+          const float4 d = *reinterpret_cast<const float4*>(dp);
+          const float4 k = __ldg(reinterpret_cast<const float4*>(wp));
+          acc[0] = fmaf(k.x, d.x, acc[0]); acc[1] = fmaf(k.y, d.y, acc[1]);
+          acc[2] = fmaf(k.z, d.z, acc[2]); acc[3] = fmaf(k.w, d.w, acc[3]);
+        } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (c + k < C) acc[k] = fmaf(wp[k], dp[k], acc[k]);
+          for (int k = 0; k < 4; ++k)
+            if (c + k < C) acc[k] = fmaf(wp[k], dp[k], acc[k]);
+        }
       }
     }
     float* op = din + (((long long)b * h_in + yi) * w_in + xi) * di_ld + di_off + c;
+    if (VEC) {
+      *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    } else {
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (c + k < C) op[k] = acc[k];
+      for (int k = 0; k < 4; ++k)
+        if (c + k < C) op[k] = acc[k];
+    }
   }
 }
 
 //   dW[t][c] = sum_{b,y,x} dOut[b,y,x,c] * in[b, y*s+dy-1, x*s+dx-1, c];  dBias[c] = sum dOut[b,y,x,c]
-// Stage 1: block (row-chunk j, channel group) accumulates 10 sums per channel over its output rows in
-// registers (thread = channel x pixel-slice), reduces across the pixel slices in shared memory and
-// writes partial[j][10][C].  Stage 2 (reduce_partials_kernel) sums the chunks in fixed order.
-constexpr int kDwBwdChan = 32;     // channels per block (x)
-constexpr int kDwBwdSlices = 8;    // pixel slices per block (y)
-__global__ void __launch_bounds__(kDwBwdChan * kDwBwdSlices)
+// Work item = a segment of kDwSeg consecutive outputs of one output row.  A thread owns 4 channels
+// (16-byte loads) and walks its segment with a 3x3 register window of the input that slides by
+// `stride` columns (3 | 6 new loads per output instead of 9), accumulating its 10 float4 sums in
+// registers over all the items of its slice; the block (16 channel groups x 8 slices) reduces the slices
+// in shared memory and writes partial[blockIdx.x][10][C].  Stage 2 (reduce_partials_kernel) sums the
+// blocks in fixed order: deterministic, no float atomics.
+constexpr int kDwBwdCg = 16;       // 4-channel groups per block (64 channels)
+constexpr int kDwBwdSlices = 8;
+constexpr int kDwSeg = 16;
+template <int STRIDE, bool VEC>
+__global__ void __launch_bounds__(kDwBwdCg * kDwBwdSlices)
 dwconv3x3_bwd_weight_kernel(const float* __restrict__ dout, int do_ld, int do_off, const float* __restrict__ in, int in_ld,
-                            int in_off, float* __restrict__ partial, int B, int h_in, int w_in, int C, int stride,
-                            int rows_per_chunk) {
-  const int h_out = (h_in - 1) / stride + 1, w_out = (w_in - 1) / stride + 1;
-  const int c = blockIdx.y * kDwBwdChan + threadIdx.x;
-  const long long rows = (long long)B * h_out;                 // (b, yo) rows
-  const long long r0 = (long long)blockIdx.x * rows_per_chunk;
-  const long long r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
-  float acc[10];
+                            int in_off, float* __restrict__ partial, int B, int h_in, int w_in, int C) {
+  const int h_out = (h_in - 1) / STRIDE + 1, w_out = (w_in - 1) / STRIDE + 1;
+  const int segs = (w_out + kDwSeg - 1) / kDwSeg;
+  const long long items = (long long)B * h_out * segs;
+  const int c = (blockIdx.y * kDwBwdCg + threadIdx.x) * 4;
+  float4 acc[10];
 #pragma unroll
-  for (int k = 0; k < 10; ++k) acc[k] = 0.0f;
+  for (int k = 0; k < 10; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto ld4 = [&](const float* q) -> float4 {
+    if (VEC) return *reinterpret_cast<const float4*>(q);
+    return make_float4(q[0], c + 1 < C ? q[1] : 0.f, c + 2 < C ? q[2] : 0.f, c + 3 < C ? q[3] : 0.f);
+  };
   if (c < C) {
-    for (long long r = r0; r < r1; ++r) {
+    for (long long it = (long long)blockIdx.x * kDwBwdSlices + threadIdx.y; it < items;
+         it += (long long)gridDim.x * kDwBwdSlices) {
+      const int seg = (int)(it % segs);
+      const long long r = it / segs;
       const int b = (int)(r / h_out), yo = (int)(r % h_out);
-      for (int xo = threadIdx.y; xo < w_out; xo += kDwBwdSlices) {
-        const float d = dout[(((long long)b * h_out + yo) * w_out + xo) * do_ld + do_off + c];
-        acc[9] += d;
+      const int x0 = seg * kDwSeg, x1 = min(x0 + kDwSeg, w_out);
+      const float* drow = dout + (((long long)b * h_out + yo) * w_out) * do_ld + do_off + c;
+      const float* irow[3];
+      bool rok[3];
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        const int yi = yo * STRIDE + dy - 1;
+        rok[dy] = yi >= 0 && yi < h_in;
+        irow[dy] = in + (((long long)b * h_in + (rok[dy] ? yi : 0)) * w_in) * in_ld + in_off + c;
+      }
+      float4 win[3][3];
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      // columns x0*S-1, x0*S of the first window (the third arrives in the loop's load step)
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+        for (int j = 0; j < 3 - STRIDE; ++j) {
+          const int xi = x0 * STRIDE - 1 + j + (STRIDE - 1) * 0;
+          win[dy][j + STRIDE] = (rok[dy] && xi >= 0 && xi < w_in) ? ld4(irow[dy] + (long long)xi * in_ld) : z4;
+        }
+      }
+      for (int xo = x0; xo < x1; ++xo) {
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
-          const int yi = yo * stride + dy - 1;
-          if (yi < 0 || yi >= h_in) continue;
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            const int xi = xo * stride + dx - 1;
-            if (xi < 0 || xi >= w_in) continue;
-            acc[dy * 3 + dx] = fmaf(d, in[(((long long)b * h_in + yi) * w_in + xi) * in_ld + in_off + c], acc[dy * 3 + dx]);
+          for (int j = 0; j < 3 - STRIDE; ++j) win[dy][j] = win[dy][j + STRIDE];     // slide
+#pragma unroll
+          for (int j = 3 - STRIDE; j < 3; ++j) {
+            const int xi = xo * STRIDE - 1 + j;
+            win[dy][j] = (rok[dy] && xi >= 0 && xi < w_in) ? ld4(irow[dy] + (long long)xi * in_ld) : z4;
           }
         }
+        const float4 d = ld4(drow + (long long)xo * do_ld);
+        acc[9].x += d.x; acc[9].y += d.y; acc[9].z += d.z; acc[9].w += d.w;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            float4& a = acc[dy * 3 + dx];
+            const float4 v = win[dy][dx];
+            a.x = fmaf(d.x, v.x, a.x); a.y = fmaf(d.y, v.y, a.y); a.z = fmaf(d.z, v.z, a.z); a.w = fmaf(d.w, v.w, a.w);
+          }
       }
     }
   }
-  __shared__ float sh[kDwBwdSlices][10][kDwBwdChan];
+  __shared__ float4 sh[kDwBwdSlices][10][kDwBwdCg];
 #pragma unroll
   for (int k = 0; k < 10; ++k) sh[threadIdx.y][k][threadIdx.x] = acc[k];
   __syncthreads();
   for (int k = threadIdx.y; k < 10; k += kDwBwdSlices) {
-    float s = 0.0f;
-    for (int j = 0; j < kDwBwdSlices; ++j) s += sh[j][k][threadIdx.x];
-    if (c < C) partial[((long long)blockIdx.x * 10 + k) * C + c] = s;
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < kDwBwdSlices; ++j) {
+      const float4 v = sh[j][k][threadIdx.x];
+      s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+    }
+    float* q = partial + ((long long)blockIdx.x * 10 + k) * C + c;
+    const float vals[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (c + e < C) q[e] = vals[e];
   }
 }
 
-// out[i] = sum_j partial[j][i], j in fixed order (deterministic second stage of the weight gradients).
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int chunks, long long elems, float* __restrict__ out) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < elems; i += (long long)gridDim.x * blockDim.x) {
-    float s = 0.0f;
-    for (int j = 0; j < chunks; ++j) s += partial[(long long)j * elems + i];
-    out[i] = s;
+// out[i] = sum_j partial[j][i]: 32 elements x 32 chunk slices per block, fixed summation order
+// (deterministic second stage of the weight gradients; the slices keep the serial chain short).
+constexpr int kRedSlices = 32;
+__global__ void __launch_bounds__(32 * kRedSlices) reduce_partials_kernel(const float* __restrict__ partial, int chunks,
+                                                                          long long elems, float* __restrict__ out) {
+  __shared__ float sh[kRedSlices][33];
+  const long long i = (long long)blockIdx.x * 32 + threadIdx.x;
+  float s = 0.0f;
+  if (i < elems)
+    for (int j = threadIdx.y; j < chunks; j += kRedSlices) s += partial[(long long)j * elems + i];
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < elems) {
+    float t = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kRedSlices; ++j) t += sh[j][threadIdx.x];
+    out[i] = t;
   }
 }
+inline void launch_reduce_partials(const float* partial, int chunks, long long elems, float* out, cudaStream_t st) {
+  reduce_partials_kernel<<<(unsigned)((elems + 31) / 32), dim3(32, kRedSlices), 0, st>>>(partial, chunks, elems, out);
+  YNB_COUNT_LAUNCH();
+}
 
-inline int dw_bwd_chunks(int B, int h_out) {
-  const long long rows = (long long)B * h_out;
-  long long chunks = kNumSMs * 2;
-  if (chunks > rows) chunks = rows;
-  return (int)chunks;
+inline int dw_bwd_chunks(int B, int h_out, int w_out) {
+  const long long items = (long long)B * h_out * ((w_out + kDwSeg - 1) / kDwSeg);
+  long long chunks = (items + kDwBwdSlices - 1) / kDwBwdSlices;
+  if (chunks > kNumSMs * 3) chunks = kNumSMs * 3;
+  return (int)(chunks < 1 ? 1 : chunks);
 }
 
 // ---- backward of the pointwise conv w.r.t. its weights -----------------------------------------------
 // dW[n][k] = sum_m dOut[m, n] * in[m, k];  dBias[n] = sum_m dOut[m, n].   (dIn = dOut . W is the forward
 // GEMM with the transposed weight matrix: ynb_pwconv / ynb_pwconv_tc.)
-// A reduction over M (10^4 ... 10^6 pixels) into a small N x K matrix: block (chunk of M, 64 x 64 tile of
-// (n, k)) stages 32-pixel slabs of dOut and in through shared memory, each thread owns a 4 x 4
-// register tile; partial[chunk][N][K] is summed in fixed order by reduce_partials_kernel.
-constexpr int kPwBwdTile = 64;
-constexpr int kPwBwdSlab = 32;
+// A reduction over M (10^4 ... 10^6 pixels) into a small N x K matrix, fp32 FFMA: block = (chunk of M,
+// 128 x 128 tile of (n, k)); 16-pixel slabs of dOut and in go through shared memory (next slab
+// prefetched into registers while the current one is multiplied), each thread owns an 8 x 8 register
+// tile (two 4-wide column groups 64 apart: conflict-free 16-byte shared loads).  partial[chunk][N][K] is
+// summed in fixed order by reduce_partials_kernel.
+constexpr int kPwBwdTile = 128;
+constexpr int kPwBwdSlab = 16;
 __global__ void __launch_bounds__(256) pwconv_bwd_weight_kernel(const float* __restrict__ dout, int do_ld, int do_off,
                                                                 const float* __restrict__ in, int in_ld, int in_off,
                                                                 float* __restrict__ partial_w, float* __restrict__ partial_b,
-                                                                long long M, int K, int N, long long m_per_chunk) {
-  __shared__ float sd[kPwBwdSlab][kPwBwdTile + 4];
-  __shared__ float sx[kPwBwdSlab][kPwBwdTile + 4];
+                                                                long long M, int K, int N, long long m_per_chunk, int vec) {
+  __shared__ __align__(16) float sd[kPwBwdSlab][kPwBwdTile];
+  __shared__ __align__(16) float sx[kPwBwdSlab][kPwBwdTile];
   const int n0 = blockIdx.y * kPwBwdTile, k0 = blockIdx.z * kPwBwdTile;
   const long long m0 = (long long)blockIdx.x * m_per_chunk;
   const long long m1 = m0 + m_per_chunk < M ? m0 + m_per_chunk : M;
   const int tn = (threadIdx.x >> 4) * 4, tk = (threadIdx.x & 15) * 4;
-  float acc[4][4];
+  // loader role: 512 float4 per operand per slab = 2 per thread: row = idx / 32, col4 = idx % 32
+  const int lr0 = threadIdx.x >> 5, lc = (threadIdx.x & 31) * 4;      // rows lr0 and lr0 + 8
+  float acc[8][8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-  float bsum = 0.0f;                                        // threads 0..63 (k-tile 0 only): bias gradient
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+  float bsum = 0.0f;                                        // threads 0..127 of k-tile 0: bias gradient
+  float4 pd[2], px[2];
+  auto fetch = [&](long long m) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const long long mm = m + lr0 + 8 * h;
+      float4 d = make_float4(0.f, 0.f, 0.f, 0.f), x = d;
+      if (mm < m1) {
+        const float* dp = dout + mm * do_ld + do_off + n0 + lc;
+        const float* xp = in + mm * in_ld + in_off + k0 + lc;
+        if (vec) {
+          if (n0 + lc < N) d = *reinterpret_cast<const float4*>(dp);
+          if (k0 + lc < K) x = *reinterpret_cast<const float4*>(xp);
+        } else {
+          if (n0 + lc < N) d.x = dp[0];
+          if (n0 + lc + 1 < N) d.y = dp[1];
+          if (n0 + lc + 2 < N) d.z = dp[2];
+          if (n0 + lc + 3 < N) d.w = dp[3];
+          if (k0 + lc < K) x.x = xp[0];
+          if (k0 + lc + 1 < K) x.y = xp[1];
+          if (k0 + lc + 2 < K) x.z = xp[2];
+          if (k0 + lc + 3 < K) x.w = xp[3];
+        }
+      }
+      pd[h] = d; px[h] = x;
+    }
+  };
+  fetch(m0);
   for (long long m = m0; m < m1; m += kPwBwdSlab) {
-    for (int i = threadIdx.x; i < kPwBwdSlab * kPwBwdTile; i += 256) {
-      const int r = i / kPwBwdTile, cidx = i % kPwBwdTile;
-      const long long mm = m + r;
-      sd[r][cidx] = (mm < m1 && n0 + cidx < N) ? dout[mm * do_ld + do_off + n0 + cidx] : 0.0f;
-      sx[r][cidx] = (mm < m1 && k0 + cidx < K) ? in[mm * in_ld + in_off + k0 + cidx] : 0.0f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      *reinterpret_cast<float4*>(&sd[lr0 + 8 * h][lc]) = pd[h];
+      *reinterpret_cast<float4*>(&sx[lr0 + 8 * h][lc]) = px[h];
     }
     __syncthreads();
-#pragma unroll 8
+    if (m + kPwBwdSlab < m1) fetch(m + kPwBwdSlab);
+#pragma unroll
     for (int r = 0; r < kPwBwdSlab; ++r) {
-      const float4 dv = *reinterpret_cast<const float4*>(&sd[r][tn]);
-      const float4 xv = *reinterpret_cast<const float4*>(&sx[r][tk]);
-      const float dd[4] = {dv.x, dv.y, dv.z, dv.w}, xx[4] = {xv.x, xv.y, xv.z, xv.w};
+      const float4 d0 = *reinterpret_cast<const float4*>(&sd[r][tn]), d1 = *reinterpret_cast<const float4*>(&sd[r][tn + 64]);
+      const float4 x0 = *reinterpret_cast<const float4*>(&sx[r][tk]), x1 = *reinterpret_cast<const float4*>(&sx[r][tk + 64]);
+      const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+      const float xx[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(dd[i], xx[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(dd[i], xx[j], acc[i][j]);
     }
     if (blockIdx.z == 0 && threadIdx.x < kPwBwdTile) {
+#pragma unroll
       for (int r = 0; r < kPwBwdSlab; ++r) bsum += sd[r][threadIdx.x];
     }
     __syncthreads();
   }
   float* pw = partial_w + (long long)blockIdx.x * N * K;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i) {
+    const int n = n0 + tn + (i & 3) + (i >> 2) * 64;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (n0 + tn + i < N && k0 + tk + j < K) pw[(long long)(n0 + tn + i) * K + k0 + tk + j] = acc[i][j];
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + tk + (j & 3) + (j >> 2) * 64;
+      if (n < N && k < K) pw[(long long)n * K + k] = acc[i][j];
+    }
+  }
   if (blockIdx.z == 0 && threadIdx.x < kPwBwdTile && n0 + threadIdx.x < N)
     partial_b[(long long)blockIdx.x * N + n0 + threadIdx.x] = bsum;
 }
 
 inline int pw_bwd_chunks(long long M, int K, int N) {
   const int tiles = ((N + kPwBwdTile - 1) / kPwBwdTile) * ((K + kPwBwdTile - 1) / kPwBwdTile);
-  long long chunks = (kNumSMs * 4 + tiles - 1) / tiles;       // ~4 blocks per SM in total
-  const long long max_chunks = (M + kPwBwdSlab - 1) / kPwBwdSlab;
+  long long chunks = (kNumSMs * 2 + tiles - 1) / tiles;       // ~2 blocks per SM in total
+  const long long max_chunks = (M + 4 * kPwBwdSlab - 1) / (4 * kPwBwdSlab);
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
   return (int)chunks;

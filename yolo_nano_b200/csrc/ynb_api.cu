@@ -1492,7 +1492,9 @@ bool level_geometry(int input_size, int grid[3], int stride[3]) {
 }
 }  // namespace
 
-YNB_EXPORT int64_t ynb_train_loss_workspace_bytes(void) { return (int64_t)kLossBlocks * 4 * sizeof(double); }
+YNB_EXPORT int64_t ynb_train_loss_workspace_bytes(int32_t batch, int32_t input_size) {
+  return (int64_t)train_loss_blocks(batch, input_size) * 4 * sizeof(double);
+}
 
 YNB_EXPORT int ynb_train_loss(const float* raw_s, const float* raw_m, const float* raw_l, int32_t raw_ld,
                               const float* target, int32_t batch, int32_t input_size, const float* anchors_wh,
@@ -1501,8 +1503,8 @@ YNB_EXPORT int ynb_train_loss(const float* raw_s, const float* raw_m, const floa
   TrainLossParams p{};
   if (!raw_s || !raw_m || !raw_l || !target || !anchors_wh || !losses || !grad_s || !grad_m || !grad_l || !ws ||
       batch <= 0 || num_anchors <= 0 || num_anchors > kTrainMaxAnchors || num_classes <= 0 ||
-      raw_ld < num_anchors * (1 + num_classes + 4) || ws_bytes < ynb_train_loss_workspace_bytes() ||
-      !level_geometry(input_size, p.grid, p.stride))
+      raw_ld < num_anchors * (1 + num_classes + 4) || !level_geometry(input_size, p.grid, p.stride) ||
+      ws_bytes < ynb_train_loss_workspace_bytes(batch, input_size))
     return fail(nullptr, YNB_ERR_INVALID, "ynb_train_loss: bad arguments / workspace too small");
   p.raw[0] = raw_s; p.raw[1] = raw_m; p.raw[2] = raw_l;
   p.grad[0] = grad_s; p.grad[1] = grad_m; p.grad[2] = grad_l;
@@ -1560,39 +1562,57 @@ YNB_EXPORT int ynb_dwconv3x3_bwd_data(const float* dout, int32_t do_ld, int32_t 
                                       int32_t channels, int32_t stride, void* stream) {
   if (!dout || !din || !w || batch <= 0 || h_in <= 0 || w_in <= 0 || channels <= 0 || (stride != 1 && stride != 2))
     return fail(nullptr, YNB_ERR_INVALID, "ynb_dwconv3x3_bwd_data: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = channels % 4 == 0 && do_ld % 4 == 0 && do_off % 4 == 0 && di_ld % 4 == 0 && di_off % 4 == 0 &&
+                   ((uintptr_t)dout | (uintptr_t)din | (uintptr_t)w) % 16 == 0;
+  CUtensorMap tm;
+  if (stride == 1 && vec && !getenv("YNB_DW_NO_TMA") &&
+      make_tmap_dw(&tm, dout, do_ld, do_off, batch, h_in, w_in, channels, 1)) {
+    // stride 1: the forward convolution of d_out with the taps reversed, on the TMA halo-tile kernel
+    UNIT_TRY(launch_dwconv3x3_tma(tm, din, di_ld, di_off, w, nullptr, batch, h_in, w_in, channels, 1, YNB_ACT_NONE, st,
+                                  /*reversed_taps=*/true));
+    return YNB_OK;
+  }
   const long long total = (long long)batch * h_in * w_in * ((channels + 3) / 4);
   const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
-  dwconv3x3_bwd_data_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dout, do_ld, do_off, din, di_ld, di_off, w, batch,
-                                                                      h_in, w_in, channels, stride);
+  if (vec)
+    dwconv3x3_bwd_data_kernel<true><<<blocks, 256, 0, st>>>(dout, do_ld, do_off, din, di_ld, di_off, w, batch, h_in, w_in,
+                                                            channels, stride);
+  else
+    dwconv3x3_bwd_data_kernel<false><<<blocks, 256, 0, st>>>(dout, do_ld, do_off, din, di_ld, di_off, w, batch, h_in, w_in,
+                                                             channels, stride);
   YNB_COUNT_LAUNCH();
   UNIT_TRY(cudaGetLastError());
   return YNB_OK;
 }
 
-YNB_EXPORT int64_t ynb_dwconv3x3_bwd_weight_workspace_bytes(int32_t batch, int32_t h_in, int32_t channels, int32_t stride) {
-  const int h_out = (h_in - 1) / stride + 1;
-  return (int64_t)dw_bwd_chunks(batch, h_out) * 10 * channels * sizeof(float);
+YNB_EXPORT int64_t ynb_dwconv3x3_bwd_weight_workspace_bytes(int32_t batch, int32_t h_in, int32_t w_in, int32_t channels,
+                                                            int32_t stride) {
+  const int h_out = (h_in - 1) / stride + 1, w_out = (w_in - 1) / stride + 1;
+  return (int64_t)dw_bwd_chunks(batch, h_out, w_out) * 10 * channels * sizeof(float);
 }
 
 YNB_EXPORT int ynb_dwconv3x3_bwd_weight(const float* dout, int32_t do_ld, int32_t do_off, const float* in, int32_t in_ld,
                                         int32_t in_off, float* dwdb, int32_t batch, int32_t h_in, int32_t w_in,
                                         int32_t channels, int32_t stride, void* ws, int64_t ws_bytes, void* stream) {
   if (!dout || !in || !dwdb || !ws || batch <= 0 || h_in <= 0 || w_in <= 0 || channels <= 0 ||
-      (stride != 1 && stride != 2) || ws_bytes < ynb_dwconv3x3_bwd_weight_workspace_bytes(batch, h_in, channels, stride))
+      (stride != 1 && stride != 2) ||
+      ws_bytes < ynb_dwconv3x3_bwd_weight_workspace_bytes(batch, h_in, w_in, channels, stride))
     return fail(nullptr, YNB_ERR_INVALID, "ynb_dwconv3x3_bwd_weight: bad arguments / workspace too small");
-  const int h_out = (h_in - 1) / stride + 1;
-  const int chunks = dw_bwd_chunks(batch, h_out);
-  const long long rows = (long long)batch * h_out;
-  const int rows_per_chunk = (int)((rows + chunks - 1) / chunks);
-  dim3 grid(chunks, (channels + kDwBwdChan - 1) / kDwBwdChan), block(kDwBwdChan, kDwBwdSlices);
+  const int h_out = (h_in - 1) / stride + 1, w_out = (w_in - 1) / stride + 1;
+  const int chunks = dw_bwd_chunks(batch, h_out, w_out);
+  const bool vec = channels % 4 == 0 && do_ld % 4 == 0 && do_off % 4 == 0 && in_ld % 4 == 0 && in_off % 4 == 0 &&
+                   ((uintptr_t)dout | (uintptr_t)in) % 16 == 0;
+  dim3 grid(chunks, (channels + kDwBwdCg * 4 - 1) / (kDwBwdCg * 4)), block(kDwBwdCg, kDwBwdSlices);
   cudaStream_t st = (cudaStream_t)stream;
-  UNIT_TRY(cudaMemsetAsync(ws, 0, (size_t)chunks * 10 * channels * sizeof(float), st));
-  dwconv3x3_bwd_weight_kernel<<<grid, block, 0, st>>>(dout, do_ld, do_off, in, in_ld, in_off, (float*)ws, batch, h_in,
-                                                      w_in, channels, stride, rows_per_chunk);
+  float* part = (float*)ws;
+#define YNB_DWBW(S, V) \
+  dwconv3x3_bwd_weight_kernel<S, V><<<grid, block, 0, st>>>(dout, do_ld, do_off, in, in_ld, in_off, part, batch, h_in, w_in, channels)
+  if (stride == 1) { if (vec) YNB_DWBW(1, true); else YNB_DWBW(1, false); }
+  else             { if (vec) YNB_DWBW(2, true); else YNB_DWBW(2, false); }
+#undef YNB_DWBW
   YNB_COUNT_LAUNCH();
-  const long long elems = 10LL * channels;
-  reduce_partials_kernel<<<(int)((elems + 127) / 128), 128, 0, st>>>((const float*)ws, chunks, elems, dwdb);
-  YNB_COUNT_LAUNCH();
+  launch_reduce_partials(part, chunks, 10LL * channels, dwdb, st);
   UNIT_TRY(cudaGetLastError());
   return YNB_OK;
 }
@@ -1613,16 +1633,15 @@ YNB_EXPORT int ynb_pwconv_bwd_weight(const float* dout, int32_t do_ld, int32_t d
   float* pw = (float*)ws;
   float* pb = pw + (long long)chunks * cout * cin;
   cudaStream_t st = (cudaStream_t)stream;
-  UNIT_TRY(cudaMemsetAsync(ws, 0, (size_t)chunks * ((size_t)cout * cin + cout) * sizeof(float), st));
+  // a chunk past the end of M (rounding of m_per_chunk) writes zeros: no memset needed
+  const int vec = cin % 4 == 0 && cout % 4 == 0 && do_ld % 4 == 0 && do_off % 4 == 0 && in_ld % 4 == 0 &&
+                  in_off % 4 == 0 && ((uintptr_t)dout | (uintptr_t)in) % 16 == 0;
   dim3 grid(chunks, (cout + kPwBwdTile - 1) / kPwBwdTile, (cin + kPwBwdTile - 1) / kPwBwdTile);
   pwconv_bwd_weight_kernel<<<grid, 256, 0, st>>>(dout, do_ld, do_off, in, in_ld, in_off, pw, pb, pixels, cin, cout,
-                                                 m_per_chunk);
+                                                 m_per_chunk, vec);
   YNB_COUNT_LAUNCH();
-  const long long ew = (long long)cout * cin;
-  reduce_partials_kernel<<<(int)std::min<long long>((ew + 127) / 128, kNumSMs * 8), 128, 0, st>>>(pw, chunks, ew, dw);
-  YNB_COUNT_LAUNCH();
-  reduce_partials_kernel<<<(cout + 127) / 128, 128, 0, st>>>(pb, chunks, cout, db);
-  YNB_COUNT_LAUNCH();
+  launch_reduce_partials(pw, chunks, (long long)cout * cin, dw, st);
+  launch_reduce_partials(pb, chunks, cout, db, st);
   UNIT_TRY(cudaGetLastError());
   return YNB_OK;
 }

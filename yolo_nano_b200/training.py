@@ -74,7 +74,7 @@ def train_loss(raw: Sequence[torch.Tensor], target: torch.Tensor, input_size: in
         raise EngineError("target must be [B, N, 11]")
     grads = tuple(torch.empty_like(r) for r in raw)
     losses = torch.empty(4, device=dev, dtype=torch.float32)
-    wsb = lib.ynb_train_loss_workspace_bytes()
+    wsb = lib.ynb_train_loss_workspace_bytes(b, input_size)
     ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
     _check(lib.ynb_train_loss(_ptr(raw[0]), _ptr(raw[1]), _ptr(raw[2]), ld, _ptr(target), b, input_size, anc, a,
                               num_classes, _ptr(losses), _ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2]),
@@ -127,7 +127,7 @@ def dwconv3x3_backward(dout: torch.Tensor, x: torch.Tensor, w9c: torch.Tensor, s
     dx = torch.empty_like(x)
     _check(lib.ynb_dwconv3x3_bwd_data(_ptr(dout), c, 0, _ptr(dx), c, 0, _ptr(w9c), b, h, w, c, stride,
                                       _stream_ptr(dev)), "ynb_dwconv3x3_bwd_data")
-    wsb = lib.ynb_dwconv3x3_bwd_weight_workspace_bytes(b, h, c, stride)
+    wsb = lib.ynb_dwconv3x3_bwd_weight_workspace_bytes(b, h, w, c, stride)
     ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
     dwdb = torch.empty((10, c), device=dev, dtype=torch.float32)
     _check(lib.ynb_dwconv3x3_bwd_weight(_ptr(dout), c, 0, _ptr(x), c, 0, _ptr(dwdb), b, h, w, c, stride,
