@@ -302,6 +302,15 @@ int  ynb_train_loss(const float* raw_s_dev, const float* raw_m_dev, const float*
                     float* grad_m_dev, float* grad_l_dev, void* workspace_dev, int64_t workspace_bytes,
                     void* stream);
 
+/* YOLONano.forward(x, target) with trainable = True (models/yolo_nano.py:282-358) while the BatchNorm
+ * layers are in eval mode (running statistics, folded): backbone + neck + heads on the engine, then
+ * ynb_train_loss directly on the engine's head maps.  grad_*_dev: [B, H*W, ynb_raw_ld(e)].  BatchNorm
+ * with batch statistics (model.train()) is not built. */
+int32_t ynb_raw_ld(const ynb_engine* e);
+int  ynb_forward_train_loss(ynb_engine* e, const float* x_dev, int32_t batch, const float* target_dev,
+                            float* losses_dev, float* grad_s_dev, float* grad_m_dev, float* grad_l_dev,
+                            void* workspace_dev, int64_t workspace_bytes, void* stream);
+
 /* One torch.optim.SGD step (train.py:167-171,230) over a flat float32 vector of n elements:
  *   d = grad_scale * g + weight_decay * p;  buf = first_step ? d : momentum * buf + d;  p -= lr * buf.
  * grad_scale = 1 / world_size folds the averaging of the data-parallel all-reduce into the

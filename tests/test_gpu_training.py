@@ -177,3 +177,36 @@ def test_act_backward(G, TR, act):
     out.backward(dy)
     got = TR.act_backward(dy.to(G.DEV), out.detach().to(G.DEV), act)
     np.testing.assert_array_equal(got.cpu().numpy(), pre.grad.numpy())
+
+
+def test_forward_with_target_matches_reference_end_to_end(G, g7):
+    """model(x, target) with trainable=True on running-statistics BatchNorm: input images -> four losses
+    and head gradients, against the REAL reference run in the same state (fixture g7).  The network part
+    is the tensor-core path (3xTF32, raw head outputs within 1e-3 + 1e-4 rel), hence the looser bar."""
+    import contextlib, io
+    import yolo_nano_b200 as pkg
+    size, classes, seed = int(g7["size"]), int(g7["classes"]), int(g7["seed"])
+    sd = W.calibrated(classes, seed=seed)
+    x = W.synthetic_input(2, size, seed=seed)
+    assert W.digest(sd) == str(g7["sd_digest"]) and W.digest(x) == str(g7["x_digest"])
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = pkg.YOLONano(G.DEV, size, classes, anchor_size=W.anchors_for(classes))
+    m.load_state_dict(sd)
+    m = m.to(G.DEV)
+    m.trainable = True
+    with pytest.raises(NotImplementedError):          # BatchNorm with batch statistics is not built
+        m.train()(x.to(G.DEV), target=torch.from_numpy(g7["target"]).to(G.DEV))
+    m.eval()
+    ls = m(x.to(G.DEV), target=torch.from_numpy(g7["target"]).to(G.DEV))
+    got = np.array([float(v) for v in ls], dtype=np.float32)
+    np.testing.assert_allclose(got, g7["losses"], rtol=2e-3)
+    ch = 3 * (1 + classes + 4)
+    for k, g in zip(("pred_s", "pred_m", "pred_l"), m.head_gradients):
+        want = g7["grad_" + k]
+        b, _, h, w = want.shape
+        gg = g.cpu()[:, :, :ch].reshape(b, h, w, ch).permute(0, 3, 1, 2).numpy()
+        assert np.abs(gg - want).max() <= 3e-3 * np.abs(want).max(), k
+    # same weights, same input, the eval branch still works on the same model object
+    m.trainable = False
+    bboxes, scores, cls_inds = m(x[:1].to(G.DEV))
+    assert bboxes.shape[1] == 4 and len(scores) == len(cls_inds)

@@ -89,6 +89,8 @@ SIGNATURES = {
     "ynb_train_loss_workspace_bytes": (_i64, [_i32, _i32]),
     "ynb_train_loss": (C.c_int, [_p, _p, _p, _i32, _p, _i32, _i32, C.POINTER(_f), _i32, _i32, _p, _p, _p, _p,
                                  _p, _i64, _p]),
+    "ynb_raw_ld": (_i32, [_p]),
+    "ynb_forward_train_loss": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "ynb_sgd_step": (C.c_int, [_p, _p, _p, _i64, _f, _f, _f, _i32, _f, _p]),
     "ynb_dwconv3x3_bwd_data": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _p, _i32, _i32, _i32, _i32, _i32, _p]),
     "ynb_dwconv3x3_bwd_weight_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32]),

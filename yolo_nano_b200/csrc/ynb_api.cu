@@ -1659,3 +1659,45 @@ YNB_EXPORT int ynb_act_bwd(const float* dout, int32_t do_ld, int32_t do_off, con
   UNIT_TRY(cudaGetLastError());
   return YNB_OK;
 }
+
+// YOLONano.forward(x, target) with trainable = True and the BatchNorm layers in eval mode (running
+// statistics: the network part is the inference network): backbone + neck + heads on the tensor-core
+// path, then the loss / gradient kernel directly on the engine's NHWC head maps (no permute, no copy).
+YNB_EXPORT int ynb_forward_train_loss(ynb_engine* e, const float* x_dev, int32_t batch, const float* target,
+                                      float* losses, float* grad_s, float* grad_m, float* grad_l, void* ws,
+                                      int64_t ws_bytes, void* stream) {
+  if (!e || !x_dev || !target || !losses || !grad_s || !grad_m || !grad_l || !ws)
+    return fail(e, YNB_ERR_INVALID, "null argument");
+  if (ws_bytes < ynb_train_loss_workspace_bytes(batch, e->cfg.input_size))
+    return fail(e, YNB_ERR_INVALID, "ynb_forward_train_loss: workspace too small");
+  cudaStream_t user = (cudaStream_t)stream;
+  CounterScope cs(e);
+  Plan* plan = nullptr;
+  int rc = prepare(e, batch, &plan);
+  if (rc || (rc = enter(e, user)) || (rc = run_network(e, x_dev, plan))) return rc;
+  TrainLossParams p{};
+  level_geometry(e->cfg.input_size, p.grid, p.stride);
+  float* grads[3] = {grad_s, grad_m, grad_l};
+  int off = 0;
+  for (int l = 0; l < 3; ++l) {
+    p.raw[l] = e->raw[l].p; p.grad[l] = grads[l];
+    p.cells[l] = p.grid[l] * p.grid[l];
+    p.cell_off[l] = off;
+    off += p.cells[l];
+    for (int a = 0; a < e->cfg.num_anchors; ++a) {
+      p.anchors[l][a][0] = e->cfg.anchors[(l * e->cfg.num_anchors + a) * 2];
+      p.anchors[l][a][1] = e->cfg.anchors[(l * e->cfg.num_anchors + a) * 2 + 1];
+    }
+  }
+  p.cells_total = off;
+  p.target = target; p.partials = (double*)ws; p.ld = e->raw[0].ld; p.B = batch; p.A = e->cfg.num_anchors;
+  p.C = e->cfg.num_classes; p.S = e->cfg.input_size;
+  if (p.ld != ynb_raw_ld(e)) return fail(e, YNB_ERR_STATE, "ynb_forward_train_loss: head map stride changed");
+  CUDA_TRY(e, launch_train_loss(p, losses, e->s_main));
+  if ((rc = leave(e, user))) return rc;
+  return e->cfg.gemm_mode == YNB_GEMM_FP32_FFMA ? YNB_OK : check_device_error(e);
+}
+
+YNB_EXPORT int32_t ynb_raw_ld(const ynb_engine* e) {
+  return e ? round_up(e->cfg.num_anchors * (1 + e->cfg.num_classes + 4), 4) : 0;   // = plan_workspace's raw[l].ld
+}

@@ -143,6 +143,25 @@ class Engine:
                     "ynb_forward_raw")
         return outs
 
+    def forward_train_loss(self, x: torch.Tensor, target: torch.Tensor):
+        """backbone + neck + heads, then the training branch (models/yolo_nano.py:333-358) on the
+        engine's own NHWC head maps: (losses [4] on the device, gradients [B, H*W, ld] x 3)."""
+        x = self._check_input(x)
+        b, s = x.shape[0], self.input_size
+        n = self.num_boxes
+        if (not target.is_cuda or target.dtype != torch.float32 or not target.is_contiguous()
+                or tuple(target.shape) != (b, n, 11)):
+            raise EngineError(f"target must be a contiguous float32 CUDA tensor [B={b}, N={n}, 11]")
+        ld = int(self.lib.ynb_raw_ld(self._h))
+        grads = [torch.empty((b, (s // st) ** 2, ld), device=self.device, dtype=torch.float32) for st in (8, 16, 32)]
+        losses = torch.empty(4, device=self.device, dtype=torch.float32)
+        wsb = int(self.lib.ynb_train_loss_workspace_bytes(b, s))
+        ws = torch.empty(wsb, device=self.device, dtype=torch.uint8)
+        self._check(self.lib.ynb_forward_train_loss(self._h, _ptr(x), b, _ptr(target), _ptr(losses), _ptr(grads[0]),
+                                                    _ptr(grads[1]), _ptr(grads[2]), _ptr(ws), wsb,
+                                                    _stream_ptr(self.device)), "ynb_forward_train_loss")
+        return losses, grads
+
     def forward_decode(self, x: torch.Tensor):
         x = self._check_input(x)
         b, n = x.shape[0], self.num_boxes

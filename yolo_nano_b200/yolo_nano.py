@@ -317,8 +317,20 @@ class YOLONano(nn.Module):
 
     def forward(self, x, target=None):
         if self.trainable:
-            raise NotImplementedError(
-                "training branch (models/yolo_nano.py:333-358) is not built yet in this round; "
-                "set model.trainable = False for the detection forward path")
+            # training branch (models/yolo_nano.py:333-358).  Built for BatchNorm in eval mode (running
+            # statistics, folded into the convs): losses of the whole batch and, kept on the model as
+            # `head_gradients`, d(sum of the four)/d(raw head maps) — what train.py:222-229 back-propagates
+            # into the heads.  BatchNorm with batch statistics (model.train()) is not built.
+            if self.training:
+                raise NotImplementedError(
+                    "training-mode BatchNorm (batch statistics) is not built: call model.eval() and keep "
+                    "model.trainable = True for the loss branch on running statistics")
+            if target is None:
+                raise ValueError("trainable forward needs target [B, N, 11] (tools.multi_gt_creator)")
+            eng = self.engine(int(x.shape[0]))
+            dev = eng.device
+            losses, self.head_gradients = eng.forward_train_loss(
+                x.to(dev, torch.float32), target.to(dev, torch.float32).contiguous())
+            return losses[0], losses[1], losses[2], losses[3]
         # eval: the reference decodes image 0 only (models/yolo_nano.py:365-367)
         return self.detect(x[:1])[0]
