@@ -432,6 +432,57 @@ __global__ void __launch_bounds__(256) dwconv3x3_bwd_data_kernel(const float* __
   }
 }
 
+// Stride 2, aligned views: a thread owns the 2 x 2 input block (2p..2p+1, 2q..2q+1) of 4 channels.  By
+// parity an input pixel receives 1 / 2 / 2 / 4 taps, all from the four outputs (p..p+1, q..q+1): 4 loads
+// and 9 FMAs per channel for 4 pixels (the generic kernel walks 9 guarded taps per pixel).  The 9 x C
+// weights sit in shared memory.
+__global__ void __launch_bounds__(256) dwconv3x3_s2_bwd_data_kernel(const float* __restrict__ dout, int do_ld, int do_off,
+                                                                    float* __restrict__ din, int di_ld, int di_off,
+                                                                    const float* __restrict__ w, int B, int h_in, int w_in,
+                                                                    int C) {
+  extern __shared__ __align__(16) float sw[];            // [9][C]
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int c4n = C >> 2;
+  const int h_out = (h_in - 1) / 2 + 1, w_out = (w_in - 1) / 2 + 1;
+  const int hb = (h_in + 1) >> 1, wb = (w_in + 1) >> 1;
+  const long long total = (long long)B * hb * wb * c4n;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4n) * 4;
+    long long r = i / c4n;
+    const int q = (int)(r % wb);
+    r /= wb;
+    const int pp = (int)(r % hb);
+    const int b = (int)(r / hb);
+    const float* d00p = dout + (((long long)b * h_out + pp) * w_out + q) * do_ld + do_off + c;
+    const bool py = pp + 1 < h_out, qx = q + 1 < w_out;
+    const float4 d00 = *reinterpret_cast<const float4*>(d00p);
+    const float4 d01 = qx ? *reinterpret_cast<const float4*>(d00p + do_ld) : z4;
+    const float4 d10 = py ? *reinterpret_cast<const float4*>(d00p + (long long)w_out * do_ld) : z4;
+    const float4 d11 = (py && qx) ? *reinterpret_cast<const float4*>(d00p + (long long)(w_out + 1) * do_ld) : z4;
+    float4 k[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) k[t] = *reinterpret_cast<const float4*>(sw + t * C + c);
+    auto mul = [](const float4& a, const float4& x) { return make_float4(a.x * x.x, a.y * x.y, a.z * x.z, a.w * x.w); };
+    auto fma4 = [](const float4& a, const float4& x, const float4& y) {
+      return make_float4(fmaf(a.x, x.x, y.x), fmaf(a.y, x.y, y.y), fmaf(a.z, x.z, y.z), fmaf(a.w, x.w, y.w));
+    };
+    // tap order = ascending (dy, dx) as in the generic kernel: identical rounding
+    const float4 ee = mul(k[4], d00);
+    const float4 eo = fma4(k[5], d00, mul(k[3], d01));
+    const float4 oe = fma4(k[7], d00, mul(k[1], d10));
+    const float4 oo = fma4(k[8], d00, fma4(k[6], d01, fma4(k[2], d10, mul(k[0], d11))));
+    const int yi = 2 * pp, xi = 2 * q;
+    float* o = din + (((long long)b * h_in + yi) * w_in + xi) * di_ld + di_off + c;
+    const bool y1 = yi + 1 < h_in, x1 = xi + 1 < w_in;
+    *reinterpret_cast<float4*>(o) = ee;
+    if (x1) *reinterpret_cast<float4*>(o + di_ld) = eo;
+    if (y1) *reinterpret_cast<float4*>(o + (long long)w_in * di_ld) = oe;
+    if (y1 && x1) *reinterpret_cast<float4*>(o + (long long)(w_in + 1) * di_ld) = oo;
+  }
+}
+
 //   dW[t][c] = sum_{b,y,x} dOut[b,y,x,c] * in[b, y*s+dy-1, x*s+dx-1, c];  dBias[c] = sum dOut[b,y,x,c]
 // Work item = a segment of kDwSeg consecutive outputs of one output row.  A thread owns 4 channels
 // (16-byte loads) and walks its segment with a 3x3 register window of the input that slides by

@@ -1573,6 +1573,15 @@ YNB_EXPORT int ynb_dwconv3x3_bwd_data(const float* dout, int32_t do_ld, int32_t 
                                   /*reversed_taps=*/true));
     return YNB_OK;
   }
+  if (stride == 2 && vec && 9 * channels * 4 <= 48 * 1024) {
+    const long long items = (long long)batch * ((h_in + 1) / 2) * ((w_in + 1) / 2) * (channels / 4);
+    const int nb = (int)std::min<long long>((items + 255) / 256, (long long)kNumSMs * 8);
+    dwconv3x3_s2_bwd_data_kernel<<<nb, 256, 9 * channels * sizeof(float), st>>>(dout, do_ld, do_off, din, di_ld, di_off, w,
+                                                                               batch, h_in, w_in, channels);
+    YNB_COUNT_LAUNCH();
+    UNIT_TRY(cudaGetLastError());
+    return YNB_OK;
+  }
   const long long total = (long long)batch * h_in * w_in * ((channels + 3) / 4);
   const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
   if (vec)
