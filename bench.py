@@ -6,8 +6,9 @@ neck + heads + decode + NMS) on N B200s, batch-sharded, no collective.
     python bench.py --impl reference --gpus N ...             # CPU restatement of the reference
 
 A "step" is one pass of the hot path over one batch of synthetic images.  Workload at
-every N = BASELINE.json configs[1]: 416x416, 64 images per GPU, COCO-80, fp32 parity mode
-(tcgen05 3xTF32), reference random-init weights (torch.manual_seed), conf 0.001 / nms 0.5
+every N = the configuration BASELINE.json's metric is quoted on ("416 bs256"): configs[1]'s model
+(416x416, COCO-80, fp32 parity mode, incl. decode + NMS) at 256 images per GPU (`--batch 64` is
+configs[1]'s own batch; `--size 608 --batch 256` is configs[2]), tcgen05 3xTF32, reference random-init weights (torch.manual_seed), conf 0.001 / nms 0.5
 — with this init EVERY anchor passes the threshold, i.e. worst-case NMS.
 `value` times the device path with inputs resident in HBM; `e2e` times the C-ABI host call
 (pinned host input, H2D + D2H inside the timed region).
@@ -29,8 +30,11 @@ sys.path.insert(0, str(ROOT))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-METRIC = "images/sec YOLO-Nano-1.0x 416 bs64 fp32-parity e2e (backbone+neck+head+decode+NMS)"
-SIZE, BATCH, CLASSES = 416, 64, 80
+SIZE, BATCH, CLASSES = 416, 256, 80
+
+
+def metric_name(a):
+    return (f"images/sec YOLO-Nano-1.0x {a.size} bs{a.batch} fp32-parity e2e (backbone+neck+head+decode+NMS)")
 CONF, NMS_T = 0.001, 0.5
 
 
@@ -110,11 +114,16 @@ def cpu_baseline(sd, seconds: float, size: int):
             "network_ms_per_image": 1e3 * net_t / n, "nms_ms_per_image": 1e3 * (el - net_t) / n}
 
 
-def load_traffic(kernel_substr: str):
+def traffic_file(a) -> Path:
+    """The committed ncu DRAM-traffic capture of this command at this workload (416^2 only)."""
+    name = {256: "r01_dram_traffic_b256.csv", 64: "r01_dram_traffic.csv"}.get(a.batch if a.size == 416 else -1, "none")
+    return ROOT / "profiles" / name
+
+
+def load_traffic(kernel_substr: str, p: Path):
     """DRAM bytes per launch (read + write) of a kernel family from the committed ncu capture
-    of this same command (profiles/r01_dram_traffic.csv); None if the capture is absent."""
+    of this same command; None if there is no capture for this workload."""
     import csv
-    p = ROOT / "profiles" / "r01_dram_traffic.csv"
     if not p.exists():
         return None
     rows, hdr = [], None
@@ -175,7 +184,7 @@ def run_reference(a, rank, world):
     torch.set_num_threads(cores)
     sd = W.reference_init(CLASSES, seed=3) if a.weights == "refinit" else W.calibrated(CLASSES, seed=2)
     anchors = W.anchors_for(CLASSES)
-    per_step = 2                      # bounded sample of the 64-image batch
+    per_step = 2                      # bounded sample of the batch
     x = W.synthetic_input(per_step, a.size, seed=11)
     def step():
         O.detect(sd, x, a.size, CLASSES, anchors, CONF, NMS_T, tie="numpy")
@@ -186,7 +195,7 @@ def run_reference(a, rank, world):
         step()
     dt = time.perf_counter() - t0
     v = a.steps * per_step / dt
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": a.gpus,
+    line = {"impl": "reference", "metric": metric_name(a), "value": v, "unit": "images/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(a),
@@ -198,14 +207,15 @@ def run_reference(a, rank, world):
 
 
 def workload_config(a):
-    return {"workload": f"BASELINE configs[1]: YOLO-Nano-1.0x inference {a.size}x{a.size}, batch {a.batch} per GPU, "
-                        f"COCO {CLASSES} classes, fp32 parity mode, incl. decode+NMS",
+    return {"workload": f"BASELINE metric config (configs[1] at the metric's batch): YOLO-Nano-1.0x inference "
+                        f"{a.size}x{a.size}, batch {a.batch} per GPU, COCO {CLASSES} classes, fp32 parity mode, "
+                        "incl. decode+NMS",
             "input_size": a.size, "batch_per_gpu": a.batch, "num_classes": CLASSES, "conf_thresh": CONF,
             "nms_thresh": NMS_T, "weights": "reference random init (torch.manual_seed(3))" if a.weights == "refinit"
             else "calibrated synthetic (oracle/weights.py seed 2)",
             "gemm_mode": a.mode, "sharding": "batch-sharded, one process per GPU, no collective",
-            "l2": f"inputs {a.batch * 3 * a.size * a.size * 4 / 1e6:.0f} MB per step (> 126 MB L2 at batch 64), "
-                  "4 rotating input batches; intermediate activations ~1.5 GB per step"}
+            "l2": f"inputs {a.batch * 3 * a.size * a.size * 4 / 1e6:.0f} MB per step (> 126 MB L2), "
+                  f"4 rotating input batches; intermediate activations ~{a.batch * 24 * (a.size / 416) ** 2 / 1e3:.1f} GB per step"}
 
 
 def main():
@@ -359,8 +369,9 @@ def main():
     sass_name = {"pw_tcgen05": "tc_gemm_kernel", "conv3x3_tcgen05": "tc_gemm_kernel", "nms": "nms_segment_kernel",
                  "dwconv3x3": "dwconv3x3_kernel", "stem_pool": "stem_pool_kernel", "decode": "decode_level_kernel"}.get(dk, dk)
     roofline = {"bound": "hbm", "kernel": dk, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": load_traffic(sass_name), "traffic_note": "avg DRAM read+write bytes per launch of " + sass_name +
-                " (ncu, profiles/r01_dram_traffic.csv); algorithmic bytes per launch = " +
+                "traffic": load_traffic(sass_name, traffic_file(a)),
+                "traffic_note": "avg DRAM read+write bytes per launch of " + sass_name +
+                f" (ncu, profiles/{traffic_file(a).name}); algorithmic bytes per launch = " +
                 f"{dd['bytes'] / max(dd['launches'], 1e-9):.3e}", "peak_source": peak_src,
                 "launches_per_step": dd["launches"], "ms_per_step": dd["ms"],
                 "share_of_step": dd["ms"] / total_prof_ms,
@@ -381,7 +392,7 @@ def main():
         cpu = cpu_baseline(sd, a.cpu_seconds, a.size)
 
     imgs = world * a.batch * a.steps
-    line = {"metric": METRIC, "value": imgs / (ms_dev * 1e-3), "unit": "images/s", "n_gpus": world, "steps": a.steps,
+    line = {"metric": metric_name(a), "value": imgs / (ms_dev * 1e-3), "unit": "images/s", "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (tcgen05 3xTF32 split, fp32 accumulate)" if a.mode == "3xtf32" else
             ("f32" if a.mode == "ffma" else "tf32"),

@@ -157,19 +157,26 @@ __global__ void __launch_bounds__(kLossThreads) train_loss_kernel(const TrainLos
   // c in [A(1+C), used) -> box gradient; everything else (class columns, padding) 0.
   const int box0 = A * (1 + C);
   if ((p.ld & 3) == 0) {
+    // a warp per row, a lane per 16-byte column group: no index division, and the class-only groups
+    // (59 of 64 at A = 3, C = 80) are stored as zeros without touching shared memory
     const int ld4 = p.ld >> 2;
-    for (int i = threadIdx.x; i < ncell * ld4; i += kLossThreads) {
-      const int cl = i / ld4, c = (i - cl * ld4) << 2;
-      float v[4];
+    const int lane2 = threadIdx.x & 31, warp2 = threadIdx.x >> 5;
+    for (int cl = warp2; cl < ncell; cl += kLossThreads / 32) {
+      float4* grow4 = reinterpret_cast<float4*>(g + (long long)cl * p.ld);
+      const float* gq = sh_g + cl * A * 5;
+      for (int c4 = lane2; c4 < ld4; c4 += 32) {
+        const int c = c4 << 2;
+        float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (c < A || c + 3 >= box0) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int cc = c + k;
-        float val = 0.0f;
-        if (cc < A) val = sh_g[(cl * A + cc) * 5];
-        else if (cc >= box0 && cc < used) val = sh_g[(cl * A + ((cc - box0) >> 2)) * 5 + 1 + ((cc - box0) & 3)];
-        v[k] = val;
+          for (int k = 0; k < 4; ++k) {
+            const int cc = c + k;
+            if (cc < A) v[k] = gq[cc * 5];
+            else if (cc >= box0 && cc < used) v[k] = gq[((cc - box0) >> 2) * 5 + 1 + ((cc - box0) & 3)];
+          }
+        }
+        grow4[c4] = make_float4(v[0], v[1], v[2], v[3]);
       }
-      reinterpret_cast<float4*>(g + (long long)cl * p.ld)[c >> 2] = make_float4(v[0], v[1], v[2], v[3]);
     }
   } else {
     for (int i = threadIdx.x; i < ncell * p.ld; i += kLossThreads) {
