@@ -637,11 +637,11 @@ __global__ void __launch_bounds__(256) pwconv_bwd_weight_kernel(const float* __r
   const int tn = (threadIdx.x >> 4) * 4, tk = (threadIdx.x & 15) * 4;
   // loader role: 512 float4 per operand per slab = 2 per thread: row = idx / 32, col4 = idx % 32
   const int lr0 = threadIdx.x >> 5, lc = (threadIdx.x & 31) * 4;      // rows lr0 and lr0 + 8
-  float acc[8][8];
+  float2 acc[8][4];                                         // packed pairs along k: FFMA2 (2 fp32 FMAs per issue)
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.0f, 0.0f);
   float bsum = 0.0f;                                        // threads 0..127 of k-tile 0: bias gradient
   float4 pd[2], px[2];
   auto fetch = [&](long long m) {
@@ -683,11 +683,14 @@ __global__ void __launch_bounds__(256) pwconv_bwd_weight_kernel(const float* __r
       const float4 d0 = *reinterpret_cast<const float4*>(&sd[r][tn]), d1 = *reinterpret_cast<const float4*>(&sd[r][tn + 64]);
       const float4 x0 = *reinterpret_cast<const float4*>(&sx[r][tk]), x1 = *reinterpret_cast<const float4*>(&sx[r][tk + 64]);
       const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-      const float xx[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      const float2 xx[4] = {make_float2(x0.x, x0.y), make_float2(x0.z, x0.w), make_float2(x1.x, x1.y),
+                            make_float2(x1.z, x1.w)};
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i) {
+        const float2 d2 = make_float2(dd[i], dd[i]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(dd[i], xx[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(d2, xx[j], acc[i][j]);
+      }
     }
     if (blockIdx.z == 0 && threadIdx.x < kPwBwdTile) {
 #pragma unroll
@@ -702,16 +705,109 @@ __global__ void __launch_bounds__(256) pwconv_bwd_weight_kernel(const float* __r
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int k = k0 + tk + (j & 3) + (j >> 2) * 64;
-      if (n < N && k < K) pw[(long long)n * K + k] = acc[i][j];
+      const float2 a2 = acc[i][j >> 1];
+      if (n < N && k < K) pw[(long long)n * K + k] = (j & 1) ? a2.y : a2.x;
     }
   }
   if (blockIdx.z == 0 && threadIdx.x < kPwBwdTile && n0 + threadIdx.x < N)
     partial_b[(long long)blockIdx.x * N + n0 + threadIdx.x] = bsum;
 }
 
+// Aligned views (the product layouts): the same tile computation fed by a 4-stage cp.async pipeline — the
+// slabs go global -> shared without passing through registers, three slabs (48 pixels x 2 operands) are
+// in flight per block while one is multiplied, which covers the DRAM latency that the register-prefetch
+// variant above exposes (one slab of lookahead, 1 block per SM).  2 blocks per SM.
+constexpr int kPwBwdStages = 4;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(256, 2) pwconv_bwd_weight_async_kernel(const float* __restrict__ dout, int do_ld, int do_off,
+                                                                         const float* __restrict__ in, int in_ld, int in_off,
+                                                                         float* __restrict__ partial_w,
+                                                                         float* __restrict__ partial_b, long long M, int K,
+                                                                         int N, long long m_per_chunk) {
+  extern __shared__ __align__(16) float smem_pw[];          // [stages][2][16][128]
+  auto sd = [&](int st, int r) { return smem_pw + ((st * 2 + 0) * kPwBwdSlab + r) * kPwBwdTile; };
+  auto sx = [&](int st, int r) { return smem_pw + ((st * 2 + 1) * kPwBwdSlab + r) * kPwBwdTile; };
+  const int n0 = blockIdx.y * kPwBwdTile, k0 = blockIdx.z * kPwBwdTile;
+  const long long m0 = (long long)blockIdx.x * m_per_chunk;
+  const long long m1 = m0 + m_per_chunk < M ? m0 + m_per_chunk : M;
+  const int tn = (threadIdx.x >> 4) * 4, tk = (threadIdx.x & 15) * 4;
+  const int lr0 = threadIdx.x >> 5, lc = (threadIdx.x & 31) * 4;
+  const int nslab = m1 > m0 ? (int)((m1 - m0 + kPwBwdSlab - 1) / kPwBwdSlab) : 0;
+  const bool dcol = n0 + lc < N, xcol = k0 + lc < K;        // N, K multiples of 4 here
+  auto issue = [&](int slab) {
+    if (slab < nslab) {
+      const int st = slab % kPwBwdStages;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = lr0 + 8 * h;
+        const long long mm = m0 + (long long)slab * kPwBwdSlab + r;
+        const bool rok = mm < m1;
+        const long long ms = rok ? mm : m0;                  // a valid address even when nothing is read
+        cp_async16(sd(st, r) + lc, dout + ms * do_ld + do_off + n0 + (dcol ? lc : 0), rok && dcol ? 16 : 0);
+        cp_async16(sx(st, r) + lc, in + ms * in_ld + in_off + k0 + (xcol ? lc : 0), rok && xcol ? 16 : 0);
+      }
+    }
+    cp_async_commit();
+  };
+  float2 acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.0f, 0.0f);
+  float bsum = 0.0f;
+#pragma unroll
+  for (int sl = 0; sl < kPwBwdStages - 1; ++sl) issue(sl);
+  for (int slab = 0; slab < nslab; ++slab) {
+    cp_async_wait<kPwBwdStages - 2>();                       // slab `slab` has landed (this thread's copies)
+    __syncthreads();                                         // ... everyone's; and slab - 1 is fully consumed
+    issue(slab + kPwBwdStages - 1);                          // refills the stage slab - 1 used
+    const int st = slab % kPwBwdStages;
+#pragma unroll
+    for (int r = 0; r < kPwBwdSlab; ++r) {
+      const float4 d0 = *reinterpret_cast<const float4*>(sd(st, r) + tn), d1 = *reinterpret_cast<const float4*>(sd(st, r) + tn + 64);
+      const float4 x0 = *reinterpret_cast<const float4*>(sx(st, r) + tk), x1 = *reinterpret_cast<const float4*>(sx(st, r) + tk + 64);
+      const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+      const float2 xx[4] = {make_float2(x0.x, x0.y), make_float2(x0.z, x0.w), make_float2(x1.x, x1.y),
+                            make_float2(x1.z, x1.w)};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 d2 = make_float2(dd[i], dd[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(d2, xx[j], acc[i][j]);
+      }
+    }
+    if (blockIdx.z == 0 && threadIdx.x < kPwBwdTile) {
+#pragma unroll
+      for (int r = 0; r < kPwBwdSlab; ++r) bsum += sd(st, r)[threadIdx.x];
+    }
+  }
+  cp_async_wait<0>();
+  float* pw = partial_w + (long long)blockIdx.x * N * K;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int n = n0 + tn + (i & 3) + (i >> 2) * 64;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + tk + (j & 3) + (j >> 2) * 64;
+      const float2 a2 = acc[i][j >> 1];
+      if (n < N && k < K) pw[(long long)n * K + k] = (j & 1) ? a2.y : a2.x;
+    }
+  }
+  if (blockIdx.z == 0 && threadIdx.x < kPwBwdTile && n0 + threadIdx.x < N)
+    partial_b[(long long)blockIdx.x * N + n0 + threadIdx.x] = bsum;
+}
+constexpr size_t kPwBwdAsyncSmem = (size_t)kPwBwdStages * 2 * kPwBwdSlab * kPwBwdTile * sizeof(float);   // 64 KB
+
 inline int pw_bwd_chunks(long long M, int K, int N) {
   const int tiles = ((N + kPwBwdTile - 1) / kPwBwdTile) * ((K + kPwBwdTile - 1) / kPwBwdTile);
-  long long chunks = (kNumSMs * 2 + tiles - 1) / tiles;       // ~2 blocks per SM in total
+  long long chunks = (kNumSMs * 2 + tiles - 1) / tiles;       // 2 resident blocks per SM: one wave
   const long long max_chunks = (M + 4 * kPwBwdSlab - 1) / (4 * kPwBwdSlab);
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;

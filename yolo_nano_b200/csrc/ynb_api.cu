@@ -1646,8 +1646,19 @@ YNB_EXPORT int ynb_pwconv_bwd_weight(const float* dout, int32_t do_ld, int32_t d
   const int vec = cin % 4 == 0 && cout % 4 == 0 && do_ld % 4 == 0 && do_off % 4 == 0 && in_ld % 4 == 0 &&
                   in_off % 4 == 0 && ((uintptr_t)dout | (uintptr_t)in) % 16 == 0;
   dim3 grid(chunks, (cout + kPwBwdTile - 1) / kPwBwdTile, (cin + kPwBwdTile - 1) / kPwBwdTile);
-  pwconv_bwd_weight_kernel<<<grid, 256, 0, st>>>(dout, do_ld, do_off, in, in_ld, in_off, pw, pb, pixels, cin, cout,
-                                                 m_per_chunk, vec);
+  if (vec && !getenv("YNB_PWBW_NO_ASYNC")) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      UNIT_TRY(cudaFuncSetAttribute(pwconv_bwd_weight_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)kPwBwdAsyncSmem));
+      attr_set = true;
+    }
+    pwconv_bwd_weight_async_kernel<<<grid, 256, kPwBwdAsyncSmem, st>>>(dout, do_ld, do_off, in, in_ld, in_off, pw, pb,
+                                                                       pixels, cin, cout, m_per_chunk);
+  } else {
+    pwconv_bwd_weight_kernel<<<grid, 256, 0, st>>>(dout, do_ld, do_off, in, in_ld, in_off, pw, pb, pixels, cin, cout,
+                                                   m_per_chunk, vec);
+  }
   YNB_COUNT_LAUNCH();
   launch_reduce_partials(pw, chunks, (long long)cout * cin, dw, st);
   launch_reduce_partials(pb, chunks, cout, db, st);
