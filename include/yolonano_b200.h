@@ -349,6 +349,27 @@ int  ynb_act_bwd(const float* dout_dev, int32_t dout_ld, int32_t dout_off, const
                  int32_t out_off, float* dpre_dev, int32_t dpre_ld, int32_t dpre_off, int64_t pixels,
                  int32_t channels, int32_t act, void* stream);
 
+/* nn.BatchNorm2d in TRAINING mode (utils/modules.py:13; backbone/shufflenetv2.py:47,56,61; eps 1e-5,
+ * momentum 0.1) fused with the following ReLU / LeakyReLU(0.1), on an NHWC view [pixels, ld] with channels
+ * [off, off + C):  mean / biased variance over the pixels -> y = act((x - mean) * rstd * gamma + beta);
+ * running_mean / running_var (may be NULL) are updated in place with the unbiased variance, as torch
+ * does; save_mean / save_rstd [C] are kept for the backward.  Deterministic.  channels, strides and
+ * offsets multiples of 4, 16-byte aligned pointers.  workspace: ynb_bn_workspace_bytes(pixels, C). */
+int64_t ynb_bn_workspace_bytes(int64_t pixels, int32_t channels);
+int  ynb_bn_train_fwd(const float* x_dev, int32_t x_ld, int32_t x_off, float* y_dev, int32_t y_ld, int32_t y_off,
+                      const float* gamma_dev, const float* beta_dev, float* running_mean_dev,
+                      float* running_var_dev, float* save_mean_dev, float* save_rstd_dev, int64_t pixels,
+                      int32_t channels, float eps, float momentum, int32_t act, void* workspace_dev,
+                      int64_t workspace_bytes, void* stream);
+/* Its backward, activation included (y_dev = the forward output, needed only when act != NONE):
+ *   g = dy * act'(y);  dbeta = sum g;  dgamma = sum g * x_hat;
+ *   dx = gamma * rstd * (g - dbeta / M - x_hat * dgamma / M).   dgamma_dbeta_dev = [dgamma[C] | dbeta[C]]. */
+int  ynb_bn_train_bwd(const float* dy_dev, int32_t dy_ld, int32_t dy_off, const float* x_dev, int32_t x_ld,
+                      int32_t x_off, const float* y_dev, int32_t y_ld, int32_t y_off, const float* gamma_dev,
+                      const float* save_mean_dev, const float* save_rstd_dev, float* dx_dev, int32_t dx_ld,
+                      int32_t dx_off, float* dgamma_dbeta_dev, int64_t pixels, int32_t channels, int32_t act,
+                      void* workspace_dev, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -210,3 +210,34 @@ def test_forward_with_target_matches_reference_end_to_end(G, g7):
     m.trainable = False
     bboxes, scores, cls_inds = m(x[:1].to(G.DEV))
     assert bboxes.shape[1] == 4 and len(scores) == len(cls_inds)
+
+
+@pytest.mark.parametrize("m,c,act", [(2 * 2704, 116, 1), (3 * 676, 232, 0), (4 * 169, 464, 1), (5408, 96, 2), (7, 4, 2),
+                                     (64 * 2704, 60, 1)])
+def test_batchnorm_training_mode(G, TR, m, c, act):
+    """nn.BatchNorm2d(train) + activation, forward / running statistics / backward vs torch autograd."""
+    torch.manual_seed(m + c)
+    x = (torch.randn(m, c) * 1.7 + 0.6).requires_grad_(True)
+    bn = torch.nn.BatchNorm1d(c)          # same arithmetic as BatchNorm2d on [M, C] = (N*H*W, C)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.3)
+        bn.running_mean.normal_(0, 0.1); bn.running_var.uniform_(0.5, 2.0)
+    mine = TR.BatchNormTrain(bn.weight.detach().clone().to(G.DEV), bn.bias.detach().clone().to(G.DEV),
+                             bn.running_mean.clone().to(G.DEV), bn.running_var.clone().to(G.DEV), act=act)
+    bn.train()
+    pre = bn(x)
+    y = pre if act == 0 else (F.relu(pre) if act == 1 else F.leaky_relu(pre, 0.1))
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    got = mine.forward(x.detach().to(G.DEV))
+    torch.testing.assert_close(got.cpu(), y.detach(), rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(mine.running_mean.cpu(), bn.running_mean, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(mine.running_var.cpu(), bn.running_var, rtol=1e-5, atol=1e-6)
+    dx, dg, db = mine.backward(dy.to(G.DEV))
+    # elements whose pre-activation sits within rounding of 0 may take the other branch of act'
+    near0 = pre.detach().abs() < 1e-5
+    scale = float(x.grad.abs().max())
+    diff = (dx.cpu() - x.grad).abs()
+    assert float(diff[~near0].max()) <= 2e-4 * scale
+    torch.testing.assert_close(dg.cpu(), bn.weight.grad, rtol=2e-4, atol=2e-4 * float(bn.weight.grad.abs().max()))
+    torch.testing.assert_close(db.cpu(), bn.bias.grad, rtol=2e-4, atol=2e-4 * float(bn.bias.grad.abs().max()))

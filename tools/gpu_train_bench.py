@@ -110,6 +110,27 @@ def main():
         r["tflops"] = round(2 * m * k * n / ms / 1e9, 1)
         out.append(r)
         del xs, dys
+    # ---- BatchNorm (training mode) + activation, stage-2 / neck shapes
+    for (m, c, act) in ((B * 2704, 60, 1), (B * 2704, 96, 2), (B * 676, 232, 1)):
+        sets = 3
+        xs = [torch.randn(m, c, device=DEV) for _ in range(sets)]
+        dys = [torch.randn(m, c, device=DEV) for _ in range(sets)]
+        gamma, beta = torch.rand(c, device=DEV) + 0.5, torch.randn(c, device=DEV)
+        rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+        y, dx = torch.empty_like(xs[0]), torch.empty_like(xs[0])
+        mean, rstd, dgb = torch.empty(c, device=DEV), torch.empty(c, device=DEV), torch.empty(2 * c, device=DEV)
+        wsb = lib.ynb_bn_workspace_bytes(m, c)
+        ws = torch.empty(wsb, device=DEV, dtype=torch.uint8)
+        P = TR._ptr
+        ms = timed(lambda i: lib.ynb_bn_train_fwd(P(xs[i]), c, 0, P(y), c, 0, P(gamma), P(beta), P(rm), P(rv), P(mean),
+                                                  P(rstd), m, c, 1e-5, 0.1, act, P(ws), wsb, st), sets)
+        out.append(row(f"bn_train_fwd M={m} C={c} act={act}", ms, 4 * m * c * 2,
+                       "x is read twice (statistics, apply): 3 passes of traffic for 2 algorithmic"))
+        ms = timed(lambda i: lib.ynb_bn_train_bwd(P(dys[i]), c, 0, P(xs[i]), c, 0, P(y), c, 0, P(gamma), P(mean), P(rstd),
+                                                  P(dx), c, 0, P(dgb), m, c, act, P(ws), wsb, st), sets)
+        out.append(row(f"bn_train_bwd M={m} C={c} act={act}", ms, 4 * m * c * 4,
+                       "reads dy, x, y, writes dx; the reduction pass re-reads dy, x, y"))
+        del xs, dys
     for r in out:
         print(json.dumps(r))
     if len(sys.argv) > 1:

@@ -98,6 +98,11 @@ SIGNATURES = {
                                            _p, _i64, _p]),
     "ynb_pwconv_bwd_weight_workspace_bytes": (_i64, [_i64, _i32, _i32]),
     "ynb_pwconv_bwd_weight": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _p, _p, _i64, _i32, _i32, _p, _i64, _p]),
+    "ynb_bn_workspace_bytes": (_i64, [_i64, _i32]),
+    "ynb_bn_train_fwd": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _i64, _i32, _f, _f, _i32,
+                                   _p, _i64, _p]),
+    "ynb_bn_train_bwd": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _p, _i32, _i32, _p, _p, _p, _p, _i32, _i32, _p,
+                                   _i64, _i32, _i32, _p, _i64, _p]),
     "ynb_act_bwd": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _p, _i32, _i32, _i64, _i32, _i32, _p]),
 }
 

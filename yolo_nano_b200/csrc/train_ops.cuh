@@ -814,6 +814,134 @@ inline int pw_bwd_chunks(long long M, int K, int N) {
   return (int)chunks;
 }
 
+// ---- BatchNorm2d in training mode (utils/modules.py:13, backbone/shufflenetv2.py:47-62; nn.BatchNorm2d
+// defaults eps 1e-5, momentum 0.1) on NHWC views [M, ld], channels [off, off + C) -------------------------
+// Forward: batch mean / biased variance per channel -> y = act((x - mean) * rstd * gamma + beta); running
+// statistics updated with the UNBIASED variance as torch does.  Two streaming passes over x (statistics,
+// apply) + a fixed-order second stage: deterministic.
+// Column-sum kernel shared by forward statistics (a = x, b = x) and backward (a = dy_eff, b = x_hat):
+//   partial[chunk][0][c] = sum_m a[m][c];  partial[chunk][1][c] = sum_m a[m][c] * b[m][c]
+// MODE 0: a = x, b = x.   MODE 1: a = dy * act'(y), b = (x - mean) * rstd.
+constexpr int kBnCg = 16, kBnSlices = 16;
+template <int MODE>
+__global__ void __launch_bounds__(kBnCg * kBnSlices)
+bn_colsum_kernel(const float* __restrict__ x, int x_ld, int x_off, const float* __restrict__ dy, int dy_ld, int dy_off,
+                 const float* __restrict__ y, int y_ld, int y_off, const float* __restrict__ mean,
+                 const float* __restrict__ rstd, float slope, int use_act, float* __restrict__ partial, long long M, int C,
+                 long long rows_per_chunk) {
+  const int c = (blockIdx.y * kBnCg + threadIdx.x) * 4;
+  const long long r0 = (long long)blockIdx.x * rows_per_chunk;
+  const long long r1 = r0 + rows_per_chunk < M ? r0 + rows_per_chunk : M;
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  if (c < C) {
+    float4 mu = s1, rs = s1;
+    if (MODE == 1) {
+      mu = *reinterpret_cast<const float4*>(mean + c);
+      rs = *reinterpret_cast<const float4*>(rstd + c);
+    }
+    for (long long m = r0 + threadIdx.y; m < r1; m += kBnSlices) {
+      const float4 xv = *reinterpret_cast<const float4*>(x + m * x_ld + x_off + c);
+      float4 a = xv, b = xv;
+      if (MODE == 1) {
+        a = *reinterpret_cast<const float4*>(dy + m * dy_ld + dy_off + c);
+        if (use_act) {
+          const float4 yv = *reinterpret_cast<const float4*>(y + m * y_ld + y_off + c);
+          a.x *= yv.x > 0.f ? 1.f : slope; a.y *= yv.y > 0.f ? 1.f : slope;
+          a.z *= yv.z > 0.f ? 1.f : slope; a.w *= yv.w > 0.f ? 1.f : slope;
+        }
+        b = make_float4((xv.x - mu.x) * rs.x, (xv.y - mu.y) * rs.y, (xv.z - mu.z) * rs.z, (xv.w - mu.w) * rs.w);
+      }
+      s1.x += a.x; s1.y += a.y; s1.z += a.z; s1.w += a.w;
+      s2.x = fmaf(a.x, b.x, s2.x); s2.y = fmaf(a.y, b.y, s2.y); s2.z = fmaf(a.z, b.z, s2.z); s2.w = fmaf(a.w, b.w, s2.w);
+    }
+  }
+  __shared__ float4 sh[kBnSlices][2][kBnCg];
+  sh[threadIdx.y][0][threadIdx.x] = s1;
+  sh[threadIdx.y][1][threadIdx.x] = s2;
+  __syncthreads();
+  if (threadIdx.y < 2 && c < C) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < kBnSlices; ++j) {
+      const float4 v = sh[j][threadIdx.y][threadIdx.x];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    *reinterpret_cast<float4*>(partial + ((long long)blockIdx.x * 2 + threadIdx.y) * C + c) = t;
+  }
+}
+
+// sums[2][C] (float) -> mean, rstd, running statistics; double for the E[x^2] - mean^2 cancellation.
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, long long M, int C, float eps, float momentum,
+                                   float* __restrict__ save_mean, float* __restrict__ save_rstd,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = (double)sums[c] / (double)M;
+  double var = (double)sums[C + c] / (double)M - mean * mean;
+  if (var < 0.0) var = 0.0;
+  save_mean[c] = (float)mean;
+  save_rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)mean;
+  if (running_var) {
+    const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+    running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// MODE 0: y = act((x - mean) * rstd * gamma + beta)
+// MODE 1: dx = gamma * rstd * (dy_eff - sum(dy_eff) / M - x_hat * sum(dy_eff * x_hat) / M);  sums = [dbeta | dgamma]
+template <int MODE>
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const float* __restrict__ x, int x_ld, int x_off, const float* __restrict__ dy, int dy_ld, int dy_off,
+                const float* __restrict__ y, int y_ld, int y_off, float* __restrict__ out, int o_ld, int o_off,
+                const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                const float* __restrict__ rstd, const float* __restrict__ sums, float slope, int act, long long M, int C) {
+  const int c4n = C >> 2;
+  const long long total = M * c4n;
+  const float invM = 1.0f / (float)M;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / c4n;
+    const int c = (int)(i - m * c4n) * 4;
+    const float4 xv = *reinterpret_cast<const float4*>(x + m * x_ld + x_off + c);
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + c)), rs = __ldg(reinterpret_cast<const float4*>(rstd + c));
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, mus[4] = {mu.x, mu.y, mu.z, mu.w}, rss[4] = {rs.x, rs.y, rs.z, rs.w};
+    const float gas[4] = {ga.x, ga.y, ga.z, ga.w};
+    float o[4];
+    if (MODE == 0) {
+      const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+      const float bes[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float v = (xs[k] - mus[k]) * rss[k] * gas[k] + bes[k];
+        o[k] = act == YNB_ACT_NONE ? v : (v > 0.f ? v : slope * v);
+      }
+    } else {
+      const float4 dv = *reinterpret_cast<const float4*>(dy + m * dy_ld + dy_off + c);
+      float ds[4] = {dv.x, dv.y, dv.z, dv.w};
+      if (act != YNB_ACT_NONE) {
+        const float4 yv = *reinterpret_cast<const float4*>(y + m * y_ld + y_off + c);
+        const float ys[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ds[k] *= ys[k] > 0.f ? 1.f : slope;
+      }
+      const float4 sb = __ldg(reinterpret_cast<const float4*>(sums + c)), sg = __ldg(reinterpret_cast<const float4*>(sums + C + c));
+      const float sbs[4] = {sb.x, sb.y, sb.z, sb.w}, sgs[4] = {sg.x, sg.y, sg.z, sg.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float xh = (xs[k] - mus[k]) * rss[k];
+        o[k] = gas[k] * rss[k] * (ds[k] - sbs[k] * invM - xh * sgs[k] * invM);
+      }
+    }
+    *reinterpret_cast<float4*>(out + m * o_ld + o_off + c) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+inline int bn_chunks(long long M) {
+  long long chunks = (M + kBnSlices * 4 - 1) / (kBnSlices * 4);
+  if (chunks > kNumSMs * 4) chunks = kNumSMs * 4;
+  return (int)(chunks < 1 ? 1 : chunks);
+}
+
 // dOut *= act'(out)  in place is avoided: writes dPre[m, c] = dOut[m, c] * (out > 0 ? 1 : slope), slope = 0
 // (ReLU) or 0.1 (LeakyReLU), for channel ranges given as (ld, off).  `out` is the forward OUTPUT (its sign
 // equals the sign of the pre-activation for both activations).

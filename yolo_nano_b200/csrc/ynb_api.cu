@@ -1647,12 +1647,9 @@ YNB_EXPORT int ynb_pwconv_bwd_weight(const float* dout, int32_t do_ld, int32_t d
                   in_off % 4 == 0 && ((uintptr_t)dout | (uintptr_t)in) % 16 == 0;
   dim3 grid(chunks, (cout + kPwBwdTile - 1) / kPwBwdTile, (cin + kPwBwdTile - 1) / kPwBwdTile);
   if (vec && !getenv("YNB_PWBW_NO_ASYNC")) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      UNIT_TRY(cudaFuncSetAttribute(pwconv_bwd_weight_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)kPwBwdAsyncSmem));
-      attr_set = true;
-    }
+    // per device, cheap: set on every call (one process may drive several devices)
+    UNIT_TRY(cudaFuncSetAttribute(pwconv_bwd_weight_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kPwBwdAsyncSmem));
     pwconv_bwd_weight_async_kernel<<<grid, 256, kPwBwdAsyncSmem, st>>>(dout, do_ld, do_off, in, in_ld, in_off, pw, pb,
                                                                        pixels, cin, cout, m_per_chunk);
   } else {
@@ -1720,4 +1717,79 @@ YNB_EXPORT int ynb_forward_train_loss(ynb_engine* e, const float* x_dev, int32_t
 
 YNB_EXPORT int32_t ynb_raw_ld(const ynb_engine* e) {
   return e ? round_up(e->cfg.num_anchors * (1 + e->cfg.num_classes + 4), 4) : 0;   // = plan_workspace's raw[l].ld
+}
+
+// ---- BatchNorm2d in training mode ----------------------------------------------------------------------
+namespace {
+bool bn_args_ok(long long M, int C, std::initializer_list<int> strides, std::initializer_list<const void*> ptrs) {
+  if (M <= 0 || C <= 0 || C % 4) return false;
+  for (int v : strides) if (v % 4) return false;
+  for (const void* q : ptrs) if (!q || ((uintptr_t)q & 15u)) return false;
+  return true;
+}
+}  // namespace
+
+YNB_EXPORT int64_t ynb_bn_workspace_bytes(int64_t pixels, int32_t channels) {
+  return ((int64_t)bn_chunks(pixels) * 2 * channels + 2 * channels) * sizeof(float);
+}
+
+YNB_EXPORT int ynb_bn_train_fwd(const float* x, int32_t x_ld, int32_t x_off, float* y, int32_t y_ld, int32_t y_off,
+                                const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                float* save_mean, float* save_rstd, int64_t pixels, int32_t channels, float eps,
+                                float momentum, int32_t act, void* ws, int64_t ws_bytes, void* stream) {
+  if (!bn_args_ok(pixels, channels, {x_ld, x_off, y_ld, y_off}, {x, y, gamma, beta, save_mean, save_rstd, ws}) ||
+      ws_bytes < ynb_bn_workspace_bytes(pixels, channels) || act < 0 || act > 2)
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_bn_train_fwd: bad arguments (channels / strides multiples of 4, 16-byte aligned)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunks = bn_chunks(pixels);
+  const long long rpc = (pixels + chunks - 1) / chunks;
+  float* part = (float*)ws;
+  float* sums = part + (long long)chunks * 2 * channels;
+  dim3 grid(chunks, (channels + kBnCg * 4 - 1) / (kBnCg * 4)), block(kBnCg, kBnSlices);
+  bn_colsum_kernel<0><<<grid, block, 0, st>>>(x, x_ld, x_off, nullptr, 0, 0, nullptr, 0, 0, nullptr, nullptr, 0.f, 0, part,
+                                              pixels, channels, rpc);
+  YNB_COUNT_LAUNCH();
+  launch_reduce_partials(part, chunks, 2LL * channels, sums, st);
+  bn_finalize_kernel<<<(channels + 127) / 128, 128, 0, st>>>(sums, pixels, channels, eps, momentum, save_mean, save_rstd,
+                                                            running_mean, running_var);
+  YNB_COUNT_LAUNCH();
+  const long long total = pixels * (channels / 4);
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
+  bn_apply_kernel<0><<<blocks, 256, 0, st>>>(x, x_ld, x_off, nullptr, 0, 0, nullptr, 0, 0, y, y_ld, y_off, gamma, beta,
+                                             save_mean, save_rstd, nullptr, act == YNB_ACT_LEAKY ? 0.1f : 0.0f, act, pixels,
+                                             channels);
+  YNB_COUNT_LAUNCH();
+  UNIT_TRY(cudaGetLastError());
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_bn_train_bwd(const float* dy, int32_t dy_ld, int32_t dy_off, const float* x, int32_t x_ld, int32_t x_off,
+                                const float* y, int32_t y_ld, int32_t y_off, const float* gamma, const float* save_mean,
+                                const float* save_rstd, float* dx, int32_t dx_ld, int32_t dx_off, float* dgamma_dbeta,
+                                int64_t pixels, int32_t channels, int32_t act, void* ws, int64_t ws_bytes, void* stream) {
+  if (!bn_args_ok(pixels, channels, {dy_ld, dy_off, x_ld, x_off, dx_ld, dx_off},
+                  {dy, x, gamma, save_mean, save_rstd, dx, dgamma_dbeta, ws}) ||
+      ws_bytes < ynb_bn_workspace_bytes(pixels, channels) || act < 0 || act > 2 ||
+      (act != YNB_ACT_NONE && (!y || y_ld % 4 || y_off % 4)))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_bn_train_bwd: bad arguments (channels / strides multiples of 4, 16-byte aligned)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunks = bn_chunks(pixels);
+  const long long rpc = (pixels + chunks - 1) / chunks;
+  float* part = (float*)ws;
+  float* sums = part + (long long)chunks * 2 * channels;      // [dbeta | dgamma]
+  const float slope = act == YNB_ACT_LEAKY ? 0.1f : 0.0f;
+  dim3 grid(chunks, (channels + kBnCg * 4 - 1) / (kBnCg * 4)), block(kBnCg, kBnSlices);
+  bn_colsum_kernel<1><<<grid, block, 0, st>>>(x, x_ld, x_off, dy, dy_ld, dy_off, y, y_ld, y_off, save_mean, save_rstd, slope,
+                                              act != YNB_ACT_NONE, part, pixels, channels, rpc);
+  YNB_COUNT_LAUNCH();
+  launch_reduce_partials(part, chunks, 2LL * channels, sums, st);
+  const long long total = pixels * (channels / 4);
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
+  bn_apply_kernel<1><<<blocks, 256, 0, st>>>(x, x_ld, x_off, dy, dy_ld, dy_off, y, y_ld, y_off, dx, dx_ld, dx_off, gamma,
+                                             nullptr, save_mean, save_rstd, sums, slope, act, pixels, channels);
+  YNB_COUNT_LAUNCH();
+  UNIT_TRY(cudaMemcpyAsync(dgamma_dbeta, sums + channels, channels * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  UNIT_TRY(cudaMemcpyAsync(dgamma_dbeta + channels, sums, channels * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  UNIT_TRY(cudaGetLastError());
+  return YNB_OK;
 }

@@ -180,3 +180,44 @@ def act_backward(dout: torch.Tensor, out: torch.Tensor, act: int) -> torch.Tenso
            "ynb_act_bwd")
     return dpre
 
+
+
+class BatchNormTrain:
+    """nn.BatchNorm2d in training mode + the following activation on an NHWC matrix [M, C] (C % 4 == 0):
+    `forward` normalises with the batch statistics and updates the running ones in place, `backward`
+    returns (dx, dgamma, dbeta).  utils/modules.py:13-14, backbone/shufflenetv2.py:47-62."""
+
+    def __init__(self, gamma, beta, running_mean, running_var, eps: float = 1e-5, momentum: float = 0.1, act: int = 0):
+        _dev(gamma, beta, running_mean, running_var)
+        self.gamma, self.beta, self.running_mean, self.running_var = gamma, beta, running_mean, running_var
+        self.eps, self.momentum, self.act = float(eps), float(momentum), int(act)
+        self.saved = None
+
+    def _ws(self, m, c, dev):
+        wsb = _lib.load().ynb_bn_workspace_bytes(m, c)
+        return torch.empty(wsb, device=dev, dtype=torch.uint8), wsb
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        dev = _dev(x)
+        m, c = x.shape
+        y = torch.empty_like(x)
+        mean, rstd = torch.empty(c, device=dev), torch.empty(c, device=dev)
+        ws, wsb = self._ws(m, c, dev)
+        _check(_lib.load().ynb_bn_train_fwd(_ptr(x), c, 0, _ptr(y), c, 0, _ptr(self.gamma), _ptr(self.beta),
+                                            _ptr(self.running_mean), _ptr(self.running_var), _ptr(mean), _ptr(rstd),
+                                            m, c, self.eps, self.momentum, self.act, _ptr(ws), wsb, _stream_ptr(dev)),
+               "ynb_bn_train_fwd")
+        self.saved = (x, y, mean, rstd)
+        return y
+
+    def backward(self, dy: torch.Tensor):
+        dev = _dev(dy)
+        x, y, mean, rstd = self.saved
+        m, c = x.shape
+        dx = torch.empty_like(x)
+        dgb = torch.empty(2 * c, device=dev)
+        ws, wsb = self._ws(m, c, dev)
+        _check(_lib.load().ynb_bn_train_bwd(_ptr(dy), c, 0, _ptr(x), c, 0, _ptr(y), c, 0, _ptr(self.gamma), _ptr(mean),
+                                            _ptr(rstd), _ptr(dx), c, 0, _ptr(dgb), m, c, self.act, _ptr(ws), wsb,
+                                            _stream_ptr(dev)), "ynb_bn_train_bwd")
+        return dx, dgb[:c], dgb[c:]
