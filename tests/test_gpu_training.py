@@ -241,3 +241,75 @@ def test_batchnorm_training_mode(G, TR, m, c, act):
     assert float(diff[~near0].max()) <= 2e-4 * scale
     torch.testing.assert_close(dg.cpu(), bn.weight.grad, rtol=2e-4, atol=2e-4 * float(bn.weight.grad.abs().max()))
     torch.testing.assert_close(db.cpu(), bn.bias.grad, rtol=2e-4, atol=2e-4 * float(bn.bias.grad.abs().max()))
+
+
+def _bn_layer(TR, G, bn, act):
+    return TR.BnActTrain(bn.weight.detach().clone().to(G.DEV), bn.bias.detach().clone().to(G.DEV),
+                         bn.running_mean.clone().to(G.DEV), bn.running_var.clone().to(G.DEV), eps=bn.eps,
+                         momentum=bn.momentum, act=act)
+
+
+def _check_block(G, TR, ref, layers, x, tol=3e-4):
+    """ref: torch module in train mode (NCHW); layers: SequentialTrain (NHWC).  Output, input gradient and
+    every parameter gradient, each within `tol` of its own scale."""
+    x = x.clone().requires_grad_(True)
+    ref.train()
+    y = ref(x)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    nhwc = lambda t: t.detach().permute(0, 2, 3, 1).contiguous().to(G.DEV)  # noqa: E731
+    got = layers.forward(nhwc(x))
+    err = lambda a, b: float((a - b).abs().max() / b.abs().max())  # noqa: E731
+    assert err(got.cpu().permute(0, 3, 1, 2), y.detach()) <= tol
+    dx = layers.backward(nhwc(dy))
+    assert err(dx.cpu().permute(0, 3, 1, 2), x.grad) <= tol
+    return layers.grads(), err
+
+
+def test_conv_module_train_step_matches_autograd(G, TR):
+    """utils/modules.py:8-18 `Conv(c1, c2, k=1)` in TRAINING mode: conv(+bias) -> BN(batch stats) -> LeakyReLU,
+    forward + backward composed from the kernels (tcgen05 GEMM, BN, weight-gradient, W^T GEMM)."""
+    torch.manual_seed(11)
+    c1, c2 = 232, 96
+    conv, bn = torch.nn.Conv2d(c1, c2, 1), torch.nn.BatchNorm2d(c2)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.3)
+    ref = torch.nn.Sequential(conv, bn, torch.nn.LeakyReLU(0.1))
+    layers = TR.SequentialTrain(TR.PwConvTrain(conv.weight.detach().view(c2, c1).contiguous().to(G.DEV),
+                                               conv.bias.detach().clone().to(G.DEV)), _bn_layer(TR, G, bn, 2))
+    grads, err = _check_block(G, TR, ref, layers, torch.randn(3, c1, 26, 26))
+    assert err(grads[0]["weight"].cpu().view_as(conv.weight), conv.weight.grad) <= 3e-4
+    assert err(grads[1]["weight"].cpu(), bn.weight.grad) <= 3e-4 and err(grads[1]["bias"].cpu(), bn.bias.grad) <= 3e-4
+    # the conv bias gradient is ~0 by construction (BatchNorm removes the mean): compare on the weight-grad scale
+    assert float((grads[0]["bias"].cpu() - conv.bias.grad).abs().max()) <= 3e-4 * float(conv.weight.grad.abs().max()) * 26
+
+
+def test_shuffle_branch2_train_step_matches_autograd(G, TR):
+    """backbone/shufflenetv2.py:53-63 branch2 of a stride-1 stage-3 unit in TRAINING mode:
+    pw -> BN -> ReLU -> dw3x3 -> BN -> pw -> BN -> ReLU, forward + backward, all parameter gradients."""
+    torch.manual_seed(12)
+    c = 116
+    pw1, bn1 = torch.nn.Conv2d(c, c, 1, bias=False), torch.nn.BatchNorm2d(c)
+    dw, bn2 = torch.nn.Conv2d(c, c, 3, 1, 1, groups=c, bias=False), torch.nn.BatchNorm2d(c)
+    pw2, bn3 = torch.nn.Conv2d(c, c, 1, bias=False), torch.nn.BatchNorm2d(c)
+    with torch.no_grad():
+        for bn in (bn1, bn2, bn3):
+            bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.3)
+    ref = torch.nn.Sequential(pw1, bn1, torch.nn.ReLU(), dw, bn2, pw2, bn3, torch.nn.ReLU())
+    dev = G.DEV
+    layers = TR.SequentialTrain(
+        TR.PwConvTrain(pw1.weight.detach().view(c, c).contiguous().to(dev)), _bn_layer(TR, G, bn1, 1),
+        TR.DwConvTrain(dw.weight.detach().view(c, 9).t().contiguous().to(dev), 1), _bn_layer(TR, G, bn2, 0),
+        TR.PwConvTrain(pw2.weight.detach().view(c, c).contiguous().to(dev)), _bn_layer(TR, G, bn3, 1))
+    grads, err = _check_block(G, TR, ref, layers, torch.randn(4, c, 26, 26), tol=1e-3)
+    assert err(grads[0]["weight"].cpu().view_as(pw1.weight), pw1.weight.grad) <= 1e-3
+    assert err(grads[2]["weight"].cpu().t().reshape(c, 1, 3, 3), dw.weight.grad) <= 1e-3
+    assert err(grads[4]["weight"].cpu().view_as(pw2.weight), pw2.weight.grad) <= 1e-3
+    for i, bn in ((1, bn1), (3, bn2), (5, bn3)):
+        assert err(grads[i]["weight"].cpu(), bn.weight.grad) <= 1e-3
+        # bn2's bias gradient is analytically 0 (a constant shift goes through the linear pw2 and is removed
+        # by bn3): both sides are rounding noise there, so the bias gradients are compared on the scale of the
+        # layer's weight gradient
+        assert float((grads[i]["bias"].cpu() - bn.bias.grad).abs().max()) <= 1e-3 * float(bn.weight.grad.abs().max())
+    # running statistics moved exactly as torch moves them
+    torch.testing.assert_close(layers.layers[1].running_var.cpu(), bn1.running_var, rtol=1e-4, atol=1e-6)

@@ -221,3 +221,100 @@ class BatchNormTrain:
                                             _ptr(rstd), _ptr(dx), c, 0, _ptr(dgb), m, c, self.act, _ptr(ws), wsb,
                                             _stream_ptr(dev)), "ynb_bn_train_bwd")
         return dx, dgb[:c], dgb[c:]
+
+
+# ---- layer objects: the kernels above composed into forward / backward of the reference's blocks ---------
+class PwConvTrain:
+    """1x1 conv (`nn.Conv2d(cin, cout, 1)`, optional bias) on [M, cin] -> [M, cout]; forward on the
+    tcgen05 GEMM (3xTF32), backward = weight gradient kernel + the forward GEMM with W^T."""
+
+    def __init__(self, weight_nk: torch.Tensor, bias: Optional[torch.Tensor] = None):
+        _dev(weight_nk, bias)
+        self.w, self.b = weight_nk, bias
+        self.grads = {}
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        dev = _dev(x)
+        m, k = x.shape
+        n = self.w.shape[0]
+        self.x = x
+        y = torch.empty((m, n), device=dev, dtype=torch.float32)
+        b = self.b if self.b is not None else torch.zeros(n, device=dev)
+        lib = _lib.load()
+        for n0 in range(0, n, 256):
+            nc = min(256, n - n0)
+            _check(lib.ynb_pwconv_tc(_ptr(x), k, 0, _ptr(y), n, n0, 1, _ptr(self.w[n0:n0 + nc]), _ptr(b[n0:n0 + nc]), m, k,
+                                     nc, 0, _lib.GEMM_TC_3XTF32, _stream_ptr(dev)), "ynb_pwconv_tc")
+        return y
+
+    def backward(self, dy: torch.Tensor) -> torch.Tensor:
+        dw, db = pwconv_backward_weight(dy, self.x)
+        self.grads = {"weight": dw} if self.b is None else {"weight": dw, "bias": db}
+        return pwconv_backward_data(dy, self.w)
+
+
+class DwConvTrain:
+    """Depthwise 3x3 (`nn.Conv2d(c, c, 3, stride, 1, groups=c, bias=False)`) on NHWC [B, H, W, C]."""
+
+    def __init__(self, weight_9c: torch.Tensor, stride: int):
+        _dev(weight_9c)
+        self.w, self.stride = weight_9c, int(stride)
+        self.grads = {}
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        dev = _dev(x)
+        b, h, w, c = x.shape
+        self.x = x
+        ho, wo = (h - 1) // self.stride + 1, (w - 1) // self.stride + 1
+        y = torch.empty((b, ho, wo, c), device=dev, dtype=torch.float32)
+        zero = torch.zeros(c, device=dev)
+        _check(_lib.load().ynb_dwconv3x3(_ptr(x), c, 0, _ptr(y), c, 0, 1, _ptr(self.w), _ptr(zero), b, h, w, c, self.stride,
+                                         0, _stream_ptr(dev)), "ynb_dwconv3x3")
+        return y
+
+    def backward(self, dy: torch.Tensor) -> torch.Tensor:
+        dx, dw, _db = dwconv3x3_backward(dy, self.x, self.w, self.stride)
+        self.grads = {"weight": dw}
+        return dx
+
+
+class BnActTrain(BatchNormTrain):
+    """BatchNormTrain on tensors of any leading shape [..., C] (NHWC maps or [M, C] matrices)."""
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        self.shape = x.shape
+        return super().forward(x.reshape(-1, x.shape[-1])).reshape(self.shape)
+
+    def backward(self, dy: torch.Tensor) -> torch.Tensor:
+        dx, dg, db = super().backward(dy.reshape(-1, dy.shape[-1]))
+        self.grads = {"weight": dg, "bias": db}
+        return dx.reshape(self.shape)
+
+
+class SequentialTrain:
+    """forward through the layers, backward in reverse; `grads()` lists the parameter gradients in
+    layer order — what `total_loss.backward()` (train.py:229) leaves in `.grad` for this block."""
+
+    def __init__(self, *layers):
+        self.layers = list(layers)
+
+    def forward(self, x):
+        for layer in self.layers:
+            if isinstance(layer, PwConvTrain) and x.dim() == 4:
+                shp = x.shape
+                x = layer.forward(x.reshape(-1, shp[-1])).reshape(*shp[:-1], -1)
+            else:
+                x = layer.forward(x)
+        return x
+
+    def backward(self, dy):
+        for layer in reversed(self.layers):
+            if isinstance(layer, PwConvTrain) and dy.dim() == 4:
+                shp = dy.shape
+                dy = layer.backward(dy.reshape(-1, shp[-1]).contiguous()).reshape(*shp[:-1], -1)
+            else:
+                dy = layer.backward(dy.contiguous())
+        return dy
+
+    def grads(self):
+        return [layer.grads for layer in self.layers]
