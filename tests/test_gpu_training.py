@@ -8,6 +8,9 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
+import os  # noqa: E402
+os.environ.setdefault("YNB_SYNC_CHECK", "1")   # surface bounded-wait timeouts of the tcgen05 weight-gradient kernel
+
 from oracle import train_oracle as T  # noqa: E402
 from oracle import weights as W  # noqa: E402
 

@@ -1,0 +1,206 @@
+// Weight gradient of the pointwise conv on tcgen05 tensor cores, fp32 parity mode (3xTF32):
+//   dW[n][k] = sum_m dY[m][n] * X[m][k],   db[n] = sum_m dY[m][n]          (config 5)
+// As an MMA:  D[128 x KPAD] += A[128 x 8] * B[KPAD x 8]^T with the PIXELS as the contraction dimension:
+// A = dY^T (rows n), B = X^T (rows k).  Both activations are stored pixel-major ([m][channel]), i.e. the
+// contraction index is the SLOW one, so the operands cannot be fetched by TMA into the K-major layout
+// the MMA wants.  The threads have to touch every element anyway for the hi/lo split of the 3xTF32
+// scheme, so the 8 producer warps do both at once: coalesced 32-byte-sector reads of 32 pixels x 8
+// channels per warp instruction, round-to-nearest split x = hi + lo, and a TRANSPOSING store into the
+// 128-byte-swizzled K-major tiles (conflict-free: a warp writes 8 rows x one 16-byte chunk each).
+// Row K of the B tile is all ones, so column K of the accumulator is the bias gradient for free.
+//
+//   warps 0-7  producers (global -> split -> swizzled smem, mbarrier `full`), then the epilogue
+//              (TMEM -> registers -> partial[chunk][N][K], main + correction accumulators added)
+//   warp  8    one thread issues tcgen05.mma kind::tf32: per 8-pixel sub-step  main += A_hi*B_hi,
+//              corr += A_lo*B_hi, corr += A_hi*B_lo; tcgen05.commit releases the stage (`empty`)
+// One CTA per SM owns a contiguous range of pixels; the partials are summed in fixed order by
+// reduce_partials_kernel (deterministic).  Every mbarrier wait is bounded (ptx::mbar_wait).
+#pragma once
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace ynb {
+
+constexpr int kWgThreads = 288;
+constexpr int kWgStepPix = 32;
+constexpr uint32_t kWgABytes = 128 * 128;          // one A plane: 128 rows (n) x 32 floats of pixels
+
+struct WgradParams {
+  const float* dout; int do_ld, do_off;
+  const float* in;   int in_ld, in_off;
+  float* partial_w;                                // [chunks][N][K]
+  float* partial_b;                                // [chunks][N]
+  long long M; int K, N;
+  int stages;
+  long long steps_per_chunk;
+  int* err;
+};
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+  const float r = x - hi;                          // exact
+  lo = __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xffffe000u);
+}
+
+template <int KPAD>
+__global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t wg_smem_raw[];
+  uint8_t* smem = wg_smem_raw + ((1024u - (ptx::smem_u32(wg_smem_raw) & 1023u)) & 1023u);
+  __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], done_bar;
+  __shared__ uint32_t tmem_ptr;
+  constexpr uint32_t kBBytes = KPAD * 128;
+  constexpr uint32_t kStageBytes = 2 * kWgABytes + 2 * kBBytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * 128;
+  const long long total_steps = (p.M + kWgStepPix - 1) / kWgStepPix;
+  const long long s0 = (long long)blockIdx.x * p.steps_per_chunk;
+  const long long s1 = s0 + p.steps_per_chunk < total_steps ? s0 + p.steps_per_chunk : total_steps;
+  const int nsteps = s1 > s0 ? (int)(s1 - s0) : 0;
+  const int stages = p.stages;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) { ptx::mbar_init(&full_bar[i], 8); ptx::mbar_init(&empty_bar[i], 1); }
+    ptx::mbar_init(&done_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 8) { ptx::tmem_alloc(&tmem_ptr, 512); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem = tmem_ptr;
+
+  if (warp < 8) {
+    // ---------------- producers ----------------
+    const int c_lo = lane >> 2, m_lo = lane & 3;            // 8 channels x 4 pixels per warp instruction
+    const int kk = 4 * warp + m_lo;                         // pixel inside the step = position along the contraction
+    const uint32_t in_row = ((uint32_t)(warp ^ c_lo) << 4) + (uint32_t)m_lo * 4u;   // swizzled 16-byte chunk (row % 8 == c_lo)
+    for (int t = 0; t < nsteps; ++t) {
+      const int s = t % stages;
+      const long long m = (s0 + t) * kWgStepPix + kk;
+      const bool mok = m < p.M;
+      const float* drow = p.dout + m * p.do_ld + p.do_off + n0 + c_lo;
+      const float* xrow = p.in + m * p.in_ld + p.in_off + c_lo;
+      float av[16], bv[KPAD / 8];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) av[i] = (mok && n0 + 8 * i + c_lo < p.N) ? drow[8 * i] : 0.0f;
+#pragma unroll
+      for (int i = 0; i < KPAD / 8; ++i) {
+        const int k = 8 * i + c_lo;
+        bv[i] = !mok ? 0.0f : (k < p.K ? xrow[8 * i] : (k == p.K ? 1.0f : 0.0f));
+      }
+      if (t >= stages) ptx::mbar_wait(&empty_bar[s], ((t / stages) - 1) & 1, p.err, 1);
+      uint8_t* st = smem + (size_t)s * kStageBytes;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float hi, lo;
+        split_tf32(av[i], hi, lo);
+        const uint32_t off = (uint32_t)(8 * i + c_lo) * 128u + in_row;
+        *reinterpret_cast<float*>(st + off) = hi;
+        *reinterpret_cast<float*>(st + kWgABytes + off) = lo;
+      }
+#pragma unroll
+      for (int i = 0; i < KPAD / 8; ++i) {
+        float hi, lo;
+        split_tf32(bv[i], hi, lo);
+        const uint32_t off = (uint32_t)(8 * i + c_lo) * 128u + in_row;
+        *reinterpret_cast<float*>(st + 2 * kWgABytes + off) = hi;
+        *reinterpret_cast<float*>(st + 2 * kWgABytes + kBBytes + off) = lo;
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&full_bar[s]);
+    }
+    // ---------------- epilogue ----------------
+    float* pw = p.partial_w + (long long)blockIdx.x * p.N * p.K;
+    float* pb = p.partial_b + (long long)blockIdx.x * p.N;
+    const int lane_base = 32 * (warp & 3), half = warp >> 2;
+    const int n = n0 + lane_base + lane;
+    if (nsteps > 0) {
+      ptx::mbar_wait(&done_bar, 0, p.err, 2);
+      ptx::tc_fence_after_sync();
+    }
+#pragma unroll 1
+    for (int c0 = half * (KPAD / 2); c0 < (half + 1) * (KPAD / 2); c0 += 16) {
+      uint32_t r1[16], r2[16];
+      if (nsteps > 0) {
+        ptx::tmem_ld_32x16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)c0, r1);
+        ptx::tmem_ld_32x16(tmem + ((uint32_t)lane_base << 16) + (uint32_t)(KPAD + c0), r2);
+        ptx::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { r1[j] = 0u; r2[j] = 0u; }
+      }
+      if (n < p.N) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int k = c0 + j;
+          const float v = __uint_as_float(r1[j]) + __uint_as_float(r2[j]);
+          if (k < p.K) pw[(long long)n * p.K + k] = v;
+          else if (k == p.K) pb[n] = v;
+        }
+      }
+    }
+  } else {
+    if (lane == 0) {
+    // ---------------- MMA issuer ----------------
+    const uint32_t idesc = ptx::make_idesc(2, 128, KPAD);
+    for (int t = 0; t < nsteps; ++t) {
+      const int s = t % stages;
+      ptx::mbar_wait(&full_bar[s], (t / stages) & 1, p.err, 3);
+      ptx::tc_fence_after_sync();
+      const uint32_t a_hi = ptx::smem_u32(smem + (size_t)s * kStageBytes), a_lo = a_hi + kWgABytes;
+      const uint32_t b_hi = a_hi + 2 * kWgABytes, b_lo = b_hi + kBBytes;
+#pragma unroll
+      for (int sub = 0; sub < 4; ++sub) {
+        const uint32_t ko = sub * 32;
+        const uint32_t acc = (t | sub) != 0;
+        ptx::mma_tf32_ss(tmem, ptx::make_sw128_kmajor_desc(a_hi + ko), ptx::make_sw128_kmajor_desc(b_hi + ko), idesc, acc);
+        ptx::mma_tf32_ss(tmem + KPAD, ptx::make_sw128_kmajor_desc(a_lo + ko), ptx::make_sw128_kmajor_desc(b_hi + ko), idesc, acc);
+        ptx::mma_tf32_ss(tmem + KPAD, ptx::make_sw128_kmajor_desc(a_hi + ko), ptx::make_sw128_kmajor_desc(b_lo + ko), idesc, 1u);
+      }
+      ptx::mma_commit(&empty_bar[s]);
+    }
+    if (nsteps > 0) ptx::mma_commit(&done_bar);
+    }
+    __syncwarp();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 8) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem, 512);
+  }
+}
+
+inline int wgrad_tc_kpad(int K) { return K + 1 <= 128 ? 128 : (K + 1 <= 256 ? 256 : 0); }
+inline int wgrad_tc_chunks(long long M, int N) {
+  const int ntile = (N + 127) / 128;
+  long long chunks = kNumSMs / ntile;
+  const long long total_steps = (M + kWgStepPix - 1) / kWgStepPix;
+  if (chunks > total_steps) chunks = total_steps;
+  return (int)(chunks < 1 ? 1 : chunks);
+}
+
+inline cudaError_t launch_pw_wgrad_tc(WgradParams p, int chunks, cudaStream_t st) {
+  const int kpad = wgrad_tc_kpad(p.K);
+  const long long total_steps = (p.M + kWgStepPix - 1) / kWgStepPix;
+  p.steps_per_chunk = (total_steps + chunks - 1) / chunks;
+  p.stages = kpad == 128 ? 3 : 2;
+  const size_t stage = 2 * kWgABytes + 2 * (size_t)kpad * 128;
+  const size_t smem = stage * p.stages + 1024;
+  dim3 grid(chunks, (p.N + 127) / 128);
+  cudaError_t e;
+  if (kpad == 128) {
+    e = cudaFuncSetAttribute(pw_wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    pw_wgrad_tc_kernel<128><<<grid, kWgThreads, smem, st>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(pw_wgrad_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    pw_wgrad_tc_kernel<256><<<grid, kWgThreads, smem, st>>>(p);
+  }
+  YNB_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+}  // namespace ynb

@@ -24,6 +24,7 @@
 #include "gemm_tc.cuh"
 #include "kernels_basic.cuh"
 #include "train_ops.cuh"
+#include "wgrad_tc.cuh"
 #include "topology.h"
 
 #define YNB_EXPORT extern "C" __attribute__((visibility("default")))
@@ -1626,8 +1627,11 @@ YNB_EXPORT int ynb_dwconv3x3_bwd_weight(const float* dout, int32_t do_ld, int32_
   return YNB_OK;
 }
 
+static bool pw_wgrad_use_tc(int cin) { return wgrad_tc_kpad(cin) != 0 && !getenv("YNB_PWBW_FFMA"); }
+
 YNB_EXPORT int64_t ynb_pwconv_bwd_weight_workspace_bytes(int64_t pixels, int32_t cin, int32_t cout) {
-  return (int64_t)pw_bwd_chunks(pixels, cin, cout) * ((int64_t)cout * cin + cout) * sizeof(float);
+  const int chunks = std::max(pw_bwd_chunks(pixels, cin, cout), wgrad_tc_chunks(pixels, cout));
+  return (int64_t)chunks * ((int64_t)cout * cin + cout) * sizeof(float) + 16;     // + the device error word
 }
 
 YNB_EXPORT int ynb_pwconv_bwd_weight(const float* dout, int32_t do_ld, int32_t do_off, const float* in, int32_t in_ld,
@@ -1636,6 +1640,29 @@ YNB_EXPORT int ynb_pwconv_bwd_weight(const float* dout, int32_t do_ld, int32_t d
   if (!dout || !in || !dw || !db || !ws || pixels <= 0 || cin <= 0 || cout <= 0 ||
       ws_bytes < ynb_pwconv_bwd_weight_workspace_bytes(pixels, cin, cout))
     return fail(nullptr, YNB_ERR_INVALID, "ynb_pwconv_bwd_weight: bad arguments / workspace too small");
+  if (pw_wgrad_use_tc(cin)) {
+    // tcgen05 path (3xTF32 = fp32 parity): pixels are the contraction dimension
+    cudaStream_t st = (cudaStream_t)stream;
+    const int chunks = wgrad_tc_chunks(pixels, cout);
+    float* pw = (float*)ws;
+    float* pb = pw + (long long)chunks * cout * cin;
+    int* err = (int*)((char*)ws + ynb_pwconv_bwd_weight_workspace_bytes(pixels, cin, cout) - 16);
+    UNIT_TRY(cudaMemsetAsync(err, 0, 4, st));
+    WgradParams p{};
+    p.dout = dout; p.do_ld = do_ld; p.do_off = do_off; p.in = in; p.in_ld = in_ld; p.in_off = in_off;
+    p.partial_w = pw; p.partial_b = pb; p.M = pixels; p.K = cin; p.N = cout; p.err = err;
+    UNIT_TRY(launch_pw_wgrad_tc(p, chunks, st));
+    launch_reduce_partials(pw, chunks, (long long)cout * cin, dw, st);
+    launch_reduce_partials(pb, chunks, cout, db, st);
+    UNIT_TRY(cudaGetLastError());
+    if (getenv("YNB_SYNC_CHECK")) {          // tests: surface a bounded-wait timeout instead of wrong numbers
+      int flag = 0;
+      UNIT_TRY(cudaStreamSynchronize(st));
+      UNIT_TRY(cudaMemcpy(&flag, err, 4, cudaMemcpyDeviceToHost));
+      if (flag) return fail(nullptr, YNB_ERR_CUDA, "ynb_pwconv_bwd_weight: mbarrier timeout code " + std::to_string(flag));
+    }
+    return YNB_OK;
+  }
   const int chunks = pw_bwd_chunks(pixels, cin, cout);
   long long m_per_chunk = (pixels + chunks - 1) / chunks;
   m_per_chunk = (m_per_chunk + kPwBwdSlab - 1) / kPwBwdSlab * kPwBwdSlab;
