@@ -603,6 +603,30 @@ __global__ void __launch_bounds__(32 * kRedSlices) reduce_partials_kernel(const 
     out[i] = t;
   }
 }
+// Same for a partial made of two consecutive pieces per chunk (dW then db): ONE launch, two outputs.
+__global__ void __launch_bounds__(32 * kRedSlices) reduce_partials2_kernel(const float* __restrict__ partial, int chunks,
+                                                                           long long elems_a, float* __restrict__ out_a,
+                                                                           long long elems_b, float* __restrict__ out_b) {
+  __shared__ float sh[kRedSlices][33];
+  const long long elems = elems_a + elems_b;
+  const long long i = (long long)blockIdx.x * 32 + threadIdx.x;
+  float s = 0.0f;
+  if (i < elems)
+    for (int j = threadIdx.y; j < chunks; j += kRedSlices) s += partial[(long long)j * elems + i];
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < elems) {
+    float t = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kRedSlices; ++j) t += sh[j][threadIdx.x];
+    if (i < elems_a) out_a[i] = t; else out_b[i - elems_a] = t;
+  }
+}
+inline void launch_reduce_partials2(const float* partial, int chunks, long long ea, float* oa, long long eb, float* ob,
+                                    cudaStream_t st) {
+  reduce_partials2_kernel<<<(unsigned)((ea + eb + 31) / 32), dim3(32, kRedSlices), 0, st>>>(partial, chunks, ea, oa, eb, ob);
+  YNB_COUNT_LAUNCH();
+}
 inline void launch_reduce_partials(const float* partial, int chunks, long long elems, float* out, cudaStream_t st) {
   reduce_partials_kernel<<<(unsigned)((elems + 31) / 32), dim3(32, kRedSlices), 0, st>>>(partial, chunks, elems, out);
   YNB_COUNT_LAUNCH();

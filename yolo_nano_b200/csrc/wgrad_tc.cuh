@@ -28,8 +28,7 @@ constexpr uint32_t kWgABytes = 128 * 128;          // one A plane: 128 rows (n) 
 struct WgradParams {
   const float* dout; int do_ld, do_off;
   const float* in;   int in_ld, in_off;
-  float* partial_w;                                // [chunks][N][K]
-  float* partial_b;                                // [chunks][N]
+  float* partial;                                  // [chunks][N*K + N]: dW partial, then db partial
   long long M; int K, N;
   int stages;
   long long steps_per_chunk;
@@ -74,13 +73,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(const WgradP
     const int c_lo = lane >> 2, m_lo = lane & 3;            // 8 channels x 4 pixels per warp instruction
     const int kk = 4 * warp + m_lo;                         // pixel inside the step = position along the contraction
     const uint32_t in_row = ((uint32_t)(warp ^ c_lo) << 4) + (uint32_t)m_lo * 4u;   // swizzled 16-byte chunk (row % 8 == c_lo)
-    for (int t = 0; t < nsteps; ++t) {
-      const int s = t % stages;
+    // Two register sets: the global loads of step t + 1 are in flight while step t is split and stored
+    // (DRAM latency would otherwise sit on the producers' critical path once per step).
+    auto load = [&](int t, float (&av)[16], float (&bv)[KPAD / 8]) {
       const long long m = (s0 + t) * kWgStepPix + kk;
       const bool mok = m < p.M;
       const float* drow = p.dout + m * p.do_ld + p.do_off + n0 + c_lo;
       const float* xrow = p.in + m * p.in_ld + p.in_off + c_lo;
-      float av[16], bv[KPAD / 8];
 #pragma unroll
       for (int i = 0; i < 16; ++i) av[i] = (mok && n0 + 8 * i + c_lo < p.N) ? drow[8 * i] : 0.0f;
 #pragma unroll
@@ -88,6 +87,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(const WgradP
         const int k = 8 * i + c_lo;
         bv[i] = !mok ? 0.0f : (k < p.K ? xrow[8 * i] : (k == p.K ? 1.0f : 0.0f));
       }
+    };
+    auto store = [&](int t, const float (&av)[16], const float (&bv)[KPAD / 8]) {
+      const int s = t % stages;
       if (t >= stages) ptx::mbar_wait(&empty_bar[s], ((t / stages) - 1) & 1, p.err, 1);
       uint8_t* st = smem + (size_t)s * kStageBytes;
 #pragma unroll
@@ -109,10 +111,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(const WgradP
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&full_bar[s]);
+    };
+    float av0[16], bv0[KPAD / 8], av1[16], bv1[KPAD / 8];
+    if (nsteps > 0) load(0, av0, bv0);
+#pragma unroll 1
+    for (int t = 0; t < nsteps; t += 2) {
+      if (t + 1 < nsteps) load(t + 1, av1, bv1);
+      store(t, av0, bv0);
+      if (t + 2 < nsteps) load(t + 2, av0, bv0);
+      if (t + 1 < nsteps) store(t + 1, av1, bv1);
     }
     // ---------------- epilogue ----------------
-    float* pw = p.partial_w + (long long)blockIdx.x * p.N * p.K;
-    float* pb = p.partial_b + (long long)blockIdx.x * p.N;
+    float* pw = p.partial + (long long)blockIdx.x * ((long long)p.N * p.K + p.N);
+    float* pb = pw + (long long)p.N * p.K;
     const int lane_base = 32 * (warp & 3), half = warp >> 2;
     const int n = n0 + lane_base + lane;
     if (nsteps > 0) {

@@ -1644,16 +1644,13 @@ YNB_EXPORT int ynb_pwconv_bwd_weight(const float* dout, int32_t do_ld, int32_t d
     // tcgen05 path (3xTF32 = fp32 parity): pixels are the contraction dimension
     cudaStream_t st = (cudaStream_t)stream;
     const int chunks = wgrad_tc_chunks(pixels, cout);
-    float* pw = (float*)ws;
-    float* pb = pw + (long long)chunks * cout * cin;
     int* err = (int*)((char*)ws + ynb_pwconv_bwd_weight_workspace_bytes(pixels, cin, cout) - 16);
     UNIT_TRY(cudaMemsetAsync(err, 0, 4, st));
     WgradParams p{};
     p.dout = dout; p.do_ld = do_ld; p.do_off = do_off; p.in = in; p.in_ld = in_ld; p.in_off = in_off;
-    p.partial_w = pw; p.partial_b = pb; p.M = pixels; p.K = cin; p.N = cout; p.err = err;
+    p.partial = (float*)ws; p.M = pixels; p.K = cin; p.N = cout; p.err = err;
     UNIT_TRY(launch_pw_wgrad_tc(p, chunks, st));
-    launch_reduce_partials(pw, chunks, (long long)cout * cin, dw, st);
-    launch_reduce_partials(pb, chunks, cout, db, st);
+    launch_reduce_partials2((const float*)ws, chunks, (long long)cout * cin, dw, cout, db, st);
     UNIT_TRY(cudaGetLastError());
     if (getenv("YNB_SYNC_CHECK")) {          // tests: surface a bounded-wait timeout instead of wrong numbers
       int flag = 0;
