@@ -4,9 +4,9 @@
 // A = dY^T (rows n), B = X^T (rows k).  Both activations are stored pixel-major ([m][channel]), i.e. the
 // contraction index is the SLOW one, so the operands cannot be fetched by TMA into the K-major layout
 // the MMA wants.  The threads have to touch every element anyway for the hi/lo split of the 3xTF32
-// scheme, so the 8 producer warps do both at once: coalesced 32-byte-sector reads of 32 pixels x 8
-// channels per warp instruction, round-to-nearest split x = hi + lo, and a TRANSPOSING store into the
-// 128-byte-swizzled K-major tiles (conflict-free: a warp writes 8 rows x one 16-byte chunk each).
+// scheme, so the 8 producer warps do both at once: 128-byte coalesced row reads (a lane = one channel,
+// four consecutive pixels), round-to-nearest split x = hi + lo, and a TRANSPOSING 16-byte store per plane
+// into the 128-byte-swizzled K-major tiles (conflict-free: row = channel, chunk = pixel group ^ row % 8).
 // Row K of the B tile is all ones, so column K of the accumulator is the bias gradient for free.
 //
 //   warps 0-7  producers (global -> split -> swizzled smem, mbarrier `full`), then the epilogue
@@ -70,22 +70,28 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(const WgradP
 
   if (warp < 8) {
     // ---------------- producers ----------------
-    const int c_lo = lane >> 2, m_lo = lane & 3;            // 8 channels x 4 pixels per warp instruction
-    const int kk = 4 * warp + m_lo;                         // pixel inside the step = position along the contraction
-    const uint32_t in_row = ((uint32_t)(warp ^ c_lo) << 4) + (uint32_t)m_lo * 4u;   // swizzled 16-byte chunk (row % 8 == c_lo)
+    // Warp w owns pixels 4w .. 4w+3 of the step (= 16-byte chunk w of every tile row); a lane owns one
+    // channel of a group of 32: four 128-byte coalesced row loads give it four consecutive pixels of its
+    // channel = ONE 16-byte store per plane into row (32 i + lane), chunk (w ^ row % 8): conflict-free.
+    const uint32_t in_row = (uint32_t)lane * 128u + ((uint32_t)(warp ^ (lane & 7)) << 4);
     // Two register sets: the global loads of step t + 1 are in flight while step t is split and stored
     // (DRAM latency would otherwise sit on the producers' critical path once per step).
     auto load = [&](int t, float (&av)[16], float (&bv)[KPAD / 8]) {
-      const long long m = (s0 + t) * kWgStepPix + kk;
-      const bool mok = m < p.M;
-      const float* drow = p.dout + m * p.do_ld + p.do_off + n0 + c_lo;
-      const float* xrow = p.in + m * p.in_ld + p.in_off + c_lo;
+      const long long m = (s0 + t) * kWgStepPix + 4 * warp;
+      const float* drow = p.dout + m * p.do_ld + p.do_off + n0 + lane;
+      const float* xrow = p.in + m * p.in_ld + p.in_off + lane;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) av[i] = (mok && n0 + 8 * i + c_lo < p.N) ? drow[8 * i] : 0.0f;
+      for (int i = 0; i < 4; ++i) {
+        const bool cok = n0 + 32 * i + lane < p.N;
 #pragma unroll
-      for (int i = 0; i < KPAD / 8; ++i) {
-        const int k = 8 * i + c_lo;
-        bv[i] = !mok ? 0.0f : (k < p.K ? xrow[8 * i] : (k == p.K ? 1.0f : 0.0f));
+        for (int j = 0; j < 4; ++j) av[4 * i + j] = (cok && m + j < p.M) ? drow[(long long)j * p.do_ld + 32 * i] : 0.0f;
+      }
+#pragma unroll
+      for (int i = 0; i < KPAD / 32; ++i) {
+        const int k = 32 * i + lane;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          bv[4 * i + j] = m + j >= p.M ? 0.0f : (k < p.K ? xrow[(long long)j * p.in_ld + 32 * i] : (k == p.K ? 1.0f : 0.0f));
       }
     };
     auto store = [&](int t, const float (&av)[16], const float (&bv)[KPAD / 8]) {
@@ -93,20 +99,22 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(const WgradP
       if (t >= stages) ptx::mbar_wait(&empty_bar[s], ((t / stages) - 1) & 1, p.err, 1);
       uint8_t* st = smem + (size_t)s * kStageBytes;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float hi, lo;
-        split_tf32(av[i], hi, lo);
-        const uint32_t off = (uint32_t)(8 * i + c_lo) * 128u + in_row;
-        *reinterpret_cast<float*>(st + off) = hi;
-        *reinterpret_cast<float*>(st + kWgABytes + off) = lo;
+      for (int i = 0; i < 4; ++i) {
+        float4 hi, lo;
+        split_tf32(av[4 * i + 0], hi.x, lo.x); split_tf32(av[4 * i + 1], hi.y, lo.y);
+        split_tf32(av[4 * i + 2], hi.z, lo.z); split_tf32(av[4 * i + 3], hi.w, lo.w);
+        const uint32_t off = (uint32_t)i * 4096u + in_row;
+        *reinterpret_cast<float4*>(st + off) = hi;
+        *reinterpret_cast<float4*>(st + kWgABytes + off) = lo;
       }
 #pragma unroll
-      for (int i = 0; i < KPAD / 8; ++i) {
-        float hi, lo;
-        split_tf32(bv[i], hi, lo);
-        const uint32_t off = (uint32_t)(8 * i + c_lo) * 128u + in_row;
-        *reinterpret_cast<float*>(st + 2 * kWgABytes + off) = hi;
-        *reinterpret_cast<float*>(st + 2 * kWgABytes + kBBytes + off) = lo;
+      for (int i = 0; i < KPAD / 32; ++i) {
+        float4 hi, lo;
+        split_tf32(bv[4 * i + 0], hi.x, lo.x); split_tf32(bv[4 * i + 1], hi.y, lo.y);
+        split_tf32(bv[4 * i + 2], hi.z, lo.z); split_tf32(bv[4 * i + 3], hi.w, lo.w);
+        const uint32_t off = (uint32_t)i * 4096u + in_row;
+        *reinterpret_cast<float4*>(st + 2 * kWgABytes + off) = hi;
+        *reinterpret_cast<float4*>(st + 2 * kWgABytes + kBBytes + off) = lo;
       }
       ptx::fence_proxy_async_smem();
       __syncwarp();
@@ -155,6 +163,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(const WgradP
     if (lane == 0) {
     // ---------------- MMA issuer ----------------
     const uint32_t idesc = ptx::make_idesc(2, 128, KPAD);
+    const uint32_t idesc2 = ptx::make_idesc(2, 128, KPAD == 128 ? 256 : KPAD);
     for (int t = 0; t < nsteps; ++t) {
       const int s = t % stages;
       ptx::mbar_wait(&full_bar[s], (t / stages) & 1, p.err, 3);
@@ -165,9 +174,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(const WgradP
       for (int sub = 0; sub < 4; ++sub) {
         const uint32_t ko = sub * 32;
         const uint32_t acc = (t | sub) != 0;
-        ptx::mma_tf32_ss(tmem, ptx::make_sw128_kmajor_desc(a_hi + ko), ptx::make_sw128_kmajor_desc(b_hi + ko), idesc, acc);
-        ptx::mma_tf32_ss(tmem + KPAD, ptx::make_sw128_kmajor_desc(a_lo + ko), ptx::make_sw128_kmajor_desc(b_hi + ko), idesc, acc);
-        ptx::mma_tf32_ss(tmem + KPAD, ptx::make_sw128_kmajor_desc(a_hi + ko), ptx::make_sw128_kmajor_desc(b_lo + ko), idesc, 1u);
+        if (KPAD == 128) {
+          // [B_hi; B_lo] are adjacent in shared memory and [main | corr] adjacent in tensor memory: A_hi x both
+          // is ONE instruction of N = 256 (an MMA costs the same for any N <= 256) - 2 instead of 3 per sub-step
+          ptx::mma_tf32_ss(tmem, ptx::make_sw128_kmajor_desc(a_hi + ko), ptx::make_sw128_kmajor_desc(b_hi + ko), idesc2, acc);
+          ptx::mma_tf32_ss(tmem + KPAD, ptx::make_sw128_kmajor_desc(a_lo + ko), ptx::make_sw128_kmajor_desc(b_hi + ko), idesc, 1u);
+        } else {
+          ptx::mma_tf32_ss(tmem, ptx::make_sw128_kmajor_desc(a_hi + ko), ptx::make_sw128_kmajor_desc(b_hi + ko), idesc, acc);
+          ptx::mma_tf32_ss(tmem + KPAD, ptx::make_sw128_kmajor_desc(a_lo + ko), ptx::make_sw128_kmajor_desc(b_hi + ko), idesc, acc);
+          ptx::mma_tf32_ss(tmem + KPAD, ptx::make_sw128_kmajor_desc(a_hi + ko), ptx::make_sw128_kmajor_desc(b_lo + ko), idesc, 1u);
+        }
       }
       ptx::mma_commit(&empty_bar[s]);
     }
