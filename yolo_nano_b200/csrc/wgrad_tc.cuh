@@ -4,8 +4,8 @@
 // A = dY^T (rows n), B = X^T (rows k).  Both activations are stored pixel-major ([m][channel]), i.e. the
 // contraction index is the SLOW one, so the operands cannot be fetched by TMA into the K-major layout
 // the MMA wants.  The threads have to touch every element anyway for the hi/lo split of the 3xTF32
-// scheme, so the 8 producer warps do both at once: 128-byte coalesced row reads (a lane = one channel,
-// four consecutive pixels), round-to-nearest split x = hi + lo, and a TRANSPOSING 16-byte store per plane
+// scheme, so the 8 producer warps do both at once: 16-byte loads (a lane = four channels of four consecutive
+// pixels, a warp instruction = one whole 512-byte row), round-to-nearest split x = hi + lo, and a TRANSPOSING 16-byte store per plane
 // into the 128-byte-swizzled K-major tiles (conflict-free: row = channel, chunk = pixel group ^ row % 8).
 // Row K of the B tile is all ones, so column K of the accumulator is the bias gradient for free.
 //
@@ -74,24 +74,32 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(const WgradP
     // channel of a group of 32: four 128-byte coalesced row loads give it four consecutive pixels of its
     // channel = ONE 16-byte store per plane into row (32 i + lane), chunk (w ^ row % 8): conflict-free.
     const uint32_t in_row = (uint32_t)lane * 128u + ((uint32_t)(warp ^ (lane & 7)) << 4);
-    // Two register sets: the global loads of step t + 1 are in flight while step t is split and stored
-    // (DRAM latency would otherwise sit on the producers' critical path once per step).
+    // 16-byte loads: a lane reads channels 4*lane .. 4*lane+3 of four consecutive pixels (a warp = one whole
+    // 512-byte row of 128 channels per instruction).  Channel 4*lane + c lives in tile row 32*c + lane (any
+    // fixed permutation of the rows works - the epilogue undoes it), which keeps the stores conflict-free.
     auto load = [&](int t, float (&av)[16], float (&bv)[KPAD / 8]) {
       const long long m = (s0 + t) * kWgStepPix + 4 * warp;
-      const float* drow = p.dout + m * p.do_ld + p.do_off + n0 + lane;
-      const float* xrow = p.in + m * p.in_ld + p.in_off + lane;
+      const float* drow = p.dout + m * p.do_ld + p.do_off + n0 + 4 * lane;
+      const float* xrow = p.in + m * p.in_ld + p.in_off + 4 * lane;
+      const bool aok = n0 + 4 * lane < p.N;                   // N, K are multiples of 4 on this path
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const bool cok = n0 + 32 * i + lane < p.N;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) av[4 * i + j] = (cok && m + j < p.M) ? drow[(long long)j * p.do_ld + 32 * i] : 0.0f;
+      for (int j = 0; j < 4; ++j) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (aok && m + j < p.M) v = *reinterpret_cast<const float4*>(drow + (long long)j * p.do_ld);
+        av[j] = v.x; av[4 + j] = v.y; av[8 + j] = v.z; av[12 + j] = v.w;
       }
 #pragma unroll
-      for (int i = 0; i < KPAD / 32; ++i) {
-        const int k = 32 * i + lane;
+      for (int g = 0; g < KPAD / 128; ++g) {
+        const int k = 128 * g + 4 * lane;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          bv[4 * i + j] = m + j >= p.M ? 0.0f : (k < p.K ? xrow[(long long)j * p.in_ld + 32 * i] : (k == p.K ? 1.0f : 0.0f));
+        for (int j = 0; j < 4; ++j) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m + j < p.M) {
+            if (k < p.K) v = *reinterpret_cast<const float4*>(xrow + (long long)j * p.in_ld + 128 * g);
+            else if (k == p.K) v.x = 1.0f;                    // the ones row: accumulator column K = bias gradient
+          }
+          bv[16 * g + j] = v.x; bv[16 * g + 4 + j] = v.y; bv[16 * g + 8 + j] = v.z; bv[16 * g + 12 + j] = v.w;
+        }
       }
     };
     auto store = [&](int t, const float (&av)[16], const float (&bv)[KPAD / 8]) {
@@ -120,20 +128,25 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(const WgradP
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&full_bar[s]);
     };
-    float av0[16], bv0[KPAD / 8], av1[16], bv1[KPAD / 8];
-    if (nsteps > 0) load(0, av0, bv0);
+    // D register sets: the loads of steps t+1 .. t+D-1 are in flight while step t is split and stored.
+    constexpr int D = 2;          // 3 sets measured no faster (the step time is not load-latency bound)
+    float av[D][16], bv[D][KPAD / 8];
+#pragma unroll
+    for (int d = 0; d < D - 1; ++d)
+      if (d < nsteps) load(d, av[d], bv[d]);
 #pragma unroll 1
-    for (int t = 0; t < nsteps; t += 2) {
-      if (t + 1 < nsteps) load(t + 1, av1, bv1);
-      store(t, av0, bv0);
-      if (t + 2 < nsteps) load(t + 2, av0, bv0);
-      if (t + 1 < nsteps) store(t + 1, av1, bv1);
+    for (int t = 0; t < nsteps; t += D) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        if (t + d + D - 1 < nsteps) load(t + d + D - 1, av[(d + D - 1) % D], bv[(d + D - 1) % D]);
+        if (t + d < nsteps) store(t + d, av[d], bv[d]);
+      }
     }
     // ---------------- epilogue ----------------
     float* pw = p.partial + (long long)blockIdx.x * ((long long)p.N * p.K + p.N);
     float* pb = pw + (long long)p.N * p.K;
     const int lane_base = 32 * (warp & 3), half = warp >> 2;
-    const int n = n0 + lane_base + lane;
+    const int n = n0 + 4 * lane + (warp & 3);               // accumulator row 32*c + lane holds channel 4*lane + c
     if (nsteps > 0) {
       ptx::mbar_wait(&done_bar, 0, p.err, 2);
       ptx::tc_fence_after_sync();
@@ -152,7 +165,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(const WgradP
       if (n < p.N) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int k = c0 + j;
+          const int col = c0 + j;                             // column 128*g + 32*c + l holds input channel 128*g + 4*l + c
+          const int k = (col & ~127) + 4 * (col & 31) + ((col >> 5) & 3);
           const float v = __uint_as_float(r1[j]) + __uint_as_float(r2[j]);
           if (k < p.K) pw[(long long)n * p.K + k] = v;
           else if (k == p.K) pb[n] = v;

@@ -1640,7 +1640,9 @@ YNB_EXPORT int ynb_pwconv_bwd_weight(const float* dout, int32_t do_ld, int32_t d
   if (!dout || !in || !dw || !db || !ws || pixels <= 0 || cin <= 0 || cout <= 0 ||
       ws_bytes < ynb_pwconv_bwd_weight_workspace_bytes(pixels, cin, cout))
     return fail(nullptr, YNB_ERR_INVALID, "ynb_pwconv_bwd_weight: bad arguments / workspace too small");
-  if (pw_wgrad_use_tc(cin)) {
+  const bool aligned = cin % 4 == 0 && cout % 4 == 0 && do_ld % 4 == 0 && do_off % 4 == 0 && in_ld % 4 == 0 &&
+                       in_off % 4 == 0 && ((uintptr_t)dout | (uintptr_t)in) % 16 == 0;
+  if (pw_wgrad_use_tc(cin) && aligned) {
     // tcgen05 path (3xTF32 = fp32 parity): pixels are the contraction dimension
     cudaStream_t st = (cudaStream_t)stream;
     const int chunks = wgrad_tc_chunks(pixels, cout);
