@@ -28,7 +28,7 @@ constexpr uint32_t kWgABytes = 128 * 128;          // one A plane: 128 rows (n) 
 struct WgradParams {
   const float* dout; int do_ld, do_off;
   const float* in;   int in_ld, in_off;
-  float* partial;                                  // [chunks][N*K + N]: dW partial, then db partial
+  float* partial;                                  // [chunks][n tiles][128 rows][KPAD] in ACCUMULATOR order (permuted)
   long long M; int K, N;
   int stages;
   long long steps_per_chunk;
@@ -143,10 +143,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(const WgradP
       }
     }
     // ---------------- epilogue ----------------
-    float* pw = p.partial + (long long)blockIdx.x * ((long long)p.N * p.K + p.N);
-    float* pb = pw + (long long)p.N * p.K;
+    // The accumulator tile goes out as it sits in tensor memory (row = TMEM lane, 64 contiguous bytes per
+    // lane and iteration: whole sectors); the row / column permutation of the producers and the padding are
+    // undone ONCE by wgrad_reduce_kernel when it writes dW / db.
     const int lane_base = 32 * (warp & 3), half = warp >> 2;
-    const int n = n0 + 4 * lane + (warp & 3);               // accumulator row 32*c + lane holds channel 4*lane + c
+    float* pt = p.partial + (((long long)blockIdx.x * gridDim.y + blockIdx.y) * 128 + lane_base + lane) * KPAD;
     if (nsteps > 0) {
       ptx::mbar_wait(&done_bar, 0, p.err, 2);
       ptx::tc_fence_after_sync();
@@ -162,16 +163,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(const WgradP
 #pragma unroll
         for (int j = 0; j < 16; ++j) { r1[j] = 0u; r2[j] = 0u; }
       }
-      if (n < p.N) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int col = c0 + j;                             // column 128*g + 32*c + l holds input channel 128*g + 4*l + c
-          const int k = (col & ~127) + 4 * (col & 31) + ((col >> 5) & 3);
-          const float v = __uint_as_float(r1[j]) + __uint_as_float(r2[j]);
-          if (k < p.K) pw[(long long)n * p.K + k] = v;
-          else if (k == p.K) pb[n] = v;
-        }
-      }
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(pt + c0 + j) =
+            make_float4(__uint_as_float(r1[j]) + __uint_as_float(r2[j]), __uint_as_float(r1[j + 1]) + __uint_as_float(r2[j + 1]),
+                        __uint_as_float(r1[j + 2]) + __uint_as_float(r2[j + 2]), __uint_as_float(r1[j + 3]) + __uint_as_float(r2[j + 3]));
     }
   } else {
     if (lane == 0) {
@@ -213,6 +209,36 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(const WgradP
   }
 }
 
+// Second stage: fixed-order sum over the chunks in accumulator order (coalesced), then ONE permuted write:
+// tile row 32*c + l = output channel 4*l + c; column 128*g + 32*c + l = input channel 128*g + 4*l + c;
+// column K = bias gradient.
+__global__ void __launch_bounds__(1024) wgrad_reduce_kernel(const float* __restrict__ partial, int chunks, int ntiles,
+                                                            int kpad, int N, int K, float* __restrict__ dw,
+                                                            float* __restrict__ db) {
+  __shared__ float sh[32][33];
+  const long long elems = (long long)ntiles * 128 * kpad;
+  const long long e = (long long)blockIdx.x * 32 + threadIdx.x;
+  float s = 0.0f;
+  if (e < elems)
+    for (int j = threadIdx.y; j < chunks; j += 32) s += partial[(long long)j * elems + e];
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && e < elems) {
+    float t = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t += sh[j][threadIdx.x];
+    const int col = (int)(e % kpad);
+    const long long row = e / kpad;
+    const int r = (int)(row % 128), tile = (int)(row / 128);
+    const int n = tile * 128 + 4 * (r & 31) + (r >> 5);
+    const int k = (col & ~127) + 4 * (col & 31) + ((col >> 5) & 3);
+    if (n < N) {
+      if (k < K) dw[(long long)n * K + k] = t;
+      else if (k == K) db[n] = t;
+    }
+  }
+}
+
 inline int wgrad_tc_kpad(int K) { return K + 1 <= 128 ? 128 : (K + 1 <= 256 ? 256 : 0); }
 inline int wgrad_tc_chunks(long long M, int N) {
   const int ntile = (N + 127) / 128;
@@ -220,6 +246,10 @@ inline int wgrad_tc_chunks(long long M, int N) {
   const long long total_steps = (M + kWgStepPix - 1) / kWgStepPix;
   if (chunks > total_steps) chunks = total_steps;
   return (int)(chunks < 1 ? 1 : chunks);
+}
+
+inline long long wgrad_tc_partial_floats(long long M, int K, int N) {
+  return (long long)wgrad_tc_chunks(M, N) * ((N + 127) / 128) * 128 * wgrad_tc_kpad(K);
 }
 
 inline cudaError_t launch_pw_wgrad_tc(WgradParams p, int chunks, cudaStream_t st) {

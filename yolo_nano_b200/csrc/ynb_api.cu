@@ -1630,8 +1630,9 @@ YNB_EXPORT int ynb_dwconv3x3_bwd_weight(const float* dout, int32_t do_ld, int32_
 static bool pw_wgrad_use_tc(int cin) { return wgrad_tc_kpad(cin) != 0 && !getenv("YNB_PWBW_FFMA"); }
 
 YNB_EXPORT int64_t ynb_pwconv_bwd_weight_workspace_bytes(int64_t pixels, int32_t cin, int32_t cout) {
-  const int chunks = std::max(pw_bwd_chunks(pixels, cin, cout), wgrad_tc_chunks(pixels, cout));
-  return (int64_t)chunks * ((int64_t)cout * cin + cout) * sizeof(float) + 16;     // + the device error word
+  int64_t floats = (int64_t)pw_bwd_chunks(pixels, cin, cout) * ((int64_t)cout * cin + cout);
+  if (wgrad_tc_kpad(cin)) floats = std::max<int64_t>(floats, wgrad_tc_partial_floats(pixels, cin, cout));
+  return floats * sizeof(float) + 16;     // + the device error word
 }
 
 YNB_EXPORT int ynb_pwconv_bwd_weight(const float* dout, int32_t do_ld, int32_t do_off, const float* in, int32_t in_ld,
@@ -1652,7 +1653,13 @@ YNB_EXPORT int ynb_pwconv_bwd_weight(const float* dout, int32_t do_ld, int32_t d
     p.dout = dout; p.do_ld = do_ld; p.do_off = do_off; p.in = in; p.in_ld = in_ld; p.in_off = in_off;
     p.partial = (float*)ws; p.M = pixels; p.K = cin; p.N = cout; p.err = err;
     UNIT_TRY(launch_pw_wgrad_tc(p, chunks, st));
-    launch_reduce_partials2((const float*)ws, chunks, (long long)cout * cin, dw, cout, db, st);
+    {
+      const int ntiles = (cout + 127) / 128, kpad = wgrad_tc_kpad(cin);
+      const long long elems = (long long)ntiles * 128 * kpad;
+      wgrad_reduce_kernel<<<(unsigned)((elems + 31) / 32), dim3(32, 32), 0, st>>>((const float*)ws, chunks, ntiles, kpad, cout,
+                                                                                cin, dw, db);
+      YNB_COUNT_LAUNCH();
+    }
     UNIT_TRY(cudaGetLastError());
     if (getenv("YNB_SYNC_CHECK")) {          // tests: surface a bounded-wait timeout instead of wrong numbers
       int flag = 0;
