@@ -316,3 +316,30 @@ def test_shuffle_branch2_train_step_matches_autograd(G, TR):
         assert float((grads[i]["bias"].cpu() - bn.bias.grad).abs().max()) <= 1e-3 * float(bn.weight.grad.abs().max())
     # running statistics moved exactly as torch moves them
     torch.testing.assert_close(layers.layers[1].running_var.cpu(), bn1.running_var, rtol=1e-4, atol=1e-6)
+
+
+def test_train_loss_full_config5_batch_is_additive(G, TR):
+    """BASELINE config 5's per-GPU shape (32 images, 416^2, COCO-80), size-independent property: the loss sums
+    are additive over images and the gradient of an anchor depends on its own image only.  With power-of-two
+    batch sizes the 1/B factors are exact, so the B=32 gradients equal 1/4 of the B=8 gradients of the same
+    images BIT FOR BIT, and 32 * loss(B=32) equals the sum of 8 * loss(B=8) over the four sub-batches."""
+    torch.manual_seed(5)
+    size, classes, batch, ld = 416, 80, 32, 256
+    anchors = W.anchors_for(classes)
+    grids = [size // s for s in (8, 16, 32)]
+    labels = torch.rand(batch, 24, 5, device=G.DEV)
+    xy, wh = labels[..., :2] * 0.6, labels[..., 2:4] * 0.35 + 0.02
+    labels = torch.cat([xy, xy + wh, (labels[..., 4:] * classes).floor()], -1).contiguous()
+    target = TR.build_targets(labels, None, size, anchors)
+    assert int((target[:, :, 0] > 0).sum()) > 300
+    raw = [torch.randn(batch, g * g, ld, device=G.DEV) * 1.5 for g in grids]
+    losses, grads = TR.train_loss(raw, target, size, classes, anchors)
+    total = torch.zeros(4, dtype=torch.float64)
+    for b0 in range(0, batch, 8):
+        l8, g8 = TR.train_loss([r[b0:b0 + 8].contiguous() for r in raw], target[b0:b0 + 8].contiguous(), size, classes,
+                               anchors)
+        total += l8.cpu().double() * 8
+        for full, part in zip(grads, g8):
+            assert torch.equal(full[b0:b0 + 8] * 4.0, part)
+    np.testing.assert_allclose(losses.cpu().double().numpy() * batch, total.numpy(), rtol=1e-6)
+    assert torch.isfinite(losses).all() and all(torch.isfinite(g).all() for g in grads)

@@ -124,23 +124,27 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(const WgradP
         *reinterpret_cast<float4*>(st + 2 * kWgABytes + off) = hi;
         *reinterpret_cast<float4*>(st + 2 * kWgABytes + kBBytes + off) = lo;
       }
+    };
+    // fence.proxy.async compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC: the membar DRAINS every outstanding
+    // global load of the thread, so loads cannot be kept in flight across it.  Hence the loop works on PAIRS of
+    // steps: both steps' loads are issued together (one DRAM latency per pair), both tiles are stored, ONE
+    // fence publishes both stages.
+    auto publish = [&](int t) {
+      if (lane == 0) ptx::mbar_arrive(&full_bar[t % stages]);
+    };
+    float av[2][16], bv[2][KPAD / 8];
+    const int pair = stages >= 3 ? 2 : 1;          // with 2 stages a pair would serialise producers and MMA
+#pragma unroll 1
+    for (int t = 0; t < nsteps; t += pair) {
+      const bool two = pair == 2 && t + 1 < nsteps;
+      load(t, av[0], bv[0]);
+      if (two) load(t + 1, av[1], bv[1]);
+      store(t, av[0], bv[0]);
+      if (two) store(t + 1, av[1], bv[1]);
       ptx::fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&full_bar[s]);
-    };
-    // D register sets: the loads of steps t+1 .. t+D-1 are in flight while step t is split and stored.
-    constexpr int D = 2;          // 3 sets measured no faster (the step time is not load-latency bound)
-    float av[D][16], bv[D][KPAD / 8];
-#pragma unroll
-    for (int d = 0; d < D - 1; ++d)
-      if (d < nsteps) load(d, av[d], bv[d]);
-#pragma unroll 1
-    for (int t = 0; t < nsteps; t += D) {
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        if (t + d + D - 1 < nsteps) load(t + d + D - 1, av[(d + D - 1) % D], bv[(d + D - 1) % D]);
-        if (t + d < nsteps) store(t + d, av[d], bv[d]);
-      }
+      publish(t);
+      if (two) publish(t + 1);
     }
     // ---------------- epilogue ----------------
     // The accumulator tile goes out as it sits in tensor memory (row = TMEM lane, 64 contiguous bytes per
