@@ -31,6 +31,7 @@ struct WgradParams {
   float* partial;                                  // [chunks][n tiles][128 rows][KPAD] in ACCUMULATOR order (permuted)
   long long M; int K, N;
   int stages;
+  int raw_slots;                                   // KPAD = 128: thread-private cp.async staging slots (0 = register path)
   long long steps_per_chunk;
   int* err;
 };
@@ -132,6 +133,58 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(const WgradP
     auto publish = [&](int t) {
       if (lane == 0) ptx::mbar_arrive(&full_bar[t % stages]);
     };
+    if (KPAD == 128 && p.raw_slots > 0) {
+      // Deep prefetch that survives the fence: the raw 16-byte pieces of the next steps travel global ->
+      // shared with cp.async into THREAD-PRIVATE slots behind the operand stages (a thread reads back only
+      // what it copied itself, so cp.async.wait_group is the only synchronisation).  cp.async copies are not
+      // "outstanding loads" of the thread, so the membar of the proxy fence does not wait for them:
+      // raw_slots - 1 whole steps stay in flight per thread.
+      const int R = p.raw_slots;
+      float4* rawbase = reinterpret_cast<float4*>(smem + (size_t)stages * kStageBytes);   // [R][8][256] float4
+      auto issue = [&](int t) {
+        if (t < nsteps) {
+          const long long m = (s0 + t) * kWgStepPix + 4 * warp;
+          float4* slot = rawbase + (size_t)(t % R) * 8 * 256 + threadIdx.x;
+          const float* drow = p.dout + m * p.do_ld + p.do_off + n0 + 4 * lane;
+          const float* xrow = p.in + m * p.in_ld + p.in_off + 4 * lane;
+          const bool aok = n0 + 4 * lane < p.N, bok = 4 * lane < p.K;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const bool rok = m + j < p.M;
+            ptx::cp_async_16(slot + j * 256, (rok && aok) ? (const void*)(drow + (long long)j * p.do_ld) : (const void*)p.dout,
+                             (rok && aok) ? 16u : 0u);
+            ptx::cp_async_16(slot + (4 + j) * 256, (rok && bok) ? (const void*)(xrow + (long long)j * p.in_ld) : (const void*)p.in,
+                             (rok && bok) ? 16u : 0u);
+          }
+        }
+        ptx::cp_async_commit();
+      };
+      for (int t = 0; t < R; ++t) issue(t);
+      float av[16], bv[16];
+#pragma unroll 1
+      for (int t = 0; t < nsteps; ++t) {
+        // groups committed so far: R + t; step t's group is complete when at most R - 1 are pending
+        if (R == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else if (R == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        const float4* slot = rawbase + (size_t)(t % R) * 8 * 256 + threadIdx.x;
+        const long long m = (s0 + t) * kWgStepPix + 4 * warp;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 a = slot[j * 256];
+          float4 b = slot[(4 + j) * 256];
+          if (4 * lane == p.K && m + j < p.M) b.x = 1.0f;      // the ones row (bias gradient)
+          av[j] = a.x; av[4 + j] = a.y; av[8 + j] = a.z; av[12 + j] = a.w;
+          bv[j] = b.x; bv[4 + j] = b.y; bv[8 + j] = b.z; bv[12 + j] = b.w;
+        }
+        store(t, av, reinterpret_cast<const float (&)[KPAD / 8]>(bv));
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        publish(t);
+        issue(t + R);                                          // refills the slot just consumed
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else {
     float av[2][16], bv[2][KPAD / 8];
     const int pair = stages >= 3 ? 2 : 1;          // with 2 stages a pair would serialise producers and MMA
 #pragma unroll 1
@@ -145,6 +198,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(const WgradP
       __syncwarp();
       publish(t);
       if (two) publish(t + 1);
+    }
     }
     // ---------------- epilogue ----------------
     // The accumulator tile goes out as it sits in tensor memory (row = TMEM lane, 64 contiguous bytes per
@@ -260,9 +314,11 @@ inline cudaError_t launch_pw_wgrad_tc(WgradParams p, int chunks, cudaStream_t st
   const int kpad = wgrad_tc_kpad(p.K);
   const long long total_steps = (p.M + kWgStepPix - 1) / kWgStepPix;
   p.steps_per_chunk = (total_steps + chunks - 1) / chunks;
-  p.stages = kpad == 128 ? 3 : 2;
   const size_t stage = 2 * kWgABytes + 2 * (size_t)kpad * 128;
-  const size_t smem = stage * p.stages + 1024;
+  static const bool no_raw = getenv("YNB_WGRAD_NO_RAW") != nullptr;
+  if (kpad == 128 && !no_raw) { p.stages = 2; p.raw_slots = 3; }       // 2 x 64 KB operand stages + 3 x 32 KB raw slots
+  else { p.stages = kpad == 128 ? 3 : 2; p.raw_slots = 0; }
+  const size_t smem = stage * p.stages + (size_t)p.raw_slots * 32768 + 1024;
   dim3 grid(chunks, (p.N + 127) / 128);
   cudaError_t e;
   if (kpad == 128) {
