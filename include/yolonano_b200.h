@@ -343,6 +343,15 @@ int  ynb_pwconv_bwd_weight(const float* dout_dev, int32_t dout_ld, int32_t dout_
                            int64_t pixels, int32_t cin, int32_t cout,
                            void* workspace_dev, int64_t workspace_bytes, void* stream);
 
+/* Weight / bias gradient of a dense 3x3 conv, pad 1, stride 1 (the `smooth` convs, models/yolo_nano.py:44-47;
+ * utils/modules.py:11 with k = 3), NHWC views of [batch, h, w]: nine tap-shifted pointwise weight gradients on
+ * the tcgen05 kernel.  dw9_dev [9][cout][cin], tap t = ky * 3 + kx  (torch: weight.grad[n][k][ky][kx]);
+ * db_dev [cout].  Needs 16-byte aligned views, cin <= 255.  workspace: ynb_pwconv_bwd_weight_workspace_bytes. */
+int  ynb_conv3x3_bwd_weight(const float* dout_dev, int32_t dout_ld, int32_t dout_off,
+                            const float* in_dev, int32_t in_ld, int32_t in_off, float* dw9_dev, float* db_dev,
+                            int32_t batch, int32_t h, int32_t w, int32_t cin, int32_t cout,
+                            void* workspace_dev, int64_t workspace_bytes, void* stream);
+
 /* Backward of ReLU / LeakyReLU(0.1) (YNB_ACT_RELU | YNB_ACT_LEAKY) from the forward OUTPUT:
  *   dpre[m, c] = dout[m, c] * (out[m, c] > 0 ? 1 : slope). */
 int  ynb_act_bwd(const float* dout_dev, int32_t dout_ld, int32_t dout_off, const float* out_dev, int32_t out_ld,

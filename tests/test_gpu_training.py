@@ -343,3 +343,21 @@ def test_train_loss_full_config5_batch_is_additive(G, TR):
             assert torch.equal(full[b0:b0 + 8] * 4.0, part)
     np.testing.assert_allclose(losses.cpu().double().numpy() * batch, total.numpy(), rtol=1e-6)
     assert torch.isfinite(losses).all() and all(torch.isfinite(g).all() for g in grads)
+
+
+@pytest.mark.parametrize("b,hw,k,n", [(2, 26, 96, 96), (3, 13, 96, 96), (1, 52, 96, 96), (2, 7, 8, 4)])
+def test_conv3x3_backward_weight(G, TR, b, hw, k, n):
+    """models/yolo_nano.py:44-47 `smooth_*` = Conv(96, 96, k=3, p=1): weight / bias gradient of the dense 3x3 conv
+    (nine tap-shifted tcgen05 weight gradients, zero padding by predication) vs autograd."""
+    torch.manual_seed(b + hw + k)
+    x = torch.randn(b, k, hw, hw)
+    w = (torch.randn(n, k, 3, 3) / (3 * k ** 0.5)).requires_grad_(True)
+    bias = torch.randn(n, requires_grad=True)
+    y = F.conv2d(x, w, bias, 1, 1)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    nhwc = lambda t_: t_.detach().permute(0, 2, 3, 1).contiguous().to(G.DEV)  # noqa: E731
+    dw, db = TR.conv3x3_backward_weight(nhwc(dy), nhwc(x))
+    got = dw.cpu().view(3, 3, n, k).permute(2, 3, 0, 1)
+    torch.testing.assert_close(got, w.grad, rtol=1e-4, atol=2e-5 * float(w.grad.abs().max()))
+    torch.testing.assert_close(db.cpu(), bias.grad, rtol=1e-4, atol=2e-5 * float(bias.grad.abs().max()))

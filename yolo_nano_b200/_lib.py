@@ -103,6 +103,7 @@ SIGNATURES = {
                                    _p, _i64, _p]),
     "ynb_bn_train_bwd": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _p, _i32, _i32, _p, _p, _p, _p, _i32, _i32, _p,
                                    _i64, _i32, _i32, _p, _i64, _p]),
+    "ynb_conv3x3_bwd_weight": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _p, _p, _i32, _i32, _i32, _i32, _i32, _p, _i64, _p]),
     "ynb_act_bwd": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _p, _i32, _i32, _i64, _i32, _i32, _p]),
 }
 

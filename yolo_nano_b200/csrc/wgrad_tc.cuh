@@ -31,6 +31,8 @@ struct WgradParams {
   float* partial;                                  // [chunks][n tiles][128 rows][KPAD] in ACCUMULATOR order (permuted)
   long long M; int K, N;
   int stages;
+  int H, W, dy, dx;                                // H > 0: tap (dy, dx) of a 3x3 conv (pad 1, stride 1): X row = pixel shifted by the
+                                                   // tap, zero outside the image (the conv's padding); H = 0: pointwise
   int raw_slots;                                   // KPAD = 128: thread-private cp.async staging slots (0 = register path)
   long long steps_per_chunk;
   int* err;
@@ -78,6 +80,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(const WgradP
     // 16-byte loads: a lane reads channels 4*lane .. 4*lane+3 of four consecutive pixels (a warp = one whole
     // 512-byte row of 128 channels per instruction).  Channel 4*lane + c lives in tile row 32*c + lane (any
     // fixed permutation of the rows works - the epilogue undoes it), which keeps the stores conflict-free.
+    // source pixel of X for output pixel m (3x3 tap: shifted, invalid outside the image)
+    auto xsrc = [&](long long m, bool& ok) -> long long {
+      ok = m < p.M;
+      if (p.H > 0 && ok) {
+        const int mi = (int)m;
+        const int x = mi % p.W, y = (mi / p.W) % p.H;
+        ok = (unsigned)(y + p.dy) < (unsigned)p.H && (unsigned)(x + p.dx) < (unsigned)p.W;
+        return m + p.dy * p.W + p.dx;
+      }
+      return m;
+    };
     auto load = [&](int t, float (&av)[16], float (&bv)[KPAD / 8]) {
       const long long m = (s0 + t) * kWgStepPix + 4 * warp;
       const float* drow = p.dout + m * p.do_ld + p.do_off + n0 + 4 * lane;
@@ -96,7 +109,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(const WgradP
         for (int j = 0; j < 4; ++j) {
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
           if (m + j < p.M) {
-            if (k < p.K) v = *reinterpret_cast<const float4*>(xrow + (long long)j * p.in_ld + 128 * g);
+            bool xok;
+            const long long xs = xsrc(m + j, xok);
+            if (k < p.K) { if (xok) v = *reinterpret_cast<const float4*>(p.in + xs * p.in_ld + p.in_off + 4 * lane + 128 * g); }
             else if (k == p.K) v.x = 1.0f;                    // the ones row: accumulator column K = bias gradient
           }
           bv[16 * g + j] = v.x; bv[16 * g + 4 + j] = v.y; bv[16 * g + 8 + j] = v.z; bv[16 * g + 12 + j] = v.w;
@@ -153,8 +168,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(const WgradP
             const bool rok = m + j < p.M;
             ptx::cp_async_16(slot + j * 256, (rok && aok) ? (const void*)(drow + (long long)j * p.do_ld) : (const void*)p.dout,
                              (rok && aok) ? 16u : 0u);
-            ptx::cp_async_16(slot + (4 + j) * 256, (rok && bok) ? (const void*)(xrow + (long long)j * p.in_ld) : (const void*)p.in,
-                             (rok && bok) ? 16u : 0u);
+            bool xok;
+            const long long xs = xsrc(m + j, xok);
+            ptx::cp_async_16(slot + (4 + j) * 256,
+                             (xok && bok) ? (const void*)(p.in + xs * p.in_ld + p.in_off + 4 * lane) : (const void*)p.in,
+                             (xok && bok) ? 16u : 0u);
           }
         }
         ptx::cp_async_commit();

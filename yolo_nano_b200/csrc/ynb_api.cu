@@ -1752,6 +1752,46 @@ YNB_EXPORT int32_t ynb_raw_ld(const ynb_engine* e) {
   return e ? round_up(e->cfg.num_anchors * (1 + e->cfg.num_classes + 4), 4) : 0;   // = plan_workspace's raw[l].ld
 }
 
+// Weight gradient of a dense 3x3 conv (pad 1, stride 1: the four `smooth` convs, models/yolo_nano.py:44-47):
+// nine tap-shifted pointwise weight gradients on the tcgen05 kernel, dW[t][n][k] = sum_m dY[m][n] * X[m + tap_t][k]
+// with X = 0 outside the image.
+YNB_EXPORT int ynb_conv3x3_bwd_weight(const float* dout, int32_t do_ld, int32_t do_off, const float* in, int32_t in_ld,
+                                      int32_t in_off, float* dw9, float* db, int32_t batch, int32_t h, int32_t w_,
+                                      int32_t cin, int32_t cout, void* ws, int64_t ws_bytes, void* stream) {
+  const int64_t pixels = (int64_t)batch * h * w_;
+  const bool aligned = cin % 4 == 0 && cout % 4 == 0 && do_ld % 4 == 0 && do_off % 4 == 0 && in_ld % 4 == 0 &&
+                       in_off % 4 == 0 && ((uintptr_t)dout | (uintptr_t)in) % 16 == 0;
+  if (!dout || !in || !dw9 || !db || !ws || batch <= 0 || h <= 0 || w_ <= 0 || cin <= 0 || cout <= 0 ||
+      pixels >= (1LL << 31) || ws_bytes < ynb_pwconv_bwd_weight_workspace_bytes(pixels, cin, cout))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_conv3x3_bwd_weight: bad arguments / workspace too small");
+  if (!aligned || !wgrad_tc_kpad(cin))
+    return fail(nullptr, YNB_ERR_UNSUPPORTED, "ynb_conv3x3_bwd_weight: needs 16-byte aligned views and cin <= 255");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunks = wgrad_tc_chunks(pixels, cout);
+  int* err = (int*)((char*)ws + ynb_pwconv_bwd_weight_workspace_bytes(pixels, cin, cout) - 16);
+  UNIT_TRY(cudaMemsetAsync(err, 0, 4, st));
+  const int ntiles = (cout + 127) / 128, kpad = wgrad_tc_kpad(cin);
+  const long long elems = (long long)ntiles * 128 * kpad;
+  for (int t = 0; t < 9; ++t) {
+    WgradParams p{};
+    p.dout = dout; p.do_ld = do_ld; p.do_off = do_off; p.in = in; p.in_ld = in_ld; p.in_off = in_off;
+    p.partial = (float*)ws; p.M = pixels; p.K = cin; p.N = cout; p.err = err;
+    p.H = h; p.W = w_; p.dy = t / 3 - 1; p.dx = t % 3 - 1;
+    UNIT_TRY(launch_pw_wgrad_tc(p, chunks, st));
+    wgrad_reduce_kernel<<<(unsigned)((elems + 31) / 32), dim3(32, 32), 0, st>>>((const float*)ws, chunks, ntiles, kpad, cout,
+                                                                              cin, dw9 + (long long)t * cout * cin, db);
+    YNB_COUNT_LAUNCH();
+  }
+  UNIT_TRY(cudaGetLastError());
+  if (getenv("YNB_SYNC_CHECK")) {
+    int flag = 0;
+    UNIT_TRY(cudaStreamSynchronize(st));
+    UNIT_TRY(cudaMemcpy(&flag, err, 4, cudaMemcpyDeviceToHost));
+    if (flag) return fail(nullptr, YNB_ERR_CUDA, "ynb_conv3x3_bwd_weight: mbarrier timeout code " + std::to_string(flag));
+  }
+  return YNB_OK;
+}
+
 // ---- BatchNorm2d in training mode ----------------------------------------------------------------------
 namespace {
 bool bn_args_ok(long long M, int C, std::initializer_list<int> strides, std::initializer_list<const void*> ptrs) {

@@ -150,6 +150,22 @@ def pwconv_backward_weight(dout: torch.Tensor, x: torch.Tensor):
     return dw, db
 
 
+def conv3x3_backward_weight(dout: torch.Tensor, x: torch.Tensor):
+    """Dense 3x3 conv, pad 1, stride 1 (the `smooth` convs): dout [B,H,W,N], x [B,H,W,K] ->
+    (dw [9, N, K] tap-major, db [N])."""
+    dev = _dev(dout, x)
+    lib = _lib.load()
+    b, h, w, n = dout.shape
+    k = x.shape[-1]
+    wsb = lib.ynb_pwconv_bwd_weight_workspace_bytes(b * h * w, k, n)
+    ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
+    dw = torch.empty((9, n, k), device=dev, dtype=torch.float32)
+    db = torch.empty((n,), device=dev, dtype=torch.float32)
+    _check(lib.ynb_conv3x3_bwd_weight(_ptr(dout), n, 0, _ptr(x), k, 0, _ptr(dw), _ptr(db), b, h, w, k, n, _ptr(ws), wsb,
+                                      _stream_ptr(dev)), "ynb_conv3x3_bwd_weight")
+    return dw, db
+
+
 def pwconv_backward_data(dout: torch.Tensor, w_nk: torch.Tensor, tensor_cores: bool = True) -> torch.Tensor:
     """dx [M, K] = dout [M, N] . w [N, K]: the forward pointwise GEMM with the transposed weights and a
     zero bias (tcgen05 3xTF32 by default).  N and K must be multiples of 4."""
