@@ -223,19 +223,21 @@ __global__ void __launch_bounds__(kLossThreads) train_loss_kernel(const TrainLos
   }
 }
 
-// Second stage: fixed-order sum of the block partials, / batch_size.
-__global__ void train_loss_finalize_kernel(const double* __restrict__ partials, int blocks, int B, float* __restrict__ losses) {
-  __shared__ double sh[4][32];
-  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;     // 128 threads: one warp per loss
+// Second stage: fixed-order sum of the block partials, / batch_size.  256 threads per loss keep the serial
+// chain at blocks / 256 loads (a single warp per loss cost 9 us at 1824 blocks), then a fixed tree.
+__global__ void __launch_bounds__(1024) train_loss_finalize_kernel(const double* __restrict__ partials, int blocks, int B,
+                                                                   float* __restrict__ losses) {
+  __shared__ double sh[4][256];
+  const int k = threadIdx.x >> 8, i = threadIdx.x & 255;
   double s = 0.0;
-  for (int i = lane; i < blocks; i += 32) s += partials[(long long)i * 4 + k];
-  sh[k][lane] = s;
+  for (int j = i; j < blocks; j += 256) s += partials[(long long)j * 4 + k];
+  sh[k][i] = s;
   __syncthreads();
-  if (lane == 0) {
-    double t = 0.0;
-    for (int i = 0; i < 32; ++i) t += sh[k][i];
-    losses[k] = (float)(t / (double)B);
+  for (int o = 128; o > 0; o >>= 1) {
+    if (i < o) sh[k][i] += sh[k][i + o];
+    __syncthreads();
   }
+  if (i == 0) losses[k] = (float)(sh[k][0] / (double)B);
 }
 
 inline int train_loss_blocks(int batch, int input_size) {
@@ -254,7 +256,7 @@ inline cudaError_t launch_train_loss(TrainLossParams p, float* losses, cudaStrea
   const size_t smem = (size_t)kLossCells * p.A * (11 + 5) * sizeof(float);
   train_loss_kernel<<<blocks, kLossThreads, smem, st>>>(p);
   YNB_COUNT_LAUNCH();
-  train_loss_finalize_kernel<<<1, 128, 0, st>>>(p.partials, blocks, p.B, losses);
+  train_loss_finalize_kernel<<<1, 1024, 0, st>>>(p.partials, blocks, p.B, losses);
   YNB_COUNT_LAUNCH();
   return cudaGetLastError();
 }
