@@ -236,7 +236,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   // Weights do not depend on the previous kernel: the resident W planes are requested before
   // the programmatic-dependency wait, i.e. while the predecessor is still draining.
-  if (warp == kTcProducerWarp && lane == 0 && p.w_resident) {
+  if (warp == kTcProducerWarp && p.w_resident && ptx::elect_one()) {
     ptx::mbar_arrive_expect_tx(w_full, w_res_bytes);
     for (int st = 0; st < p.num_steps; ++st) {
       ptx::tma_load_2d(w_hi_ptr(0, st), &tmWhi, w_full, st * kTcBK, 0);
@@ -248,7 +248,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int prole = warp == kTcProducerWarp ? 0 : (warp == 14 ? 1 : (warp == 15 ? 2 : -1));
   if (prole >= 0) {
     // ================= TMA producers (role r issues the boxes j with j % nprod == r) =================
-    if (lane == 0 && prole < nprod) {
+    // elect.sync in a warp-uniform branch (not `lane == 0`): the compiler then knows a single thread runs the
+    // loop and keeps descriptors / coordinates in UNIFORM registers — no R2UR + ELECT waterfall loop around
+    // every UTMALDG / UTCHMMA (measured, tools/mma_probe2.cu: 142 -> 67 cycles per issued MMA).
+    if (prole < nprod && ptx::elect_one()) {
       const bool do_a = 0 % nprod == prole;
       const bool do_alo = box_alo >= 0 && box_alo % nprod == prole;
       const bool do_whi = box_whi >= 0 && box_whi % nprod == prole;
@@ -288,7 +291,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == kTcMmaWarp) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       const uint32_t idesc = ptx::make_idesc(2 /*tf32*/, kTcBM, p.Npad);
       const uint32_t idesc2 = ptx::make_idesc(2, kTcBM, 2 * p.Npad);
       int s = 0;
@@ -616,7 +619,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       for (int c0 = col_begin; c0 < col_end; c0 += 32) {
         if (p.tma_store) {
-          if (lane == 0) ptx::bulk_wait_read<0>();   // the previous store has finished reading the box
+          if (ptx::elect_one()) ptx::bulk_wait_read<0>();   // the previous store (same elected lane) has finished reading the box
           __syncwarp();
         }
         drain16(c0, 0);
@@ -630,7 +633,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // ---- plain pointwise output: the swizzled box leaves through one TMA store ----
           ptx::fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (ptx::elect_one()) {
             ptx::tma_store_2d(&tmOut, sbox, c0, (int)m_base);   // rows >= M / cols >= N4 are clipped
             ptx::bulk_commit();
           }
@@ -673,7 +676,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (lane == 0 && q == 0) YNB_TRACE(5, tile, group);
     }
-    if (p.tma_store && lane == 0) ptx::bulk_wait<0>();   // all output boxes have landed
+    __syncwarp();
+    if (p.tma_store && ptx::elect_one()) ptx::bulk_wait<0>();   // all output boxes have landed
   }
 
   ptx::tc_fence_before_sync();

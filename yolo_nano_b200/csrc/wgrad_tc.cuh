@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(const WgradP
                         __uint_as_float(r1[j + 2]) + __uint_as_float(r2[j + 2]), __uint_as_float(r1[j + 3]) + __uint_as_float(r2[j + 3]));
     }
   } else {
-    if (lane == 0) {
+    if (ptx::elect_one()) {   // elect.sync (not lane == 0): operands stay in uniform registers, MMAs issue back to back
     // ---------------- MMA issuer ----------------
     const uint32_t idesc = ptx::make_idesc(2, 128, KPAD);
     const uint32_t idesc2 = ptx::make_idesc(2, 128, KPAD == 128 ? 256 : KPAD);

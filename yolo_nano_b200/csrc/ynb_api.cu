@@ -101,7 +101,7 @@ struct ynb_engine {
   PreLut prelut;                           // uint8 -> normalised float32 table (ynb_set_normalization)
   PreLut* d_prelut = nullptr;              // its device copy
   struct StemMap { CUtensorMap tm; int ok; };
-  std::map<std::pair<const float*, int>, StemMap> stem_maps;   // TMA maps over caller inputs
+  std::map<std::tuple<const float*, int, int>, StemMap> stem_maps;   // TMA maps over caller inputs, by (pointer, batch, S)
   bool committed = false;
 
   // workspace
@@ -367,7 +367,7 @@ int ensure_workspace(ynb_engine* e, int batch) {
   int nb = std::max(batch, std::max(e->ws_batch, (int)e->cfg.max_batch));
   CUDA_TRY(e, cudaDeviceSynchronize());
   e->plans.clear();
-  e->tc_store.clear(); e->dw_maps.clear();
+  e->tc_store.clear(); e->dw_maps.clear(); e->stem_maps.clear();
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
   e->graphs.clear();
   e->graph_seen.clear();
@@ -587,9 +587,9 @@ int build_plan(ynb_engine* e, int B, Plan** out) {
     double px = (double)B * S * S;
     plan->net.push_back({"backbone.conv1.0+maxpool", "stem_pool", 4.0 * (3 * px + 24 * px / 16) + 4.0 * 27 * 24,
                          2.0 * 27 * 24 * px / 4, [=](cudaStream_t st) {
-      // the input pointer is the caller's: one tensor map per (pointer, batch), built on first sight
+      // the input pointer is the caller's: one tensor map per (pointer, batch, S), built on first sight
       const float* xin = e->d_x_bound;
-      auto key = std::make_pair(xin, B);
+      auto key = std::make_tuple(xin, B, S);   // the map encodes dims / strides from S
       auto it = e->stem_maps.find(key);
       if (it == e->stem_maps.end()) {
         ynb_engine::StemMap sm{};
@@ -941,6 +941,7 @@ YNB_EXPORT int ynb_set_grid(ynb_engine* e, int32_t input_size) {
   if (!e) return YNB_ERR_INVALID;
   if (input_size < 32 || input_size % 32 || input_size > 1024)
     return fail(e, YNB_ERR_INVALID, "input_size must be a multiple of 32 in [32, 1024]");
+  if (input_size != e->S) e->stem_maps.clear();
   e->S = input_size;   // workspace / plans are rebuilt lazily on the next forward
   return YNB_OK;
 }
@@ -1718,7 +1719,7 @@ YNB_EXPORT int ynb_forward_train_loss(ynb_engine* e, const float* x_dev, int32_t
                                       int64_t ws_bytes, void* stream) {
   if (!e || !x_dev || !target || !losses || !grad_s || !grad_m || !grad_l || !ws)
     return fail(e, YNB_ERR_INVALID, "null argument");
-  if (ws_bytes < ynb_train_loss_workspace_bytes(batch, e->cfg.input_size))
+  if (ws_bytes < ynb_train_loss_workspace_bytes(batch, e->S))
     return fail(e, YNB_ERR_INVALID, "ynb_forward_train_loss: workspace too small");
   cudaStream_t user = (cudaStream_t)stream;
   CounterScope cs(e);
@@ -1726,7 +1727,7 @@ YNB_EXPORT int ynb_forward_train_loss(ynb_engine* e, const float* x_dev, int32_t
   int rc = prepare(e, batch, &plan);
   if (rc || (rc = enter(e, user)) || (rc = run_network(e, x_dev, plan))) return rc;
   TrainLossParams p{};
-  level_geometry(e->cfg.input_size, p.grid, p.stride);
+  level_geometry(e->S, p.grid, p.stride);   // the CURRENT grid (ynb_set_grid), not the creation-time one
   float* grads[3] = {grad_s, grad_m, grad_l};
   int off = 0;
   for (int l = 0; l < 3; ++l) {
@@ -1741,7 +1742,7 @@ YNB_EXPORT int ynb_forward_train_loss(ynb_engine* e, const float* x_dev, int32_t
   }
   p.cells_total = off;
   p.target = target; p.partials = (double*)ws; p.ld = e->raw[0].ld; p.B = batch; p.A = e->cfg.num_anchors;
-  p.C = e->cfg.num_classes; p.S = e->cfg.input_size;
+  p.C = e->cfg.num_classes; p.S = e->S;
   if (p.ld != ynb_raw_ld(e)) return fail(e, YNB_ERR_STATE, "ynb_forward_train_loss: head map stride changed");
   CUDA_TRY(e, launch_train_loss(p, losses, e->s_main));
   if ((rc = leave(e, user))) return rc;

@@ -193,10 +193,20 @@ class Engine:
                 torch.empty((batch, n), dtype=torch.int32, **kw),
                 torch.empty((batch,), dtype=torch.int32, **kw))
 
+    def _check_host_shape(self, t: torch.Tensor, channels_last: bool, what: str):
+        """The C side copies 3*S*S*batch elements using the engine's CURRENT grid size: a buffer built for
+        another size (e.g. before a set_grid) must be an error, not an out-of-bounds read."""
+        s = self.input_size
+        want = (s, s, 3) if channels_last else (3, s, s)
+        if tuple(t.shape[1:]) != want:
+            raise EngineError(f"{what}: buffer is {tuple(t.shape)} but the grid is set for {s}x{s} "
+                              f"(expected [B,{want[0]},{want[1]},{want[2]}]); call set_grid first")
+
     def detect_host(self, x_host: torch.Tensor, out_host=None):
         """Host buffers in, host buffers out; copies happen inside the call."""
         if x_host.is_cuda or x_host.dtype != torch.float32 or x_host.dim() != 4:
             raise EngineError("detect_host wants a float32 host tensor [B,3,S,S]")
+        self._check_host_shape(x_host, False, "detect_host")
         x_host = x_host.contiguous()
         b = x_host.shape[0]
         if out_host is None:
@@ -212,6 +222,7 @@ class Engine:
         `x_host` and `out_host` (pinned) must stay alive until wait_host(slot)."""
         if x_host.is_cuda or x_host.dtype != torch.float32 or x_host.dim() != 4 or not x_host.is_contiguous():
             raise EngineError("submit_host wants a contiguous float32 host tensor [B,3,S,S]")
+        self._check_host_shape(x_host, False, "submit_host")
         boxes, scores, cls, counts = out_host
         self._check(self.lib.ynb_submit_host(self._h, int(slot), _ptr(x_host), x_host.shape[0], _ptr(boxes),
                                              _ptr(scores), _ptr(cls), _ptr(counts), _stream_ptr(self.device)),
@@ -224,6 +235,7 @@ class Engine:
         if img_host.is_cuda or img_host.dtype != torch.uint8 or img_host.dim() != 4 or img_host.shape[-1] != 3 \
                 or not img_host.is_contiguous():
             raise EngineError("submit_host_u8 wants a contiguous uint8 host tensor [B,S,S,3]")
+        self._check_host_shape(img_host, True, "submit_host_u8")
         if rects_host is not None and (rects_host.dtype != torch.int32 or tuple(rects_host.shape) != (img_host.shape[0], 4)
                                        or not rects_host.is_contiguous() or rects_host.is_cuda):
             raise EngineError("rects_host must be a contiguous int32 host tensor [B,4]")
@@ -237,6 +249,10 @@ class Engine:
         """uint8 [B,S,S,3] BGR device tensor -> the float32 [B,3,S,S] RGB tensor of ValTransforms."""
         if not img.is_cuda or img.dtype != torch.uint8 or img.dim() != 4 or not img.is_contiguous():
             raise EngineError("preprocess_u8 wants a contiguous uint8 CUDA tensor [B,S,S,3]")
+        self._check_host_shape(img, True, "preprocess_u8")
+        if rects is not None and (not rects.is_cuda or rects.dtype != torch.int32 or not rects.is_contiguous()
+                                  or tuple(rects.shape) != (img.shape[0], 4)):
+            raise EngineError("rects must be a contiguous int32 CUDA tensor [B,4]")
         b, s = img.shape[0], img.shape[1]
         x = torch.empty((b, 3, s, s), dtype=torch.float32, device=img.device)
         self._check(self.lib.ynb_preprocess_u8(self._h, _ptr(img), _ptr(rects) if rects is not None else None, b,
