@@ -224,6 +224,22 @@ int  ynb_pwconv_tc(const float* in_dev, int32_t in_ld, int32_t in_off,
                    int64_t pixels, int32_t cin, int32_t cout, int32_t act,
                    int32_t mode, void* stream);
 
+/* Fused unit tail: depthwise 3x3 (stride 1, pad 1) + bias (+ dw_act) kept in shared memory as the A operand of
+ * the pointwise 1x1 conv on tcgen05, + bias + act; one launch (yolo_nano_b200/csrc/unit_tc.cuh).  Replaces
+ * branch2[3..7] of a stride-1 ShuffleV2Block (backbone/shufflenetv2.py:57-63) and, with pass_dev != NULL, the
+ * torch.cat + channel_shuffle that follow it (:70-76, 14-28):
+ *     out[m, 2i] = pass[m, i],  out[m, 2i+1] = act(pw(dw(in)))[m, i]          (out_ld >= 2*cout)
+ * and a (depthwise Conv, pointwise Conv) pair of a detection head (models/yolo_nano.py:50-58) with
+ * pass_dev == NULL: out[m, i] = act(pw(dw_act(dw(in))))[m, i].
+ * in_dev: NHWC view [batch][h][w][channels of in_ld], 16-byte aligned, channels % 4 == 0; dw_w_dev [9][channels]
+ * tap-major, dw_b_dev [channels]; pw_w_dev [cout][channels], pw_b_dev [cout]; cout <= 128; out_dev / pass_dev
+ * 16-byte aligned with out_ld, pass_ld multiples of 4 floats.
+ * mode = YNB_GEMM_TC_3XTF32 | YNB_GEMM_TC_TF32.  Synchronous test hook (packs the weights on the host). */
+int  ynb_dwpw_tc(const float* in_dev, int32_t in_ld, const float* dw_w_dev, const float* dw_b_dev, int32_t dw_act,
+                 const float* pw_w_dev, const float* pw_b_dev, int32_t act,
+                 float* out_dev, int32_t out_ld, const float* pass_dev, int32_t pass_ld,
+                 int32_t batch, int32_t h, int32_t w, int32_t channels, int32_t cout, int32_t mode, void* stream);
+
 /* Stem: Conv2d(3,24,3,2,1)+BN+ReLU then MaxPool2d(3,2,1), fused
  * (backbone/shufflenetv2.py:109-116,158-159).  x_dev NCHW [B,3,S,S];
  * out_dev NHWC [B,S/4,S/4,24]; w_dev [27][24] ((ci,ky,kx)-major), b_dev [24]. */

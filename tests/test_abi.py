@@ -99,3 +99,20 @@ def test_reference_api_surface():
     with pytest.raises(SystemExit):
         with contextlib.redirect_stdout(io.StringIO()):
             pkg.YOLONano(torch.device("cpu"), 416, 80, anchor_size=pkg.MULTI_ANCHOR_SIZE_COCO, backbone="0.5x")
+
+
+def test_create_grid_values_match_reference_layout():
+    """create_grid (models/yolo_nano.py:86-112): values, not only shapes — grid_xy = (col, row) row-major per
+    level, strides and anchors repeated per cell — against the oracle's restatement."""
+    import contextlib
+    import io
+    import yolo_nano_b200 as pkg
+    from oracle import yolo_nano_oracle as O
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = pkg.YOLONano(torch.device("cpu"), 320, 20, anchor_size=pkg.MULTI_ANCHOR_SIZE)
+    want = O.grid_tensors(320, pkg.MULTI_ANCHOR_SIZE)
+    for got, w_ in zip(m.create_grid(320), want):
+        assert got.shape == w_.shape and torch.equal(got.cpu(), w_)
+    m.set_grid(416)
+    for got, w_ in zip((m.grid_cell, m.stride_tensor, m.all_anchors_wh), O.grid_tensors(416, pkg.MULTI_ANCHOR_SIZE)):
+        assert torch.equal(got.cpu(), w_)

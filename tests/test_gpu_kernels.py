@@ -111,6 +111,61 @@ def test_pwconv_strided_views(lib, G):
         assert float(out[:, 0::2].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("mode,tol", [(1, 3e-5), (2, 2e-2)])
+@pytest.mark.parametrize("batch,h,w,c,cout,dw_act,with_pass", [
+    (2, 52, 52, 60, 58, 0, True),      # stage-2 stride-1 unit tail (58 channels stored with ld 60)
+    (3, 26, 26, 116, 116, 0, True),    # stage 3: streamed weight chunks
+    (2, 13, 13, 116, 116, 0, True),    # one partial tile per image
+    (1, 40, 40, 60, 58, 0, True),      # 320^2 input
+    (2, 52, 52, 96, 96, 2, False),     # detection-head pair (LeakyReLU after the depthwise conv too)
+    (5, 19, 19, 96, 96, 2, False),     # 608^2 level 5
+    (1, 7, 9, 32, 16, 1, False),       # tiny non-square map, ReLU in between
+])
+def test_fused_dw_pw_unit_tail(lib, G, batch, h, w, c, cout, dw_act, with_pass, mode, tol):
+    """dwpw_tc_kernel = depthwise 3x3 + bias (+act) -> pointwise + bias + act (+ cat/channel_shuffle with the
+    pass-through half) in one launch, against torch (backbone/shufflenetv2.py:57-63,70-76; models/yolo_nano.py:50-58)."""
+    g = torch.Generator().manual_seed(h * 131 + c)
+    creal = min(c, 58) if c == 60 else c                      # physical pads (58 -> 60) carry zeros
+    x = torch.zeros(batch, h, w, c)
+    x[..., :creal] = torch.randn(batch, h, w, creal, generator=g)
+    dw_w = torch.zeros(c, 3, 3)
+    dw_w[:creal] = torch.randn(creal, 3, 3, generator=g) / 3
+    dw_b = torch.zeros(c)
+    dw_b[:creal] = torch.randn(creal, generator=g) * 0.2
+    pw_w = torch.zeros(cout, c)
+    pw_w[:, :creal] = torch.randn(cout, creal, generator=g) / creal ** 0.5
+    pw_b = torch.randn(cout, generator=g) * 0.3
+    act = 2 if dw_act == 2 else 1
+    f = {0: lambda t: t, 1: torch.relu, 2: lambda t: F.leaky_relu(t, 0.1)}
+    xn = x.permute(0, 3, 1, 2).double()
+    mid = f[dw_act](F.conv2d(xn, dw_w.double().unsqueeze(1), dw_b.double(), 1, 1, groups=c))
+    ref = f[act](F.conv2d(mid, pw_w.double()[:, :, None, None], pw_b.double())).permute(0, 2, 3, 1)
+    xd = x.to(G.DEV)
+    dwp = dw_w.reshape(c, 9).t().contiguous().to(G.DEV)      # [9][C] tap-major
+    dbd, pwd, pbd = dw_b.to(G.DEV), pw_w.contiguous().to(G.DEV), pw_b.to(G.DEV)
+    if with_pass:
+        ld = 2 * cout + 4
+        pld = (cout + 3) // 4 * 4 + 4                                          # pass rows are read 16 bytes at a time
+        x1 = torch.randn(batch, h, w, pld, generator=g).to(G.DEV)
+        out = torch.full((batch, h, w, ld), float("nan"), device=G.DEV)
+        rc = lib.ynb_dwpw_tc(G.ptr(xd), c, G.ptr(dwp), G.ptr(dbd), dw_act, G.ptr(pwd), G.ptr(pbd), act, G.ptr(out), ld,
+                             G.ptr(x1), pld, batch, h, w, c, cout, mode, G.stream())
+        assert rc == 0, lib.ynb_last_error(None)
+        torch.cuda.synchronize()
+        assert torch.equal(out[..., 0:2 * cout:2], x1[..., :cout])           # pass-through half, bit for bit
+        torch.testing.assert_close(out[..., 1:2 * cout:2].double().cpu(), ref, rtol=tol, atol=tol)
+        assert bool(torch.isnan(out[..., 2 * cout:]).all())                  # nothing written past the unit's channels
+    else:
+        ld = (cout + 3) // 4 * 4 + 4
+        out = torch.full((batch, h, w, ld), float("nan"), device=G.DEV)
+        rc = lib.ynb_dwpw_tc(G.ptr(xd), c, G.ptr(dwp), G.ptr(dbd), dw_act, G.ptr(pwd), G.ptr(pbd), act, G.ptr(out), ld,
+                             None, 0, batch, h, w, c, cout, mode, G.stream())
+        assert rc == 0, lib.ynb_last_error(None)
+        torch.cuda.synchronize()
+        torch.testing.assert_close(out[..., :cout].double().cpu(), ref, rtol=tol, atol=tol)
+        assert bool(torch.isnan(out[..., cout:]).all())
+
+
 @pytest.mark.parametrize("batch,size", [(1, 64), (2, 128), (1, 320), (2, 416)])
 def test_stem_pool(lib, G, batch, size):
     g = torch.Generator().manual_seed(size)

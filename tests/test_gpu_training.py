@@ -361,3 +361,30 @@ def test_conv3x3_backward_weight(G, TR, b, hw, k, n):
     got = dw.cpu().view(3, 3, n, k).permute(2, 3, 0, 1)
     torch.testing.assert_close(got, w.grad, rtol=1e-4, atol=2e-5 * float(w.grad.abs().max()))
     torch.testing.assert_close(db.cpu(), bias.grad, rtol=1e-4, atol=2e-5 * float(bias.grad.abs().max()))
+
+
+@pytest.mark.parametrize("first_size", [96, 192])
+def test_training_branch_follows_set_grid(G, g7, first_size):
+    """Multi-scale training calls model.set_grid(s) between steps (train.py:205,264): the loss kernel must take its
+    level geometry from the CURRENT grid, not from the size the engine was created with (advisor finding) —
+    created smaller and larger than the fixture's size, then set_grid, then the fixture's losses / gradients."""
+    import contextlib, io
+    import yolo_nano_b200 as pkg
+    size, classes, seed = int(g7["size"]), int(g7["classes"]), int(g7["seed"])
+    sd = W.calibrated(classes, seed=seed)
+    x = W.synthetic_input(2, size, seed=seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = pkg.YOLONano(G.DEV, first_size, classes, anchor_size=W.anchors_for(classes))
+    m.load_state_dict(sd)
+    m = m.to(G.DEV).eval()
+    m(W.synthetic_input(1, first_size, 1).to(G.DEV))            # engine + workspace exist at the first size
+    m.set_grid(size)
+    m.trainable = True
+    ls = m(x.to(G.DEV), target=torch.from_numpy(g7["target"]).to(G.DEV))
+    np.testing.assert_allclose(np.array([float(v) for v in ls], dtype=np.float32), g7["losses"], rtol=2e-3)
+    ch = 3 * (1 + classes + 4)
+    for k, g in zip(("pred_s", "pred_m", "pred_l"), m.head_gradients):
+        want = g7["grad_" + k]
+        b, _, h, w = want.shape
+        gg = g.cpu()[:, :, :ch].reshape(b, h, w, ch).permute(0, 3, 1, 2).numpy()
+        assert np.abs(gg - want).max() <= 3e-3 * np.abs(want).max(), k

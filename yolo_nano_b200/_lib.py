@@ -72,6 +72,8 @@ SIGNATURES = {
                              _i64, _i32, _i32, _i32, _p]),
     "ynb_pwconv_tc": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _p, _p,
                                 _i64, _i32, _i32, _i32, _i32, _p]),
+    "ynb_dwpw_tc": (C.c_int, [_p, _i32, _p, _p, _i32, _p, _p, _i32, _p, _i32, _p, _i32,
+                              _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "ynb_stem_pool": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _p]),
     "ynb_decode_level": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _i32, _i32,
                                    C.POINTER(_f), _i32, _i32, _i64, _i64, _p]),

@@ -22,6 +22,7 @@
 #include "nms_grid.cuh"
 #include "gemm_ffma.cuh"
 #include "gemm_tc.cuh"
+#include "unit_tc.cuh"
 #include "kernels_basic.cuh"
 #include "train_ops.cuh"
 #include "wgrad_tc.cuh"
@@ -141,6 +142,7 @@ struct ynb_engine {
 
   std::map<int, std::unique_ptr<Plan>> plans;
   std::deque<std::deque<TcGemmLaunch>> tc_store;
+  std::deque<std::deque<DwPwLaunch>> dp_store;   // fused depthwise -> pointwise launches
   std::deque<CUtensorMap> dw_maps;         // input maps of the depthwise launches (stable addresses)
 
   // execution resources: all engine work runs on the engine's own streams, ordered against
@@ -329,6 +331,7 @@ size_t layout_workspace(ynb_engine* e, int batch, int S, char* base) {
   for (int l = 0; l < 3; ++l) {
     tensor("head" + std::to_string(l) + ".a", 96, 96, hs[l]);
     tensor("head" + std::to_string(l) + ".b", 96, 96, hs[l]);
+    tensor("head" + std::to_string(l) + ".c", 96, 96, hs[l]);
     e->raw[l] = tensor(pn[l], ch, round_up(ch, 4), hs[l]);
   }
   // aliases used as taps
@@ -367,7 +370,7 @@ int ensure_workspace(ynb_engine* e, int batch) {
   int nb = std::max(batch, std::max(e->ws_batch, (int)e->cfg.max_batch));
   CUDA_TRY(e, cudaDeviceSynchronize());
   e->plans.clear();
-  e->tc_store.clear(); e->dw_maps.clear(); e->stem_maps.clear();
+  e->tc_store.clear(); e->dp_store.clear(); e->dw_maps.clear(); e->stem_maps.clear();
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
   e->graphs.clear();
   e->graph_seen.clear();
@@ -389,6 +392,7 @@ struct Planner {
   int B;
   Plan* plan;
   std::deque<TcGemmLaunch>* tc;
+  std::deque<DwPwLaunch>* dp;
   std::string error;
   std::vector<Op>* dst = nullptr;   // op list under construction (defaults to plan->net)
   std::vector<Op>& ops() { return dst ? *dst : plan->net; }
@@ -500,6 +504,40 @@ struct Planner {
     ops().push_back(op);
   }
 
+  // Fused depthwise 3x3 (stride 1) -> pointwise conv in ONE launch (unit_tc.cuh); `pass` as in pw().
+  // Returns false when the pair has to stay unfused (FFMA cross-check mode, shape does not fit, switched off).
+  bool dwpw(const std::string& dw_name, const std::string& pw_name, const Tensor& in, const Tensor& out,
+            const Tensor* pass) {
+    static const bool off = getenv("YNB_NO_FUSED_DWPW") != nullptr;
+    if (off || e->cfg.gemm_mode == YNB_GEMM_FP32_FFMA) return false;
+    const PackedConv& dc = conv(dw_name);
+    const PackedConv& pc = conv(pw_name);
+    const ConvSpec& ds = spec(dw_name);
+    const ConvSpec& ps = spec(pw_name);
+    if (ds.stride != 1 || dc.n != pc.ktot) return false;
+    dp->emplace_back();
+    DwPwLaunch& L = dp->back();
+    DwPwParams& p = L.p;
+    memset(&p, 0, sizeof(p));
+    p.dw_w = dc.w_dev; p.dw_b = dc.b_dev; p.dw_act = ds.act;
+    p.out = out.p; p.out_ld = out.ld; p.out_off = 0; p.omap = out.map;
+    p.bias = pc.b_dev; p.act = ps.act;
+    p.pass = pass ? pass->p : nullptr; p.pass_ld = pass ? pass->ld : 0;
+    p.err_flag = e->d_err;
+    if (!plan_dwpw(L, in.p, in.ld, B, in.H, in.W, ds.cin, dc.n, &pc.tc, e->cfg.gemm_mode)) {
+      dp->pop_back();
+      return false;
+    }
+    const double M = (double)B * in.H * in.W;
+    const double bytes = 4.0 * M * (ds.cin + ps.cout * (pass ? 3.0 : 1.0)) + 4.0 * ps.cin * ps.cout + 4.0 * ps.cout +
+                         40.0 * ds.cin;
+    const double flops = 2.0 * M * ps.cin * ps.cout + 18.0 * M * ds.cin;
+    const DwPwLaunch* Lp = &L;
+    ops().push_back({dw_name + "+pw", "dwpw_tcgen05", bytes, flops,
+                     [=](cudaStream_t st) { return launch_dwpw_tc(*Lp, st); }});
+    return true;
+  }
+
   // dense 3x3 (smooth): out = act(conv3x3(a + resample(a2)))
   void conv3(const std::string& name, const Tensor& a, const Tensor* a2, int a2_mode, const Tensor& sum,
              const Tensor& sum_lo, const Tensor& out) {
@@ -577,7 +615,8 @@ int build_plan(ynb_engine* e, int B, Plan** out) {
   auto plan = std::make_unique<Plan>();
   plan->batch = B;
   e->tc_store.emplace_back();
-  Planner P{e, B, plan.get(), &e->tc_store.back(), ""};
+  e->dp_store.emplace_back();
+  Planner P{e, B, plan.get(), &e->tc_store.back(), &e->dp_store.back(), ""};
   const int S = e->S;
 
   // stem + pool
@@ -627,9 +666,11 @@ int build_plan(ynb_engine* e, int B, Plan** out) {
         plan->net.back().mark = true;            // fork point: x is complete here
         P.passthrough(u, x, o, h);               // o[slot(2i)] = x[i]
       }
-      P.dw(u + ".branch2.3", mid1, 0, mid2);
-      // tensor-core path: the epilogue writes whole interleaved rows (x1 | branch2)
-      P.pw(u + ".branch2.5", mid2, 0, o, 1, 2, false, &x);
+      // tensor-core path: depthwise + pointwise fused, the epilogue writes whole interleaved rows (x1 | branch2)
+      if (!P.dwpw(u + ".branch2.3", u + ".branch2.5", mid1, o, &x)) {
+        P.dw(u + ".branch2.3", mid1, 0, mid2);
+        P.pw(u + ".branch2.5", mid2, 0, o, 1, 2, false, &x);
+      }
       x = o;
     }
   }
@@ -650,10 +691,15 @@ int build_plan(ynb_engine* e, int B, Plan** out) {
   for (int l = 0; l < 3; ++l) {
     std::string hd = "head_det_" + std::to_string(l + 1);
     Tensor ta = P.T("head" + std::to_string(l) + ".a"), tb = P.T("head" + std::to_string(l) + ".b");
-    P.dw(hd + ".0.convs.0", feats[l], 0, ta);
-    P.pw(hd + ".1.convs.0", ta, 0, tb, 0, 1);
-    P.dw(hd + ".2.convs.0", tb, 0, ta);
-    P.pw(hd + ".3.convs.0", ta, 0, tb, 0, 1);
+    if (!P.dwpw(hd + ".0.convs.0", hd + ".1.convs.0", feats[l], ta, nullptr)) {
+      P.dw(hd + ".0.convs.0", feats[l], 0, tb);
+      P.pw(hd + ".1.convs.0", tb, 0, ta, 0, 1);
+    }
+    if (!P.dwpw(hd + ".2.convs.0", hd + ".3.convs.0", ta, tb, nullptr)) {
+      Tensor tc2 = P.T("head" + std::to_string(l) + ".c");
+      P.dw(hd + ".2.convs.0", ta, 0, tc2);
+      P.pw(hd + ".3.convs.0", tc2, 0, tb, 0, 1);
+    }
     head_in[l] = tb;
   }
   P.dst = &plan->raw_tail;
@@ -957,7 +1003,7 @@ YNB_EXPORT int ynb_set_gemm_mode(ynb_engine* e, int32_t mode) {
   if (mode < 0 || mode > YNB_GEMM_TC_TF32) return fail(e, YNB_ERR_INVALID, "bad gemm_mode");
   if (mode != e->cfg.gemm_mode) {
     cudaDeviceSynchronize();
-    e->cfg.gemm_mode = mode; e->plans.clear(); e->tc_store.clear(); e->dw_maps.clear(); drop_graphs(e);
+    e->cfg.gemm_mode = mode; e->plans.clear(); e->tc_store.clear(); e->dp_store.clear(); e->dw_maps.clear(); drop_graphs(e);
   }
   return YNB_OK;
 }
@@ -1012,7 +1058,7 @@ YNB_EXPORT int ynb_commit_weights(ynb_engine* e) {
     if (!e->convs[i].loaded) return fail(e, YNB_ERR_STATE, "conv not loaded: " + e->table[i].name);
   CUDA_TRY(e, cudaDeviceSynchronize());   // nothing in flight may still read the old buffers
   e->plans.clear();
-  e->tc_store.clear(); e->dw_maps.clear();
+  e->tc_store.clear(); e->dp_store.clear(); e->dw_maps.clear();
   drop_graphs(e);
   for (size_t i = 0; i < e->convs.size(); ++i) {
     int rc = pack_conv(e, (int)i);
@@ -1422,6 +1468,54 @@ YNB_EXPORT int ynb_pwconv_tc(const float* in, int32_t in_ld, int32_t in_off, flo
     }
   }
   if (d_trace) cudaFree(d_trace);
+  cudaFree(t.hi); cudaFree(t.lo); cudaFree(d_err);
+  return rc;
+}
+
+YNB_EXPORT int ynb_dwpw_tc(const float* in, int32_t in_ld, const float* dw_w, const float* dw_b, int32_t dw_act,
+                           const float* pw_w, const float* pw_b, int32_t act, float* out, int32_t out_ld,
+                           const float* pass, int32_t pass_ld, int32_t batch, int32_t h, int32_t w_, int32_t channels,
+                           int32_t cout, int32_t mode, void* stream) {
+  if (!in || !dw_w || !dw_b || !pw_w || !pw_b || !out || channels % 4 || in_ld % 4 || out_ld % 4 || cout > 128 ||
+      cout < 1 || batch < 1 || h < 1 || w_ < 1 || (mode != YNB_GEMM_TC_3XTF32 && mode != YNB_GEMM_TC_TF32) ||
+      (pass && (out_ld < 2 * cout || pass_ld < cout || pass_ld % 4 || ((uintptr_t)pass & 15u))) || (!pass && out_ld < cout) ||
+      ((uintptr_t)out & 15u))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_dwpw_tc: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<float> wv((size_t)cout * channels);
+  UNIT_TRY(cudaMemcpy(wv.data(), pw_w, wv.size() * 4, cudaMemcpyDeviceToHost));
+  TcWeights t;
+  t.N = cout; t.Npad = round_up(cout, 16); t.Kpad = round_up(channels, kTcBK);
+  std::vector<float> hi((size_t)t.Npad * t.Kpad, 0.f), lo((size_t)t.Npad * t.Kpad, 0.f);
+  for (int n = 0; n < cout; ++n)
+    for (int k = 0; k < channels; ++k)
+      split_tf32_host(wv[(size_t)n * channels + k], &hi[(size_t)n * t.Kpad + k], &lo[(size_t)n * t.Kpad + k]);
+  int* d_err = nullptr;
+  UNIT_TRY(cudaMalloc(&t.hi, hi.size() * 4));
+  UNIT_TRY(cudaMalloc(&t.lo, lo.size() * 4));
+  UNIT_TRY(cudaMalloc(&d_err, 4));
+  UNIT_TRY(cudaMemset(d_err, 0, 4));
+  UNIT_TRY(cudaMemcpy(t.hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice));
+  UNIT_TRY(cudaMemcpy(t.lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice));
+  int rc = YNB_OK;
+  DwPwLaunch L;
+  DwPwParams& p = L.p;
+  memset(&p, 0, sizeof(p));
+  p.dw_w = dw_w; p.dw_b = dw_b; p.dw_act = dw_act;
+  p.out = out; p.out_ld = out_ld; p.out_off = 0; p.omap = dense_map();
+  p.bias = pw_b; p.act = act; p.pass = pass; p.pass_ld = pass ? pass_ld : 0; p.err_flag = d_err;
+  if (!make_tmap_2d(&t.tm_hi, t.hi, t.Kpad, t.Npad, t.Kpad, t.Npad) ||
+      !make_tmap_2d(&t.tm_lo, t.lo, t.Kpad, t.Npad, t.Kpad, t.Npad) ||
+      !plan_dwpw(L, in, in_ld, batch, h, w_, channels, channels, &t, mode)) {
+    rc = fail(nullptr, YNB_ERR_CUDA, "ynb_dwpw_tc: tensor map / smem planning failed");
+  } else {
+    cudaError_t r = launch_dwpw_tc(L, st);
+    if (r == cudaSuccess) r = cudaStreamSynchronize(st);
+    int flag = 0;
+    if (r == cudaSuccess) r = cudaMemcpy(&flag, d_err, 4, cudaMemcpyDeviceToHost);
+    if (r != cudaSuccess) rc = fail(nullptr, YNB_ERR_CUDA, std::string("ynb_dwpw_tc: ") + cudaGetErrorString(r));
+    else if (flag) rc = fail(nullptr, YNB_ERR_CUDA, "ynb_dwpw_tc: mbarrier timeout code " + std::to_string(flag));
+  }
   cudaFree(t.hi); cudaFree(t.lo); cudaFree(d_err);
   return rc;
 }
