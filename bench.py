@@ -10,8 +10,10 @@ every N = the configuration BASELINE.json's metric is quoted on ("416 bs256"): c
 (416x416, COCO-80, fp32 parity mode, incl. decode + NMS) at 256 images per GPU (`--batch 64` is
 configs[1]'s own batch; `--size 608 --batch 256` is configs[2]), tcgen05 3xTF32, reference random-init weights (torch.manual_seed), conf 0.001 / nms 0.5
 — with this init EVERY anchor passes the threshold, i.e. worst-case NMS.
-`value` times the device path with inputs resident in HBM; `e2e` times the C-ABI host call
-(pinned host input, H2D + D2H inside the timed region).
+`value` times the device path with inputs resident in HBM; `e2e` times the C-ABI host call on the reference's
+real input — uint8 images, data/transforms.py:445-458 — from pinned host memory (H2D + D2H inside the timed
+region); `e2e_f32` is the same through the float32 [B,3,S,S] entry.  `parity` checks two images of the timed batch
+against the CPU oracle in the same run.  `--strong` splits `--batch` over the ranks (BASELINE configs[2]).
 """
 from __future__ import annotations
 
@@ -34,7 +36,8 @@ SIZE, BATCH, CLASSES = 416, 256, 80
 
 
 def metric_name(a):
-    return (f"images/sec YOLO-Nano-1.0x {a.size} bs{a.batch} fp32-parity e2e (backbone+neck+head+decode+NMS)")
+    bs = getattr(a, "total_batch", a.batch)
+    return (f"images/sec YOLO-Nano-1.0x {a.size} bs{bs} fp32-parity e2e (backbone+neck+head+decode+NMS)")
 CONF, NMS_T = 0.001, 0.5
 
 
@@ -51,6 +54,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--dump-profile", default="")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: --batch is the TOTAL batch, split evenly over the ranks (configs[2])")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run oracle check of two images")
+    ap.add_argument("--no-latency", action="store_true", help="skip the batch-1 drop-in latency measurement")
     return ap.parse_args()
 
 
@@ -115,33 +122,83 @@ def cpu_baseline(sd, seconds: float, size: int):
 
 
 def traffic_file(a) -> Path:
-    """The committed ncu DRAM-traffic capture of this command at this workload (416^2 only)."""
-    name = {256: "r01_dram_traffic_b256.csv", 64: "r01_dram_traffic.csv"}.get(a.batch if a.size == 416 else -1, "none")
+    """The committed ncu DRAM-traffic capture of this command at this workload (416^2, 256 images only), reduced to
+    bytes per launch and kernel family by tools/ncu_traffic_by_kind.py (launches matched to the plan's ops in order)."""
+    name = "r02_dram_traffic_by_kind_b256.json" if (a.size == 416 and a.batch == 256 and a.mode == "3xtf32") else "none"
     return ROOT / "profiles" / name
 
 
-def load_traffic(kernel_substr: str, p: Path):
-    """DRAM bytes per launch (read + write) of a kernel family from the committed ncu capture
-    of this same command; None if there is no capture for this workload."""
-    import csv
+def load_traffic_by_kind(kind: str, p: Path):
     if not p.exists():
         return None
-    rows, hdr = [], None
-    for r in csv.reader(open(p)):
-        if len(r) > 5 and r[0] == "ID":
-            hdr = r
-        elif hdr and len(r) == len(hdr):
-            rows.append(dict(zip(hdr, r)))
-    per_launch = {}
-    for d in rows:
-        if kernel_substr not in d["Kernel Name"] or not d["Metric Name"].startswith("dram__bytes"):
-            continue
-        if kernel_substr == "tc_gemm_kernel" and ("80>" in d["Kernel Name"] or "20>" in d["Kernel Name"]):
-            continue        # the fused decode variants are their own family (pw_decode_tcgen05)
-        v = float(d["Metric Value"].replace(",", ""))
-        v *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(d["Metric Unit"], 1)
-        per_launch[d["ID"]] = per_launch.get(d["ID"], 0.0) + v
-    return sum(per_launch.values()) / len(per_launch) if per_launch else None
+    d = json.loads(p.read_text()).get("per_kind", {}).get(kind)
+    return None if d is None else d["dram_bytes_per_launch"]
+
+
+def parity_check(eng, sd, x_host, x_dev, size):
+    """Two images of the TIMED batch through the CPU oracle (the checker, never the path) in this same run:
+    raw head maps in units of the north_star tolerance (1e-3 + 1e-4 |ref|), decoded boxes in pixels, and the
+    keep-sets — exact against the oracle's NMS on the engine's own candidates, and against the oracle end to end
+    with the differing boxes counted (on reference-init weights they are exact score ties / 1-ulp order flips)."""
+    from oracle import weights as W
+    from oracle import yolo_nano_oracle as O
+    anchors = W.anchors_for(CLASSES)
+    ref_raw = O.network(sd, x_host)
+    raw = eng.forward_raw(x_dev)
+    worst, over, n = 0.0, 0, 0
+    for got, want in zip(raw, ref_raw):
+        err = np.abs(got.cpu().numpy() - want.numpy())
+        tol = 1e-3 + 1e-4 * np.abs(want.numpy())
+        worst = max(worst, float((err / tol).max())); over += int((err > tol).sum()); n += err.size
+    bb, cl = O.decode(ref_raw, size, CLASSES, anchors)
+    boxes, scores, cls = eng.forward_decode(x_dev)
+    ob, os_, oc, on = eng.forward_detect(x_dev)
+    res = {"images": int(x_host.shape[0]), "raw_worst_err_in_tol": round(worst, 4), "raw_over_tol": over, "raw_outputs": n,
+           "box_err_px": 0.0, "kept": [], "oracle_kept": [], "keepset_exact_on_own_candidates": True,
+           "keepset_differ_vs_oracle": 0}
+    for i in range(x_host.shape[0]):
+        bh, sh, ch = boxes[i].cpu().numpy(), scores[i].cpu().numpy(), cls[i].cpu().numpy().astype(np.int64)
+        res["box_err_px"] = max(res["box_err_px"], float(np.abs(bh - bb[i].numpy()).max()) * size)
+        _, _, _, idx = O.postprocess_flat(bh, sh, ch, CLASSES, CONF, NMS_T)
+        k = int(on[i])
+        same = k == len(idx) and np.array_equal(ob[i, :k].cpu().numpy(), bh[idx]) and \
+            np.array_equal(oc[i, :k].cpu().numpy().astype(np.int64), ch[idx])
+        res["keepset_exact_on_own_candidates"] = bool(res["keepset_exact_on_own_candidates"] and same)
+        _, _, _, ridx = O.postprocess(bb[i].numpy(), cl[i].numpy(), CLASSES, CONF, NMS_T)
+        res["kept"].append(k); res["oracle_kept"].append(int(len(ridx)))
+        res["keepset_differ_vs_oracle"] += int(len(np.setxor1d(idx, ridx)))
+    res["box_err_px"] = round(res["box_err_px"], 6)
+    res["ok"] = bool(over == 0 and res["keepset_exact_on_own_candidates"] and res["box_err_px"] < 1e-3
+                     and res["keepset_differ_vs_oracle"] <= 0.05 * sum(res["oracle_kept"]))
+    return res
+
+
+def latency_b1(sd, dev, size, mode):
+    """The reference's own timing method (benchmark.py:40-82): batch 1 through the drop-in class, one image at a
+    time, device input, host ndarray results (the call syncs like the reference's .to('cpu')), ms per image."""
+    import contextlib
+    import io
+    import yolo_nano_b200 as pkg
+    from oracle import weights as W
+    out = {}
+    for s in sorted({320, size}):
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = pkg.YOLONano(dev, input_size=s, num_classes=CLASSES, conf_thresh=CONF, nms_thresh=NMS_T,
+                             anchor_size=W.anchors_for(CLASSES), gemm_mode=mode)
+        m.load_state_dict(sd)
+        m = m.to(dev).eval()
+        xs = [W.synthetic_input(1, s, seed=20 + i).to(dev) for i in range(4)]
+        for i in range(8):
+            m(xs[i % 4])
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        n = 50
+        for i in range(n):
+            m(xs[i % 4])
+        out[str(s)] = round(1e3 * (time.perf_counter() - t0) / n, 4)
+        del m
+    return {"unit": "ms/image", "batch": 1, "call": "YOLONano.forward(x) -> (bboxes, scores, cls_inds) host ndarrays",
+            "by_input_size": out}
 
 
 def bind_to_gpu_numa_node(index: int):
@@ -210,10 +267,12 @@ def workload_config(a):
     return {"workload": f"BASELINE metric config (configs[1] at the metric's batch): YOLO-Nano-1.0x inference "
                         f"{a.size}x{a.size}, batch {a.batch} per GPU, COCO {CLASSES} classes, fp32 parity mode, "
                         "incl. decode+NMS",
-            "input_size": a.size, "batch_per_gpu": a.batch, "num_classes": CLASSES, "conf_thresh": CONF,
+            "input_size": a.size, "batch_per_gpu": a.batch, "total_batch_if_strong": getattr(a, "total_batch", a.batch)
+            if getattr(a, "strong", False) else None, "num_classes": CLASSES, "conf_thresh": CONF,
             "nms_thresh": NMS_T, "weights": "reference random init (torch.manual_seed(3))" if a.weights == "refinit"
             else "calibrated synthetic (oracle/weights.py seed 2)",
-            "gemm_mode": a.mode, "sharding": "batch-sharded, one process per GPU, no collective",
+            "gemm_mode": a.mode, "sharding": "batch-sharded, one process per GPU, no collective" +
+            (" (strong scaling: the total batch is split over the ranks)" if getattr(a, "strong", False) else ""),
             "l2": f"inputs {a.batch * 3 * a.size * a.size * 4 / 1e6:.0f} MB per step (> 126 MB L2), "
                   f"4 rotating input batches; intermediate activations ~{a.batch * 24 * (a.size / 416) ** 2 / 1e3:.1f} GB per step"}
 
@@ -223,6 +282,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    a.total_batch = a.batch
+    if a.strong:
+        if a.batch % max(world, a.gpus):
+            raise SystemExit(f"--strong: batch {a.batch} is not divisible by {max(world, a.gpus)} ranks")
+        a.batch //= max(world, a.gpus)
     if a.impl == "reference":
         run_reference(a, rank, world)
         return
@@ -367,11 +431,12 @@ def main():
     dk, dd = dom
     ach = dd["bytes"] / (dd["ms"] * 1e-3) / 1e9
     sass_name = {"pw_tcgen05": "tc_gemm_kernel", "conv3x3_tcgen05": "tc_gemm_kernel", "nms": "nms_segment_kernel",
+                 "dwpw_tcgen05": "dwpw_tc_kernel",
                  "dwconv3x3": "dwconv3x3_kernel", "stem_pool": "stem_pool_kernel", "decode": "decode_level_kernel"}.get(dk, dk)
     roofline = {"bound": "hbm", "kernel": dk, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": load_traffic(sass_name, traffic_file(a)),
-                "traffic_note": "avg DRAM read+write bytes per launch of " + sass_name +
-                f" (ncu, profiles/{traffic_file(a).name}); algorithmic bytes per launch = " +
+                "traffic": load_traffic_by_kind(dk, traffic_file(a)),
+                "traffic_note": "avg DRAM read+write bytes per launch of the `" + dk + "` launches (" + sass_name +
+                f"; ncu, profiles/{traffic_file(a).name}); algorithmic bytes per launch = " +
                 f"{dd['bytes'] / max(dd['launches'], 1e-9):.3e}", "peak_source": peak_src,
                 "launches_per_step": dd["launches"], "ms_per_step": dd["ms"],
                 "share_of_step": dd["ms"] / total_prof_ms,
@@ -390,21 +455,28 @@ def main():
     cpu = None
     if not a.no_cpu_baseline and a.gpus == 1:
         cpu = cpu_baseline(sd, a.cpu_seconds, a.size)
+    parity = None if a.no_parity else parity_check(eng, sd, host_x[0][:2], dev_x[0][:2].contiguous(), a.size)
+    latency = None if (a.no_latency or world > 1) else latency_b1(sd, dev, a.size, modes[a.mode])
 
     imgs = world * a.batch * a.steps
     line = {"metric": metric_name(a), "value": imgs / (ms_dev * 1e-3), "unit": "images/s", "n_gpus": world, "steps": a.steps,
-            "warmup": max(a.warmup, 3), "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(a.warmup, 3), "ms_per_step": ms_dev / a.steps, "higher_is_better": True,
+            "scaling": "strong" if a.strong else "weak",
             "vs_baseline": None, "dtype": "f32 (tcgen05 3xTF32 split, fp32 accumulate)" if a.mode == "3xtf32" else
             ("f32" if a.mode == "ffma" else "tf32"),
             "data": "synthetic", "config": workload_config(a),
-            "e2e": {"value": imgs / (wall_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": wall_e2e / a.steps,
-                    "call": "ynb_submit_host / ynb_wait_host, 2 slots (pinned host input, host outputs; "
-                            "step i's PCIe copy overlaps step i-1's compute)"},
-            "e2e_u8": {"value": imgs / (wall_u8 * 1e-3), "unit": "images/s",
-                       "h2d_bytes_per_step": a.batch * 3 * a.size * a.size, "ms_per_step": wall_u8 / a.steps,
-                       "call": "ynb_submit_host_u8 / ynb_wait_host: uint8 HWC BGR images, Normalize + ToTensor of "
-                               "data/transforms.py on the device (bit-identical tensor), then the same path"},
+            # the reference's real input is a uint8 image (data/transforms.py:445-458): that entry is the declared
+            # end-to-end number; the float32 [B,3,S,S] entry (4x the bytes over PCIe) is kept beside it
+            "e2e": {"value": imgs / (wall_u8 * 1e-3), "unit": "images/s",
+                    "h2d_bytes_per_step": a.batch * 3 * a.size * a.size, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": wall_u8 / a.steps,
+                    "call": "ynb_submit_host_u8 / ynb_wait_host, 2 slots: pinned uint8 HWC BGR images in, Normalize + "
+                            "ToTensor of data/transforms.py on the device (bit-identical tensor), pinned host detections "
+                            "out; step i's PCIe copy overlaps step i-1's compute"},
+            "e2e_f32": {"value": imgs / (wall_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": wall_e2e / a.steps,
+                        "call": "ynb_submit_host / ynb_wait_host: the same with float32 [B,3,S,S] host input"},
+            "parity": parity, "latency_b1": latency,
             "host_affinity": None if numa is None else {"first_cpu": numa[0], "cpus": numa[1]},
             "gpu_launches": launches, "clocks": sampler.summary() if sampler else None,
             "roofline": roofline, "cpu_baseline": cpu,

@@ -166,6 +166,8 @@ class YOLONano(nn.Module):
         object.__setattr__(self, "_engine", None)
         object.__setattr__(self, "_engine_key", None)
         object.__setattr__(self, "_weights_key", None)
+        object.__setattr__(self, "_wt_cache", None)
+        object.__setattr__(self, "_out_cache", None)
 
     # ---- reference API ---------------------------------------------------------------
     def init_bias(self):
@@ -227,8 +229,17 @@ class YOLONano(nn.Module):
                 out[spec.name] = (w, b)
         return out
 
+    def _weight_tensors(self):
+        """The 469 (154 after fuse_conv_bn) tensors the engine weights are derived from, cached per module
+        structure (fuse_conv_bn replaces modules: `_modules` ids change and the list is rebuilt)."""
+        key = tuple(id(m) for m in self.modules())
+        if self._wt_cache is None or self._wt_cache[0] != key:
+            object.__setattr__(self, "_wt_cache", (key, list(self.state_dict(keep_vars=True).values())))
+        return self._wt_cache[1]
+
     def _weights_fingerprint(self):
-        return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+        # (storage, in-place version) of every tensor: changes on load_state_dict / optimizer steps / .to()
+        return tuple((t.data_ptr(), t._version) for t in self._weight_tensors())
 
     def _device(self) -> torch.device:
         p = next(self.parameters())
@@ -267,7 +278,7 @@ class YOLONano(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ("_engine", "_engine_key", "_weights_key"):
+            if k in ("_engine", "_engine_key", "_weights_key", "_wt_cache", "_out_cache"):
                 object.__setattr__(new, k, None)
             else:
                 object.__setattr__(new, k, copy.deepcopy(v, memo))
@@ -278,17 +289,28 @@ class YOLONano(nn.Module):
     def detect(self, x: torch.Tensor) -> List[Tuple[np.ndarray, np.ndarray, np.ndarray]]:
         """Batched extension: one (bboxes [K,4] f32, scores [K] f32, cls_inds [K] i64)
         triple per image, each what the reference returns for that image alone."""
-        eng = self.engine(x.shape[0])
-        boxes, scores, cls, counts = eng.forward_detect(x)
-        counts_h = counts.cpu().numpy()
+        nb = int(x.shape[0])
+        eng = self.engine(nb)
+        # device outputs are reused between calls (same addresses -> the engine replays its CUDA graph)
+        oc_ = self._out_cache
+        if oc_ is None or oc_[0] is not eng or oc_[1] != (nb, eng.num_boxes):
+            oc_ = (eng, (nb, eng.num_boxes), eng.alloc_outputs(nb))
+            object.__setattr__(self, "_out_cache", oc_)
+        boxes, scores, cls, counts = eng.forward_detect(x, oc_[2])
+        counts_h = counts.cpu().numpy()                       # the one synchronising copy (the reference's .to('cpu'))
+        kmax = int(counts_h.max()) if nb else 0
+        # rows [0, max count) of every image: three copies per call, not three per image
+        bh = boxes[:, :kmax].cpu().numpy()
+        sh = scores[:, :kmax].cpu().numpy()
+        ch = cls[:, :kmax].cpu().numpy()
         res = []
-        for b in range(x.shape[0]):
+        for b in range(nb):
             k = int(counts_h[b])
             # owned, writable host arrays: callers rescale boxes in place
             # (evaluator/cocoapi_evaluator.py:85-87, test.py:133-135)
-            res.append((np.array(boxes[b, :k].cpu().numpy(), dtype=np.float32, copy=True),
-                        np.array(scores[b, :k].cpu().numpy(), dtype=np.float32, copy=True),
-                        cls[b, :k].cpu().numpy().astype(np.int64)))
+            res.append((np.array(bh[b, :k], dtype=np.float32, copy=True),
+                        np.array(sh[b, :k], dtype=np.float32, copy=True),
+                        ch[b, :k].astype(np.int64)))
         return res
 
     def detect_images(self, canvases, rects=None) -> List[Tuple[np.ndarray, np.ndarray, np.ndarray]]:
