@@ -349,6 +349,15 @@ int  ynb_dwconv3x3_bwd_weight(const float* dout_dev, int32_t dout_ld, int32_t do
                               int32_t batch, int32_t h_in, int32_t w_in, int32_t channels, int32_t stride,
                               void* workspace_dev, int64_t workspace_bytes, void* stream);
 
+/* ModelEMA.update (utils/misc.py:78-86): for every floating-point state tensor  v = v * d + (1 - d) * m  with the
+ * reference's two roundings (bit-identical), ALL tensors in one launch.  The caller passes device tables:
+ * ema_ptrs_dev / model_ptrs_dev [T] device addresses of the float32 tensors, sizes_dev [T] element counts, and a
+ * chunk map (chunk c covers elements [chunk_index[c] * E, +E) of tensor chunk_tensor[c], E = ynb_ema_chunk_elems()). */
+int32_t ynb_ema_chunk_elems(void);
+int  ynb_ema_update(const uint64_t* ema_ptrs_dev, const uint64_t* model_ptrs_dev, const int64_t* sizes_dev,
+                    const int32_t* chunk_tensor_dev, const int32_t* chunk_index_dev, int32_t num_chunks,
+                    float d, float one_minus_d, void* stream);
+
 /* Backward of the pointwise conv (ynb_pwconv) w.r.t. weights and bias:
  *   dw[n][k] = sum_m d_out[m, dout_off + n] * in[m, in_off + k];  db[n] = sum_m d_out[m, dout_off + n].
  * (The gradient w.r.t. the input is the forward GEMM with the transposed weight matrix and no bias:

@@ -373,6 +373,27 @@ def train_golden():
     print("g7 losses", out["losses"], "positives", int((target[:, :, 0] > 0).sum()), "ignored", int((target[:, :, 0] < 0).sum()))
 
 
+def ema_golden():
+    """g8: the REAL ModelEMA (utils/misc.py:67-86) over three updates of a model whose weights change between
+    updates the way an optimizer would change them (deterministic perturbations)."""
+    _import_reference()
+    from utils.misc import ModelEMA  # type: ignore
+    from oracle.train_oracle import ema_model, ema_perturb
+    seed = 8
+    m = ema_model(seed)
+    ema = ModelEMA(m, decay=0.9999, updates=1500)
+    out = {"seed": seed, "start_updates": 1500}
+    g = torch.Generator().manual_seed(seed + 1)
+    for step in range(3):
+        ema_perturb(m, g)
+        ema.update(m)
+        out[f"decay{step}"] = np.float64(ema.decay(ema.updates))
+    for k, v in ema.ema.state_dict().items():
+        out["ema." + k] = v.numpy()
+    np.savez_compressed(OUT / "g8_ema.npz", torch=torch.__version__, **out)
+    print("g8_ema.npz:", len(out), "entries, updates", ema.updates)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "evalfmt":
         evalfmt_golden()
@@ -380,6 +401,8 @@ if __name__ == "__main__":
         preprocess_golden()
     elif len(sys.argv) > 1 and sys.argv[1] == "tta":
         tta_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == "ema":
+        ema_golden()
     elif len(sys.argv) > 1 and sys.argv[1] == "train":
         train_golden()
     else:

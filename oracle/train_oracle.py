@@ -176,3 +176,46 @@ def sgd_step(p: torch.Tensor, g: torch.Tensor, buf, lr: float, momentum: float =
 
 
 _ = split_predictions  # re-exported for the tests
+
+
+# --------------------------------------------------------------------------------------
+# ModelEMA (utils/misc.py:67-86)
+# --------------------------------------------------------------------------------------
+def ema_decay(updates: int, decay: float = 0.9999) -> float:
+    """utils/misc.py:72: decay * (1 - exp(-x / 2000)), Python double."""
+    import math
+    return decay * (1 - math.exp(-updates / 2000.))
+
+
+@torch.no_grad()
+def ema_update(ema_sd: dict, model_sd: dict, d: float) -> None:
+    """ModelEMA.update body (utils/misc.py:82-86), in place on `ema_sd`: the same two in-place tensor ops per
+    floating-point entry; integer entries (num_batches_tracked) are left alone."""
+    for k, v in ema_sd.items():
+        if v.dtype.is_floating_point:
+            v *= d
+            v += (1. - d) * model_sd[k].detach()
+
+
+def ema_model(seed: int):
+    """Small conv + BatchNorm stack (parameters, running statistics, an integer counter) for the ModelEMA fixture g8 —
+    the class is model-agnostic (utils/misc.py:67-86); sizes chosen to cover vector tails and 4-byte-only alignment."""
+    torch.manual_seed(seed)
+    m = torch.nn.Sequential(torch.nn.Conv2d(3, 7, 3), torch.nn.BatchNorm2d(7), torch.nn.Conv2d(7, 129, 1),
+                            torch.nn.BatchNorm2d(129), torch.nn.Conv2d(129, 33, 3, bias=False))
+    with torch.no_grad():
+        for b in m.buffers():
+            if b.dtype.is_floating_point:
+                b.uniform_(0.5, 1.5)
+    return m
+
+
+@torch.no_grad()
+def ema_perturb(m, g: torch.Generator) -> None:
+    """What an optimizer step + a BatchNorm forward would do to the model between two EMA updates (deterministic)."""
+    for v in m.state_dict().values():
+        if v.dtype.is_floating_point:
+            v += (0.05 * torch.randn(v.shape, generator=g)).to(v.device)
+        else:
+            v += 1
+

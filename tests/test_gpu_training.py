@@ -388,3 +388,58 @@ def test_training_branch_follows_set_grid(G, g7, first_size):
         b, _, h, w = want.shape
         gg = g.cpu()[:, :, :ch].reshape(b, h, w, ch).permute(0, 3, 1, 2).numpy()
         assert np.abs(gg - want).max() <= 3e-3 * np.abs(want).max(), k
+
+
+def test_model_ema_one_launch_bit_exact(G, golden):
+    """yolo_nano_b200.ModelEMA (one multi-tensor kernel launch per update) against the REAL reference class over three
+    updates (fixture g8: parameters, BatchNorm statistics, vector tails, an integer counter) — bit-identical."""
+    from yolo_nano_b200.ema import ModelEMA
+    from oracle import train_oracle as T
+    g8 = golden("g8_ema.npz")
+    m = T.ema_model(int(g8["seed"])).to(G.DEV)
+    ema = ModelEMA(m, decay=0.9999, updates=int(g8["start_updates"]))
+    assert not ema.ema.training and all(not p.requires_grad for p in ema.ema.parameters())
+    g = torch.Generator().manual_seed(int(g8["seed"]) + 1)
+    for step in range(3):
+        T.ema_perturb(m, g)
+        ema.update(m)
+        assert ema.decay(ema.updates) == float(g8[f"decay{step}"])
+    for k, v in ema.ema.state_dict().items():
+        np.testing.assert_array_equal(v.cpu().numpy(), g8["ema." + k], err_msg=k)
+
+
+def test_model_ema_of_the_detector_feeds_its_engine(G):
+    """train.py:147,233-235 + eval of `ema.ema`: the EMA copy of the drop-in detector is a working detector whose engine
+    picks up the averaged weights (the kernel writes them behind autograd's version counters)."""
+    import contextlib, io
+    import yolo_nano_b200 as pkg
+    from yolo_nano_b200.ema import ModelEMA
+    sd = W.calibrated(20, seed=3)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = pkg.YOLONano(G.DEV, 128, 20, anchor_size=W.anchors_for(20))
+    m.load_state_dict(sd)
+    m = m.to(G.DEV).eval()
+    x = W.synthetic_input(1, 128, 3).to(G.DEV)
+    ema = ModelEMA(m, updates=100000)                       # decay ~ 0.9999
+    before = ema.ema(x)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.mul_(0.5)
+    for _ in range(3):
+        ema.update(m)
+    d = 1.0
+    for u in (100001, 100002, 100003):
+        d *= ema.decay(u)
+    want = {k: (v * (d + (1 - d) * 0.5) if v.dtype.is_floating_point and "running" not in k else v) for k, v in sd.items()}
+    for k, v in ema.ema.state_dict().items():
+        if v.dtype.is_floating_point:
+            torch.testing.assert_close(v.cpu(), want[k], rtol=1e-5, atol=1e-7, msg=k)
+    after = ema.ema(x)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = pkg.YOLONano(G.DEV, 128, 20, anchor_size=W.anchors_for(20))
+    ref.load_state_dict(ema.ema.state_dict())
+    ref = ref.to(G.DEV).eval()
+    want_out = ref(x)
+    for a, b in zip(after, want_out):
+        np.testing.assert_array_equal(a, b)
+    assert len(before[1]) > 0

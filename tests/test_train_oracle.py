@@ -40,3 +40,22 @@ def test_sgd_step_matches_torch_optim(g7):
     np.testing.assert_array_equal(p1.numpy(), g7["sgd_p1"])
     p2, _ = T.sgd_step(p1, g2, buf, 1e-3)
     np.testing.assert_array_equal(p2.numpy(), g7["sgd_p2"])
+
+
+def test_ema_update_matches_reference_class(golden):
+    """oracle ema_update / ema_decay against the REAL ModelEMA (utils/misc.py:67-86) over three updates (g8)."""
+    from copy import deepcopy
+    g8 = golden("g8_ema.npz")
+    m = T.ema_model(int(g8["seed"]))
+    ema_sd = deepcopy(m).eval().state_dict()
+    g = torch.Generator().manual_seed(int(g8["seed"]) + 1)
+    updates = int(g8["start_updates"])
+    for step in range(3):
+        T.ema_perturb(m, g)
+        updates += 1
+        d = T.ema_decay(updates)
+        assert d == float(g8[f"decay{step}"])
+        T.ema_update(ema_sd, m.state_dict(), d)
+    for k, v in ema_sd.items():
+        np.testing.assert_array_equal(v.numpy(), g8["ema." + k], err_msg=k)
+    assert int(ema_sd["1.num_batches_tracked"]) == 0            # integer state is not averaged

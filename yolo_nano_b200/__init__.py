@@ -10,6 +10,7 @@ from .fuse_conv_bn import fuse_conv_bn  # noqa: F401
 from .yolo_nano import YOLONano, Conv, ShuffleNetV2, ShuffleV2Block  # noqa: F401
 from .engine import Engine, EngineError  # noqa: F401
 from .tta import TestTimeAugmentation, resize_bilinear  # noqa: F401
+from .ema import ModelEMA  # noqa: F401
 from . import evalfmt  # noqa: F401
 
 # anchors of the reference (data/config.py:11-17): constructor inputs, data not code

@@ -1653,6 +1653,20 @@ YNB_EXPORT int ynb_sgd_step(float* params, const float* grads, float* momentum_b
   return YNB_OK;
 }
 
+YNB_EXPORT int32_t ynb_ema_chunk_elems(void) { return kEmaChunk; }
+
+YNB_EXPORT int ynb_ema_update(const uint64_t* ema_ptrs_dev, const uint64_t* model_ptrs_dev, const int64_t* sizes_dev,
+                              const int32_t* chunk_tensor_dev, const int32_t* chunk_index_dev, int32_t num_chunks,
+                              float d, float one_minus_d, void* stream) {
+  if (!ema_ptrs_dev || !model_ptrs_dev || !sizes_dev || !chunk_tensor_dev || !chunk_index_dev || num_chunks < 0)
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_ema_update: bad arguments");
+  UNIT_TRY(launch_ema_update(reinterpret_cast<const unsigned long long*>(ema_ptrs_dev),
+                             reinterpret_cast<const unsigned long long*>(model_ptrs_dev),
+                             reinterpret_cast<const long long*>(sizes_dev), chunk_tensor_dev, chunk_index_dev, num_chunks,
+                             d, one_minus_d, (cudaStream_t)stream));
+  return YNB_OK;
+}
+
 YNB_EXPORT int ynb_dwconv3x3_bwd_data(const float* dout, int32_t do_ld, int32_t do_off, float* din, int32_t di_ld,
                                       int32_t di_off, const float* w, int32_t batch, int32_t h_in, int32_t w_in,
                                       int32_t channels, int32_t stride, void* stream) {

@@ -241,6 +241,11 @@ class YOLONano(nn.Module):
         # (storage, in-place version) of every tensor: changes on load_state_dict / optimizer steps / .to()
         return tuple((t.data_ptr(), t._version) for t in self._weight_tensors())
 
+    def mark_weights_dirty(self):
+        """Force a re-pack of the engine weights on the next forward (for writers that bypass autograd's
+        version counters, e.g. the fused ModelEMA / SGD kernels)."""
+        object.__setattr__(self, "_weights_key", None)
+
     def _device(self) -> torch.device:
         p = next(self.parameters())
         return p.device
