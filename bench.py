@@ -37,7 +37,8 @@ SIZE, BATCH, CLASSES = 416, 256, 80
 
 def metric_name(a):
     bs = getattr(a, "total_batch", a.batch)
-    return (f"images/sec YOLO-Nano-1.0x {a.size} bs{bs} fp32-parity e2e (backbone+neck+head+decode+NMS)")
+    tag = "bf16" if getattr(a, "mode", "") == "bf16" else "fp32-parity"
+    return (f"images/sec YOLO-Nano-1.0x {a.size} bs{bs} {tag} e2e (backbone+neck+head+decode+NMS)")
 CONF, NMS_T = 0.001, 0.5
 
 
@@ -49,7 +50,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--size", type=int, default=SIZE)
-    ap.add_argument("--mode", default="3xtf32", choices=["ffma", "3xtf32", "tf32"])
+    ap.add_argument("--mode", default="3xtf32", choices=["ffma", "3xtf32", "tf32", "bf16"],
+                    help="3xtf32 = the fp32 parity mode (default, the headline); bf16 = BASELINE configs[3] throughput mode")
     ap.add_argument("--weights", default="refinit", choices=["refinit", "calibrated"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -135,7 +137,7 @@ def load_traffic_by_kind(kind: str, p: Path):
     return None if d is None else d["dram_bytes_per_launch"]
 
 
-def parity_check(eng, sd, x_host, x_dev, size):
+def parity_check(eng, sd, x_host, x_dev, size, mode="3xtf32"):
     """Two images of the TIMED batch through the CPU oracle (the checker, never the path) in this same run:
     raw head maps in units of the north_star tolerance (1e-3 + 1e-4 |ref|), decoded boxes in pixels, and the
     keep-sets — exact against the oracle's NMS on the engine's own candidates, and against the oracle end to end
@@ -145,9 +147,10 @@ def parity_check(eng, sd, x_host, x_dev, size):
     anchors = W.anchors_for(CLASSES)
     ref_raw = O.network(sd, x_host)
     raw = eng.forward_raw(x_dev)
-    worst, over, n = 0.0, 0, 0
+    worst, over, n, worst_abs = 0.0, 0, 0, 0.0
     for got, want in zip(raw, ref_raw):
         err = np.abs(got.cpu().numpy() - want.numpy())
+        worst_abs = max(worst_abs, float(err.max()))
         tol = 1e-3 + 1e-4 * np.abs(want.numpy())
         worst = max(worst, float((err / tol).max())); over += int((err > tol).sum()); n += err.size
     bb, cl = O.decode(ref_raw, size, CLASSES, anchors)
@@ -168,8 +171,14 @@ def parity_check(eng, sd, x_host, x_dev, size):
         res["kept"].append(k); res["oracle_kept"].append(int(len(ridx)))
         res["keepset_differ_vs_oracle"] += int(len(np.setxor1d(idx, ridx)))
     res["box_err_px"] = round(res["box_err_px"], 6)
-    res["ok"] = bool(over == 0 and res["keepset_exact_on_own_candidates"] and res["box_err_px"] < 1e-3
-                     and res["keepset_differ_vs_oracle"] <= 0.05 * sum(res["oracle_kept"]))
+    res["raw_worst_abs_err"] = round(worst_abs, 6)
+    if mode == "bf16":      # throughput mode: its own stated tolerance (tests/test_gpu_forward.py::test_bf16_mode_*)
+        res["tolerance"] = "bf16 mode: raw head maps within 2e-2 absolute on reference-init weights; NMS exact on its inputs"
+        res["ok"] = bool(worst_abs < 2e-2 and res["keepset_exact_on_own_candidates"])
+    else:
+        res["tolerance"] = "north_star: raw 1e-3 + 1e-4 |ref|, boxes 1e-3 px, keep-sets exact up to score ties (counted)"
+        res["ok"] = bool(over == 0 and res["keepset_exact_on_own_candidates"] and res["box_err_px"] < 1e-3
+                         and res["keepset_differ_vs_oracle"] <= 0.05 * sum(res["oracle_kept"]))
     return res
 
 
@@ -305,7 +314,8 @@ def main():
     numa = bind_to_gpu_numa_node(local)      # pinned host buffers are then allocated next to the GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    modes = {"ffma": _lib.GEMM_FP32_FFMA, "3xtf32": _lib.GEMM_TC_3XTF32, "tf32": _lib.GEMM_TC_TF32}
+    modes = {"ffma": _lib.GEMM_FP32_FFMA, "3xtf32": _lib.GEMM_TC_3XTF32, "tf32": _lib.GEMM_TC_TF32,
+             "bf16": _lib.GEMM_TC_BF16}
 
     sd = W.reference_init(CLASSES, seed=3) if a.weights == "refinit" else W.calibrated(CLASSES, seed=2)
     eng = Engine(dev, a.size, CLASSES, W.anchors_for(CLASSES), CONF, NMS_T, False, modes[a.mode], a.batch)
@@ -455,15 +465,16 @@ def main():
     cpu = None
     if not a.no_cpu_baseline and a.gpus == 1:
         cpu = cpu_baseline(sd, a.cpu_seconds, a.size)
-    parity = None if a.no_parity else parity_check(eng, sd, host_x[0][:2], dev_x[0][:2].contiguous(), a.size)
+    parity = None if a.no_parity else parity_check(eng, sd, host_x[0][:2], dev_x[0][:2].contiguous(), a.size, a.mode)
     latency = None if (a.no_latency or world > 1) else latency_b1(sd, dev, a.size, modes[a.mode])
 
     imgs = world * a.batch * a.steps
     line = {"metric": metric_name(a), "value": imgs / (ms_dev * 1e-3), "unit": "images/s", "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms_dev / a.steps, "higher_is_better": True,
             "scaling": "strong" if a.strong else "weak",
-            "vs_baseline": None, "dtype": "f32 (tcgen05 3xTF32 split, fp32 accumulate)" if a.mode == "3xtf32" else
-            ("f32" if a.mode == "ffma" else "tf32"),
+            "vs_baseline": None, "dtype": {"3xtf32": "f32 (tcgen05 3xTF32 split, fp32 accumulate)", "ffma": "f32", "tf32": "tf32",
+                      "bf16": "bf16 storage + tcgen05 kind::f16, fp32 accumulate (throughput mode, tolerance in "
+                              "tests/test_gpu_forward.py::test_bf16_mode_*)"}[a.mode],
             "data": "synthetic", "config": workload_config(a),
             # the reference's real input is a uint8 image (data/transforms.py:445-458): that entry is the declared
             # end-to-end number; the float32 [B,3,S,S] entry (4x the bytes over PCIe) is kept beside it

@@ -48,6 +48,8 @@ extern "C" {
 #define YNB_GEMM_FP32_FFMA   0   /* CUDA-core fp32 FMA (debug / cross-check path)            */
 #define YNB_GEMM_TC_3XTF32   1   /* tcgen05 kind::tf32, 3-term split: fp32 parity mode        */
 #define YNB_GEMM_TC_TF32     2   /* tcgen05 kind::tf32 single pass: throughput mode           */
+#define YNB_GEMM_TC_BF16     3   /* bf16 activations + weights in HBM, tcgen05 kind::f16, fp32 accumulate:
+                                    throughput mode of BASELINE configs[3] (tolerance reported separately) */
 
 typedef struct ynb_engine ynb_engine;
 

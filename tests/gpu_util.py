@@ -13,7 +13,8 @@ from yolo_nano_b200.engine import Engine
 from yolo_nano_b200.topology import conv_table
 
 DEV = torch.device("cuda", 0)
-MODES = {"ffma": _lib.GEMM_FP32_FFMA, "3xtf32": _lib.GEMM_TC_3XTF32, "tf32": _lib.GEMM_TC_TF32}
+MODES = {"ffma": _lib.GEMM_FP32_FFMA, "3xtf32": _lib.GEMM_TC_3XTF32, "tf32": _lib.GEMM_TC_TF32,
+         "bf16": _lib.GEMM_TC_BF16}
 
 
 def make_engine(sd, size, classes, mode="3xtf32", max_batch=2, **kw) -> Engine:

@@ -534,3 +534,61 @@ def test_host_entries_reject_buffers_of_another_grid_size(G):
     eng.submit_host(0, torch.zeros(1, 3, 96, 96).pin_memory(), out)
     eng.wait_host(0)
     eng.close()
+
+
+def test_bf16_mode_tolerance_reported(G, g2):
+    """BASELINE configs[3] throughput mode (YNB_GEMM_TC_BF16): bf16 activations and weights in HBM, kind::f16 tensor
+    cores, fp32 accumulation / bias / activation / depthwise taps.  Reported separately from the fp32 parity mode, with
+    its tolerance stated here, against the REAL reference's tensors on the calibrated weights — the WORST case for a
+    storage format: an untrained random network amplifies every rounding through its 45 layers (single-pass TF32,
+    2^-11 per operand, already reaches 0.15-0.3 of the layer scale at the deepest taps: LAYER_TOL above; bf16 rounds
+    at 2^-9).  Stated tolerance: one kernel <= 2e-2 of the layer scale in max norm (the stage-2 taps, 1-4 kernels
+    deep, measure it); after 45 layers <= 0.6 in max norm and <= 0.35 in RMS (measured 0.41 / 0.29).  On the reference-init BASELINE
+    weights the head maps are within 2e-2 absolute (next test).  The NMS stage stays exact on its inputs."""
+    sd = W.calibrated(80, seed=1)
+    x = W.synthetic_input(2, 128, 1).to(G.DEV)
+    eng = G.make_engine(sd, 128, 80, "bf16")
+    eng.forward_raw(x)
+    torch.cuda.synchronize()
+    worst, rms = {}, {}
+    for name in TAPS:
+        got = eng.read_tap(name, 2).cpu().numpy().astype(np.float64)
+        want = np.concatenate([g2[f"img{i}.{name}"] for i in range(2)]).astype(np.float64)
+        worst[name] = float(np.abs(got - want).max() / np.abs(want).max())
+        rms[name] = float(np.sqrt(((got - want) ** 2).mean()) / np.sqrt((want ** 2).mean()))
+    print("[report] bf16 per-layer max error / layer scale:", {k: round(v, 4) for k, v in worst.items()})
+    print("[report] bf16 per-layer rms error / layer rms:", {k: round(v, 4) for k, v in rms.items()})
+    assert all(worst[k] < 2e-2 for k in ("pool", "stage2.0", "stage2.1", "stage2.2", "stage2.3", "lat3")), worst
+    assert max(worst.values()) < 0.6 and max(rms.values()) < 0.35, (worst, rms)
+    boxes, scores, cls = eng.forward_decode(x)
+    ob, os_, oc, on = eng.forward_detect(x)
+    for i in range(2):
+        bh, sh, ch = boxes[i].cpu().numpy(), scores[i].cpu().numpy(), cls[i].cpu().numpy().astype(np.int64)
+        box_px = float(np.median(np.abs(bh - g2[f"img{i}.all_bbox"]).max(axis=1))) * 128
+        cls_flip = float((ch != g2[f"img{i}.all_cls"]).mean())
+        _, _, _, idx = O.postprocess_flat(bh, sh, ch, 80, 0.001, 0.5)
+        k = int(on[i])
+        assert k == len(idx)                                                   # NMS itself stays exact on its inputs
+        np.testing.assert_array_equal(ob[i, :k].cpu().numpy(), bh[idx])
+        ref_idx = g2[f"img{i}.keep_idx"]
+        diff = len(np.setxor1d(idx, ref_idx))
+        print(f"[report] bf16 img{i} (calibrated, worst case): median box error {box_px:.3f} px, class flips "
+              f"{cls_flip:.4f}, kept {k} vs reference {len(ref_idx)}, {diff} boxes differ")
+    eng.close()
+
+
+@pytest.mark.parametrize("size,classes", [(416, 80), (320, 20)])
+def test_bf16_mode_reference_init_workloads(G, size, classes):
+    """bf16 mode on the BASELINE weights (reference init) at configs[3]'s size and at C1's: raw head maps against the
+    fp32 oracle — tolerance 2e-2 absolute (the maps are O(1) logits dominated by the biases) —, detections run."""
+    sd = W.reference_init(classes, seed=3)
+    x = W.synthetic_input(2, size, 5)
+    ref = O.network(sd, x)
+    eng = G.make_engine(sd, size, classes, "bf16")
+    raw = eng.forward_raw(x.to(G.DEV))
+    worst = max(float(np.abs(g.cpu().numpy() - r.numpy()).max()) for g, r in zip(raw, ref))
+    print(f"[report] bf16 {size}/{classes} reference init: worst raw head error {worst:.5f}")
+    assert worst < 2e-2
+    ob, os_, oc, on = eng.forward_detect(x.to(G.DEV))
+    assert int(on.min()) > 0
+    eng.close()

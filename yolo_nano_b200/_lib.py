@@ -12,7 +12,7 @@ LIB_PATH = Path(__file__).resolve().parent / "libyolonano_b200.so"
 
 YNB_ABI_VERSION = 1
 YNB_OK = 0
-GEMM_FP32_FFMA, GEMM_TC_3XTF32, GEMM_TC_TF32 = 0, 1, 2
+GEMM_FP32_FFMA, GEMM_TC_3XTF32, GEMM_TC_TF32, GEMM_TC_BF16 = 0, 1, 2, 3
 
 
 class YnbConfig(C.Structure):

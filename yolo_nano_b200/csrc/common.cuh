@@ -1,5 +1,6 @@
 // Shared helpers for the sm_100a kernels of the YOLO-Nano forward path.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <limits.h>
@@ -35,6 +36,28 @@ struct ChanMap {
   __host__ __device__ __forceinline__ int slot(int j) const { return j + (j >= gap_at ? gap : 0); }
 };
 __host__ __device__ inline ChanMap dense_map() { return ChanMap{INT_MAX, 0}; }
+
+// ---- activation storage type: float32 (parity / tf32 modes) or bfloat16 (YNB_GEMM_TC_BF16) ---------------
+// Arithmetic is always fp32 (depthwise taps, bias, activation, accumulators); only what sits in HBM between
+// kernels changes.  4 consecutive channels are the unit every HBM-bound kernel moves: 16 bytes as float, 8 as bf16.
+using bf16 = __nv_bfloat16;
+
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const bf16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                     __uint_as_float(u.y & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {     // round to nearest even, lo in bits [0,16)
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store4(bf16* p, float4 v) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
+__device__ __forceinline__ float to_float(float v) { return v; }
+__device__ __forceinline__ float to_float(bf16 v) { return __bfloat162float(v); }
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 inline int64_t round_up64(int64_t v, int64_t m) { return (v + m - 1) / m * m; }

@@ -59,7 +59,9 @@ struct TcGemmParams {
   int num_steps;          // K chunks per tile (pointwise: ceil(K/32); 3x3: 9 * C/32)
   int chunks_per_tap;     // 3x3: C/32; pointwise: num_steps
   int is3x3;
-  int mode;               // YNB_GEMM_TC_3XTF32 | YNB_GEMM_TC_TF32
+  int mode;               // YNB_GEMM_TC_3XTF32 | YNB_GEMM_TC_TF32 | YNB_GEMM_TC_BF16
+  int bf16_in;            // A and W are bf16 (K chunk = 64 elements = the same 128 bytes): kind::f16, one pass
+  int out_bf16;           // the output tensor is bf16 (fp32 accumulators, bias and activation; rounded on store)
   int num_stages;
   int w_resident;
   int64_t M;              // pointwise: rows
@@ -165,6 +167,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
 
   const bool split = p.mode == YNB_GEMM_TC_3XTF32;
+  const int kchunk = p.bf16_in ? 64 : kTcBK;       // elements per K chunk (128 bytes)
   // TMA boxes per K step: A (hi) [, A_lo when pre-split] [, W_hi [, W_lo] when W is streamed].  Issuing a
   // box costs the issuing thread ~600 cycles whatever its size (tools/tma_probe.cu), and that cost
   // overlaps across warps (1 issuer 27 B/clk/SM, 2: 54, 4: 104) — so the boxes of a step are spread over
@@ -239,8 +242,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == kTcProducerWarp && p.w_resident && ptx::elect_one()) {
     ptx::mbar_arrive_expect_tx(w_full, w_res_bytes);
     for (int st = 0; st < p.num_steps; ++st) {
-      ptx::tma_load_2d(w_hi_ptr(0, st), &tmWhi, w_full, st * kTcBK, 0);
-      if (split) ptx::tma_load_2d(w_lo_ptr(0, st), &tmWlo, w_full, st * kTcBK, 0);
+      ptx::tma_load_2d(w_hi_ptr(0, st), &tmWhi, w_full, st * kchunk, 0);
+      if (split) ptx::tma_load_2d(w_lo_ptr(0, st), &tmWlo, w_full, st * kchunk, 0);
     }
   }
   pdl_wait();
@@ -277,13 +280,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (p.is3x3) {
             int tap = st / p.chunks_per_tap, kc = st - tap * p.chunks_per_tap;
             int dy = tap / 3, dx = tap - dy * 3;
-            if (do_a) ptx::tma_load_4d(stage_a(s), &tmA, &full[s], kc * kTcBK, x0 + dx - 1, y0 + dy - 1, b);
-            if (do_alo) ptx::tma_load_4d(stage_alo(s), &tmAlo, &full[s], kc * kTcBK, x0 + dx - 1, y0 + dy - 1, b);
+            if (do_a) ptx::tma_load_4d(stage_a(s), &tmA, &full[s], kc * kchunk, x0 + dx - 1, y0 + dy - 1, b);
+            if (do_alo) ptx::tma_load_4d(stage_alo(s), &tmAlo, &full[s], kc * kchunk, x0 + dx - 1, y0 + dy - 1, b);
           } else {
-            if (do_a) ptx::tma_load_2d(stage_a(s), &tmA, &full[s], st * kTcBK, (int)(tile * kTcBM));
+            if (do_a) ptx::tma_load_2d(stage_a(s), &tmA, &full[s], st * kchunk, (int)(tile * kTcBM));
           }
-          if (do_whi) ptx::tma_load_2d(w_hi_ptr(s, st), &tmWhi, &full[s], st * kTcBK, 0);
-          if (do_wlo) ptx::tma_load_2d(w_lo_ptr(s, st), &tmWlo, &full[s], st * kTcBK, 0);
+          if (do_whi) ptx::tma_load_2d(w_hi_ptr(s, st), &tmWhi, &full[s], st * kchunk, 0);
+          if (do_wlo) ptx::tma_load_2d(w_lo_ptr(s, st), &tmWlo, &full[s], st * kchunk, 0);
           if (prole == 0) YNB_TRACE(1, tile, st);
           if (++s == p.num_stages) { s = 0; ph ^= 1; }
         }
@@ -294,6 +297,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (ptx::elect_one()) {
       const uint32_t idesc = ptx::make_idesc(2 /*tf32*/, kTcBM, p.Npad);
       const uint32_t idesc2 = ptx::make_idesc(2, kTcBM, 2 * p.Npad);
+      const uint32_t idesc_bf = ptx::make_idesc(1 /*bf16*/, kTcBM, p.Npad);
       int s = 0;
       uint32_t ph = 0;
       int acc = 0;
@@ -324,6 +328,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t da = ptx::make_sw128_kmajor_desc(a_hi + ko);
             const uint64_t db = ptx::make_sw128_kmajor_desc(b_hi + ko);
             const int slot = t % p.nmain;
+            if (p.bf16_in) {
+              ptx::mma_bf16_ss(d_tmem, da, db, idesc_bf, t != 0);
+              continue;
+            }
             if (p.stack_b) {
               // [main | corr] (+)= a_hi x [b_hi; b_lo]   then   corr += a_lo x b_hi
               ptx::mma_tf32_ss(d_tmem, da, db, idesc2, t != 0);
@@ -617,13 +625,36 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         return *reinterpret_cast<const float*>(sbox + r * 128 + ((((l >> 2) ^ (r & 7)) << 4) | ((l & 3) << 2)));
       };
 
+      // bf16 output through TMA: this thread's 16 columns as 32 bytes of its dense 64-byte staging row
+      auto drain16_bf16 = [&](int c0, int half) {
+        uint32_t r[16];
+        ptx::tmem_ld_32x16(t_base + c0, r);
+        ptx::tmem_ld_wait();
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float x0 = __uint_as_float(r[2 * j]) + s_bias[c0 + 2 * j], x1 = __uint_as_float(r[2 * j + 1]) + s_bias[c0 + 2 * j + 1];
+          w[j] = pack_bf16x2(fmaxf(x0, x0 * slope), fmaxf(x1, x1 * slope));
+        }
+        uint4* dst = reinterpret_cast<uint4*>(sbox + lane * 64 + half * 32);
+        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      };
+      const bool bf16_box = p.out_bf16 && p.tma_store && !kPass;
+      bf16* const out_bf = reinterpret_cast<bf16*>(p.out);
+
       for (int c0 = col_begin; c0 < col_end; c0 += 32) {
         if (p.tma_store) {
           if (ptx::elect_one()) ptx::bulk_wait_read<0>();   // the previous store (same elected lane) has finished reading the box
           __syncwarp();
         }
-        drain16(c0, 0);
-        if (c0 + 16 < col_end) drain16(c0 + 16, 4);
+        if (bf16_box) {
+          drain16_bf16(c0, 0);
+          if (c0 + 16 < col_end) drain16_bf16(c0 + 16, 1);
+        } else {
+          drain16(c0, 0);
+          if (c0 + 16 < col_end) drain16(c0 + 16, 4);
+        }
         if (c0 + 32 >= col_end && !shared) {   // all TMEM reads of this tile are done: hand the stage back
           ptx::tc_fence_before_sync();          // (a shared tile is the CTA's last: nobody waits for the stage)
           __syncwarp();
@@ -658,17 +689,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int col = vec ? p.out_off + i : p.omap.slot(p.out_off + (col_ok ? i : 0) * p.out_step);
           if (!p.is3x3) {
             const int nrow = col_ok ? (int)min((int64_t)32, p.M - m_base) : 0;
-            float* o = p.out + m_base * p.out_ld + col;
+            if (p.out_bf16) {
+              bf16* o = out_bf + m_base * p.out_ld + col;
 #pragma unroll 8
-            for (int r = 0; r < 32; ++r, o += p.out_ld)
-              if (r < nrow) *o = staged(r, lane);
+              for (int r = 0; r < 32; ++r, o += p.out_ld)
+                if (r < nrow) *o = __float2bfloat16_rn(staged(r, lane));
+            } else {
+              float* o = p.out + m_base * p.out_ld + col;
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r, o += p.out_ld)
+                if (r < nrow) *o = staged(r, lane);
+            }
           } else {
             // spatial tile: row -> pixel is not affine, take it from the lane that owns the row
             const int64_t off = valid ? m * p.out_ld : -1;
 #pragma unroll 8
             for (int r = 0; r < 32; ++r) {
               const int64_t offr = __shfl_sync(0xffffffffu, off, r);
-              if (col_ok && offr >= 0) p.out[offr + col] = staged(r, lane);
+              if (col_ok && offr >= 0) {
+                if (p.out_bf16) out_bf[offr + col] = __float2bfloat16_rn(staged(r, lane));
+                else p.out[offr + col] = staged(r, lane);
+              }
             }
           }
         }
@@ -708,32 +749,36 @@ inline PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
-// rank-2 map over a K-major fp32 matrix: dim0 = K (contiguous), dim1 = rows.
-inline bool make_tmap_2d(CUtensorMap* m, const float* base, uint64_t k, uint64_t rows, uint64_t row_stride_floats,
-                         uint32_t box_rows) {
+// rank-2 map over a K-major matrix (fp32, or bf16 with `bf16` set): dim0 = K (contiguous), dim1 = rows; boxes of
+// 128 bytes of K (32 floats | 64 bf16) x box_rows.  Strides / extents in ELEMENTS.
+inline bool make_tmap_2d(CUtensorMap* m, const void* base, uint64_t k, uint64_t rows, uint64_t row_stride_elems,
+                         uint32_t box_rows, bool bf16 = false) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return false;
+  const uint64_t es = bf16 ? 2 : 4;
   cuuint64_t dims[2] = {k, rows};
-  cuuint64_t strides[1] = {row_stride_floats * 4};
-  cuuint32_t box[2] = {(cuuint32_t)kTcBK, box_rows};
+  cuuint64_t strides[1] = {row_stride_elems * es};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / es), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  return enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims,
+             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// rank-4 map over an NHWC activation [B][H][W][ld] exposing C channels: (c, x, y, b).
-inline bool make_tmap_nhwc(CUtensorMap* m, const float* base, int C, int W, int H, int B, int ld, int box_w,
-                           int box_h) {
+// rank-4 map over an NHWC activation [B][H][W][ld] exposing C channels: (c, x, y, b); boxes of 128 bytes of
+// channels (32 floats | 64 bf16) x box_w x box_h pixels.
+inline bool make_tmap_nhwc(CUtensorMap* m, const void* base, int C, int W, int H, int B, int ld, int box_w,
+                           int box_h, bool bf16 = false) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return false;
+  const uint64_t es = bf16 ? 2 : 4;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)ld * 4 * W, (cuuint64_t)ld * 4 * W * H};
-  cuuint32_t box[4] = {(cuuint32_t)kTcBK, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * es, (cuuint64_t)ld * es * W, (cuuint64_t)ld * es * W * H};
+  cuuint32_t box[4] = {(cuuint32_t)(128 / es), (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  return enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims,
+             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // rank-4 map over the NCHW fp32 network input [B][3][S][S] for the stem: boxes of
@@ -753,16 +798,18 @@ inline bool make_tmap_stem_input(CUtensorMap* m, const float* x, int S, int B) {
 
 // rank-2 STORE map over an output view [rows][ld] exposing `cols` channels (multiple of 4):
 // boxes of 32 channels x 32 rows, 128-byte swizzle (matches the epilogue's staging layout).
-inline bool make_tmap_out(CUtensorMap* m, float* base, uint64_t cols, uint64_t rows, uint64_t ld) {
+// bf16: the staging box is [32 rows x 64 bytes] (32 bf16 columns), no swizzle.
+inline bool make_tmap_out(CUtensorMap* m, void* base, uint64_t cols, uint64_t rows, uint64_t ld, bool bf16 = false) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return false;
+  const uint64_t es = bf16 ? 2 : 4;
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 4};
+  cuuint64_t strides[1] = {ld * es};
   cuuint32_t box[2] = {32, 32};
   cuuint32_t estr[2] = {1, 1};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
-         CUDA_SUCCESS;
+  return enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box,
+             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, bf16 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // Weights packed for the tensor-core path: [Npad][Kpad] fp32, Kpad multiple of 32, split
@@ -770,6 +817,7 @@ inline bool make_tmap_out(CUtensorMap* m, float* base, uint64_t cols, uint64_t r
 struct TcWeights {
   float* hi = nullptr;
   float* lo = nullptr;
+  bf16* bw = nullptr;     // bf16 mode: ONE plane [Npad][Kpad], Kpad multiple of 64; tm_hi maps it, tm_lo unused
   int N = 0, Npad = 0, Kpad = 0;
   CUtensorMap tm_hi, tm_lo;
 };

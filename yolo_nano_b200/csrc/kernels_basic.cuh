@@ -46,8 +46,9 @@ struct StemWeights {
 // accumulators; per tap it reads two input pixels and three 16-byte weight vectors (broadcast)
 // and issues 12 FFMA2.  (Measured on B200, tools/fma_probe.cu: FFMA with a constant-bank /
 // uniform-register operand runs at half rate, which is what the previous version did.)
+template <typename OutT>
 __global__ void __launch_bounds__(kStemThreads)
-stem_pool_kernel(const float* __restrict__ x, float* __restrict__ out, const __grid_constant__ StemWeights wt,
+stem_pool_kernel(const float* __restrict__ x, OutT* __restrict__ out, const __grid_constant__ StemWeights wt,
                  const __grid_constant__ CUtensorMap tmX, int use_tma, int S) {
   __shared__ __align__(128) float s_in[3][kStemIn][kStemInPitch];
   __shared__ __align__(16) float s_conv[kStemConv * kStemConv][kStemCP];
@@ -161,17 +162,19 @@ stem_pool_kernel(const float* __restrict__ x, float* __restrict__ out, const __g
         const float4 v = *reinterpret_cast<const float4*>(&s_conv[(2 * r + dy) * kStemConv + 2 * q + dx][c4]);
         m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
       }
-    *reinterpret_cast<float4*>(out + (((size_t)b * Hp + py) * Hp + px) * kStemC + c4) = m;
+    store4(out + (((size_t)b * Hp + py) * Hp + px) * kStemC + c4, m);
   }
 }
 
 // tmX: rank-4 map over the NCHW input (make_tmap_stem_input); pass use_tma = 0 (any map) when the
 // input pointer is not 16-byte aligned.
-inline cudaError_t launch_stem_pool(const float* x, float* out, const StemWeights& wt, const CUtensorMap& tmX,
-                                    int use_tma, int batch, int S, cudaStream_t st) {
+inline cudaError_t launch_stem_pool(const float* x, void* out, bool out_bf16, const StemWeights& wt,
+                                    const CUtensorMap& tmX, int use_tma, int batch, int S, cudaStream_t st) {
   int Hp = S / 4;
   dim3 grid((Hp + kStemTile - 1) / kStemTile, (Hp + kStemTile - 1) / kStemTile, batch);
-  cudaError_t r = launch_pdl(stem_pool_kernel, grid, dim3(kStemThreads), 0, st, x, out, wt, tmX, use_tma, S);
+  cudaError_t r = out_bf16
+      ? launch_pdl(stem_pool_kernel<bf16>, grid, dim3(kStemThreads), 0, st, x, static_cast<bf16*>(out), wt, tmX, use_tma, S)
+      : launch_pdl(stem_pool_kernel<float>, grid, dim3(kStemThreads), 0, st, x, static_cast<float*>(out), wt, tmX, use_tma, S);
   YNB_COUNT_LAUNCH();
   return r;
 }
@@ -394,24 +397,26 @@ dwconv3x3_kernel(const float* __restrict__ in, int in_ld, int in_off,
 // thread then computes a 1x4 strip of outputs for one 4-channel group from shared memory: no bounds
 // checks, no address arithmetic per tap — ~5x fewer instructions per output than the register-tiled
 // global-load kernel above, which stays as the fallback for unaligned views.
-template <int STRIDE>
+template <int STRIDE, typename E = float>
 struct DwTile {
   static constexpr int TW = STRIDE == 1 ? 16 : 8;      // outputs per tile
   static constexpr int TH = 8;
   static constexpr int IW = (TW - 1) * STRIDE + 3;     // 18 | 17 input pixels with halo
   static constexpr int IH = (TH - 1) * STRIDE + 3;     // 10 | 17
-  static constexpr int THREADS = (TW / 4) * TH * 8;    // strips x 8 channel groups: 256 | 128
+  static constexpr int CGS = 32 / sizeof(E);           // 4-channel groups per 128-byte pixel row: 8 (float) | 16 (bf16)
+  static constexpr int CHUNK = CGS * 4;                // channels per CTA: 32 | 64
+  static constexpr int THREADS = (TW / 4) * TH * CGS;  // strips x channel groups: 256 | 128 (float), 512 | 256 (bf16)
   static constexpr int BYTES = IW * IH * 128;
 };
 
 // REV: taps reversed and no bias = the gradient of a stride-1 depthwise conv w.r.t. its input
 // (train_ops.cuh / ynb_dwconv3x3_bwd_data).
-template <int STRIDE, bool REV = false>
-__global__ void __launch_bounds__(DwTile<STRIDE>::THREADS)
-dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmIn, float* __restrict__ out, int out_ld, int out_off,
+template <int STRIDE, bool REV = false, typename E = float>
+__global__ void __launch_bounds__(DwTile<STRIDE, E>::THREADS)
+dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmIn, E* __restrict__ out, int out_ld, int out_off,
                      const float* __restrict__ w, const float* __restrict__ bias, int Ho, int Wo, int C4,
                      int tiles_x, int act) {
-  using T = DwTile<STRIDE>;
+  using T = DwTile<STRIDE, E>;
   __shared__ __align__(1024) uint8_t s_tile[T::BYTES];
   __shared__ __align__(8) uint64_t s_bar;
   const int tid = threadIdx.x;
@@ -424,8 +429,8 @@ dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmIn, float* __restrict
     ptx::fence_barrier_init();
   }
   // weights of this thread's 4 channels (independent of the previous kernel)
-  const int cg = tid & 7;                               // 4-channel group inside the chunk
-  const int c = chunk * 32 + cg * 4;
+  const int cg = tid & (T::CGS - 1);                    // 4-channel group inside the chunk
+  const int c = chunk * T::CHUNK + cg * 4;
   const bool c_ok = c < C4;
   float4 kw[9], bv = make_float4(0.f, 0.f, 0.f, 0.f);
   if (c_ok) {
@@ -436,12 +441,12 @@ dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmIn, float* __restrict
   pdl_wait();
   if (tid == 0) {
     ptx::mbar_arrive_expect_tx(&s_bar, T::BYTES);
-    ptx::tma_load_4d(s_tile, &tmIn, &s_bar, chunk * 32, x0 * STRIDE - 1, y0 * STRIDE - 1, b);
+    ptx::tma_load_4d(s_tile, &tmIn, &s_bar, chunk * T::CHUNK, x0 * STRIDE - 1, y0 * STRIDE - 1, b);
   }
   __syncthreads();                                      // barrier init visible
   ptx::mbar_wait(&s_bar, 0, nullptr, 0);
   if (!c_ok) return;
-  const int strip = tid >> 3;                           // (sy, sx): 4 outputs along x
+  const int strip = tid / T::CGS;                       // (sy, sx): 4 outputs along x
   const int sy = strip / (T::TW / 4), sx = strip - sy * (T::TW / 4);
   const int yo = y0 + sy, xo = x0 + sx * 4;
   if (yo >= Ho || xo >= Wo) return;
@@ -454,7 +459,9 @@ dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmIn, float* __restrict
 #pragma unroll
     for (int j = 0; j < NIN; ++j) {
       const int r = r0 + j;
-      v[j] = *reinterpret_cast<const float4*>(s_tile + r * 128 + ((cg ^ (r & 7)) << 4));
+      // 128-byte swizzle: 16-byte chunk index ^ (row & 7); a 4-channel group is a whole chunk (float) or half of one (bf16)
+      if (sizeof(E) == 4) v[j] = load4(reinterpret_cast<const E*>(s_tile + r * 128 + ((cg ^ (r & 7)) << 4)));
+      else v[j] = load4(reinterpret_cast<const E*>(s_tile + r * 128 + ((((cg >> 1) ^ (r & 7)) << 4) | ((cg & 1) << 3))));
     }
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
@@ -468,47 +475,60 @@ dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmIn, float* __restrict
       }
     }
   }
-  float* ob = out + (size_t)b * Ho * Wo * out_ld + (yo * Wo + xo) * out_ld + out_off + c;
+  E* ob = out + (size_t)b * Ho * Wo * out_ld + (yo * Wo + xo) * out_ld + out_off + c;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     if (xo + q < Wo) {
       float4 a = acc[q];
       a.x = apply_act(a.x, act); a.y = apply_act(a.y, act); a.z = apply_act(a.z, act); a.w = apply_act(a.w, act);
-      *reinterpret_cast<float4*>(ob + q * out_ld) = a;
+      store4(ob + q * out_ld, a);
     }
   }
 }
 
-// tensor map over the input view [B][Hin][Win][C4 of ld]: boxes of 32 channels x IW x IH pixels
-inline bool make_tmap_dw(CUtensorMap* m, const float* in, int in_ld, int in_off, int batch, int Hin, int Win, int C4,
-                         int stride) {
-  if ((reinterpret_cast<uintptr_t>(in + in_off) & 15u) || (in_ld & 3)) return false;
-  return stride == 1 ? make_tmap_nhwc(m, in + in_off, C4, Win, Hin, batch, in_ld, DwTile<1>::IW, DwTile<1>::IH)
-                     : make_tmap_nhwc(m, in + in_off, C4, Win, Hin, batch, in_ld, DwTile<2>::IW, DwTile<2>::IH);
+// tensor map over the input view [B][Hin][Win][C4 of ld]: boxes of 128 bytes of channels x IW x IH pixels
+inline bool make_tmap_dw(CUtensorMap* m, const void* in, int in_ld, int in_off, int batch, int Hin, int Win, int C4,
+                         int stride, bool is_bf16 = false) {
+  const int es = is_bf16 ? 2 : 4;
+  const char* base = static_cast<const char*>(in) + (size_t)in_off * es;
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) || ((in_ld * es) & 15)) return false;
+  return stride == 1 ? make_tmap_nhwc(m, base, C4, Win, Hin, batch, in_ld, DwTile<1>::IW, DwTile<1>::IH, is_bf16)
+                     : make_tmap_nhwc(m, base, C4, Win, Hin, batch, in_ld, DwTile<2>::IW, DwTile<2>::IH, is_bf16);
 }
 
-inline cudaError_t launch_dwconv3x3_tma(const CUtensorMap& tm, float* out, int out_ld, int out_off, const float* w,
-                                        const float* b, int batch, int Hin, int Win, int C4, int stride, int act,
-                                        cudaStream_t st, bool reversed_taps = false) {
+template <typename E>
+inline cudaError_t launch_dwconv3x3_tma_t(const CUtensorMap& tm, E* out, int out_ld, int out_off, const float* w,
+                                          const float* b, int batch, int Hin, int Win, int C4, int stride, int act,
+                                          cudaStream_t st, bool reversed_taps) {
   const int Ho = (Hin - 1) / stride + 1, Wo = (Win - 1) / stride + 1;
   if (batch <= 0 || C4 <= 0) return cudaSuccess;
   const int TW = stride == 1 ? DwTile<1>::TW : DwTile<2>::TW, TH = DwTile<1>::TH;
   const int tiles_x = (Wo + TW - 1) / TW, tiles_y = (Ho + TH - 1) / TH;
-  dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)((C4 + 31) / 32), (unsigned)batch);
+  constexpr int CH = DwTile<1, E>::CHUNK;
+  dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)((C4 + CH - 1) / CH), (unsigned)batch);
   if (reversed_taps) {
     if (stride != 1) return cudaErrorInvalidValue;
-    cudaError_t rr = launch_pdl(dwconv3x3_tma_kernel<1, true>, grid, dim3(DwTile<1>::THREADS), 0, st, tm, out, out_ld,
+    cudaError_t rr = launch_pdl(dwconv3x3_tma_kernel<1, true, E>, grid, dim3(DwTile<1, E>::THREADS), 0, st, tm, out, out_ld,
                                 out_off, w, b, Ho, Wo, C4, tiles_x, act);
     YNB_COUNT_LAUNCH();
     return rr;
   }
   cudaError_t r = stride == 1
-      ? launch_pdl(dwconv3x3_tma_kernel<1>, grid, dim3(DwTile<1>::THREADS), 0, st, tm, out, out_ld, out_off, w, b, Ho, Wo,
-                   C4, tiles_x, act)
-      : launch_pdl(dwconv3x3_tma_kernel<2>, grid, dim3(DwTile<2>::THREADS), 0, st, tm, out, out_ld, out_off, w, b, Ho, Wo,
-                   C4, tiles_x, act);
+      ? launch_pdl(dwconv3x3_tma_kernel<1, false, E>, grid, dim3(DwTile<1, E>::THREADS), 0, st, tm, out, out_ld, out_off, w,
+                   b, Ho, Wo, C4, tiles_x, act)
+      : launch_pdl(dwconv3x3_tma_kernel<2, false, E>, grid, dim3(DwTile<2, E>::THREADS), 0, st, tm, out, out_ld, out_off, w,
+                   b, Ho, Wo, C4, tiles_x, act);
   YNB_COUNT_LAUNCH();
   return r;
+}
+
+inline cudaError_t launch_dwconv3x3_tma(const CUtensorMap& tm, void* out, int out_ld, int out_off, const float* w,
+                                        const float* b, int batch, int Hin, int Win, int C4, int stride, int act,
+                                        cudaStream_t st, bool reversed_taps = false, bool is_bf16 = false) {
+  return is_bf16 ? launch_dwconv3x3_tma_t(tm, static_cast<bf16*>(out), out_ld, out_off, w, b, batch, Hin, Win, C4, stride,
+                                          act, st, reversed_taps)
+                 : launch_dwconv3x3_tma_t(tm, static_cast<float*>(out), out_ld, out_off, w, b, batch, Hin, Win, C4, stride,
+                                          act, st, reversed_taps);
 }
 
 inline cudaError_t launch_dwconv3x3(const float* in, int in_ld, int in_off, float* out, int out_ld,
@@ -557,8 +577,9 @@ inline cudaError_t launch_interleave_copy(const float* in, int in_ld, float* out
 // Tap / parity hook: internal NHWC (with channel map) -> canonical NCHW.
 // Tiled transpose through shared memory: coalesced on both sides.
 // =====================================================================================
+template <typename E>
 __global__ void __launch_bounds__(256)
-nhwc_to_nchw_kernel(const float* __restrict__ in, int in_ld, ChanMap imap, float* __restrict__ out,
+nhwc_to_nchw_kernel(const E* __restrict__ in, int in_ld, ChanMap imap, float* __restrict__ out,
                     int C, int HW) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
@@ -567,7 +588,7 @@ nhwc_to_nchw_kernel(const float* __restrict__ in, int in_ld, ChanMap imap, float
   for (int r = ty; r < 32; r += 8) {
     int p = p0 + r, c = c0 + tx;
     float v = 0.0f;
-    if (p < HW && c < C) v = in[((size_t)b * HW + p) * in_ld + imap.slot(c)];
+    if (p < HW && c < C) v = to_float(in[((size_t)b * HW + p) * in_ld + imap.slot(c)]);
     tile[r][tx] = v;
   }
   __syncthreads();
@@ -577,10 +598,11 @@ nhwc_to_nchw_kernel(const float* __restrict__ in, int in_ld, ChanMap imap, float
   }
 }
 
-inline cudaError_t launch_nhwc_to_nchw(const float* in, int in_ld, ChanMap imap, float* out,
-                                       int batch, int C, int HW, cudaStream_t st) {
+inline cudaError_t launch_nhwc_to_nchw(const void* in, int in_ld, ChanMap imap, float* out,
+                                       int batch, int C, int HW, cudaStream_t st, bool in_bf16 = false) {
   dim3 grid((HW + 31) / 32, (C + 31) / 32, batch);
-  nhwc_to_nchw_kernel<<<grid, 256, 0, st>>>(in, in_ld, imap, out, C, HW);
+  if (in_bf16) nhwc_to_nchw_kernel<<<grid, 256, 0, st>>>(static_cast<const bf16*>(in), in_ld, imap, out, C, HW);
+  else nhwc_to_nchw_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(in), in_ld, imap, out, C, HW);
   YNB_COUNT_LAUNCH();
   return cudaGetLastError();
 }
@@ -594,9 +616,10 @@ __device__ __forceinline__ float tf32_rn(float x) {     // same bits as rn_tf32_
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
+template <typename E>
 __global__ void __launch_bounds__(256)
-resample_add_kernel(const float* __restrict__ a, const float* __restrict__ a2, float* __restrict__ out,
-                    float* __restrict__ out_lo, int batch, int H, int W, int ld, int mode) {
+resample_add_kernel(const E* __restrict__ a, const E* __restrict__ a2, E* __restrict__ out,
+                    E* __restrict__ out_lo, int batch, int H, int W, int ld, int mode) {
   const int groups = ld >> 2;
   const int64_t total = (int64_t)batch * H * W * groups;
   const int H2 = mode == 1 ? H >> 1 : H << 1, W2 = mode == 1 ? W >> 1 : W << 1;
@@ -610,33 +633,36 @@ resample_add_kernel(const float* __restrict__ a, const float* __restrict__ a2, f
     int y = (int)((p / W) % H);
     int b = (int)(p / ((int64_t)W * H));
     int y2 = mode == 1 ? y >> 1 : y << 1, x2 = mode == 1 ? x >> 1 : x << 1;
-    float4 u = __ldg(reinterpret_cast<const float4*>(a + p * ld) + g);
-    float4 v = __ldg(reinterpret_cast<const float4*>(a2 + (((size_t)b * H2 + y2) * W2 + x2) * ld) + g);
+    float4 u = load4(a + p * ld + 4 * g);
+    float4 v = load4(a2 + (((size_t)b * H2 + y2) * W2 + x2) * ld + 4 * g);
     u.x += v.x; u.y += v.y; u.z += v.z; u.w += v.w;
-    if (out_lo != nullptr) {
+    if (sizeof(E) == 4 && out_lo != nullptr) {
       // The sum feeds a 3x3 conv on the tensor cores in fp32-parity mode: every element would be
       // split into exact-tf32 hi + lo nine times (once per tap) inside the GEMM.  Split it ONCE here
       // (round to nearest, as the GEMM's splitters do) and let the GEMM load both planes.
       float4 h, l;
       h.x = tf32_rn(u.x); h.y = tf32_rn(u.y); h.z = tf32_rn(u.z); h.w = tf32_rn(u.w);
       l.x = tf32_rn(u.x - h.x); l.y = tf32_rn(u.y - h.y); l.z = tf32_rn(u.z - h.z); l.w = tf32_rn(u.w - h.w);
-      reinterpret_cast<float4*>(out + p * ld)[g] = h;
-      reinterpret_cast<float4*>(out_lo + p * ld)[g] = l;
+      store4(out + p * ld + 4 * g, h);
+      store4(out_lo + p * ld + 4 * g, l);
     } else {
-      reinterpret_cast<float4*>(out + p * ld)[g] = u;
+      store4(out + p * ld + 4 * g, u);
     }
   }
 }
 
-inline cudaError_t launch_resample_add(const float* a, const float* a2, float* out, float* out_lo, int batch, int H,
-                                       int W, int ld, int mode, cudaStream_t st) {
+inline cudaError_t launch_resample_add(const void* a, const void* a2, void* out, void* out_lo, int batch, int H,
+                                       int W, int ld, int mode, cudaStream_t st, bool is_bf16 = false) {
   int64_t total = (int64_t)batch * H * W * (ld / 4);
   int64_t blocks = (total + 255) / 256;
   int64_t cap = (int64_t)kNumSMs * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  cudaError_t r = launch_pdl(resample_add_kernel, dim3((unsigned)blocks), dim3(256), 0, st, a, a2, out, out_lo, batch, H, W, ld,
-                             mode);
+  cudaError_t r = is_bf16
+      ? launch_pdl(resample_add_kernel<bf16>, dim3((unsigned)blocks), dim3(256), 0, st, static_cast<const bf16*>(a),
+                   static_cast<const bf16*>(a2), static_cast<bf16*>(out), static_cast<bf16*>(nullptr), batch, H, W, ld, mode)
+      : launch_pdl(resample_add_kernel<float>, dim3((unsigned)blocks), dim3(256), 0, st, static_cast<const float*>(a),
+                   static_cast<const float*>(a2), static_cast<float*>(out), static_cast<float*>(out_lo), batch, H, W, ld, mode);
   YNB_COUNT_LAUNCH();
   return r;
 }

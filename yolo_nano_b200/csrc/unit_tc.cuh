@@ -23,6 +23,10 @@
 //                its output row (interleaved with the pass-through half for ShuffleNet units) in a swizzled
 //                staging box, the warp copies the box out 16 bytes per lane
 //
+// Storage type E = float (fp32 parity / tf32 modes: K chunks of 32 channels, A split into hi / lo planes) or
+// bf16 (YNB_GEMM_TC_BF16: K chunks of 64 channels — the same 128 bytes per row —, kind::f16 MMAs, one plane);
+// depthwise taps, bias, activations and accumulators are fp32 in both.
+//
 // Arithmetic is identical to the unfused pair (dwconv3x3_tma_kernel + tc_gemm_kernel): same FFMA2 tap order,
 // same split, same MMAs — the fused and unfused paths agree bit for bit on the depthwise values and to the
 // accumulation order on the GEMM.
@@ -67,7 +71,7 @@ struct DpSmemLayout {
 };
 
 __host__ __device__ inline DpSmemLayout dp_smem_layout(int Npad, int num_chunks, int lgTW, int a_stages, int raw_stages,
-                                                       bool w_resident, bool split) {
+                                                       bool w_resident, bool split, int chunk_ch = 32) {
   DpSmemLayout L;
   const int TW = 1 << lgTW, TH = kTcBM >> lgTW;
   L.w_chunk_bytes = (uint32_t)Npad * 128;
@@ -77,7 +81,7 @@ __host__ __device__ inline DpSmemLayout dp_smem_layout(int Npad, int num_chunks,
   L.w_res_off = L.a_off + L.a_stride * a_stages;
   const uint32_t w_res = w_resident ? L.w_chunk_bytes * (split ? 2 : 1) * num_chunks : 0;
   L.dww_off = L.w_res_off + w_res;
-  L.bias_off = L.dww_off + (((uint32_t)(10 * num_chunks * 32 * 4) + 1023u) & ~1023u);   // 9 taps + bias
+  L.bias_off = L.dww_off + (((uint32_t)(10 * num_chunks * chunk_ch * 4) + 1023u) & ~1023u);   // 9 taps + bias
   L.stg_off = L.bias_off + 1024;
   L.bar_off = L.stg_off + kDpStgBytes;
   L.total = L.bar_off + 256 + 1024;
@@ -91,7 +95,7 @@ __device__ __forceinline__ float cvt_rna_tf32(float x) {
   return __uint_as_float(r);
 }
 
-template <bool kPass>
+template <bool kPass, typename E>
 __global__ void __launch_bounds__(kDpThreads, 1)
 dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmWhi,
                const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmPass,
@@ -99,10 +103,13 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
 
-  const bool split = p.mode == YNB_GEMM_TC_3XTF32;
-  const DpSmemLayout lay = dp_smem_layout(p.Npad, p.num_chunks, p.lgTW, p.a_stages, p.raw_stages, p.w_resident != 0, split);
+  constexpr bool kBf16 = sizeof(E) == 2;
+  constexpr int CH = 128 / (int)sizeof(E);          // channels per K chunk (one 128-byte swizzle row): 32 | 64
+  constexpr int CGS = CH / 4;                       // 4-channel groups per chunk: 8 | 16
+  const bool split = !kBf16 && p.mode == YNB_GEMM_TC_3XTF32;
+  const DpSmemLayout lay = dp_smem_layout(p.Npad, p.num_chunks, p.lgTW, p.a_stages, p.raw_stages, p.w_resident != 0, split, CH);
   const uint32_t w_chunk_bytes = lay.w_chunk_bytes;
-  const int KC = p.num_chunks * 32;
+  const int KC = p.num_chunks * CH;
   const int TW = 1 << p.lgTW, TH = kTcBM >> p.lgTW;
   float* s_dww = reinterpret_cast<float*>(smem + lay.dww_off);     // [10][KC]: taps 0..8, row 9 = bias
   float* s_bias = reinterpret_cast<float*>(smem + lay.bias_off);
@@ -168,8 +175,8 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
   if (warp == kDpRawWarp && p.w_resident && ptx::elect_one()) {
     ptx::mbar_arrive_expect_tx(&w_full[0], w_chunk_bytes * (split ? 2 : 1) * p.num_chunks);
     for (int kc = 0; kc < p.num_chunks; ++kc) {
-      ptx::tma_load_2d(w_hi_ptr(0, kc), &tmWhi, &w_full[0], kc * kTcBK, 0);
-      if (split) ptx::tma_load_2d(w_hi_ptr(0, kc) + w_chunk_bytes, &tmWlo, &w_full[0], kc * kTcBK, 0);
+      ptx::tma_load_2d(w_hi_ptr(0, kc), &tmWhi, &w_full[0], kc * CH, 0);
+      if (split) ptx::tma_load_2d(w_hi_ptr(0, kc) + w_chunk_bytes, &tmWlo, &w_full[0], kc * CH, 0);
     }
   }
   pdl_wait();
@@ -186,12 +193,12 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
         const int rr = (int)(tile - (int64_t)b * per_img);
         const int y0 = (rr / p.tiles_x) * TH, x0 = (rr % p.tiles_x) * TW;
         // the pass-through half of this tile is read by the epilogue a few microseconds from now: pull it into L2
-        for (int cb = 0; cb < p.pass_blocks; ++cb) ptx::tma_prefetch_4d(&tmPass, cb * 32, x0, y0, b);
+        for (int cb = 0; cb < p.pass_blocks; ++cb) ptx::tma_prefetch_4d(&tmPass, cb * CH, x0, y0, b);
         for (int kc = 0; kc < p.num_chunks; ++kc) {
           ok = ptx::mbar_wait(&raw_empty[r], ph ^ 1, p.err_flag, 1);
           if (!ok) break;
           ptx::mbar_arrive_expect_tx(&raw_full[r], raw_bytes);
-          ptx::tma_load_4d(smem + (size_t)r * lay.raw_stride, &tmIn, &raw_full[r], kc * kTcBK, x0 - 1, y0 - 1, b);
+          ptx::tma_load_4d(smem + (size_t)r * lay.raw_stride, &tmIn, &raw_full[r], kc * CH, x0 - 1, y0 - 1, b);
           if (++r == p.raw_stages) { r = 0; ph ^= 1; }
         }
       }
@@ -207,8 +214,8 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
           ok = ptx::mbar_wait(&a_empty[s], ph ^ 1, p.err_flag, 2);
           if (!ok) break;
           ptx::mbar_arrive_expect_tx(&w_full[s], w_chunk_bytes * (split ? 2 : 1));
-          ptx::tma_load_2d(w_hi_ptr(s, kc), &tmWhi, &w_full[s], kc * kTcBK, 0);
-          if (split) ptx::tma_load_2d(w_hi_ptr(s, kc) + w_chunk_bytes, &tmWlo, &w_full[s], kc * kTcBK, 0);
+          ptx::tma_load_2d(w_hi_ptr(s, kc), &tmWhi, &w_full[s], kc * CH, 0);
+          if (split) ptx::tma_load_2d(w_hi_ptr(s, kc) + w_chunk_bytes, &tmWlo, &w_full[s], kc * CH, 0);
           if (++s == p.a_stages) { s = 0; ph ^= 1; }
         }
       }
@@ -216,7 +223,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
   } else if (warp == kDpMmaWarp) {
     // ================= MMA issuer =================
     if (ptx::elect_one()) {
-      const uint32_t idesc = ptx::make_idesc(2 /*tf32*/, kTcBM, p.Npad);
+      const uint32_t idesc = ptx::make_idesc(kBf16 ? 1 : 2 /*bf16 | tf32*/, kTcBM, p.Npad);
       const uint32_t idesc2 = ptx::make_idesc(2, kTcBM, 2 * p.Npad);
       const bool stack_b = split && 2 * p.Npad <= 256;
       int s = 0, acc = 0;
@@ -246,7 +253,9 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
             const uint32_t accum = (kc | k) != 0;
             const uint64_t da = ptx::make_sw128_kmajor_desc(a_hi + ko);
             const uint64_t db = ptx::make_sw128_kmajor_desc(b_hi + ko);
-            if (stack_b) {
+            if (kBf16) {
+              ptx::mma_bf16_ss(d_tmem, da, db, idesc, accum);
+            } else if (stack_b) {
               ptx::mma_tf32_ss(d_tmem, da, db, idesc2, accum);
               ptx::mma_tf32_ss(c_tmem, ptx::make_sw128_kmajor_desc(a_lo + ko), db, idesc, 1);
             } else if (split) {
@@ -266,12 +275,11 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
     }
   } else if (warp >= kDpDwWarp0 && warp < kDpDwWarp0 + kDpDwWarps) {
     // ================= depthwise producers: thread = (1x4 output strip, 4 channels) =================
+    // 32 strips x CGS channel groups per chunk = 256 (float) | 512 (bf16) tasks for 256 threads; a thread's
+    // channel group is the same in every round, so its taps are read once per chunk.
     const int t = threadIdx.x - kDpDwWarp0 * 32;          // 0..255
-    const int cg = t & 7;
-    const int strip = t >> 3;                             // 0..31
-    const int sy = strip >> (p.lgTW - 2), sx = strip & ((TW >> 2) - 1);
+    const int cg = t & (CGS - 1);
     const int IW = TW + 2;
-    const int row0 = sy * TW + sx * 4;                    // first of this thread's 4 tile rows (= A rows)
     const bool has_act = p.dw_act != YNB_ACT_NONE;
     const float slope = p.dw_act == YNB_ACT_RELU ? 0.0f : 0.1f;
     int r = 0, s = 0;
@@ -279,64 +287,73 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
     bool ok = true;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
       for (int kc = 0; kc < p.num_chunks; ++kc) {
-        const float* wv = s_dww + kc * 32 + cg * 4;
+        const float* wv = s_dww + kc * CH + cg * 4;
         float4 kw[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) kw[k] = *reinterpret_cast<const float4*>(wv + k * KC);
         const float4 bv = *reinterpret_cast<const float4*>(wv + 9 * KC);
         ok = ptx::mbar_wait(&raw_full[r], rph, p.err_flag, 7);
+        if (ok) ok = ptx::mbar_wait(&a_empty[s], sph ^ 1, p.err_flag, 8);
         if (!ok) break;
         const uint8_t* raw = smem + (size_t)r * lay.raw_stride;
-        float4 acc[4] = {bv, bv, bv, bv};
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          const int r0 = (sy + ky) * IW + sx * 4;
-          float4 v[6];
-#pragma unroll
-          for (int j = 0; j < 6; ++j) {
-            const int rr = r0 + j;
-            v[j] = *reinterpret_cast<const float4*>(raw + rr * 128 + ((cg ^ (rr & 7)) << 4));
-          }
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const float4 k = kw[ky * 3 + kx];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 u = v[q + kx];
-              const float2 lo = __ffma2_rn(make_float2(u.x, u.y), make_float2(k.x, k.y), make_float2(acc[q].x, acc[q].y));
-              const float2 hi = __ffma2_rn(make_float2(u.z, u.w), make_float2(k.z, k.w), make_float2(acc[q].z, acc[q].w));
-              acc[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
-            }
-          }
-        }
-        // the raw tile has been consumed into registers: hand it back before the (longer) store phase
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&raw_empty[r]);
-        if (has_act) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            acc[q].x = fmaxf(acc[q].x, acc[q].x * slope); acc[q].y = fmaxf(acc[q].y, acc[q].y * slope);
-            acc[q].z = fmaxf(acc[q].z, acc[q].z * slope); acc[q].w = fmaxf(acc[q].w, acc[q].w * slope);
-          }
-        }
-        ok = ptx::mbar_wait(&a_empty[s], sph ^ 1, p.err_flag, 8);
-        if (!ok) break;
         uint8_t* a_hi = a_stage(s);
         uint8_t* a_lo = a_hi + kTcAStageBytes;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int row = row0 + q;
-          const uint32_t o = (uint32_t)row * 128 + ((uint32_t)(cg ^ (row & 7)) << 4);
-          const float4 a = acc[q];
-          if (split) {
-            float4 h, l;
-            h.x = cvt_rna_tf32(a.x); h.y = cvt_rna_tf32(a.y); h.z = cvt_rna_tf32(a.z); h.w = cvt_rna_tf32(a.w);
-            l.x = cvt_rna_tf32(a.x - h.x); l.y = cvt_rna_tf32(a.y - h.y);
-            l.z = cvt_rna_tf32(a.z - h.z); l.w = cvt_rna_tf32(a.w - h.w);
-            *reinterpret_cast<float4*>(a_hi + o) = h;
-            *reinterpret_cast<float4*>(a_lo + o) = l;
-          } else {
-            *reinterpret_cast<float4*>(a_hi + o) = a;
+        for (int rd = 0; rd < CGS / 8; ++rd) {
+          const int strip = (t / CGS) + rd * (256 / CGS);      // 0..31
+          const int sy = strip >> (p.lgTW - 2), sx = strip & ((TW >> 2) - 1);
+          float4 acc[4] = {bv, bv, bv, bv};
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const int r0 = (sy + ky) * IW + sx * 4;
+            float4 v[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              const int rr = r0 + j;
+              if (!kBf16) v[j] = load4(reinterpret_cast<const E*>(raw + rr * 128 + ((cg ^ (rr & 7)) << 4)));
+              else v[j] = load4(reinterpret_cast<const E*>(raw + rr * 128 + ((((cg >> 1) ^ (rr & 7)) << 4) | ((cg & 1) << 3))));
+            }
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const float4 k = kw[ky * 3 + kx];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 u = v[q + kx];
+                const float2 lo = __ffma2_rn(make_float2(u.x, u.y), make_float2(k.x, k.y), make_float2(acc[q].x, acc[q].y));
+                const float2 hi = __ffma2_rn(make_float2(u.z, u.w), make_float2(k.z, k.w), make_float2(acc[q].z, acc[q].w));
+                acc[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
+              }
+            }
+          }
+          if (rd == CGS / 8 - 1) {         // the raw tile has been consumed into registers: hand it back
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&raw_empty[r]);
+          }
+          const int row0 = sy * TW + sx * 4;                  // first of this strip's 4 tile rows (= A rows)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int row = row0 + q;
+            float4 a = acc[q];
+            if (has_act) {
+              a.x = fmaxf(a.x, a.x * slope); a.y = fmaxf(a.y, a.y * slope);
+              a.z = fmaxf(a.z, a.z * slope); a.w = fmaxf(a.w, a.w * slope);
+            }
+            if (kBf16) {
+              const uint32_t o = (uint32_t)row * 128 + ((uint32_t)((cg >> 1) ^ (row & 7)) << 4) + ((uint32_t)(cg & 1) << 3);
+              *reinterpret_cast<uint2*>(a_hi + o) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+            } else {
+              const uint32_t o = (uint32_t)row * 128 + ((uint32_t)(cg ^ (row & 7)) << 4);
+              if (split) {
+                float4 h, l;
+                h.x = cvt_rna_tf32(a.x); h.y = cvt_rna_tf32(a.y); h.z = cvt_rna_tf32(a.z); h.w = cvt_rna_tf32(a.w);
+                l.x = cvt_rna_tf32(a.x - h.x); l.y = cvt_rna_tf32(a.y - h.y);
+                l.z = cvt_rna_tf32(a.z - h.z); l.w = cvt_rna_tf32(a.w - h.w);
+                *reinterpret_cast<float4*>(a_hi + o) = h;
+                *reinterpret_cast<float4*>(a_lo + o) = l;
+              } else {
+                *reinterpret_cast<float4*>(a_hi + o) = a;
+              }
+            }
           }
         }
         ptx::fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core
@@ -347,11 +364,11 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
       }
     }
   } else if (warp < kDpEpiWarps) {
-    // ================= epilogue: warp q drains TMEM lanes [32q, 32q + 32) of every tile =================
+    // ================= epilogue: two groups of four warps (group g owns accumulator stage g) =================
     // The thread that owns a tile row builds 128 bytes of its OUTPUT row in the warp's swizzled staging box
     // (interleaved with the pass-through half for ShuffleNet units) — no transposition: it owns the same row
-    // of the accumulator — and the warp then copies the box out with 16-byte (8-byte across a layout gap)
-    // accesses, four (two) complete 128-byte row segments per instruction.
+    // of the accumulator — and the warp then copies the box out with 16-byte accesses (whole 128-byte row
+    // segments per instruction); across a layout gap the unit is one (x1, conv) pair.
     const int group = warp >> 2, q = warp & 3;            // group g drains the tiles with (local index & 1) == g
     const int row = q * 32 + lane;
     const float slope = p.act == YNB_ACT_RELU ? 0.0f : (p.act == YNB_ACT_LEAKY ? 0.1f : 1.0f);
@@ -359,8 +376,13 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
     const int sw = lane & 7;
     const int yy = row >> p.lgTW, xx = row & (TW - 1);
     const bool gap = p.omap.gap != 0;
-    const int nbox = kPass ? (p.Npad + 15) / 16 : (p.Npad + 31) / 32;     // 32 output floats per row and box
-    const int out_cols = kPass ? 2 * p.N : ((p.N + 3) & ~3);              // logical output floats per row
+    constexpr int BOX = 128 / (int)sizeof(E);              // output elements per row and box: 32 | 64
+    constexpr int CPB = kPass ? BOX / 2 : BOX;             // accumulator columns per box: 16/32 | 32/64
+    constexpr int EPC = 16 / (int)sizeof(E);               // elements per 16-byte chunk: 4 | 8
+    const int nbox = (p.Npad + CPB - 1) / CPB;
+    const int out_cols = kPass ? 2 * p.N : ((p.N + EPC - 1) / EPC) * EPC;   // logical output elements per row
+    E* const outp = reinterpret_cast<E*>(p.out);
+    const E* const passp = reinterpret_cast<const E*>(p.pass);
     const int acc = group;
     bool ok = true;
     int lt = group;
@@ -372,13 +394,13 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
       const bool valid = y < p.H && x < p.W;
       const int pix = (b * p.H + y) * p.W + x;
       const int ooff = valid ? pix * p.out_ld : -1;        // element offsets fit 32 bits (checked at plan time)
-      const float* prow = p.pass + (valid ? (size_t)pix * p.pass_ld : 0);
-      float4 x1v[4];
+      const E* prow = passp + (valid ? (size_t)pix * p.pass_ld : 0);
+      uint4 x1v[4];                                        // the CPB pass-through elements of the next box (64 bytes)
       auto fetch_x1 = [&](int c0) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          x1v[j] = (kPass && valid && c0 + 4 * j < p.N) ? __ldg(reinterpret_cast<const float4*>(prow + c0) + j)
-                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+          x1v[j] = (kPass && valid && c0 + EPC * j < p.N) ? __ldg(reinterpret_cast<const uint4*>(prow + c0) + j)
+                                                         : make_uint4(0u, 0u, 0u, 0u);
       };
       if (kPass) fetch_x1(0);
       ok = ptx::mbar_wait(&tmem_full[acc], acc_ph, p.err_flag, 9);
@@ -408,60 +430,105 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * slope);
       };
+      auto put_chunk = [&](int j, uint4 val) {               // 16-byte chunk j of this thread's staging row
+        *reinterpret_cast<uint4*>(sbox + lane * 128 + ((j ^ sw) << 4)) = val;
+      };
       for (int bx = 0; bx < nbox; ++bx) {
-        if (kPass) {
+        const int c0 = bx * CPB;
+        if (!kBf16 && kPass) {
           float v[16];
-          drain16(bx * 16, v);
-          const float x1f[16] = {x1v[0].x, x1v[0].y, x1v[0].z, x1v[0].w, x1v[1].x, x1v[1].y, x1v[1].z, x1v[1].w,
-                                 x1v[2].x, x1v[2].y, x1v[2].z, x1v[2].w, x1v[3].x, x1v[3].y, x1v[3].z, x1v[3].w};
+          drain16(c0, v);
+          const uint32_t xw[16] = {x1v[0].x, x1v[0].y, x1v[0].z, x1v[0].w, x1v[1].x, x1v[1].y, x1v[1].z, x1v[1].w,
+                                   x1v[2].x, x1v[2].y, x1v[2].z, x1v[2].w, x1v[3].x, x1v[3].y, x1v[3].z, x1v[3].w};
 #pragma unroll
           for (int j = 0; j < 8; ++j)      // chunk j = (x1[2j], conv[2j], x1[2j+1], conv[2j+1])
-            *reinterpret_cast<float4*>(sbox + lane * 128 + ((j ^ sw) << 4)) =
-                make_float4(x1f[2 * j], v[2 * j], x1f[2 * j + 1], v[2 * j + 1]);
-          if (bx + 1 < nbox) fetch_x1((bx + 1) * 16);
-        } else {
+            put_chunk(j, make_uint4(xw[2 * j], __float_as_uint(v[2 * j]), xw[2 * j + 1], __float_as_uint(v[2 * j + 1])));
+        } else if (!kBf16) {
           float v[16];
-          drain16(bx * 32, v);
+          drain16(c0, v);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<float4*>(sbox + lane * 128 + ((j ^ sw) << 4)) =
-                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          if (bx * 32 + 16 < p.Npad) {
-            drain16(bx * 32 + 16, v);
+            put_chunk(j, make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                                    __float_as_uint(v[4 * j + 3])));
+          if (c0 + 16 < p.Npad) {
+            drain16(c0 + 16, v);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<float4*>(sbox + lane * 128 + (((4 + j) ^ sw) << 4)) =
-                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              put_chunk(4 + j, make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                          __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
+          }
+        } else if (kPass) {
+          // bf16: one 32-bit word per output pair = (x1[i] in the low half, conv[i] in the high half)
+          const uint32_t xw[16] = {x1v[0].x, x1v[0].y, x1v[0].z, x1v[0].w, x1v[1].x, x1v[1].y, x1v[1].z, x1v[1].w,
+                                   x1v[2].x, x1v[2].y, x1v[2].z, x1v[2].w, x1v[3].x, x1v[3].y, x1v[3].z, x1v[3].w};
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h == 0 || c0 + 16 < p.Npad) {
+              float v[16];
+              drain16(c0 + 16 * h, v);
+              uint32_t w[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const uint32_t xs = xw[8 * h + (i >> 1)];
+                const uint32_t x1bits = (i & 1) ? (xs >> 16) : (xs & 0xffffu);
+                w[i] = x1bits | (pack_bf16x2(0.0f, v[i]) & 0xffff0000u);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) put_chunk(4 * h + j, make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            if (h == 0 || c0 + 16 * h < p.Npad) {
+              float v[16];
+              drain16(c0 + 16 * h, v);
+              put_chunk(2 * h, make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                          pack_bf16x2(v[6], v[7])));
+              put_chunk(2 * h + 1, make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                                              pack_bf16x2(v[14], v[15])));
+            }
           }
         }
+        if (kPass && bx + 1 < nbox) fetch_x1((bx + 1) * CPB);
         if (bx == nbox - 1) {              // all TMEM reads of this tile are done: hand the stage back
           ptx::tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
         }
         __syncwarp();
-        const int j0 = bx * 32;            // first logical output float of this box
+        const int j0 = bx * BOX;           // first logical output element of this box
         if (!gap) {
           const int ch = lane & 7;
-          const int jc = j0 + 4 * ch;
+          const int jc = j0 + EPC * ch;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const int r = (lane >> 3) + 4 * k;
             const int oo = __shfl_sync(0xffffffffu, ooff, r);
-            const float4 val = *reinterpret_cast<const float4*>(sbox + r * 128 + ((ch ^ (r & 7)) << 4));
-            if (oo >= 0 && jc < out_cols) *reinterpret_cast<float4*>(p.out + oo + p.out_off + jc) = val;
+            const uint4 val = *reinterpret_cast<const uint4*>(sbox + r * 128 + ((ch ^ (r & 7)) << 4));
+            if (oo >= 0 && jc < out_cols) *reinterpret_cast<uint4*>(outp + oo + p.out_off + jc) = val;
           }
-        } else {
-          const int pr = lane & 15;
+        } else if (!kBf16) {
+          const int pr = lane & 15;        // 8-byte (x1, conv) pair
           const int jc = j0 + 2 * pr;
           const int col = p.omap.slot(p.out_off + jc);
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
             const int r = (lane >> 4) + 2 * k;
             const int oo = __shfl_sync(0xffffffffu, ooff, r);
-            const float2 val =
-                *reinterpret_cast<const float2*>(sbox + r * 128 + ((((pr >> 1) ^ (r & 7)) << 4) | ((pr & 1) << 3)));
-            if (oo >= 0 && jc < out_cols) *reinterpret_cast<float2*>(p.out + oo + col) = val;
+            const uint2 val =
+                *reinterpret_cast<const uint2*>(sbox + r * 128 + ((((pr >> 1) ^ (r & 7)) << 4) | ((pr & 1) << 3)));
+            if (oo >= 0 && jc < out_cols) *reinterpret_cast<uint2*>(outp + oo + col) = val;
+          }
+        } else {
+          const int jc = j0 + 2 * lane;    // bf16: 4-byte (x1, conv) pair per lane, one 128-byte row per instruction
+          const int col = p.omap.slot(p.out_off + jc);
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            const int oo = __shfl_sync(0xffffffffu, ooff, r);
+            const uint32_t val =
+                *reinterpret_cast<const uint32_t*>(sbox + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+            if (oo >= 0 && jc < out_cols) *reinterpret_cast<uint32_t*>(outp + oo + col) = val;
           }
         }
         __syncwarp();
@@ -491,11 +558,14 @@ struct DwPwLaunch {
 
 // Tile, stages and residency for one fused launch; false = use the unfused pair (shape does not fit).
 // in: view [B][H][W][C4 of in_ld] starting at `in` (16-byte aligned), out / pass views likewise.
-inline bool plan_dwpw(DwPwLaunch& L, const float* in, int in_ld, int B, int H, int W, int C, int C4, const TcWeights* w,
+inline bool plan_dwpw(DwPwLaunch& L, const void* in, int in_ld, int B, int H, int W, int C, int C4, const TcWeights* w,
                       int mode) {
   DwPwParams& p = L.p;
   const bool split = mode == YNB_GEMM_TC_3XTF32;
-  if (w->Npad > 128 || (reinterpret_cast<uintptr_t>(in) & 15u) || (in_ld & 3)) return false;
+  const bool is_bf16 = mode == YNB_GEMM_TC_BF16;
+  const int es = is_bf16 ? 2 : 4, chunk_ch = 128 / es;
+  // TMEM: two accumulator stages of (main [+ corr]) x Npad columns
+  if (2 * (split ? 2 : 1) * w->Npad > 512 || (reinterpret_cast<uintptr_t>(in) & 15u) || ((in_ld * es) & 15)) return false;
   if ((int64_t)B * H * W * std::max(p.out_ld, std::max(p.pass_ld, 1)) >= (1LL << 31)) return false;
   p.H = H; p.W = W;
   {   // 16 x 8 or 32 x 4 output pixels per tile: whichever covers the map with fewer tiles
@@ -507,8 +577,8 @@ inline bool plan_dwpw(DwPwLaunch& L, const float* in, int in_ld, int B, int H, i
   p.tiles_y = (H + TH - 1) / TH;
   p.num_tiles = (int64_t)B * p.tiles_x * p.tiles_y;
   p.C4 = C4;
-  p.num_chunks = w->Kpad / kTcBK;
-  p.ksub = (C + 7) / 8;
+  p.num_chunks = w->Kpad / chunk_ch;
+  p.ksub = (C * es + 31) / 32;            // valid 32-byte K sub-steps (8 tf32 | 16 bf16 per MMA)
   p.N = w->N; p.Npad = w->Npad;
   p.mode = mode;
   p.tmem_cols = 32;
@@ -518,20 +588,22 @@ inline bool plan_dwpw(DwPwLaunch& L, const float* in, int in_ld, int B, int H, i
   bool found = false;
   for (int raw = kDpMaxRawStages; raw >= 2 && !found; --raw)
     for (int resident = 1; resident >= 0 && !found; --resident) {
-      DpSmemLayout lay = dp_smem_layout(p.Npad, p.num_chunks, p.lgTW, 2, raw, resident != 0, split);
+      DpSmemLayout lay = dp_smem_layout(p.Npad, p.num_chunks, p.lgTW, 2, raw, resident != 0, split, chunk_ch);
       if (lay.total <= (uint32_t)kTcSmemBudget) {
         p.a_stages = 2; p.raw_stages = raw; p.w_resident = resident; L.smem = lay.total;
         found = true;
       }
     }
   if (!found) return false;
-  if ((reinterpret_cast<uintptr_t>(p.out) & 15u) || (p.out_ld & 3) || (p.out_off & 3)) return false;
+  const int epc = 16 / es;                // elements per 16 bytes
+  if ((reinterpret_cast<uintptr_t>(p.out) & 15u) || (p.out_ld % epc) || (p.out_off % epc)) return false;
   p.pass_blocks = 0;
   if (p.pass) {
-    if ((reinterpret_cast<uintptr_t>(p.pass) & 15u) || (p.pass_ld & 3)) return false;
-    if (make_tmap_nhwc(&L.tmPass, p.pass, (p.N + 3) & ~3, W, H, B, p.pass_ld, TW, TH)) p.pass_blocks = (p.N + 31) / 32;
+    if ((reinterpret_cast<uintptr_t>(p.pass) & 15u) || (p.pass_ld % epc)) return false;
+    if (make_tmap_nhwc(&L.tmPass, p.pass, (p.N + epc - 1) / epc * epc, W, H, B, p.pass_ld, TW, TH, is_bf16))
+      p.pass_blocks = (p.N + chunk_ch - 1) / chunk_ch;
   }
-  if (!make_tmap_nhwc(&L.tmIn, in, C4, W, H, B, in_ld, TW + 2, TH + 2)) return false;
+  if (!make_tmap_nhwc(&L.tmIn, in, C4, W, H, B, in_ld, TW + 2, TH + 2, is_bf16)) return false;
   L.w = w;
   L.grid = (unsigned)std::min<int64_t>(p.num_tiles, kNumSMs);
   return true;
@@ -539,7 +611,8 @@ inline bool plan_dwpw(DwPwLaunch& L, const float* in, int in_ld, int B, int H, i
 
 inline cudaError_t launch_dwpw_tc(const DwPwLaunch& L, cudaStream_t st) {
   using KernelT = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, DwPwParams);
-  static const KernelT kernels[2] = {dwpw_tc_kernel<false>, dwpw_tc_kernel<true>};
+  static const KernelT kernels[4] = {dwpw_tc_kernel<false, float>, dwpw_tc_kernel<true, float>,
+                                     dwpw_tc_kernel<false, bf16>, dwpw_tc_kernel<true, bf16>};
   static bool attr_set = false;
   if (!attr_set) {
     for (KernelT k : kernels) {
@@ -548,7 +621,8 @@ inline cudaError_t launch_dwpw_tc(const DwPwLaunch& L, cudaStream_t st) {
     }
     attr_set = true;
   }
-  cudaError_t r = launch_pdl(kernels[L.p.pass != nullptr ? 1 : 0], dim3(L.grid), dim3(kDpThreads), (size_t)L.smem, st,
+  const int ki = (L.p.mode == YNB_GEMM_TC_BF16 ? 2 : 0) + (L.p.pass != nullptr ? 1 : 0);
+  cudaError_t r = launch_pdl(kernels[ki], dim3(L.grid), dim3(kDpThreads), (size_t)L.smem, st,
                              L.tmIn, L.w->tm_hi, L.w->tm_lo, L.p.pass_blocks ? L.tmPass : L.tmIn, L.p);
   YNB_COUNT_LAUNCH();
   return r;

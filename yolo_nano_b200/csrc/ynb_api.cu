@@ -37,12 +37,14 @@ static thread_local std::string g_create_error;
 
 // Physical NHWC tensor in the workspace.
 struct Tensor {
-  float* p = nullptr;
+  float* p = nullptr;   // base address (element type: float, or bf16 when es == 2 — use at())
+  int es = 4;       // element size in bytes
   int C = 0;        // logical channels
-  int ld = 0;       // floats per pixel
+  int ld = 0;       // elements per pixel
   int H = 0, W = 0;
   ChanMap map = {INT_MAX, 0};
   size_t floats_per_image() const { return (size_t)H * W * ld; }
+  void* at(int off = 0) const { return reinterpret_cast<char*>(p) + (size_t)off * es; }   // address of element `off`
 };
 
 // How a conv's input channels are laid out physically (static per conv).
@@ -174,6 +176,10 @@ struct ynb_engine {
   }
 };
 
+namespace ynb {
+inline bool is_bf16(const ynb_engine* e) { return e->cfg.gemm_mode == YNB_GEMM_TC_BF16; }
+}  // namespace ynb
+
 namespace {
 
 int fail(ynb_engine* e, int code, const std::string& msg) {
@@ -193,23 +199,36 @@ struct CounterScope {
 };
 
 // ---- static layout knowledge -----------------------------------------------------------
-const ChanMap kGap58 = {58, 2};   // stage-2 tensors: [58 | 2 pad | 58 | 2 pad]
+// Channel halves of a stage output must start 16-byte aligned (TMA views, 16-byte loads): 4 floats or 8 bf16.
+//   float: stage 2 = [58 | 2 pad | 58 | 2 pad] (ld 120), stages 3 / 4 dense (116 x 4 B and 232 x 4 B are aligned)
+//   bf16 : stage 2 = [58 | 6 pad | 58 | 6 pad] (ld 128), stage 3 = [116 | 4 pad | 116 | 4 pad] (ld 240), stage 4 dense
+struct StageLayout { int ld; ChanMap map; };
+StageLayout stage_layout(bool bf, int si) {
+  const int cout = stage_channels()[si + 1], h = cout / 2, a = bf ? 8 : 4;
+  const int hp = round_up(h, a);
+  if (hp == h) return {cout, dense_map()};
+  return {2 * hp, ChanMap{h, hp - h}};
+}
 
 // Input layout of conv `name` (see plan_network for the producers).
-InLayout in_layout(const ConvSpec& c) {
+InLayout in_layout(const ConvSpec& c, bool bf) {
   const std::string& n = c.name;
   if (c.kind == kDense3x3) return {c.cin == 3 ? 27 : 9 * c.cin, dense_map()};
   bool reads_c3 = n == "backbone.stage3.0.branch1.0" || n == "backbone.stage3.0.branch1.2" ||
                   n == "backbone.stage3.0.branch2.0" || n == "conv1x1_0.convs.0";
-  if (reads_c3) return {120, kGap58};
-  return {round_up(c.cin, 4), dense_map()};
+  bool reads_c4 = n == "backbone.stage4.0.branch1.0" || n == "backbone.stage4.0.branch1.2" ||
+                  n == "backbone.stage4.0.branch2.0" || n == "conv1x1_1.convs.0";
+  if (reads_c3) { StageLayout L = stage_layout(bf, 0); return {L.ld, L.map}; }
+  if (reads_c4) { StageLayout L = stage_layout(bf, 1); return {L.ld, L.map}; }
+  return {round_up(c.cin, bf ? 8 : 4), dense_map()};
 }
 
 // ---- weight packing ----------------------------------------------------------------------
 int pack_conv(ynb_engine* e, int i) {
   const ConvSpec& c = e->table[i];
   PackedConv& pc = e->convs[i];
-  InLayout il = in_layout(c);
+  const bool bf = is_bf16(e);
+  InLayout il = in_layout(c, bf);
   std::vector<float> w, b;
   if (c.kind == kDense3x3 && c.cin == 3) {            // stem: [27][24]
     w.assign(27 * 24, 0.f);
@@ -255,7 +274,28 @@ int pack_conv(ynb_engine* e, int i) {
   CUDA_TRY(e, cudaMemcpy(pc.b_dev, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
 
   // tensor-core layout for the dense contractions (not the stem: K = 27 is HBM-bound)
-  if ((c.kind == kPw1x1) || (c.kind == kDense3x3 && c.cin != 3)) {
+  if (bf && ((c.kind == kPw1x1) || (c.kind == kDense3x3 && c.cin != 3))) {
+    // bf16 mode: ONE plane [Npad][Kpad] of bf16 (round to nearest even), K in chunks of 64; a 3x3 conv pads every
+    // tap to whole chunks ([N][tap][128] for 96 channels) so that a K step never straddles two taps
+    TcWeights& t = pc.tc;
+    t.N = pc.n;
+    t.Npad = round_up(pc.n, 16);
+    const int taps = c.kind == kDense3x3 ? 9 : 1;
+    const int kin = pc.ktot / taps, kin_pad = round_up(kin, 64);
+    t.Kpad = taps * kin_pad;
+    std::vector<bf16> bw((size_t)t.Npad * t.Kpad, __float2bfloat16(0.0f));
+    for (int n = 0; n < pc.n; ++n)
+      for (int tp = 0; tp < taps; ++tp)
+        for (int k = 0; k < kin; ++k)
+          bw[(size_t)n * t.Kpad + (size_t)tp * kin_pad + k] = __float2bfloat16_rn(w[(size_t)n * pc.ktot + (size_t)tp * kin + k]);
+    if (t.bw) cudaFree(t.bw);
+    t.bw = nullptr;
+    CUDA_TRY(e, cudaMalloc(&t.bw, bw.size() * 2));
+    CUDA_TRY(e, cudaMemcpy(t.bw, bw.data(), bw.size() * 2, cudaMemcpyHostToDevice));
+    if (!make_tmap_2d(&t.tm_hi, t.bw, t.Kpad, t.Npad, t.Kpad, t.Npad, true))
+      return fail(e, YNB_ERR_CUDA, "cuTensorMapEncodeTiled failed for weights of " + c.name);
+    t.tm_lo = t.tm_hi;
+  } else if ((c.kind == kPw1x1) || (c.kind == kDense3x3 && c.cin != 3)) {
     TcWeights& t = pc.tc;
     t.N = pc.n;
     t.Npad = round_up(pc.n, 16);
@@ -292,10 +332,13 @@ struct Bump {
 // measures.  Keep in sync with plan_network.
 size_t layout_workspace(ynb_engine* e, int batch, int S, char* base) {
   Bump bump;
-  auto tensor = [&](const std::string& name, int C, int ld, int H, ChanMap map = dense_map()) {
+  const bool bf = is_bf16(e);
+  const int es_act = bf ? 2 : 4, al = bf ? 8 : 4;
+  auto tensor = [&](const std::string& name, int C, int ld, int H, ChanMap map = dense_map(), int es = 0) {
     Tensor t;
+    t.es = es ? es : es_act;
     t.C = C; t.ld = ld; t.H = H; t.W = H; t.map = map;
-    size_t o = bump.take((size_t)batch * H * H * ld * 4);
+    size_t o = bump.take((size_t)batch * H * H * ld * t.es);
     t.p = base ? reinterpret_cast<float*>(base + o) : nullptr;
     e->taps[name] = t;
     return t;
@@ -304,20 +347,22 @@ size_t layout_workspace(ynb_engine* e, int batch, int S, char* base) {
   const int H1 = S / 4;
   tensor("pool", 24, 24, H1);
   int hin = H1;
+  int ld_in = 24;
+  ChanMap map_in = dense_map();
   for (int si = 0; si < 3; ++si) {
     int cout = stage_channels()[si + 1], h = cout / 2, cin = stage_channels()[si];
     int hout = hin / 2;
     std::string st = "stage" + std::to_string(si + 2);
-    int ld_out = si == 0 ? 120 : cout;
-    ChanMap omap = si == 0 ? kGap58 : dense_map();
-    int ld_h = round_up(h, 4);
-    int ld_in = si == 0 ? 24 : (si == 1 ? 120 : cin);
-    tensor(st + ".b1dw", cin, ld_in, hout, si == 1 ? kGap58 : dense_map());   // branch1 dw output
+    const StageLayout sl = stage_layout(bf, si);
+    int ld_h = round_up(h, al);
+    tensor(st + ".b1dw", cin, ld_in, hout, map_in);                            // branch1 dw output (layout of its input)
     tensor(st + ".b2pw", h, ld_h, hin);                                        // branch2 first pw @ input res
     tensor(st + ".mid1", h, ld_h, hout);                                       // pw1 / dw scratch
     tensor(st + ".mid2", h, ld_h, hout);
-    for (int bi = 0; bi < stage_repeats()[si]; ++bi) tensor(st + "." + std::to_string(bi), cout, ld_out, hout, omap);
+    for (int bi = 0; bi < stage_repeats()[si]; ++bi) tensor(st + "." + std::to_string(bi), cout, sl.ld, hout, sl.map);
     hin = hout;
+    ld_in = sl.ld;
+    map_in = sl.map;
   }
   const int H3 = S / 8, H4 = S / 16, H5 = S / 32;
   const int hs[3] = {H3, H4, H5};
@@ -332,7 +377,7 @@ size_t layout_workspace(ynb_engine* e, int batch, int S, char* base) {
     tensor("head" + std::to_string(l) + ".a", 96, 96, hs[l]);
     tensor("head" + std::to_string(l) + ".b", 96, 96, hs[l]);
     tensor("head" + std::to_string(l) + ".c", 96, 96, hs[l]);
-    e->raw[l] = tensor(pn[l], ch, round_up(ch, 4), hs[l]);
+    e->raw[l] = tensor(pn[l], ch, round_up(ch, 4), hs[l], dense_map(), 4);    // raw head maps stay float32
   }
   // aliases used as taps
   e->taps["c3"] = e->taps["stage2.3"];
@@ -407,17 +452,19 @@ struct Planner {
     int B_ = B, c4 = pc.n, stride = c.stride, act = c.act;
     const float *w = pc.w_dev, *b = pc.b_dev;
     double px_in = (double)B * in.H * in.W, px_out = (double)B * out.H * out.W;
-    const double bytes = 4.0 * c.cin * (px_in + px_out) + 40.0 * c.cin, flops = 18.0 * c.cin * px_out;
+    const bool bf = is_bf16(e);
+    const double bytes = (double)in.es * c.cin * (px_in + px_out) + 40.0 * c.cin, flops = 18.0 * c.cin * px_out;
     // product path: halo tiles through TMA; register-tiled global loads if the view is not 16-byte aligned
     static const bool no_tma = getenv("YNB_DW_NO_TMA") != nullptr;
     e->dw_maps.emplace_back();
     CUtensorMap* tm = &e->dw_maps.back();
-    if (!no_tma && make_tmap_dw(tm, in.p, in.ld, in_off, B, in.H, in.W, c4, stride)) {
+    if ((!no_tma || bf) && make_tmap_dw(tm, in.p, in.ld, in_off, B, in.H, in.W, c4, stride, bf)) {
       plan->net.push_back({name, "dwconv3x3", bytes, flops, [=](cudaStream_t st) {
-        return launch_dwconv3x3_tma(*tm, out.p, out.ld, 0, w, b, B_, in.H, in.W, c4, stride, act, st);
+        return launch_dwconv3x3_tma(*tm, out.p, out.ld, 0, w, b, B_, in.H, in.W, c4, stride, act, st, false, bf);
       }});
       return;
     }
+    if (bf) { error = "bf16 depthwise conv needs a 16-byte aligned view: " + name; return; }
     plan->net.push_back({name, "dwconv3x3", bytes, flops, [=](cudaStream_t st) {
       return launch_dwconv3x3(in.p, in.ld, in_off, out.p, out.ld, 0, w, b, B_, in.H, in.W, c4, stride, act, st);
     }});
@@ -443,8 +490,9 @@ struct Planner {
     const ConvSpec& c = spec(name);
     int64_t M = (int64_t)B * in.H * in.W;
     const bool tc_mode = e->cfg.gemm_mode != YNB_GEMM_FP32_FFMA;
-    const double abytes = 4.0 * M * (c.cin + c.cout + (pass && tc_mode ? 2.0 * c.cout : 0.0)) + 4.0 * c.cin * c.cout +
-                          4.0 * c.cout;
+    const bool bf = is_bf16(e);
+    const double abytes = (double)in.es * M * c.cin + (double)out.es * M * (c.cout + (pass && tc_mode ? 2.0 * c.cout : 0.0)) +
+                          (bf ? 2.0 : 4.0) * c.cin * c.cout + 4.0 * c.cout;
     const double aflops = 2.0 * M * c.cin * c.cout;
     if (e->cfg.gemm_mode == YNB_GEMM_FP32_FFMA) {
       GemmParams g{};
@@ -465,9 +513,12 @@ struct Planner {
     memset(&p, 0, sizeof(p));
     p.mode = e->cfg.gemm_mode;
     p.is3x3 = 0;
-    p.num_steps = pc.tc.Kpad / kTcBK;
+    p.bf16_in = bf ? 1 : 0;
+    p.out_bf16 = out.es == 2 ? 1 : 0;
+    if (bf && pass) { error = "bf16 mode: the pass-through GEMM epilogue is not built (unit tails go through dwpw): " + name; return; }
+    p.num_steps = pc.tc.Kpad / (bf ? 64 : kTcBK);
     p.chunks_per_tap = p.num_steps;
-    p.ksub = (pc.ktot + 7) / 8;
+    p.ksub = bf ? (pc.ktot + 15) / 16 : (pc.ktot + 7) / 8;      // valid 32-byte K sub-steps
     p.M = M;
     p.num_tiles = (M + kTcBM - 1) / kTcBM;
     p.N = pc.n; p.Npad = pc.tc.Npad;
@@ -483,13 +534,14 @@ struct Planner {
       p.dec = *dec;
       L.dec_classes = e->cfg.num_classes;
     }
-    p.tma_store = (!dec && !pass && out_step == 1 && out.map.gap == 0 && out_off % 4 == 0 && out.ld % 4 == 0) ? 1 : 0;
-    if (p.tma_store && !make_tmap_out(&L.tmOut, out.p + out_off, (uint64_t)round_up(pc.n, 4), (uint64_t)M,
-                                      (uint64_t)out.ld)) {
+    const int oal = 16 / out.es;                                // output elements per 16 bytes
+    p.tma_store = (!dec && !pass && out_step == 1 && out.map.gap == 0 && out_off % oal == 0 && out.ld % oal == 0) ? 1 : 0;
+    if (p.tma_store && !make_tmap_out(&L.tmOut, out.at(out_off), (uint64_t)round_up(pc.n, oal), (uint64_t)M,
+                                      (uint64_t)out.ld, out.es == 2)) {
       error = "cuTensorMapEncodeTiled failed for output of " + name;
       return;
     }
-    if (!make_tmap_2d(&L.tmA, in.p + in_off, (uint64_t)pc.ktot, (uint64_t)M, (uint64_t)in.ld, kTcBM)) {
+    if (!make_tmap_2d(&L.tmA, in.at(in_off), (uint64_t)pc.ktot, (uint64_t)M, (uint64_t)in.ld, kTcBM, bf)) {
       error = "cuTensorMapEncodeTiled failed for input of " + name;
       return;
     }
@@ -497,7 +549,7 @@ struct Planner {
     L.grid = (unsigned)std::min<int64_t>(p.num_tiles, kNumSMs);
     const TcGemmLaunch* Lp = &L;
     // fused decode: the raw map (4*M*cout) is not written; boxes/scores/classes (24 B per anchor) are
-    const double obytes = dec ? abytes - 4.0 * M * c.cout + 24.0 * M * 3 : abytes;
+    const double obytes = dec ? abytes - (double)out.es * M * c.cout + 24.0 * M * 3 : abytes;
     Op op{dec ? name + "+decode" : name, dec ? "pw_decode_tcgen05" : "pw_tcgen05", obytes, aflops,
           [=](cudaStream_t st) { return launch_tc_gemm(*Lp, st); }};
     op.join = join;
@@ -529,8 +581,8 @@ struct Planner {
       return false;
     }
     const double M = (double)B * in.H * in.W;
-    const double bytes = 4.0 * M * (ds.cin + ps.cout * (pass ? 3.0 : 1.0)) + 4.0 * ps.cin * ps.cout + 4.0 * ps.cout +
-                         40.0 * ds.cin;
+    const double bytes = (double)in.es * M * (ds.cin + ps.cout * (pass ? 3.0 : 1.0)) + (double)in.es * ps.cin * ps.cout +
+                         4.0 * ps.cout + 40.0 * ds.cin;
     const double flops = 2.0 * M * ps.cin * ps.cout + 18.0 * M * ds.cin;
     const DwPwLaunch* Lp = &L;
     ops().push_back({dw_name + "+pw", "dwpw_tcgen05", bytes, flops,
@@ -544,10 +596,12 @@ struct Planner {
     const PackedConv& pc = conv(name);
     const ConvSpec& c = spec(name);
     int64_t M = (int64_t)B * a.H * a.W;
-    const double wbytes = 4.0 * 9 * c.cin * c.cout + 4.0 * c.cout;
+    const bool bf = is_bf16(e);
+    const double eb = a.es;
+    const double wbytes = eb * 9 * c.cin * c.cout + 4.0 * c.cout;
     const double aflops = 2.0 * M * 9 * c.cin * c.cout;
     // fused form reads a and the useful part of a2 once and writes the output once
-    const double a2bytes = a2 ? 4.0 * c.cin * M * (a2_mode == 1 ? 0.25 : 1.0) : 0.0;
+    const double a2bytes = a2 ? eb * c.cin * M * (a2_mode == 1 ? 0.25 : 1.0) : 0.0;
     if (e->cfg.gemm_mode == YNB_GEMM_FP32_FFMA) {
       GemmParams g{};
       g.a = a.p; g.a_ld = a.ld; g.a_off = 0;
@@ -568,9 +622,9 @@ struct Planner {
     if (a2) {
       Tensor a_ = a, a2_ = *a2, s_ = sum, sl_ = sum_lo;
       int B_ = B;
-      plan->net.push_back({name + "+merge", "resample_add", (presplit ? 12.0 : 8.0) * M * c.cin + a2bytes,
+      plan->net.push_back({name + "+merge", "resample_add", (presplit ? 3.0 : 2.0) * eb * M * c.cin + a2bytes,
                            1.0 * M * c.cin, [=](cudaStream_t st) {
-        return launch_resample_add(a_.p, a2_.p, s_.p, presplit ? sl_.p : nullptr, B_, a_.H, a_.W, a_.ld, a2_mode, st);
+        return launch_resample_add(a_.p, a2_.p, s_.p, presplit ? sl_.p : nullptr, B_, a_.H, a_.W, a_.ld, a2_mode, st, bf);
       }});
       src = sum;
     }
@@ -581,7 +635,9 @@ struct Planner {
     memset(&p, 0, sizeof(p));
     p.mode = e->cfg.gemm_mode;
     p.is3x3 = 1;
-    p.chunks_per_tap = c.cin / kTcBK;
+    p.bf16_in = bf ? 1 : 0;
+    p.out_bf16 = out.es == 2 ? 1 : 0;
+    p.chunks_per_tap = bf ? (c.cin + 63) / 64 : c.cin / kTcBK;   // bf16: every tap padded to whole 64-channel chunks
     p.num_steps = 9 * p.chunks_per_tap;
     p.H = a.H; p.W = a.W;
     tc_pick_tile(p.H, p.W, &p.TH, &p.TW);
@@ -595,7 +651,7 @@ struct Planner {
     p.out = out.p; p.out_ld = out.ld; p.out_off = 0; p.out_step = 1; p.omap = dense_map();
     p.bias = pc.b_dev; p.act = c.act;
     p.err_flag = e->d_err;
-    if (!make_tmap_nhwc(&L.tmA, src.p, c.cin, src.W, src.H, B, src.ld, p.TW, p.TH) ||
+    if (!make_tmap_nhwc(&L.tmA, src.p, c.cin, src.W, src.H, B, src.ld, p.TW, p.TH, bf) ||
         (presplit && !make_tmap_nhwc(&L.tmAlo, sum_lo.p, c.cin, src.W, src.H, B, src.ld, p.TW, p.TH))) {
       error = "cuTensorMapEncodeTiled failed for input of " + name;
       return;
@@ -604,7 +660,7 @@ struct Planner {
     if (!tc_plan_smem(L)) { error = "no smem configuration for " + name; return; }
     L.grid = (unsigned)std::min<int64_t>(p.num_tiles, kNumSMs);
     const TcGemmLaunch* Lp = &L;
-    plan->net.push_back({name, "conv3x3_tcgen05", 4.0 * M * (c.cin + c.cout) + wbytes, aflops,
+    plan->net.push_back({name, "conv3x3_tcgen05", eb * M * (c.cin + c.cout) + wbytes, aflops,
                          [=](cudaStream_t st) { return launch_tc_gemm(*Lp, st); }});
   }
 };
@@ -624,7 +680,8 @@ int build_plan(ynb_engine* e, int B, Plan** out) {
     Tensor pool = P.T("pool");
     // input pointer is bound at run time (first op takes it from the engine)
     double px = (double)B * S * S;
-    plan->net.push_back({"backbone.conv1.0+maxpool", "stem_pool", 4.0 * (3 * px + 24 * px / 16) + 4.0 * 27 * 24,
+    const bool bf = is_bf16(e);
+    plan->net.push_back({"backbone.conv1.0+maxpool", "stem_pool", 4.0 * 3 * px + (bf ? 2.0 : 4.0) * 24 * px / 16 + 4.0 * 27 * 24,
                          2.0 * 27 * 24 * px / 4, [=](cudaStream_t st) {
       // the input pointer is the caller's: one tensor map per (pointer, batch, S), built on first sight
       const float* xin = e->d_x_bound;
@@ -636,7 +693,7 @@ int build_plan(ynb_engine* e, int B, Plan** out) {
         if (e->stem_maps.size() > 64) e->stem_maps.clear();
         it = e->stem_maps.emplace(key, sm).first;
       }
-      return launch_stem_pool(xin, pool.p, e->stem_w, it->second.tm, it->second.ok, B, S, st);
+      return launch_stem_pool(xin, pool.p, bf, e->stem_w, it->second.tm, it->second.ok, B, S, st);
     }});
   }
   Tensor x = P.T("pool");
@@ -900,7 +957,7 @@ YNB_EXPORT int ynb_create(const ynb_config* cfg, ynb_engine** out) {
   if (cfg->num_classes < 1 || cfg->num_classes > 255) return fail(nullptr, YNB_ERR_INVALID, "num_classes out of range");
   if (cfg->input_size < 32 || cfg->input_size % 32 || cfg->input_size > 1024)
     return fail(nullptr, YNB_ERR_INVALID, "input_size must be a multiple of 32 in [32, 1024]");
-  if (cfg->gemm_mode < 0 || cfg->gemm_mode > YNB_GEMM_TC_TF32) return fail(nullptr, YNB_ERR_INVALID, "bad gemm_mode");
+  if (cfg->gemm_mode < 0 || cfg->gemm_mode > YNB_GEMM_TC_BF16) return fail(nullptr, YNB_ERR_INVALID, "bad gemm_mode");
   int ndev = 0;
   cudaError_t st = cudaGetDeviceCount(&ndev);
   if (st != cudaSuccess || ndev == 0)
@@ -978,6 +1035,7 @@ YNB_EXPORT void ynb_destroy(ynb_engine* e) {
     if (pc.b_dev) cudaFree(pc.b_dev);
     if (pc.tc.hi) cudaFree(pc.tc.hi);
     if (pc.tc.lo) cudaFree(pc.tc.lo);
+    if (pc.tc.bw) cudaFree(pc.tc.bw);
   }
   if (e->ws) cudaFree(e->ws);
   delete e;
@@ -1000,7 +1058,10 @@ YNB_EXPORT int ynb_set_thresholds(ynb_engine* e, float conf, float nms, int32_t 
 
 YNB_EXPORT int ynb_set_gemm_mode(ynb_engine* e, int32_t mode) {
   if (!e) return YNB_ERR_INVALID;
-  if (mode < 0 || mode > YNB_GEMM_TC_TF32) return fail(e, YNB_ERR_INVALID, "bad gemm_mode");
+  if (mode < 0 || mode > YNB_GEMM_TC_BF16) return fail(e, YNB_ERR_INVALID, "bad gemm_mode");
+  if ((mode == YNB_GEMM_TC_BF16) != (e->cfg.gemm_mode == YNB_GEMM_TC_BF16))
+    return fail(e, YNB_ERR_UNSUPPORTED, "bf16 mode changes the activation storage and the weight packing: create the "
+                                        "engine with gemm_mode = YNB_GEMM_TC_BF16 instead of switching");
   if (mode != e->cfg.gemm_mode) {
     cudaDeviceSynchronize();
     e->cfg.gemm_mode = mode; e->plans.clear(); e->tc_store.clear(); e->dp_store.clear(); e->dw_maps.clear(); drop_graphs(e);
@@ -1079,7 +1140,7 @@ YNB_EXPORT int ynb_forward_raw(ynb_engine* e, const float* x_dev, int32_t batch,
   float* outs[3] = {ps, pm, pl};
   for (int l = 0; l < 3; ++l) {
     const Tensor& t = e->raw[l];
-    CUDA_TRY(e, launch_nhwc_to_nchw(t.p, t.ld, t.map, outs[l], batch, t.C, t.H * t.W, e->s_main));
+    CUDA_TRY(e, launch_nhwc_to_nchw(t.p, t.ld, t.map, outs[l], batch, t.C, t.H * t.W, e->s_main, t.es == 2));
   }
   if ((rc = leave(e, user))) return rc;
   return e->cfg.gemm_mode == YNB_GEMM_FP32_FFMA ? YNB_OK : check_device_error(e);
@@ -1322,7 +1383,7 @@ YNB_EXPORT int ynb_read_tap(ynb_engine* e, const char* tap, int32_t batch, float
   CounterScope cs(e);
   int rc = enter(e, (cudaStream_t)stream);
   if (rc) return rc;
-  CUDA_TRY(e, launch_nhwc_to_nchw(t.p, t.ld, t.map, out_dev, batch, t.C, t.H * t.W, e->s_main));
+  CUDA_TRY(e, launch_nhwc_to_nchw(t.p, t.ld, t.map, out_dev, batch, t.C, t.H * t.W, e->s_main, t.es == 2));
   return leave(e, (cudaStream_t)stream);
 }
 
@@ -1528,7 +1589,7 @@ YNB_EXPORT int ynb_stem_pool(const float* x, float* out, const float* w, const f
   UNIT_TRY(cudaMemcpy(wt.b, b, sizeof(wt.b), cudaMemcpyDeviceToHost));
   CUtensorMap tmx{};
   const int use_tma = make_tmap_stem_input(&tmx, x, input_size, batch) ? 1 : 0;
-  UNIT_TRY(launch_stem_pool(x, out, wt, tmx, use_tma, batch, input_size, (cudaStream_t)stream));
+  UNIT_TRY(launch_stem_pool(x, out, false, wt, tmx, use_tma, batch, input_size, (cudaStream_t)stream));
   return YNB_OK;
 }
 
