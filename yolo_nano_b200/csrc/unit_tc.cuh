@@ -51,6 +51,7 @@ struct DwPwParams {
   int N, Npad;
   int mode;           // YNB_GEMM_TC_3XTF32 | YNB_GEMM_TC_TF32
   int w_resident, a_stages, raw_stages;
+  int prefetch_tiles; // L2 prefetch distance of the raw tiles, in tiles of this CTA (0: off)
   int pass_blocks;    // 32-channel blocks of the pass-through half to prefetch into L2 per tile (0: none)
   uint32_t tmem_cols;
   const float* dw_w;  // [9][C4] tap-major, BN folded
@@ -64,7 +65,15 @@ struct DwPwParams {
   const float* pass;  // stride-1 unit: x1 (same pixels, N channels) -> out[slot(2i)]; conv -> out[slot(2i+1)]
   int pass_ld;
   int* err_flag;
+  long long* trace;   // debug timeline (tools/gpu_dp_trace.py): CTA 0 stores clock64 at [role][local tile][chunk]
 };
+
+// roles: 0 raw issued, 1 raw landed (seen by dw warp 0), 2 A written, 3 MMAs issued, 4 accumulator ready (epilogue), 5 epilogue done
+#define YNB_DP_TRACE(role, lt, kc)                                                              \
+  do {                                                                                           \
+    if (p.trace != nullptr && blockIdx.x == 0 && (lt) < 16)                                      \
+      p.trace[((role) * 16 + (lt)) * 8 + ((kc) & 7)] = clock64();                               \
+  } while (0)
 
 struct DpSmemLayout {
   uint32_t raw_stride, a_off, a_stride, w_chunk_bytes, w_res_off, dww_off, bias_off, stg_off, bar_off, total;
@@ -194,11 +203,24 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
         const int y0 = (rr / p.tiles_x) * TH, x0 = (rr % p.tiles_x) * TW;
         // the pass-through half of this tile is read by the epilogue a few microseconds from now: pull it into L2
         for (int cb = 0; cb < p.pass_blocks; ++cb) ptx::tma_prefetch_4d(&tmPass, cb * CH, x0, y0, b);
+        // A TMA box takes ~4 k cycles from issue to landing when it comes from HBM (measured, tools/gpu_dp_trace.py)
+        // and only raw_stages x 26 KB fit in flight: the HBM rate would be latency-bound.  Pull the tile this CTA
+        // loads `pf` tiles from now into L2 (no shared memory needed), so that its loads are L2 hits.
+        if (p.prefetch_tiles > 0) {
+          const int64_t tp = tile + (int64_t)p.prefetch_tiles * gridDim.x;
+          if (tp < p.num_tiles) {
+            const int bp = (int)(tp / per_img);
+            const int rp = (int)(tp - (int64_t)bp * per_img);
+            const int yp = (rp / p.tiles_x) * TH, xp = (rp % p.tiles_x) * TW;
+            for (int kc = 0; kc < p.num_chunks; ++kc) ptx::tma_prefetch_4d(&tmIn, kc * CH, xp - 1, yp - 1, bp);
+          }
+        }
         for (int kc = 0; kc < p.num_chunks; ++kc) {
           ok = ptx::mbar_wait(&raw_empty[r], ph ^ 1, p.err_flag, 1);
           if (!ok) break;
           ptx::mbar_arrive_expect_tx(&raw_full[r], raw_bytes);
           ptx::tma_load_4d(smem + (size_t)r * lay.raw_stride, &tmIn, &raw_full[r], kc * CH, x0 - 1, y0 - 1, b);
+          YNB_DP_TRACE(0, (int)((tile - blockIdx.x) / gridDim.x), kc);
           if (++r == p.raw_stages) { r = 0; ph ^= 1; }
         }
       }
@@ -266,6 +288,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
               ptx::mma_tf32_ss(d_tmem, da, db, idesc, accum);
             }
           }
+          YNB_DP_TRACE(3, (int)((tile - blockIdx.x) / gridDim.x), kc);
           ptx::mma_commit(&a_empty[s]);
           if (kc == p.num_chunks - 1) ptx::mma_commit(&tmem_full[acc]);
           if (++s == p.a_stages) { s = 0; ph ^= 1; }
@@ -287,71 +310,81 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
     bool ok = true;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
       for (int kc = 0; kc < p.num_chunks; ++kc) {
-        const float* wv = s_dww + kc * CH + cg * 4;
-        float4 kw[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) kw[k] = *reinterpret_cast<const float4*>(wv + k * KC);
+        const float* wv = s_dww + kc * CH + cg * 4;        // this thread's taps: read per filter row (3 x 16 B, broadcast)
         const float4 bv = *reinterpret_cast<const float4*>(wv + 9 * KC);
         ok = ptx::mbar_wait(&raw_full[r], rph, p.err_flag, 7);
         if (ok) ok = ptx::mbar_wait(&a_empty[s], sph ^ 1, p.err_flag, 8);
         if (!ok) break;
+        if (t == 0) YNB_DP_TRACE(1, (int)((tile - blockIdx.x) / gridDim.x), kc);
         const uint8_t* raw = smem + (size_t)r * lay.raw_stride;
         uint8_t* a_hi = a_stage(s);
         uint8_t* a_lo = a_hi + kTcAStageBytes;
+        // one block of ROWS x 4 output pixels per thread: 32 strips x 8 groups (float) or 16 two-row blocks x 16 groups
+        // (bf16: the two rows share two of their three input rows — 24 instead of 36 tile reads)
+        constexpr int ROWS = CGS / 8;
+        const int bidx = t / CGS;
+        const int nsx = TW >> 2;
+        const int sx = bidx % nsx, sy = (bidx / nsx) * ROWS;
+        float4 acc[ROWS][4];
 #pragma unroll
-        for (int rd = 0; rd < CGS / 8; ++rd) {
-          const int strip = (t / CGS) + rd * (256 / CGS);      // 0..31
-          const int sy = strip >> (p.lgTW - 2), sx = strip & ((TW >> 2) - 1);
-          float4 acc[4] = {bv, bv, bv, bv};
+        for (int o = 0; o < ROWS; ++o)
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
-            const int r0 = (sy + ky) * IW + sx * 4;
-            float4 v[6];
+          for (int q = 0; q < 4; ++q) acc[o][q] = bv;
 #pragma unroll
-            for (int j = 0; j < 6; ++j) {
-              const int rr = r0 + j;
-              if (!kBf16) v[j] = load4(reinterpret_cast<const E*>(raw + rr * 128 + ((cg ^ (rr & 7)) << 4)));
-              else v[j] = load4(reinterpret_cast<const E*>(raw + rr * 128 + ((((cg >> 1) ^ (rr & 7)) << 4) | ((cg & 1) << 3))));
-            }
+        for (int ir = 0; ir < ROWS + 2; ++ir) {
+          const int r0 = (sy + ir) * IW + sx * 4;
+          float4 v[6];
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            const int rr = r0 + j;
+            if (!kBf16) v[j] = load4(reinterpret_cast<const E*>(raw + rr * 128 + ((cg ^ (rr & 7)) << 4)));
+            else v[j] = load4(reinterpret_cast<const E*>(raw + rr * 128 + ((((cg >> 1) ^ (rr & 7)) << 4) | ((cg & 1) << 3))));
+          }
+#pragma unroll
+          for (int o = 0; o < ROWS; ++o) {
+            const int ky = ir - o;
+            if (ky < 0 || ky > 2) continue;
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-              const float4 k = kw[ky * 3 + kx];
+              const float4 k = *reinterpret_cast<const float4*>(wv + (ky * 3 + kx) * KC);
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const float4 u = v[q + kx];
-                const float2 lo = __ffma2_rn(make_float2(u.x, u.y), make_float2(k.x, k.y), make_float2(acc[q].x, acc[q].y));
-                const float2 hi = __ffma2_rn(make_float2(u.z, u.w), make_float2(k.z, k.w), make_float2(acc[q].z, acc[q].w));
-                acc[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                const float2 lo = __ffma2_rn(make_float2(u.x, u.y), make_float2(k.x, k.y), make_float2(acc[o][q].x, acc[o][q].y));
+                const float2 hi = __ffma2_rn(make_float2(u.z, u.w), make_float2(k.z, k.w), make_float2(acc[o][q].z, acc[o][q].w));
+                acc[o][q] = make_float4(lo.x, lo.y, hi.x, hi.y);
               }
             }
           }
-          if (rd == CGS / 8 - 1) {         // the raw tile has been consumed into registers: hand it back
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&raw_empty[r]);
-          }
-          const int row0 = sy * TW + sx * 4;                  // first of this strip's 4 tile rows (= A rows)
+        }
+        // the raw tile has been consumed into registers: hand it back before the store phase
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&raw_empty[r]);
+#pragma unroll
+        for (int o = 0; o < ROWS; ++o) {
+          const int row0 = (sy + o) * TW + sx * 4;            // first of this strip's 4 tile rows (= A rows)
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int row = row0 + q;
-            float4 a = acc[q];
+            float4 a = acc[o][q];
             if (has_act) {
               a.x = fmaxf(a.x, a.x * slope); a.y = fmaxf(a.y, a.y * slope);
               a.z = fmaxf(a.z, a.z * slope); a.w = fmaxf(a.w, a.w * slope);
             }
             if (kBf16) {
-              const uint32_t o = (uint32_t)row * 128 + ((uint32_t)((cg >> 1) ^ (row & 7)) << 4) + ((uint32_t)(cg & 1) << 3);
-              *reinterpret_cast<uint2*>(a_hi + o) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+              const uint32_t o2 = (uint32_t)row * 128 + ((uint32_t)((cg >> 1) ^ (row & 7)) << 4) + ((uint32_t)(cg & 1) << 3);
+              *reinterpret_cast<uint2*>(a_hi + o2) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
             } else {
-              const uint32_t o = (uint32_t)row * 128 + ((uint32_t)(cg ^ (row & 7)) << 4);
+              const uint32_t o2 = (uint32_t)row * 128 + ((uint32_t)(cg ^ (row & 7)) << 4);
               if (split) {
                 float4 h, l;
                 h.x = cvt_rna_tf32(a.x); h.y = cvt_rna_tf32(a.y); h.z = cvt_rna_tf32(a.z); h.w = cvt_rna_tf32(a.w);
                 l.x = cvt_rna_tf32(a.x - h.x); l.y = cvt_rna_tf32(a.y - h.y);
                 l.z = cvt_rna_tf32(a.z - h.z); l.w = cvt_rna_tf32(a.w - h.w);
-                *reinterpret_cast<float4*>(a_hi + o) = h;
-                *reinterpret_cast<float4*>(a_lo + o) = l;
+                *reinterpret_cast<float4*>(a_hi + o2) = h;
+                *reinterpret_cast<float4*>(a_lo + o2) = l;
               } else {
-                *reinterpret_cast<float4*>(a_hi + o) = a;
+                *reinterpret_cast<float4*>(a_hi + o2) = a;
               }
             }
           }
@@ -359,6 +392,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
         ptx::fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&a_ready[s]);
+        if (t == 0) YNB_DP_TRACE(2, (int)((tile - blockIdx.x) / gridDim.x), kc);
         if (++r == p.raw_stages) { r = 0; rph ^= 1; }
         if (++s == p.a_stages) { s = 0; sph ^= 1; }
       }
@@ -406,6 +440,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
       ok = ptx::mbar_wait(&tmem_full[acc], acc_ph, p.err_flag, 9);
       if (!ok) break;
       ptx::tc_fence_after_sync();
+      if (q == 0 && lane == 0) YNB_DP_TRACE(4, lt, 0);
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_cols);
       // 16 accumulator columns -> bias -> activation, in registers
       auto drain16 = [&](int c0, float (&v)[16]) {
@@ -533,6 +568,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
         }
         __syncwarp();
       }
+      if (q == 0 && lane == 0) YNB_DP_TRACE(5, lt, 0);
     }
   }
 
@@ -595,6 +631,10 @@ inline bool plan_dwpw(DwPwLaunch& L, const void* in, int in_ld, int B, int H, in
       }
     }
   if (!found) return false;
+  {
+    static const int pf = getenv("YNB_DP_PREFETCH") ? atoi(getenv("YNB_DP_PREFETCH")) : 2;
+    p.prefetch_tiles = pf;
+  }
   const int epc = 16 / es;                // elements per 16 bytes
   if ((reinterpret_cast<uintptr_t>(p.out) & 15u) || (p.out_ld % epc) || (p.out_off % epc)) return false;
   p.pass_blocks = 0;

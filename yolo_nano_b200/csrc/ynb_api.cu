@@ -1537,8 +1537,11 @@ YNB_EXPORT int ynb_dwpw_tc(const float* in, int32_t in_ld, const float* dw_w, co
                            const float* pw_w, const float* pw_b, int32_t act, float* out, int32_t out_ld,
                            const float* pass, int32_t pass_ld, int32_t batch, int32_t h, int32_t w_, int32_t channels,
                            int32_t cout, int32_t mode, void* stream) {
-  if (!in || !dw_w || !dw_b || !pw_w || !pw_b || !out || channels % 4 || in_ld % 4 || out_ld % 4 || cout > 128 ||
-      cout < 1 || batch < 1 || h < 1 || w_ < 1 || (mode != YNB_GEMM_TC_3XTF32 && mode != YNB_GEMM_TC_TF32) ||
+  const bool bfm = mode == YNB_GEMM_TC_BF16;        // in / out / pass are bf16 tensors then (ld in elements, multiples of 8)
+  const int al = bfm ? 8 : 4;
+  if (!in || !dw_w || !dw_b || !pw_w || !pw_b || !out || channels % al || in_ld % al || out_ld % al || cout > (bfm ? 240 : 128) ||
+      cout < 1 || batch < 1 || h < 1 || w_ < 1 ||
+      (mode != YNB_GEMM_TC_3XTF32 && mode != YNB_GEMM_TC_TF32 && mode != YNB_GEMM_TC_BF16) ||
       (pass && (out_ld < 2 * cout || pass_ld < cout || pass_ld % 4 || ((uintptr_t)pass & 15u))) || (!pass && out_ld < cout) ||
       ((uintptr_t)out & 15u))
     return fail(nullptr, YNB_ERR_INVALID, "ynb_dwpw_tc: bad arguments");
@@ -1546,11 +1549,14 @@ YNB_EXPORT int ynb_dwpw_tc(const float* in, int32_t in_ld, const float* dw_w, co
   std::vector<float> wv((size_t)cout * channels);
   UNIT_TRY(cudaMemcpy(wv.data(), pw_w, wv.size() * 4, cudaMemcpyDeviceToHost));
   TcWeights t;
-  t.N = cout; t.Npad = round_up(cout, 16); t.Kpad = round_up(channels, kTcBK);
+  t.N = cout; t.Npad = round_up(cout, 16); t.Kpad = round_up(channels, bfm ? 64 : kTcBK);
   std::vector<float> hi((size_t)t.Npad * t.Kpad, 0.f), lo((size_t)t.Npad * t.Kpad, 0.f);
+  std::vector<bf16> bwv((size_t)t.Npad * t.Kpad, __float2bfloat16(0.0f));
   for (int n = 0; n < cout; ++n)
-    for (int k = 0; k < channels; ++k)
+    for (int k = 0; k < channels; ++k) {
       split_tf32_host(wv[(size_t)n * channels + k], &hi[(size_t)n * t.Kpad + k], &lo[(size_t)n * t.Kpad + k]);
+      bwv[(size_t)n * t.Kpad + k] = __float2bfloat16_rn(wv[(size_t)n * channels + k]);
+    }
   int* d_err = nullptr;
   UNIT_TRY(cudaMalloc(&t.hi, hi.size() * 4));
   UNIT_TRY(cudaMalloc(&t.lo, lo.size() * 4));
@@ -1558,6 +1564,7 @@ YNB_EXPORT int ynb_dwpw_tc(const float* in, int32_t in_ld, const float* dw_w, co
   UNIT_TRY(cudaMemset(d_err, 0, 4));
   UNIT_TRY(cudaMemcpy(t.hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice));
   UNIT_TRY(cudaMemcpy(t.lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice));
+  if (bfm) UNIT_TRY(cudaMemcpy(t.hi, bwv.data(), bwv.size() * 2, cudaMemcpyHostToDevice));   // one bf16 plane
   int rc = YNB_OK;
   DwPwLaunch L;
   DwPwParams& p = L.p;
@@ -1565,7 +1572,14 @@ YNB_EXPORT int ynb_dwpw_tc(const float* in, int32_t in_ld, const float* dw_w, co
   p.dw_w = dw_w; p.dw_b = dw_b; p.dw_act = dw_act;
   p.out = out; p.out_ld = out_ld; p.out_off = 0; p.omap = dense_map();
   p.bias = pw_b; p.act = act; p.pass = pass; p.pass_ld = pass ? pass_ld : 0; p.err_flag = d_err;
-  if (!make_tmap_2d(&t.tm_hi, t.hi, t.Kpad, t.Npad, t.Kpad, t.Npad) ||
+  long long* d_trace = nullptr;
+  const bool want_trace = getenv("YNB_DP_TRACE") != nullptr;
+  if (want_trace) {
+    UNIT_TRY(cudaMalloc(&d_trace, 6 * 16 * 8 * 8));
+    UNIT_TRY(cudaMemset(d_trace, 0, 6 * 16 * 8 * 8));
+    p.trace = d_trace;
+  }
+  if (!make_tmap_2d(&t.tm_hi, t.hi, t.Kpad, t.Npad, t.Kpad, t.Npad, bfm) ||
       !make_tmap_2d(&t.tm_lo, t.lo, t.Kpad, t.Npad, t.Kpad, t.Npad) ||
       !plan_dwpw(L, in, in_ld, batch, h, w_, channels, channels, &t, mode)) {
     rc = fail(nullptr, YNB_ERR_CUDA, "ynb_dwpw_tc: tensor map / smem planning failed");
@@ -1576,7 +1590,24 @@ YNB_EXPORT int ynb_dwpw_tc(const float* in, int32_t in_ld, const float* dw_w, co
     if (r == cudaSuccess) r = cudaMemcpy(&flag, d_err, 4, cudaMemcpyDeviceToHost);
     if (r != cudaSuccess) rc = fail(nullptr, YNB_ERR_CUDA, std::string("ynb_dwpw_tc: ") + cudaGetErrorString(r));
     else if (flag) rc = fail(nullptr, YNB_ERR_CUDA, "ynb_dwpw_tc: mbarrier timeout code " + std::to_string(flag));
+    if (want_trace && r == cudaSuccess) {
+      std::vector<long long> h(6 * 16 * 8);
+      cudaMemcpy(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost);
+      long long t0 = 0;
+      for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+      fprintf(stderr, "YNB_DP_TRACE chunks=%d a_stages=%d raw_stages=%d resident=%d lgTW=%d tiles=%lld grid=%u\n", L.p.num_chunks,
+              L.p.a_stages, L.p.raw_stages, L.p.w_resident, L.p.lgTW, (long long)L.p.num_tiles, L.grid);
+      const char* names[6] = {"raw_issued", "raw_landed", "A_written", "mma_issued", "acc_ready", "epi_done"};
+      for (int lt = 0; lt < 16; ++lt)
+        for (int role = 0; role < 6; ++role) {
+          std::string line;
+          for (int kc = 0; kc < 8; ++kc)
+            if (h[(role * 16 + lt) * 8 + kc]) line += " " + std::to_string(h[(role * 16 + lt) * 8 + kc] - t0);
+          if (!line.empty()) fprintf(stderr, "TRACE tile %2d %-11s%s\n", lt, names[role], line.c_str());
+        }
+    }
   }
+  if (d_trace) cudaFree(d_trace);
   cudaFree(t.hi); cudaFree(t.lo); cudaFree(d_err);
   return rc;
 }
