@@ -208,6 +208,29 @@ int  ynb_dwconv3x3(const float* in_dev, int32_t in_ld, int32_t in_off,
                    int32_t batch, int32_t h_in, int32_t w_in, int32_t channels,
                    int32_t stride, int32_t act, void* stream);
 
+/* Whole ValTransforms on the device (data/transforms.py:73-119, 59-70, 394-398, 445-458): letterbox Resize
+ * (cv2.resize bilinear, restated bit-exactly, + padding with mean*255) + Normalize + ToTensor from the ORIGINAL
+ * uint8 BGR images of any shapes (tightly packed h0 x w0 x 3, one after the other in src_dev) to the float32
+ * [batch,3,S,S] tensor of the engine's current grid size.  The caller fills one descriptor per image exactly as
+ * Resize computes its geometry (yolo_nano_b200/engine.py: letterbox_desc). */
+typedef struct ynb_image_desc {
+  int64_t offset;            /* byte offset of the image in src_dev                                   */
+  int32_t h0, w0;            /* source size                                                           */
+  int32_t nw, nh;            /* content size on the S x S canvas: (int(w0/h0*S), S) | (S, int(h0/w0*S)) | (S, S) */
+  int32_t left, top;         /* content position: ((nh-nw)//2, 0) | (0, (nw-nh)//2) | (0, 0)           */
+  int32_t mode;              /* 0: copy (h0 == w0 == S), 1: bilinear, 2: exact 2x downscale (2x2 mean) */
+  int32_t reserved;
+  double  scale_x, scale_y;  /* 1 / (nw / w0), 1 / (nh / h0) in float64                               */
+} ynb_image_desc;
+int  ynb_preprocess_letterbox_u8(ynb_engine* e, const uint8_t* src_dev, const ynb_image_desc* descs_dev,
+                                 int32_t batch, float* x_dev, void* stream);
+
+/* The evaluators' inverse box mapping (evaluator/cocoapi_evaluator.py:85-87, test.py:133-135) on the NMS output,
+ * in place:  boxes = ((boxes - offset) / scale) * size  with the reference's float64-operand roundings.
+ * boxes_dev [batch][n_per_image][4], counts_dev [batch], maps_dev [batch][12] = offset[4], scale[4], size[4]. */
+int  ynb_map_boxes(float* boxes_dev, const int32_t* counts_dev, const double* maps_dev, int32_t batch,
+                   int64_t n_per_image, void* stream);
+
 /* Pointwise 1x1 conv = GEMM over pixels, + bias + activation, fp32 FFMA variant
  * (backbone/shufflenetv2.py:46,54,60; utils/modules.py:11 with k=1).
  * w_dev is [cout][cin] row-major, b_dev [cout].

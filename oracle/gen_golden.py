@@ -373,6 +373,34 @@ def train_golden():
     print("g7 losses", out["losses"], "positives", int((target[:, :, 0] > 0).sum()), "ignored", int((target[:, :, 0] < 0).sum()))
 
 
+def letterbox_golden():
+    """g9: the REAL ValTransforms (data/transforms.py:445-458, cv2.resize inside) on uint8 BGR images of assorted
+    shapes at size 96, and the evaluator's inverse box mapping (evaluator/cocoapi_evaluator.py:85-87) on fixed boxes."""
+    import cv2
+    sys.dont_write_bytecode = True
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from data.transforms import ValTransforms  # type: ignore
+    rng = np.random.default_rng(9)
+    size = 96
+    shapes = [(96, 96), (60, 60), (192, 192), (75, 100), (100, 75), (37, 91), (200, 131), (192, 150), (48, 192), (333, 500)]
+    out = {"size": size, "n": len(shapes)}
+    for i, (h0, w0) in enumerate(shapes):
+        img = rng.integers(0, 256, (h0, w0, 3), dtype=np.uint8)
+        tensor, _, _, scale, offset = ValTransforms(size)(img)
+        boxes = rng.random((7, 4)).astype(np.float32)
+        mapped = boxes.copy()
+        mapped -= offset
+        mapped /= scale
+        mapped *= np.array([[w0, h0, w0, h0]])
+        out[f"img{i}"] = img
+        out[f"x{i}"] = tensor.numpy().astype(np.float32)
+        out[f"boxes{i}"] = boxes
+        out[f"mapped{i}"] = mapped
+    np.savez_compressed(OUT / "g9_letterbox96.npz", cv2=cv2.__version__, numpy=np.__version__, **out)
+    print("g9_letterbox96.npz:", len(shapes), "images")
+
+
 def ema_golden():
     """g8: the REAL ModelEMA (utils/misc.py:67-86) over three updates of a model whose weights change between
     updates the way an optimizer would change them (deterministic perturbations)."""
@@ -401,6 +429,8 @@ if __name__ == "__main__":
         preprocess_golden()
     elif len(sys.argv) > 1 and sys.argv[1] == "tta":
         tta_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == "letterbox":
+        letterbox_golden()
     elif len(sys.argv) > 1 and sys.argv[1] == "ema":
         ema_golden()
     elif len(sys.argv) > 1 and sys.argv[1] == "train":

@@ -365,6 +365,88 @@ def preprocess_u8(canvas: np.ndarray, rect=None, mean=VAL_MEAN_BGR, std=VAL_STD_
     return np.ascontiguousarray(np.transpose(image, (2, 0, 1))).astype(np.float32)
 
 
+def cv2_resize_linear_u8(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """`cv2.resize(src, (dw, dh))` for uint8 HWC images (default INTER_LINEAR), restated from OpenCV 4.x
+    imgproc/src/resize.cpp (third-party code of the reference's call at data/transforms.py:80,94,108; not pinned by
+    the reference — installed here: opencv 4.13): source index and weight per destination index in float32
+    (`fx = (float)((dx + 0.5) * scale - 0.5)`), 11-bit fixed-point weights (cvRound), horizontal pass in int32,
+    vertical pass `(((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2`; an exact 2x downscale in both
+    directions takes the INTER_AREA fast path (2x2 mean, rounded).  Checked bit-exact against cv2 in
+    tests/test_oracle_golden.py."""
+    sh, sw = src.shape[:2]
+
+    def coeffs(dn, sn):
+        scale = 1.0 / (np.float64(dn) / np.float64(sn))
+        d = np.arange(dn, dtype=np.float64)
+        f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+        s = np.floor(f).astype(np.int64)
+        return s, (f - s.astype(np.float32)).astype(np.float32), scale
+
+    sx, fx, scale_x = coeffs(dw, sw)
+    sy, fy, scale_y = coeffs(dh, sh)
+    eps = np.finfo(np.float64).eps
+    if abs(scale_x - 2) < eps and abs(scale_y - 2) < eps:
+        s = src.astype(np.int32)
+        return ((s[0::2, 0::2] + s[0::2, 1::2] + s[1::2, 0::2] + s[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+    neg = sx < 0
+    fx = np.where(neg, np.float32(0), fx); sx = np.where(neg, 0, sx)
+    big = sx >= sw - 1
+    fx = np.where(big, np.float32(0), fx); sx = np.where(big, sw - 1, sx)
+    rnd = lambda v: np.rint(v.astype(np.float32)).astype(np.int64)          # cvRound: half to even
+    a0, a1 = rnd((np.float32(1.0) - fx) * np.float32(2048)), rnd(fx * np.float32(2048))
+    b0, b1 = rnd((np.float32(1.0) - fy) * np.float32(2048)), rnd(fy * np.float32(2048))
+    x1 = np.minimum(sx + 1, sw - 1)
+    y0, y1 = np.clip(sy, 0, sh - 1), np.clip(sy + 1, 0, sh - 1)
+    S = src.astype(np.int64)
+    H = S[:, sx, :] * a0[None, :, None] + S[:, x1, :] * a1[None, :, None]
+    out = (((b0[:, None, None] * (H[y0] >> 4)) >> 16) + ((b1[:, None, None] * (H[y1] >> 4)) >> 16) + 2) >> 2
+    return out.astype(np.uint8)
+
+
+def letterbox_geometry(h0: int, w0: int, size: int):
+    """Resize (data/transforms.py:73-119): (new_w, new_h, left, top) of the content on the size x size canvas, and
+    the (scale, offset) the evaluators use to map boxes back (float64, as the reference builds them)."""
+    if h0 > w0:
+        nw, nh = int(w0 / h0 * size), size
+        left, top = (nh - nw) // 2, 0
+        offset = np.array([[left / nh, 0., left / nh, 0.]])
+        scale = np.array([[nw / nh, 1., nw / nh, 1.]])
+    elif h0 < w0:
+        nw, nh = size, int(h0 / w0 * size)
+        left, top = 0, (nw - nh) // 2
+        offset = np.array([[0., top / nw, 0., top / nw]])
+        scale = np.array([1., nh / nw, 1., nh / nw])
+    else:
+        nw, nh, left, top = size, size, 0, 0
+        offset = np.zeros([1, 4])
+        scale = 1.
+    return nw, nh, left, top, scale, offset
+
+
+def val_transform(img: np.ndarray, size: int, mean=VAL_MEAN_BGR, std=VAL_STD_BGR):
+    """ValTransforms (data/transforms.py:445-458) = Resize (letterbox, cv2 bilinear, padding mean*255) + Normalize +
+    ToTensor on a uint8 BGR image of any shape: (x float32 [3,S,S] RGB, scale, offset)."""
+    h0, w0 = img.shape[:2]
+    nw, nh, left, top, scale, offset = letterbox_geometry(h0, w0, size)
+    if h0 == w0 and h0 == size:
+        content = img
+    else:
+        content = cv2_resize_linear_u8(img, nw, nh)
+    canvas = np.zeros((size, size, 3), np.uint8)
+    canvas[top:top + nh, left:left + nw] = content
+    rect = None if h0 == w0 else (left, top, nw, nh)
+    return preprocess_u8(canvas, rect, mean, std), scale, offset
+
+
+def map_boxes_to_image(bboxes: np.ndarray, scale, offset, w: int, h: int) -> np.ndarray:
+    """evaluator/cocoapi_evaluator.py:85-87 (test.py:133-135): in-place float32 ops with float64 operands."""
+    b = np.array(bboxes, dtype=np.float32, copy=True)
+    b -= offset
+    b /= scale
+    b *= np.array([[w, h, w, h]])
+    return b
+
+
 # ---------------------------------------------------------------------------------------------
 # Test-time augmentation (SURVEY 8f row 2): utils/misc.py:90-148
 def tta_merge(bboxes: np.ndarray, scores: np.ndarray, labels: np.ndarray, num_classes: int, nms_thresh: float,

@@ -592,3 +592,47 @@ def test_bf16_mode_reference_init_workloads(G, size, classes):
     ob, os_, oc, on = eng.forward_detect(x.to(G.DEV))
     assert int(on.min()) > 0
     eng.close()
+
+
+def test_letterbox_preprocess_on_device_bit_identical(G, golden):
+    """SURVEY §8f row 1, the whole ValTransforms on the device: original uint8 images of assorted shapes (square,
+    no-resize, exact 2x downscale, up-scaling, extreme aspect ratios) -> the float32 tensor of the REAL reference
+    transform (golden g9: cv2.resize inside), bit for bit; and the evaluators' inverse box mapping on the device."""
+    g9 = golden("g9_letterbox96.npz")
+    size, n = int(g9["size"]), int(g9["n"])
+    sd = W.calibrated(20, seed=2)
+    eng = G.make_engine(sd, size, 20, "3xtf32", max_batch=n)
+    imgs = [g9[f"img{i}"] for i in range(n)]
+    x, maps = eng.preprocess_images(imgs)
+    for i in range(n):
+        np.testing.assert_array_equal(x[i].cpu().numpy(), g9[f"x{i}"], err_msg=f"image {i} {imgs[i].shape}")
+    boxes = torch.from_numpy(np.stack([g9[f"boxes{i}"] for i in range(n)])).to(G.DEV).contiguous()
+    counts = torch.tensor([7, 5, 7, 0, 7, 3, 7, 7, 1, 7], dtype=torch.int32, device=G.DEV)
+    eng.map_boxes(boxes, counts, maps)
+    for i in range(n):
+        k = int(counts[i])
+        np.testing.assert_array_equal(boxes[i, :k].cpu().numpy(), g9[f"mapped{i}"][:k])
+        np.testing.assert_array_equal(boxes[i, k:].cpu().numpy(), g9[f"boxes{i}"][k:])      # rows past the count untouched
+    eng.close()
+
+
+def test_detect_raw_images_equals_reference_evaluator_loop(G, golden):
+    """Drop-in: detect_raw_images(list of original images) == for each image: ValTransforms -> model -> inverse mapping
+    (evaluator/cocoapi_evaluator.py:70-87), with the oracle transform (pinned to the real one by g9) as the host side."""
+    import yolo_nano_b200 as pkg
+    g9 = golden("g9_letterbox96.npz")
+    size = int(g9["size"])
+    sd = W.calibrated(20, seed=2)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = pkg.YOLONano(G.DEV, size, 20, anchor_size=W.anchors_for(20))
+    m.load_state_dict(sd)
+    m = m.to(G.DEV).eval()
+    imgs = [g9[f"img{i}"] for i in (3, 4, 5, 9)]
+    got = m.detect_raw_images(imgs)
+    for im, (gb, gs, gc) in zip(imgs, got):
+        x, scale, offset = O.val_transform(im, size)
+        b, s, c = m(torch.from_numpy(x)[None].to(G.DEV))
+        want = O.map_boxes_to_image(b, scale, offset, im.shape[1], im.shape[0])
+        np.testing.assert_array_equal(gb, want)
+        np.testing.assert_array_equal(gs, s)
+        np.testing.assert_array_equal(gc, c)

@@ -183,3 +183,31 @@ def test_evaluator_glue_matches_reference_evaluators(golden):
     assert rows == json.loads(str(g["coco_json"]))
     for c in labelmap:
         assert voc[c] == str(g[f"voc.{c}"]), c
+
+
+def test_letterbox_transform_and_box_mapping_match_reference(golden):
+    """oracle.val_transform (cv2 bilinear resize restated + letterbox + Normalize + ToTensor) and
+    oracle.map_boxes_to_image against the REAL ValTransforms / evaluator code (golden g9): bit-identical."""
+    g9 = golden("g9_letterbox96.npz")
+    size = int(g9["size"])
+    for i in range(int(g9["n"])):
+        img = g9[f"img{i}"]
+        x, scale, offset = O.val_transform(img, size)
+        np.testing.assert_array_equal(x, g9[f"x{i}"], err_msg=f"image {i} {img.shape}")
+        got = O.map_boxes_to_image(g9[f"boxes{i}"], scale, offset, img.shape[1], img.shape[0])
+        np.testing.assert_array_equal(got, g9[f"mapped{i}"])
+
+
+def test_cv2_resize_restatement_is_bit_exact():
+    """The restated OpenCV bilinear uint8 resize against the installed cv2 over random shapes (incl. the exact 2x
+    downscale fast path and up-scaling)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(1)
+    shapes = [(480, 640, 416, 312), (640, 480, 312, 416), (100, 100, 416, 416), (832, 832, 416, 416), (37, 91, 416, 169)]
+    for _ in range(25):
+        h0, w0 = int(rng.integers(20, 700)), int(rng.integers(20, 700))
+        s = int(rng.choice([320, 416, 608]))
+        shapes.append((h0, w0, max(1, int(w0 / h0 * s)) if h0 > w0 else s, s if h0 >= w0 else max(1, int(h0 / w0 * s))))
+    for h0, w0, dw, dh in shapes:
+        img = rng.integers(0, 256, (h0, w0, 3), dtype=np.uint8)
+        np.testing.assert_array_equal(O.cv2_resize_linear_u8(img, dw, dh), cv2.resize(img, (dw, dh)), err_msg=str((h0, w0, dw, dh)))

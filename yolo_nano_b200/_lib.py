@@ -83,6 +83,8 @@ SIGNATURES = {
     "ynb_resize_bilinear": (C.c_int, [_p, _i32, _i32, _i32, _p, _i32, _i32, _p]),
     "ynb_set_normalization": (C.c_int, [_p, C.POINTER(_f), C.POINTER(_f)]),
     "ynb_preprocess_u8": (C.c_int, [_p, _p, _p, _i32, _p, _p]),
+    "ynb_preprocess_letterbox_u8": (C.c_int, [_p, _p, _p, _i32, _p, _p]),
+    "ynb_map_boxes": (C.c_int, [_p, _p, _p, _i32, _i64, _p]),
     "ynb_submit_host_u8": (C.c_int, [_p, _i32, _p, _p, _i32, _p, _p, _p, _p, _p]),
     "ynb_nms_grid_workspace_bytes": (_i64, [_i32, _i32]),
     "ynb_nms_grid": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _f, _f, _i32,

@@ -314,6 +314,128 @@ inline cudaError_t launch_preprocess_u8(const uint8_t* img, const int32_t* rects
 }
 
 // =====================================================================================
+// Whole ValTransforms on the device (data/transforms.py:73-119, 59-70, 394-398, 445-458):
+// letterbox Resize (cv2.resize bilinear of the uint8 image + padding with mean*255) + Normalize + ToTensor, from
+// the ORIGINAL uint8 BGR images (any shapes, packed in one buffer) straight to the float32 NCHW tensor the stem
+// reads — the resized canvas never exists.  The bilinear resize restates OpenCV's 8-bit INTER_LINEAR exactly
+// (imgproc/src/resize.cpp): float32 source coordinate, 11-bit fixed-point weights (cvRound), int32 horizontal
+// pass, `(((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2` vertically; exact 2x downscale = 2x2 mean.
+// One thread per canvas pixel (three planes written, coalesced along x).
+// =====================================================================================
+struct ImageDesc {          // = ynb_image_desc of the C ABI
+  long long offset;         // byte offset of the h0 x w0 x 3 uint8 image in the source buffer
+  int h0, w0;               // source size
+  int nw, nh;               // content size on the canvas
+  int left, top;            // content position
+  int mode;                 // 0: copy, 1: bilinear, 2: exact 2x2 area
+  int pad_;
+  double scale_x, scale_y;  // 1 / (nw / w0), 1 / (nh / h0) in float64, as cv::resize computes them
+};
+
+__device__ __forceinline__ void linear_coeff(int d, double scale, int sn, bool clamp_x, int* s0, int* s1, int* c0, int* c1) {
+  const float f0 = (float)__dsub_rn(__dmul_rn(__dadd_rn((double)d, 0.5), scale), 0.5);
+  int s = (int)floorf(f0);
+  float f = __fsub_rn(f0, (float)s);
+  if (clamp_x) {            // horizontal: out-of-range source columns get weight (1, 0) on the border column
+    if (s < 0) { f = 0.0f; s = 0; }
+    if (s >= sn - 1) { f = 0.0f; s = sn - 1; }
+    *s0 = s; *s1 = min(s + 1, sn - 1);
+  } else {                  // vertical: weights kept, rows clipped
+    *s0 = min(max(s, 0), sn - 1); *s1 = min(max(s + 1, 0), sn - 1);
+  }
+  *c0 = __float2int_rn(__fmul_rn(__fsub_rn(1.0f, f), 2048.0f));
+  *c1 = __float2int_rn(__fmul_rn(f, 2048.0f));
+}
+
+__global__ void __launch_bounds__(256)
+letterbox_preprocess_kernel(const uint8_t* __restrict__ src, const ImageDesc* __restrict__ descs, float* __restrict__ out,
+                            const PreLut* __restrict__ lut, int S) {
+  __shared__ float s_lut[3][256];
+  __shared__ float s_pad[3];
+  const float* lg = &lut->v[0][0];
+  for (int i = threadIdx.x; i < 768; i += 256) (&s_lut[0][0])[i] = __ldg(lg + i);
+  if (threadIdx.x < 3) s_pad[threadIdx.x] = __ldg(&lut->pad[threadIdx.x]);
+  __syncthreads();
+  const int b = blockIdx.z, y = blockIdx.y;
+  const int x = blockIdx.x * 256 + threadIdx.x;
+  if (x >= S) return;
+  const ImageDesc d = descs[b];
+  const int dx = x - d.left, dy = y - d.top;
+  float r[3];
+  if (dx >= 0 && dx < d.nw && dy >= 0 && dy < d.nh) {
+    const uint8_t* img = src + d.offset;
+    const size_t pitch = (size_t)d.w0 * 3;
+    int v[3];
+    if (d.mode == 0) {
+      const uint8_t* p = img + (size_t)dy * pitch + (size_t)dx * 3;
+      v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
+    } else if (d.mode == 2) {
+      const uint8_t* p = img + (size_t)(2 * dy) * pitch + (size_t)(2 * dx) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = ((int)p[c] + p[3 + c] + p[pitch + c] + p[pitch + 3 + c] + 2) >> 2;
+    } else {
+      int x0, x1, a0, a1, y0, y1, b0, b1;
+      linear_coeff(dx, d.scale_x, d.w0, true, &x0, &x1, &a0, &a1);
+      linear_coeff(dy, d.scale_y, d.h0, false, &y0, &y1, &b0, &b1);
+      const uint8_t* r0 = img + (size_t)y0 * pitch;
+      const uint8_t* r1 = img + (size_t)y1 * pitch;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int h0v = (int)r0[x0 * 3 + c] * a0 + (int)r0[x1 * 3 + c] * a1;
+        const int h1v = (int)r1[x0 * 3 + c] * a0 + (int)r1[x1 * 3 + c] * a1;
+        v[c] = (((b0 * (h0v >> 4)) >> 16) + ((b1 * (h1v >> 4)) >> 16) + 2) >> 2;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) r[c] = s_lut[c][min(max(v[c], 0), 255)];
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) r[c] = s_pad[c];
+  }
+#pragma unroll
+  for (int oc = 0; oc < 3; ++oc)      // RGB output plane <- BGR input channel
+    out[(((size_t)b * 3 + oc) * S + y) * S + x] = r[2 - oc];
+}
+
+inline cudaError_t launch_letterbox_preprocess(const uint8_t* src, const ImageDesc* descs, float* out, const PreLut* lut,
+                                               int batch, int S, cudaStream_t st) {
+  if (batch <= 0) return cudaSuccess;
+  dim3 grid((unsigned)((S + 255) / 256), (unsigned)S, (unsigned)batch);
+  letterbox_preprocess_kernel<<<grid, 256, 0, st>>>(src, descs, out, lut, S);
+  YNB_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+// Inverse box mapping of the evaluators (evaluator/cocoapi_evaluator.py:85-87, test.py:133-135) on the NMS output:
+//   bboxes -= offset; bboxes /= scale; bboxes *= size      float32 array, float64 operands: each op in double,
+// rounded to float32.  maps [B][12] = offset[4], scale[4], size[4]; rows [0, counts[b]) of image b.
+__global__ void __launch_bounds__(256)
+map_boxes_kernel(float* __restrict__ boxes, const int* __restrict__ counts, const double* __restrict__ maps, int batch,
+                 long long n_per_image) {
+  const int b = blockIdx.y;
+  const double* m = maps + (size_t)b * 12;
+  const long long total = (long long)min((long long)counts[b], n_per_image) * 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i & 3);
+    float* p = boxes + (size_t)b * n_per_image * 4 + i;
+    float v = *p;
+    v = (float)__dsub_rn((double)v, m[k]);
+    v = (float)__ddiv_rn((double)v, m[4 + k]);
+    v = (float)__dmul_rn((double)v, m[8 + k]);
+    *p = v;
+  }
+}
+
+inline cudaError_t launch_map_boxes(float* boxes, const int* counts, const double* maps, int batch, long long n_per_image,
+                                    cudaStream_t st) {
+  if (batch <= 0 || n_per_image <= 0) return cudaSuccess;
+  const unsigned bx = (unsigned)std::min<long long>((n_per_image * 4 + 255) / 256, 64);
+  map_boxes_kernel<<<dim3(bx, (unsigned)batch), 256, 0, st>>>(boxes, counts, maps, batch, n_per_image);
+  YNB_COUNT_LAUNCH();
+  return cudaGetLastError();
+}
+
+// =====================================================================================
 // Depthwise 3x3, pad 1, stride 1|2, + bias (+ activation).  NHWC, 4 channels per thread
 // with 16-byte loads; consecutive threads take consecutive channel groups of one pixel,
 // so a warp reads whole 128-byte lines.  (backbone/shufflenetv2.py:66-67; heads

@@ -1315,6 +1315,27 @@ YNB_EXPORT int ynb_preprocess_u8(ynb_engine* e, const uint8_t* img_dev, const in
   return YNB_OK;
 }
 
+static_assert(sizeof(ynb_image_desc) == sizeof(ImageDesc), "ynb_image_desc and the kernel's ImageDesc must agree");
+
+YNB_EXPORT int ynb_preprocess_letterbox_u8(ynb_engine* e, const uint8_t* src_dev, const ynb_image_desc* descs_dev,
+                                           int32_t batch, float* x_dev, void* stream) {
+  if (!e || !src_dev || !descs_dev || !x_dev || batch <= 0) return fail(e, YNB_ERR_INVALID, "null argument");
+  CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+  cudaError_t r = launch_letterbox_preprocess(src_dev, reinterpret_cast<const ImageDesc*>(descs_dev), x_dev, e->d_prelut,
+                                              batch, e->S, (cudaStream_t)stream);
+  if (r != cudaSuccess) return fail(e, YNB_ERR_CUDA, std::string("letterbox_preprocess: ") + cudaGetErrorString(r));
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_map_boxes(float* boxes_dev, const int32_t* counts_dev, const double* maps_dev, int32_t batch,
+                             int64_t n_per_image, void* stream) {
+  if (!boxes_dev || !counts_dev || !maps_dev || batch <= 0 || n_per_image <= 0)
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_map_boxes: bad arguments");
+  cudaError_t r = launch_map_boxes(boxes_dev, counts_dev, maps_dev, batch, n_per_image, (cudaStream_t)stream);
+  if (r != cudaSuccess) return fail(nullptr, YNB_ERR_CUDA, std::string("map_boxes: ") + cudaGetErrorString(r));
+  return YNB_OK;
+}
+
 YNB_EXPORT int ynb_wait_host(ynb_engine* e, int32_t slot_id) {
   if (!e || slot_id < 0 || slot_id > 1) return fail(e, YNB_ERR_INVALID, "bad slot");
   ynb_engine::HostSlot& sl = e->slot[slot_id];

@@ -259,6 +259,70 @@ class Engine:
                                                _ptr(x), _stream_ptr(self.device)), "ynb_preprocess_u8")
         return x
 
+    @staticmethod
+    def letterbox_desc(h0: int, w0: int, size: int):
+        """Geometry of the reference's Resize (data/transforms.py:73-119) for one image: (nw, nh, left, top, mode,
+        scale_x, scale_y) and the evaluators' (scale[4], offset[4]) as float64 — the same Python expressions."""
+        if h0 > w0:
+            nw, nh = int(w0 / h0 * size), size
+            left, top = (nh - nw) // 2, 0
+            offset, scale = [left / nh, 0., left / nh, 0.], [nw / nh, 1., nw / nh, 1.]
+        elif h0 < w0:
+            nw, nh = size, int(h0 / w0 * size)
+            left, top = 0, (nw - nh) // 2
+            offset, scale = [0., top / nw, 0., top / nw], [1., nh / nw, 1., nh / nw]
+        else:
+            nw, nh, left, top = size, size, 0, 0
+            offset, scale = [0., 0., 0., 0.], [1., 1., 1., 1.]
+        if nw < 1 or nh < 1:
+            raise EngineError(f"image {h0}x{w0} collapses at size {size}")
+        sx, sy = 1.0 / (nw / w0), 1.0 / (nh / h0)
+        eps = 2.220446049250313e-16
+        mode = 0 if (h0 == w0 == size) else (2 if abs(sx - 2) < eps and abs(sy - 2) < eps else 1)
+        return nw, nh, left, top, mode, sx, sy, scale, offset
+
+    def preprocess_images(self, images):
+        """ValTransforms (letterbox Resize + Normalize + ToTensor) of a list of uint8 BGR HWC arrays of ANY shapes, on
+        the device in one launch: returns (x float32 [B,3,S,S], maps float64 [B,12] = offset, scale, size for
+        `map_boxes`).  Bit-identical to the reference transform (cv2 bilinear restated)."""
+        import numpy as np
+        s = self.input_size
+        descs = np.zeros(len(images), dtype=np.dtype([("offset", "<i8"), ("h0", "<i4"), ("w0", "<i4"), ("nw", "<i4"),
+                                                      ("nh", "<i4"), ("left", "<i4"), ("top", "<i4"), ("mode", "<i4"),
+                                                      ("reserved", "<i4"), ("sx", "<f8"), ("sy", "<f8")]))
+        maps = np.zeros((len(images), 12), dtype=np.float64)
+        off = 0
+        for i, im in enumerate(images):
+            if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
+                raise EngineError("preprocess_images wants uint8 [H,W,3] BGR arrays")
+            h0, w0 = int(im.shape[0]), int(im.shape[1])
+            nw, nh, left, top, mode, sx, sy, scale, offset = self.letterbox_desc(h0, w0, s)
+            descs[i] = (off, h0, w0, nw, nh, left, top, mode, 0, sx, sy)
+            maps[i, 0:4], maps[i, 4:8], maps[i, 8:12] = offset, scale, [w0, h0, w0, h0]
+            off += (h0 * w0 * 3 + 15) // 16 * 16
+        packed = torch.empty(off, dtype=torch.uint8).pin_memory()
+        pk = packed.numpy()
+        for i, im in enumerate(images):
+            o = int(descs[i]["offset"])
+            pk[o:o + im.size] = np.ascontiguousarray(im).reshape(-1)
+        src = packed.to(self.device, non_blocking=True)
+        d_desc = torch.from_numpy(descs.view(np.uint8).reshape(-1)).to(self.device)
+        x = torch.empty((len(images), 3, s, s), dtype=torch.float32, device=self.device)
+        self._check(self.lib.ynb_preprocess_letterbox_u8(self._h, _ptr(src), _ptr(d_desc), len(images), _ptr(x),
+                                                         _stream_ptr(self.device)), "ynb_preprocess_letterbox_u8")
+        return x, torch.from_numpy(maps).to(self.device)
+
+    def map_boxes(self, boxes: torch.Tensor, counts: torch.Tensor, maps: torch.Tensor):
+        """In place: boxes [B,N,4] (normalised, NMS output) -> original image pixels, rows [0, counts[b])
+        (evaluator/cocoapi_evaluator.py:85-87)."""
+        if not (boxes.is_cuda and boxes.dtype == torch.float32 and boxes.is_contiguous() and boxes.dim() == 3
+                and maps.is_cuda and maps.dtype == torch.float64 and tuple(maps.shape) == (boxes.shape[0], 12)
+                and counts.is_cuda and counts.dtype == torch.int32):
+            raise EngineError("map_boxes wants boxes f32 [B,N,4], counts i32 [B], maps f64 [B,12] on the GPU")
+        self._check(self.lib.ynb_map_boxes(_ptr(boxes), _ptr(counts), _ptr(maps.contiguous()), boxes.shape[0],
+                                           boxes.shape[1], _stream_ptr(self.device)), "ynb_map_boxes")
+        return boxes
+
     def set_normalization(self, mean_bgr, std_bgr):
         m = (C.c_float * 3)(*[float(v) for v in mean_bgr])
         sd = (C.c_float * 3)(*[float(v) for v in std_bgr])

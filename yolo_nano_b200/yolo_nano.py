@@ -342,6 +342,23 @@ class YOLONano(nn.Module):
                         cls[i, :k].numpy().astype(np.int64)))
         return res
 
+    def detect_raw_images(self, images) -> List[Tuple[np.ndarray, np.ndarray, np.ndarray]]:
+        """The evaluators' per-image loop (evaluator/cocoapi_evaluator.py:70-87, vocapi_evaluator.py) for a list of
+        ORIGINAL uint8 BGR images of any shapes: ValTransforms (letterbox resize + normalisation) on the device, the
+        detector, and the inverse box mapping `bboxes = (bboxes - offset) / scale * [w, h, w, h]` on the NMS output —
+        returns boxes in pixels of each original image."""
+        nb = len(images)
+        eng = self.engine(nb)
+        x, maps = eng.preprocess_images(images)
+        boxes, scores, cls, counts = eng.forward_detect(x)
+        eng.map_boxes(boxes, counts, maps)
+        counts_h = counts.cpu().numpy()
+        kmax = int(counts_h.max()) if nb else 0
+        bh, sh, ch = boxes[:, :kmax].cpu().numpy(), scores[:, :kmax].cpu().numpy(), cls[:, :kmax].cpu().numpy()
+        return [(np.array(bh[b, :int(counts_h[b])], dtype=np.float32, copy=True),
+                 np.array(sh[b, :int(counts_h[b])], dtype=np.float32, copy=True),
+                 ch[b, :int(counts_h[b])].astype(np.int64)) for b in range(nb)]
+
     def forward(self, x, target=None):
         if self.trainable:
             # training branch (models/yolo_nano.py:333-358).  Built for BatchNorm in eval mode (running
