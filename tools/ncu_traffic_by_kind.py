@@ -38,12 +38,17 @@ def read_launches(path):
             continue
         d = dict(zip(hdr, r))
         lid = int(d["ID"])
-        e = launches.setdefault(lid, {"name": d["Kernel Name"], "dram": 0.0, "time_s": 0.0})
-        v = float(d["Metric Value"].replace(",", "")) * UNIT.get(d["Metric Unit"], 1.0)
+        e = launches.setdefault(lid, {"name": d["Kernel Name"], "dram": 0.0, "time_s": 0.0, "pct": {}})
+        try:
+            v = float(d["Metric Value"].replace(",", "")) * UNIT.get(d["Metric Unit"], 1.0)
+        except ValueError:
+            continue
         if d["Metric Name"].startswith("dram__bytes"):
             e["dram"] += v
         elif d["Metric Name"].startswith("gpu__time_duration"):
             e["time_s"] += v
+        elif d["Metric Unit"] == "%":
+            e["pct"][d["Metric Name"]] = v
     return [launches[k] for k in sorted(launches)]
 
 
@@ -63,12 +68,14 @@ def main():
                 if not got:
                     ok = False
                     break
-                rows.append((name, kind, sum(g["dram"] for g in got), sum(g["time_s"] for g in got), len(got)))
+                tt = sum(g["time_s"] for g in got) or 1.0
+                pct = {k: sum(g["pct"].get(k, 0.0) * g["time_s"] for g in got) / tt for k in got[0]["pct"]}
+                rows.append((name, kind, sum(g["dram"] for g in got), sum(g["time_s"] for g in got), len(got), pct))
                 continue
             if i >= len(launches) or want not in launches[i]["name"]:
                 ok = False
                 break
-            rows.append((name, kind, launches[i]["dram"], launches[i]["time_s"], 1))
+            rows.append((name, kind, launches[i]["dram"], launches[i]["time_s"], 1, launches[i]["pct"]))
             i += 1
         if ok:
             forwards.append(rows)
@@ -77,14 +84,17 @@ def main():
     use = forwards[1:] if len(forwards) > 1 else forwards
     per_kind, total_t = {}, 0.0
     for rows in use:
-        for name, kind, dram, t, n in rows:
-            d = per_kind.setdefault(kind, {"dram": 0.0, "time_s": 0.0, "launches": 0, "kernels": 0})
+        for name, kind, dram, t, n, pct in rows:
+            d = per_kind.setdefault(kind, {"dram": 0.0, "time_s": 0.0, "launches": 0, "kernels": 0, "pct": {}})
             d["dram"] += dram; d["time_s"] += t; d["launches"] += 1; d["kernels"] += n
+            for k, v in pct.items():
+                d["pct"][k] = d["pct"].get(k, 0.0) + v * t          # time-weighted
             total_t += t
     out = {"source": sys.argv[1], "forwards_captured": len(forwards), "forwards_used": len(use),
            "note": "per-launch ncu times are cold-cache and serialised: compare SHARES with the CUDA-event numbers",
            "per_kind": {k: {"dram_bytes_per_launch": v["dram"] / v["launches"], "dram_bytes_per_step": v["dram"] / len(use),
-                            "launches_per_step": v["launches"] / len(use), "time_share": v["time_s"] / total_t}
+                            "launches_per_step": v["launches"] / len(use), "time_share": v["time_s"] / total_t,
+                            "pct_time_weighted": {k: round(x / v["time_s"], 2) for k, x in sorted(v["pct"].items())}}
                         for k, v in sorted(per_kind.items())},
            "dram_bytes_per_step": sum(v["dram"] for v in per_kind.values()) / len(use)}
     json.dump(out, open(sys.argv[3], "w"), indent=1)

@@ -75,6 +75,9 @@ struct TcGemmParams {
                           // not issued: K = 116 needs 15 of 16, K = 232 29 of 32, K = 24 3 of 4); 0 = all
   int presplit;           // parity mode, 3x3: A arrives as two planes (hi, lo) written by the producer kernel —
                           // two TMA boxes per step, no splitter pass (tmAlo)
+  int a2_step;            // pointwise, > 0: K steps [a2_step, num_steps) read a SECOND activation tensor (tmAlo) — the
+                          // two branches of a stride-2 ShuffleNetV2 unit concatenated along K against block-diagonal,
+                          // row-interleaved weights: torch.cat + channel_shuffle as one plain GEMM output
   int stack_b;            // parity mode, nmain = 1, 2*Npad <= 256: a_hi x [b_hi; b_lo] as ONE MMA of N = 2*Npad
                           // into [main | corr] (the planes are adjacent in smem and in TMEM): 2 MMAs per
                           // K-step instead of 3, a_hi and b_hi are fetched once less
@@ -197,7 +200,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == kTcProducerWarp && lane == 0) {
     ptx::prefetch_tmap(&tmA);
-    if (p.presplit) ptx::prefetch_tmap(&tmAlo);
+    if (p.presplit || p.a2_step > 0) ptx::prefetch_tmap(&tmAlo);
     ptx::prefetch_tmap(&tmWhi);
     if (split) ptx::prefetch_tmap(&tmWlo);
     if (p.tma_store) ptx::prefetch_tmap(&tmOut);
@@ -283,7 +286,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (do_a) ptx::tma_load_4d(stage_a(s), &tmA, &full[s], kc * kchunk, x0 + dx - 1, y0 + dy - 1, b);
             if (do_alo) ptx::tma_load_4d(stage_alo(s), &tmAlo, &full[s], kc * kchunk, x0 + dx - 1, y0 + dy - 1, b);
           } else {
-            if (do_a) ptx::tma_load_2d(stage_a(s), &tmA, &full[s], st * kchunk, (int)(tile * kTcBM));
+            if (do_a) {
+              const bool second = p.a2_step > 0 && st >= p.a2_step;
+              ptx::tma_load_2d(stage_a(s), second ? &tmAlo : &tmA, &full[s], (second ? st - p.a2_step : st) * kchunk,
+                               (int)(tile * kTcBM));
+            }
           }
           if (do_whi) ptx::tma_load_2d(w_hi_ptr(s, st), &tmWhi, &full[s], st * kchunk, 0);
           if (do_wlo) ptx::tma_load_2d(w_lo_ptr(s, st), &tmWlo, &full[s], st * kchunk, 0);
@@ -321,29 +328,38 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t b_hi = ptx::smem_u32(w_hi_ptr(s, st));
           const uint32_t b_lo = ptx::smem_u32(w_lo_ptr(s, st));
           const int nk = p.ksub > 0 ? min(kTcBK / 8, p.ksub - st * (kTcBK / 8)) : kTcBK / 8;
+          // one code path per arithmetic mode (the issue loop is latency-critical: no per-MMA mode tests)
+          if (p.bf16_in) {
 #pragma unroll
-          for (int k = 0; k < kTcBK / 8; ++k, ++t) {
-            if (k >= nk) break;
-            const uint32_t ko = k * 32;   // 8 tf32 = 32 bytes inside the 128-byte swizzled row
-            const uint64_t da = ptx::make_sw128_kmajor_desc(a_hi + ko);
-            const uint64_t db = ptx::make_sw128_kmajor_desc(b_hi + ko);
-            const int slot = t % p.nmain;
-            if (p.bf16_in) {
-              ptx::mma_bf16_ss(d_tmem, da, db, idesc_bf, t != 0);
-              continue;
+            for (int k = 0; k < kTcBK / 8; ++k, ++t) {
+              if (k >= nk) break;
+              ptx::mma_bf16_ss(d_tmem, ptx::make_sw128_kmajor_desc(a_hi + k * 32), ptx::make_sw128_kmajor_desc(b_hi + k * 32),
+                               idesc_bf, t != 0);
             }
-            if (p.stack_b) {
+          } else if (p.stack_b) {
+#pragma unroll
+            for (int k = 0; k < kTcBK / 8; ++k, ++t) {
+              if (k >= nk) break;
+              const uint64_t db = ptx::make_sw128_kmajor_desc(b_hi + k * 32);
               // [main | corr] (+)= a_hi x [b_hi; b_lo]   then   corr += a_lo x b_hi
-              ptx::mma_tf32_ss(d_tmem, da, db, idesc2, t != 0);
-              ptx::mma_tf32_ss(c_tmem, ptx::make_sw128_kmajor_desc(a_lo + ko), db, idesc, 1);
-              continue;
+              ptx::mma_tf32_ss(d_tmem, ptx::make_sw128_kmajor_desc(a_hi + k * 32), db, idesc2, t != 0);
+              ptx::mma_tf32_ss(c_tmem, ptx::make_sw128_kmajor_desc(a_lo + k * 32), db, idesc, 1);
             }
-            if (split) {
-              ptx::mma_tf32_ss(c_tmem, ptx::make_sw128_kmajor_desc(a_lo + ko), db, idesc, t != 0);
-              ptx::mma_tf32_ss(c_tmem, da, ptx::make_sw128_kmajor_desc(b_lo + ko), idesc, 1);
+          } else {
+#pragma unroll
+            for (int k = 0; k < kTcBK / 8; ++k, ++t) {
+              if (k >= nk) break;
+              const uint32_t ko = k * 32;   // 8 tf32 = 32 bytes inside the 128-byte swizzled row
+              const uint64_t da = ptx::make_sw128_kmajor_desc(a_hi + ko);
+              const uint64_t db = ptx::make_sw128_kmajor_desc(b_hi + ko);
+              const int slot = t % p.nmain;
+              if (split) {
+                ptx::mma_tf32_ss(c_tmem, ptx::make_sw128_kmajor_desc(a_lo + ko), db, idesc, t != 0);
+                ptx::mma_tf32_ss(c_tmem, da, ptx::make_sw128_kmajor_desc(b_lo + ko), idesc, 1);
+              }
+              ptx::mma_tf32_ss(d_tmem + (uint32_t)(slot * p.Npad), da, db, idesc,
+                               (split && p.merge_corr) ? 1 : (t >= p.nmain));
             }
-            ptx::mma_tf32_ss(d_tmem + (uint32_t)(slot * p.Npad), da, db, idesc,
-                             (split && p.merge_corr) ? 1 : (t >= p.nmain));
           }
           YNB_TRACE(3, tile, st);
           ptx::mma_commit(&empty[s]);                       // frees the smem stage when the MMAs retire
@@ -841,7 +857,7 @@ struct TcGemmLaunch {
   CUtensorMap tmA;
   CUtensorMap tmOut;      // valid when p.tma_store
   const TcWeights* w = nullptr;
-  CUtensorMap tmAlo;      // lo plane of A (presplit)
+  CUtensorMap tmAlo;      // lo plane of A (presplit) | second activation tensor (a2_step > 0)
   TcGemmParams p;
   uint32_t smem = 0;
   unsigned grid = 0;
@@ -929,7 +945,7 @@ inline cudaError_t launch_tc_gemm(const TcGemmLaunch& L, cudaStream_t st) {
   }
   const CUtensorMap& tmo = L.p.tma_store ? L.tmOut : L.tmA;   // unused unless tma_store
   KernelT kern = L.dec_classes == 80 ? kernels[2] : (L.dec_classes == 20 ? kernels[3] : kernels[L.p.pass != nullptr ? 1 : 0]);
-  const CUtensorMap& tmalo = L.p.presplit ? L.tmAlo : L.tmA;   // unused unless presplit
+  const CUtensorMap& tmalo = (L.p.presplit || L.p.a2_step > 0) ? L.tmAlo : L.tmA;   // unused otherwise
   cudaError_t r = launch_pdl(kern, dim3(L.grid), dim3(kTcThreads), (size_t)L.smem, st, L.tmA, tmalo, L.w->tm_hi,
                              L.w->tm_lo, tmo, L.p);
   YNB_COUNT_LAUNCH();

@@ -142,10 +142,10 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
     if (p.pass_blocks) ptx::prefetch_tmap(&tmPass);
     for (int s = 0; s < kDpMaxRawStages; ++s) {
       ptx::mbar_init(&raw_full[s], 1);
-      ptx::mbar_init(&raw_empty[s], kDpDwWarps);
+      ptx::mbar_init(&raw_empty[s], kBf16 ? kDpDwWarps : kDpDwWarps / 2);   // the warps of ONE producer group
     }
     for (int s = 0; s < kDpMaxAStages; ++s) {
-      ptx::mbar_init(&a_ready[s], kDpDwWarps);
+      ptx::mbar_init(&a_ready[s], kBf16 ? kDpDwWarps : kDpDwWarps / 2);
       ptx::mbar_init(&a_empty[s], 1);
       ptx::mbar_init(&w_full[s], 1);
     }
@@ -202,6 +202,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
         const int rr = (int)(tile - (int64_t)b * per_img);
         const int y0 = (rr / p.tiles_x) * TH, x0 = (rr % p.tiles_x) * TW;
         // the pass-through half of this tile is read by the epilogue a few microseconds from now: pull it into L2
+#pragma unroll 1
         for (int cb = 0; cb < p.pass_blocks; ++cb) ptx::tma_prefetch_4d(&tmPass, cb * CH, x0, y0, b);
         // A TMA box takes ~4 k cycles from issue to landing when it comes from HBM (measured, tools/gpu_dp_trace.py)
         // and only raw_stages x 26 KB fit in flight: the HBM rate would be latency-bound.  Pull the tile this CTA
@@ -212,6 +213,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
             const int bp = (int)(tp / per_img);
             const int rp = (int)(tp - (int64_t)bp * per_img);
             const int yp = (rp / p.tiles_x) * TH, xp = (rp % p.tiles_x) * TW;
+#pragma unroll 1
             for (int kc = 0; kc < p.num_chunks; ++kc) ptx::tma_prefetch_4d(&tmIn, kc * CH, xp - 1, yp - 1, bp);
           }
         }
@@ -297,32 +299,40 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
       }
     }
   } else if (warp >= kDpDwWarp0 && warp < kDpDwWarp0 + kDpDwWarps) {
-    // ================= depthwise producers: thread = (1x4 output strip, 4 channels) =================
-    // 32 strips x CGS channel groups per chunk = 256 (float) | 512 (bf16) tasks for 256 threads; a thread's
-    // channel group is the same in every round, so its taps are read once per chunk.
-    const int t = threadIdx.x - kDpDwWarp0 * 32;          // 0..255
+    // ================= depthwise producers: thread = (2x4 output block, 4 channels) =================
+    // A chunk is 16 two-row blocks x CGS channel groups = 128 (float) | 256 (bf16) tasks.  bf16: all eight warps work
+    // on one chunk.  float: warps 8-11 take the even chunks of this CTA's chunk sequence and warps 12-15 the odd
+    // ones — two raw stages are consumed concurrently — so that every thread still owns a two-row block (the rows
+    // share two of their three input rows: 24 + 9 shared-memory reads per 8 outputs instead of 2 x (18 + 9); the
+    // kernel is bound by the shared-memory pipe, tools/gpu_dp_trace.py + ncu l1tex 70 %).
+    constexpr int NGROUPS = kBf16 ? 1 : 2;
+    constexpr int GTHREADS = 256 / NGROUPS;
+    const int t = (threadIdx.x - kDpDwWarp0 * 32) % GTHREADS;
+    const int grp = (threadIdx.x - kDpDwWarp0 * 32) / GTHREADS;
     const int cg = t & (CGS - 1);
     const int IW = TW + 2;
     const bool has_act = p.dw_act != YNB_ACT_NONE;
     const float slope = p.dw_act == YNB_ACT_RELU ? 0.0f : 0.1f;
-    int r = 0, s = 0;
-    uint32_t rph = 0, sph = 0;
+    const int nloc = (int64_t)blockIdx.x < p.num_tiles
+                         ? (int)((p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;   // tiles of this CTA
+    const int total_chunks = nloc * p.num_chunks;
     bool ok = true;
-    for (int64_t tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
-      for (int kc = 0; kc < p.num_chunks; ++kc) {
+    {
+      for (int gc = grp; gc < total_chunks && ok; gc += NGROUPS) {
+        const int lt_ = gc / p.num_chunks, kc = gc - lt_ * p.num_chunks;
+        const int r = gc % p.raw_stages, s = gc % p.a_stages;
+        const uint32_t rph = (uint32_t)((gc / p.raw_stages) & 1), sph = (uint32_t)((gc / p.a_stages) & 1);
         const float* wv = s_dww + kc * CH + cg * 4;        // this thread's taps: read per filter row (3 x 16 B, broadcast)
         const float4 bv = *reinterpret_cast<const float4*>(wv + 9 * KC);
         ok = ptx::mbar_wait(&raw_full[r], rph, p.err_flag, 7);
         if (ok) ok = ptx::mbar_wait(&a_empty[s], sph ^ 1, p.err_flag, 8);
         if (!ok) break;
-        if (t == 0) YNB_DP_TRACE(1, (int)((tile - blockIdx.x) / gridDim.x), kc);
+        if (t == 0) YNB_DP_TRACE(1, lt_, kc);
         const uint8_t* raw = smem + (size_t)r * lay.raw_stride;
         uint8_t* a_hi = a_stage(s);
         uint8_t* a_lo = a_hi + kTcAStageBytes;
-        // one block of ROWS x 4 output pixels per thread: 32 strips x 8 groups (float) or 16 two-row blocks x 16 groups
-        // (bf16: the two rows share two of their three input rows — 24 instead of 36 tile reads)
-        constexpr int ROWS = CGS / 8;
-        const int bidx = t / CGS;
+        constexpr int ROWS = 2;
+        const int bidx = t / CGS;                          // 0..15
         const int nsx = TW >> 2;
         const int sx = bidx % nsx, sy = (bidx / nsx) * ROWS;
         float4 acc[ROWS][4];
@@ -392,9 +402,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
         ptx::fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&a_ready[s]);
-        if (t == 0) YNB_DP_TRACE(2, (int)((tile - blockIdx.x) / gridDim.x), kc);
-        if (++r == p.raw_stages) { r = 0; rph ^= 1; }
-        if (++s == p.a_stages) { s = 0; sph ^= 1; }
+        if (t == 0) YNB_DP_TRACE(2, lt_, kc);
       }
     }
   } else if (warp < kDpEpiWarps) {
@@ -632,7 +640,7 @@ inline bool plan_dwpw(DwPwLaunch& L, const void* in, int in_ld, int B, int H, in
     }
   if (!found) return false;
   {
-    static const int pf = getenv("YNB_DP_PREFETCH") ? atoi(getenv("YNB_DP_PREFETCH")) : 2;
+    static const int pf = getenv("YNB_DP_PREFETCH") ? atoi(getenv("YNB_DP_PREFETCH")) : 0;   // measured: no gain
     p.prefetch_tiles = pf;
   }
   const int epc = 16 / es;                // elements per 16 bytes

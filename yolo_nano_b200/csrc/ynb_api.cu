@@ -100,6 +100,10 @@ struct ynb_engine {
   std::vector<ConvSpec> table;
   std::map<std::string, int> index;
   std::vector<PackedConv> convs;
+  // merged (branch1.2 | branch2.5) pointwise convs of the three stride-2 units, split along N when wider than one
+  // MMA tile: cat[stage][part]; K = [branch1 dw output | branch2 dw output], rows = interleaved output slots
+  struct CatConv { PackedConv pc; int n0 = 0, k1p = 0, k2p = 0; };
+  std::vector<CatConv> cat[3];
   StemWeights stem_w;                      // folded stem weights, passed as a kernel parameter
   PreLut prelut;                           // uint8 -> normalised float32 table (ynb_set_normalization)
   PreLut* d_prelut = nullptr;              // its device copy
@@ -224,6 +228,101 @@ InLayout in_layout(const ConvSpec& c, bool bf) {
 }
 
 // ---- weight packing ----------------------------------------------------------------------
+// Packs a dense [n][ktot] fp32 matrix (ktot = taps x kin) for the tensor-core path of the engine's mode:
+//   fp32 modes: [Npad][Kpad] split into exact-tf32 hi and lo planes, K chunks of 32;
+//   bf16 mode : ONE plane of bf16 (round to nearest even), K chunks of 64; a 3x3 conv pads every tap to whole chunks
+//               ([N][tap][128] for 96 channels) so that a K step never straddles two taps.
+int pack_tc_matrix(ynb_engine* e, TcWeights& t, const float* w, int n, int ktot, int taps, const std::string& name) {
+  const bool bf = is_bf16(e);
+  t.N = n;
+  t.Npad = round_up(n, 16);
+  if (t.hi) cudaFree(t.hi);
+  if (t.lo) cudaFree(t.lo);
+  if (t.bw) cudaFree(t.bw);
+  t.hi = t.lo = nullptr; t.bw = nullptr;
+  if (bf) {
+    const int kin = ktot / taps, kin_pad = round_up(kin, 64);
+    t.Kpad = taps * kin_pad;
+    std::vector<bf16> bw((size_t)t.Npad * t.Kpad, __float2bfloat16(0.0f));
+    for (int r = 0; r < n; ++r)
+      for (int tp = 0; tp < taps; ++tp)
+        for (int k = 0; k < kin; ++k)
+          bw[(size_t)r * t.Kpad + (size_t)tp * kin_pad + k] = __float2bfloat16_rn(w[(size_t)r * ktot + (size_t)tp * kin + k]);
+    CUDA_TRY(e, cudaMalloc(&t.bw, bw.size() * 2));
+    CUDA_TRY(e, cudaMemcpy(t.bw, bw.data(), bw.size() * 2, cudaMemcpyHostToDevice));
+    if (!make_tmap_2d(&t.tm_hi, t.bw, t.Kpad, t.Npad, t.Kpad, t.Npad, true))
+      return fail(e, YNB_ERR_CUDA, "cuTensorMapEncodeTiled failed for weights of " + name);
+    t.tm_lo = t.tm_hi;
+    return YNB_OK;
+  }
+  t.Kpad = round_up(ktot, kTcBK);
+  std::vector<float> hi((size_t)t.Npad * t.Kpad, 0.f), lo((size_t)t.Npad * t.Kpad, 0.f);
+  for (int r = 0; r < n; ++r)
+    for (int k = 0; k < ktot; ++k)
+      split_tf32_host(w[(size_t)r * ktot + k], &hi[(size_t)r * t.Kpad + k], &lo[(size_t)r * t.Kpad + k]);
+  CUDA_TRY(e, cudaMalloc(&t.hi, hi.size() * 4));
+  CUDA_TRY(e, cudaMalloc(&t.lo, lo.size() * 4));
+  CUDA_TRY(e, cudaMemcpy(t.hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(e, cudaMemcpy(t.lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice));
+  if (!make_tmap_2d(&t.tm_hi, t.hi, t.Kpad, t.Npad, t.Kpad, t.Npad) ||
+      !make_tmap_2d(&t.tm_lo, t.lo, t.Kpad, t.Npad, t.Kpad, t.Npad))
+    return fail(e, YNB_ERR_CUDA, "cuTensorMapEncodeTiled failed for weights of " + name);
+  return YNB_OK;
+}
+
+// The two output branches of a stride-2 ShuffleNetV2 unit as ONE pointwise conv (backbone/shufflenetv2.py:43-49,
+// 57-63, 73-76): A = [branch1 dw output | branch2 dw output] concatenated along K (each padded to whole K chunks),
+// weights block-diagonal with the rows interleaved the way channel_shuffle interleaves the branches:
+//   row slot(2i)   = [ W_branch1.2[i] | 0 ],   row slot(2i+1) = [ 0 | W_branch2.5[i] ]      (+ zero rows on pad slots)
+// so that torch.cat + channel_shuffle is the GEMM's plain dense output (TMA-store epilogue) instead of two launches
+// with 4-byte scattered stores.  Wider than one MMA tile (stage 4: 464 columns) -> split along N.
+int pack_cat(ynb_engine* e, int si) {
+  const bool bf = is_bf16(e);
+  const std::string bk = "backbone.stage" + std::to_string(si + 2) + ".0.";
+  const int i1 = e->index.at(bk + "branch1.2"), i2 = e->index.at(bk + "branch2.5");
+  const ConvSpec& c1 = e->table[i1];
+  const ConvSpec& c2 = e->table[i2];
+  const PackedConv& p1 = e->convs[i1];
+  const PackedConv& p2 = e->convs[i2];
+  const InLayout il1 = in_layout(c1, bf), il2 = in_layout(c2, bf);
+  const StageLayout sl = stage_layout(bf, si);
+  const int ch = bf ? 64 : kTcBK;
+  const int k1p = round_up(il1.ktot, ch), k2p = round_up(il2.ktot, ch), ktot = k1p + k2p;
+  const int h = c1.cout;
+  std::vector<float> w((size_t)sl.ld * ktot, 0.f), b((size_t)sl.ld, 0.f);
+  for (int i = 0; i < h; ++i) {
+    const int r1 = sl.map.slot(2 * i), r2 = sl.map.slot(2 * i + 1);
+    for (int k = 0; k < c1.cin; ++k) w[(size_t)r1 * ktot + il1.map.slot(k)] = p1.w_host[(size_t)i * c1.cin + k];
+    for (int k = 0; k < c2.cin; ++k) w[(size_t)r2 * ktot + k1p + il2.map.slot(k)] = p2.w_host[(size_t)i * c2.cin + k];
+    b[r1] = p1.b_host[i];
+    b[r2] = p2.b_host[i];
+  }
+  const int parts = (sl.ld + 239) / 240;                    // N <= 240 per launch (TMEM: 2 x 240 columns in parity mode)
+  const int npart = round_up((sl.ld + parts - 1) / parts, bf ? 8 : 4);
+  for (auto& cc : e->cat[si]) {
+    if (cc.pc.b_dev) cudaFree(cc.pc.b_dev);
+    if (cc.pc.tc.hi) cudaFree(cc.pc.tc.hi);
+    if (cc.pc.tc.lo) cudaFree(cc.pc.tc.lo);
+    if (cc.pc.tc.bw) cudaFree(cc.pc.tc.bw);
+  }
+  e->cat[si].clear();
+  e->cat[si].resize(parts);
+  for (int pi = 0; pi < parts; ++pi) {
+    ynb_engine::CatConv& cc = e->cat[si][pi];
+    cc.n0 = pi * npart;
+    const int n = std::min(npart, sl.ld - cc.n0);
+    cc.k1p = k1p; cc.k2p = k2p;
+    cc.pc.n = n; cc.pc.ktot = ktot; cc.pc.loaded = true;
+    CUDA_TRY(e, cudaMalloc(&cc.pc.b_dev, round_up(n, 4) * 4));
+    CUDA_TRY(e, cudaMemset(cc.pc.b_dev, 0, round_up(n, 4) * 4));
+    CUDA_TRY(e, cudaMemcpy(cc.pc.b_dev, b.data() + cc.n0, n * 4, cudaMemcpyHostToDevice));
+    // the K blocks are already padded to whole chunks: pack as ONE tap of width ktot
+    int rc = pack_tc_matrix(e, cc.pc.tc, w.data() + (size_t)cc.n0 * ktot, n, ktot, 1, bk + "cat");
+    if (rc) return rc;
+  }
+  return YNB_OK;
+}
+
 int pack_conv(ynb_engine* e, int i) {
   const ConvSpec& c = e->table[i];
   PackedConv& pc = e->convs[i];
@@ -274,46 +373,9 @@ int pack_conv(ynb_engine* e, int i) {
   CUDA_TRY(e, cudaMemcpy(pc.b_dev, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
 
   // tensor-core layout for the dense contractions (not the stem: K = 27 is HBM-bound)
-  if (bf && ((c.kind == kPw1x1) || (c.kind == kDense3x3 && c.cin != 3))) {
-    // bf16 mode: ONE plane [Npad][Kpad] of bf16 (round to nearest even), K in chunks of 64; a 3x3 conv pads every
-    // tap to whole chunks ([N][tap][128] for 96 channels) so that a K step never straddles two taps
-    TcWeights& t = pc.tc;
-    t.N = pc.n;
-    t.Npad = round_up(pc.n, 16);
-    const int taps = c.kind == kDense3x3 ? 9 : 1;
-    const int kin = pc.ktot / taps, kin_pad = round_up(kin, 64);
-    t.Kpad = taps * kin_pad;
-    std::vector<bf16> bw((size_t)t.Npad * t.Kpad, __float2bfloat16(0.0f));
-    for (int n = 0; n < pc.n; ++n)
-      for (int tp = 0; tp < taps; ++tp)
-        for (int k = 0; k < kin; ++k)
-          bw[(size_t)n * t.Kpad + (size_t)tp * kin_pad + k] = __float2bfloat16_rn(w[(size_t)n * pc.ktot + (size_t)tp * kin + k]);
-    if (t.bw) cudaFree(t.bw);
-    t.bw = nullptr;
-    CUDA_TRY(e, cudaMalloc(&t.bw, bw.size() * 2));
-    CUDA_TRY(e, cudaMemcpy(t.bw, bw.data(), bw.size() * 2, cudaMemcpyHostToDevice));
-    if (!make_tmap_2d(&t.tm_hi, t.bw, t.Kpad, t.Npad, t.Kpad, t.Npad, true))
-      return fail(e, YNB_ERR_CUDA, "cuTensorMapEncodeTiled failed for weights of " + c.name);
-    t.tm_lo = t.tm_hi;
-  } else if ((c.kind == kPw1x1) || (c.kind == kDense3x3 && c.cin != 3)) {
-    TcWeights& t = pc.tc;
-    t.N = pc.n;
-    t.Npad = round_up(pc.n, 16);
-    t.Kpad = round_up(pc.ktot, kTcBK);
-    std::vector<float> hi((size_t)t.Npad * t.Kpad, 0.f), lo((size_t)t.Npad * t.Kpad, 0.f);
-    for (int n = 0; n < pc.n; ++n)
-      for (int k = 0; k < pc.ktot; ++k)
-        split_tf32_host(w[(size_t)n * pc.ktot + k], &hi[(size_t)n * t.Kpad + k], &lo[(size_t)n * t.Kpad + k]);
-    if (t.hi) cudaFree(t.hi);
-    if (t.lo) cudaFree(t.lo);
-    t.hi = t.lo = nullptr;
-    CUDA_TRY(e, cudaMalloc(&t.hi, hi.size() * 4));
-    CUDA_TRY(e, cudaMalloc(&t.lo, lo.size() * 4));
-    CUDA_TRY(e, cudaMemcpy(t.hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice));
-    CUDA_TRY(e, cudaMemcpy(t.lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice));
-    if (!make_tmap_2d(&t.tm_hi, t.hi, t.Kpad, t.Npad, t.Kpad, t.Npad) ||
-        !make_tmap_2d(&t.tm_lo, t.lo, t.Kpad, t.Npad, t.Kpad, t.Npad))
-      return fail(e, YNB_ERR_CUDA, "cuTensorMapEncodeTiled failed for weights of " + c.name);
+  if ((c.kind == kPw1x1) || (c.kind == kDense3x3 && c.cin != 3)) {
+    int rc = pack_tc_matrix(e, pc.tc, w.data(), pc.n, pc.ktot, c.kind == kDense3x3 ? 9 : 1, c.name);
+    if (rc) return rc;
   }
   return YNB_OK;
 }
@@ -556,6 +618,59 @@ struct Planner {
     ops().push_back(op);
   }
 
+  // The two output convs of a stride-2 unit as one GEMM over K = [b1dw | mid2] (pack_cat): plain dense output.
+  // Returns false when the unit keeps its two strided-store GEMMs (FFMA cross-check mode, switched off).
+  bool catpw(int si, const std::string& unit, const Tensor& b1dw, const Tensor& mid2, const Tensor& out) {
+    static const bool off = getenv("YNB_NO_CAT_GEMM") != nullptr;
+    if (off || e->cfg.gemm_mode == YNB_GEMM_FP32_FFMA || e->cat[si].empty()) return false;
+    const bool bf = is_bf16(e);
+    const int64_t M = (int64_t)B * out.H * out.W;
+    const ConvSpec& c1 = spec(unit + "branch1.2");
+    const ConvSpec& c2 = spec(unit + "branch2.5");
+    for (size_t pi = 0; pi < e->cat[si].size(); ++pi) {
+      const ynb_engine::CatConv& cc = e->cat[si][pi];
+      tc->emplace_back();
+      TcGemmLaunch& L = tc->back();
+      L.w = &cc.pc.tc;
+      TcGemmParams& p = L.p;
+      memset(&p, 0, sizeof(p));
+      p.mode = e->cfg.gemm_mode;
+      p.bf16_in = bf ? 1 : 0;
+      p.out_bf16 = out.es == 2 ? 1 : 0;
+      const int ch = bf ? 64 : kTcBK;
+      p.num_steps = cc.pc.tc.Kpad / ch;
+      p.chunks_per_tap = p.num_steps;
+      p.a2_step = cc.k1p / ch;
+      p.ksub = 0;                                   // both K blocks are whole chunks (zero padded)
+      p.M = M;
+      p.num_tiles = (M + kTcBM - 1) / kTcBM;
+      p.N = cc.pc.n; p.Npad = cc.pc.tc.Npad;
+      tc_plan_tmem(p);
+      p.a_box_bytes = kTcAStageBytes;
+      p.out = out.p; p.out_ld = out.ld; p.out_off = cc.n0; p.out_step = 1; p.omap = dense_map();
+      p.bias = cc.pc.b_dev; p.act = c1.act;
+      p.err_flag = e->d_err;
+      p.tma_store = 1;
+      const int oal = 16 / out.es;
+      if (!make_tmap_out(&L.tmOut, out.at(cc.n0), (uint64_t)round_up(cc.pc.n, oal), (uint64_t)M, (uint64_t)out.ld, out.es == 2) ||
+          !make_tmap_2d(&L.tmA, b1dw.p, (uint64_t)b1dw.ld, (uint64_t)M, (uint64_t)b1dw.ld, kTcBM, bf) ||
+          !make_tmap_2d(&L.tmAlo, mid2.p, (uint64_t)mid2.ld, (uint64_t)M, (uint64_t)mid2.ld, kTcBM, bf)) {
+        error = "cuTensorMapEncodeTiled failed for the merged stride-2 conv of " + unit;
+        return true;
+      }
+      if (!tc_plan_smem(L)) { error = "no smem configuration for the merged stride-2 conv of " + unit; return true; }
+      L.grid = (unsigned)std::min<int64_t>(p.num_tiles, kNumSMs);
+      const TcGemmLaunch* Lp = &L;
+      const double frac = (double)cc.pc.n / out.ld;
+      const double bytes = (double)b1dw.es * M * (c1.cin + c2.cin) + (double)out.es * M * 2.0 * c1.cout * frac +
+                           (bf ? 2.0 : 4.0) * (c1.cin + c2.cin) * c1.cout;
+      const double flops = 2.0 * M * (c1.cin + c2.cin) * c1.cout * frac;
+      ops().push_back({unit + "branch1.2|branch2.5" + (e->cat[si].size() > 1 ? "." + std::to_string(pi) : ""), "pw_tcgen05", bytes,
+                       flops, [=](cudaStream_t st) { return launch_tc_gemm(*Lp, st); }});
+    }
+    return true;
+  }
+
   // Fused depthwise 3x3 (stride 1) -> pointwise conv in ONE launch (unit_tc.cuh); `pass` as in pw().
   // Returns false when the pair has to stay unfused (FFMA cross-check mode, shape does not fit, switched off).
   bool dwpw(const std::string& dw_name, const std::string& pw_name, const Tensor& in, const Tensor& out,
@@ -706,10 +821,12 @@ int build_plan(ynb_engine* e, int B, Plan** out) {
     Tensor o0 = P.T(st + ".0");
     P.dw(bk + "0.branch1.0", x, 0, b1dw);
     if (si > 0) plan->net.back().join = true;    // x = previous stage's last unit (side copy pending)
-    P.pw(bk + "0.branch1.2", b1dw, 0, o0, 0, 2);
     P.pw(bk + "0.branch2.0", x, 0, b2pw, 0, 1);
     P.dw(bk + "0.branch2.3", b2pw, 0, mid2);
-    P.pw(bk + "0.branch2.5", mid2, 0, o0, 1, 2);
+    if (!P.catpw(si, bk + "0.", b1dw, mid2, o0)) {
+      P.pw(bk + "0.branch1.2", b1dw, 0, o0, 0, 2);
+      P.pw(bk + "0.branch2.5", mid2, 0, o0, 1, 2);
+    }
     x = o0;
     // ---- stride-1 units: x1 passes through to slot 2i, branch2(x2) lands in slot 2i+1 (:70-76)
     for (int bi = 1; bi < stage_repeats()[si]; ++bi) {
@@ -1037,6 +1154,13 @@ YNB_EXPORT void ynb_destroy(ynb_engine* e) {
     if (pc.tc.lo) cudaFree(pc.tc.lo);
     if (pc.tc.bw) cudaFree(pc.tc.bw);
   }
+  for (int si = 0; si < 3; ++si)
+    for (auto& cc : e->cat[si]) {
+      if (cc.pc.b_dev) cudaFree(cc.pc.b_dev);
+      if (cc.pc.tc.hi) cudaFree(cc.pc.tc.hi);
+      if (cc.pc.tc.lo) cudaFree(cc.pc.tc.lo);
+      if (cc.pc.tc.bw) cudaFree(cc.pc.tc.bw);
+    }
   if (e->ws) cudaFree(e->ws);
   delete e;
 }
@@ -1125,6 +1249,11 @@ YNB_EXPORT int ynb_commit_weights(ynb_engine* e) {
     int rc = pack_conv(e, (int)i);
     if (rc) return rc;
   }
+  if (e->cfg.gemm_mode != YNB_GEMM_FP32_FFMA)
+    for (int si = 0; si < 3; ++si) {
+      int rc = pack_cat(e, si);
+      if (rc) return rc;
+    }
   e->committed = true;
   return YNB_OK;
 }
