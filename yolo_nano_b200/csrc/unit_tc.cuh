@@ -615,6 +615,8 @@ inline bool plan_dwpw(DwPwLaunch& L, const void* in, int in_ld, int B, int H, in
   {   // 16 x 8 or 32 x 4 output pixels per tile: whichever covers the map with fewer tiles
     const int t16 = ((W + 15) / 16) * ((H + 7) / 8), t32 = ((W + 31) / 32) * ((H + 3) / 4);
     p.lgTW = t32 < t16 ? 5 : 4;
+    static const int force = getenv("YNB_DP_LGTW") ? atoi(getenv("YNB_DP_LGTW")) : 0;      // experiment knob
+    if (force == 4 || force == 5) p.lgTW = force;
   }
   const int TW = 1 << p.lgTW, TH = kTcBM >> p.lgTW;
   p.tiles_x = (W + TW - 1) / TW;
@@ -630,8 +632,10 @@ inline bool plan_dwpw(DwPwLaunch& L, const void* in, int in_ld, int B, int H, in
   // Shared memory: a 2-deep A ring is enough (it only decouples the depthwise producers from the MMAs, both
   // on chip); everything else goes to the raw ring — the TMA bytes in flight per SM are what bounds the HBM rate.
   bool found = false;
+  static const int wres = getenv("YNB_DP_WRES") ? atoi(getenv("YNB_DP_WRES")) : -1;          // experiment knob: 0 | 1
   for (int raw = kDpMaxRawStages; raw >= 2 && !found; --raw)
     for (int resident = 1; resident >= 0 && !found; --resident) {
+      if (wres >= 0 && resident != wres) continue;
       DpSmemLayout lay = dp_smem_layout(p.Npad, p.num_chunks, p.lgTW, 2, raw, resident != 0, split, chunk_ch);
       if (lay.total <= (uint32_t)kTcSmemBudget) {
         p.a_stages = 2; p.raw_stages = raw; p.w_resident = resident; L.smem = lay.total;

@@ -4,8 +4,11 @@ BASELINE config 5), over the C ABI of include/yolonano_b200.h.
 Built: target assignment (`tools.multi_gt_creator`), the four losses + their gradient w.r.t. the raw
 head maps (`models/yolo_nano.py:333-358`, `tools.py:12-34,219-276`), the SGD update
 (`train.py:167-171`), the gradient all-reduce of the data-parallel config, and the
-backward kernels of the depthwise / pointwise convolutions.  NOT built: BatchNorm with batch
-statistics and the chaining into `YOLONano.forward(x, target)` (raises NotImplementedError).
+backward kernels of the depthwise / pointwise / dense 3x3 convolutions and of training-mode BatchNorm (batch
+statistics, running-statistics update) + activation, composable per module (`SequentialTrain`).  NOT built: the
+chaining of these modules through the whole network — `YOLONano.forward(x, target)` in `.train()` mode raises
+NotImplementedError and the losses of the `.eval()` training branch carry no `grad_fn` (this package is a drop-in
+for the detection forward path, not for `train.py`'s `total_loss.backward()`).
 
 PyTorch supplies device memory, the stream and `torch.distributed`; every computation is in
 libyolonano_b200.so.  No CPU fallback: CPU tensors raise.

@@ -364,11 +364,14 @@ class YOLONano(nn.Module):
             # training branch (models/yolo_nano.py:333-358).  Built for BatchNorm in eval mode (running
             # statistics, folded into the convs): losses of the whole batch and, kept on the model as
             # `head_gradients`, d(sum of the four)/d(raw head maps) — what train.py:222-229 back-propagates
-            # into the heads.  BatchNorm with batch statistics (model.train()) is not built.
+            # into the heads.  The returned losses are plain device scalars WITHOUT a grad_fn: the backward chain
+            # through the 77 convolutions is not built, so train.py's `total_loss.backward()` has no counterpart
+            # here (this class is a drop-in for the detection forward path only).
             if self.training:
                 raise NotImplementedError(
-                    "training-mode BatchNorm (batch statistics) is not built: call model.eval() and keep "
-                    "model.trainable = True for the loss branch on running statistics")
+                    "the chained training step (batch-statistics BatchNorm through the 77 convolutions + backward) is "
+                    "not built: this class replaces the detection forward path, not train.py.  For the losses and "
+                    "the head gradients on running statistics call model.eval() and keep model.trainable = True")
             if target is None:
                 raise ValueError("trainable forward needs target [B, N, 11] (tools.multi_gt_creator)")
             eng = self.engine(int(x.shape[0]))
