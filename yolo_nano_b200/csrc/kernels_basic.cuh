@@ -25,8 +25,8 @@ constexpr int kStemInPitch = 40;               // TMA box rows: 40 floats; the b
 constexpr int kStemC = 24;
 constexpr int kStemCP = 24;                    // s_conv pitch: 16-byte aligned rows, 45.5 KB static smem in total
 constexpr int kStemPairs = (kStemConv + 1) / 2;                  // 9 column pairs per conv row
-constexpr int kStemTasks = kStemConv * kStemPairs * 2;           // (row, column pair, channel half) = 306
-constexpr int kStemThreads = 320;
+constexpr int kStemTasks2 = kStemConv * kStemPairs;              // (row, column pair) = 153, all 24 channels each
+constexpr int kStemThreads = 160;
 
 // Folded stem weights travel as a kernel parameter (constant bank) and are staged in shared
 // memory by every CTA.
@@ -52,8 +52,6 @@ stem_pool_kernel(const float* __restrict__ x, OutT* __restrict__ out, const __gr
                  const __grid_constant__ CUtensorMap tmX, int use_tma, int S) {
   __shared__ __align__(128) float s_in[3][kStemIn][kStemInPitch];
   __shared__ __align__(16) float s_conv[kStemConv * kStemConv][kStemCP];
-  __shared__ __align__(16) float s_w[27][kStemC];
-  __shared__ __align__(16) float s_b[kStemC];
   __shared__ __align__(8) uint64_t s_bar;
 
   const int Hc = S / 2, Hp = S / 4;
@@ -67,8 +65,6 @@ stem_pool_kernel(const float* __restrict__ x, OutT* __restrict__ out, const __gr
     ptx::mbar_init(&s_bar, 1);
     ptx::fence_barrier_init();
   }
-  for (int i = tid; i < 27 * kStemC; i += kStemThreads) (&s_w[0][0])[i] = (&wt.w[0][0])[i];
-  if (tid < kStemC) s_b[tid] = wt.b[tid];
   pdl_wait();          // the previous forward may still be reading / writing these buffers
 
   if (use_tma) {
@@ -92,38 +88,32 @@ stem_pool_kernel(const float* __restrict__ x, OutT* __restrict__ out, const __gr
     __syncthreads();
   }
 
-  // conv + bias + ReLU
-  if (tid < kStemTasks) {
-    const int half = tid & 1;                     // channels [12*half, 12*half + 12)
-    const int pr = tid >> 1;
-    const int r = pr / kStemPairs, q0 = (pr - r * kStemPairs) * 2;
+  // conv + bias + ReLU.  Round 2: the kernel was bound by the shared-memory pipe (ncu l1tex 96 %): a broadcast
+  // LDS.128 of weights still costs four wavefronts per warp and there were 81 of them per thread.  The weights now
+  // come straight from the constant bank (the kernel parameter) as FFMA operands — half the FMA issue rate
+  // (tools/fma_probe.cu: 65 vs 126 FMA/clk/SM) but no shared-memory traffic at all; a thread owns two horizontally
+  // adjacent conv positions and ALL 24 output channels (48 accumulators), every constant feeds both positions.
+  if (tid < kStemTasks2) {
+    const int r = tid / kStemPairs, q0 = (tid - r * kStemPairs) * 2;
     const bool has2 = q0 + 1 < kStemConv;
-    const int c0 = half * 12;
-    float2 acc0[6], acc1[6];
+    float acc0[kStemC], acc1[kStemC];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) acc0[j] = acc1[j] = make_float2(s_b[c0 + 2 * j], s_b[c0 + 2 * j + 1]);
+    for (int j = 0; j < kStemC; ++j) acc0[j] = acc1[j] = wt.b[j];
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
-        // input columns 2*q0 .. 2*q0+4 of row 2r+ky feed both positions (the last pair of a row has
-        // one position only: clamp the index)
         const float* row = &s_in[ci][2 * r + ky][1];
         float in[5];
 #pragma unroll
         for (int j = 0; j < 5; ++j) in[j] = row[min(2 * q0 + j, kStemIn - 1)];
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const float4* wv = reinterpret_cast<const float4*>(&s_w[(ci * 3 + ky) * 3 + kx][c0]);
-          const float2 v0 = make_float2(in[kx], in[kx]), v1 = make_float2(in[kx + 2], in[kx + 2]);
 #pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const float4 w4 = wv[j];
-            const float2 wa = make_float2(w4.x, w4.y), wb = make_float2(w4.z, w4.w);
-            acc0[2 * j] = __ffma2_rn(v0, wa, acc0[2 * j]);
-            acc0[2 * j + 1] = __ffma2_rn(v0, wb, acc0[2 * j + 1]);
-            acc1[2 * j] = __ffma2_rn(v1, wa, acc1[2 * j]);
-            acc1[2 * j + 1] = __ffma2_rn(v1, wb, acc1[2 * j + 1]);
+          for (int j = 0; j < kStemC; ++j) {
+            const float w = wt.w[(ci * 3 + ky) * 3 + kx][j];
+            acc0[j] = fmaf(in[kx], w, acc0[j]);
+            acc1[j] = fmaf(in[kx + 2], w, acc1[j]);
           }
         }
       }
@@ -131,18 +121,18 @@ stem_pool_kernel(const float* __restrict__ x, OutT* __restrict__ out, const __gr
     const bool row_in = cy >= 0 && cy < Hc;
     const bool in0 = row_in && cx0 + q0 >= 0 && cx0 + q0 < Hc;
     const bool in1 = row_in && cx0 + q0 + 1 >= 0 && cx0 + q0 + 1 < Hc;
-    float4* d0 = reinterpret_cast<float4*>(&s_conv[r * kStemConv + q0][c0]);
+    float4* d0 = reinterpret_cast<float4*>(&s_conv[r * kStemConv + q0][0]);
 #pragma unroll
-    for (int j = 0; j < 3; ++j)
-      d0[j] = in0 ? make_float4(fmaxf(acc0[2 * j].x, 0.f), fmaxf(acc0[2 * j].y, 0.f), fmaxf(acc0[2 * j + 1].x, 0.f),
-                                fmaxf(acc0[2 * j + 1].y, 0.f))
+    for (int j = 0; j < kStemC / 4; ++j)
+      d0[j] = in0 ? make_float4(fmaxf(acc0[4 * j], 0.f), fmaxf(acc0[4 * j + 1], 0.f), fmaxf(acc0[4 * j + 2], 0.f),
+                                fmaxf(acc0[4 * j + 3], 0.f))
                   : make_float4(0.f, 0.f, 0.f, 0.f);
     if (has2) {
-      float4* d1 = reinterpret_cast<float4*>(&s_conv[r * kStemConv + q0 + 1][c0]);
+      float4* d1 = reinterpret_cast<float4*>(&s_conv[r * kStemConv + q0 + 1][0]);
 #pragma unroll
-      for (int j = 0; j < 3; ++j)
-        d1[j] = in1 ? make_float4(fmaxf(acc1[2 * j].x, 0.f), fmaxf(acc1[2 * j].y, 0.f), fmaxf(acc1[2 * j + 1].x, 0.f),
-                                  fmaxf(acc1[2 * j + 1].y, 0.f))
+      for (int j = 0; j < kStemC / 4; ++j)
+        d1[j] = in1 ? make_float4(fmaxf(acc1[4 * j], 0.f), fmaxf(acc1[4 * j + 1], 0.f), fmaxf(acc1[4 * j + 2], 0.f),
+                                  fmaxf(acc1[4 * j + 3], 0.f))
                     : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
