@@ -480,96 +480,75 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_cols);
       if constexpr (kDecC > 0) {
         // ================= fused decode epilogue (one pixel = one thread) =================
-        constexpr int A = 3, C = kDecC, NCOL = A * (1 + C + 4), NBLK = (NCOL + 15) / 16;
-        // 16 raw columns (accumulator sum + bias) into registers
-        auto raw16 = [&](int c0, float (&v)[16]) {
+        // Round 2: the fully unrolled column walk was ~15 k instructions (250 KB of SASS) and ran at ~70 cycles per
+        // column — instruction-cache bound.  Now ROLLED loops over 16-column blocks per anchor (class logits of
+        // anchor a are columns [A + a*C, A + (a+1)*C): a tcgen05.ld may start at any column), two passes as before
+        // (max + first arg-max, then the softmax denominator) — the same values in the same order as
+        // decode_level_kernel, bit for bit.
+        constexpr int A = 3, C = kDecC, CB = (C + 15) / 16;
+        auto ld16 = [&](int c0, float (&v)[16]) {          // 16 raw columns: accumulator sum(s), no bias yet
           uint32_t r[16];
           ptx::tmem_ld_32x16(t_base + c0, r);
-          for (int a = 1; a < p.nacc; ++a) {
-            uint32_t r2[16];
-            ptx::tmem_ld_32x16(t_base + (uint32_t)(a * p.Npad) + c0, r2);
-            ptx::tmem_ld_wait();
+          if (p.nacc > 1) {
+            for (int a2 = 1; a2 < p.nacc; ++a2) {
+              uint32_t r2[16];
+              ptx::tmem_ld_32x16(t_base + (uint32_t)(a2 * p.Npad) + c0, r2);
+              ptx::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+              for (int jj = 0; jj < 16; ++jj) r[jj] = __float_as_uint(__uint_as_float(r[jj]) + __uint_as_float(r2[jj]));
+            }
           }
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + s_bias[c0 + j];
+          for (int jj = 0; jj < 16; ++jj) v[jj] = __uint_as_float(r[jj]);
         };
         float objl[A], mx[A], sum[A], tb[4 * A];
         int am[A];
-#pragma unroll
-        for (int a = 0; a < A; ++a) { mx[a] = -INFINITY; sum[a] = 0.0f; am[a] = 0; objl[a] = 0.0f; }
-        // what each pass does with 16 raw columns
-        auto pass1 = [&](int blk, const float (&v)[16]) {     // objectness / box logits, class max + first arg-max
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int col = blk * 16 + j;            // compile-time after unrolling
-            if (col < A) {
-              objl[col] = v[j];
-            } else if (col < A + A * C) {
-              const int a = (col - A) / C, c = (col - A) % C;
-              if (v[j] > mx[a]) { mx[a] = v[j]; am[a] = c; }
-            } else if (col < NCOL) {
-              tb[col - A - A * C] = v[j];
-            }
-          }
-        };
-        auto pass2 = [&](int blk, const float (&v)[16]) {     // softmax denominators
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int col = blk * 16 + j;
-            if (col >= A && col < A + A * C) sum[(col - A) / C] += softmax_exp(v[j] - mx[(col - A) / C]);
-          }
-        };
-        constexpr int P2_FIRST = 0, P2_LAST = (A + A * C - 1) / 16;     // blocks that hold class logits
-        if (p.nacc == 1) {
-          // One accumulator (the head convs): software-pipelined TMEM reads — block k+1 is in flight
-          // while block k is processed, so the ~32 tcgen05.ld latencies per tile overlap the math.
-          uint32_t ra[16], rb[16];
+        {   // objectness logits: columns [0, A); box logits: columns [A + A*C, A + A*C + 4A)
           float v[16];
-          ptx::tmem_ld_32x16(t_base, ra);
+          ld16(0, v);
 #pragma unroll
-          for (int blk = 0; blk < NBLK; ++blk) {
-            ptx::tmem_ld_wait();
-            if (blk + 1 < NBLK) {
-              if (blk & 1) ptx::tmem_ld_32x16(t_base + (blk + 1) * 16, ra);
-              else ptx::tmem_ld_32x16(t_base + (blk + 1) * 16, rb);
-            } else {
-              ptx::tmem_ld_32x16(t_base + P2_FIRST * 16, (blk & 1) ? ra : rb);     // first block of pass 2
-            }
+          for (int a = 0; a < A; ++a) objl[a] = v[a] + s_bias[a];
+          // (the 16-column read must stay inside this accumulator stage: start at most at Npad - 16)
+          constexpr int NPADC = (A * (1 + C + 4) + 15) / 16 * 16;
+          constexpr int B0 = (A + A * C) < (NPADC - 16) ? (A + A * C) : (NPADC - 16);
+          constexpr int BOFF = A + A * C - B0;
+          ld16(B0, v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float((blk & 1) ? rb[j] : ra[j]) + s_bias[blk * 16 + j];
-            pass1(blk, v);
-          }
-          // pass 2 (TMEM is re-read: cheaper than holding 3*C logits); parity continues from pass 1
-#pragma unroll
-          for (int blk = P2_FIRST; blk <= P2_LAST; ++blk) {
-            ptx::tmem_ld_wait();
-            // the prefetch at the end of pass 1 landed in the set pass 1's last block did not use
-            const bool cur_is_a = (((NBLK - 1) & 1) != 0) ^ (((blk - P2_FIRST) & 1) != 0);
-            if (blk < P2_LAST) {
-              if (cur_is_a) ptx::tmem_ld_32x16(t_base + (blk + 1) * 16, rb);
-              else ptx::tmem_ld_32x16(t_base + (blk + 1) * 16, ra);
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(cur_is_a ? ra[j] : rb[j]) + s_bias[blk * 16 + j];
-            pass2(blk, v);
-          }
-        } else {
-#pragma unroll
-          for (int blk = 0; blk < NBLK; ++blk) {
-            float v[16];
-            raw16(blk * 16, v);
-            pass1(blk, v);
-          }
-#pragma unroll
-          for (int blk = P2_FIRST; blk <= P2_LAST; ++blk) {
-            float v[16];
-            raw16(blk * 16, v);
-            pass2(blk, v);
-          }
+          for (int k = 0; k < 4 * A; ++k) tb[k] = v[BOFF + k] + s_bias[A + A * C + k];
         }
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+          const int cbase = A + a * C;
+          float m = -INFINITY;
+          int arg = 0;
+#pragma unroll 1
+          for (int blk = 0; blk < CB; ++blk) {              // pass 1: class max + first arg-max
+            float v[16];
+            ld16(cbase + blk * 16, v);
+            const float* bb = s_bias + cbase + blk * 16;
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              const int c = blk * 16 + jj;
+              const float x = v[jj] + bb[jj];
+              if ((C % 16 == 0 || c < C) && x > m) { m = x; arg = c; }
+            }
+          }
+          float sm = 0.0f;
+#pragma unroll 1
+          for (int blk = 0; blk < CB; ++blk) {              // pass 2: softmax denominator (TMEM re-read: cheaper than 3*C registers)
+            float v[16];
+            ld16(cbase + blk * 16, v);
+            const float* bb = s_bias + cbase + blk * 16;
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              const int c = blk * 16 + jj;
+              if (C % 16 == 0 || c < C) sm += softmax_exp((v[jj] + bb[jj]) - m);
+            }
+          }
+          mx[a] = m; am[a] = arg; sum[a] = sm;
+        }
+        (void)mx;
         {   // all TMEM reads of this tile are done: hand the stage back
           ptx::tc_fence_before_sync();
           __syncwarp();
