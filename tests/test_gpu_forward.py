@@ -636,3 +636,34 @@ def test_detect_raw_images_equals_reference_evaluator_loop(G, golden):
         np.testing.assert_array_equal(gb, want)
         np.testing.assert_array_equal(gs, s)
         np.testing.assert_array_equal(gc, c)
+
+
+@pytest.mark.parametrize("size,batch", [(96, 1), (160, 3), (224, 2), (352, 1), (512, 2), (640, 1)])
+def test_odd_grid_sizes_and_batches(G, size, batch):
+    """Grid sizes whose feature maps are not multiples of the kernels' tiles (12, 20, 28, 44, 64, 80 at stride 8: partial
+    32x4 / 16x8 tiles of the fused unit tails, partial GEMM tiles, odd batches): raw head maps and stage outputs against
+    the oracle in the fp32 parity mode, the head maps in bf16 mode within its stated tolerance, NMS exact on the
+    engine's own candidates."""
+    sd = W.reference_init(20, seed=size)
+    x = W.synthetic_input(batch, size, size)
+    taps = {}
+    ref = O.network(sd, x, taps=taps)
+    eng = G.make_engine(sd, size, 20, "3xtf32", max_batch=batch)
+    raw = eng.forward_raw(x.to(G.DEV))
+    for got, want in zip(raw, ref):
+        np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-3)
+    for name in ("c3", "c4", "c5", "p3", "p4", "p5"):
+        assert G.rel_err(eng.read_tap(name, batch).cpu().numpy(), taps[name].numpy()) < 1e-4, name
+    boxes, scores, cls = eng.forward_decode(x.to(G.DEV))
+    ob, os_, oc, on = eng.forward_detect(x.to(G.DEV))
+    for i in range(batch):
+        bh, sh, ch = boxes[i].cpu().numpy(), scores[i].cpu().numpy(), cls[i].cpu().numpy().astype(np.int64)
+        _, _, _, idx = O.postprocess_flat(bh, sh, ch, 20, 0.001, 0.5)
+        assert int(on[i]) == len(idx)
+        np.testing.assert_array_equal(ob[i, : len(idx)].cpu().numpy(), bh[idx])
+    eng.close()
+    engb = G.make_engine(sd, size, 20, "bf16", max_batch=batch)
+    rawb = engb.forward_raw(x.to(G.DEV))
+    worst = max(float(np.abs(g.cpu().numpy() - r.numpy()).max()) for g, r in zip(rawb, ref))
+    assert worst < 2e-2, worst
+    engb.close()
