@@ -374,6 +374,36 @@ int  ynb_dwconv3x3_bwd_weight(const float* dout_dev, int32_t dout_ld, int32_t do
                               int32_t batch, int32_t h_in, int32_t w_in, int32_t channels, int32_t stride,
                               void* workspace_dev, int64_t workspace_bytes, void* stream);
 
+/* ---- pieces of the chained training step (BASELINE config 5; yolo_nano_b200/train_step.py) ---------------------
+ * Stem conv UNFUSED (training needs the pre-BatchNorm output): Conv2d(3, 24, 3, stride 2, pad 1, bias=False),
+ * backbone/shufflenetv2.py:109-113.  x NCHW [batch,3,S,S]; w [27][24] (index (ci*9+ky*3+kx)*24+co); out NHWC
+ * [batch,S/2,S/2,24].  Its weight gradient dw [27][24] (no input gradient: the image needs none). */
+int  ynb_stem_conv_fwd(const float* x_dev, const float* w2724_dev, float* out_dev, int32_t batch, int32_t input_size,
+                       void* stream);
+int64_t ynb_stem_conv_bwd_weight_workspace_bytes(int32_t batch, int32_t input_size);
+int  ynb_stem_conv_bwd_weight(const float* dout_dev, const float* x_dev, float* dw2724_dev, int32_t batch,
+                              int32_t input_size, void* workspace_dev, int64_t workspace_bytes, void* stream);
+/* nn.MaxPool2d(3, 2, 1) on NHWC (backbone/shufflenetv2.py:116) and its backward (gradient to the FIRST maximum of a
+ * window in row-major order, as ATen; deterministic, no atomics). */
+int  ynb_maxpool3x3s2_fwd(const float* in_dev, float* out_dev, int32_t batch, int32_t h, int32_t w, int32_t channels,
+                          void* stream);
+int  ynb_maxpool3x3s2_bwd(const float* dout_dev, const float* in_dev, float* din_dev, int32_t batch, int32_t h, int32_t w,
+                          int32_t channels, void* stream);
+/* FPN / PAN merge out = a + F.interpolate(a2) (models/yolo_nano.py:291-296; mode 1: a2 is (h/2 x w/2), nearest x2;
+ * mode 2: a2 is (2h x 2w), [::2, ::2]) and the gradient w.r.t. a2 (d a = d out). */
+int  ynb_resample_add(const float* a_dev, const float* a2_dev, float* out_dev, int32_t batch, int32_t h, int32_t w,
+                      int32_t channels, int32_t mode, void* stream);
+int  ynb_resample_bwd(const float* dout_dev, float* da2_dev, int32_t batch, int32_t h, int32_t w, int32_t channels,
+                      int32_t mode, void* stream);
+/* out = a + b: gradient accumulation where a tensor feeds two consumers. */
+int  ynb_add(const float* a_dev, const float* b_dev, float* out_dev, int64_t n, void* stream);
+/* Dense 3x3 conv (pad 1, stride 1) + bias + act on the tcgen05 implicit-GEMM path, standalone: forward of the
+ * `smooth` convs (models/yolo_nano.py:44-47) and, with transposed / tap-reversed weights, their input gradient.
+ * w_dev [cout][9][cin] tap-major, cin % 32 == 0, cout <= 256.  Synchronous hook (packs the weights on the host). */
+int  ynb_conv3x3_tc(const float* in_dev, int32_t in_ld, float* out_dev, int32_t out_ld, const float* w_dev,
+                    const float* b_dev, int32_t batch, int32_t h, int32_t w, int32_t cin, int32_t cout, int32_t act,
+                    int32_t mode, void* stream);
+
 /* ModelEMA.update (utils/misc.py:78-86): for every floating-point state tensor  v = v * d + (1 - d) * m  with the
  * reference's two roundings (bit-identical), ALL tensors in one launch.  The caller passes device tables:
  * ema_ptrs_dev / model_ptrs_dev [T] device addresses of the float32 tensors, sizes_dev [T] element counts, and a

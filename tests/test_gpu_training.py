@@ -443,3 +443,109 @@ def test_model_ema_of_the_detector_feeds_its_engine(G):
     for a, b in zip(after, want_out):
         np.testing.assert_array_equal(a, b)
     assert len(before[1]) > 0
+
+
+# ---- round 2: the pieces of the chained training step ---------------------------------------------------------------
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("batch,size", [(2, 64), (3, 96)])
+def test_stem_conv_forward_and_weight_gradient(G, batch, size):
+    """Unfused stem conv (backbone/shufflenetv2.py:109-113) and its weight gradient against autograd."""
+    import torch.nn.functional as F
+    lib = G._lib.load()
+    g = torch.Generator().manual_seed(size)
+    x = torch.randn(batch, 3, size, size, generator=g)
+    w = (torch.randn(24, 3, 3, 3, generator=g) / 3).requires_grad_(True)
+    y = F.conv2d(x, w, None, 2, 1)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    xd = x.to(G.DEV)
+    wp = w.detach().permute(1, 2, 3, 0).reshape(27, 24).contiguous().to(G.DEV)
+    out = torch.empty(batch, size // 2, size // 2, 24, device=G.DEV)
+    assert lib.ynb_stem_conv_fwd(G.ptr(xd), G.ptr(wp), G.ptr(out), batch, size, G.stream()) == 0
+    torch.testing.assert_close(out.cpu(), _nhwc(y.detach()), rtol=1e-5, atol=1e-5)
+    wsb = lib.ynb_stem_conv_bwd_weight_workspace_bytes(batch, size)
+    ws = torch.empty(wsb, device=G.DEV, dtype=torch.uint8)
+    dw = torch.empty(27, 24, device=G.DEV)
+    dyd = _nhwc(dy).to(G.DEV)
+    assert lib.ynb_stem_conv_bwd_weight(G.ptr(dyd), G.ptr(xd), G.ptr(dw), batch, size, G.ptr(ws), wsb, G.stream()) == 0
+    want = w.grad.permute(1, 2, 3, 0).reshape(27, 24)
+    torch.testing.assert_close(dw.cpu(), want, rtol=1e-4, atol=1e-4 * float(want.abs().max()))
+
+
+@pytest.mark.parametrize("batch,h,w,c", [(2, 32, 32, 24), (1, 17, 23, 8)])
+def test_maxpool_forward_backward(G, batch, h, w, c):
+    """MaxPool2d(3, 2, 1) (backbone/shufflenetv2.py:116): forward exact, backward = ATen's (first maximum takes the
+    gradient; ties included: the input is quantised so that windows hold equal values)."""
+    import torch.nn.functional as F
+    lib = G._lib.load()
+    g = torch.Generator().manual_seed(h)
+    x = (torch.randn(batch, c, h, w, generator=g) * 2).round() / 2          # many exact ties
+    x.requires_grad_(True)
+    y = F.max_pool2d(x, 3, 2, 1)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    xd = _nhwc(x.detach()).to(G.DEV)
+    out = torch.empty(batch, y.shape[2], y.shape[3], c, device=G.DEV)
+    assert lib.ynb_maxpool3x3s2_fwd(G.ptr(xd), G.ptr(out), batch, h, w, c, G.stream()) == 0
+    assert torch.equal(out.cpu(), _nhwc(y.detach()))
+    din = torch.empty_like(xd)
+    dyd = _nhwc(dy).to(G.DEV)
+    assert lib.ynb_maxpool3x3s2_bwd(G.ptr(dyd), G.ptr(xd), G.ptr(din), batch, h, w, c, G.stream()) == 0
+    torch.testing.assert_close(din.cpu(), _nhwc(x.grad), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_resample_add_forward_backward(G, mode):
+    """p + F.interpolate(q) (models/yolo_nano.py:291-296) and the gradient w.r.t. q, against autograd."""
+    import torch.nn.functional as F
+    lib = G._lib.load()
+    g = torch.Generator().manual_seed(mode)
+    b, h, w, c = 2, 12, 12, 96
+    a = torch.randn(b, c, h, w, generator=g)
+    a2 = torch.randn(b, c, h // 2 if mode == 1 else h * 2, w // 2 if mode == 1 else w * 2, generator=g, requires_grad=True)
+    y = a + F.interpolate(a2, scale_factor=2.0 if mode == 1 else 0.5)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    ad, a2d = _nhwc(a).to(G.DEV), _nhwc(a2.detach()).to(G.DEV)
+    out = torch.empty(b, h, w, c, device=G.DEV)
+    assert lib.ynb_resample_add(G.ptr(ad), G.ptr(a2d), G.ptr(out), b, h, w, c, mode, G.stream()) == 0
+    torch.testing.assert_close(out.cpu(), _nhwc(y.detach()), rtol=0, atol=0)
+    da2 = torch.empty_like(a2d)
+    dyd = _nhwc(dy).to(G.DEV)
+    assert lib.ynb_resample_bwd(G.ptr(dyd), G.ptr(da2), b, h, w, c, mode, G.stream()) == 0
+    torch.testing.assert_close(da2.cpu(), _nhwc(a2.grad), rtol=1e-6, atol=1e-6)
+    s = torch.empty_like(ad)
+    assert lib.ynb_add(G.ptr(ad), G.ptr(out), G.ptr(s), ad.numel(), G.stream()) == 0
+    assert torch.equal(s.cpu(), (ad + out).cpu())
+
+
+@pytest.mark.parametrize("b,hw", [(2, 13), (1, 26)])
+def test_conv3x3_dense_forward_and_input_gradient(G, b, hw):
+    """The standalone dense 3x3 entry (ynb_conv3x3_tc, 3xTF32): forward of a `smooth` conv and — with
+    w'[k][8 - t][n] = w[n][t][k] — its input gradient, against autograd."""
+    import torch.nn.functional as F
+    lib = G._lib.load()
+    g = torch.Generator().manual_seed(hw)
+    c = 96
+    x = torch.randn(b, c, hw, hw, generator=g, requires_grad=True)
+    w = (torch.randn(c, c, 3, 3, generator=g) / (9 * c) ** 0.5)
+    bias = torch.randn(c, generator=g) * 0.1
+    y = F.conv2d(x, w, bias, 1, 1)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    xd = _nhwc(x.detach()).to(G.DEV)
+    wt = w.permute(0, 2, 3, 1).reshape(c, 9, c).contiguous().to(G.DEV)                  # [n][t][k]
+    out = torch.empty(b, hw, hw, c, device=G.DEV)
+    bd = bias.to(G.DEV)
+    assert lib.ynb_conv3x3_tc(G.ptr(xd), c, G.ptr(out), c, G.ptr(wt), G.ptr(bd), b, hw, hw, c, c, 0, 1, G.stream()) == 0, \
+        lib.ynb_last_error(None)
+    torch.testing.assert_close(out.cpu(), _nhwc(y.detach()), rtol=1e-4, atol=1e-4)
+    wd = w.permute(1, 2, 3, 0).reshape(c, 9, c).flip(1).contiguous().to(G.DEV)          # [k][8 - t][n]
+    dx = torch.empty(b, hw, hw, c, device=G.DEV)
+    dyd = _nhwc(dy).to(G.DEV)
+    zero = torch.zeros(c, device=G.DEV)
+    assert lib.ynb_conv3x3_tc(G.ptr(dyd), c, G.ptr(dx), c, G.ptr(wd), G.ptr(zero), b, hw, hw, c, c, 0, 1, G.stream()) == 0
+    torch.testing.assert_close(dx.cpu(), _nhwc(x.grad), rtol=1e-4, atol=1e-4)

@@ -108,6 +108,15 @@ SIGNATURES = {
     "ynb_bn_train_bwd": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _p, _i32, _i32, _p, _p, _p, _p, _i32, _i32, _p,
                                    _i64, _i32, _i32, _p, _i64, _p]),
     "ynb_conv3x3_bwd_weight": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _p, _p, _i32, _i32, _i32, _i32, _i32, _p, _i64, _p]),
+    "ynb_stem_conv_fwd": (C.c_int, [_p, _p, _p, _i32, _i32, _p]),
+    "ynb_stem_conv_bwd_weight_workspace_bytes": (_i64, [_i32, _i32]),
+    "ynb_stem_conv_bwd_weight": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _i64, _p]),
+    "ynb_maxpool3x3s2_fwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p]),
+    "ynb_maxpool3x3s2_bwd": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _p]),
+    "ynb_resample_add": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
+    "ynb_resample_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
+    "ynb_add": (C.c_int, [_p, _p, _p, _i64, _p]),
+    "ynb_conv3x3_tc": (C.c_int, [_p, _i32, _p, _i32, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "ynb_ema_chunk_elems": (_i32, []),
     "ynb_ema_update": (C.c_int, [_p, _p, _p, _p, _p, _i32, _f, _f, _p]),
     "ynb_act_bwd": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _p, _i32, _i32, _i64, _i32, _i32, _p]),

@@ -1036,3 +1036,172 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ 
 }
 
 }  // namespace ynb
+
+// =====================================================================================================
+// Round 2: the pieces the chained training step (config 5) still lacked as callable entries.
+// =====================================================================================================
+namespace ynb {
+
+// ---- stem conv (backbone/shufflenetv2.py:109-113): Conv2d(3, 24, 3, stride 2, pad 1, bias=False), UNFUSED ---------
+// Training needs the pre-BatchNorm conv output (batch statistics), so the fused stem_pool_kernel does not apply.
+//   x NCHW [B,3,S,S];  w [27][24] (index (ci*9 + ky*3 + kx)*24 + co, as the inference stem);  out NHWC [B,S/2,S/2,24]
+__global__ void __launch_bounds__(256)
+stem_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ out, int B, int S) {
+  __shared__ float s_w[27 * 24];
+  for (int i = threadIdx.x; i < 27 * 24; i += 256) s_w[i] = w[i];
+  __syncthreads();
+  const int Hc = S / 2;
+  const long long total = (long long)B * Hc * Hc * 6;             // 4 channels per thread
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int g = (int)(i % 6);
+    const long long pix = i / 6;
+    const int xo = (int)(pix % Hc), yo = (int)((pix / Hc) % Hc), b = (int)(pix / ((long long)Hc * Hc));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yi = 2 * yo + ky - 1;
+        if (yi < 0 || yi >= S) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xi = 2 * xo + kx - 1;
+          if (xi < 0 || xi >= S) continue;
+          const float v = __ldg(x + (((size_t)b * 3 + ci) * S + yi) * S + xi);
+          const float4 k = *reinterpret_cast<const float4*>(s_w + (ci * 9 + ky * 3 + kx) * 24 + 4 * g);
+          acc.x = fmaf(v, k.x, acc.x); acc.y = fmaf(v, k.y, acc.y); acc.z = fmaf(v, k.z, acc.z); acc.w = fmaf(v, k.w, acc.w);
+        }
+      }
+    *reinterpret_cast<float4*>(out + pix * 24 + 4 * g) = acc;
+  }
+}
+
+// dW[tap][co] = sum over output pixels of dout[pix][co] * x[pix shifted by tap]: a block owns a chunk of output
+// pixels, thread t = (tap, co) of the 27 x 24 = 648 products; per-chunk partials, fixed-order second stage.
+constexpr int kStemWgThreads = 27 * 24;
+__global__ void __launch_bounds__(kStemWgThreads)
+stem_conv_bwd_weight_kernel(const float* __restrict__ dout, const float* __restrict__ x, float* __restrict__ partial, int B,
+                            int S, long long pix_per_chunk) {
+  const int Hc = S / 2;
+  const long long total = (long long)B * Hc * Hc;
+  const int tap = threadIdx.x / 24, co = threadIdx.x - tap * 24;
+  const int ci = tap / 9, ky = (tap % 9) / 3, kx = tap % 3;
+  const long long p0 = (long long)blockIdx.x * pix_per_chunk, p1 = min(p0 + pix_per_chunk, total);
+  float s = 0.0f;
+  for (long long pix = p0; pix < p1; ++pix) {
+    const int xo = (int)(pix % Hc), yo = (int)((pix / Hc) % Hc), b = (int)(pix / ((long long)Hc * Hc));
+    const int yi = 2 * yo + ky - 1, xi = 2 * xo + kx - 1;
+    if (yi < 0 || yi >= S || xi < 0 || xi >= S) continue;
+    s = fmaf(__ldg(dout + pix * 24 + co), __ldg(x + (((size_t)b * 3 + ci) * S + yi) * S + xi), s);
+  }
+  partial[(long long)blockIdx.x * kStemWgThreads + threadIdx.x] = s;
+}
+inline int stem_wg_chunks(int B, int S) {
+  const long long total = (long long)B * (S / 2) * (S / 2);
+  long long c = (total + 255) / 256;
+  if (c > kNumSMs * 16) c = kNumSMs * 16;
+  return (int)(c < 1 ? 1 : c);
+}
+
+// ---- MaxPool2d(3, stride 2, pad 1) on NHWC (backbone/shufflenetv2.py:116), forward and backward ------------------
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1, G = C / 4;
+  const long long total = (long long)B * Ho * Wo * G;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int g = (int)(i % G);
+    const long long pix = i / G;
+    const int xo = (int)(pix % Wo), yo = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yi = 2 * yo + ky - 1;
+      if (yi < 0 || yi >= H) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xi = 2 * xo + kx - 1;
+        if (xi < 0 || xi >= W) continue;
+        const float4 v = *reinterpret_cast<const float4*>(in + (((size_t)b * H + yi) * W + xi) * C + 4 * g);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    }
+    *reinterpret_cast<float4*>(out + pix * C + 4 * g) = m;
+  }
+}
+// Backward, deterministic (no atomics): one thread per INPUT element looks at the <= 4 windows that contain it and
+// takes d_out of those whose FIRST maximum (row-major scan, as ATen's max_pool2d_with_indices) is this element.
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ in, float* __restrict__ din, int B, int H,
+                        int W, int C) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long total = (long long)B * H * W * C;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int c = (int)(i % C);
+    const long long pix = i / C;
+    const int xi = (int)(pix % W), yi = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
+    const float me = in[i];
+    float g = 0.0f;
+    // windows (yo, xo) with 2*yo - 1 <= yi <= 2*yo + 1
+    for (int yo = max(0, yi / 2); yo <= min(Ho - 1, (yi + 1) / 2); ++yo)
+      for (int xo = max(0, xi / 2); xo <= min(Wo - 1, (xi + 1) / 2); ++xo) {
+        bool first = true;                                 // is (yi, xi) the first maximum of this window?
+        for (int ky = 0; ky < 3 && first; ++ky) {
+          const int y2 = 2 * yo + ky - 1;
+          if (y2 < 0 || y2 >= H) continue;
+          for (int kx = 0; kx < 3; ++kx) {
+            const int x2 = 2 * xo + kx - 1;
+            if (x2 < 0 || x2 >= W) continue;
+            const float v = in[(((size_t)b * H + y2) * W + x2) * C + c];
+            const bool before = y2 < yi || (y2 == yi && x2 < xi);
+            if (v > me || (before && v == me)) { first = false; break; }
+          }
+        }
+        if (first) g += dout[(((size_t)b * Ho + yo) * Wo + xo) * C + c];
+      }
+    din[i] = g;
+  }
+}
+
+// ---- FPN / PAN merge backward (models/yolo_nano.py:291-296): out = a + resample(a2) => d a = d out (identity) and
+//   mode 1 (a2 up-sampled x2, nearest):  d a2[y, x] = sum of the 2x2 block of d out
+//   mode 2 (a2 down-sampled [::2, ::2]):  d a2[2y, 2x] = d out[y, x], zero elsewhere
+// da2 has the shape of a2: (H/2 x W/2) in mode 1, (2H x 2W) in mode 2; H, W = the size of out.
+__global__ void __launch_bounds__(256)
+resample_bwd_kernel(const float* __restrict__ dout, float* __restrict__ da2, int B, int H, int W, int C, int mode) {
+  const int H2 = mode == 1 ? H >> 1 : H << 1, W2 = mode == 1 ? W >> 1 : W << 1, G = C / 4;
+  const long long total = (long long)B * H2 * W2 * G;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int g = (int)(i % G);
+    const long long pix = i / G;
+    const int x = (int)(pix % W2), y = (int)((pix / W2) % H2), b = (int)(pix / ((long long)W2 * H2));
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mode == 1) {
+      for (int dy = 0; dy < 2; ++dy)
+        for (int dx = 0; dx < 2; ++dx) {
+          const int yy = 2 * y + dy, xx = 2 * x + dx;
+          if (yy < H && xx < W) {
+            const float4 v = *reinterpret_cast<const float4*>(dout + (((size_t)b * H + yy) * W + xx) * C + 4 * g);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+          }
+        }
+    } else if (!(y & 1) && !(x & 1) && (y >> 1) < H && (x >> 1) < W) {
+      s = *reinterpret_cast<const float4*>(dout + (((size_t)b * H + (y >> 1)) * W + (x >> 1)) * C + 4 * g);
+    }
+    *reinterpret_cast<float4*>(da2 + pix * C + 4 * g) = s;
+  }
+}
+
+// out = a + b (gradient accumulation where a tensor feeds two consumers), 16 bytes per thread
+__global__ void __launch_bounds__(256) add_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                   float* __restrict__ out, long long n4) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    const float4 u = reinterpret_cast<const float4*>(a)[i], v = reinterpret_cast<const float4*>(b)[i];
+    reinterpret_cast<float4*>(out)[i] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+  }
+}
+
+inline unsigned grid_for(long long items) {
+  long long blocks = (items + 255) / 256;
+  if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+  return (unsigned)(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace ynb

@@ -2143,6 +2143,155 @@ YNB_EXPORT int ynb_conv3x3_bwd_weight(const float* dout, int32_t do_ld, int32_t 
   return YNB_OK;
 }
 
+// ---- round 2: entries of the chained training step (yolo_nano_b200/train_step.py) ------------------------------
+YNB_EXPORT int ynb_stem_conv_fwd(const float* x, const float* w2724, float* out, int32_t batch, int32_t input_size,
+                                 void* stream) {
+  if (!x || !w2724 || !out || batch <= 0 || input_size <= 0 || input_size % 2)
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_stem_conv_fwd: bad arguments");
+  const long long items = (long long)batch * (input_size / 2) * (input_size / 2) * 6;
+  stem_conv_fwd_kernel<<<grid_for(items), 256, 0, (cudaStream_t)stream>>>(x, w2724, out, batch, input_size);
+  YNB_COUNT_LAUNCH();
+  UNIT_TRY(cudaGetLastError());
+  return YNB_OK;
+}
+
+YNB_EXPORT int64_t ynb_stem_conv_bwd_weight_workspace_bytes(int32_t batch, int32_t input_size) {
+  return (int64_t)stem_wg_chunks(batch, input_size) * kStemWgThreads * sizeof(float);
+}
+
+YNB_EXPORT int ynb_stem_conv_bwd_weight(const float* dout, const float* x, float* dw2724, int32_t batch, int32_t input_size,
+                                        void* ws, int64_t ws_bytes, void* stream) {
+  if (!dout || !x || !dw2724 || !ws || batch <= 0 || input_size <= 0 || input_size % 2 ||
+      ws_bytes < ynb_stem_conv_bwd_weight_workspace_bytes(batch, input_size))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_stem_conv_bwd_weight: bad arguments / workspace too small");
+  const int chunks = stem_wg_chunks(batch, input_size);
+  const long long total = (long long)batch * (input_size / 2) * (input_size / 2);
+  const long long ppc = (total + chunks - 1) / chunks;
+  cudaStream_t st = (cudaStream_t)stream;
+  stem_conv_bwd_weight_kernel<<<chunks, kStemWgThreads, 0, st>>>(dout, x, (float*)ws, batch, input_size, ppc);
+  YNB_COUNT_LAUNCH();
+  launch_reduce_partials((const float*)ws, chunks, kStemWgThreads, dw2724, st);
+  UNIT_TRY(cudaGetLastError());
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_maxpool3x3s2_fwd(const float* in, float* out, int32_t batch, int32_t h, int32_t w_, int32_t channels,
+                                    void* stream) {
+  if (!in || !out || batch <= 0 || h <= 0 || w_ <= 0 || channels <= 0 || channels % 4)
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_maxpool3x3s2_fwd: bad arguments");
+  const long long items = (long long)batch * ((h - 1) / 2 + 1) * ((w_ - 1) / 2 + 1) * (channels / 4);
+  maxpool3x3s2_fwd_kernel<<<grid_for(items), 256, 0, (cudaStream_t)stream>>>(in, out, batch, h, w_, channels);
+  YNB_COUNT_LAUNCH();
+  UNIT_TRY(cudaGetLastError());
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_maxpool3x3s2_bwd(const float* dout, const float* in, float* din, int32_t batch, int32_t h, int32_t w_,
+                                    int32_t channels, void* stream) {
+  if (!dout || !in || !din || batch <= 0 || h <= 0 || w_ <= 0 || channels <= 0)
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_maxpool3x3s2_bwd: bad arguments");
+  const long long items = (long long)batch * h * w_ * channels;
+  maxpool3x3s2_bwd_kernel<<<grid_for(items), 256, 0, (cudaStream_t)stream>>>(dout, in, din, batch, h, w_, channels);
+  YNB_COUNT_LAUNCH();
+  UNIT_TRY(cudaGetLastError());
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_resample_add(const float* a, const float* a2, float* out, int32_t batch, int32_t h, int32_t w_,
+                                int32_t channels, int32_t mode, void* stream) {
+  if (!a || !a2 || !out || batch <= 0 || h <= 0 || w_ <= 0 || channels <= 0 || channels % 4 || (mode != 1 && mode != 2) ||
+      (mode == 1 && ((h | w_) & 1)))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_resample_add: bad arguments");
+  UNIT_TRY(launch_resample_add(a, a2, out, nullptr, batch, h, w_, channels, mode, (cudaStream_t)stream));
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_resample_bwd(const float* dout, float* da2, int32_t batch, int32_t h, int32_t w_, int32_t channels,
+                                int32_t mode, void* stream) {
+  if (!dout || !da2 || batch <= 0 || h <= 0 || w_ <= 0 || channels <= 0 || channels % 4 || (mode != 1 && mode != 2) ||
+      (mode == 1 && ((h | w_) & 1)))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_resample_bwd: bad arguments");
+  const int h2 = mode == 1 ? h / 2 : h * 2, w2 = mode == 1 ? w_ / 2 : w_ * 2;
+  const long long items = (long long)batch * h2 * w2 * (channels / 4);
+  resample_bwd_kernel<<<grid_for(items), 256, 0, (cudaStream_t)stream>>>(dout, da2, batch, h, w_, channels, mode);
+  YNB_COUNT_LAUNCH();
+  UNIT_TRY(cudaGetLastError());
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_add(const float* a, const float* b, float* out, int64_t n, void* stream) {
+  if (!a || !b || !out || n <= 0 || n % 4 || (((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15u))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_add: n must be a multiple of 4, buffers 16-byte aligned");
+  add_kernel<<<grid_for(n / 4), 256, 0, (cudaStream_t)stream>>>(a, b, out, n / 4);
+  YNB_COUNT_LAUNCH();
+  UNIT_TRY(cudaGetLastError());
+  return YNB_OK;
+}
+
+// Dense 3x3 conv, pad 1, stride 1, + bias + activation on the tcgen05 implicit-GEMM path (3xTF32 | TF32), standalone:
+// forward of the `smooth` convs (models/yolo_nano.py:44-47) and, with w'[k][8 - t][n] = w[n][t][k], their input
+// gradient.  w_dev [cout][9][cin] tap-major (cin % 32 == 0, cout <= 256).  Synchronous test / training hook (packs the
+// weights on the host, like ynb_pwconv_tc).
+YNB_EXPORT int ynb_conv3x3_tc(const float* in, int32_t in_ld, float* out, int32_t out_ld, const float* w_dev,
+                              const float* b_dev, int32_t batch, int32_t h, int32_t w_, int32_t cin, int32_t cout,
+                              int32_t act, int32_t mode, void* stream) {
+  if (!in || !out || !w_dev || !b_dev || batch <= 0 || h <= 0 || w_ <= 0 || cin <= 0 || cin % kTcBK || in_ld % 4 ||
+      out_ld % 4 || cout < 1 || cout > 256 || (mode != YNB_GEMM_TC_3XTF32 && mode != YNB_GEMM_TC_TF32) ||
+      (((uintptr_t)in | (uintptr_t)out) & 15u))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_conv3x3_tc: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ktot = 9 * cin;
+  std::vector<float> wv((size_t)cout * ktot);
+  UNIT_TRY(cudaMemcpy(wv.data(), w_dev, wv.size() * 4, cudaMemcpyDeviceToHost));
+  TcWeights t;
+  t.N = cout; t.Npad = round_up(cout, 16); t.Kpad = ktot;
+  std::vector<float> hi((size_t)t.Npad * t.Kpad, 0.f), lo((size_t)t.Npad * t.Kpad, 0.f);
+  for (int n = 0; n < cout; ++n)
+    for (int k = 0; k < ktot; ++k)
+      split_tf32_host(wv[(size_t)n * ktot + k], &hi[(size_t)n * t.Kpad + k], &lo[(size_t)n * t.Kpad + k]);
+  int* d_err = nullptr;
+  UNIT_TRY(cudaMalloc(&t.hi, hi.size() * 4));
+  UNIT_TRY(cudaMalloc(&t.lo, lo.size() * 4));
+  UNIT_TRY(cudaMalloc(&d_err, 4));
+  UNIT_TRY(cudaMemset(d_err, 0, 4));
+  UNIT_TRY(cudaMemcpy(t.hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice));
+  UNIT_TRY(cudaMemcpy(t.lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice));
+  int rc = YNB_OK;
+  TcGemmLaunch L;
+  L.w = &t;
+  TcGemmParams& p = L.p;
+  memset(&p, 0, sizeof(p));
+  p.mode = mode; p.is3x3 = 1;
+  p.chunks_per_tap = cin / kTcBK;
+  p.num_steps = 9 * p.chunks_per_tap;
+  p.H = h; p.W = w_;
+  tc_pick_tile(p.H, p.W, &p.TH, &p.TW);
+  p.tiles_x = (p.W + p.TW - 1) / p.TW;
+  p.tiles_y = (p.H + p.TH - 1) / p.TH;
+  p.num_tiles = (int64_t)batch * p.tiles_x * p.tiles_y;
+  p.M = (int64_t)batch * h * w_;
+  p.N = cout; p.Npad = t.Npad;
+  tc_plan_tmem(p);
+  p.a_box_bytes = (uint32_t)(p.TH * p.TW * 128);
+  p.out = out; p.out_ld = out_ld; p.out_off = 0; p.out_step = 1; p.omap = dense_map();
+  p.bias = b_dev; p.act = act; p.err_flag = d_err;
+  if (!make_tmap_2d(&t.tm_hi, t.hi, t.Kpad, t.Npad, t.Kpad, t.Npad) ||
+      !make_tmap_2d(&t.tm_lo, t.lo, t.Kpad, t.Npad, t.Kpad, t.Npad) ||
+      !make_tmap_nhwc(&L.tmA, in, cin, w_, h, batch, in_ld, p.TW, p.TH) || !tc_plan_smem(L)) {
+    rc = fail(nullptr, YNB_ERR_CUDA, "ynb_conv3x3_tc: tensor map / smem planning failed");
+  } else {
+    L.grid = (unsigned)std::min<int64_t>(p.num_tiles, kNumSMs);
+    cudaError_t r = launch_tc_gemm(L, st);
+    if (r == cudaSuccess) r = cudaStreamSynchronize(st);
+    int flag = 0;
+    if (r == cudaSuccess) r = cudaMemcpy(&flag, d_err, 4, cudaMemcpyDeviceToHost);
+    if (r != cudaSuccess) rc = fail(nullptr, YNB_ERR_CUDA, std::string("ynb_conv3x3_tc: ") + cudaGetErrorString(r));
+    else if (flag) rc = fail(nullptr, YNB_ERR_CUDA, "ynb_conv3x3_tc: mbarrier timeout code " + std::to_string(flag));
+  }
+  cudaFree(t.hi); cudaFree(t.lo); cudaFree(d_err);
+  return rc;
+}
+
 // ---- BatchNorm2d in training mode ----------------------------------------------------------------------
 namespace {
 bool bn_args_ok(long long M, int C, std::initializer_list<int> strides, std::initializer_list<const void*> ptrs) {
