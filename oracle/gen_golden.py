@@ -373,6 +373,50 @@ def train_golden():
     print("g7 losses", out["losses"], "positives", int((target[:, :, 0] > 0).sum()), "ignored", int((target[:, :, 0] < 0).sum()))
 
 
+def train_step_golden():
+    """g10: the REAL reference in train() mode (BatchNorm on batch statistics): forward(x, target) with
+    trainable=True, total_loss.backward() (train.py:219-229) at 128^2 / VOC-20 / batch 4, calibrated weights.
+    Stored: the four losses, (sum, abs-sum, max-abs) of every parameter gradient (247 x 3), a few gradients in
+    full, the running statistics of three BatchNorm layers after the step."""
+    from oracle import weights as W
+    YOLONano, config, _ = _import_reference()
+    import tools  # type: ignore  (reference)
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    size, classes, batch, seed = 128, 20, 4, 10
+    sd = W.calibrated(classes, seed=seed)
+    m = _build(YOLONano, size, classes, config.MULTI_ANCHOR_SIZE, sd=sd)
+    m.trainable = True
+    m.train()
+    x = W.synthetic_input(batch, size, seed=seed)
+    labels = train_labels(batch, seed)
+    target = tools.multi_gt_creator(size, m.stride, labels, anchor_size=config.MULTI_ANCHOR_SIZE)
+    ls = m(x, target=target)
+    sum(ls).backward()
+    names, stats = [], []
+    out = {"size": size, "classes": classes, "batch": batch, "seed": seed, "sd_digest": W.digest(sd), "x_digest": W.digest(x),
+           "target": target.numpy(), "losses": np.array([float(v.detach()) for v in ls], dtype=np.float32)}
+    for k, p_ in m.named_parameters():
+        g = p_.grad
+        names.append(k)
+        stats.append([float(g.double().sum()), float(g.double().abs().sum()), float(g.abs().max())])
+    out["grad_names"] = np.array(names)
+    out["grad_stats"] = np.array(stats, dtype=np.float64)
+    full = ["backbone.conv1.0.weight", "backbone.conv1.1.weight", "backbone.stage2.0.branch1.0.weight",
+            "backbone.stage2.1.branch2.0.weight", "backbone.stage3.3.branch2.4.bias", "backbone.stage4.3.branch2.5.weight",
+            "conv1x1_1.convs.0.bias", "smooth_1.convs.1.weight", "head_det_1.0.convs.0.weight", "head_det_2.4.bias",
+            "head_det_3.4.weight"]
+    pd = dict(m.named_parameters())
+    for k in full:
+        out["grad." + k] = pd[k].grad.numpy().copy()
+    msd = m.state_dict()
+    for k in ("backbone.conv1.1", "backbone.stage3.0.branch2.4", "head_det_1.3.convs.1"):
+        out["rm." + k] = msd[k + ".running_mean"].numpy().copy()
+        out["rv." + k] = msd[k + ".running_var"].numpy().copy()
+        out["nbt." + k] = msd[k + ".num_batches_tracked"].numpy().copy()
+    np.savez_compressed(OUT / "g10_trainstep128.npz", torch=torch.__version__, **out)
+    print("g10_trainstep128.npz: losses", out["losses"], len(names), "parameters")
+
+
 def letterbox_golden():
     """g9: the REAL ValTransforms (data/transforms.py:445-458, cv2.resize inside) on uint8 BGR images of assorted
     shapes at size 96, and the evaluator's inverse box mapping (evaluator/cocoapi_evaluator.py:85-87) on fixed boxes."""
@@ -429,6 +473,8 @@ if __name__ == "__main__":
         preprocess_golden()
     elif len(sys.argv) > 1 and sys.argv[1] == "tta":
         tta_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == "trainstep":
+        train_step_golden()
     elif len(sys.argv) > 1 and sys.argv[1] == "letterbox":
         letterbox_golden()
     elif len(sys.argv) > 1 and sys.argv[1] == "ema":

@@ -219,3 +219,43 @@ def ema_perturb(m, g: torch.Generator) -> None:
         else:
             v += 1
 
+
+# --------------------------------------------------------------------------------------
+# the whole training step (train.py:219-231): model.train()(x, target) -> losses, backward, SGD
+# --------------------------------------------------------------------------------------
+def train_forward_backward(sd: dict, x: torch.Tensor, target: torch.Tensor, input_size: int, num_classes: int,
+                           anchor_size, num_anchors: int = 3):
+    """YOLONano in train() mode with trainable=True (models/yolo_nano.py:333-358): BatchNorm on batch statistics
+    (running statistics updated, momentum 0.1), the four losses, `total_loss.backward()` (train.py:222-229).
+    Returns (losses [4], grads {parameter name: tensor}, new_state {running_* / num_batches_tracked after the step}).
+    `sd` is not modified."""
+    from . import yolo_nano_oracle as O
+    work = {}
+    for k, v in sd.items():
+        if k.endswith("running_mean") or k.endswith("running_var") or k.endswith("num_batches_tracked"):
+            work[k] = v.detach().clone()
+        else:
+            work[k] = v.detach().clone().requires_grad_(True)
+    O._BN_TRAIN = True
+    try:
+        preds = O.network_graph(work, x)
+    finally:
+        O._BN_TRAIN = False
+    confs, clss, boxes = [], [], []
+    a, c = num_anchors, num_classes
+    for pred in preds:
+        b, ch, h, w = pred.shape
+        q = pred.permute(0, 2, 3, 1).contiguous().view(b, h * w, ch)
+        confs.append(q[:, :, :a].contiguous().view(b, h * w * a, 1))
+        clss.append(q[:, :, a:(1 + c) * a].contiguous().view(b, h * w * a, c))
+        boxes.append(q[:, :, (1 + c) * a:].contiguous().view(b, h * w * a, 4))
+    ls = losses_from_predictions(torch.cat(confs, 1), torch.cat(clss, 1), torch.cat(boxes, 1), target, input_size,
+                                 anchor_size, num_anchors)
+    sum(ls).backward()
+    grads = {k: v.grad for k, v in work.items() if v.requires_grad}
+    state = {k: v for k, v in work.items() if not v.requires_grad}
+    for k in state:
+        if k.endswith("num_batches_tracked"):
+            state[k] = state[k] + 1          # F.batch_norm does not count; nn.BatchNorm2d.forward does
+    return [float(v.detach()) for v in ls], grads, state
+

@@ -41,6 +41,9 @@ def _conv(sd: StateDict, prefix: str, x, stride=1, padding=0, groups=1):
 
 # oracle/weights.py flips this to measure activation statistics (calibrated test weights)
 _CALIBRATE = False
+# oracle/train_oracle.py flips this for the training branch: nn.BatchNorm2d in train() mode (batch statistics,
+# running statistics updated in place with momentum 0.1)
+_BN_TRAIN = False
 
 
 def _bn(sd: StateDict, prefix: str, x):
@@ -48,6 +51,9 @@ def _bn(sd: StateDict, prefix: str, x):
     (utils/fuse_conv_bn.py:47-48) has replaced the slot by nn.Identity (no keys left)."""
     if prefix + ".running_mean" not in sd:
         return x
+    if _BN_TRAIN:
+        return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"],
+                            sd[prefix + ".weight"], sd[prefix + ".bias"], True, 0.1, BN_EPS)
     if _CALIBRATE:   # batch statistics, written back into the running buffers (momentum 1)
         return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"],
                             sd[prefix + ".weight"], sd[prefix + ".bias"], True, 1.0, BN_EPS)
@@ -102,6 +108,11 @@ def network(sd: StateDict, x: torch.Tensor, taps: Optional[dict] = None):
     """Backbone + neck + heads (backbone/shufflenetv2.py:157-167,
     models/yolo_nano.py:284-301).  Returns raw (pred_s, pred_m, pred_l) in NCHW.
     If `taps` is a dict it receives every stage boundary named as ynb_read_tap names."""
+    return network_graph(sd, x, taps)
+
+
+def network_graph(sd: StateDict, x: torch.Tensor, taps: Optional[dict] = None):
+    """`network` without the no_grad guard (the training oracle differentiates through it)."""
     def tap(name, t):
         if taps is not None:
             taps[name] = t

@@ -59,3 +59,32 @@ def test_ema_update_matches_reference_class(golden):
     for k, v in ema_sd.items():
         np.testing.assert_array_equal(v.numpy(), g8["ema." + k], err_msg=k)
     assert int(ema_sd["1.num_batches_tracked"]) == 0            # integer state is not averaged
+
+
+def test_train_step_oracle_matches_reference_in_train_mode(golden):
+    """oracle train_forward_backward (BatchNorm on batch statistics, the four losses, total.backward()) against the
+    REAL reference in train() mode (golden g10): losses, every parameter gradient by (sum, abs-sum, max), eleven
+    gradients in full, running statistics after the step."""
+    g = golden("g10_trainstep128.npz")
+    size, classes, seed, batch = int(g["size"]), int(g["classes"]), int(g["seed"]), int(g["batch"])
+    sd = W.calibrated(classes, seed=seed)
+    x = W.synthetic_input(batch, size, seed=seed)
+    assert W.digest(sd) == str(g["sd_digest"]) and W.digest(x) == str(g["x_digest"])
+    ls, grads, state = T.train_forward_backward(sd, x, torch.from_numpy(g["target"]), size, classes, W.anchors_for(classes))
+    np.testing.assert_allclose(np.array(ls, dtype=np.float32), g["losses"], rtol=1e-5)
+    names = [str(n) for n in g["grad_names"]]
+    assert len(names) == 247 and set(names) == set(grads)
+    for n, (s, a, mx) in zip(names, g["grad_stats"]):
+        gr = grads[n]
+        assert abs(float(gr.double().abs().sum()) - a) <= 2e-4 * a + 1e-9, n
+        assert abs(float(gr.abs().max()) - mx) <= 2e-4 * mx + 1e-9, n
+    for k in g.files:
+        if k.startswith("grad."):
+            want = g[k]
+            np.testing.assert_allclose(grads[k[5:]].numpy(), want, rtol=2e-3, atol=2e-5 * float(np.abs(want).max()), err_msg=k)
+        elif k.startswith("rm."):
+            np.testing.assert_allclose(state[k[3:] + ".running_mean"].numpy(), want := g[k], rtol=1e-5, atol=1e-6)
+        elif k.startswith("rv."):
+            np.testing.assert_allclose(state[k[3:] + ".running_var"].numpy(), g[k], rtol=1e-5, atol=1e-6)
+        elif k.startswith("nbt."):
+            assert int(state[k[4:] + ".num_batches_tracked"]) == int(g[k])
