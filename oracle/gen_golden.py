@@ -413,6 +413,22 @@ def train_step_golden():
         out["rm." + k] = msd[k + ".running_mean"].numpy().copy()
         out["rv." + k] = msd[k + ".running_var"].numpy().copy()
         out["nbt." + k] = msd[k + ".num_batches_tracked"].numpy().copy()
+    # The reference's OWN float32 rounding sensitivity: LeakyReLU / ReLU / max-pool are piecewise linear, the forward
+    # amplifies a 1-ulp input change to ~1e-4 at the deep activations, so a handful of units change side and the
+    # gradients of the layers below move by per cent.  Stored per parameter: the largest change of the gradient
+    # (relative to its max-abs) over four input perturbations of relative size 1e-6 — the bound any other float32
+    # implementation of the same graph (different summation order) can be held to.
+    base = {k: p_.grad.clone() for k, p_ in m.named_parameters()}
+    sens = np.zeros(len(names))
+    for trial in range(4):
+        m.zero_grad()
+        noise = torch.randn(x.shape, generator=torch.Generator().manual_seed(100 + trial))
+        sum(m(x * (1.0 + 1e-6 * noise), target=target)).backward()
+        for i, (k, p_) in enumerate(m.named_parameters()):
+            sens[i] = max(sens[i], float((p_.grad - base[k]).abs().max() / base[k].abs().max().clamp_min(1e-30)))
+    out["grad_sens"] = sens
+    for k, p_ in m.named_parameters():
+        p_.grad = base[k]
     np.savez_compressed(OUT / "g10_trainstep128.npz", torch=torch.__version__, **out)
     print("g10_trainstep128.npz: losses", out["losses"], len(names), "parameters")
 

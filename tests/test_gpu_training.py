@@ -549,3 +549,77 @@ def test_conv3x3_dense_forward_and_input_gradient(G, b, hw):
     zero = torch.zeros(c, device=G.DEV)
     assert lib.ynb_conv3x3_tc(G.ptr(dyd), c, G.ptr(dx), c, G.ptr(wd), G.ptr(zero), b, hw, hw, c, c, 0, 1, G.stream()) == 0
     torch.testing.assert_close(dx.cpu(), _nhwc(x.grad), rtol=1e-4, atol=1e-4)
+
+
+def test_chained_training_step_matches_reference_train_mode(G, golden):
+    """BASELINE config 5's step, chained: TrainStep.forward_backward = model.train()(x, target) + total.backward() of
+    the reference (BatchNorm on batch statistics, 77 convs forward and backward, every kernel from the library) against
+    the train-mode oracle, itself pinned to the REAL reference by golden g10.
+
+    What can be asserted: ReLU / LeakyReLU / max-pool make the gradient piecewise linear in the activations, and the
+    reference's own forward amplifies a 1-ulp input change to ~1e-4 at the deep layers, so a few units change side and
+    the REFERENCE's gradients move by per cent (g10 `grad_sens`: the largest relative change of each gradient over four
+    1e-6 input perturbations, median 4e-2).  Hence three checks:
+      1. the four losses (rtol 2e-4) and the running statistics after the step (rtol 2e-3);
+      2. every backward op of the chain, in place, against torch.autograd of the same op on the same inputs and incoming
+         gradient: forward, d input and parameter gradients within 2e-5 of their max (float32 / 3xTF32 rounding) — no
+         systematic error in any of the 154 conv / BatchNorm / merge ops (stem conv, max-pool: own unit tests);
+      3. every one of the 247 parameter gradients against the oracle within 2 x the reference's own sensitivity + 2e-4
+         of the largest gradient of its module (composition: residual sums, chunk / cat / shuffle, resampling, pooling)."""
+    import contextlib, io
+    import yolo_nano_b200 as pkg
+    from train_step_checker import CheckedTrainStep
+    from oracle import train_oracle as T
+    g = golden("g10_trainstep128.npz")
+    size, classes, seed, batch = int(g["size"]), int(g["classes"]), int(g["seed"]), int(g["batch"])
+    sd = W.calibrated(classes, seed=seed)
+    x = W.synthetic_input(batch, size, seed=seed)
+    target = torch.from_numpy(g["target"])
+    want_l, want_g, want_state = T.train_forward_backward(sd, x, target, size, classes, W.anchors_for(classes))
+    np.testing.assert_allclose(np.array(want_l, dtype=np.float32), g["losses"], rtol=1e-5)      # oracle == real reference
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = pkg.YOLONano(G.DEV, size, classes, anchor_size=W.anchors_for(classes))
+    m.load_state_dict(sd)
+    m = m.to(G.DEV)
+    m.trainable = True
+    m.train()
+    step = CheckedTrainStep(m)
+    losses, grads = step.forward_backward(x.to(G.DEV), target.to(G.DEV))
+    # 1. losses
+    np.testing.assert_allclose(losses.cpu().numpy(), g["losses"], rtol=2e-4)
+    # 2. every op of the chain against autograd of the same op
+    assert len(step.records) >= 150, len(step.records)
+    worst_op = max(step.records, key=lambda r: max([r["fwd"], r["dx"]] + list(r["params"].values())))
+    print("[report] chained training step: %d ops checked in place, worst %s" % (len(step.records), worst_op))
+    for r in step.records:
+        assert r["fwd"] < 2e-5 and r["dx"] < 2e-5 and all(v < 2e-5 for v in r["params"].values()), r
+    # 3. all parameter gradients against the oracle, bounded by the reference's own rounding sensitivity
+    assert set(grads) == set(want_g) and len(grads) == 247
+    sens = dict(zip([str(n) for n in g["grad_names"]], g["grad_sens"]))
+    module_scale = {}
+    for k, wg in want_g.items():
+        mod = k.rsplit(".", 1)[0]
+        module_scale[mod] = max(module_scale.get(mod, 0.0), float(wg.abs().max()))
+    bad, ratios = {}, []
+    for k, wg in want_g.items():
+        got = grads[k].cpu()
+        assert tuple(got.shape) == tuple(wg.shape), k
+        err = float((got - wg).abs().max())
+        bound = 2.0 * sens[k] * float(wg.abs().max()) + 2e-4 * module_scale[k.rsplit(".", 1)[0]]
+        ratios.append(err / max(float(wg.abs().max()), 1e-30))
+        if not err <= bound:
+            bad[k] = (err, bound)
+    flat_got = step.flat_gradient(grads).cpu().double()
+    flat_want = torch.cat([want_g[k].reshape(-1) for k, _ in m.named_parameters()]).double()
+    cos = float(torch.dot(flat_got, flat_want) / (flat_got.norm() * flat_want.norm()))
+    print("[report] chained training step: gradient error / max, median %.2e (reference's own sensitivity: median %.2e); "
+          "cosine of the flat gradient %.6f" % (float(np.median(ratios)), float(np.median(g["grad_sens"])), cos))
+    assert not bad, bad
+    assert cos > 0.999, cos
+    msd = m.state_dict()
+    for k, v in want_state.items():
+        if k.endswith("num_batches_tracked"):
+            assert int(msd[k]) == int(v), k
+        else:
+            torch.testing.assert_close(msd[k].cpu(), v, rtol=2e-3, atol=2e-4, msg=k)
+    assert flat_got.numel() == sum(p.numel() for p in m.parameters())

@@ -1,0 +1,361 @@
+"""The chained training step of BASELINE config 5: `model.train()(x, target)` of the reference
+(`models/yolo_nano.py:282-358` with BatchNorm on BATCH statistics) + `total_loss.backward()` (`train.py:222-229`),
+every arithmetic step a kernel of libyolonano_b200.so:
+
+    stem conv -> BN(batch) -> ReLU -> max-pool -> 16 ShuffleV2 units -> laterals -> FPN/PAN merges + 3x3 smooth convs
+    -> three heads -> loss + d loss / d head maps (train_loss_kernel) -> the same chain backwards
+
+A tape records one closure per forward op; `backward()` replays them in reverse, accumulating the gradient of a tensor
+that feeds several consumers with `ynb_add`.  PyTorch moves data only (views, channel padding to multiples of 4,
+`chunk` / `cat` / `channel_shuffle` as index permutations, weight-layout transposes): no torch arithmetic on
+activations or gradients.  Correctness first: the convs run on the parity-tested stand-alone entries (the
+tensor-core hooks re-pack their weights per call), so this path is NOT tuned — the fused inference kernels do not
+apply in training mode (batch statistics need the pre-BN conv outputs).
+
+    step = TrainStep(model)                       # model: yolo_nano_b200.YOLONano on a CUDA device
+    losses, grads = step.forward_backward(x, target)          # grads: {parameter name: tensor, reference shapes}
+    flat = step.flat_gradient(grads)              # parameter order = model.parameters() (train.py:167)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Tuple
+
+import torch
+
+from . import _lib
+from . import training as T
+from .engine import EngineError, _ptr, _stream_ptr
+from .topology import STAGE_CHANNELS, STAGE_REPEATS
+
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+
+
+def _pad4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+def _padc(t: torch.Tensor, n: int) -> torch.Tensor:
+    """Zero-pad the LAST dimension to n (data movement)."""
+    if t.shape[-1] == n:
+        return t.contiguous()
+    out = t.new_zeros(*t.shape[:-1], n)
+    out[..., : t.shape[-1]] = t
+    return out
+
+
+class _Tape:
+    def __init__(self, dev):
+        self.dev = dev
+        self.ops: List = []
+        self.grad: Dict[int, torch.Tensor] = {}
+        self.keep: List[torch.Tensor] = []          # tensors whose id() keys self.grad must stay alive
+        self.pgrad: Dict[str, torch.Tensor] = {}
+
+    def add_grad(self, t: torch.Tensor, g: torch.Tensor):
+        g = g.contiguous()
+        k = id(t)
+        if k in self.grad:
+            a = self.grad[k]
+            out = torch.empty_like(a)
+            T._check(_lib.load().ynb_add(_ptr(a), _ptr(g), _ptr(out), a.numel(), _stream_ptr(self.dev)), "ynb_add")
+            self.grad[k] = out
+        else:
+            self.grad[k] = g
+        self.keep.append(t)
+
+    def take(self, t: torch.Tensor) -> torch.Tensor:
+        return self.grad.pop(id(t))
+
+    def backward(self):
+        for fn in reversed(self.ops):
+            fn()
+
+
+class TrainStep:
+    """Forward + backward of the whole detector in training mode.  Holds padded working copies of the BatchNorm
+    running statistics and writes them back to the model's buffers after every step (as nn.BatchNorm2d does)."""
+
+    def __init__(self, model):
+        self.model = model
+        p = next(model.parameters())
+        if p.device.type != "cuda":
+            raise EngineError("TrainStep needs the model on a CUDA device (no CPU fallback)")
+        self.dev = p.device
+        self.lib = _lib.load()
+
+    # ---- kernel wrappers (NHWC float32, dense) ------------------------------------------------------------------
+    def _st(self):
+        return _stream_ptr(self.dev)
+
+    def _pw_fwd(self, x2d, w_nk, b):
+        m, k = x2d.shape
+        n = w_nk.shape[0]
+        y = torch.empty((m, n), device=self.dev, dtype=torch.float32)
+        for n0 in range(0, n, 256):
+            nc = min(256, n - n0)
+            T._check(self.lib.ynb_pwconv_tc(_ptr(x2d), k, 0, _ptr(y), n, n0, 1, _ptr(w_nk[n0:n0 + nc].contiguous()),
+                                            _ptr(b[n0:n0 + nc].contiguous()), m, k, nc, 0, _lib.GEMM_TC_3XTF32, self._st()),
+                     "ynb_pwconv_tc")
+        return y
+
+    # ---- ops: forward now, closure for backward -----------------------------------------------------------------
+    def _param(self, name):
+        return self.sd[name]
+
+    def pw(self, tape, x, conv, bias: bool):
+        """1x1 conv on [B,H,W,K] (K, N padded to multiples of 4 with zero weights)."""
+        w = self._param(conv + ".weight")
+        n, k = w.shape[0], w.shape[1]
+        np_, kp = _pad4(n), x.shape[-1]
+        wp = torch.zeros((np_, kp), device=self.dev)
+        wp[:n, :k] = w.reshape(n, k)
+        bp = torch.zeros(np_, device=self.dev)
+        if bias:
+            bp[:n] = self._param(conv + ".bias")
+        shp = x.shape
+        x2 = x.reshape(-1, kp)
+        y = self._pw_fwd(x2, wp, bp).reshape(*shp[:-1], np_)
+
+        def bw():
+            dy = tape.take(y).reshape(-1, np_)
+            dw, db = T.pwconv_backward_weight(dy, x2)
+            tape.pgrad[conv + ".weight"] = dw[:n, :k].reshape(n, k, 1, 1).contiguous()
+            if bias:
+                tape.pgrad[conv + ".bias"] = db[:n].contiguous()
+            tape.add_grad(x, T.pwconv_backward_data(dy, wp).reshape(shp))
+        tape.ops.append(bw)
+        return y
+
+    def dw(self, tape, x, conv, stride: int, bias: bool):
+        """depthwise 3x3 on [B,H,W,C] (C padded)."""
+        w = self._param(conv + ".weight")                        # [C,1,3,3]
+        c, cp = w.shape[0], x.shape[-1]
+        w9 = torch.zeros((9, cp), device=self.dev)
+        w9[:, :c] = w.reshape(c, 9).t()
+        bp = torch.zeros(cp, device=self.dev)
+        if bias:
+            bp[:c] = self._param(conv + ".bias")
+        b_, h, w_, _ = x.shape
+        ho, wo = (h - 1) // stride + 1, (w_ - 1) // stride + 1
+        y = torch.empty((b_, ho, wo, cp), device=self.dev)
+        T._check(self.lib.ynb_dwconv3x3(_ptr(x), cp, 0, _ptr(y), cp, 0, 1, _ptr(w9), _ptr(bp), b_, h, w_, cp, stride, 0,
+                                        self._st()), "ynb_dwconv3x3")
+
+        def bw():
+            dy = tape.take(y)
+            dx, dw9, db = T.dwconv3x3_backward(dy, x, w9, stride)
+            tape.pgrad[conv + ".weight"] = dw9[:, :c].t().reshape(c, 1, 3, 3).contiguous()
+            if bias:
+                tape.pgrad[conv + ".bias"] = db[:c].contiguous()
+            tape.add_grad(x, dx)
+        tape.ops.append(bw)
+        return y
+
+    def conv3(self, tape, x, conv):
+        """dense 3x3, pad 1, stride 1, with bias (the smooth convs)."""
+        w = self._param(conv + ".weight")                        # [N,K,3,3]
+        n, k = w.shape[0], w.shape[1]
+        wf = w.permute(0, 2, 3, 1).reshape(n, 9, k).contiguous()            # [n][t][k]
+        bias = self._param(conv + ".bias").contiguous()
+        b_, h, w_, _ = x.shape
+        y = torch.empty((b_, h, w_, n), device=self.dev)
+        T._check(self.lib.ynb_conv3x3_tc(_ptr(x), k, _ptr(y), n, _ptr(wf), _ptr(bias), b_, h, w_, k, n, 0,
+                                         _lib.GEMM_TC_3XTF32, self._st()), "ynb_conv3x3_tc")
+
+        def bw():
+            dy = tape.take(y)
+            dw9, db = T.conv3x3_backward_weight(dy, x)              # [9, N, K]
+            tape.pgrad[conv + ".weight"] = dw9.permute(1, 2, 0).reshape(n, k, 3, 3).contiguous()
+            tape.pgrad[conv + ".bias"] = db
+            wd = w.permute(1, 2, 3, 0).reshape(k, 9, n).flip(1).contiguous()  # [k][8 - t][n]
+            dx = torch.empty_like(x)
+            zero = torch.zeros(k, device=self.dev)
+            T._check(self.lib.ynb_conv3x3_tc(_ptr(dy), n, _ptr(dx), k, _ptr(wd), _ptr(zero), b_, h, w_, n, k, 0,
+                                             _lib.GEMM_TC_3XTF32, self._st()), "ynb_conv3x3_tc (dgrad)")
+            tape.add_grad(x, dx)
+        tape.ops.append(bw)
+        return y
+
+    def bn(self, tape, x, bn_name, act: int):
+        """nn.BatchNorm2d in training mode + activation; running statistics updated in the model's buffers."""
+        g, b = self._param(bn_name + ".weight"), self._param(bn_name + ".bias")
+        c, cp = g.shape[0], x.shape[-1]
+        gp = torch.ones(cp, device=self.dev); gp[:c] = g
+        bp = torch.zeros(cp, device=self.dev); bp[:c] = b
+        rm = torch.zeros(cp, device=self.dev); rm[:c] = self.sd[bn_name + ".running_mean"]
+        rv = torch.ones(cp, device=self.dev); rv[:c] = self.sd[bn_name + ".running_var"]
+        layer = T.BnActTrain(gp, bp, rm, rv, act=act)
+        y = layer.forward(x)
+        self.new_stats[bn_name] = (rm[:c], rv[:c])
+
+        def bw():
+            dx = layer.backward(tape.take(y))
+            tape.pgrad[bn_name + ".weight"] = layer.grads["weight"][:c].contiguous()
+            tape.pgrad[bn_name + ".bias"] = layer.grads["bias"][:c].contiguous()
+            tape.add_grad(x, dx)
+        tape.ops.append(bw)
+        return y
+
+    def movement(self, tape, ins, out_fn, back_fn):
+        """A pure data-movement op (views / permutations): out = out_fn(*ins); backward distributes with back_fn."""
+        y = out_fn(*ins).contiguous()
+
+        def bw():
+            dy = tape.take(y)
+            for t, g in zip(ins, back_fn(dy)):
+                if g is not None:
+                    tape.add_grad(t, g)
+        tape.ops.append(bw)
+        return y
+
+    # ---- blocks ----------------------------------------------------------------------------------------------------
+    def shuffle_unit(self, tape, x, prefix, cin, cout, stride):
+        h = cout // 2
+        hp = _pad4(h)
+
+        def branch2(t):
+            t = self.bn(tape, self.pw(tape, t, prefix + ".branch2.0", False), prefix + ".branch2.1", ACT_RELU)
+            t = self.bn(tape, self.dw(tape, t, prefix + ".branch2.3", stride, False), prefix + ".branch2.4", ACT_NONE)
+            return self.bn(tape, self.pw(tape, t, prefix + ".branch2.5", False), prefix + ".branch2.6", ACT_RELU)
+
+        def interleave(a, b):       # cat + channel_shuffle: out[2i] = a[i], out[2i+1] = b[i]   (a, b: [.., hp])
+            return torch.stack((a[..., :h], b[..., :h]), dim=-1).reshape(*a.shape[:-1], 2 * h)
+
+        def de_interleave(dy):
+            d2 = dy.reshape(*dy.shape[:-1], h, 2)
+            return _padc(d2[..., 0], hp), _padc(d2[..., 1], hp)
+
+        if stride == 1:
+            x1 = self.movement(tape, [x], lambda t: _padc(t[..., :h], hp), lambda d: [_padc(d[..., :h], 2 * h)])
+            x2 = self.movement(tape, [x], lambda t: _padc(t[..., h:], hp),
+                               lambda d: [torch.cat((d.new_zeros(*d.shape[:-1], h), d[..., :h]), dim=-1)])
+            b2 = branch2(x2)
+            return self.movement(tape, [x1, b2], interleave, de_interleave)
+        t = self.bn(tape, self.dw(tape, x, prefix + ".branch1.0", stride, False), prefix + ".branch1.1", ACT_NONE)
+        b1 = self.bn(tape, self.pw(tape, t, prefix + ".branch1.2", False), prefix + ".branch1.3", ACT_RELU)
+        b2 = branch2(x)
+        return self.movement(tape, [b1, b2], interleave, de_interleave)
+
+    def conv_module(self, tape, x, prefix, k, groups):
+        """`Conv` (utils/modules.py:8-18): Conv2d(bias) + BN + LeakyReLU(0.1)."""
+        if k == 1:
+            y = self.pw(tape, x, prefix + ".convs.0", True)
+        elif groups > 1:
+            y = self.dw(tape, x, prefix + ".convs.0", 1, True)
+        else:
+            y = self.conv3(tape, x, prefix + ".convs.0")
+        return self.bn(tape, y, prefix + ".convs.1", ACT_LEAKY)
+
+    def merge(self, tape, a, a2, mode):
+        """a + F.interpolate(a2) (models/yolo_nano.py:291-296)."""
+        b_, h, w_, c = a.shape
+        y = torch.empty_like(a)
+        T._check(self.lib.ynb_resample_add(_ptr(a), _ptr(a2), _ptr(y), b_, h, w_, c, mode, self._st()), "ynb_resample_add")
+
+        def bw():
+            dy = tape.take(y)
+            da2 = torch.empty_like(a2)
+            T._check(self.lib.ynb_resample_bwd(_ptr(dy), _ptr(da2), b_, h, w_, c, mode, self._st()), "ynb_resample_bwd")
+            tape.add_grad(a, dy)
+            tape.add_grad(a2, da2)
+        tape.ops.append(bw)
+        return y
+
+    # ---- the step ----------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_backward(self, x: torch.Tensor, target: torch.Tensor) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+        m = self.model
+        dev = self.dev
+        if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != x.shape[3]:
+            raise EngineError("x must be a float32 CUDA tensor [B,3,S,S]")
+        x = x.contiguous()
+        bsz, s = int(x.shape[0]), int(x.shape[2])
+        self.sd = {k: v.detach() for k, v in m.state_dict(keep_vars=True).items()}
+        self.new_stats: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
+        tape = _Tape(dev)
+        lib = self.lib
+
+        # stem: conv -> BN -> ReLU -> max-pool (backbone/shufflenetv2.py:109-116, 158-159)
+        w0 = self.sd["backbone.conv1.0.weight"]
+        w2724 = w0.permute(1, 2, 3, 0).reshape(27, 24).contiguous()
+        c1 = torch.empty((bsz, s // 2, s // 2, 24), device=dev)
+        T._check(lib.ynb_stem_conv_fwd(_ptr(x), _ptr(w2724), _ptr(c1), bsz, s, self._st()), "ynb_stem_conv_fwd")
+
+        def stem_bw():
+            dy = tape.take(c1)
+            wsb = lib.ynb_stem_conv_bwd_weight_workspace_bytes(bsz, s)
+            ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
+            dwt = torch.empty((27, 24), device=dev)
+            T._check(lib.ynb_stem_conv_bwd_weight(_ptr(dy), _ptr(x), _ptr(dwt), bsz, s, _ptr(ws), wsb, self._st()),
+                     "ynb_stem_conv_bwd_weight")
+            tape.pgrad["backbone.conv1.0.weight"] = dwt.reshape(3, 3, 3, 24).permute(3, 0, 1, 2).contiguous()
+        tape.ops.append(stem_bw)
+        a1 = self.bn(tape, c1, "backbone.conv1.1", ACT_RELU)
+        hp_ = (s // 2 - 1) // 2 + 1
+        pool = torch.empty((bsz, hp_, hp_, 24), device=dev)
+        T._check(lib.ynb_maxpool3x3s2_fwd(_ptr(a1), _ptr(pool), bsz, s // 2, s // 2, 24, self._st()), "ynb_maxpool3x3s2_fwd")
+
+        def pool_bw():
+            dy = tape.take(pool)
+            din = torch.empty_like(a1)
+            T._check(lib.ynb_maxpool3x3s2_bwd(_ptr(dy), _ptr(a1), _ptr(din), bsz, s // 2, s // 2, 24, self._st()),
+                     "ynb_maxpool3x3s2_bwd")
+            tape.add_grad(a1, din)
+        tape.ops.append(pool_bw)
+
+        # backbone stages
+        t = pool
+        feats = []
+        cin = STAGE_CHANNELS[0]
+        for si, (rep, cout) in enumerate(zip(STAGE_REPEATS, STAGE_CHANNELS[1:])):
+            for i in range(rep):
+                t = self.shuffle_unit(tape, t, f"backbone.stage{si + 2}.{i}", cin if i == 0 else cout, cout, 2 if i == 0 else 1)
+            cin = cout
+            feats.append(t)
+        c3, c4, c5 = feats
+        # neck (models/yolo_nano.py:286-296)
+        p3 = self.conv_module(tape, c3, "conv1x1_0", 1, 1)
+        p4 = self.conv_module(tape, c4, "conv1x1_1", 1, 1)
+        p5 = self.conv_module(tape, c5, "conv1x1_2", 1, 1)
+        p4 = self.conv_module(tape, self.merge(tape, p4, p5, 1), "smooth_0", 3, 1)
+        p3 = self.conv_module(tape, self.merge(tape, p3, p4, 1), "smooth_1", 3, 1)
+        p4 = self.conv_module(tape, self.merge(tape, p4, p3, 2), "smooth_2", 3, 1)
+        p5 = self.conv_module(tape, self.merge(tape, p5, p4, 2), "smooth_3", 3, 1)
+        # heads (models/yolo_nano.py:50-70, 299-301); the raw maps keep the padded width the loss kernel reads (ld)
+        raws = []
+        for li, f in enumerate((p3, p4, p5)):
+            hd = f"head_det_{li + 1}"
+            u = self.conv_module(tape, f, hd + ".0", 3, 96)
+            u = self.conv_module(tape, u, hd + ".1", 1, 1)
+            u = self.conv_module(tape, u, hd + ".2", 3, 96)
+            u = self.conv_module(tape, u, hd + ".3", 1, 1)
+            raws.append(self.pw(tape, u, hd + ".4", True))
+        raw2 = [r.reshape(bsz, -1, r.shape[-1]) for r in raws]
+        losses, grads = T.train_loss(raw2, target.contiguous(), s, m.num_classes, m.anchor_size.view(-1, 2).tolist())
+        nch = m.num_anchors * (1 + m.num_classes + 4)
+        for r, g in zip(raws, grads):
+            g[..., nch:] = 0.0                      # pad columns of the raw maps carry no gradient
+            tape.add_grad(r, g.reshape(r.shape))
+        tape.backward()
+
+        # running statistics / counters, as nn.BatchNorm2d.forward leaves them
+        full = m.state_dict(keep_vars=True)
+        for name, (rm, rv) in self.new_stats.items():
+            full[name + ".running_mean"].copy_(rm)
+            full[name + ".running_var"].copy_(rv)
+            full[name + ".num_batches_tracked"].add_(1)
+        if hasattr(m, "mark_weights_dirty"):
+            m.mark_weights_dirty()
+        self.sd = None
+        return losses, tape.pgrad
+
+    def flat_gradient(self, grads: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """The gradients concatenated in `model.parameters()` order (what train.py:167's optimizer walks)."""
+        parts = []
+        for name, p in self.model.named_parameters():
+            g = grads[name]
+            if tuple(g.shape) != tuple(p.shape):
+                raise EngineError(f"gradient of {name} has shape {tuple(g.shape)}, parameter {tuple(p.shape)}")
+            parts.append(g.reshape(-1))
+        return torch.cat(parts)
