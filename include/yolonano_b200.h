@@ -404,6 +404,22 @@ int  ynb_conv3x3_tc(const float* in_dev, int32_t in_ld, float* out_dev, int32_t 
                     const float* b_dev, int32_t batch, int32_t h, int32_t w, int32_t cin, int32_t cout, int32_t act,
                     int32_t mode, void* stream);
 
+/* Training-grade tensor-core convs (replace nn.Conv2d forward / the input-gradient GEMM inside train.py:222-229's
+ * step): asynchronous on `stream`, no allocation, no host round trip — the hi / lo TF32 weight planes are packed by a
+ * kernel into `workspace` (>= ynb_tc_async_workspace_bytes(cout, ktot) bytes, 256-byte aligned; ktot = cin, or 9 * cin
+ * for the 3x3) right before the GEMM.  The last int32 of the workspace is the GEMM's pipeline-timeout flag (0 = ok).
+ * pointwise: out[pixels, cout] = act(in[pixels, cin] . W^T + b) with W [w_rows x w_cols] (w_rows <= cout, w_cols <= cin,
+ * zero beyond: channel padding) given as w_dev[w_rows][w_ld], or, w_trans = 1, as its transpose w_dev[w_cols][w_ld]
+ * (the input gradient of the layer whose weights are w_dev, without a transpose copy). */
+int64_t ynb_tc_async_workspace_bytes(int32_t cout, int32_t ktot);
+int  ynb_pwconv_tc_async(const float* in_dev, int32_t in_ld, int32_t in_off, float* out_dev, int32_t out_ld,
+                         int32_t out_off, int32_t out_step, const float* w_dev, int32_t w_ld, int32_t w_rows,
+                         int32_t w_cols, int32_t w_trans, const float* b_dev, int64_t pixels, int32_t cin, int32_t cout, int32_t act,
+                         int32_t mode, void* workspace, int64_t workspace_bytes, void* stream);
+int  ynb_conv3x3_tc_async(const float* in_dev, int32_t in_ld, float* out_dev, int32_t out_ld, const float* w_dev,
+                          const float* b_dev, int32_t batch, int32_t h, int32_t w, int32_t cin, int32_t cout,
+                          int32_t act, int32_t mode, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ModelEMA.update (utils/misc.py:78-86): for every floating-point state tensor  v = v * d + (1 - d) * m  with the
  * reference's two roundings (bit-identical), ALL tensors in one launch.  The caller passes device tables:
  * ema_ptrs_dev / model_ptrs_dev [T] device addresses of the float32 tensors, sizes_dev [T] element counts, and a

@@ -94,8 +94,10 @@ def test_reference_api_surface():
     m2 = copy.deepcopy(m)            # ModelEMA does this (utils/misc.py:70)
     assert len(m2.state_dict()) == 469
     m.trainable = True
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):                    # the training branch needs target (models/yolo_nano.py:333)
         m(torch.zeros(1, 3, 320, 320))
+    with pytest.raises(pkg.EngineError):               # and a CUDA device: no CPU fallback
+        m(torch.zeros(1, 3, 320, 320), target=torch.zeros(1, 2100, 11))
     with pytest.raises(SystemExit):
         with contextlib.redirect_stdout(io.StringIO()):
             pkg.YOLONano(torch.device("cpu"), 416, 80, anchor_size=pkg.MULTI_ANCHOR_SIZE_COCO, backbone="0.5x")

@@ -197,8 +197,11 @@ def test_forward_with_target_matches_reference_end_to_end(G, g7):
     m.load_state_dict(sd)
     m = m.to(G.DEV)
     m.trainable = True
-    with pytest.raises(NotImplementedError):          # BatchNorm with batch statistics is not built
-        m.train()(x.to(G.DEV), target=torch.from_numpy(g7["target"]).to(G.DEV))
+    keep = {k: v.clone() for k, v in m.state_dict().items()}
+    lt = m.train()(x.to(G.DEV), target=torch.from_numpy(g7["target"]).to(G.DEV))      # batch statistics + backward chain
+    assert len(lt) == 4 and all(bool(torch.isfinite(v)) for v in lt)
+    assert len(m.gradients) == 247 and all(tuple(m.gradients[k].shape) == tuple(p.shape) for k, p in m.named_parameters())
+    m.load_state_dict(keep)                            # the train() call moved the running statistics
     m.eval()
     ls = m(x.to(G.DEV), target=torch.from_numpy(g7["target"]).to(G.DEV))
     got = np.array([float(v) for v in ls], dtype=np.float32)
@@ -623,3 +626,86 @@ def test_chained_training_step_matches_reference_train_mode(G, golden):
         else:
             torch.testing.assert_close(msd[k].cpu(), v, rtol=2e-3, atol=2e-4, msg=k)
     assert flat_got.numel() == sum(p.numel() for p in m.parameters())
+
+
+def test_trainer_iterations_are_sgd_on_the_chained_gradients(G, golden):
+    """`Trainer.step` = train.py:219-235's loop body: two iterations (momentum buffer live in the second) against the
+    chained gradients of an identical second model + the CPU SGD oracle (`torch.optim.SGD` restated, train_oracle.py)
+    — parameters equal after each iteration, state_dict layout unchanged, BatchNorm counters advanced, and the
+    inference path of the trained model sees the new weights."""
+    import contextlib, io
+    import yolo_nano_b200 as pkg
+    from yolo_nano_b200.train_step import TrainStep, Trainer
+    from oracle import train_oracle as T
+    g = golden("g10_trainstep128.npz")
+    size, classes, seed, batch = int(g["size"]), int(g["classes"]), int(g["seed"]), int(g["batch"])
+    sd = W.calibrated(classes, seed=seed)
+    target = torch.from_numpy(g["target"]).to(G.DEV)
+    models = []
+    for _ in range(2):
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = pkg.YOLONano(G.DEV, size, classes, anchor_size=W.anchors_for(classes))
+        m.load_state_dict(sd)
+        m = m.to(G.DEV)
+        m.trainable = True
+        m.train()
+        models.append(m)
+    a, b = models
+    lr = 1e-5
+    ema = pkg.ModelEMA(a)
+    trainer = Trainer(a, lr=lr, ema=ema)
+    assert list(a.state_dict().keys()) == list(sd.keys())
+    fb = TrainStep(b)
+    buf = None
+    for it in range(2):
+        x = W.synthetic_input(batch, size, seed=seed + it).to(G.DEV)
+        la = trainer.step(x, target)
+        lb, gb = fb.forward_backward(x, target)
+        assert torch.equal(la, lb), (it, la, lb)
+        flat_p = torch.cat([p.detach().reshape(-1) for p in b.parameters()]).cpu()
+        new_p, buf = T.sgd_step(flat_p, fb.flat_gradient(gb).cpu(), buf, lr)
+        off = 0
+        for p in b.parameters():
+            p.data.copy_(new_p[off:off + p.numel()].view(p.shape))
+            off += p.numel()
+        b.mark_weights_dirty()
+        got = torch.cat([p.detach().reshape(-1) for p in a.parameters()]).cpu()
+        exact = bool(torch.equal(got, new_p))
+        print("[report] trainer iteration %d: parameters bit-identical to CPU SGD on the chained gradients: %s" % (it, exact))
+        torch.testing.assert_close(got, new_p, rtol=1e-6, atol=1e-7)
+        assert float((got - flat_p).abs().max()) > 0
+    assert trainer.flat.data_ptr() == next(a.parameters()).data_ptr()
+    assert int(a.state_dict()["backbone.conv1.1.num_batches_tracked"]) == 2 and ema.updates == 2
+    # the trained weights reach the inference plan
+    a.eval(); a.trainable = False
+    with contextlib.redirect_stdout(io.StringIO()):
+        fresh = pkg.YOLONano(G.DEV, size, classes, anchor_size=W.anchors_for(classes))
+    fresh.load_state_dict({k: v.detach().cpu() for k, v in a.state_dict().items()})
+    fresh = fresh.to(G.DEV).eval()
+    xe = W.synthetic_input(2, size, seed=3).to(G.DEV)
+    ra, rf = a.engine(2).forward_raw(xe), fresh.engine(2).forward_raw(xe)
+    for u, v in zip(ra, rf):
+        assert torch.equal(u, v)
+
+
+@pytest.mark.parametrize("m,k,kw,n,nreal,trans", [(1000, 60, 58, 60, 58, False), (333, 116, 116, 464, 464, False),
+                                                  (4096, 96, 96, 256, 255, False), (777, 60, 58, 116, 116, True),
+                                                  (64, 256, 255, 96, 96, True)])
+def test_async_pointwise_gemm_pads_and_transposes_on_the_device(G, m, k, kw, n, nreal, trans):
+    """`ynb_pwconv_tc_async` (the training step's GEMM): weights packed by a kernel — channel padding (zero rows /
+    columns) and the transposed read for the input gradient — against float64 matmul; 3xTF32 tolerance 2e-5 of max."""
+    from yolo_nano_b200 import training as TR
+    g = torch.Generator().manual_seed(m + n)
+    x = torch.randn(m, k, generator=g)
+    w = torch.randn(nreal, kw, generator=g) * 0.2          # logical W [out x in]
+    b = torch.randn(nreal, generator=g)
+    flags = []
+    wd = (w.t().contiguous() if trans else w).to(G.DEV)
+    y = TR.pwconv_forward(x.to(G.DEV), wd, b.to(G.DEV), act=0, transposed=trans, cout=n, flags=flags)
+    torch.cuda.synchronize()
+    assert not bool(torch.cat(flags).view(torch.int32).any())
+    want = torch.zeros(m, n, dtype=torch.float64)
+    want[:, :nreal] = x[:, :kw].double() @ w.double().t() + b.double()
+    err = float((y.cpu().double() - want).abs().max() / want.abs().max())
+    assert tuple(y.shape) == (m, n) and err < 2e-5, err
+    assert float(y[:, nreal:].abs().max()) == 0.0 if n > nreal else True

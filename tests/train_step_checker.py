@@ -20,6 +20,7 @@ class CheckedTrainStep(TrainStep):
     def __init__(self, model):
         super().__init__(model)
         self.records = []
+        self.check_flags = True
 
     def _wrap(self, tape, name, x, y, ref_fn, pnames):
         """ref_fn(x_req) -> y_ref, [param tensors requiring grad] ; compares dx and the parameter gradients."""

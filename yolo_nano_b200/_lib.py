@@ -117,6 +117,10 @@ SIGNATURES = {
     "ynb_resample_bwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
     "ynb_add": (C.c_int, [_p, _p, _p, _i64, _p]),
     "ynb_conv3x3_tc": (C.c_int, [_p, _i32, _p, _i32, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
+    "ynb_tc_async_workspace_bytes": (C.c_int64, [_i32, _i32]),
+    "ynb_pwconv_tc_async": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _p, _i32, _i32, _i32, _i32, _p, _i64, _i32, _i32,
+                                      _i32, _i32, _p, _i64, _p]),
+    "ynb_conv3x3_tc_async": (C.c_int, [_p, _i32, _p, _i32, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i64, _p]),
     "ynb_ema_chunk_elems": (_i32, []),
     "ynb_ema_update": (C.c_int, [_p, _p, _p, _p, _p, _i32, _f, _f, _p]),
     "ynb_act_bwd": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _p, _i32, _i32, _i64, _i32, _i32, _p]),

@@ -2292,6 +2292,129 @@ YNB_EXPORT int ynb_conv3x3_tc(const float* in, int32_t in_ld, float* out, int32_
   return rc;
 }
 
+// ---- training-grade tensor-core convs: asynchronous, no allocation, weights packed on the device -------------
+// The `ynb_pwconv_tc` / `ynb_conv3x3_tc` hooks above pack the weights on the host and synchronise (they exist for
+// the kernel unit tests).  A training step changes every weight every iteration, so here the hi / lo TF32 planes are
+// produced by a kernel into a caller-provided workspace, right before the GEMM on the same stream; nothing blocks.
+namespace {
+// w element (n, k) = trans ? w[k * w_ld + n] : w[n * w_ld + k]; zero outside rows x cols.
+__global__ void pack_tc_weights_kernel(const float* __restrict__ w, int w_ld, int rows, int cols, int trans,
+                                       float* __restrict__ hi, float* __restrict__ lo, int Npad, int Kpad, int* err_flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && err_flag) *err_flag = 0;
+  if (i >= Npad * Kpad) return;
+  const int n = i / Kpad, k = i - n * Kpad;
+  float v = 0.f;
+  if (n < rows && k < cols) v = trans ? w[(size_t)k * w_ld + n] : w[(size_t)n * w_ld + k];
+  const uint32_t h = rn_tf32_bits(__float_as_uint(v));
+  hi[i] = __uint_as_float(h);
+  lo[i] = __uint_as_float(rn_tf32_bits(__float_as_uint(v - __uint_as_float(h))));
+}
+
+struct AsyncWs { float* hi; float* lo; int* flag; };
+int64_t tc_async_bytes(int Npad, int Kpad) { return (int64_t)2 * Npad * Kpad * 4 + 256; }
+bool carve_async(void* ws, int64_t bytes, int Npad, int Kpad, AsyncWs* o) {
+  if (!ws || ((uintptr_t)ws & 255u) || bytes < tc_async_bytes(Npad, Kpad)) return false;
+  o->hi = (float*)ws;
+  o->lo = o->hi + (size_t)Npad * Kpad;
+  o->flag = (int*)(o->lo + (size_t)Npad * Kpad);
+  return true;
+}
+}  // namespace
+
+YNB_EXPORT int64_t ynb_tc_async_workspace_bytes(int32_t cout, int32_t ktot) {
+  return tc_async_bytes(round_up(cout, 16), round_up(ktot, kTcBK));
+}
+
+// Pointwise conv / dense layer out[M, cout] = act(in[M, cin] . W^T + b) on the tcgen05 path; W [w_rows x w_cols]
+// (zero beyond: channel padding) given as w_dev[w_rows][w_ld] (w_trans = 0) or as its transpose w_dev[w_cols][w_ld]
+// (w_trans = 1: the input-gradient GEMM of the same layer without a host-side transpose).
+// The last int of the workspace is the kernel's mbarrier-timeout flag (0 = fine), readable after the stream drains.
+YNB_EXPORT int ynb_pwconv_tc_async(const float* in, int32_t in_ld, int32_t in_off, float* out, int32_t out_ld,
+                                   int32_t out_off, int32_t out_step, const float* w_dev, int32_t w_ld, int32_t w_rows,
+                                   int32_t w_cols, int32_t w_trans, const float* b_dev, int64_t pixels, int32_t cin, int32_t cout, int32_t act,
+                                   int32_t mode, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!in || !out || !w_dev || !b_dev || cin % 4 || in_ld % 4 || in_off % 4 || out_ld % 4 || pixels < 1 || cout < 1 ||
+      w_cols < 1 || w_cols > cin || w_rows < 1 || w_rows > cout || w_ld < (w_trans ? w_rows : w_cols) ||
+      (out_step == 1 && out_off % 4) || cout > 256 || (mode != YNB_GEMM_TC_3XTF32 && mode != YNB_GEMM_TC_TF32))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_pwconv_tc_async: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  TcWeights t;
+  t.N = cout; t.Npad = round_up(cout, 16); t.Kpad = round_up(cin, kTcBK);
+  AsyncWs a;
+  if (!carve_async(workspace, workspace_bytes, t.Npad, t.Kpad, &a))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_pwconv_tc_async: workspace too small or not 256-byte aligned");
+  t.hi = a.hi; t.lo = a.lo;
+  const int total = t.Npad * t.Kpad;
+  pack_tc_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(w_dev, w_ld, w_rows, w_cols, w_trans, t.hi, t.lo, t.Npad,
+                                                              t.Kpad, a.flag);
+  TcGemmLaunch L;
+  L.w = &t;
+  TcGemmParams& p = L.p;
+  memset(&p, 0, sizeof(p));
+  p.mode = mode; p.num_steps = t.Kpad / kTcBK; p.chunks_per_tap = p.num_steps; p.ksub = (cin + 7) / 8;
+  p.M = pixels; p.num_tiles = (pixels + kTcBM - 1) / kTcBM; p.N = cout; p.Npad = t.Npad;
+  tc_plan_tmem(p);
+  p.a_box_bytes = kTcAStageBytes;
+  p.out = out; p.out_ld = out_ld; p.out_off = out_off; p.out_step = out_step; p.omap = dense_map();
+  p.bias = b_dev; p.act = act; p.err_flag = a.flag;
+  p.tma_store = (out_step == 1 && out_off % 4 == 0) ? 1 : 0;
+  if (!make_tmap_2d(&t.tm_hi, t.hi, t.Kpad, t.Npad, t.Kpad, t.Npad) ||
+      !make_tmap_2d(&t.tm_lo, t.lo, t.Kpad, t.Npad, t.Kpad, t.Npad) ||
+      (p.tma_store && !make_tmap_out(&L.tmOut, out + out_off, (uint64_t)round_up(cout, 4), (uint64_t)pixels,
+                                     (uint64_t)out_ld)) ||
+      !make_tmap_2d(&L.tmA, in + in_off, cin, pixels, in_ld, kTcBM) || !tc_plan_smem(L))
+    return fail(nullptr, YNB_ERR_CUDA, "ynb_pwconv_tc_async: tensor map / smem planning failed");
+  L.grid = (unsigned)std::min<int64_t>(p.num_tiles, kNumSMs);
+  UNIT_TRY(launch_tc_gemm(L, st));
+  return YNB_OK;
+}
+
+// Dense 3x3 conv, pad 1, stride 1 (w_dev [cout][9][cin] tap-major) — ynb_conv3x3_tc without the host round trip.
+YNB_EXPORT int ynb_conv3x3_tc_async(const float* in, int32_t in_ld, float* out, int32_t out_ld, const float* w_dev,
+                                    const float* b_dev, int32_t batch, int32_t h, int32_t w_, int32_t cin, int32_t cout,
+                                    int32_t act, int32_t mode, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!in || !out || !w_dev || !b_dev || batch <= 0 || h <= 0 || w_ <= 0 || cin <= 0 || cin % kTcBK || in_ld % 4 ||
+      out_ld % 4 || cout < 1 || cout > 256 || (mode != YNB_GEMM_TC_3XTF32 && mode != YNB_GEMM_TC_TF32) ||
+      (((uintptr_t)in | (uintptr_t)out) & 15u))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_conv3x3_tc_async: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ktot = 9 * cin;
+  TcWeights t;
+  t.N = cout; t.Npad = round_up(cout, 16); t.Kpad = ktot;
+  AsyncWs a;
+  if (!carve_async(workspace, workspace_bytes, t.Npad, t.Kpad, &a))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_conv3x3_tc_async: workspace too small or not 256-byte aligned");
+  t.hi = a.hi; t.lo = a.lo;
+  const int total = t.Npad * t.Kpad;
+  pack_tc_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(w_dev, ktot, cout, ktot, 0, t.hi, t.lo, t.Npad, t.Kpad, a.flag);
+  TcGemmLaunch L;
+  L.w = &t;
+  TcGemmParams& p = L.p;
+  memset(&p, 0, sizeof(p));
+  p.mode = mode; p.is3x3 = 1;
+  p.chunks_per_tap = cin / kTcBK;
+  p.num_steps = 9 * p.chunks_per_tap;
+  p.H = h; p.W = w_;
+  tc_pick_tile(p.H, p.W, &p.TH, &p.TW);
+  p.tiles_x = (p.W + p.TW - 1) / p.TW;
+  p.tiles_y = (p.H + p.TH - 1) / p.TH;
+  p.num_tiles = (int64_t)batch * p.tiles_x * p.tiles_y;
+  p.M = (int64_t)batch * h * w_;
+  p.N = cout; p.Npad = t.Npad;
+  tc_plan_tmem(p);
+  p.a_box_bytes = (uint32_t)(p.TH * p.TW * 128);
+  p.out = out; p.out_ld = out_ld; p.out_off = 0; p.out_step = 1; p.omap = dense_map();
+  p.bias = b_dev; p.act = act; p.err_flag = a.flag;
+  if (!make_tmap_2d(&t.tm_hi, t.hi, t.Kpad, t.Npad, t.Kpad, t.Npad) ||
+      !make_tmap_2d(&t.tm_lo, t.lo, t.Kpad, t.Npad, t.Kpad, t.Npad) ||
+      !make_tmap_nhwc(&L.tmA, in, cin, w_, h, batch, in_ld, p.TW, p.TH) || !tc_plan_smem(L))
+    return fail(nullptr, YNB_ERR_CUDA, "ynb_conv3x3_tc_async: tensor map / smem planning failed");
+  L.grid = (unsigned)std::min<int64_t>(p.num_tiles, kNumSMs);
+  UNIT_TRY(launch_tc_gemm(L, st));
+  return YNB_OK;
+}
+
 // ---- BatchNorm2d in training mode ----------------------------------------------------------------------
 namespace {
 bool bn_args_ok(long long M, int C, std::initializer_list<int> strides, std::initializer_list<const void*> ptrs) {

@@ -83,39 +83,28 @@ class TrainStep:
             raise EngineError("TrainStep needs the model on a CUDA device (no CPU fallback)")
         self.dev = p.device
         self.lib = _lib.load()
+        # debug: collect the pipeline-timeout flag of every tensor-core GEMM of a step and check them at its end
+        self.check_flags = False
+        self.flags = None
 
     # ---- kernel wrappers (NHWC float32, dense) ------------------------------------------------------------------
     def _st(self):
         return _stream_ptr(self.dev)
-
-    def _pw_fwd(self, x2d, w_nk, b):
-        m, k = x2d.shape
-        n = w_nk.shape[0]
-        y = torch.empty((m, n), device=self.dev, dtype=torch.float32)
-        for n0 in range(0, n, 256):
-            nc = min(256, n - n0)
-            T._check(self.lib.ynb_pwconv_tc(_ptr(x2d), k, 0, _ptr(y), n, n0, 1, _ptr(w_nk[n0:n0 + nc].contiguous()),
-                                            _ptr(b[n0:n0 + nc].contiguous()), m, k, nc, 0, _lib.GEMM_TC_3XTF32, self._st()),
-                     "ynb_pwconv_tc")
-        return y
 
     # ---- ops: forward now, closure for backward -----------------------------------------------------------------
     def _param(self, name):
         return self.sd[name]
 
     def pw(self, tape, x, conv, bias: bool):
-        """1x1 conv on [B,H,W,K] (K, N padded to multiples of 4 with zero weights)."""
+        """1x1 conv on [B,H,W,K] (K, N padded to multiples of 4: zero weights, packed by the GEMM's own pack kernel)."""
         w = self._param(conv + ".weight")
         n, k = w.shape[0], w.shape[1]
+        w2 = w.reshape(n, k)
         np_, kp = _pad4(n), x.shape[-1]
-        wp = torch.zeros((np_, kp), device=self.dev)
-        wp[:n, :k] = w.reshape(n, k)
-        bp = torch.zeros(np_, device=self.dev)
-        if bias:
-            bp[:n] = self._param(conv + ".bias")
+        b = self._param(conv + ".bias") if bias else None
         shp = x.shape
         x2 = x.reshape(-1, kp)
-        y = self._pw_fwd(x2, wp, bp).reshape(*shp[:-1], np_)
+        y = T.pwconv_forward(x2, w2, b, cout=np_, flags=self.flags).reshape(*shp[:-1], np_)
 
         def bw():
             dy = tape.take(y).reshape(-1, np_)
@@ -123,7 +112,7 @@ class TrainStep:
             tape.pgrad[conv + ".weight"] = dw[:n, :k].reshape(n, k, 1, 1).contiguous()
             if bias:
                 tape.pgrad[conv + ".bias"] = db[:n].contiguous()
-            tape.add_grad(x, T.pwconv_backward_data(dy, wp).reshape(shp))
+            tape.add_grad(x, T.pwconv_forward(dy, w2, None, transposed=True, cout=kp, flags=self.flags).reshape(shp))
         tape.ops.append(bw)
         return y
 
@@ -159,9 +148,7 @@ class TrainStep:
         wf = w.permute(0, 2, 3, 1).reshape(n, 9, k).contiguous()            # [n][t][k]
         bias = self._param(conv + ".bias").contiguous()
         b_, h, w_, _ = x.shape
-        y = torch.empty((b_, h, w_, n), device=self.dev)
-        T._check(self.lib.ynb_conv3x3_tc(_ptr(x), k, _ptr(y), n, _ptr(wf), _ptr(bias), b_, h, w_, k, n, 0,
-                                         _lib.GEMM_TC_3XTF32, self._st()), "ynb_conv3x3_tc")
+        y = T.conv3x3_forward(x, wf, bias, flags=self.flags)
 
         def bw():
             dy = tape.take(y)
@@ -169,11 +156,7 @@ class TrainStep:
             tape.pgrad[conv + ".weight"] = dw9.permute(1, 2, 0).reshape(n, k, 3, 3).contiguous()
             tape.pgrad[conv + ".bias"] = db
             wd = w.permute(1, 2, 3, 0).reshape(k, 9, n).flip(1).contiguous()  # [k][8 - t][n]
-            dx = torch.empty_like(x)
-            zero = torch.zeros(k, device=self.dev)
-            T._check(self.lib.ynb_conv3x3_tc(_ptr(dy), n, _ptr(dx), k, _ptr(wd), _ptr(zero), b_, h, w_, n, k, 0,
-                                             _lib.GEMM_TC_3XTF32, self._st()), "ynb_conv3x3_tc (dgrad)")
-            tape.add_grad(x, dx)
+            tape.add_grad(x, T.conv3x3_forward(dy, wd, torch.zeros(k, device=self.dev), flags=self.flags))
         tape.ops.append(bw)
         return y
 
@@ -273,6 +256,7 @@ class TrainStep:
         bsz, s = int(x.shape[0]), int(x.shape[2])
         self.sd = {k: v.detach() for k, v in m.state_dict(keep_vars=True).items()}
         self.new_stats: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self.flags = [] if self.check_flags else None
         tape = _Tape(dev)
         lib = self.lib
 
@@ -338,6 +322,11 @@ class TrainStep:
             g[..., nch:] = 0.0                      # pad columns of the raw maps carry no gradient
             tape.add_grad(r, g.reshape(r.shape))
         tape.backward()
+        if self.flags:
+            bad = torch.cat(self.flags).view(torch.int32)
+            if bool(bad.any()):
+                raise EngineError("a tensor-core GEMM of the training step reported a pipeline timeout: %s"
+                                  % bad.nonzero().flatten().tolist())
 
         # running statistics / counters, as nn.BatchNorm2d.forward leaves them
         full = m.state_dict(keep_vars=True)
@@ -359,3 +348,53 @@ class TrainStep:
                 raise EngineError(f"gradient of {name} has shape {tuple(g.shape)}, parameter {tuple(p.shape)}")
             parts.append(g.reshape(-1))
         return torch.cat(parts)
+
+
+class Trainer:
+    """One iteration of the reference's loop body (train.py:219-235) per `step(images, targets)`:
+
+        losses = model(images, target=targets); total = sum(losses)
+        if isnan(total): continue                      # skip_nan (train.py:225-226; costs a host read, as there)
+        total.backward(); optimizer.step(); optimizer.zero_grad()
+        if ema: ema.update(model)
+
+    The parameters are moved into ONE flat float32 vector (each `p.data` becomes a view of it, state_dict layout
+    unchanged), so that the data-parallel step is one NCCL all-reduce of 5.3 MB + one fused SGD launch
+    (`FlatSGD`; `DistributedDataParallel`'s gradient averaging = the 1 / world folded into that kernel), and the
+    EMA one more launch.  `set_lr` = train.py:337-339."""
+
+    def __init__(self, model, lr: float, momentum: float = 0.9, weight_decay: float = 5e-4, ema=None, group=None,
+                 skip_nan: bool = True):
+        self.model, self.ema, self.group, self.skip_nan = model, ema, group, skip_nan
+        self.fb = TrainStep(model)
+        ps = list(model.parameters())
+        for p in ps:
+            if p.dtype != torch.float32 or not p.is_cuda:
+                raise EngineError("Trainer: parameters must be float32 CUDA tensors (no CPU fallback)")
+        flat = torch.cat([p.detach().reshape(-1) for p in ps])
+        off = 0
+        for p in ps:
+            n = p.numel()
+            p.data = flat[off:off + n].view(p.shape)
+            off += n
+        self.flat = flat
+        self.opt = T.FlatSGD(flat, lr, momentum, weight_decay)
+        self.skipped = 0
+        if hasattr(model, "mark_weights_dirty"):
+            model.mark_weights_dirty()
+
+    def set_lr(self, lr: float):
+        self.opt.set_lr(lr)
+
+    @torch.no_grad()
+    def step(self, images: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+        losses, grads = self.fb.forward_backward(images, targets)
+        if self.skip_nan and bool(torch.isnan(losses.sum()).item()):
+            self.skipped += 1
+            return losses
+        self.opt.step(self.fb.flat_gradient(grads), self.group)
+        if hasattr(self.model, "mark_weights_dirty"):
+            self.model.mark_weights_dirty()
+        if self.ema is not None:
+            self.ema.update(self.model)
+        return losses

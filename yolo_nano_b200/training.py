@@ -169,25 +169,82 @@ def conv3x3_backward_weight(dout: torch.Tensor, x: torch.Tensor):
     return dw, db
 
 
-def pwconv_backward_data(dout: torch.Tensor, w_nk: torch.Tensor, tensor_cores: bool = True) -> torch.Tensor:
-    """dx [M, K] = dout [M, N] . w [N, K]: the forward pointwise GEMM with the transposed weights and a
+def _tc_workspace(cout: int, ktot: int, dev):
+    n = int(_lib.load().ynb_tc_async_workspace_bytes(cout, ktot))
+    return torch.empty(n, device=dev, dtype=torch.uint8), n
+
+
+def pwconv_forward(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], act: int = 0, transposed: bool = False,
+                   cout: Optional[int] = None, flags: Optional[list] = None) -> torch.Tensor:
+    """y [M, N] = act(x [M, K] . W^T + b) on the tcgen05 GEMM (3xTF32), asynchronous (`ynb_pwconv_tc_async`: the weights
+    are split into hi / lo planes by a kernel on the same stream).
+    transposed = False: W = w [N, Kw] (Kw <= K; missing input channels have zero weight), N = w.shape[0] or `cout`
+                        (rows beyond w.shape[0] are zero: channel padding).
+    transposed = True:  W^T = w [Kw, Nw]: y = x . w — the input gradient of the layer whose weight is w."""
+    dev = _dev(x, w, b)
+    lib = _lib.load()
+    m, k = x.shape
+    if w.stride(-1) != 1:
+        w = w.contiguous()
+    ld = w.stride(0)
+    if transposed:
+        kw, n_real = w.shape
+    else:
+        n_real, kw = w.shape
+    n = n_real if cout is None else int(cout)
+    y = torch.empty((m, n), device=dev, dtype=torch.float32)
+    if b is None:
+        b = torch.zeros(n, device=dev, dtype=torch.float32)
+    elif b.numel() < n:
+        b = torch.cat((b, b.new_zeros(n - b.numel())))
+    for n0 in range(0, n, 256):                       # the GEMM holds at most 256 output columns in TMEM
+        nc = min(256, n - n0)
+        rows = max(0, min(nc, n_real - n0))           # real weight rows in this slice (the rest: zero rows)
+        if rows == 0:
+            y[:, n0:n0 + nc] = b[n0:n0 + nc]
+            continue
+        ws, wsb = _tc_workspace(nc, k, dev)
+        wp = w[:, n0:] if transposed else w[n0:]
+        # rows < nc only when padding the channel count: the pack kernel zero-fills rows >= `rows`
+        _check(lib.ynb_pwconv_tc_async(_ptr(x), k, 0, _ptr(y), n, n0, 1, _ptr(wp), ld, rows, kw, int(transposed), _ptr(b[n0:]),
+                                       m, k, nc, act, _lib.GEMM_TC_3XTF32, _ptr(ws), wsb, _stream_ptr(dev)),
+               "ynb_pwconv_tc_async")
+        if flags is not None:
+            flags.append(ws[-256:-252])
+    return y
+
+
+def pwconv_backward_data(dout: torch.Tensor, w_nk: torch.Tensor, tensor_cores: bool = True, flags: Optional[list] = None
+                         ) -> torch.Tensor:
+    """dx [M, K] = dout [M, N] . w [N, K]: the forward pointwise GEMM with the weights read transposed and a
     zero bias (tcgen05 3xTF32 by default).  N and K must be multiples of 4."""
     dev = _dev(dout, w_nk)
+    if tensor_cores:
+        return pwconv_forward(dout, w_nk, None, transposed=True, flags=flags)
     lib = _lib.load()
     m, n = dout.shape
     k = w_nk.shape[1]
     wt = w_nk.t().contiguous()                      # [K][N]: "cout" = K, "cin" = N
     zero = torch.zeros(k, device=dev, dtype=torch.float32)
     dx = torch.empty((m, k), device=dev, dtype=torch.float32)
-    if tensor_cores:
-        for k0 in range(0, k, 256):                 # the tcgen05 GEMM holds at most 256 output columns in TMEM
-            kc = min(256, k - k0)
-            _check(lib.ynb_pwconv_tc(_ptr(dout), n, 0, _ptr(dx), k, k0, 1, _ptr(wt[k0:k0 + kc]), _ptr(zero), m, n, kc, 0,
-                                     _lib.GEMM_TC_3XTF32, _stream_ptr(dev)), "ynb_pwconv_tc")
-    else:
-        _check(lib.ynb_pwconv(_ptr(dout), n, 0, _ptr(dx), k, 0, 1, _ptr(wt), _ptr(zero), m, n, k, 0,
-                              _stream_ptr(dev)), "ynb_pwconv")
+    _check(lib.ynb_pwconv(_ptr(dout), n, 0, _ptr(dx), k, 0, 1, _ptr(wt), _ptr(zero), m, n, k, 0,
+                          _stream_ptr(dev)), "ynb_pwconv")
     return dx
+
+
+def conv3x3_forward(x: torch.Tensor, w_ntk: torch.Tensor, b: torch.Tensor, act: int = 0, flags: Optional[list] = None
+                    ) -> torch.Tensor:
+    """Dense 3x3, pad 1, stride 1 on NHWC x [B,H,W,K] (K % 32 == 0) with w [N][9][K] tap-major (asynchronous)."""
+    dev = _dev(x, w_ntk, b)
+    bsz, h, w_, k = x.shape
+    n = w_ntk.shape[0]
+    y = torch.empty((bsz, h, w_, n), device=dev, dtype=torch.float32)
+    ws, wsb = _tc_workspace(n, 9 * k, dev)
+    _check(_lib.load().ynb_conv3x3_tc_async(_ptr(x), k, _ptr(y), n, _ptr(w_ntk), _ptr(b), bsz, h, w_, k, n, act,
+                                            _lib.GEMM_TC_3XTF32, _ptr(ws), wsb, _stream_ptr(dev)), "ynb_conv3x3_tc_async")
+    if flags is not None:
+        flags.append(ws[-256:-252])
+    return y
 
 
 def act_backward(dout: torch.Tensor, out: torch.Tensor, act: int) -> torch.Tensor:
@@ -257,14 +314,7 @@ class PwConvTrain:
         m, k = x.shape
         n = self.w.shape[0]
         self.x = x
-        y = torch.empty((m, n), device=dev, dtype=torch.float32)
-        b = self.b if self.b is not None else torch.zeros(n, device=dev)
-        lib = _lib.load()
-        for n0 in range(0, n, 256):
-            nc = min(256, n - n0)
-            _check(lib.ynb_pwconv_tc(_ptr(x), k, 0, _ptr(y), n, n0, 1, _ptr(self.w[n0:n0 + nc]), _ptr(b[n0:n0 + nc]), m, k,
-                                     nc, 0, _lib.GEMM_TC_3XTF32, _stream_ptr(dev)), "ynb_pwconv_tc")
-        return y
+        return pwconv_forward(x, self.w, self.b)
 
     def backward(self, dy: torch.Tensor) -> torch.Tensor:
         dw, db = pwconv_backward_weight(dy, self.x)

@@ -168,6 +168,7 @@ class YOLONano(nn.Module):
         object.__setattr__(self, "_weights_key", None)
         object.__setattr__(self, "_wt_cache", None)
         object.__setattr__(self, "_out_cache", None)
+        object.__setattr__(self, "_train_step", None)
 
     # ---- reference API ---------------------------------------------------------------
     def init_bias(self):
@@ -283,7 +284,7 @@ class YOLONano(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ("_engine", "_engine_key", "_weights_key", "_wt_cache", "_out_cache"):
+            if k in ("_engine", "_engine_key", "_weights_key", "_wt_cache", "_out_cache", "_train_step"):
                 object.__setattr__(new, k, None)
             else:
                 object.__setattr__(new, k, copy.deepcopy(v, memo))
@@ -361,17 +362,25 @@ class YOLONano(nn.Module):
 
     def forward(self, x, target=None):
         if self.trainable:
-            # training branch (models/yolo_nano.py:333-358).  Built for BatchNorm in eval mode (running
-            # statistics, folded into the convs): losses of the whole batch and, kept on the model as
-            # `head_gradients`, d(sum of the four)/d(raw head maps) — what train.py:222-229 back-propagates
-            # into the heads.  The returned losses are plain device scalars WITHOUT a grad_fn: the backward chain
-            # through the 77 convolutions is not built, so train.py's `total_loss.backward()` has no counterpart
-            # here (this class is a drop-in for the detection forward path only).
+            # training branch (models/yolo_nano.py:333-358).  The returned losses are plain device scalars WITHOUT a
+            # grad_fn — there is no autograd graph on this path.
+            #   model.train():  BatchNorm on batch statistics; the SAME call also runs the backward chain through
+            #     all 77 convolutions (train_step.TrainStep) and leaves d(sum of the four losses)/d(parameter) in
+            #     `model.gradients` {name: tensor} — what train.py:229's `total_loss.backward()` leaves in `.grad`.
+            #     `train_step.Trainer` is the loop body of train.py (SGD / all-reduce / EMA on top of this).
+            #   model.eval():   running statistics folded into the convs; losses + `model.head_gradients`
+            #     (d/d raw head maps) from the inference engine.
             if self.training:
-                raise NotImplementedError(
-                    "the chained training step (batch-statistics BatchNorm through the 77 convolutions + backward) is "
-                    "not built: this class replaces the detection forward path, not train.py.  For the losses and "
-                    "the head gradients on running statistics call model.eval() and keep model.trainable = True")
+                if target is None:
+                    raise ValueError("trainable forward needs target [B, N, 11] (tools.multi_gt_creator)")
+                from .train_step import TrainStep
+                if self._train_step is None:
+                    object.__setattr__(self, "_train_step", TrainStep(self))
+                dev = self._device()
+                losses, grads = self._train_step.forward_backward(
+                    x.to(dev, torch.float32), target.to(dev, torch.float32))
+                object.__setattr__(self, "gradients", grads)
+                return losses[0], losses[1], losses[2], losses[3]
             if target is None:
                 raise ValueError("trainable forward needs target [B, N, 11] (tools.multi_gt_creator)")
             eng = self.engine(int(x.shape[0]))
