@@ -389,6 +389,12 @@ int  ynb_maxpool3x3s2_fwd(const float* in_dev, float* out_dev, int32_t batch, in
                           void* stream);
 int  ynb_maxpool3x3s2_bwd(const float* dout_dev, const float* in_dev, float* din_dev, int32_t batch, int32_t h, int32_t w,
                           int32_t channels, void* stream);
+/* The same pair keeping the arg-max like ATen's max_pool2d_with_indices: idx_dev [B, Ho, Wo, C] uint8 = winning tap
+ * (ky * 3 + kx, first maximum in row-major order); the backward is then a gather (no re-scan of the windows). */
+int  ynb_maxpool3x3s2_fwd_idx(const float* in_dev, float* out_dev, uint8_t* idx_dev, int32_t batch, int32_t h, int32_t w,
+                              int32_t channels, void* stream);
+int  ynb_maxpool3x3s2_bwd_idx(const float* dout_dev, const uint8_t* idx_dev, float* din_dev, int32_t batch, int32_t h,
+                              int32_t w, int32_t channels, void* stream);
 /* FPN / PAN merge out = a + F.interpolate(a2) (models/yolo_nano.py:291-296; mode 1: a2 is (h/2 x w/2), nearest x2;
  * mode 2: a2 is (2h x 2w), [::2, ::2]) and the gradient w.r.t. a2 (d a = d out). */
 int  ynb_resample_add(const float* a_dev, const float* a2_dev, float* out_dev, int32_t batch, int32_t h, int32_t w,

@@ -628,8 +628,9 @@ def test_chained_training_step_matches_reference_train_mode(G, golden):
     assert flat_got.numel() == sum(p.numel() for p in m.parameters())
 
 
-def test_trainer_iterations_are_sgd_on_the_chained_gradients(G, golden):
-    """`Trainer.step` = train.py:219-235's loop body: two iterations (momentum buffer live in the second) against the
+def test_trainer_iterations_are_sgd_on_the_chained_gradients(G, golden, monkeypatch):
+    """`Trainer.step` = train.py:219-235's loop body: three iterations (momentum buffer live from the second; the first
+    runs eagerly, the second is captured into a CUDA graph and replayed, the third replays it) against the
     chained gradients of an identical second model + the CPU SGD oracle (`torch.optim.SGD` restated, train_oracle.py)
     — parameters equal after each iteration, state_dict layout unchanged, BatchNorm counters advanced, and the
     inference path of the trained model sees the new weights."""
@@ -637,6 +638,7 @@ def test_trainer_iterations_are_sgd_on_the_chained_gradients(G, golden):
     import yolo_nano_b200 as pkg
     from yolo_nano_b200.train_step import TrainStep, Trainer
     from oracle import train_oracle as T
+    monkeypatch.delenv("YNB_SYNC_CHECK", raising=False)      # a host read of a kernel flag cannot be captured into a graph
     g = golden("g10_trainstep128.npz")
     size, classes, seed, batch = int(g["size"]), int(g["classes"]), int(g["seed"]), int(g["batch"])
     sd = W.calibrated(classes, seed=seed)
@@ -653,11 +655,11 @@ def test_trainer_iterations_are_sgd_on_the_chained_gradients(G, golden):
     a, b = models
     lr = 1e-5
     ema = pkg.ModelEMA(a)
-    trainer = Trainer(a, lr=lr, ema=ema)
+    trainer = Trainer(a, lr=lr, ema=ema, cuda_graph=True)      # iteration 0 eager, 1 captured + replayed, 2 replayed
     assert list(a.state_dict().keys()) == list(sd.keys())
     fb = TrainStep(b)
     buf = None
-    for it in range(2):
+    for it in range(3):
         x = W.synthetic_input(batch, size, seed=seed + it).to(G.DEV)
         la = trainer.step(x, target)
         lb, gb = fb.forward_backward(x, target)
@@ -675,7 +677,8 @@ def test_trainer_iterations_are_sgd_on_the_chained_gradients(G, golden):
         torch.testing.assert_close(got, new_p, rtol=1e-6, atol=1e-7)
         assert float((got - flat_p).abs().max()) > 0
     assert trainer.flat.data_ptr() == next(a.parameters()).data_ptr()
-    assert int(a.state_dict()["backbone.conv1.1.num_batches_tracked"]) == 2 and ema.updates == 2
+    assert int(a.state_dict()["backbone.conv1.1.num_batches_tracked"]) == 3 and ema.updates == 3
+    assert int(a.state_dict()["backbone.stage2.1.branch2.4.num_batches_tracked"]) == 3
     # the trained weights reach the inference plan
     a.eval(); a.trainable = False
     with contextlib.redirect_stdout(io.StringIO()):

@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32, help="images per GPU")
     ap.add_argument("--size", type=int, default=416)
+    ap.add_argument("--no-graph", action="store_true", help="launch the ~1600 kernels of a step one by one")
+    ap.add_argument("--profile", action="store_true", help="host enqueue time + kernel table (torch.profiler / CUPTI)")
     ap.add_argument("out", nargs="?", default="")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -48,7 +50,7 @@ def main():
     with contextlib.redirect_stdout(io.StringIO()):
         m = pkg.YOLONano(dev, a.size, classes, anchor_size=anchors, trainable=True)
     m = m.to(dev).train()
-    trainer = Trainer(m, lr=1e-3, skip_nan=False)
+    trainer = Trainer(m, lr=1e-3, skip_nan=False, cuda_graph=not a.no_graph)
     g = torch.Generator().manual_seed(100 + rank)
     x_h = torch.randn(a.batch, 3, a.size, a.size, generator=g).pin_memory()
     nlab = 8
@@ -89,6 +91,25 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), ls
 
+    if a.profile:
+        import time
+        from torch.profiler import ProfilerActivity, profile
+        for _ in range(3):
+            step_dev()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            step_dev()
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        print("host enqueue %.1f ms/step, drained after %.1f ms more" % ((t1 - t0) / 5 * 1e3, (t2 - t1) * 1e3))
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                step_dev()
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+        return
     ms, ls = timed(step_dev)
     ms_e2e, _ = timed(step_host)
     res = {"metric": "images/sec YOLO-Nano-1.0x training step %d bs%d/GPU (train-mode BN, backward, all-reduce, SGD)" % (a.size, a.batch),
@@ -99,7 +120,7 @@ def main():
                       "parameters": int(trainer.flat.numel()), "optimizer": "SGD momentum 0.9 wd 5e-4, one flat all-reduce"},
            "e2e": {"value": world * a.batch / (ms_e2e * 1e-3), "unit": "images/sec",
                    "h2d_bytes_per_step": int(x_h.numel() * 4 + lab_h.numel() * 4), "d2h_bytes_per_step": 16},
-           "losses_last_step": [float(v) for v in ls.cpu()], "tuned": False}
+           "losses_last_step": [float(v) for v in ls.cpu()], "cuda_graph": not a.no_graph}
     if rank == 0:
         print(json.dumps(res), flush=True)
         if a.out:

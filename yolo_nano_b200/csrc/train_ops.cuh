@@ -1076,32 +1076,62 @@ stem_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, f
   }
 }
 
-// dW[tap][co] = sum over output pixels of dout[pix][co] * x[pix shifted by tap]: a block owns a chunk of output
-// pixels, thread t = (tap, co) of the 27 x 24 = 648 products; per-chunk partials, fixed-order second stage.
-constexpr int kStemWgThreads = 27 * 24;
+// dW[tap][co] = sum over output pixels of dout[pix][co] * x[pix shifted by tap]  (27 x 24 outputs, ~10^6 pixels).
+// Work item = a segment of <= 128 output pixels of one output row: the 9 input rows (3 channels x 3 filter rows) it
+// touches and its d out rows are staged in shared memory with coalesced loads; thread = (half, tap, group of 4 output
+// channels) of 2 x 27 x 6 = 324, one 4-byte and one 16-byte shared load per 4 FMAs; the two halves take alternate
+// pixels.  A block walks its items in a fixed order; per-(block, half) partials, fixed-order second stage.
+constexpr int kStemWgOut = 27 * 24;
+constexpr int kStemWgTW = 128;
+constexpr int kStemWgThreads = 352;
 __global__ void __launch_bounds__(kStemWgThreads)
 stem_conv_bwd_weight_kernel(const float* __restrict__ dout, const float* __restrict__ x, float* __restrict__ partial, int B,
-                            int S, long long pix_per_chunk) {
+                            int S, int items, int nseg) {
+  __shared__ float in_s[9][2 * kStemWgTW + 2];
+  __shared__ float4 dy_s[kStemWgTW][6];
   const int Hc = S / 2;
-  const long long total = (long long)B * Hc * Hc;
-  const int tap = threadIdx.x / 24, co = threadIdx.x - tap * 24;
-  const int ci = tap / 9, ky = (tap % 9) / 3, kx = tap % 3;
-  const long long p0 = (long long)blockIdx.x * pix_per_chunk, p1 = min(p0 + pix_per_chunk, total);
-  float s = 0.0f;
-  for (long long pix = p0; pix < p1; ++pix) {
-    const int xo = (int)(pix % Hc), yo = (int)((pix / Hc) % Hc), b = (int)(pix / ((long long)Hc * Hc));
-    const int yi = 2 * yo + ky - 1, xi = 2 * xo + kx - 1;
-    if (yi < 0 || yi >= S || xi < 0 || xi >= S) continue;
-    s = fmaf(__ldg(dout + pix * 24 + co), __ldg(x + (((size_t)b * 3 + ci) * S + yi) * S + xi), s);
+  const int t = threadIdx.x;
+  const bool active = t < 324;
+  const int h = t / 162, r = t - h * 162;
+  const int tap = r / 6, cg = r - tap * 6;
+  const int row_s = (tap / 9) * 3 + (tap % 9) / 3, kx = tap % 3;
+  const float4* dout4 = reinterpret_cast<const float4*>(dout);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int seg = item % nseg, row = item / nseg;
+    const int yo = row % Hc, b = row / Hc;
+    const int x0 = seg * kStemWgTW, tw = min(kStemWgTW, Hc - x0);
+    const int ncols = 2 * tw + 1;
+    __syncthreads();
+    for (int i = t; i < 9 * ncols; i += kStemWgThreads) {
+      const int rr = i / ncols, cc = i - rr * ncols;
+      const int yi = 2 * yo + (rr % 3) - 1, xi = 2 * x0 - 1 + cc;
+      float v = 0.f;
+      if (yi >= 0 && yi < S && xi >= 0 && xi < S) v = __ldg(x + (((size_t)b * 3 + rr / 3) * S + yi) * S + xi);
+      in_s[rr][cc] = v;
+    }
+    const size_t base4 = (((size_t)b * Hc + yo) * Hc + x0) * 6;
+    for (int i = t; i < tw * 6; i += kStemWgThreads) (&dy_s[0][0])[i] = __ldg(dout4 + base4 + i);
+    __syncthreads();
+    if (active) {
+#pragma unroll 4
+      for (int p = h; p < tw; p += 2) {
+        const float xv = in_s[row_s][2 * p + kx];
+        const float4 d = dy_s[p][cg];
+        acc.x = fmaf(xv, d.x, acc.x); acc.y = fmaf(xv, d.y, acc.y);
+        acc.z = fmaf(xv, d.z, acc.z); acc.w = fmaf(xv, d.w, acc.w);
+      }
+    }
   }
-  partial[(long long)blockIdx.x * kStemWgThreads + threadIdx.x] = s;
+  if (active)
+    *reinterpret_cast<float4*>(partial + ((size_t)blockIdx.x * 2 + h) * kStemWgOut + tap * 24 + cg * 4) = acc;
 }
-inline int stem_wg_chunks(int B, int S) {
-  const long long total = (long long)B * (S / 2) * (S / 2);
-  long long c = (total + 255) / 256;
-  if (c > kNumSMs * 16) c = kNumSMs * 16;
-  return (int)(c < 1 ? 1 : c);
+inline int stem_wg_nseg(int S) { return (S / 2 + kStemWgTW - 1) / kStemWgTW; }
+inline int stem_wg_grid(int B, int S) {
+  const long long items = (long long)B * (S / 2) * stem_wg_nseg(S);
+  return (int)std::min<long long>(items, (long long)kNumSMs * 4);
 }
+inline int stem_wg_chunks(int B, int S) { return 2 * stem_wg_grid(B, S); }     // partial rows of 648 floats
 
 // ---- MaxPool2d(3, stride 2, pad 1) on NHWC (backbone/shufflenetv2.py:116), forward and backward ------------------
 __global__ void __launch_bounds__(256)
@@ -1157,6 +1187,63 @@ maxpool3x3s2_bwd_kernel(const float* __restrict__ dout, const float* __restrict_
         if (first) g += dout[(((size_t)b * Ho + yo) * Wo + xo) * C + c];
       }
     din[i] = g;
+  }
+}
+
+// The same pair with the arg-max kept (what ATen's max_pool2d_with_indices does): forward also writes, per output
+// element, which of the 9 taps (ky * 3 + kx, first maximum in row-major order) won; backward is then a gather — one
+// thread per 4 input channels reads the <= 4 windows that contain its pixel (4 index bytes + 16 bytes of d out each).
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_fwd_idx_kernel(const float* __restrict__ in, float* __restrict__ out, uint8_t* __restrict__ idx, int B, int H,
+                            int W, int C) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1, G = C / 4;
+  const long long total = (long long)B * Ho * Wo * G;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int g = (int)(i % G);
+    const long long pix = i / G;
+    const int xo = (int)(pix % Wo), yo = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    uchar4 w = make_uchar4(255, 255, 255, 255);
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yi = 2 * yo + ky - 1;
+      if (yi < 0 || yi >= H) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xi = 2 * xo + kx - 1;
+        if (xi < 0 || xi >= W) continue;
+        const float4 v = *reinterpret_cast<const float4*>(in + (((size_t)b * H + yi) * W + xi) * C + 4 * g);
+        const unsigned char tp = (unsigned char)(ky * 3 + kx);
+        if (v.x > m.x || w.x == 255) { m.x = v.x; w.x = tp; }
+        if (v.y > m.y || w.y == 255) { m.y = v.y; w.y = tp; }
+        if (v.z > m.z || w.z == 255) { m.z = v.z; w.z = tp; }
+        if (v.w > m.w || w.w == 255) { m.w = v.w; w.w = tp; }
+      }
+    }
+    *reinterpret_cast<float4*>(out + pix * C + 4 * g) = m;
+    *reinterpret_cast<uchar4*>(idx + pix * C + 4 * g) = w;
+  }
+}
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_bwd_idx_kernel(const float* __restrict__ dout, const uint8_t* __restrict__ idx, float* __restrict__ din, int B,
+                            int H, int W, int C) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1, G = C / 4;
+  const long long total = (long long)B * H * W * G;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int g = (int)(i % G);
+    const long long pix = i / G;
+    const int xi = (int)(pix % W), yi = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int yo = max(0, yi / 2); yo <= min(Ho - 1, (yi + 1) / 2); ++yo)          // ascending (yo, xo): fixed order
+      for (int xo = max(0, xi / 2); xo <= min(Wo - 1, (xi + 1) / 2); ++xo) {
+        const unsigned char me = (unsigned char)((yi - 2 * yo + 1) * 3 + (xi - 2 * xo + 1));
+        const size_t o = (((size_t)b * Ho + yo) * Wo + xo) * C + 4 * g;
+        const uchar4 w = *reinterpret_cast<const uchar4*>(idx + o);
+        const float4 d = *reinterpret_cast<const float4*>(dout + o);
+        if (w.x == me) s.x += d.x;
+        if (w.y == me) s.y += d.y;
+        if (w.z == me) s.z += d.z;
+        if (w.w == me) s.w += d.w;
+      }
+    *reinterpret_cast<float4*>(din + pix * C + 4 * g) = s;
   }
 }
 

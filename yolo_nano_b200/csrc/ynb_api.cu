@@ -2156,7 +2156,7 @@ YNB_EXPORT int ynb_stem_conv_fwd(const float* x, const float* w2724, float* out,
 }
 
 YNB_EXPORT int64_t ynb_stem_conv_bwd_weight_workspace_bytes(int32_t batch, int32_t input_size) {
-  return (int64_t)stem_wg_chunks(batch, input_size) * kStemWgThreads * sizeof(float);
+  return (int64_t)stem_wg_chunks(batch, input_size) * kStemWgOut * sizeof(float);
 }
 
 YNB_EXPORT int ynb_stem_conv_bwd_weight(const float* dout, const float* x, float* dw2724, int32_t batch, int32_t input_size,
@@ -2164,13 +2164,15 @@ YNB_EXPORT int ynb_stem_conv_bwd_weight(const float* dout, const float* x, float
   if (!dout || !x || !dw2724 || !ws || batch <= 0 || input_size <= 0 || input_size % 2 ||
       ws_bytes < ynb_stem_conv_bwd_weight_workspace_bytes(batch, input_size))
     return fail(nullptr, YNB_ERR_INVALID, "ynb_stem_conv_bwd_weight: bad arguments / workspace too small");
-  const int chunks = stem_wg_chunks(batch, input_size);
-  const long long total = (long long)batch * (input_size / 2) * (input_size / 2);
-  const long long ppc = (total + chunks - 1) / chunks;
+  if (((uintptr_t)dout | (uintptr_t)ws) & 15u)
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_stem_conv_bwd_weight: dout / workspace must be 16-byte aligned");
+  const int grid = stem_wg_grid(batch, input_size), nseg = stem_wg_nseg(input_size);
+  const long long items = (long long)batch * (input_size / 2) * nseg;
+  if (items > INT32_MAX) return fail(nullptr, YNB_ERR_INVALID, "ynb_stem_conv_bwd_weight: batch too large");
   cudaStream_t st = (cudaStream_t)stream;
-  stem_conv_bwd_weight_kernel<<<chunks, kStemWgThreads, 0, st>>>(dout, x, (float*)ws, batch, input_size, ppc);
+  stem_conv_bwd_weight_kernel<<<grid, kStemWgThreads, 0, st>>>(dout, x, (float*)ws, batch, input_size, (int)items, nseg);
   YNB_COUNT_LAUNCH();
-  launch_reduce_partials((const float*)ws, chunks, kStemWgThreads, dw2724, st);
+  launch_reduce_partials((const float*)ws, 2 * grid, kStemWgOut, dw2724, st);
   UNIT_TRY(cudaGetLastError());
   return YNB_OK;
 }
@@ -2192,6 +2194,30 @@ YNB_EXPORT int ynb_maxpool3x3s2_bwd(const float* dout, const float* in, float* d
     return fail(nullptr, YNB_ERR_INVALID, "ynb_maxpool3x3s2_bwd: bad arguments");
   const long long items = (long long)batch * h * w_ * channels;
   maxpool3x3s2_bwd_kernel<<<grid_for(items), 256, 0, (cudaStream_t)stream>>>(dout, in, din, batch, h, w_, channels);
+  YNB_COUNT_LAUNCH();
+  UNIT_TRY(cudaGetLastError());
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_maxpool3x3s2_fwd_idx(const float* in, float* out, uint8_t* idx, int32_t batch, int32_t h, int32_t w_,
+                                        int32_t channels, void* stream) {
+  if (!in || !out || !idx || batch <= 0 || h <= 0 || w_ <= 0 || channels <= 0 || channels % 4 ||
+      (((uintptr_t)in | (uintptr_t)out) & 15u) || ((uintptr_t)idx & 3u))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_maxpool3x3s2_fwd_idx: bad arguments");
+  const long long items = (long long)batch * ((h - 1) / 2 + 1) * ((w_ - 1) / 2 + 1) * (channels / 4);
+  maxpool3x3s2_fwd_idx_kernel<<<grid_for(items), 256, 0, (cudaStream_t)stream>>>(in, out, idx, batch, h, w_, channels);
+  YNB_COUNT_LAUNCH();
+  UNIT_TRY(cudaGetLastError());
+  return YNB_OK;
+}
+
+YNB_EXPORT int ynb_maxpool3x3s2_bwd_idx(const float* dout, const uint8_t* idx, float* din, int32_t batch, int32_t h,
+                                        int32_t w_, int32_t channels, void* stream) {
+  if (!dout || !idx || !din || batch <= 0 || h <= 0 || w_ <= 0 || channels <= 0 || channels % 4 ||
+      (((uintptr_t)dout | (uintptr_t)din) & 15u) || ((uintptr_t)idx & 3u))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_maxpool3x3s2_bwd_idx: bad arguments");
+  const long long items = (long long)batch * h * w_ * (channels / 4);
+  maxpool3x3s2_bwd_idx_kernel<<<grid_for(items), 256, 0, (cudaStream_t)stream>>>(dout, idx, din, batch, h, w_, channels);
   YNB_COUNT_LAUNCH();
   UNIT_TRY(cudaGetLastError());
   return YNB_OK;

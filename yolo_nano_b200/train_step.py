@@ -164,18 +164,22 @@ class TrainStep:
         """nn.BatchNorm2d in training mode + activation; running statistics updated in the model's buffers."""
         g, b = self._param(bn_name + ".weight"), self._param(bn_name + ".bias")
         c, cp = g.shape[0], x.shape[-1]
-        gp = torch.ones(cp, device=self.dev); gp[:c] = g
-        bp = torch.zeros(cp, device=self.dev); bp[:c] = b
-        rm = torch.zeros(cp, device=self.dev); rm[:c] = self.sd[bn_name + ".running_mean"]
-        rv = torch.ones(cp, device=self.dev); rv[:c] = self.sd[bn_name + ".running_var"]
+        if c == cp:            # the kernel updates the model's running statistics in place
+            gp, bp, rm, rv = g, b, self.sd[bn_name + ".running_mean"], self.sd[bn_name + ".running_var"]
+        else:                  # 58-channel layers of stage 2 run on 60 channels: padded working copies
+            gp = torch.ones(cp, device=self.dev); gp[:c] = g
+            bp = torch.zeros(cp, device=self.dev); bp[:c] = b
+            rm = torch.zeros(cp, device=self.dev); rm[:c] = self.sd[bn_name + ".running_mean"]
+            rv = torch.ones(cp, device=self.dev); rv[:c] = self.sd[bn_name + ".running_var"]
+            self.new_stats[bn_name] = (rm[:c], rv[:c])
+        self.bn_names.append(bn_name)
         layer = T.BnActTrain(gp, bp, rm, rv, act=act)
         y = layer.forward(x)
-        self.new_stats[bn_name] = (rm[:c], rv[:c])
 
         def bw():
             dx = layer.backward(tape.take(y))
-            tape.pgrad[bn_name + ".weight"] = layer.grads["weight"][:c].contiguous()
-            tape.pgrad[bn_name + ".bias"] = layer.grads["bias"][:c].contiguous()
+            tape.pgrad[bn_name + ".weight"] = layer.grads["weight"][:c]
+            tape.pgrad[bn_name + ".bias"] = layer.grads["bias"][:c]
             tape.add_grad(x, dx)
         tape.ops.append(bw)
         return y
@@ -256,6 +260,7 @@ class TrainStep:
         bsz, s = int(x.shape[0]), int(x.shape[2])
         self.sd = {k: v.detach() for k, v in m.state_dict(keep_vars=True).items()}
         self.new_stats: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self.bn_names: List[str] = []
         self.flags = [] if self.check_flags else None
         tape = _Tape(dev)
         lib = self.lib
@@ -278,13 +283,15 @@ class TrainStep:
         a1 = self.bn(tape, c1, "backbone.conv1.1", ACT_RELU)
         hp_ = (s // 2 - 1) // 2 + 1
         pool = torch.empty((bsz, hp_, hp_, 24), device=dev)
-        T._check(lib.ynb_maxpool3x3s2_fwd(_ptr(a1), _ptr(pool), bsz, s // 2, s // 2, 24, self._st()), "ynb_maxpool3x3s2_fwd")
+        pidx = torch.empty((bsz, hp_, hp_, 24), device=dev, dtype=torch.uint8)
+        T._check(lib.ynb_maxpool3x3s2_fwd_idx(_ptr(a1), _ptr(pool), _ptr(pidx), bsz, s // 2, s // 2, 24, self._st()),
+                 "ynb_maxpool3x3s2_fwd_idx")
 
         def pool_bw():
             dy = tape.take(pool)
             din = torch.empty_like(a1)
-            T._check(lib.ynb_maxpool3x3s2_bwd(_ptr(dy), _ptr(a1), _ptr(din), bsz, s // 2, s // 2, 24, self._st()),
-                     "ynb_maxpool3x3s2_bwd")
+            T._check(lib.ynb_maxpool3x3s2_bwd_idx(_ptr(dy), _ptr(pidx), _ptr(din), bsz, s // 2, s // 2, 24, self._st()),
+                     "ynb_maxpool3x3s2_bwd_idx")
             tape.add_grad(a1, din)
         tape.ops.append(pool_bw)
 
@@ -333,20 +340,24 @@ class TrainStep:
         for name, (rm, rv) in self.new_stats.items():
             full[name + ".running_mean"].copy_(rm)
             full[name + ".running_var"].copy_(rv)
-            full[name + ".num_batches_tracked"].add_(1)
+        torch._foreach_add_([full[name + ".num_batches_tracked"] for name in self.bn_names], 1)
         if hasattr(m, "mark_weights_dirty"):
             m.mark_weights_dirty()
         self.sd = None
         return losses, tape.pgrad
 
-    def flat_gradient(self, grads: Dict[str, torch.Tensor]) -> torch.Tensor:
-        """The gradients concatenated in `model.parameters()` order (what train.py:167's optimizer walks)."""
+    def flat_gradient(self, grads: Dict[str, torch.Tensor], align: int = 1) -> torch.Tensor:
+        """The gradients concatenated in `model.parameters()` order (what train.py:167's optimizer walks); with
+        align > 1 every tensor starts at a multiple of `align` elements (zeros in between: `Trainer`'s layout)."""
         parts = []
         for name, p in self.model.named_parameters():
             g = grads[name]
             if tuple(g.shape) != tuple(p.shape):
                 raise EngineError(f"gradient of {name} has shape {tuple(g.shape)}, parameter {tuple(p.shape)}")
             parts.append(g.reshape(-1))
+            pad = -g.numel() % align
+            if pad:
+                parts.append(T._zeros(pad, self.dev))
         return torch.cat(parts)
 
 
@@ -364,19 +375,28 @@ class Trainer:
     EMA one more launch.  `set_lr` = train.py:337-339."""
 
     def __init__(self, model, lr: float, momentum: float = 0.9, weight_decay: float = 5e-4, ema=None, group=None,
-                 skip_nan: bool = True):
+                 skip_nan: bool = True, cuda_graph: bool = False):
         self.model, self.ema, self.group, self.skip_nan = model, ema, group, skip_nan
+        # cuda_graph: the ~1600 launches of forward + backward (+ the gradient flattening) are captured ONCE per input
+        # shape into a CUDA graph and replayed; the first step of a shape runs eagerly (lazy initialisations),
+        # the second is captured.  SGD / all-reduce / EMA stay outside (their scalars change every iteration).
+        self.cuda_graph = cuda_graph
+        self._gkey, self._graph = None, None
         self.fb = TrainStep(model)
         ps = list(model.parameters())
         for p in ps:
             if p.dtype != torch.float32 or not p.is_cuda:
                 raise EngineError("Trainer: parameters must be float32 CUDA tensors (no CPU fallback)")
-        flat = torch.cat([p.detach().reshape(-1) for p in ps])
+        # every tensor starts on a 16-byte boundary (the kernels read parameters with 16-byte loads); the <= 3 pad
+        # elements after a tensor are zero, get zero gradient and stay zero under SGD with weight decay
+        self.align = 4
+        flat = torch.zeros(sum(p.numel() + (-p.numel() % self.align) for p in ps), device=ps[0].device)
         off = 0
         for p in ps:
             n = p.numel()
+            flat[off:off + n] = p.detach().reshape(-1)
             p.data = flat[off:off + n].view(p.shape)
-            off += n
+            off += n + (-n % self.align)
         self.flat = flat
         self.opt = T.FlatSGD(flat, lr, momentum, weight_decay)
         self.skipped = 0
@@ -386,13 +406,38 @@ class Trainer:
     def set_lr(self, lr: float):
         self.opt.set_lr(lr)
 
+    def _forward_backward(self, images, targets):
+        if not self.cuda_graph:
+            losses, grads = self.fb.forward_backward(images, targets)
+            return losses, self.fb.flat_gradient(grads, self.align)
+        key = (tuple(images.shape), tuple(targets.shape))
+        if key != self._gkey:                         # new shape (multi-scale training): eager now, capture next time
+            self._gkey, self._graph = key, None
+            losses, grads = self.fb.forward_backward(images, targets)
+            return losses, self.fb.flat_gradient(grads, self.align)
+        if self._graph is None:
+            sx, st = images.clone(), targets.clone()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                losses, grads = self.fb.forward_backward(sx, st)
+                flat = self.fb.flat_gradient(grads, self.align)
+            self._graph = (g, sx, st, losses, flat)
+        else:
+            g, sx, st, losses, flat = self._graph
+            sx.copy_(images)
+            st.copy_(targets)
+        g.replay()
+        if hasattr(self.model, "mark_weights_dirty"):
+            self.model.mark_weights_dirty()
+        return losses, flat
+
     @torch.no_grad()
     def step(self, images: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
-        losses, grads = self.fb.forward_backward(images, targets)
+        losses, flat_grad = self._forward_backward(images, targets)
         if self.skip_nan and bool(torch.isnan(losses.sum()).item()):
             self.skipped += 1
             return losses
-        self.opt.step(self.fb.flat_gradient(grads), self.group)
+        self.opt.step(flat_grad, self.group)
         if hasattr(self.model, "mark_weights_dirty"):
             self.model.mark_weights_dirty()
         if self.ema is not None:

@@ -169,6 +169,18 @@ def conv3x3_backward_weight(dout: torch.Tensor, x: torch.Tensor):
     return dw, db
 
 
+_ZEROS = {}
+
+
+def _zeros(n: int, dev) -> torch.Tensor:
+    """A shared read-only zero vector (bias of bias-free convs): allocated once per (device, size bucket)."""
+    key = (dev, (n + 511) // 512)
+    z = _ZEROS.get(key)
+    if z is None:
+        z = _ZEROS[key] = torch.zeros(key[1] * 512, device=dev, dtype=torch.float32)
+    return z[:n]
+
+
 def _tc_workspace(cout: int, ktot: int, dev):
     n = int(_lib.load().ynb_tc_async_workspace_bytes(cout, ktot))
     return torch.empty(n, device=dev, dtype=torch.uint8), n
@@ -194,7 +206,7 @@ def pwconv_forward(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], 
     n = n_real if cout is None else int(cout)
     y = torch.empty((m, n), device=dev, dtype=torch.float32)
     if b is None:
-        b = torch.zeros(n, device=dev, dtype=torch.float32)
+        b = _zeros(n, dev)
     elif b.numel() < n:
         b = torch.cat((b, b.new_zeros(n - b.numel())))
     for n0 in range(0, n, 256):                       # the GEMM holds at most 256 output columns in TMEM
