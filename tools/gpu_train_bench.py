@@ -37,6 +37,9 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU")
     ap.add_argument("--size", type=int, default=416)
     ap.add_argument("--no-graph", action="store_true", help="launch the ~1600 kernels of a step one by one")
+    ap.add_argument("--cpu-baseline", action="store_true",
+                    help="also time the train-mode oracle (= the reference's PyTorch CPU path restated) on the host cores, "
+                         "one 8-image step at the same size")
     ap.add_argument("--profile", action="store_true", help="host enqueue time + kernel table (torch.profiler / CUPTI)")
     ap.add_argument("out", nargs="?", default="")
     a = ap.parse_args()
@@ -121,6 +124,19 @@ def main():
            "e2e": {"value": world * a.batch / (ms_e2e * 1e-3), "unit": "images/sec",
                    "h2d_bytes_per_step": int(x_h.numel() * 4 + lab_h.numel() * 4), "d2h_bytes_per_step": 16},
            "losses_last_step": [float(v) for v in ls.cpu()], "cuda_graph": not a.no_graph}
+    if a.cpu_baseline and rank == 0:
+        import time
+        from oracle import train_oracle as TO          # the checker, used here only as the reported CPU baseline
+        sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+        nb = 8
+        tgt = TR.build_targets(lab_d[:nb], None, a.size, anchors).cpu()
+        TO.train_forward_backward(sd, x_h[:2].clone(), tgt[:2], a.size, classes, anchors)       # warm-up
+        t0 = time.perf_counter()
+        TO.train_forward_backward(sd, x_h[:nb].clone(), tgt, a.size, classes, anchors)
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": nb / dt, "unit": "images/sec", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": "one forward + backward of %d images at %d (train-mode oracle, PyTorch CPU, %d threads)"
+                                         % (nb, a.size, torch.get_num_threads())}
     if rank == 0:
         print(json.dumps(res), flush=True)
         if a.out:
