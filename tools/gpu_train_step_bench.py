@@ -5,9 +5,9 @@ losses, the backward chain through all 77 convolutions, ONE NCCL all-reduce of t
 fused SGD(momentum 0.9, wd 5e-4) kernel — `yolo_nano_b200.train_step.Trainer.step`, every arithmetic step a kernel of
 libyolonano_b200.so (or NCCL).  Random-init weights, synthetic images and labels.
 
-    python tools/gpu_train_bench.py [--steps K --warmup W --batch 32 --size 416] [out.json]
+    python tools/gpu_train_step_bench.py [--steps K --warmup W --batch 32 --size 416] [out.json]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 \
-        tools/gpu_train_bench.py ...
+        tools/gpu_train_step_bench.py ...
 
 `value` times the step with inputs resident in HBM; `e2e` adds, per step, the H2D copy of the images and labels from
 pinned host memory and the D2H read of the four losses (what train.py:215-226 does).  CUDA events, max over ranks.
