@@ -53,6 +53,7 @@ struct DwPwParams {
   int w_resident, a_stages, raw_stages;
   int prefetch_tiles; // L2 prefetch distance of the raw tiles, in tiles of this CTA (0: off)
   int pass_blocks;    // 32-channel blocks of the pass-through half to prefetch into L2 per tile (0: none)
+  int tma_out;        // float, gap-free output layout: every warp's staging box leaves through ONE TMA tensor store (tmOut)
   uint32_t tmem_cols;
   const float* dw_w;  // [9][C4] tap-major, BN folded
   const float* dw_b;  // [C4]
@@ -108,7 +109,7 @@ template <bool kPass, typename E>
 __global__ void __launch_bounds__(kDpThreads, 1)
 dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmWhi,
                const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmPass,
-               const DwPwParams p) {
+               const __grid_constant__ CUtensorMap tmOut, const DwPwParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
 
@@ -140,6 +141,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
     ptx::prefetch_tmap(&tmWhi);
     if (split) ptx::prefetch_tmap(&tmWlo);
     if (p.pass_blocks) ptx::prefetch_tmap(&tmPass);
+    if (p.tma_out) ptx::prefetch_tmap(&tmOut);
     for (int s = 0; s < kDpMaxRawStages; ++s) {
       ptx::mbar_init(&raw_full[s], 1);
       ptx::mbar_init(&raw_empty[s], kBf16 ? kDpDwWarps : kDpDwWarps / 2);   // the warps of ONE producer group
@@ -476,8 +478,13 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
       auto put_chunk = [&](int j, uint4 val) {               // 16-byte chunk j of this thread's staging row
         *reinterpret_cast<uint4*>(sbox + lane * 128 + ((j ^ sw) << 4)) = val;
       };
+      const bool tma_out = !kBf16 && p.tma_out;
       for (int bx = 0; bx < nbox; ++bx) {
         const int c0 = bx * CPB;
+        if (tma_out) {                   // the previous store of this warp has finished READING the staging box
+          if (ptx::elect_one()) ptx::bulk_wait_read<0>();
+          __syncwarp();
+        }
         if (!kBf16 && kPass) {
           float v[16];
           drain16(c0, v);
@@ -541,6 +548,17 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
         }
         __syncwarp();
         const int j0 = bx * BOX;           // first logical output element of this box
+        if (tma_out) {
+          // the warp's 32 tile rows are TW x (32 / TW) pixels of one image: the swizzled box leaves through ONE
+          // tensor store, rows outside the image and channels >= the logical width clipped by the copy engine
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (ptx::elect_one()) {
+            ptx::tma_store_4d(&tmOut, sbox, j0, (rr % p.tiles_x) * TW, (rr / p.tiles_x) * TH + q * (32 >> p.lgTW), b);
+            ptx::bulk_commit();
+          }
+          continue;
+        }
         if (!gap) {
           const int ch = lane & 7;
           const int jc = j0 + EPC * ch;
@@ -578,6 +596,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
       }
       if (q == 0 && lane == 0) YNB_DP_TRACE(5, lt, 0);
     }
+    if (!kBf16 && p.tma_out && ptx::elect_one()) ptx::bulk_wait<0>();     // all output boxes have landed
   }
 
   ptx::tc_fence_before_sync();
@@ -593,6 +612,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
 // --------------------------------------------------------------------------------------
 struct DwPwLaunch {
   CUtensorMap tmIn;
+  CUtensorMap tmOut;      // valid when p.tma_out
   CUtensorMap tmPass;     // pass-through half (L2 prefetch only); valid when p.pass_blocks > 0
   const TcWeights* w = nullptr;
   DwPwParams p;
@@ -656,13 +676,21 @@ inline bool plan_dwpw(DwPwLaunch& L, const void* in, int in_ld, int B, int H, in
       p.pass_blocks = (p.N + chunk_ch - 1) / chunk_ch;
   }
   if (!make_tmap_nhwc(&L.tmIn, in, C4, W, H, B, in_ld, TW + 2, TH + 2, is_bf16)) return false;
+  p.tma_out = 0;
+  {
+    static const bool no_ts = getenv("YNB_DP_NO_TMA_STORE") != nullptr;                     // experiment knob
+    const int out_cols = p.pass ? 2 * p.N : (p.N + epc - 1) / epc * epc;
+    if (!no_ts && !is_bf16 && p.omap.gap == 0 && p.out_off == 0 &&
+        make_tmap_nhwc(&L.tmOut, p.out, out_cols, W, H, B, p.out_ld, TW, 32 / TW, false))
+      p.tma_out = 1;
+  }
   L.w = w;
   L.grid = (unsigned)std::min<int64_t>(p.num_tiles, kNumSMs);
   return true;
 }
 
 inline cudaError_t launch_dwpw_tc(const DwPwLaunch& L, cudaStream_t st) {
-  using KernelT = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, DwPwParams);
+  using KernelT = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, DwPwParams);
   static const KernelT kernels[4] = {dwpw_tc_kernel<false, float>, dwpw_tc_kernel<true, float>,
                                      dwpw_tc_kernel<false, bf16>, dwpw_tc_kernel<true, bf16>};
   static bool attr_set = false;
@@ -675,7 +703,8 @@ inline cudaError_t launch_dwpw_tc(const DwPwLaunch& L, cudaStream_t st) {
   }
   const int ki = (L.p.mode == YNB_GEMM_TC_BF16 ? 2 : 0) + (L.p.pass != nullptr ? 1 : 0);
   cudaError_t r = launch_pdl(kernels[ki], dim3(L.grid), dim3(kDpThreads), (size_t)L.smem, st,
-                             L.tmIn, L.w->tm_hi, L.w->tm_lo, L.p.pass_blocks ? L.tmPass : L.tmIn, L.p);
+                             L.tmIn, L.w->tm_hi, L.w->tm_lo, L.p.pass_blocks ? L.tmPass : L.tmIn,
+                             L.p.tma_out ? L.tmOut : L.tmIn, L.p);
   YNB_COUNT_LAUNCH();
   return r;
 }
