@@ -763,7 +763,7 @@ inline bool make_tmap_2d(CUtensorMap* m, const void* base, uint64_t k, uint64_t 
 // rank-4 map over an NHWC activation [B][H][W][ld] exposing C channels: (c, x, y, b); boxes of 128 bytes of
 // channels (32 floats | 64 bf16) x box_w x box_h pixels.
 inline bool make_tmap_nhwc(CUtensorMap* m, const void* base, int C, int W, int H, int B, int ld, int box_w,
-                           int box_h, bool bf16 = false) {
+                           int box_h, bool bf16 = false, bool swizzle = true) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return false;
   const uint64_t es = bf16 ? 2 : 4;
@@ -772,7 +772,8 @@ inline bool make_tmap_nhwc(CUtensorMap* m, const void* base, int C, int W, int H
   cuuint32_t box[4] = {(cuuint32_t)(128 / es), (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   return enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims,
-             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 

@@ -349,8 +349,8 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 6; ++j) {
             const int rr = r0 + j;
-            if (!kBf16) v[j] = load4(reinterpret_cast<const E*>(raw + rr * 128 + ((cg ^ (rr & 7)) << 4)));
-            else v[j] = load4(reinterpret_cast<const E*>(raw + rr * 128 + ((((cg >> 1) ^ (rr & 7)) << 4) | ((cg & 1) << 3))));
+            if (!kBf16) v[j] = load4(reinterpret_cast<const E*>(raw + rr * 128 + (cg << 4)));
+            else v[j] = load4(reinterpret_cast<const E*>(raw + rr * 128 + (cg << 3)));
           }
 #pragma unroll
           for (int o = 0; o < ROWS; ++o) {
@@ -472,8 +472,13 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
           const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * j);
           v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
         }
+        if (p.act == YNB_ACT_RELU) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * slope);
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * slope);
+        }
       };
       auto put_chunk = [&](int j, uint4 val) {               // 16-byte chunk j of this thread's staging row
         *reinterpret_cast<uint4*>(sbox + lane * 128 + ((j ^ sw) << 4)) = val;
@@ -675,7 +680,9 @@ inline bool plan_dwpw(DwPwLaunch& L, const void* in, int in_ld, int B, int H, in
     if (make_tmap_nhwc(&L.tmPass, p.pass, (p.N + epc - 1) / epc * epc, W, H, B, p.pass_ld, TW, TH, is_bf16))
       p.pass_blocks = (p.N + chunk_ch - 1) / chunk_ch;
   }
-  if (!make_tmap_nhwc(&L.tmIn, in, C4, W, H, B, in_ld, TW + 2, TH + 2, is_bf16)) return false;
+  // the raw tile is NOT swizzled: the depthwise threads that read one tile row together cover its 128 bytes
+  // (lane = channel group fastest), so plain rows are conflict-free and need no XOR per load
+  if (!make_tmap_nhwc(&L.tmIn, in, C4, W, H, B, in_ld, TW + 2, TH + 2, is_bf16, false)) return false;
   p.tma_out = 0;
   {
     static const bool no_ts = getenv("YNB_DP_NO_TMA_STORE") != nullptr;                     // experiment knob

@@ -288,23 +288,35 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(const WgradP
 // Second stage: fixed-order sum over the chunks in accumulator order (coalesced), then ONE permuted write:
 // tile row 32*c + l = output channel 4*l + c; column 128*g + 32*c + l = input channel 128*g + 4*l + c;
 // column K = bias gradient.
-__global__ void __launch_bounds__(1024) wgrad_reduce_kernel(const float* __restrict__ partial, int chunks, int ntiles,
-                                                            int kpad, int N, int K, float* __restrict__ dw,
-                                                            float* __restrict__ db) {
-  __shared__ float sh[32][33];
-  const long long elems = (long long)ntiles * 128 * kpad;
-  const long long e = (long long)blockIdx.x * 32 + threadIdx.x;
-  float s = 0.0f;
+// A block = 64 consecutive accumulator elements (16 threads x 16 bytes) x 32 chunk slices: every thread keeps
+// chunks / 32 independent 16-byte loads in flight (the partials were just written: L2 reads).  Summation order per
+// element: slice y adds chunks y, y + 32, ... ascending, then the slices 0..31 ascending — fixed, run-to-run identical.
+constexpr int kWgRedElems = 64;
+__global__ void __launch_bounds__(512) wgrad_reduce_kernel(const float* __restrict__ partial, int chunks, int ntiles,
+                                                           int kpad, int N, int K, float* __restrict__ dw,
+                                                           float* __restrict__ db) {
+  __shared__ float4 sh[32][17];
+  const long long elems = (long long)ntiles * 128 * kpad;          // multiple of 64
+  const long long e = (long long)blockIdx.x * kWgRedElems + 4 * threadIdx.x;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (e < elems)
-    for (int j = threadIdx.y; j < chunks; j += 32) s += partial[(long long)j * elems + e];
+    for (int j = threadIdx.y; j < chunks; j += 32) {
+      const float4 v = *reinterpret_cast<const float4*>(partial + (long long)j * elems + e);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
   sh[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
-  if (threadIdx.y == 0 && e < elems) {
+  if (threadIdx.y < 4 && e < elems) {          // 64 threads finish one element each: (x, component y)
+    const int comp = threadIdx.y;
     float t = 0.0f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) t += sh[j][threadIdx.x];
-    const int col = (int)(e % kpad);
-    const long long row = e / kpad;
+    for (int j = 0; j < 32; ++j) {
+      const float4 v = sh[j][threadIdx.x];
+      t += comp == 0 ? v.x : (comp == 1 ? v.y : (comp == 2 ? v.z : v.w));
+    }
+    const long long ee = e + comp;
+    const int col = (int)(ee % kpad);
+    const long long row = ee / kpad;
     const int r = (int)(row % 128), tile = (int)(row / 128);
     const int n = tile * 128 + 4 * (r & 31) + (r >> 5);
     const int k = (col & ~127) + 4 * (col & 31) + ((col >> 5) & 3);
@@ -313,6 +325,12 @@ __global__ void __launch_bounds__(1024) wgrad_reduce_kernel(const float* __restr
       else if (k == K) db[n] = t;
     }
   }
+}
+inline void launch_wgrad_reduce(const float* partial, int chunks, int ntiles, int kpad, int N, int K, float* dw, float* db,
+                                cudaStream_t st) {
+  const long long elems = (long long)ntiles * 128 * kpad;
+  wgrad_reduce_kernel<<<(unsigned)((elems + kWgRedElems - 1) / kWgRedElems), dim3(16, 32), 0, st>>>(partial, chunks, ntiles, kpad,
+                                                                                                  N, K, dw, db);
 }
 
 inline int wgrad_tc_kpad(int K) { return K + 1 <= 128 ? 128 : (K + 1 <= 256 ? 256 : 0); }

@@ -2007,8 +2007,7 @@ YNB_EXPORT int ynb_pwconv_bwd_weight(const float* dout, int32_t do_ld, int32_t d
     {
       const int ntiles = (cout + 127) / 128, kpad = wgrad_tc_kpad(cin);
       const long long elems = (long long)ntiles * 128 * kpad;
-      wgrad_reduce_kernel<<<(unsigned)((elems + 31) / 32), dim3(32, 32), 0, st>>>((const float*)ws, chunks, ntiles, kpad, cout,
-                                                                                cin, dw, db);
+      launch_wgrad_reduce((const float*)ws, chunks, ntiles, kpad, cout, cin, dw, db, st);
       YNB_COUNT_LAUNCH();
     }
     UNIT_TRY(cudaGetLastError());
@@ -2129,8 +2128,7 @@ YNB_EXPORT int ynb_conv3x3_bwd_weight(const float* dout, int32_t do_ld, int32_t 
     p.partial = (float*)ws; p.M = pixels; p.K = cin; p.N = cout; p.err = err;
     p.H = h; p.W = w_; p.dy = t / 3 - 1; p.dx = t % 3 - 1;
     UNIT_TRY(launch_pw_wgrad_tc(p, chunks, st));
-    wgrad_reduce_kernel<<<(unsigned)((elems + 31) / 32), dim3(32, 32), 0, st>>>((const float*)ws, chunks, ntiles, kpad, cout,
-                                                                              cin, dw9 + (long long)t * cout * cin, db);
+    launch_wgrad_reduce((const float*)ws, chunks, ntiles, kpad, cout, cin, dw9 + (long long)t * cout * cin, db, st);
     YNB_COUNT_LAUNCH();
   }
   UNIT_TRY(cudaGetLastError());
