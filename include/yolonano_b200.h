@@ -389,6 +389,11 @@ int  ynb_maxpool3x3s2_fwd(const float* in_dev, float* out_dev, int32_t batch, in
                           void* stream);
 int  ynb_maxpool3x3s2_bwd(const float* dout_dev, const float* in_dev, float* din_dev, int32_t batch, int32_t h, int32_t w,
                           int32_t channels, void* stream);
+/* Data movement of a ShuffleV2 unit in the training step (backbone/shufflenetv2.py:14-28, 66-78), one launch each:
+ * op 0  x.chunk(2): x [rows, 2*half] -> a, b [rows, half_padded] (zero-padded halves);   op 1  its adjoint (a, b -> x);
+ * op 2  torch.cat + channel_shuffle: x[:, 2i] = a[:, i], x[:, 2i+1] = b[:, i];            op 3  its adjoint (x -> a, b). */
+int  ynb_shuffle_unit_move(float* x_dev, float* a_dev, float* b_dev, int64_t rows, int32_t half, int32_t half_padded,
+                           int32_t op, void* stream);
 /* The same pair keeping the arg-max like ATen's max_pool2d_with_indices: idx_dev [B, Ho, Wo, C] uint8 = winning tap
  * (ky * 3 + kx, first maximum in row-major order); the backward is then a gather (no re-scan of the windows). */
 int  ynb_maxpool3x3s2_fwd_idx(const float* in_dev, float* out_dev, uint8_t* idx_dev, int32_t batch, int32_t h, int32_t w,

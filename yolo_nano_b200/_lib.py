@@ -113,6 +113,7 @@ SIGNATURES = {
     "ynb_stem_conv_bwd_weight": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _i64, _p]),
     "ynb_maxpool3x3s2_fwd": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p]),
     "ynb_maxpool3x3s2_bwd": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _p]),
+    "ynb_shuffle_unit_move": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _p]),
     "ynb_maxpool3x3s2_fwd_idx": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _p]),
     "ynb_maxpool3x3s2_bwd_idx": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _p]),
     "ynb_resample_add": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),

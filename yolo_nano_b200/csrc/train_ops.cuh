@@ -1247,6 +1247,37 @@ maxpool3x3s2_bwd_idx_kernel(const float* __restrict__ dout, const uint8_t* __res
   }
 }
 
+// ---- ShuffleV2 unit data movement in the training step (backbone/shufflenetv2.py:14-28, 66-78) ---------------------
+// x.chunk(2) with each half zero-padded from h to hp channels (forward) / its adjoint, and torch.cat + channel_shuffle
+// (out[2i] = a[i], out[2i+1] = b[i]) / its adjoint: plain copies, one launch each instead of 4-6 ATen launches.
+// op 0: split   x [M, 2h]            -> a, b [M, hp]   (a = x[:, :h], b = x[:, h:], zero pad)
+// op 1: merge   a, b [M, hp]         -> x [M, 2h]      (adjoint of split: x[:, :h] = a[:, :h], x[:, h:] = b[:, :h])
+// op 2: shuffle a, b [M, hp]         -> x [M, 2h]      (x[:, 2i] = a[:, i], x[:, 2i+1] = b[:, i])
+// op 3: unshuffle x [M, 2h]          -> a, b [M, hp]   (adjoint of shuffle, zero pad)
+__global__ void __launch_bounds__(256)
+shuffle_unit_move_kernel(float* __restrict__ x, float* __restrict__ a, float* __restrict__ b, long long M, int h, int hp,
+                         int op) {
+  const long long total = M * hp;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long m = i / hp;
+    const int c = (int)(i - m * hp);
+    float* xr = x + m * 2 * h;
+    if (op == 0) {
+      a[i] = c < h ? xr[c] : 0.0f;
+      b[i] = c < h ? xr[h + c] : 0.0f;
+    } else if (op == 1) {
+      if (c < h) { xr[c] = a[i]; xr[h + c] = b[i]; }
+    } else if (op == 2) {
+      if (c < h) *reinterpret_cast<float2*>(xr + 2 * c) = make_float2(a[i], b[i]);
+    } else {
+      float2 v = make_float2(0.0f, 0.0f);
+      if (c < h) v = *reinterpret_cast<const float2*>(xr + 2 * c);
+      a[i] = v.x;
+      b[i] = v.y;
+    }
+  }
+}
+
 // ---- FPN / PAN merge backward (models/yolo_nano.py:291-296): out = a + resample(a2) => d a = d out (identity) and
 //   mode 1 (a2 up-sampled x2, nearest):  d a2[y, x] = sum of the 2x2 block of d out
 //   mode 2 (a2 down-sampled [::2, ::2]):  d a2[2y, 2x] = d out[y, x], zero elsewhere

@@ -2197,6 +2197,16 @@ YNB_EXPORT int ynb_maxpool3x3s2_bwd(const float* dout, const float* in, float* d
   return YNB_OK;
 }
 
+YNB_EXPORT int ynb_shuffle_unit_move(float* x, float* a, float* b, int64_t rows, int32_t half, int32_t half_padded,
+                                     int32_t op, void* stream) {
+  if (!x || !a || !b || rows <= 0 || half <= 0 || half_padded < half || op < 0 || op > 3 || (((uintptr_t)x) & 7u))
+    return fail(nullptr, YNB_ERR_INVALID, "ynb_shuffle_unit_move: bad arguments");
+  shuffle_unit_move_kernel<<<grid_for(rows * half_padded), 256, 0, (cudaStream_t)stream>>>(x, a, b, rows, half, half_padded, op);
+  YNB_COUNT_LAUNCH();
+  UNIT_TRY(cudaGetLastError());
+  return YNB_OK;
+}
+
 YNB_EXPORT int ynb_maxpool3x3s2_fwd_idx(const float* in, float* out, uint8_t* idx, int32_t batch, int32_t h, int32_t w_,
                                         int32_t channels, void* stream) {
   if (!in || !out || !idx || batch <= 0 || h <= 0 || w_ <= 0 || channels <= 0 || channels % 4 ||

@@ -196,6 +196,38 @@ class TrainStep:
         tape.ops.append(bw)
         return y
 
+    def _move(self, x, a, b, h, hp, op):
+        rows = x.numel() // (2 * h)
+        T._check(self.lib.ynb_shuffle_unit_move(_ptr(x), _ptr(a), _ptr(b), rows, h, hp, op, self._st()), "ynb_shuffle_unit_move")
+
+    def split(self, tape, x, h, hp):
+        """x.chunk(2, dim=C) with both halves zero-padded to hp channels (backbone/shufflenetv2.py:67)."""
+        shp = x.shape[:-1]
+        x1, x2 = torch.empty((*shp, hp), device=self.dev), torch.empty((*shp, hp), device=self.dev)
+        self._move(x, x1, x2, h, hp, 0)
+
+        def bw():
+            d1, d2 = tape.take(x1), tape.take(x2)
+            dx = torch.empty_like(x)
+            self._move(dx, d1, d2, h, hp, 1)
+            tape.add_grad(x, dx)
+        tape.ops.append(bw)
+        return x1, x2
+
+    def shuffle_cat(self, tape, a, b, h, hp):
+        """channel_shuffle(torch.cat((a, b), 1), 2): out[2i] = a[i], out[2i+1] = b[i] (backbone/shufflenetv2.py:14-28,76)."""
+        y = torch.empty((*a.shape[:-1], 2 * h), device=self.dev)
+        self._move(y, a, b, h, hp, 2)
+
+        def bw():
+            dy = tape.take(y)
+            da, db = torch.empty_like(a), torch.empty_like(b)
+            self._move(dy, da, db, h, hp, 3)
+            tape.add_grad(a, da)
+            tape.add_grad(b, db)
+        tape.ops.append(bw)
+        return y
+
     # ---- blocks ----------------------------------------------------------------------------------------------------
     def shuffle_unit(self, tape, x, prefix, cin, cout, stride):
         h = cout // 2
@@ -206,23 +238,12 @@ class TrainStep:
             t = self.bn(tape, self.dw(tape, t, prefix + ".branch2.3", stride, False), prefix + ".branch2.4", ACT_NONE)
             return self.bn(tape, self.pw(tape, t, prefix + ".branch2.5", False), prefix + ".branch2.6", ACT_RELU)
 
-        def interleave(a, b):       # cat + channel_shuffle: out[2i] = a[i], out[2i+1] = b[i]   (a, b: [.., hp])
-            return torch.stack((a[..., :h], b[..., :h]), dim=-1).reshape(*a.shape[:-1], 2 * h)
-
-        def de_interleave(dy):
-            d2 = dy.reshape(*dy.shape[:-1], h, 2)
-            return _padc(d2[..., 0], hp), _padc(d2[..., 1], hp)
-
         if stride == 1:
-            x1 = self.movement(tape, [x], lambda t: _padc(t[..., :h], hp), lambda d: [_padc(d[..., :h], 2 * h)])
-            x2 = self.movement(tape, [x], lambda t: _padc(t[..., h:], hp),
-                               lambda d: [torch.cat((d.new_zeros(*d.shape[:-1], h), d[..., :h]), dim=-1)])
-            b2 = branch2(x2)
-            return self.movement(tape, [x1, b2], interleave, de_interleave)
+            x1, x2 = self.split(tape, x, h, hp)
+            return self.shuffle_cat(tape, x1, branch2(x2), h, hp)
         t = self.bn(tape, self.dw(tape, x, prefix + ".branch1.0", stride, False), prefix + ".branch1.1", ACT_NONE)
         b1 = self.bn(tape, self.pw(tape, t, prefix + ".branch1.2", False), prefix + ".branch1.3", ACT_RELU)
-        b2 = branch2(x)
-        return self.movement(tape, [b1, b2], interleave, de_interleave)
+        return self.shuffle_cat(tape, b1, branch2(x), h, hp)
 
     def conv_module(self, tape, x, prefix, k, groups):
         """`Conv` (utils/modules.py:8-18): Conv2d(bias) + BN + LeakyReLU(0.1)."""
