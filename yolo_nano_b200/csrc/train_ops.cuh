@@ -964,6 +964,43 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, long long M, 
   }
 }
 
+// reduce_partials + bn_finalize in ONE launch (forward): block = 32 channels x kRedSlices chunk slices, both sums of a
+// channel reduced in the SAME order as reduce_partials_kernel (bit-identical statistics), then the finalize arithmetic.
+__global__ void __launch_bounds__(32 * kRedSlices)
+bn_reduce_finalize_kernel(const float* __restrict__ partial, int chunks, long long M, int C, float eps, float momentum,
+                          float* __restrict__ sums, float* __restrict__ save_mean, float* __restrict__ save_rstd,
+                          float* __restrict__ running_mean, float* __restrict__ running_var) {
+  __shared__ float sh[2][kRedSlices][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const long long elems = 2LL * C;
+  float s0 = 0.0f, s1 = 0.0f;
+  if (c < C)
+    for (int j = threadIdx.y; j < chunks; j += kRedSlices) {
+      s0 += partial[(long long)j * elems + c];
+      s1 += partial[(long long)j * elems + C + c];
+    }
+  sh[0][threadIdx.y][threadIdx.x] = s0;
+  sh[1][threadIdx.y][threadIdx.x] = s1;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t0 = 0.0f, t1 = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kRedSlices; ++j) { t0 += sh[0][j][threadIdx.x]; t1 += sh[1][j][threadIdx.x]; }
+    sums[c] = t0;
+    sums[C + c] = t1;
+    const double mean = (double)t0 / (double)M;
+    double var = (double)t1 / (double)M - mean * mean;
+    if (var < 0.0) var = 0.0;
+    save_mean[c] = (float)mean;
+    save_rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)mean;
+    if (running_var) {
+      const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+      running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  }
+}
+
 // MODE 0: y = act((x - mean) * rstd * gamma + beta)
 // MODE 1: dx = gamma * rstd * (dy_eff - sum(dy_eff) / M - x_hat * sum(dy_eff * x_hat) / M);  sums = [dbeta | dgamma]
 template <int MODE>

@@ -2479,9 +2479,9 @@ YNB_EXPORT int ynb_bn_train_fwd(const float* x, int32_t x_ld, int32_t x_off, flo
   bn_colsum_kernel<0><<<grid, block, 0, st>>>(x, x_ld, x_off, nullptr, 0, 0, nullptr, 0, 0, nullptr, nullptr, 0.f, 0, part,
                                               pixels, channels, rpc);
   YNB_COUNT_LAUNCH();
-  launch_reduce_partials(part, chunks, 2LL * channels, sums, st);
-  bn_finalize_kernel<<<(channels + 127) / 128, 128, 0, st>>>(sums, pixels, channels, eps, momentum, save_mean, save_rstd,
-                                                            running_mean, running_var);
+  bn_reduce_finalize_kernel<<<(channels + 31) / 32, dim3(32, kRedSlices), 0, st>>>(part, chunks, pixels, channels, eps, momentum,
+                                                                                sums, save_mean, save_rstd, running_mean,
+                                                                                running_var);
   YNB_COUNT_LAUNCH();
   const long long total = pixels * (channels / 4);
   const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
