@@ -53,7 +53,7 @@ struct DwPwParams {
   int w_resident, a_stages, raw_stages;
   int prefetch_tiles; // L2 prefetch distance of the raw tiles, in tiles of this CTA (0: off)
   int pass_blocks;    // 32-channel blocks of the pass-through half to prefetch into L2 per tile (0: none)
-  int tma_out;        // float, gap-free output layout: every warp's staging box leaves through ONE TMA tensor store (tmOut)
+  int tma_out;        // gap-free output layout: every warp's staging box leaves through ONE TMA tensor store (tmOut)
   uint32_t tmem_cols;
   const float* dw_w;  // [9][C4] tap-major, BN folded
   const float* dw_b;  // [C4]
@@ -483,7 +483,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
       auto put_chunk = [&](int j, uint4 val) {               // 16-byte chunk j of this thread's staging row
         *reinterpret_cast<uint4*>(sbox + lane * 128 + ((j ^ sw) << 4)) = val;
       };
-      const bool tma_out = !kBf16 && p.tma_out;
+      const bool tma_out = p.tma_out != 0;
       for (int bx = 0; bx < nbox; ++bx) {
         const int c0 = bx * CPB;
         if (tma_out) {                   // the previous store of this warp has finished READING the staging box
@@ -601,7 +601,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
       }
       if (q == 0 && lane == 0) YNB_DP_TRACE(5, lt, 0);
     }
-    if (!kBf16 && p.tma_out && ptx::elect_one()) ptx::bulk_wait<0>();     // all output boxes have landed
+    if (p.tma_out && ptx::elect_one()) ptx::bulk_wait<0>();     // all output boxes have landed
   }
 
   ptx::tc_fence_before_sync();
@@ -687,8 +687,8 @@ inline bool plan_dwpw(DwPwLaunch& L, const void* in, int in_ld, int B, int H, in
   {
     static const bool no_ts = getenv("YNB_DP_NO_TMA_STORE") != nullptr;                     // experiment knob
     const int out_cols = p.pass ? 2 * p.N : (p.N + epc - 1) / epc * epc;
-    if (!no_ts && !is_bf16 && p.omap.gap == 0 && p.out_off == 0 &&
-        make_tmap_nhwc(&L.tmOut, p.out, out_cols, W, H, B, p.out_ld, TW, 32 / TW, false))
+    if (!no_ts && p.omap.gap == 0 && p.out_off == 0 &&
+        make_tmap_nhwc(&L.tmOut, p.out, out_cols, W, H, B, p.out_ld, TW, 32 / TW, is_bf16))
       p.tma_out = 1;
   }
   L.w = w;
