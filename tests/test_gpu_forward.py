@@ -667,3 +667,47 @@ def test_odd_grid_sizes_and_batches(G, size, batch):
     worst = max(float(np.abs(g.cpu().numpy() - r.numpy()).max()) for g, r in zip(rawb, ref))
     assert worst < 2e-2, worst
     engb.close()
+
+
+@pytest.mark.parametrize("size,batch,mode", [(416, 256, "3xtf32"), (608, 256, "3xtf32"), (416, 256, "bf16")])
+def test_full_size_workloads_size_independent_properties(G, size, batch, mode):
+    """BASELINE's full sizes (416^2 x 256 = the metric's workload, 608^2 x 256 = configs[2], bf16 = one GPU's share of
+    configs[3] x 2), where the oracle would need minutes: properties that do not depend on the size —
+      * batch independence / permutation: the batch is 8 distinct images tiled 32 times in a shuffled order; every copy
+        of an image must give the bit-identical detections, wherever it sits in the batch;
+      * the same images run as a batch of 8 give the same detections (batch-size independence);
+      * determinism: a second run (CUDA-graph replay) is bit-identical;
+      * NMS idempotence: the kept boxes of an image, fed through the per-class NMS again, are all kept (a keep set is
+        a fixed point of greedy NMS), in the same order;
+      * every kept score >= conf_thresh, every box inside the unit square, classes in range."""
+    from yolo_nano_b200.tta import merge_nms
+    classes = 80
+    sd = W.reference_init(classes, seed=5)
+    base = W.synthetic_input(8, size, 21)
+    perm = torch.randperm(batch, generator=torch.Generator().manual_seed(1))
+    idx = (torch.arange(batch) % 8)[perm]
+    x = base[idx].contiguous().to(G.DEV)
+    eng = G.make_engine(sd, size, classes, mode, max_batch=batch)
+    a = [t.clone() for t in eng.forward_detect(x)]
+    b = [t.clone() for t in eng.forward_detect(x)]
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    boxes, scores, cls, counts = a
+    small = eng.forward_detect(base.to(G.DEV))
+    first = {}
+    for pos in range(batch):
+        img = int(idx[pos])
+        k = int(counts[pos])
+        assert k == int(small[3][img]) and k > 0
+        for u, v in zip((boxes, scores, cls), small[:3]):
+            assert torch.equal(u[pos, :k], v[img, :k]), (pos, img)
+        first.setdefault(img, pos)
+    conf = 0.001
+    for img, pos in first.items():
+        k = int(counts[pos])
+        bb, ss, cc = boxes[pos, :k].cpu().numpy(), scores[pos, :k].cpu().numpy(), cls[pos, :k].cpu().numpy()
+        assert (ss >= conf).all() and (bb >= 0).all() and (bb <= 1).all() and (cc >= 0).all() and (cc < classes).all()
+        if img < 2:
+            kb, ks, kc = merge_nms(bb, ss, cc.astype(np.int32), classes, 0.5, G.DEV)
+            assert len(ks) == k and np.array_equal(kb, bb) and np.array_equal(ks, ss) and np.array_equal(kc, cc.astype(np.int64))
+    eng.close()
