@@ -486,13 +486,18 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
       const bool tma_out = p.tma_out != 0;
       for (int bx = 0; bx < nbox; ++bx) {
         const int c0 = bx * CPB;
-        if (tma_out) {                   // the previous store of this warp has finished READING the staging box
-          if (ptx::elect_one()) ptx::bulk_wait_read<0>();
-          __syncwarp();
-        }
+        // the previous TMA store of this warp must have finished READING the staging box before it is rewritten:
+        // waited for AFTER the first accumulator load of the box, whose latency covers it
+        auto box_free = [&]() {
+          if (tma_out) {
+            if (ptx::elect_one()) ptx::bulk_wait_read<0>();
+            __syncwarp();
+          }
+        };
         if (!kBf16 && kPass) {
           float v[16];
           drain16(c0, v);
+          box_free();
           const uint32_t xw[16] = {x1v[0].x, x1v[0].y, x1v[0].z, x1v[0].w, x1v[1].x, x1v[1].y, x1v[1].z, x1v[1].w,
                                    x1v[2].x, x1v[2].y, x1v[2].z, x1v[2].w, x1v[3].x, x1v[3].y, x1v[3].z, x1v[3].w};
 #pragma unroll
@@ -501,6 +506,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
         } else if (!kBf16) {
           float v[16];
           drain16(c0, v);
+          box_free();
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             put_chunk(j, make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
@@ -513,6 +519,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
                                           __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
           }
         } else if (kPass) {
+          box_free();
           // bf16: one 32-bit word per output pair = (x1[i] in the low half, conv[i] in the high half)
           const uint32_t xw[16] = {x1v[0].x, x1v[0].y, x1v[0].z, x1v[0].w, x1v[1].x, x1v[1].y, x1v[1].z, x1v[1].w,
                                    x1v[2].x, x1v[2].y, x1v[2].z, x1v[2].w, x1v[3].x, x1v[3].y, x1v[3].z, x1v[3].w};
@@ -533,6 +540,7 @@ dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
             }
           }
         } else {
+          box_free();
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
             if (h == 0 || c0 + 16 * h < p.Npad) {
