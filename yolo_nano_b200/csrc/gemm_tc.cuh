@@ -586,6 +586,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // 16 columns: sum of the accumulators (main_0 + main_1 + ... + correction) + bias, activation
       // (branch-free: act(x) = max(x, slope*x), slope 1 / 0 / 0.1 = identity / ReLU / LeakyReLU(0.1)),
       // written as chunks jc..jc+3 of this thread's swizzled 128-byte line
+      // The previous TMA store of this warp must have finished READING the staging box before it is rewritten: waited
+      // for after the accumulator loads of the box's first 16 columns, whose latency covers it.
+      auto box_free = [&]() {
+        if (p.tma_store) {
+          if (ptx::elect_one()) ptx::bulk_wait_read<0>();
+          __syncwarp();
+        }
+      };
       auto drain16 = [&](int c0, int jc) {
         uint32_t r[16];
         ptx::tmem_ld_32x16(t_base + c0, r);
@@ -606,6 +614,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else {
           ptx::tmem_ld_wait();
         }
+        if (jc == 0) box_free();
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * j);
@@ -625,6 +634,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t r[16];
         ptx::tmem_ld_32x16(t_base + c0, r);
         ptx::tmem_ld_wait();
+        if (half == 0) box_free();
         uint32_t w[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -639,10 +649,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       bf16* const out_bf = reinterpret_cast<bf16*>(p.out);
 
       for (int c0 = col_begin; c0 < col_end; c0 += 32) {
-        if (p.tma_store) {
-          if (ptx::elect_one()) ptx::bulk_wait_read<0>();   // the previous store (same elected lane) has finished reading the box
-          __syncwarp();
-        }
         if (bf16_box) {
           drain16_bf16(c0, 0);
           if (c0 + 16 < col_end) drain16_bf16(c0 + 16, 1);
