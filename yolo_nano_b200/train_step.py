@@ -6,11 +6,12 @@ every arithmetic step a kernel of libyolonano_b200.so:
     -> three heads -> loss + d loss / d head maps (train_loss_kernel) -> the same chain backwards
 
 A tape records one closure per forward op; `backward()` replays them in reverse, accumulating the gradient of a tensor
-that feeds several consumers with `ynb_add`.  PyTorch moves data only (views, channel padding to multiples of 4,
-`chunk` / `cat` / `channel_shuffle` as index permutations, weight-layout transposes): no torch arithmetic on
-activations or gradients.  Correctness first: the convs run on the parity-tested stand-alone entries (the
-tensor-core hooks re-pack their weights per call), so this path is NOT tuned — the fused inference kernels do not
-apply in training mode (batch statistics need the pre-BN conv outputs).
+that feeds several consumers with `ynb_add`.  PyTorch moves data only (views, weight-layout transposes, padded
+parameter copies of the 58-channel layers): no torch arithmetic on activations or gradients; `chunk` / `cat` /
+`channel_shuffle` and their adjoints are one-launch copies (`ynb_shuffle_unit_move`).  The convs run on the
+asynchronous tensor-core entries (weights split into hi / lo planes by a kernel on the same stream); the fused
+inference kernels do not apply in training mode (batch statistics need the pre-BN conv outputs).  `Trainer` replays
+the whole forward + backward from a CUDA graph.
 
     step = TrainStep(model)                       # model: yolo_nano_b200.YOLONano on a CUDA device
     losses, grads = step.forward_backward(x, target)          # grads: {parameter name: tensor, reference shapes}
@@ -33,15 +34,6 @@ ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 
 def _pad4(n: int) -> int:
     return (n + 3) // 4 * 4
-
-
-def _padc(t: torch.Tensor, n: int) -> torch.Tensor:
-    """Zero-pad the LAST dimension to n (data movement)."""
-    if t.shape[-1] == n:
-        return t.contiguous()
-    out = t.new_zeros(*t.shape[:-1], n)
-    out[..., : t.shape[-1]] = t
-    return out
 
 
 class _Tape:
@@ -181,18 +173,6 @@ class TrainStep:
             tape.pgrad[bn_name + ".weight"] = layer.grads["weight"][:c]
             tape.pgrad[bn_name + ".bias"] = layer.grads["bias"][:c]
             tape.add_grad(x, dx)
-        tape.ops.append(bw)
-        return y
-
-    def movement(self, tape, ins, out_fn, back_fn):
-        """A pure data-movement op (views / permutations): out = out_fn(*ins); backward distributes with back_fn."""
-        y = out_fn(*ins).contiguous()
-
-        def bw():
-            dy = tape.take(y)
-            for t, g in zip(ins, back_fn(dy)):
-                if g is not None:
-                    tape.add_grad(t, g)
         tape.ops.append(bw)
         return y
 
