@@ -207,11 +207,26 @@ struct CounterScope {
 //   float: stage 2 = [58 | 2 pad | 58 | 2 pad] (ld 120), stages 3 / 4 dense (116 x 4 B and 232 x 4 B are aligned)
 //   bf16 : stage 2 = [58 | 6 pad | 58 | 6 pad] (ld 128), stage 3 = [116 | 4 pad | 116 | 4 pad] (ld 240), stage 4 dense
 struct StageLayout { int ld; ChanMap map; };
+// float, stage 2 (h = 58): DENSE 116 channels.  The second half starts 8 bytes off a 16-byte boundary, so the one conv
+// that reads only x2 (branch2[0] of the stride-1 units) reads the aligned window [56, 116) instead, with its weights
+// shifted by two input positions (zero weight on channels 56, 57): see x2_window() / in_layout().  A dense layout lets
+// the fused unit tails of stage 2 leave through TMA tensor stores like the other stages (a gap cannot be stored that way).
+static bool dense_stage2() {
+  static const bool off = getenv("YNB_GAP_STAGE2") != nullptr;      // experiment knob: the round-2a gap layout
+  return !off;
+}
 StageLayout stage_layout(bool bf, int si) {
   const int cout = stage_channels()[si + 1], h = cout / 2, a = bf ? 8 : 4;
   const int hp = round_up(h, a);
   if (hp == h) return {cout, dense_map()};
+  if (!bf && dense_stage2() && cout % a == 0) return {cout, dense_map()};
   return {2 * hp, ChanMap{h, hp - h}};
+}
+// Aligned window over the second half of a dense stage output with h % a != 0: start channel and weight shift.
+struct X2Window { int off, shift; };
+X2Window x2_window(const StageLayout& sl, int h, int a) {
+  if (sl.map.gap != 0) return {sl.map.slot(h), 0};
+  return {h - h % a, h % a};
 }
 
 // Input layout of conv `name` (see plan_network for the producers).
@@ -224,6 +239,16 @@ InLayout in_layout(const ConvSpec& c, bool bf) {
                   n == "backbone.stage4.0.branch2.0" || n == "conv1x1_1.convs.0";
   if (reads_c3) { StageLayout L = stage_layout(bf, 0); return {L.ld, L.map}; }
   if (reads_c4) { StageLayout L = stage_layout(bf, 1); return {L.ld, L.map}; }
+  // branch2[0] of a stride-1 unit reads x2 of its stage's layout: through an aligned, shifted window when that is dense
+  for (int si = 0; si < 3; ++si) {
+    const std::string pre = "backbone.stage" + std::to_string(si + 2) + ".";
+    if (n.compare(0, pre.size(), pre) == 0 && n.size() > pre.size() + 2 && n[pre.size()] != '0' &&
+        n.compare(n.size() - 10, 10, ".branch2.0") == 0) {
+      const int a = bf ? 8 : 4;
+      const X2Window w = x2_window(stage_layout(bf, si), c.cin, a);
+      if (w.shift) return {round_up(c.cin + w.shift, a), ChanMap{0, w.shift}};
+    }
+  }
   return {round_up(c.cin, bf ? 8 : 4), dense_map()};
 }
 
@@ -832,7 +857,7 @@ int build_plan(ynb_engine* e, int B, Plan** out) {
     for (int bi = 1; bi < stage_repeats()[si]; ++bi) {
       std::string u = bk + std::to_string(bi);
       Tensor o = P.T(st + "." + std::to_string(bi));
-      int x2_off = x.map.slot(h);
+      const int x2_off = x2_window(stage_layout(is_bf16(e), si), h, is_bf16(e) ? 8 : 4).off;
       // the previous unit's pass-through copy wrote half of x: join before reading it
       const bool ffma = e->cfg.gemm_mode == YNB_GEMM_FP32_FFMA;
       P.pw(u + ".branch2.0", x, x2_off, mid1, 0, 1, /*join=*/ffma && bi > 1);
