@@ -203,14 +203,15 @@ struct CounterScope {
 };
 
 // ---- static layout knowledge -----------------------------------------------------------
-// Channel halves of a stage output must start 16-byte aligned (TMA views, 16-byte loads): 4 floats or 8 bf16.
-//   float: stage 2 = [58 | 2 pad | 58 | 2 pad] (ld 120), stages 3 / 4 dense (116 x 4 B and 232 x 4 B are aligned)
-//   bf16 : stage 2 = [58 | 6 pad | 58 | 6 pad] (ld 128), stage 3 = [116 | 4 pad | 116 | 4 pad] (ld 240), stage 4 dense
+// TMA views and 16-byte loads must start 16-byte aligned: 4 floats or 8 bf16.  Earlier layout (YNB_GAP_STAGE2=1 keeps
+// it): a gap between the halves — float stage 2 = [58 | 2 pad | 58 | 2 pad] (ld 120), bf16 stage 2 = [58 | 6 | 58 | 6]
+// (ld 128), bf16 stage 3 = [116 | 4 | 116 | 4] (ld 240); everything else dense.
 struct StageLayout { int ld; ChanMap map; };
-// float, stage 2 (h = 58): DENSE 116 channels.  The second half starts 8 bytes off a 16-byte boundary, so the one conv
-// that reads only x2 (branch2[0] of the stride-1 units) reads the aligned window [56, 116) instead, with its weights
-// shifted by two input positions (zero weight on channels 56, 57): see x2_window() / in_layout().  A dense layout lets
-// the fused unit tails of stage 2 leave through TMA tensor stores like the other stages (a gap cannot be stored that way).
+// Stage outputs are DENSE (float stage 2: 116 channels; bf16 stage 2: 116 + 4 zero pad, stage 3: 232).  Where the second
+// half does not start on a 16-byte boundary (h = 58 floats, 58 / 116 bf16), the one conv that reads only x2 (branch2[0]
+// of the stride-1 units) reads the aligned window that starts h % a channels earlier, with its weights shifted by as
+// many input positions (zero weight on the leading channels): see x2_window() / in_layout().  A dense layout lets the
+// fused unit tails leave through TMA tensor stores (a gap between the halves cannot be stored that way).
 static bool dense_stage2() {
   static const bool off = getenv("YNB_GAP_STAGE2") != nullptr;      // experiment knob: the round-2a gap layout
   return !off;
@@ -219,7 +220,7 @@ StageLayout stage_layout(bool bf, int si) {
   const int cout = stage_channels()[si + 1], h = cout / 2, a = bf ? 8 : 4;
   const int hp = round_up(h, a);
   if (hp == h) return {cout, dense_map()};
-  if (!bf && dense_stage2() && cout % a == 0) return {cout, dense_map()};
+  if (dense_stage2()) return {round_up(cout, a), dense_map()};     // channels >= cout: zero pad at the END of the row
   return {2 * hp, ChanMap{h, hp - h}};
 }
 // Aligned window over the second half of a dense stage output with h % a != 0: start channel and weight shift.
