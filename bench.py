@@ -60,6 +60,9 @@ def parse():
                     help="strong scaling: --batch is the TOTAL batch, split evenly over the ranks (configs[2])")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run oracle check of two images")
     ap.add_argument("--no-latency", action="store_true", help="skip the batch-1 drop-in latency measurement")
+    ap.add_argument("--workload", default="detect", choices=["detect", "train"],
+                    help="train = BASELINE configs[4]: the data-parallel training step (tools/gpu_train_step_bench.py), "
+                         "32 images per GPU unless --batch is given")
     return ap.parse_args()
 
 
@@ -286,8 +289,26 @@ def workload_config(a):
                   f"4 rotating input batches; intermediate activations ~{a.batch * 24 * (a.size / 416) ** 2 / 1e3:.1f} GB per step"}
 
 
+def run_train_workload(a):
+    """BASELINE configs[4] through the same launch contract: hands over to tools/gpu_train_step_bench.py."""
+    sys.path.insert(0, str(Path(__file__).resolve().parent / "tools"))
+    import gpu_train_step_bench as tb
+    argv = ["--steps", str(a.steps), "--warmup", str(max(a.warmup, 3)), "--size", str(a.size),
+            "--batch", str(32 if a.batch == BATCH else a.batch)]
+    if not a.no_cpu_baseline:
+        argv.append("--cpu-baseline")
+    sys.argv = [sys.argv[0]] + argv
+    tb.main()
+
+
 def main():
     a = parse()
+    if a.workload == "train":
+        if a.impl == "reference":
+            raise SystemExit("--workload train has no --impl reference arm (its CPU baseline is in the line itself)")
+        a.steps = min(a.steps, 30) if a.steps == 100 else a.steps
+        run_train_workload(a)
+        return
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
